@@ -1,0 +1,434 @@
+"""Pins the plain-C oracle (oracle/gdsp_oracle.c) against the UNMODIFIED reference
+compiled into oracle/_ref/ (in-process through oracle/ref_shim.c).  CPU only.
+
+The reference ships no tests or golden vectors, so this comparison -- plus the
+fixtures in tests/golden/ generated from the same binary -- is what pins parity.
+Everything is compared bit-for-bit (the oracle follows the reference's
+floating-point evaluation order).
+"""
+import numpy as np
+import pytest
+
+from checkers import Oracle, RefGenome, have_ref
+
+pytestmark = pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+
+CHROMS = [("chrA", 5000), ("chrB", 12345), ("chrC", 777), ("chrD", 64)]
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return Oracle()
+
+
+def signal(rng, n, kind):
+    if kind == "int":       # coverage-like
+        return rng.poisson(5, n).astype(np.float64)
+    if kind == "sparse":    # long zero stretches and plateaus
+        v = np.zeros(n)
+        for _ in range(max(1, n // 200)):
+            s = rng.integers(0, n); L = rng.integers(1, 150)
+            v[s:s + L] += rng.integers(1, 4)
+        return v
+    if kind == "dyadic":
+        return rng.integers(-4096, 4096, n).astype(np.float64) / 1024.0
+    return rng.normal(0, 3, n)
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float64).view(np.uint64)
+
+
+def check(orc, rng, kind, ref_words, oracle_fn):
+    g = RefGenome(CHROMS)
+    try:
+        inputs = {}
+        for name, n in CHROMS:
+            v = signal(rng, n, kind)
+            g.vec[name][:] = v
+            inputs[name] = v.copy()
+        g.apply(*ref_words)
+        for name, n in CHROMS:
+            got = oracle_fn(inputs[name].copy())
+            want = g.vec[name]
+            assert np.array_equal(bits(got), bits(want)), (ref_words, kind, name)
+    finally:
+        g.close()
+
+
+KINDS = ["int", "sparse", "dyadic", "real"]
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("W", [3, 7, 100, 101, 1000])
+def test_block_and_sliding_sum(orc, kind, W):
+    rng = np.random.default_rng(W)
+    check(orc, rng, kind, ["sum", "--window=%d" % W], lambda v: orc.block_sum(v, W))
+    check(orc, rng, kind, ["sum", "--window=%d" % W, "--denom=actual", "--zero=-1"],
+          lambda v: orc.block_sum(v, W, actual=True, zero=-1.0))
+    check(orc, rng, kind, ["sum", "--window=%d" % W, "--denom=W"], lambda v: orc.block_sum(v, W, denom=float(W)))
+    check(orc, rng, kind, ["slidingsum", "--window=%d" % W], lambda v: orc.sliding_sum(v, W))
+    check(orc, rng, kind, ["slidingsum", "--window=%d" % W, "--denom=W"],
+          lambda v: orc.sliding_sum(v, W, float(W)))
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_block_sum_whole_chromosome(orc, kind):
+    rng = np.random.default_rng(5)
+    g = RefGenome(CHROMS)
+    try:
+        inputs = {}
+        for name, n in CHROMS:
+            inputs[name] = signal(rng, n, kind); g.vec[name][:] = inputs[name]
+        g.apply("sum", "--window=chromosome")
+        for name, n in CHROMS:
+            assert np.array_equal(bits(orc.block_sum(inputs[name].copy(), n)), bits(g.vec[name]))
+    finally:
+        g.close()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("W", [3, 11, 51, 101])
+def test_smooth(orc, kind, W):
+    rng = np.random.default_rng(W + 1)
+    check(orc, rng, kind, ["smooth", "--window=%d" % W], lambda v: orc.smooth(v, W))
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_cumulative(orc, kind):
+    check(orc, np.random.default_rng(2), kind, ["cumulativesum"], orc.cumulative)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("N", [3, 11, 101])
+def test_local_extrema(orc, kind, N):
+    rng = np.random.default_rng(N)
+    check(orc, rng, kind, ["localmax", "--neighborhood=%d" % N], lambda v: orc.local_extrema(v, N, True, 0.0))
+    check(orc, rng, kind, ["localmax", "--neighborhood=%d" % N, "--zero=-7"],
+          lambda v: orc.local_extrema(v, N, True, -7.0))
+    check(orc, rng, kind, ["localmin", "--neighborhood=%d" % N],
+          lambda v: orc.local_extrema(v, N, False, np.finfo(np.float64).max))
+    check(orc, rng, kind, ["localmin", "--neighborhood=%d" % N, "--infinity=99"],
+          lambda v: orc.local_extrema(v, N, False, 99.0))
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("W", [3, 4, 10, 100, 101, 1001])
+def test_best_extrema(orc, kind, W):
+    rng = np.random.default_rng(W)
+    check(orc, rng, kind, ["bestmax", "--window=%d" % W], lambda v: orc.best_extrema(v, W, True))
+    check(orc, rng, kind, ["bestmin", "--window=%d" % W], lambda v: orc.best_extrema(v, W, False))
+
+
+@pytest.mark.parametrize("kind", ["int", "sparse", "real"])
+@pytest.mark.parametrize("L", [1, 2, 5, 30, 101, 1001])
+def test_morphology(orc, kind, L):
+    rng = np.random.default_rng(L)
+    T = {"int": 5.0, "sparse": 0.0, "real": 0.5}[kind]
+    targ = "--threshold=%r" % T
+    check(orc, rng, kind, ["close", str(L), targ], lambda v: orc.close(v, L, T))
+    check(orc, rng, kind, ["open", str(L), targ, "--one=2", "--zero=-1"], lambda v: orc.open(v, L, T, 2.0, -1.0))
+    left, right = L // 2, L - L // 2
+    check(orc, rng, kind, ["dilate", str(L), targ], lambda v: orc.dilate(v, left, right, T))
+    check(orc, rng, kind, ["dilate", "--left=3", "--right=9", targ], lambda v: orc.dilate(v, 3, 9, T))
+
+
+@pytest.mark.parametrize("L", [1, 2, 5, 30])
+def test_erode_safe_cases(orc, L):
+    # the reference crashes (u32 wrap, morphology.c:1406-1437) when a run ends
+    # before `leftErosion`; keep the first L samples out of the set
+    rng = np.random.default_rng(L)
+    left, right = L // 2, L - L // 2
+    g = RefGenome(CHROMS)
+    try:
+        inputs = {}
+        for name, n in CHROMS:
+            v = signal(rng, n, "sparse"); v[: L + 1] = 0
+            inputs[name] = v; g.vec[name][:] = v
+        g.apply("erode", str(L))
+        for name, n in CHROMS:
+            assert np.array_equal(bits(orc.erode(inputs[name].copy(), left, right)), bits(g.vec[name]))
+    finally:
+        g.close()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_pointwise(orc, kind):
+    rng = np.random.default_rng(9)
+    check(orc, rng, kind, ["binarize", "3"], lambda v: orc.binarize(v, 3.0))
+    check(orc, rng, kind, ["binarize", "3", "--ties:above", "--one=5", "--zero=-5"],
+          lambda v: orc.binarize(v, 3.0, True, 5.0, -5.0))
+    check(orc, rng, kind, ["addconst", "2.5"], lambda v: orc.addconst(v, 2.5))
+    check(orc, rng, kind, ["abs"], orc.abs)
+    check(orc, rng, kind, ["clip", "--min=1", "--max=4"], lambda v: orc.clip(v, 1.0, 4.0))
+    check(orc, rng, kind, ["clip", "--min=1"], lambda v: orc.clip(v, 1.0, None))
+    check(orc, rng, kind, ["clip", "--max=2"], lambda v: orc.clip(v, None, 2.0))
+    check(orc, rng, kind, ["erase", "--min=1", "--max=4"], lambda v: orc.erase(v, 1.0, 4.0))
+    check(orc, rng, kind, ["erase", "--min=1", "--max=4", "--keep:inside", "--zero=-1"],
+          lambda v: orc.erase(v, 1.0, 4.0, True, -1.0))
+    check(orc, rng, kind, ["erase", "--min=2"], lambda v: orc.erase(v, 2.0, None))
+    check(orc, rng, kind, ["erase", "--max=2", "--keep:inside"], lambda v: orc.erase(v, None, 2.0, True))
+    check(orc, rng, kind, ["invert", "1.25"], lambda v: orc.invert(v, 1.25))
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_invert_auto_mid(orc, kind):
+    rng = np.random.default_rng(3)
+    g = RefGenome(CHROMS)
+    try:
+        inputs = {}
+        for name, n in CHROMS:
+            inputs[name] = signal(rng, n, kind); g.vec[name][:] = inputs[name]
+        g.apply("invert")
+        allv = np.concatenate(list(inputs.values()))
+        mid = (allv.min() + allv.max()) / 2.0
+        for name, n in CHROMS:
+            assert np.array_equal(bits(orc.invert(inputs[name].copy(), mid)), bits(g.vec[name]))
+    finally:
+        g.close()
+
+
+@pytest.mark.parametrize("kind", ["int", "sparse", "dyadic", "real"])
+@pytest.mark.parametrize("L", [1, 10, 100, 1000])
+def test_clump(orc, kind, L):
+    rng = np.random.default_rng(L)
+    T = {"int": 5.5, "sparse": 0.5, "dyadic": 0.25, "real": 0.3}[kind]
+    check(orc, rng, kind, ["clump", repr(T), "--length=%d" % L], lambda v: orc.clump(v, T, L, True))
+    check(orc, rng, kind, ["anticlump", repr(T), "--length=%d" % L], lambda v: orc.clump(v, T, L, False))
+
+
+def test_clump_all_below(orc):
+    rng = np.random.default_rng(0)
+    check(orc, rng, "int", ["clump", "1000", "--length=10"], lambda v: orc.clump(v, 1000.0, 10, True))
+
+
+def _sorted_genome(inputs, names):
+    allv = np.sort(np.concatenate([inputs[n] for n in names]))
+    out, pos = {}, 0
+    for n in names:
+        out[n] = allv[pos:pos + inputs[n].size]; pos += inputs[n].size
+    return out
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("p", ["99", "50", "99.5", "12.345", "100", "0"])
+def test_percentile_value_and_post_state(orc, kind, p):
+    rng = np.random.default_rng(7)
+    g = RefGenome(CHROMS)
+    try:
+        inputs = {}
+        for name, n in CHROMS:
+            inputs[name] = signal(rng, n, kind); g.vec[name][:] = inputs[name]
+        g.apply("percentile", p, "--quiet")
+        names = g.sorted_names()
+        samples = np.concatenate([orc.percentile_collect(inputs[n]) for n in names])
+        srt = orc.sort(samples.copy())
+        pm = int(round(float(p) * 1000))
+        if pm == 100000:
+            want = srt[-1]
+        elif pm == 0:
+            want = srt[0]
+        else:
+            want = srt[orc.percentile_rank(srt.size, pm)]
+        got = g.get_global("percentile" + p)
+        assert got is not None and np.float64(got).view(np.uint64) == np.float64(want).view(np.uint64)
+        if pm in (0, 100000):     # min/max special cases are non-destructive (percentile.c:434-530)
+            for n in names:
+                assert np.array_equal(bits(g.vec[n]), bits(inputs[n]))
+        elif float(p) >= 99:      # rank falls in the last chromosome: genome ends up globally sorted
+            post = _sorted_genome(inputs, names)
+            for n in names:
+                assert np.array_equal(g.vec[n], post[n])
+    finally:
+        g.close()
+
+
+@pytest.mark.parametrize("W", [1, 2, 5, 100])
+def test_percentile_window_and_range(orc, W):
+    rng = np.random.default_rng(W)
+    g = RefGenome(CHROMS)
+    try:
+        inputs = {}
+        for name, n in CHROMS:
+            inputs[name] = signal(rng, n, "int"); g.vec[name][:] = inputs[name]
+        g.apply("percentile", "10..90by20", "--window=%d" % W, "--min=2", "--max=9", "--quiet")
+        names = g.sorted_names()
+        samples = np.concatenate([orc.percentile_collect(inputs[n], W, 2.0, 9.0) for n in names])
+        srt = orc.sort(samples.copy())
+        for p in (10, 30, 50, 70, 90):
+            want = srt[orc.percentile_rank(srt.size, p * 1000)]
+            assert g.get_global("percentile%d" % p) == want
+    finally:
+        g.close()
+
+
+def _write_intervals(path, rows):
+    with open(path, "w") as f:
+        for r in rows:
+            f.write("\t".join(str(x) for x in r) + "\n")
+
+
+def _random_intervals(rng, m, with_val, dyadic=True):
+    rows = []
+    for _ in range(m):
+        name, n = CHROMS[rng.integers(0, len(CHROMS))]
+        s = int(rng.integers(0, n)); e = int(min(n, s + rng.integers(0, 200)))
+        if with_val:
+            val = float(rng.integers(-8, 9)) / (4.0 if dyadic else 3.0)
+            rows.append((name, s, e, repr(val)))
+        else:
+            rows.append((name, s, e))
+    return rows
+
+
+def _by_chrom(rows):
+    d = {name: ([], [], []) for name, _ in CHROMS}
+    for r in rows:
+        d[r[0]][0].append(r[1]); d[r[0]][1].append(r[2]); d[r[0]][2].append(float(r[3]) if len(r) > 3 else 1.0)
+    return d
+
+
+@pytest.mark.parametrize("novalue", [True, False])
+@pytest.mark.parametrize("overlap", [0, 1, 2])
+def test_accumulate(orc, tmp_path, novalue, overlap):
+    rng = np.random.default_rng(11 + overlap)
+    rows = _random_intervals(rng, 3000, not novalue, dyadic=False)
+    path = str(tmp_path / "iv.txt"); _write_intervals(path, rows)
+    g = RefGenome(CHROMS)
+    try:
+        clear = overlap != 0
+        g.read_intervals(path, -1 if novalue else 3, False, overlap, clear, 0.0)
+        d = _by_chrom(rows)
+        for name, n in CHROMS:
+            s, e, val = d[name]
+            v = np.zeros(n)
+            orc.accumulate(v, s, e, None if novalue else val, overlap, clear, 0.0)
+            assert np.array_equal(bits(v), bits(g.vec[name]))
+    finally:
+        g.close()
+
+
+@pytest.mark.parametrize("op,sign", [("add", 1.0), ("subtract", -1.0)])
+def test_add_subtract(orc, tmp_path, op, sign):
+    rng = np.random.default_rng(21)
+    rows = _random_intervals(rng, 2000, True, dyadic=False)
+    path = str(tmp_path / "iv.txt"); _write_intervals(path, rows)
+    g = RefGenome(CHROMS)
+    try:
+        inputs = {}
+        for name, n in CHROMS:
+            inputs[name] = signal(rng, n, "real"); g.vec[name][:] = inputs[name]
+        g.apply(op, path)
+        d = _by_chrom(rows)
+        for name, n in CHROMS:
+            s, e, val = d[name]
+            assert np.array_equal(bits(orc.add_intervals(inputs[name].copy(), s, e, val, sign)), bits(g.vec[name]))
+    finally:
+        g.close()
+
+
+def test_mask_or(orc, tmp_path):
+    rng = np.random.default_rng(22)
+    rows = _random_intervals(rng, 500, True)
+    path = str(tmp_path / "iv.txt"); _write_intervals(path, rows)
+    d = _by_chrom(rows)
+    for op in ("mask", "or"):
+        g = RefGenome(CHROMS)
+        try:
+            inputs = {}
+            for name, n in CHROMS:
+                inputs[name] = signal(rng, n, "sparse"); g.vec[name][:] = inputs[name]
+            if op == "mask":
+                g.apply("mask", path, "--mask=-3")
+            else:
+                g.apply("or", path)
+            for name, n in CHROMS:
+                s, e, val = d[name]
+                v = inputs[name].copy()
+                if op == "mask":
+                    orc.mask_intervals(v, s, e, -3.0)
+                else:
+                    orc.or_intervals(orc.logical_prep(v), s, e, val)
+                assert np.array_equal(bits(v), bits(g.vec[name])), op
+        finally:
+            g.close()
+
+
+def _sorted_disjoint(rng, skip=()):
+    rows = []
+    for name, n in CHROMS:
+        if name in skip:
+            continue
+        pos = int(rng.integers(0, 50))
+        while pos < n:
+            L = int(rng.integers(1, 120)); e = min(n, pos + L)
+            val = float(rng.integers(-6, 7)) / 2.0
+            rows.append((name, pos, e, repr(val)))
+            pos = e + int(rng.integers(0, 90))
+    return rows
+
+
+@pytest.mark.parametrize("op,kind,aux", [("multiply", 0, 0.0), ("divide", 1, np.finfo(np.float64).max),
+                                         ("masknot", 2, -2.0), ("and", 3, 0.0)])
+def test_sorted_interval_ops(orc, tmp_path, op, kind, aux):
+    rng = np.random.default_rng(30 + kind)
+    rows = _sorted_disjoint(rng, skip=("chrC",))       # chrC absent from the file
+    path = str(tmp_path / "iv.txt"); _write_intervals(path, rows)
+    d = _by_chrom(rows)
+    g = RefGenome(CHROMS)
+    try:
+        inputs = {}
+        for name, n in CHROMS:
+            inputs[name] = signal(rng, n, "real"); g.vec[name][:] = inputs[name]
+        words = [op, path] + (["--mask=-2"] if op == "masknot" else [])
+        g.apply(*words)
+        for name, n in CHROMS:
+            s, e, val = d[name]
+            v = inputs[name].copy()
+            if op == "masknot":
+                val = [1.0] * len(val)      # masknot reads no value column (mask.c:533)
+            keep = [i for i, x in enumerate(val) if x != 0.0]   # val==0 lines are skipped
+            s = [s[i] for i in keep]; e = [e[i] for i in keep]; val = [val[i] for i in keep]
+            if op == "and":
+                orc.logical_prep(v)
+            orc.sorted_intervals(v, s, e, val, kind, aux)
+            assert np.array_equal(bits(v), bits(g.vec[name])), (op, name)
+    finally:
+        g.close()
+
+
+def _parse_runs(path):
+    out = {}
+    for line in open(path):
+        c, s, e, val = line.rstrip("\n").split("\t")
+        out.setdefault(c, []).append((int(s), int(e), val))
+    return out
+
+
+@pytest.mark.parametrize("collapse", [True, False])
+@pytest.mark.parametrize("show", [0, 1, -1])
+def test_runs(orc, tmp_path, collapse, show):
+    rng = np.random.default_rng(40)
+    g = RefGenome(CHROMS)
+    try:
+        inputs = {}
+        for name, n in CHROMS:
+            v = signal(rng, n, "sparse")
+            if n > 100:
+                v[0:3] = 0.0; v[50:60] = 2.0; v[n - 4:] = 0.0
+            inputs[name] = v; g.vec[name][:] = v
+        path = str(tmp_path / "out.txt")
+        g.report(path, precision=3, collapse=collapse, show_uncovered=show)
+        ref = _parse_runs(path)
+        for name, n in CHROMS:
+            rs, re, rv = orc.runs(inputs[name], collapse, show)
+            lines, prev_end = [], 0
+            for s, e, x in zip(rs, re, rv):
+                if show == -1 and s != prev_end:
+                    lines.append((prev_end, int(s), "NA"))
+                lines.append((int(s), int(e), "%.3f" % x)); prev_end = int(e)
+            if show == -1 and prev_end != n:
+                lines.append((prev_end, n, "NA"))
+            assert lines == ref.get(name, []), (name, collapse, show)
+    finally:
+        g.close()
