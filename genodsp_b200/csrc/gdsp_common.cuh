@@ -1,0 +1,221 @@
+// gdsp_common.cuh -- shared device/host plumbing of the sm_100a operator library.
+//
+// Compiled with -fmad=false: the reference is an x86-64 baseline build without
+// FMA contraction, so every product and sum here rounds
+// separately, which is what makes smooth() bit-exact.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <float.h>
+#include <map>
+#include <vector>
+
+#include "gdsp_b200.h"
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+
+void gdsp_set_error (const char* fmt, ...);
+
+#define GDSP_CUDA(call)                                                        \
+	do {                                                                       \
+		cudaError_t e__ = (call);                                              \
+		if (e__ != cudaSuccess)                                                \
+			{                                                                  \
+			gdsp_set_error ("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, \
+			                cudaGetErrorString (e__));                         \
+			return GDSP_ERR_CUDA;                                              \
+			}                                                                  \
+	} while (0)
+
+#define GDSP_KERNEL_CHECK()  GDSP_CUDA (cudaGetLastError ())
+
+#define GDSP_REQUIRE(cond, ...)                                                \
+	do {                                                                       \
+		if (!(cond)) { gdsp_set_error (__VA_ARGS__); return GDSP_ERR_ARG; }    \
+	} while (0)
+
+#define GDSP_TRY(call)                                                         \
+	do { int s__ = (call); if (s__ != GDSP_OK) return s__; } while (0)
+
+// ---------------------------------------------------------------------------
+// segment table on the device
+// ---------------------------------------------------------------------------
+
+struct SegDev
+	{
+	uint64_t lo, hi;      // owned cells
+	uint64_t dlo, dhi;    // readable cells (chromosome clip bounds)
+	uint32_t pos0;        // chromosome coordinate of cell lo
+	uint32_t chromLen;
+	};
+
+// per-tile-size prefix of tile counts: tile t of the launch belongs to the
+// segment s with base[s] <= t < base[s+1]
+struct TileMap
+	{
+	uint32_t  tile;
+	uint64_t  ntiles;
+	uint64_t* d_base;     // nseg+1 entries
+	};
+
+struct gdsp_layout
+	{
+	gdsp_ctx*             ctx;
+	int                   nseg;
+	std::vector<gdsp_seg> h;
+	SegDev*               d;
+	uint64_t              cells;      // sum (hi-lo)
+	uint64_t              span_lo, span_hi;   // min lo, max hi
+	uint32_t              max_len;    // longest owned segment
+	std::map<uint32_t, TileMap> tiles;
+	};
+
+int gdsp_layout_tilemap (gdsp_layout* lay, uint32_t tile, TileMap* out);
+
+#define GDSP_NUM_WS 8
+
+struct gdsp_ctx
+	{
+	int          device;
+	cudaStream_t stream;
+	bool         owns_stream;
+	int          sm_count;
+	int          cc_major, cc_minor;
+	size_t       smem_optin;          // max dynamic smem per block
+	void*        ws[GDSP_NUM_WS];     // grow-only device workspaces
+	size_t       ws_bytes[GDSP_NUM_WS];
+	void*        pinned[2];           // staging buffers for *_host entry points
+	size_t       pinned_bytes;
+	cudaEvent_t  pinned_ev[2];
+	cudaEvent_t  t0, t1;
+	};
+
+// grow-only device scratch (slot 0..GDSP_NUM_WS-1); contents undefined
+int gdsp_ws (gdsp_ctx* ctx, int slot, size_t bytes, void** out);
+
+// ---------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------
+
+#ifdef __CUDACC__
+
+// which segment does tile `t` belong to, and which tile of that segment is it
+__device__ __forceinline__ void tile_to_seg (const uint64_t* __restrict__ base, int nseg,
+                                             uint64_t t, int& seg, uint64_t& tileInSeg)
+	{
+	int lo = 0, hi = nseg - 1;
+	while (lo < hi)
+		{
+		int mid = (lo + hi + 1) >> 1;
+		if (base[mid] <= t) lo = mid; else hi = mid - 1;
+		}
+	seg = lo;
+	tileInSeg = t - base[lo];
+	}
+
+__device__ __forceinline__ double shfl_up_f64 (double v, int delta)
+	{
+	int lo = __double2loint (v), hi = __double2hiint (v);
+	lo = __shfl_up_sync (0xffffffffu, lo, delta);
+	hi = __shfl_up_sync (0xffffffffu, hi, delta);
+	return __hiloint2double (hi, lo);
+	}
+
+__device__ __forceinline__ double shfl_down_f64 (double v, int delta)
+	{
+	int lo = __double2loint (v), hi = __double2hiint (v);
+	lo = __shfl_down_sync (0xffffffffu, lo, delta);
+	hi = __shfl_down_sync (0xffffffffu, hi, delta);
+	return __hiloint2double (hi, lo);
+	}
+
+__device__ __forceinline__ double shfl_idx_f64 (double v, int src)
+	{
+	int lo = __double2loint (v), hi = __double2hiint (v);
+	lo = __shfl_sync (0xffffffffu, lo, src);
+	hi = __shfl_sync (0xffffffffu, hi, src);
+	return __hiloint2double (hi, lo);
+	}
+
+__device__ __forceinline__ double shfl_xor_f64 (double v, int mask)
+	{
+	int lo = __double2loint (v), hi = __double2hiint (v);
+	lo = __shfl_xor_sync (0xffffffffu, lo, mask);
+	hi = __shfl_xor_sync (0xffffffffu, hi, mask);
+	return __hiloint2double (hi, lo);
+	}
+
+// streaming 128-bit global accesses (data touched once per kernel)
+__device__ __forceinline__ double2 ldg_stream (const double* p)
+	{
+	double2 r;
+	asm volatile ("ld.global.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
+	              : "=d"(r.x), "=d"(r.y) : "l"(p));
+	return r;
+	}
+
+__device__ __forceinline__ void stg_stream (double* p, double2 v)
+	{
+	asm volatile ("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};"
+	              :: "l"(p), "d"(v.x), "d"(v.y) : "memory");
+	}
+
+// order-preserving 64-bit key of a double: a<b  <=>  key(a)<key(b) for all
+// non-NaN a,b (with -0.0 just below +0.0)
+__device__ __forceinline__ uint64_t f64_key (double v)
+	{
+	uint64_t b = (uint64_t) __double_as_longlong (v);
+	return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+	}
+
+__device__ __forceinline__ double key_f64 (uint64_t k)
+	{
+	uint64_t b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+	return __longlong_as_double ((long long) b);
+	}
+
+// ----- mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP) -------------
+
+__device__ __forceinline__ uint32_t smem_u32 (const void* p)
+	{ return (uint32_t) __cvta_generic_to_shared (p); }
+
+__device__ __forceinline__ void mbar_init (uint64_t* bar, uint32_t count)
+	{
+	asm volatile ("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32 (bar)), "r"(count));
+	}
+
+__device__ __forceinline__ void mbar_fence_init ()
+	{ asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_expect_tx (uint64_t* bar, uint32_t bytes)
+	{
+	asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+	              :: "r"(smem_u32 (bar)), "r"(bytes) : "memory");
+	}
+
+__device__ __forceinline__ void mbar_wait (uint64_t* bar, uint32_t phase)
+	{
+	asm volatile (
+		"{\n"
+		".reg .pred p;\n"
+		"WAIT_%=:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra DONE_%=;\n"
+		"bra WAIT_%=;\n"
+		"DONE_%=:\n"
+		"}\n" :: "r"(smem_u32 (bar)), "r"(phase) : "memory");
+	}
+
+// bytes must be a multiple of 16; src/dst 16-byte aligned
+__device__ __forceinline__ void bulk_g2s (void* dstSmem, const void* srcGlobal, uint32_t bytes, uint64_t* bar)
+	{
+	asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	              :: "r"(smem_u32 (dstSmem)), "l"(srcGlobal), "r"(bytes), "r"(smem_u32 (bar)) : "memory");
+	}
+
+#endif // __CUDACC__

@@ -1,0 +1,237 @@
+// gdsp_minmax.cu -- sliding-window extrema (van Herk / Gil-Werman in shared
+// memory with warp-shuffle segmented scans).
+//
+// Replaces op_local_maxima_apply (minmax.c:1183-1227), op_local_minima_apply
+// (minmax.c:981-1022), op_best_local_max_apply (minmax.c:1616-1721) and
+// op_best_local_min_apply (minmax.c:1369-1474).
+//
+// A tile stages nOut + Wn - 1 cells (Wn = window width); cells outside the
+// chromosome's readable range are staged as the neutral element (-inf / +inf),
+// which is the reference's "clip the window to the vector" rule.  The staged
+// cells are cut into van Herk blocks of exactly Wn cells;
+//     g[j]  = extremum from the start of j's block to j   (forward scan)
+//     hs[j] = extremum from j to the end of j's block     (backward scan)
+// and the window [c, c+Wn-1] is ext(hs[c], g[c+Wn-1]).  Both scans are
+// block-wide segmented scans: every thread owns a strip of E consecutive staged
+// cells in registers; strip aggregates are combined with warp shuffles.
+#include "gdsp_common.cuh"
+
+#define MM_THREADS 512
+#define MM_WARPS   (MM_THREADS / 32)
+
+template <bool WANT_MAX> __device__ __forceinline__ double ext (double a, double b)
+	{ return WANT_MAX ? fmax (a, b) : fmin (a, b); }
+
+template <int LOGE> __device__ __forceinline__ uint32_t mm_pad (uint32_t j) { return j + (j >> LOGE); }
+
+// MODE 0: out = window extremum (bestmax/bestmin)
+// MODE 1: out = in unless the window extremum beats it, then fill (localmax/localmin)
+template <int LOGE, bool WANT_MAX, int MODE>
+__global__ void __launch_bounds__(MM_THREADS)
+k_extrema (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
+           const double* __restrict__ in, double* __restrict__ out,
+           uint32_t reachL, uint32_t Wn, uint32_t tileOut, double fill)
+	{
+	constexpr int      E    = 1 << LOGE;
+	constexpr uint32_t SCAP = (uint32_t) E * MM_THREADS;
+	constexpr uint32_t PADN = SCAP + (SCAP >> LOGE) + 2;
+	extern __shared__ double sm[];
+	double* A = sm;                 // staged cells, later g
+	double* B = sm + PADN;          // hs
+	__shared__ double s_wv[MM_WARPS];
+	__shared__ int    s_wf[MM_WARPS];
+
+	const double NEUTRAL = WANT_MAX ? -__longlong_as_double (0x7ff0000000000000ll) * 1.0 : __longlong_as_double (0x7ff0000000000000ll);
+
+	int seg;  uint64_t tis;
+	tile_to_seg (base, nseg, blockIdx.x, seg, tis);
+	const SegDev sd = segs[seg];
+	const uint64_t t0   = sd.lo + tis * tileOut;
+	const uint32_t nOut = (uint32_t) ((sd.hi - t0 < tileOut) ? (sd.hi - t0) : tileOut);
+	const uint32_t count = nOut + Wn - 1;
+	const int64_t  g0   = (int64_t) t0 - (int64_t) reachL;
+
+	for (uint32_t j = threadIdx.x; j < SCAP; j += MM_THREADS)
+		{
+		double v = NEUTRAL;
+		int64_t g = g0 + (int64_t) j;
+		if (j < count && g >= (int64_t) sd.dlo && g < (int64_t) sd.dhi) v = __ldg (in + g);
+		A[mm_pad<LOGE> (j)] = v;
+		}
+	__syncthreads ();
+
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t j0 = threadIdx.x * E;
+	double a[E];
+	#pragma unroll
+	for (int e = 0; e < E; e++) a[e] = A[mm_pad<LOGE> (j0 + e)];
+	const uint32_t m0 = j0 % Wn;
+
+	// ---------------- forward: blocks restart where j % Wn == 0 ----------------
+	{
+	double run = NEUTRAL;  int reset = 0;
+	uint32_t m = m0;
+	#pragma unroll
+	for (int e = 0; e < E; e++)
+		{
+		if (m == 0) { run = a[e];  reset = 1; } else run = ext<WANT_MAX> (run, a[e]);
+		if (++m == Wn) m = 0;
+		}
+	double val = run;  int f = reset;
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1)
+		{
+		double v2 = shfl_up_f64 (val, d);
+		int    f2 = __shfl_up_sync (0xffffffffu, f, d);
+		if (lane >= d) { if (!f) val = ext<WANT_MAX> (v2, val);  f |= f2; }
+		}
+	double exv = shfl_up_f64 (val, 1);
+	int    exf = __shfl_up_sync (0xffffffffu, f, 1);
+	if (lane == 0) { exv = NEUTRAL;  exf = 0; }
+	if (lane == 31) { s_wv[warp] = val;  s_wf[warp] = f; }
+	__syncthreads ();                    // also: every thread has read its strip of A
+	double cw = NEUTRAL;
+	for (int w = 0; w < warp; w++) cw = s_wf[w] ? s_wv[w] : ext<WANT_MAX> (cw, s_wv[w]);
+	run = exf ? exv : ext<WANT_MAX> (cw, exv);
+	m = m0;
+	#pragma unroll
+	for (int e = 0; e < E; e++)
+		{
+		if (m == 0) run = a[e]; else run = ext<WANT_MAX> (run, a[e]);
+		if (++m == Wn) m = 0;
+		A[mm_pad<LOGE> (j0 + e)] = run;
+		}
+	}
+	__syncthreads ();
+
+	// ---------------- backward: blocks restart where j % Wn == Wn-1 -------------
+	{
+	double run = NEUTRAL;  int reset = 0;
+	uint32_t m = m0 + (E - 1);  m %= Wn;          // position of the strip's last cell inside its block
+	const uint32_t mLast = m;
+	#pragma unroll
+	for (int e = E - 1; e >= 0; e--)
+		{
+		if (m == Wn - 1) { run = a[e];  reset = 1; } else run = ext<WANT_MAX> (run, a[e]);
+		m = (m == 0) ? Wn - 1 : m - 1;
+		}
+	double val = run;  int f = reset;
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1)
+		{
+		double v2 = shfl_down_f64 (val, d);
+		int    f2 = __shfl_down_sync (0xffffffffu, f, d);
+		if (lane + d < 32) { if (!f) val = ext<WANT_MAX> (v2, val);  f |= f2; }
+		}
+	double exv = shfl_down_f64 (val, 1);
+	int    exf = __shfl_down_sync (0xffffffffu, f, 1);
+	if (lane == 31) { exv = NEUTRAL;  exf = 0; }
+	if (lane == 0) { s_wv[warp] = val;  s_wf[warp] = f; }
+	__syncthreads ();
+	double cw = NEUTRAL;
+	for (int w = MM_WARPS - 1; w > warp; w--) cw = s_wf[w] ? s_wv[w] : ext<WANT_MAX> (cw, s_wv[w]);
+	run = exf ? exv : ext<WANT_MAX> (cw, exv);
+	m = mLast;
+	#pragma unroll
+	for (int e = E - 1; e >= 0; e--)
+		{
+		if (m == Wn - 1) run = a[e]; else run = ext<WANT_MAX> (run, a[e]);
+		m = (m == 0) ? Wn - 1 : m - 1;
+		B[mm_pad<LOGE> (j0 + e)] = run;
+		}
+	}
+	__syncthreads ();
+
+	for (uint32_t c = threadIdx.x; c < nOut; c += MM_THREADS)
+		{
+		double w = ext<WANT_MAX> (B[mm_pad<LOGE> (c)], A[mm_pad<LOGE> (c + Wn - 1)]);
+		if (MODE == 0) out[t0 + c] = w;
+		else
+			{
+			double v = __ldg (in + t0 + c);
+			bool beaten = WANT_MAX ? (w > v) : (w < v);
+			out[t0 + c] = beaten ? fill : v;
+			}
+		}
+	}
+
+// very wide windows: direct scan per output (correct for any width; slow)
+template <bool WANT_MAX, int MODE>
+__global__ void __launch_bounds__(256)
+k_extrema_wide (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
+                const double* __restrict__ in, double* __restrict__ out,
+                uint32_t reachL, uint32_t reachR, double fill)
+	{
+	int seg;  uint64_t tis;
+	tile_to_seg (base, nseg, blockIdx.x, seg, tis);
+	const SegDev sd = segs[seg];
+	uint64_t i = sd.lo + tis * 256 + threadIdx.x;
+	if (i >= sd.hi) return;
+	uint64_t a = (i - sd.dlo > reachL) ? i - reachL : sd.dlo;
+	uint64_t b = (sd.dhi - 1 - i > reachR) ? i + reachR : sd.dhi - 1;
+	double w = in[a];
+	for (uint64_t j = a + 1; j <= b; j++) w = ext<WANT_MAX> (w, in[j]);
+	if (MODE == 0) out[i] = w;
+	else
+		{
+		double v = in[i];
+		bool beaten = WANT_MAX ? (w > v) : (w < v);
+		out[i] = beaten ? fill : v;
+		}
+	}
+
+template <int LOGE, bool WANT_MAX, int MODE>
+static int launch_extrema_t (gdsp_ctx* c, gdsp_layout* L, const double* in, double* out,
+                             uint32_t reachL, uint32_t Wn, double fill)
+	{
+	constexpr uint32_t SCAP = (1u << LOGE) * MM_THREADS;
+	constexpr uint32_t PADN = SCAP + (SCAP >> LOGE) + 2;
+	uint32_t tileOut = SCAP - (Wn - 1);
+	tileOut &= ~63u;                                   // keep tile starts 512-byte aligned
+	size_t smem = 2 * (size_t) PADN * sizeof (double);
+	TileMap tm;
+	GDSP_TRY (gdsp_layout_tilemap (L, tileOut, &tm));
+	GDSP_CUDA (cudaFuncSetAttribute (k_extrema<LOGE, WANT_MAX, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	k_extrema<LOGE, WANT_MAX, MODE><<<(unsigned) tm.ntiles, MM_THREADS, smem, c->stream>>>
+		(L->d, tm.d_base, L->nseg, in, out, reachL, Wn, tileOut, fill);
+	GDSP_KERNEL_CHECK ();
+	return GDSP_OK;
+	}
+
+template <bool WANT_MAX, int MODE>
+static int launch_extrema (gdsp_ctx* c, gdsp_layout* L, const double* in, double* out,
+                           uint32_t reachL, uint32_t reachR, double fill)
+	{
+	uint64_t Wn64 = (uint64_t) reachL + reachR + 1;
+	if (Wn64 <= 2049) return launch_extrema_t<3, WANT_MAX, MODE> (c, L, in, out, reachL, (uint32_t) Wn64, fill);
+	if (Wn64 <= 6145) return launch_extrema_t<4, WANT_MAX, MODE> (c, L, in, out, reachL, (uint32_t) Wn64, fill);
+	TileMap tm;
+	GDSP_TRY (gdsp_layout_tilemap (L, 256, &tm));
+	k_extrema_wide<WANT_MAX, MODE><<<(unsigned) tm.ntiles, 256, 0, c->stream>>> (L->d, tm.d_base, L->nseg, in, out, reachL, reachR, fill);
+	GDSP_KERNEL_CHECK ();
+	return GDSP_OK;
+	}
+
+extern "C" int gdsp_local_extrema (gdsp_ctx* c, const gdsp_layout* L_, const double* in, double* out,
+                                   uint32_t neighborhood, int wantMax, double fill)
+	{
+	gdsp_layout* L = (gdsp_layout*) L_;
+	GDSP_REQUIRE (c && L && in && out, "gdsp_local_extrema: NULL argument");
+	GDSP_REQUIRE (in != out, "gdsp_local_extrema: in and out must be different buffers");
+	GDSP_REQUIRE (neighborhood >= 1, "gdsp_local_extrema: neighborhood must be positive");
+	uint32_t h = (neighborhood - 1) / 2;
+	return wantMax ? launch_extrema<true, 1>  (c, L, in, out, h, h, fill)
+	               : launch_extrema<false, 1> (c, L, in, out, h, h, fill);
+	}
+
+extern "C" int gdsp_best_extrema (gdsp_ctx* c, const gdsp_layout* L_, const double* in, double* out,
+                                  uint32_t window, int wantMax)
+	{
+	gdsp_layout* L = (gdsp_layout*) L_;
+	GDSP_REQUIRE (c && L && in && out, "gdsp_best_extrema: NULL argument");
+	GDSP_REQUIRE (in != out, "gdsp_best_extrema: in and out must be different buffers");
+	GDSP_REQUIRE (window >= 1, "gdsp_best_extrema: window must be positive");
+	uint32_t l = (window - 1) / 2, r = (window - 1) - l;
+	return wantMax ? launch_extrema<true, 0>  (c, L, in, out, l, r, 0.0)
+	               : launch_extrema<false, 0> (c, L, in, out, l, r, 0.0);
+	}

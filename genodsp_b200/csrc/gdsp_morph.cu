@@ -1,0 +1,261 @@
+// gdsp_morph.cu -- run-length morphology on the thresholded signal.
+//
+// Replaces op_close_apply (morphology.c:231-319), op_open_apply (:529-605),
+// op_dilate_apply (:882-1072) and op_erode_apply (:1331-1454).  The reference
+// walks each chromosome with a run-length state machine; here every output cell
+// is a function of the nearest "marker" cell on either side:
+//
+//   close / dilate : markers = cells of the set S          (S = !(v<=T))
+//   open  / erode  : markers = cells NOT in the set S       (S =  (v>T))
+//
+//   K1 k_morph_pack   reads the signal once (8 B/bp), writes 1 marker bit per
+//                     cell (warp ballots) and per-tile first/last marker
+//   K2 k_morph_apply  reads only the bit words (+ the per-tile summaries of a
+//                     bounded number of neighbouring tiles) and writes one/zero
+//                     (8 B/bp).  Distances are exact for any length L: the
+//                     in-word neighbour comes from clz/ffs, the in-tile one from
+//                     a 256-word shuffle scan, the out-of-tile one from the
+//                     neighbouring tiles' summaries.
+// Algorithmic bytes: 16 B/bp (+ 0.16 B/bp of bit traffic).
+#include "gdsp_common.cuh"
+
+#define MO_TILE    8192
+#define MO_WORDS   (MO_TILE / 32)        // 256
+#define MO_THREADS 256
+
+struct MorphWork
+	{
+	uint32_t* words;        // one bit per buffer cell (word = cell >> 5)
+	long long* tileFirst;   // per tile: chromosome coordinate of first marker, -1 if none
+	long long* tileLast;
+	};
+
+// kind: marker definition
+//   0 close : !(v<=T)        1 open : !(v>T)       2 dilate : first cell (v>T), others !(v<=T)
+//   3 erode : !(v>T)
+__global__ void __launch_bounds__(MO_THREADS)
+k_morph_pack (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
+              const double* __restrict__ sig, int kind, double T, MorphWork wk)
+	{
+	__shared__ long long s_first[MO_THREADS / 32], s_last[MO_THREADS / 32];
+	int seg;  uint64_t tis;
+	tile_to_seg (base, nseg, blockIdx.x, seg, tis);
+	const SegDev sd = segs[seg];
+	const uint64_t t0 = sd.lo + tis * MO_TILE;
+	const uint32_t n  = (uint32_t) ((sd.hi - t0 < MO_TILE) ? (sd.hi - t0) : MO_TILE);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const bool endsChrom = ((uint64_t) sd.pos0 + (sd.hi - sd.lo) == (uint64_t) sd.chromLen);
+	const bool complement = (kind == GDSP_MORPH_OPEN || kind == GDSP_MORPH_ERODE);
+
+	long long first = -1, last = -1;
+	// warp `warp` packs words warp, warp+8, ... of the tile
+	for (uint32_t w = warp; w < MO_WORDS; w += MO_THREADS / 32)
+		{
+		const uint32_t c = w * 32 + lane;
+		bool mark = false;
+		if (c < n)
+			{
+			const double v = sig[t0 + c];
+			if      (kind == GDSP_MORPH_CLOSE)  mark = !(v <= T);
+			else if (kind == GDSP_MORPH_DILATE) mark = (sd.pos0 == 0 && t0 + c == sd.lo) ? (v > T) : !(v <= T);
+			else                                mark = !(v > T);
+			}
+		else if (complement && endsChrom && c < ((n + 31u) & ~31u))
+			mark = true;                 // cells past the chromosome end bound every run
+		const uint32_t word = __ballot_sync (0xffffffffu, mark);
+		if (w * 32 < ((n + 31u) & ~31u))
+			{
+			if (lane == 0) wk.words[(t0 >> 5) + w] = word;
+			if (word != 0)
+				{
+				const long long c0 = (long long) sd.pos0 + (long long) (t0 - sd.lo) + (long long) w * 32;
+				if (first < 0) first = c0 + (__ffs (word) - 1);
+				last = c0 + (31 - __clz (word));
+				}
+			}
+		}
+	if (lane == 0) { s_first[warp] = first;  s_last[warp] = last; }
+	__syncthreads ();
+	if (threadIdx.x == 0)
+		{
+		long long f = -1, l = -1;
+		for (int w = 0; w < MO_THREADS / 32; w++)
+			{
+			if (s_first[w] >= 0 && (f < 0 || s_first[w] < f)) f = s_first[w];
+			if (s_last[w] > l) l = s_last[w];
+			}
+		wk.tileFirst[blockIdx.x] = f;
+		wk.tileLast[blockIdx.x]  = l;
+		}
+	}
+
+__global__ void __launch_bounds__(MO_THREADS)
+k_morph_apply (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
+               double* __restrict__ sig, int kind, double L, long long left, long long right,
+               double oneVal, double zeroVal, uint32_t maxTileSearch, MorphWork wk)
+	{
+	__shared__ uint32_t s_word[MO_WORDS];
+	__shared__ int      s_prevW[MO_WORDS], s_nextW[MO_WORDS];
+	__shared__ int      s_wtot[MO_THREADS / 32];
+	__shared__ long long s_carry[2];
+
+	int seg;  uint64_t tis;
+	tile_to_seg (base, nseg, blockIdx.x, seg, tis);
+	const SegDev sd = segs[seg];
+	const uint64_t t0 = sd.lo + tis * MO_TILE;
+	const uint32_t n  = (uint32_t) ((sd.hi - t0 < MO_TILE) ? (sd.hi - t0) : MO_TILE);
+	const uint32_t nw = (n + 31) >> 5;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const long long coord0 = (long long) sd.pos0 + (long long) (t0 - sd.lo);      // chromosome coordinate of tile cell 0
+	const uint64_t tilesInSeg = base[seg + 1] - base[seg];
+
+	// --- tile words and nearest non-empty word on either side (256-entry shuffle scans) ---
+	const uint32_t myWord = (threadIdx.x < nw) ? wk.words[(t0 >> 5) + threadIdx.x] : 0u;
+	s_word[threadIdx.x] = myWord;
+	int pv = myWord ? (int) threadIdx.x : -1;
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1)
+		{
+		int up = __shfl_up_sync (0xffffffffu, pv, d);
+		if (lane >= d && up > pv) pv = up;
+		}
+	if (lane == 31) s_wtot[warp] = pv;
+	__syncthreads ();
+	{
+	int carry = -1;
+	for (int w = 0; w < warp; w++) if (s_wtot[w] > carry) carry = s_wtot[w];
+	s_prevW[threadIdx.x] = (pv > carry) ? pv : carry;
+	}
+	__syncthreads ();
+	int nx = myWord ? (int) threadIdx.x : 0x7fffffff;
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1)
+		{
+		int dn = __shfl_down_sync (0xffffffffu, nx, d);
+		if (lane + d < 32 && dn < nx) nx = dn;
+		}
+	if (lane == 0) s_wtot[warp] = nx;
+	__syncthreads ();
+	{
+	int carry = 0x7fffffff;
+	for (int w = MO_THREADS / 32 - 1; w > warp; w--) if (s_wtot[w] < carry) carry = s_wtot[w];
+	int r = (nx < carry) ? nx : carry;
+	s_nextW[threadIdx.x] = (r == 0x7fffffff) ? -1 : r;
+	}
+
+	// --- nearest marker outside the tile: neighbouring tiles' summaries, bounded search ---
+	if (warp == 0)
+		{
+		long long found = -1;
+		for (uint64_t off = 1; off <= tis && off <= maxTileSearch && found < 0; off += 32)
+			{
+			uint64_t k = off + lane;
+			long long v = (k <= tis && k <= maxTileSearch) ? wk.tileLast[blockIdx.x - k] : -1;
+			unsigned m = __ballot_sync (0xffffffffu, v >= 0);
+			if (m) found = __shfl_sync (0xffffffffu, v, __ffs (m) - 1);
+			}
+		if (lane == 0) s_carry[0] = found;
+		}
+	else if (warp == 1)
+		{
+		long long found = -1;
+		const uint64_t after = tilesInSeg - 1 - tis;
+		for (uint64_t off = 1; off <= after && off <= maxTileSearch && found < 0; off += 32)
+			{
+			uint64_t k = off + lane;
+			long long v = (k <= after && k <= maxTileSearch) ? wk.tileFirst[blockIdx.x + k] : -1;
+			unsigned m = __ballot_sync (0xffffffffu, v >= 0);
+			if (m) found = __shfl_sync (0xffffffffu, v, __ffs (m) - 1);
+			}
+		if (lane == 0) s_carry[1] = found;
+		}
+	__syncthreads ();
+	const long long carryPrev = s_carry[0], carryNext = s_carry[1];
+	const long long chromEnd  = (long long) sd.chromLen;
+
+	for (uint32_t c = threadIdx.x; c < n; c += MO_THREADS)
+		{
+		const uint32_t w = c >> 5;                    // uniform across the warp
+		const uint32_t word = s_word[w];
+		const long long cp = coord0 + c;
+
+		// nearest marker at or before c  /  at or after c   (chromosome coordinates, -1 = none in reach)
+		long long prevM, nextM;
+		uint32_t m = word & (0xffffffffu >> (31 - lane));
+		if (m) prevM = coord0 + (long long) (w * 32 + 31 - __clz (m));
+		else
+			{
+			int pw = (w > 0) ? s_prevW[w - 1] : -1;
+			prevM = (pw >= 0) ? coord0 + (long long) (pw * 32 + 31 - __clz (s_word[pw])) : carryPrev;
+			}
+		m = word & (0xffffffffu << lane);
+		if (m) nextM = coord0 + (long long) (w * 32 + __ffs (m) - 1);
+		else
+			{
+			int nwd = (w + 1 < MO_WORDS) ? s_nextW[w + 1] : -1;
+			nextM = (nwd >= 0) ? coord0 + (long long) (nwd * 32 + __ffs (s_word[nwd]) - 1) : carryNext;
+			}
+
+		bool one;
+		if (kind == GDSP_MORPH_DILATE)
+			one = (prevM >= 0 && cp - prevM <= right) || (nextM >= 0 && nextM - cp <= left);
+		else if (kind == GDSP_MORPH_CLOSE)
+			one = (prevM == cp) || (prevM >= 0 && nextM >= 0 && !((double) (nextM - prevM - 1) > L));
+		else
+			{
+			// markers are the cells outside the set; a marker at cp means cp itself is outside
+			if (prevM == cp) one = false;
+			else
+				{
+				const long long s = prevM + 1;                           // prevM == -1 -> run starts at coordinate 0
+				const long long e = (nextM >= 0) ? nextM : chromEnd;
+				if (kind == GDSP_MORPH_OPEN) one = ((double) (e - s) > L);
+				else                         one = (cp >= s + right) && (cp < e - left);
+				}
+			}
+		sig[t0 + c] = one ? oneVal : zeroVal;
+		}
+	}
+
+extern "C" size_t gdsp_morph_work_bytes (uint64_t buffer_cells)
+	{
+	uint64_t words = (buffer_cells + 31) / 32 + 64;
+	uint64_t tiles = buffer_cells / MO_TILE + 4096;       // every segment adds at most one partial tile
+	return (size_t) (words * 4 + 256 + 2 * (tiles * 8 + 256));
+	}
+
+extern "C" int gdsp_morphology (gdsp_ctx* c, const gdsp_layout* L_, double* sig, uint64_t buffer_cells, void* work,
+                                int kind, double length, uint32_t left, uint32_t right,
+                                double threshold, double oneVal, double zeroVal)
+	{
+	gdsp_layout* L = (gdsp_layout*) L_;
+	GDSP_REQUIRE (c && L && sig && work, "gdsp_morphology: NULL argument");
+	GDSP_REQUIRE (kind >= GDSP_MORPH_CLOSE && kind <= GDSP_MORPH_ERODE, "gdsp_morphology: bad kind %d", kind);
+	for (int s = 0; s < L->nseg; s++)
+		GDSP_REQUIRE (L->h[s].pos0 == 0 && L->h[s].hi - L->h[s].lo == L->h[s].chrom_len,
+		              "gdsp_morphology: slab-sharded chromosomes need the carry variant (not in this build)");
+	TileMap tm;
+	GDSP_TRY (gdsp_layout_tilemap (L, MO_TILE, &tm));
+	uint64_t words = (buffer_cells + 31) / 32 + 64;
+	uint64_t tilesCap = buffer_cells / MO_TILE + 4096;
+	GDSP_REQUIRE (tm.ntiles <= tilesCap, "gdsp_morphology: layout has more tiles than the work buffer allows");
+	MorphWork wk;
+	char* p = (char*) work;
+	wk.words = (uint32_t*) p;                  p += ((words * 4 + 255) / 256) * 256;
+	wk.tileFirst = (long long*) p;             p += ((tilesCap * 8 + 255) / 256) * 256;
+	wk.tileLast  = (long long*) p;
+
+	// how far can a neighbouring marker matter?  (cells) -> tiles
+	double reach;
+	if      (kind == GDSP_MORPH_DILATE || kind == GDSP_MORPH_ERODE) reach = (double) ((left > right) ? left : right) + 1;
+	else    reach = length + 2;
+	double tilesD = reach / MO_TILE + 2;
+	uint32_t maxTileSearch = (tilesD > 4.0e9) ? 0xffffffffu : (uint32_t) tilesD;
+
+	k_morph_pack<<<(unsigned) tm.ntiles, MO_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, sig, kind, threshold, wk);
+	GDSP_KERNEL_CHECK ();
+	k_morph_apply<<<(unsigned) tm.ntiles, MO_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, sig, kind, length,
+	        (long long) left, (long long) right, oneVal, zeroVal, maxTileSearch, wk);
+	GDSP_KERNEL_CHECK ();
+	return GDSP_OK;
+	}

@@ -1,0 +1,322 @@
+// gdsp_pointwise.cu -- fused pointwise operator programs, interval tables and
+// the min/max reduction.
+//
+// One launch applies a whole chain of consecutive pointwise operators per cell
+// (binarize, addconst, abs, clip, erase, invert and the interval-file operators
+// add/subtract/multiply/divide/mask/masknot/or/and), so a chain of any length
+// costs one 8-byte read and one 8-byte write per base instead of one pass per
+// operator as in the reference's executor loop (genodsp.c:909-921).
+// Reference loops replaced: logical.c:250-263, add.c:736-739, add.c:1046-1047,
+// mask.c:893-913, mask.c:1182-1228, add.c:936, logical.c:466-473, add.c:280-281,
+// multiply.c:312-329, multiply.c:705-722, mask.c:295-296, mask.c:591-599,
+// logical.c:or/and loops.
+#include "gdsp_common.cuh"
+
+struct gdsp_ivl_table
+	{
+	gdsp_ctx* ctx;
+	uint64_t  n;
+	uint64_t* d_start;      // buffer cell index, ascending
+	uint64_t* d_end;
+	double*   d_val;
+	};
+
+struct PwOpDev
+	{
+	int32_t  code;
+	uint32_t flags;
+	double   a, b, c;
+	const uint64_t* start;
+	const uint64_t* end;
+	const double*   val;
+	uint64_t        n;
+	};
+
+struct PwProgram
+	{
+	int     nops;
+	int     hasIvl;
+	PwOpDev ops[GDSP_MAX_POINTWISE];
+	};
+
+#define PW_THREADS 256
+#define PW_TILE    4096
+
+// index of the last interval with start <= g inside [lo,hi), or lo-1
+__device__ __forceinline__ int64_t ivl_find (const uint64_t* __restrict__ start, int64_t lo, int64_t hi, uint64_t g)
+	{
+	while (lo < hi)
+		{
+		int64_t mid = (lo + hi) >> 1;
+		if (start[mid] <= g) lo = mid + 1; else hi = mid;
+		}
+	return lo - 1;
+	}
+
+__device__ __forceinline__ double pw_apply (const PwProgram& P, double v, uint64_t g,
+                                            const int64_t* s_klo, const int64_t* s_khi)
+	{
+	for (int i = 0; i < P.nops; i++)
+		{
+		const PwOpDev& op = P.ops[i];
+		switch (op.code)
+			{
+			case GDSP_PW_BINARIZE_GT:  v = (v >  op.a) ? op.b : op.c;  break;
+			case GDSP_PW_BINARIZE_GE:  v = (v >= op.a) ? op.b : op.c;  break;
+			case GDSP_PW_ADDCONST:     v = __dadd_rn (v, op.a);        break;
+			case GDSP_PW_ABS:          if (v < 0) v = -v;              break;
+			case GDSP_PW_CLIP_MIN:     if (v < op.a) v = op.a;         break;
+			case GDSP_PW_CLIP_MAX:     if (v > op.a) v = op.a;         break;
+			case GDSP_PW_CLIP_BOTH:    if (v < op.a) v = op.a; else if (v > op.b) v = op.b;  break;
+			case GDSP_PW_ERASE:
+				{
+				const bool hmin = op.flags & GDSP_PW_ERASE_HAVE_MIN, hmax = op.flags & GDSP_PW_ERASE_HAVE_MAX;
+				bool kill;
+				if (op.flags & GDSP_PW_ERASE_KEEP_INSIDE) kill = (hmin && v < op.a) || (hmax && v > op.b);
+				else                                      kill = (!hmin || v >= op.a) && (!hmax || v <= op.b);
+				if (kill) v = op.c;
+				break;
+				}
+			case GDSP_PW_INVERT:         v = __dsub_rn (op.a, v);      break;
+			case GDSP_PW_NONZERO_TO_ONE: if (v != 0.0) v = 1.0;        break;
+			default:
+				{
+				// interval-table operators
+				int64_t k = ivl_find (op.start, s_klo[i], s_khi[i], g);
+				bool inside = (k >= s_klo[i]) && (g < op.end[k]);
+				switch (op.code)
+					{
+					case GDSP_PW_IVL_ADD: if (inside) v = __dadd_rn (v, op.val[k]);  break;
+					case GDSP_PW_IVL_SUB: if (inside) v = __dsub_rn (v, op.val[k]);  break;
+					case GDSP_PW_IVL_MUL: v = inside ? __dmul_rn (v, op.val[k]) : op.a;  break;
+					case GDSP_PW_IVL_DIV: v = inside ? __ddiv_rn (v, op.val[k]) : ((v >= 0) ? op.a : -op.a);  break;
+					case GDSP_PW_IVL_SET: if (inside) v = op.a;  break;
+					case GDSP_PW_IVL_SET_OUTSIDE: if (!inside) v = op.a;  break;
+					}
+				}
+			}
+		}
+	return v;
+	}
+
+__global__ void __launch_bounds__(PW_THREADS)
+k_pointwise (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
+             const double* __restrict__ in, double* __restrict__ out, const __grid_constant__ PwProgram P)
+	{
+	__shared__ int64_t s_klo[GDSP_MAX_POINTWISE], s_khi[GDSP_MAX_POINTWISE];
+	int seg;  uint64_t tis;
+	tile_to_seg (base, nseg, blockIdx.x, seg, tis);
+	const SegDev sd = segs[seg];
+	const uint64_t t0 = sd.lo + tis * PW_TILE;
+	uint64_t t1 = t0 + PW_TILE;  if (t1 > sd.hi) t1 = sd.hi;
+
+	if (P.hasIvl)
+		{
+		// range of table entries that can touch [t0,t1): the last entry starting
+		// at or before t0 (it may cover t0) up to the last entry starting before t1
+		if (threadIdx.x < P.nops && P.ops[threadIdx.x].code >= GDSP_PW_IVL_ADD)
+			{
+			const PwOpDev& op = P.ops[threadIdx.x];
+			int64_t a = ivl_find (op.start, 0, (int64_t) op.n, t0);
+			int64_t b = ivl_find (op.start, 0, (int64_t) op.n, t1 - 1);
+			s_klo[threadIdx.x] = (a < 0) ? 0 : a;
+			s_khi[threadIdx.x] = b + 1;
+			}
+		__syncthreads ();
+		}
+
+	// t0 is even (segment starts are 64-aligned): 128-bit accesses on whole pairs
+	for (uint64_t i = t0 + 2 * threadIdx.x; i < t1; i += 2 * PW_THREADS)
+		{
+		if (i + 1 < t1)
+			{
+			double2 v = ldg_stream (in + i);
+			v.x = pw_apply (P, v.x, i,     s_klo, s_khi);
+			v.y = pw_apply (P, v.y, i + 1, s_klo, s_khi);
+			stg_stream (out + i, v);
+			}
+		else
+			out[i] = pw_apply (P, in[i], i, s_klo, s_khi);
+		}
+	}
+
+// ---------------------------------------------------------------------------
+// min / max / count reduction (strided, range-filtered)
+// ---------------------------------------------------------------------------
+
+#define MMR_TILE 8192
+
+__global__ void __launch_bounds__(256)
+k_minmax (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
+          const double* __restrict__ sig, uint32_t stride, double mnAllowed, double mxAllowed,
+          unsigned long long* __restrict__ res /* [0]=minKey [1]=maxKey [2]=count */)
+	{
+	__shared__ unsigned long long s_mn[8], s_mx[8], s_ct[8];
+	int seg;  uint64_t tis;
+	tile_to_seg (base, nseg, blockIdx.x, seg, tis);
+	const SegDev sd = segs[seg];
+	const uint64_t t0 = sd.lo + tis * MMR_TILE;
+	uint64_t t1 = t0 + MMR_TILE;  if (t1 > sd.hi) t1 = sd.hi;
+	unsigned long long mn = ~0ull, mx = 0ull, ct = 0ull;
+	for (uint64_t i = t0 + threadIdx.x; i < t1; i += 256)
+		{
+		if (stride > 1 && ((uint64_t) sd.pos0 + (i - sd.lo)) % stride != 0) continue;
+		double v = sig[i];
+		if (v < mnAllowed) continue;
+		if (v > mxAllowed) continue;
+		ct++;
+		if (v != v) continue;
+		unsigned long long k = f64_key (v);
+		if (k < mn) mn = k;
+		if (k > mx) mx = k;
+		}
+	#pragma unroll
+	for (int d = 16; d > 0; d >>= 1)
+		{
+		unsigned long long a = __shfl_xor_sync (0xffffffffu, mn, d);  if (a < mn) mn = a;
+		unsigned long long b = __shfl_xor_sync (0xffffffffu, mx, d);  if (b > mx) mx = b;
+		ct += __shfl_xor_sync (0xffffffffu, ct, d);
+		}
+	if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = mn;  s_mx[threadIdx.x >> 5] = mx;  s_ct[threadIdx.x >> 5] = ct; }
+	__syncthreads ();
+	if (threadIdx.x == 0)
+		{
+		for (int w = 1; w < 8; w++)
+			{
+			if (s_mn[w] < mn) mn = s_mn[w];
+			if (s_mx[w] > mx) mx = s_mx[w];
+			ct += s_ct[w];
+			}
+		if (ct != 0)
+			{
+			atomicMin (&res[0], mn);
+			atomicMax (&res[1], mx);
+			atomicAdd (&res[2], ct);
+			}
+		}
+	}
+
+// ---------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------
+
+extern "C" int gdsp_ivl_table_create (gdsp_ctx* c, const gdsp_layout* L_, const uint32_t* h_seg,
+                                      const uint32_t* h_start, const uint32_t* h_end, const double* h_val,
+                                      uint64_t n, gdsp_ivl_table** out)
+	{
+	const gdsp_layout* L = L_;
+	GDSP_REQUIRE (c && L && out, "gdsp_ivl_table_create: NULL argument");
+	GDSP_REQUIRE (n == 0 || (h_seg && h_start && h_end), "gdsp_ivl_table_create: NULL interval arrays");
+	std::vector<uint64_t> s, e;
+	std::vector<double> v;
+	s.reserve (n);  e.reserve (n);  v.reserve (n);
+	uint64_t prevEnd = 0;
+	for (uint64_t k = 0; k < n; k++)
+		{
+		GDSP_REQUIRE (h_seg[k] < (uint32_t) L->nseg, "gdsp_ivl_table_create: interval %llu names segment %u of %d",
+		              (unsigned long long) k, h_seg[k], L->nseg);
+		const gdsp_seg& g = L->h[h_seg[k]];
+		uint64_t p0 = g.pos0, p1 = p0 + (g.hi - g.lo);
+		if (h_start[k] >= h_end[k]) continue;
+		if ((uint64_t) h_end[k] <= p0 || (uint64_t) h_start[k] >= p1) continue;       // not on this piece
+		uint64_t a = g.lo + (((uint64_t) h_start[k] > p0 ? (uint64_t) h_start[k] : p0) - p0);
+		uint64_t b = g.lo + (((uint64_t) h_end[k]   < p1 ? (uint64_t) h_end[k]   : p1) - p0);
+		GDSP_REQUIRE (a >= prevEnd, "gdsp_ivl_table_create: intervals must be sorted in layout order and disjoint (entry %llu)",
+		              (unsigned long long) k);
+		s.push_back (a);  e.push_back (b);  v.push_back (h_val ? h_val[k] : 1.0);
+		prevEnd = b;
+		}
+	gdsp_ivl_table* t = new gdsp_ivl_table ();
+	t->ctx = c;  t->n = s.size ();  t->d_start = t->d_end = NULL;  t->d_val = NULL;
+	size_t m = t->n ? t->n : 1;
+	cudaSetDevice (c->device);
+	cudaError_t er = cudaMalloc (&t->d_start, m * sizeof (uint64_t));
+	if (er == cudaSuccess) er = cudaMalloc (&t->d_end, m * sizeof (uint64_t));
+	if (er == cudaSuccess) er = cudaMalloc (&t->d_val, m * sizeof (double));
+	if (er == cudaSuccess && t->n)
+		{
+		er = cudaMemcpyAsync (t->d_start, s.data (), t->n * sizeof (uint64_t), cudaMemcpyHostToDevice, c->stream);
+		if (er == cudaSuccess) er = cudaMemcpyAsync (t->d_end, e.data (), t->n * sizeof (uint64_t), cudaMemcpyHostToDevice, c->stream);
+		if (er == cudaSuccess) er = cudaMemcpyAsync (t->d_val, v.data (), t->n * sizeof (double), cudaMemcpyHostToDevice, c->stream);
+		if (er == cudaSuccess) er = cudaStreamSynchronize (c->stream);
+		}
+	if (er != cudaSuccess)
+		{
+		gdsp_set_error ("gdsp_ivl_table_create: %s", cudaGetErrorString (er));
+		gdsp_ivl_table_destroy (t);
+		return GDSP_ERR_CUDA;
+		}
+	*out = t;
+	return GDSP_OK;
+	}
+
+extern "C" void gdsp_ivl_table_destroy (gdsp_ivl_table* t)
+	{
+	if (t == NULL) return;
+	cudaStreamSynchronize (t->ctx->stream);
+	if (t->d_start) cudaFree (t->d_start);
+	if (t->d_end)   cudaFree (t->d_end);
+	if (t->d_val)   cudaFree (t->d_val);
+	delete t;
+	}
+
+extern "C" int gdsp_pointwise (gdsp_ctx* c, const gdsp_layout* L_, const double* in, double* out,
+                               const gdsp_pw_op* ops, int nops)
+	{
+	gdsp_layout* L = (gdsp_layout*) L_;
+	GDSP_REQUIRE (c && L && in && out && ops, "gdsp_pointwise: NULL argument");
+	GDSP_REQUIRE (nops >= 1 && nops <= GDSP_MAX_POINTWISE, "gdsp_pointwise: %d operators (1..%d allowed)", nops, GDSP_MAX_POINTWISE);
+	PwProgram P;
+	memset (&P, 0, sizeof (P));
+	P.nops = nops;
+	for (int i = 0; i < nops; i++)
+		{
+		GDSP_REQUIRE (ops[i].code >= GDSP_PW_BINARIZE_GT && ops[i].code <= GDSP_PW_IVL_SET_OUTSIDE,
+		              "gdsp_pointwise: operator %d has unknown code %d", i, ops[i].code);
+		P.ops[i].code = ops[i].code;  P.ops[i].flags = ops[i].flags;
+		P.ops[i].a = ops[i].a;  P.ops[i].b = ops[i].b;  P.ops[i].c = ops[i].c;
+		if (ops[i].code >= GDSP_PW_IVL_ADD)
+			{
+			GDSP_REQUIRE (ops[i].table != NULL, "gdsp_pointwise: operator %d needs an interval table", i);
+			P.ops[i].start = ops[i].table->d_start;  P.ops[i].end = ops[i].table->d_end;
+			P.ops[i].val = ops[i].table->d_val;      P.ops[i].n = ops[i].table->n;
+			P.hasIvl = 1;
+			}
+		}
+	TileMap tm;
+	GDSP_TRY (gdsp_layout_tilemap (L, PW_TILE, &tm));
+	k_pointwise<<<(unsigned) tm.ntiles, PW_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, in, out, P);
+	GDSP_KERNEL_CHECK ();
+	return GDSP_OK;
+	}
+
+extern "C" int gdsp_minmax (gdsp_ctx* c, const gdsp_layout* L_, const double* sig, uint32_t stride,
+                            double mnAllowed, double mxAllowed, double* h_min, double* h_max, uint64_t* h_count)
+	{
+	gdsp_layout* L = (gdsp_layout*) L_;
+	GDSP_REQUIRE (c && L && sig, "gdsp_minmax: NULL argument");
+	if (stride == 0) stride = 1;
+	void* ws;
+	GDSP_TRY (gdsp_ws (c, 2, 64, &ws));
+	unsigned long long init[3] = { ~0ull, 0ull, 0ull };
+	GDSP_CUDA (cudaMemcpyAsync (ws, init, sizeof (init), cudaMemcpyHostToDevice, c->stream));
+	GDSP_CUDA (cudaStreamSynchronize (c->stream));
+	TileMap tm;
+	GDSP_TRY (gdsp_layout_tilemap (L, MMR_TILE, &tm));
+	k_minmax<<<(unsigned) tm.ntiles, 256, 0, c->stream>>> (L->d, tm.d_base, L->nseg, sig, stride, mnAllowed, mxAllowed,
+	                                                      (unsigned long long*) ws);
+	GDSP_KERNEL_CHECK ();
+	unsigned long long res[3];
+	GDSP_CUDA (cudaMemcpyAsync (res, ws, sizeof (res), cudaMemcpyDeviceToHost, c->stream));
+	GDSP_CUDA (cudaStreamSynchronize (c->stream));
+	if (h_count) *h_count = res[2];
+	// keys back to doubles on the host (same transform as f64_key/key_f64)
+	auto unkey = [] (unsigned long long k) -> double
+		{
+		unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+		double d;  memcpy (&d, &b, 8);  return d;
+		};
+	if (h_min) *h_min = (res[0] == ~0ull && res[1] == 0ull) ? DBL_MAX  : unkey (res[0]);
+	if (h_max) *h_max = (res[0] == ~0ull && res[1] == 0ull) ? -DBL_MAX : unkey (res[1]);
+	return GDSP_OK;
+	}

@@ -1,0 +1,167 @@
+// gdsp_runs.cu -- run-length output stage.
+//
+// Replaces the per-base state machine of report_intervals (genodsp.c:1589-1678):
+// the GPU finds the maximal runs of raw-equal values, drops runs of value 0
+// unless uncovered bases are shown, and compacts (start, end, value) records;
+// the host only formats text (and derives the NA gap lines).
+//
+//   printable(i) = show || v[i] != 0
+//   head(i) = printable(i) && (first cell || !collapse || !printable(i-1) || v[i] != v[i-1])
+//   tail(i) = printable(i) && (last cell  || !collapse || !printable(i+1) || v[i+1] != v[i])
+// Heads and tails alternate, so the k-th head and the k-th tail bound the k-th
+// run; one exclusive scan of the head flags (single pass, decoupled look-back
+// across all tiles of the launch) gives every record its slot.
+// Algorithmic bytes: 8 B/bp read + 16 B/run written.
+#include "gdsp_common.cuh"
+#include "gdsp_scan.cuh"
+
+#define RUN_THREADS 256
+#define RUN_PER     16
+#define RUN_TILE    (RUN_THREADS * RUN_PER)      // 4096
+
+__device__ __forceinline__ uint32_t run_pad (uint32_t j) { return j + (j >> 4); }
+
+__global__ void __launch_bounds__(RUN_THREADS)
+k_runs (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
+        const double* __restrict__ sig, int collapse, int show,
+        uint32_t* __restrict__ oStart, uint32_t* __restrict__ oEnd, double* __restrict__ oVal,
+        uint64_t cap, unsigned long long* __restrict__ segFirst, uint64_t ntiles,
+        ScanStatus<unsigned long long> st)
+	{
+	__shared__ double s_v[RUN_TILE + 2 + ((RUN_TILE + 2) >> 4) + 2];
+	__shared__ unsigned int s_warp[RUN_THREADS / 32];
+	__shared__ unsigned long long s_excl;
+
+	const uint32_t tile = scan_take_ticket (st.ticket);
+	int seg;  uint64_t tis;
+	tile_to_seg (base, nseg, tile, seg, tis);
+	const SegDev sd = segs[seg];
+	const uint64_t t0 = sd.lo + tis * RUN_TILE;
+	const uint32_t n  = (uint32_t) ((sd.hi - t0 < RUN_TILE) ? (sd.hi - t0) : RUN_TILE);
+
+	// staged cell j <-> sig[t0 - 1 + j], j in [0, n+2); cells outside [lo,hi) are never compared
+	for (uint32_t j = threadIdx.x; j < n + 2; j += RUN_THREADS)
+		{
+		int64_t g = (int64_t) t0 - 1 + (int64_t) j;
+		double v = 0.0;
+		if (g >= (int64_t) sd.lo && g < (int64_t) sd.hi) v = sig[g];
+		s_v[run_pad (j)] = v;
+		}
+	__syncthreads ();
+
+	const uint32_t c0 = threadIdx.x * RUN_PER;
+	uint32_t heads = 0, tails = 0;
+	if (c0 < n)
+		{
+		double prev = s_v[run_pad (c0)];           // cell c0-1
+		double cur  = s_v[run_pad (c0 + 1)];
+		#pragma unroll
+		for (int k = 0; k < RUN_PER; k++)
+			{
+			const uint32_t c = c0 + k;
+			double next = s_v[run_pad (c + 2)];
+			if (c < n)
+				{
+				const bool first = (t0 + c == sd.lo), last = (t0 + c + 1 == sd.hi);
+				const bool pr = show || (cur != 0);
+				if (pr)
+					{
+					const bool prPrev = !first && (show || prev != 0);
+					const bool prNext = !last  && (show || next != 0);
+					if (first || !collapse || !prPrev || cur != prev)  heads |= 1u << k;
+					if (last  || !collapse || !prNext || next != cur)  tails |= 1u << k;
+					}
+				}
+			prev = cur;  cur = next;
+			}
+		}
+
+	// block exclusive scan of head counts
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	unsigned int cnt = __popc (heads), inc = cnt;
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1)
+		{
+		unsigned int up = __shfl_up_sync (0xffffffffu, inc, d);
+		if (lane >= d) inc += up;
+		}
+	if (lane == 31) s_warp[warp] = inc;
+	__syncthreads ();
+	unsigned int warpExcl = 0, tileTot = 0;
+	#pragma unroll
+	for (int w = 0; w < RUN_THREADS / 32; w++)
+		{
+		unsigned int t = s_warp[w];
+		if (w < warp) warpExcl += t;
+		tileTot += t;
+		}
+	if (threadIdx.x == 0)
+		{
+		unsigned long long ex = scan_lookback<unsigned long long> (st, tile, tile == 0, (unsigned long long) tileTot, 0ull,
+		                            [] (unsigned long long a, unsigned long long b) { return a + b; });
+		s_excl = ex;
+		if (tis == 0) segFirst[seg] = ex;
+		if (tile == ntiles - 1) segFirst[nseg] = ex + tileTot;
+		}
+	__syncthreads ();
+
+	unsigned long long idx = s_excl + warpExcl + (inc - cnt);      // slot of this thread's first head
+	if (c0 < n && (heads | tails))
+		{
+		#pragma unroll
+		for (int k = 0; k < RUN_PER; k++)
+			{
+			const uint32_t c = c0 + k;
+			if (heads & (1u << k))
+				{
+				if (idx < cap)
+					{
+					double v = s_v[run_pad (c + 1)];
+					const uint32_t coord = sd.pos0 + (uint32_t) (t0 + c - sd.lo);
+					// the reference's state machine starts with val=+0.0 (genodsp.c:1590): a collapsed
+					// run of zeros that begins at base 0 reports that +0.0, not v[0]
+					if (coord == 0 && collapse && v == 0) v = 0.0;
+					oStart[idx] = coord;
+					oVal[idx]   = v;
+					}
+				idx++;
+				}
+			if (tails & (1u << k))
+				{
+				// the run this tail closes is the most recent head: slot idx-1
+				if (idx - 1 < cap) oEnd[idx - 1] = sd.pos0 + (uint32_t) (t0 + c - sd.lo) + 1;
+				}
+			}
+		}
+	}
+
+extern "C" int gdsp_runs (gdsp_ctx* c, const gdsp_layout* L_, const double* sig, int collapse, int showUncovered,
+                          uint32_t* d_start, uint32_t* d_end, double* d_val, uint64_t cap,
+                          uint64_t* h_n_runs, uint64_t* h_seg_first)
+	{
+	gdsp_layout* L = (gdsp_layout*) L_;
+	GDSP_REQUIRE (c && L && sig && h_n_runs, "gdsp_runs: NULL argument");
+	GDSP_REQUIRE (cap == 0 || (d_start && d_end && d_val), "gdsp_runs: NULL output arrays");
+	TileMap tm;
+	GDSP_TRY (gdsp_layout_tilemap (L, RUN_TILE, &tm));
+	void* ws;  void* wseg;
+	GDSP_TRY (gdsp_ws (c, 0, scan_status_bytes<unsigned long long> (tm.ntiles), &ws));
+	GDSP_TRY (gdsp_ws (c, 2, sizeof (unsigned long long) * (L->nseg + 1), &wseg));
+	ScanStatus<unsigned long long> st = scan_status_carve<unsigned long long> (ws, tm.ntiles);
+	GDSP_CUDA (cudaMemsetAsync (ws, 0, scan_status_clear_bytes<unsigned long long> (tm.ntiles), c->stream));
+	k_runs<<<(unsigned) tm.ntiles, RUN_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, sig, collapse ? 1 : 0,
+	        showUncovered == 1 ? 1 : 0, d_start, d_end, d_val, cap, (unsigned long long*) wseg, tm.ntiles, st);
+	GDSP_KERNEL_CHECK ();
+	std::vector<unsigned long long> sf (L->nseg + 1);
+	GDSP_CUDA (cudaMemcpyAsync (sf.data (), wseg, sizeof (unsigned long long) * (L->nseg + 1), cudaMemcpyDeviceToHost, c->stream));
+	GDSP_CUDA (cudaStreamSynchronize (c->stream));
+	*h_n_runs = sf[L->nseg];
+	if (h_seg_first) for (int s = 0; s <= L->nseg; s++) h_seg_first[s] = sf[s];
+	if (sf[L->nseg] > cap)
+		{
+		gdsp_set_error ("gdsp_runs: %llu runs do not fit the caller's capacity of %llu",
+		                (unsigned long long) sf[L->nseg], (unsigned long long) cap);
+		return GDSP_ERR_CAPACITY;
+		}
+	return GDSP_OK;
+	}

@@ -1,0 +1,438 @@
+// gdsp_window.cu -- block sum, sliding sum and Hann smoothing.
+//
+// Replaces op_window_sum_apply (sum.c:211-252), op_sliding_sum_apply
+// (sum.c:420-463) and op_smooth_apply (sum.c:616-676).
+//
+// All three stage a tile of the signal plus its window halo in shared memory;
+// cells outside the chromosome's readable range [dlo,dhi) are staged as 0.0,
+// which is exactly the reference's "beyond the ends is zero" rule.
+#include "gdsp_common.cuh"
+
+// ---------------------------------------------------------------------------
+// staging helper: smem[idx(j)] = in[g0 + j] for j in [0,count), zero outside
+// [dlo,dhi).  g0 may be "negative" (before the buffer start): signed 64-bit.
+// ---------------------------------------------------------------------------
+
+template <int PADSHIFT>
+__device__ __forceinline__ uint32_t pad_idx (uint32_t j)
+	{ return PADSHIFT ? j + (j >> PADSHIFT) : j; }
+
+template <int PADSHIFT>
+__device__ __forceinline__ void stage_zero_padded (double* smem, const double* __restrict__ in,
+                                                   int64_t g0, uint32_t count,
+                                                   uint64_t dlo, uint64_t dhi)
+	{
+	for (uint32_t j = threadIdx.x; j < count; j += blockDim.x)
+		{
+		int64_t g = g0 + (int64_t) j;
+		double v = 0.0;
+		if (g >= (int64_t) dlo && g < (int64_t) dhi) v = __ldg (in + g);
+		smem[pad_idx<PADSHIFT> (j)] = v;
+		}
+	}
+
+// ---------------------------------------------------------------------------
+// sliding sum:  out[c] = sum in[c+h-W+1 .. c+h] / denom   (h = (W-1)/2)
+// Tile-local inclusive prefix sums in shared memory; a window sum is the
+// difference of two prefix values.  Sums of integer-valued (or dyadic) signals
+// are exact in any association order, so the result is bit-identical to the
+// reference's running sum there; for general reals it differs only by
+// rounding (tile-local prefixes keep that below 1e-13 relative).
+// ---------------------------------------------------------------------------
+
+#define SS_THREADS 256
+#define SS_TILE    4096
+
+__global__ void __launch_bounds__(SS_THREADS)
+k_sliding_sum (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
+               const double* __restrict__ in, double* __restrict__ out,
+               uint32_t W, uint32_t strip, double denom)
+	{
+	extern __shared__ double sm[];
+	double* P = sm;                               // staged cells, then prefix sums (count = SS_TILE+W-1)
+	__shared__ double s_warp[SS_THREADS / 32];
+
+	int seg;  uint64_t tis;
+	tile_to_seg (base, nseg, blockIdx.x, seg, tis);
+	const SegDev sd = segs[seg];
+	const uint64_t t0 = sd.lo + tis * SS_TILE;
+	const uint32_t n  = (uint32_t) ((sd.hi - t0 < SS_TILE) ? (sd.hi - t0) : SS_TILE);
+	const uint32_t h  = (W - 1) / 2;
+	const uint32_t reachL = W - 1 - h;
+	const uint32_t count  = n + W - 1;
+
+	stage_zero_padded<0> (P, in, (int64_t) t0 - (int64_t) reachL, count, sd.dlo, sd.dhi);
+	__syncthreads ();
+
+	// each thread owns `strip` consecutive cells (strip is odd: conflict-free 64-bit accesses)
+	const uint32_t j0 = threadIdx.x * strip;
+	const uint32_t j1 = (j0 + strip < count) ? j0 + strip : count;
+	double tot = 0.0;
+	for (uint32_t j = j0; j < j1; j++) tot += P[j];
+
+	// exclusive scan of the strip totals across the block
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	double inc = tot;
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1)
+		{
+		double up = shfl_up_f64 (inc, d);
+		if (lane >= d) inc += up;
+		}
+	if (lane == 31) s_warp[warp] = inc;
+	__syncthreads ();
+	double carry = 0.0;
+	for (int w = 0; w < warp; w++) carry += s_warp[w];
+	double ex = shfl_up_f64 (inc, 1);
+	if (lane == 0) ex = 0.0;
+	double run = carry + ex;
+	for (uint32_t j = j0; j < j1; j++) { run += P[j];  P[j] = run; }
+	__syncthreads ();
+
+	// window for local output c covers staged cells [c, c+W-1]
+	for (uint32_t c = threadIdx.x; c < n; c += blockDim.x)
+		{
+		double hi = P[c + W - 1];
+		double lo = (c > 0) ? P[c - 1] : 0.0;
+		out[t0 + c] = (hi - lo) / denom;
+		}
+	}
+
+// ---------------------------------------------------------------------------
+// block sum: blocks [kW,(k+1)W) counted from chromosome coordinate 0; the
+// left-to-right total of each block (seeded with its first cell, sum.c:230-236)
+// over denom goes to the block's first cell, zeroVal to the rest.
+// One thread folds one block sequentially from shared memory, so the order of
+// additions is the reference's.
+// ---------------------------------------------------------------------------
+
+#define BS_THREADS 256
+
+__global__ void __launch_bounds__(BS_THREADS)
+k_block_sum (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
+             double* __restrict__ sig, uint32_t W, uint32_t blocksPerTile,
+             double denom, int denomActual, double zeroVal)
+	{
+	extern __shared__ double sm[];
+	int seg;  uint64_t tis;
+	tile_to_seg (base, nseg, blockIdx.x, seg, tis);
+	const SegDev sd = segs[seg];
+	// tiles are counted in chromosome coordinates so that blocks line up with coordinate 0:
+	// the piece owns coordinates [pos0, pos0+len); its first tile starts at the block containing pos0
+	const uint64_t len    = sd.hi - sd.lo;
+	const uint64_t tileW  = (uint64_t) blocksPerTile * W;
+	const uint64_t c0     = ((uint64_t) sd.pos0 / W) * W + tis * tileW;     // chromosome coordinate of tile start
+	const uint64_t cEnd   = ((uint64_t) sd.pos0 + (sd.dhi - sd.lo) < (uint64_t) sd.chromLen)
+	                      ? (uint64_t) sd.pos0 + (sd.dhi - sd.lo) : (uint64_t) sd.chromLen; // readable end
+	uint64_t c1 = c0 + tileW;  if (c1 > cEnd) c1 = cEnd;
+	if (c0 >= c1) return;
+	const uint32_t count  = (uint32_t) (c1 - c0);
+	const uint32_t rowS   = W | 1;                                          // odd row stride
+	// cell index of chromosome coordinate c:  sd.lo + (c - pos0)   (may precede sd.lo: halo / dlo)
+	const int64_t  g0     = (int64_t) sd.lo + ((int64_t) c0 - (int64_t) sd.pos0);
+
+	for (uint32_t j = threadIdx.x; j < count; j += blockDim.x)
+		{
+		int64_t g = g0 + (int64_t) j;
+		double v = 0.0;
+		if (g >= (int64_t) sd.dlo && g < (int64_t) sd.dhi) v = sig[g];
+		uint32_t r = j / W;
+		sm[r * rowS + (j - r * W)] = v;
+		}
+	__syncthreads ();
+
+	const uint32_t nblk = (count + W - 1) / W;
+	for (uint32_t b = threadIdx.x; b < nblk; b += blockDim.x)
+		{
+		uint32_t bl = (b * W + W <= count) ? W : count - b * W;
+		const double* row = sm + b * rowS;
+		double t = row[0];
+		for (uint32_t k = 1; k < bl; k++) t += row[k];
+		sm[b * rowS] = denomActual ? t / (double) bl : t / denom;
+		}
+	__syncthreads ();
+
+	// write back only cells this piece owns
+	for (uint32_t j = threadIdx.x; j < count; j += blockDim.x)
+		{
+		int64_t g = g0 + (int64_t) j;
+		if (g < (int64_t) sd.lo || g >= (int64_t) sd.hi) continue;
+		uint32_t r = j / W;
+		sig[g] = (j == r * W) ? sm[r * rowS] : zeroVal;
+		}
+	(void) len;
+	}
+
+// big windows (W larger than a tile, or --window=chromosome): tile partial sums,
+// then one thread per block folds the partials in order
+#define BSB_TILE 4096
+__global__ void __launch_bounds__(256)
+k_block_sum_big_partial (const SegDev* __restrict__ segs, const uint64_t* __restrict__ wbase, int nseg,
+                         const double* __restrict__ sig, uint32_t W, double* __restrict__ partial)
+	{
+	// wbase: prefix over segments of (number of W-blocks * tilesPerBlock)
+	__shared__ double s_red[8];
+	int seg;  uint64_t tin;
+	tile_to_seg (wbase, nseg, blockIdx.x, seg, tin);
+	const SegDev sd = segs[seg];
+	const uint32_t tilesPerBlock = (W + BSB_TILE - 1) / BSB_TILE;
+	const uint64_t blk  = tin / tilesPerBlock, tib = tin % tilesPerBlock;
+	const uint64_t b0   = blk * (uint64_t) W;                   // chromosome coordinate (pos0 must be 0 here)
+	uint64_t b1 = b0 + W;  if (b1 > sd.chromLen) b1 = sd.chromLen;
+	uint64_t c0 = b0 + tib * BSB_TILE, c1 = c0 + BSB_TILE;  if (c1 > b1) c1 = b1;
+	double t = 0.0;
+	for (uint64_t c = c0 + threadIdx.x; c < c1; c += blockDim.x) t += sig[sd.lo + c];
+	#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) t += shfl_xor_f64 (t, d);
+	if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = t;
+	__syncthreads ();
+	if (threadIdx.x == 0)
+		{
+		double a = 0.0;
+		for (int w = 0; w < 8; w++) a += s_red[w];
+		partial[blockIdx.x] = a;
+		}
+	}
+
+__global__ void __launch_bounds__(256)
+k_block_sum_big_write (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, const uint64_t* __restrict__ wbase,
+                       int nseg, double* __restrict__ sig, uint32_t W, const double* __restrict__ partial,
+                       double denom, int denomActual, double zeroVal)
+	{
+	int seg;  uint64_t tis;
+	tile_to_seg (base, nseg, blockIdx.x, seg, tis);
+	const SegDev sd = segs[seg];
+	const uint32_t tilesPerBlock = (W + BSB_TILE - 1) / BSB_TILE;
+	uint64_t c0 = tis * BSB_TILE, c1 = c0 + BSB_TILE;
+	if (c1 > sd.hi - sd.lo) c1 = sd.hi - sd.lo;
+	for (uint64_t c = c0 + threadIdx.x; c < c1; c += blockDim.x)
+		{
+		double v = zeroVal;
+		if (c % W == 0)
+			{
+			uint64_t blk = c / W;
+			uint64_t bl  = (c + W <= sd.chromLen) ? W : sd.chromLen - c;
+			uint32_t nt  = (uint32_t) ((bl + BSB_TILE - 1) / BSB_TILE);
+			const double* p = partial + wbase[seg] + blk * tilesPerBlock;
+			double t = p[0];
+			for (uint32_t k = 1; k < nt; k++) t += p[k];
+			v = denomActual ? t / (double) bl : t / denom;
+			}
+		sig[sd.lo + c] = v;
+		}
+	}
+
+// ---------------------------------------------------------------------------
+// Hann smoothing (direct FIR).  out[i] = fold over k ascending of
+// acc + (w[k] * in[i-h+k]), product and sum rounded separately (no FMA), i.e.
+// the reference's order.  Zero-staged cells outside the chromosome contribute
+// +0.0 products, which leave the accumulator unchanged -- identical to the
+// reference skipping those taps (sum.c:655-662).
+// FP64-issue bound: 2*W double-precision instructions per base.
+//
+// Each thread produces SM_R consecutive outputs from a sliding register window,
+// so one shared-memory load feeds SM_R multiply-adds; the staged tile uses a
+// padded index (one pad cell per 8) so that the stride-8 accesses of a warp are
+// bank-conflict free.
+// ---------------------------------------------------------------------------
+
+#define SM_THREADS 128
+#define SM_R       8
+#define SM_TILE    (SM_THREADS * SM_R)       // 1024 outputs per tile
+#define SM_KC      512                        // taps per staged chunk
+
+__global__ void __launch_bounds__(SM_THREADS)
+k_smooth (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
+          const double* __restrict__ in, double* __restrict__ out,
+          uint32_t W, const double* __restrict__ taps)
+	{
+	__shared__ double s_w[SM_KC + 8];
+	__shared__ double s_x[(SM_TILE + SM_KC + 16) + ((SM_TILE + SM_KC + 16) >> 3) + 2];
+
+	int seg;  uint64_t tis;
+	tile_to_seg (base, nseg, blockIdx.x, seg, tis);
+	const SegDev sd = segs[seg];
+	const uint64_t t0 = sd.lo + tis * SM_TILE;
+	const uint32_t n  = (uint32_t) ((sd.hi - t0 < SM_TILE) ? (sd.hi - t0) : SM_TILE);
+	const uint32_t h  = (W - 1) / 2;
+
+	double acc[SM_R];
+	#pragma unroll
+	for (int r = 0; r < SM_R; r++) acc[r] = 0.0;
+
+	const uint32_t i0 = threadIdx.x * SM_R;
+
+	for (uint32_t kc = 0; kc < W; kc += SM_KC)
+		{
+		const uint32_t kn = (W - kc < SM_KC) ? (W - kc) : SM_KC;      // taps in this chunk
+		__syncthreads ();
+		for (uint32_t k = threadIdx.x; k < kn; k += blockDim.x) s_w[k] = taps[kc + k];
+		// staged cell j  <->  input index t0 - h + kc + j ; need j in [0, SM_TILE + kn - 1 + 8)
+		stage_zero_padded<3> (s_x, in, (int64_t) t0 - (int64_t) h + (int64_t) kc,
+		                      SM_TILE + kn + 8, sd.dlo, sd.dhi);
+		__syncthreads ();
+
+		double x[SM_R], y[SM_R];
+		#pragma unroll
+		for (int m = 0; m < SM_R; m++) x[m] = s_x[pad_idx<3> (i0 + m)];
+
+		uint32_t k0 = 0;
+		for (; k0 + SM_R <= kn; k0 += SM_R)
+			{
+			#pragma unroll
+			for (int m = 0; m < SM_R; m++) y[m] = s_x[pad_idx<3> (i0 + k0 + SM_R + m)];
+			#pragma unroll
+			for (int u = 0; u < SM_R; u++)
+				{
+				const double w = s_w[k0 + u];
+				#pragma unroll
+				for (int r = 0; r < SM_R; r++)
+					{
+					const double xv = (u + r < SM_R) ? x[u + r] : y[u + r - SM_R];
+					acc[r] = __dadd_rn (acc[r], __dmul_rn (w, xv));
+					}
+				}
+			#pragma unroll
+			for (int m = 0; m < SM_R; m++) x[m] = y[m];
+			}
+		if (k0 < kn)
+			{
+			#pragma unroll
+			for (int m = 0; m < SM_R; m++) y[m] = s_x[pad_idx<3> (i0 + k0 + SM_R + m)];
+			#pragma unroll
+			for (int u = 0; u < SM_R; u++)
+				{
+				if (k0 + u < kn)
+					{
+					const double w = s_w[k0 + u];
+					#pragma unroll
+					for (int r = 0; r < SM_R; r++)
+						{
+						const double xv = (u + r < SM_R) ? x[u + r] : y[u + r - SM_R];
+						acc[r] = __dadd_rn (acc[r], __dmul_rn (w, xv));
+						}
+					}
+				}
+			}
+		}
+
+	// SM_R consecutive outputs per thread: 64 contiguous bytes, 128-bit stores
+	double* o = out + t0 + i0;
+	if (i0 + SM_R <= n)
+		{
+		#pragma unroll
+		for (int r = 0; r < SM_R; r += 2) stg_stream (o + r, make_double2 (acc[r], acc[r + 1]));
+		}
+	else
+		{
+		#pragma unroll
+		for (int r = 0; r < SM_R; r++) if (i0 + r < n) o[r] = acc[r];
+		}
+	}
+
+// ---------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------
+
+extern "C" int gdsp_sliding_sum (gdsp_ctx* c, const gdsp_layout* L_, const double* in, double* out,
+                                 uint32_t W, double denom)
+	{
+	gdsp_layout* L = (gdsp_layout*) L_;
+	GDSP_REQUIRE (c && L && in && out, "gdsp_sliding_sum: NULL argument");
+	GDSP_REQUIRE (in != out, "gdsp_sliding_sum: in and out must be different buffers");
+	GDSP_REQUIRE (W >= 1, "gdsp_sliding_sum: window must be positive");
+	uint32_t count = SS_TILE + W - 1;
+	size_t smem = (size_t) count * sizeof (double);
+	GDSP_REQUIRE (smem + 1024 <= c->smem_optin,
+	              "gdsp_sliding_sum: window %u needs %zu bytes of shared memory (limit %zu)", W, smem, c->smem_optin);
+	uint32_t strip = (count + SS_THREADS - 1) / SS_THREADS;
+	strip |= 1;
+	TileMap tm;
+	GDSP_TRY (gdsp_layout_tilemap (L, SS_TILE, &tm));
+	GDSP_CUDA (cudaFuncSetAttribute (k_sliding_sum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	k_sliding_sum<<<(unsigned) tm.ntiles, SS_THREADS, smem, c->stream>>> (L->d, tm.d_base, L->nseg, in, out, W, strip, denom);
+	GDSP_KERNEL_CHECK ();
+	return GDSP_OK;
+	}
+
+extern "C" int gdsp_block_sum (gdsp_ctx* c, const gdsp_layout* L_, double* sig, uint32_t W, int windowIsChrom,
+                               double denom, int denomActual, double zeroVal)
+	{
+	gdsp_layout* L = (gdsp_layout*) L_;
+	GDSP_REQUIRE (c && L && sig, "gdsp_block_sum: NULL argument");
+	GDSP_REQUIRE (windowIsChrom || W >= 1, "gdsp_block_sum: window must be positive");
+	if (!windowIsChrom && W <= 4096)
+		{
+		uint32_t bpt = 4096 / W;  if (bpt == 0) bpt = 1;
+		uint64_t tileW = (uint64_t) bpt * W;
+		// tile counts in chromosome coordinates (first tile starts at the block containing pos0)
+		std::vector<uint64_t> base (L->nseg + 1);
+		uint64_t nt = 0;
+		for (int s = 0; s < L->nseg; s++)
+			{
+			const gdsp_seg& g = L->h[s];
+			uint64_t cs = ((uint64_t) g.pos0 / W) * W, ce = (uint64_t) g.pos0 + (g.hi - g.lo);
+			base[s] = nt;
+			nt += (ce - cs + tileW - 1) / tileW;
+			}
+		base[L->nseg] = nt;
+		void* ws;
+		GDSP_TRY (gdsp_ws (c, 2, sizeof (uint64_t) * (L->nseg + 1), &ws));
+		GDSP_CUDA (cudaMemcpyAsync (ws, base.data (), sizeof (uint64_t) * (L->nseg + 1), cudaMemcpyHostToDevice, c->stream));
+		GDSP_CUDA (cudaStreamSynchronize (c->stream));      // base[] is a host temporary
+		size_t smem = (size_t) bpt * (W | 1) * sizeof (double);
+		GDSP_CUDA (cudaFuncSetAttribute (k_block_sum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		k_block_sum<<<(unsigned) nt, BS_THREADS, smem, c->stream>>> (L->d, (const uint64_t*) ws, L->nseg, sig, W, bpt,
+		                                                            denom, denomActual, zeroVal);
+		GDSP_KERNEL_CHECK ();
+		return GDSP_OK;
+		}
+
+	// big windows: whole chromosomes must be resident on this GPU
+	for (int s = 0; s < L->nseg; s++)
+		GDSP_REQUIRE (L->h[s].pos0 == 0 && L->h[s].hi - L->h[s].lo == L->h[s].chrom_len,
+		              "gdsp_block_sum: windows above 4096 need whole chromosomes on one GPU");
+	std::vector<uint64_t> wbase (L->nseg + 1);
+	uint64_t np = 0;
+	uint32_t maxW = 0;
+	// with --window=chromosome every segment is one block; use the longest as W and clip per segment
+	if (windowIsChrom) { for (int s = 0; s < L->nseg; s++) if (L->h[s].chrom_len > maxW) maxW = L->h[s].chrom_len;  W = maxW; }
+	uint32_t tpb = (W + BSB_TILE - 1) / BSB_TILE;
+	for (int s = 0; s < L->nseg; s++)
+		{
+		wbase[s] = np;
+		np += (((uint64_t) L->h[s].chrom_len + W - 1) / W) * tpb;
+		}
+	wbase[L->nseg] = np;
+	void* ws;  void* wpart;
+	GDSP_TRY (gdsp_ws (c, 2, sizeof (uint64_t) * (L->nseg + 1), &ws));
+	GDSP_TRY (gdsp_ws (c, 3, sizeof (double) * np, &wpart));
+	GDSP_CUDA (cudaMemcpyAsync (ws, wbase.data (), sizeof (uint64_t) * (L->nseg + 1), cudaMemcpyHostToDevice, c->stream));
+	GDSP_CUDA (cudaStreamSynchronize (c->stream));
+	k_block_sum_big_partial<<<(unsigned) np, 256, 0, c->stream>>> (L->d, (const uint64_t*) ws, L->nseg, sig, W, (double*) wpart);
+	GDSP_KERNEL_CHECK ();
+	TileMap tm;
+	GDSP_TRY (gdsp_layout_tilemap (L, BSB_TILE, &tm));
+	k_block_sum_big_write<<<(unsigned) tm.ntiles, 256, 0, c->stream>>> (L->d, tm.d_base, (const uint64_t*) ws, L->nseg, sig, W,
+	                                                                   (const double*) wpart, denom, denomActual, zeroVal);
+	GDSP_KERNEL_CHECK ();
+	return GDSP_OK;
+	}
+
+extern "C" int gdsp_smooth (gdsp_ctx* c, const gdsp_layout* L_, const double* in, double* out,
+                            uint32_t W, const double* h_taps)
+	{
+	gdsp_layout* L = (gdsp_layout*) L_;
+	GDSP_REQUIRE (c && L && in && out && h_taps, "gdsp_smooth: NULL argument");
+	GDSP_REQUIRE (in != out, "gdsp_smooth: in and out must be different buffers");
+	GDSP_REQUIRE (W >= 1, "gdsp_smooth: window must be positive");
+	void* dt;
+	GDSP_TRY (gdsp_ws (c, 2, sizeof (double) * W, &dt));
+	GDSP_CUDA (cudaMemcpyAsync (dt, h_taps, sizeof (double) * W, cudaMemcpyHostToDevice, c->stream));
+	GDSP_CUDA (cudaStreamSynchronize (c->stream));          // h_taps belongs to the caller
+	TileMap tm;
+	GDSP_TRY (gdsp_layout_tilemap (L, SM_TILE, &tm));
+	k_smooth<<<(unsigned) tm.ntiles, SM_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, in, out, W, (const double*) dt);
+	GDSP_KERNEL_CHECK ();
+	return GDSP_OK;
+	}

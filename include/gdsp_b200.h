@@ -1,0 +1,275 @@
+/* gdsp_b200.h -- C-ABI of the B200 (sm_100a) per-base operator library.
+ *
+ * This is the drop-in boundary for genodsp's hot path: every entry point
+ * replaces the per-base loop of one reference function (cited as file:line into
+ * rsharris/genodsp 0.0.10).  Plain C types only: device pointers are `double*`
+ * etc. obtained from gdsp_malloc() or from any CUDA allocator (cudaMalloc,
+ * torch) on the same device; no C++/torch types cross this boundary.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative gdsp_status on failure;
+ *     gdsp_last_error() returns the message of the calling thread's last failure
+ *   - all work is issued on the context's stream and is asynchronous unless
+ *     the function returns a host value (then it synchronises that stream)
+ *   - there is NO CPU fallback: without a usable CUDA device every call fails
+ *
+ * Signal layout ("track"): the chromosomes of a genome live in ONE device
+ * buffer of doubles; each chromosome (or the slab piece of it that this GPU
+ * owns) is a segment described by gdsp_seg.  Kernels compute the cells
+ * [lo,hi) of every segment and may read [dlo,dhi) -- on a single GPU the two
+ * ranges coincide; on a slab-sharded run [dlo,dhi) additionally covers halo
+ * cells received from the neighbouring GPU.  Anything outside [dlo,dhi) is
+ * treated exactly as the reference treats positions beyond the ends of a
+ * chromosome vector.
+ */
+#ifndef GDSP_B200_H
+#define GDSP_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gdsp_ctx    gdsp_ctx;     /* device + stream + workspace          */
+typedef struct gdsp_layout gdsp_layout;  /* device copy of a segment table       */
+
+typedef enum gdsp_status
+	{
+	GDSP_OK            =  0,
+	GDSP_ERR_CUDA      = -1,   /* a CUDA runtime call or kernel failed          */
+	GDSP_ERR_ARG       = -2,   /* invalid argument                              */
+	GDSP_ERR_NOMEM     = -3,   /* device or host allocation failed              */
+	GDSP_ERR_CAPACITY  = -4,   /* caller-provided output buffer too small       */
+	GDSP_ERR_NODEVICE  = -5    /* no CUDA device / not an sm_100 class device   */
+	} gdsp_status;
+
+/* one segment = one chromosome vector (reference: spec, genodsp_interface.h:37-49)
+ * or the part of it owned by this GPU.  All ranges are element indices into the
+ * signal buffer; lo must be a multiple of GDSP_ALIGN. */
+typedef struct gdsp_seg
+	{
+	uint64_t lo, hi;        /* owned cells                                       */
+	uint64_t dlo, dhi;      /* readable cells of the same chromosome (>= owned)  */
+	uint32_t pos0;          /* chromosome coordinate (0-based index into the
+	                           reference's valVector) of cell lo                 */
+	uint32_t chrom_len;     /* spec.length of the whole chromosome               */
+	} gdsp_seg;
+
+#define GDSP_ALIGN 64       /* segment starts are multiples of 64 cells (512 B)  */
+
+/* ---- context, memory, layout ------------------------------------------- */
+
+/* `stream` is a cudaStream_t (or NULL for a private non-blocking stream). */
+int  gdsp_ctx_create   (int device, void* stream, gdsp_ctx** out);
+void gdsp_ctx_destroy  (gdsp_ctx* ctx);
+int  gdsp_ctx_set_stream (gdsp_ctx* ctx, void* stream);
+int  gdsp_sync         (gdsp_ctx* ctx);
+const char* gdsp_last_error (void);
+const char* gdsp_version    (void);
+int  gdsp_device_info  (gdsp_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor,
+                        size_t* free_bytes, size_t* total_bytes);
+
+int  gdsp_malloc       (gdsp_ctx* ctx, size_t bytes, void** dptr);
+int  gdsp_free         (gdsp_ctx* ctx, void* dptr);
+int  gdsp_host_alloc   (gdsp_ctx* ctx, size_t bytes, void** hptr);   /* pinned */
+int  gdsp_host_free    (gdsp_ctx* ctx, void* hptr);
+int  gdsp_h2d          (gdsp_ctx* ctx, void* dst, const void* src, size_t bytes);
+int  gdsp_d2h          (gdsp_ctx* ctx, void* dst, const void* src, size_t bytes);
+int  gdsp_d2d          (gdsp_ctx* ctx, void* dst, const void* src, size_t bytes);
+
+/* timing on the context's stream (CUDA events) */
+int  gdsp_timer_start  (gdsp_ctx* ctx);
+int  gdsp_timer_stop   (gdsp_ctx* ctx, float* ms);      /* synchronises */
+
+/* Pack `nseg` whole chromosomes of the given lengths back to back (each start
+ * rounded up to GDSP_ALIGN).  segs_out (optional, nseg entries) receives the
+ * table, *total_cells the buffer size the caller must allocate (already padded
+ * so that vector loads past a segment end stay inside the buffer).
+ * Reference: the per-chromosome callocs of main, genodsp.c:865-878. */
+int  gdsp_layout_pack   (const uint32_t* chrom_len, int nseg,
+                         gdsp_seg* segs_out, uint64_t* total_cells);
+int  gdsp_layout_create (gdsp_ctx* ctx, const gdsp_seg* segs, int nseg, gdsp_layout** out);
+void gdsp_layout_destroy(gdsp_layout* lay);
+int  gdsp_layout_nseg   (const gdsp_layout* lay);
+const gdsp_seg* gdsp_layout_segs (const gdsp_layout* lay);
+uint64_t gdsp_layout_cells (const gdsp_layout* lay);      /* sum of (hi-lo)      */
+
+/* fill the owned cells of every segment (pads untouched).
+ * Reference: zero fill genodsp.c:876-877; clear-to-missing genodsp.c:1218-1233 */
+int  gdsp_fill (gdsp_ctx* ctx, const gdsp_layout* lay, double* sig, double value);
+
+/* ---- interval accumulation (input stage) ---------------------------------
+ * Reference: read_intervals accumulate loops, genodsp.c:1307-1330
+ * (overlapOp sum).  Intervals are SoA arrays: segment index into the layout,
+ * chromosome start/end (0-based half-open, already origin-shifted, clipped and
+ * validated by the host reader), optional value (NULL => 1.0 each, --novalue).
+ * `*_host` variants take HOST arrays and stream them through pinned staging
+ * buffers; `*_dev` variants take device arrays.
+ *
+ *   mode GDSP_ACC_I32: int32 difference array + segmented scan; exact when all
+ *        values are integers and every partial sum fits in int32
+ *   mode GDSP_ACC_F64: fp64 difference array; exact when every partial sum is
+ *        exactly representable (integer / dyadic values), else within rounding
+ *
+ * sig is overwritten when add_to_existing==0, else the depth is added to it.
+ * `work` is a caller-provided device buffer of gdsp_accumulate_work_bytes(). */
+#define GDSP_ACC_I32 0
+#define GDSP_ACC_F64 1
+size_t gdsp_accumulate_work_bytes (const gdsp_layout* lay, uint64_t buffer_cells, int mode);
+int  gdsp_accumulate_dev  (gdsp_ctx* ctx, const gdsp_layout* lay, double* sig,
+                           uint64_t buffer_cells, void* work,
+                           const uint32_t* d_seg, const uint32_t* d_start,
+                           const uint32_t* d_end, const double* d_val,
+                           uint64_t n_intervals, int mode, int add_to_existing);
+int  gdsp_accumulate_host (gdsp_ctx* ctx, const gdsp_layout* lay, double* sig,
+                           uint64_t buffer_cells, void* work,
+                           const uint32_t* h_seg, const uint32_t* h_start,
+                           const uint32_t* h_end, const double* h_val,
+                           uint64_t n_intervals, int mode, int add_to_existing);
+
+/* ---- windowed sums -------------------------------------------------------- */
+/* op_window_sum_apply, sum.c:211-252 (in place) */
+int  gdsp_block_sum   (gdsp_ctx* ctx, const gdsp_layout* lay, double* sig,
+                       uint32_t window, int window_is_chromosome,
+                       double denom, int denom_is_actual, double zero_val);
+/* op_sliding_sum_apply, sum.c:420-463 (out of place: in -> out) */
+int  gdsp_sliding_sum (gdsp_ctx* ctx, const gdsp_layout* lay, const double* in,
+                       double* out, uint32_t window, double denom);
+/* op_smooth_apply, sum.c:616-676; taps = `window` host doubles computed by the
+ * caller with the host libm exactly as sum.c:634-645 does (out of place) */
+int  gdsp_smooth      (gdsp_ctx* ctx, const gdsp_layout* lay, const double* in,
+                       double* out, uint32_t window, const double* h_taps);
+/* op_cumulative_sum_apply, sum.c:776-792 (in place allowed: out may equal in) */
+int  gdsp_cumulative_sum (gdsp_ctx* ctx, const gdsp_layout* lay, const double* in, double* out);
+
+/* ---- sliding extrema ------------------------------------------------------ */
+/* op_local_maxima_apply minmax.c:1183-1227 (want_max=1, fill=zeroVal) and
+ * op_local_minima_apply minmax.c:981-1022 (want_max=0, fill=infinityVal) */
+int  gdsp_local_extrema (gdsp_ctx* ctx, const gdsp_layout* lay, const double* in,
+                         double* out, uint32_t neighborhood, int want_max, double fill);
+/* op_best_local_max_apply minmax.c:1616-1721 / op_best_local_min_apply :1369-1474 */
+int  gdsp_best_extrema  (gdsp_ctx* ctx, const gdsp_layout* lay, const double* in,
+                         double* out, uint32_t window, int want_max);
+
+/* ---- run-length morphology (in place) --------------------------------------
+ * op_close_apply morphology.c:231-319, op_open_apply :529-605,
+ * op_dilate_apply :882-1072, op_erode_apply :1331-1454.
+ * `work` = device buffer of gdsp_morph_work_bytes(buffer_cells). */
+#define GDSP_MORPH_CLOSE  0
+#define GDSP_MORPH_OPEN   1
+#define GDSP_MORPH_DILATE 2
+#define GDSP_MORPH_ERODE  3
+size_t gdsp_morph_work_bytes (uint64_t buffer_cells);
+int  gdsp_morphology (gdsp_ctx* ctx, const gdsp_layout* lay, double* sig,
+                      uint64_t buffer_cells, void* work, int kind,
+                      double length, uint32_t left, uint32_t right,
+                      double threshold, double one_val, double zero_val);
+
+/* ---- fused pointwise programs ---------------------------------------------
+ * One kernel applies up to GDSP_MAX_POINTWISE consecutive pointwise operators
+ * per cell, so a chain costs one read + one write of the signal. */
+typedef enum gdsp_pw_code
+	{
+	GDSP_PW_BINARIZE_GT = 1,  /* a=threshold b=one c=zero   logical.c:259-262 */
+	GDSP_PW_BINARIZE_GE,      /*                            logical.c:253-256 */
+	GDSP_PW_ADDCONST,         /* a=constant                 add.c:736-739     */
+	GDSP_PW_ABS,              /*                            add.c:1046-1047   */
+	GDSP_PW_CLIP_MIN,         /* a=min                      mask.c:896-899    */
+	GDSP_PW_CLIP_MAX,         /* a=max                      mask.c:901-904    */
+	GDSP_PW_CLIP_BOTH,        /* a=min b=max                mask.c:906-912    */
+	GDSP_PW_ERASE,            /* a=min b=max c=zero, flags  mask.c:1185-1227  */
+	GDSP_PW_INVERT,           /* a=2*mid                    add.c:936         */
+	GDSP_PW_NONZERO_TO_ONE,   /* or/and first pass          logical.c:466-473 */
+	GDSP_PW_IVL_ADD,          /* interval table, v+=val     add.c:280-281     */
+	GDSP_PW_IVL_SUB,          /*                 v-=val     add.c:573-574     */
+	GDSP_PW_IVL_MUL,          /* inside v*=val, gap a(=0)   multiply.c:193-393*/
+	GDSP_PW_IVL_DIV,          /* inside v/=val, gap +-a     multiply.c:586-787*/
+	GDSP_PW_IVL_SET,          /* inside v=a                 mask.c:295-296,
+	                                                        logical.c:or      */
+	GDSP_PW_IVL_SET_OUTSIDE   /* gap v=a                    mask.c:483-668,
+	                                                        logical.c:and     */
+	} gdsp_pw_code;
+
+#define GDSP_PW_ERASE_HAVE_MIN    1u
+#define GDSP_PW_ERASE_HAVE_MAX    2u
+#define GDSP_PW_ERASE_KEEP_INSIDE 4u
+
+/* sorted, non-overlapping interval table in buffer coordinates (cell indices
+ * of the signal buffer), on the device; built by gdsp_ivl_table_create */
+typedef struct gdsp_ivl_table gdsp_ivl_table;
+
+typedef struct gdsp_pw_op
+	{
+	int32_t  code;            /* gdsp_pw_code                                   */
+	uint32_t flags;
+	double   a, b, c;
+	const gdsp_ivl_table* table;   /* for GDSP_PW_IVL_* only                    */
+	} gdsp_pw_op;
+
+#define GDSP_MAX_POINTWISE 16
+
+/* Build a device interval table from host SoA intervals (segment index,
+ * chromosome start/end, value).  Intervals must be sorted by (layout order,
+ * start) and pairwise disjoint -- the host reader establishes that (it is what
+ * multiply.c:308-309 enforces, and what the host-side union/fold produces for
+ * add/mask/or). */
+int  gdsp_ivl_table_create (gdsp_ctx* ctx, const gdsp_layout* lay,
+                            const uint32_t* h_seg, const uint32_t* h_start,
+                            const uint32_t* h_end, const double* h_val,
+                            uint64_t n, gdsp_ivl_table** out);
+void gdsp_ivl_table_destroy (gdsp_ivl_table* t);
+
+int  gdsp_pointwise (gdsp_ctx* ctx, const gdsp_layout* lay, const double* in,
+                     double* out, const gdsp_pw_op* ops, int nops);
+
+/* min and max over all owned cells (invert's auto mid add.c:907-926;
+ * percentile 0 / 100 percentile.c:434-530 with stride/min/max filter) */
+int  gdsp_minmax (gdsp_ctx* ctx, const gdsp_layout* lay, const double* sig,
+                  uint32_t stride, double min_allowed, double max_allowed,
+                  double* h_min, double* h_max, uint64_t* h_count);
+
+/* ---- percentile -------------------------------------------------------------
+ * op_percentile_apply, percentile.c:392-751.  Order statistics of the samples
+ * v[ix], ix = 0,stride,2*stride,.. of every chromosome with
+ * min_allowed <= v <= max_allowed.  ranks[] are 0-based indices into the
+ * ascending order of the samples (computed on the host exactly as
+ * percentile.c:588,686 do); values[] receives the order statistics.
+ * Non-destructive. */
+int  gdsp_select_ranks (gdsp_ctx* ctx, const gdsp_layout* lay, const double* sig,
+                        uint32_t stride, double min_allowed, double max_allowed,
+                        const uint64_t* h_ranks, int nranks, double* h_values,
+                        uint64_t* h_num_samples);
+/* The reference's percentile is destructive; with every cell qualifying and
+ * the last requested rank in the last two chromosomes the genome ends up
+ * globally sorted in layout order (percentile.c:611-651).
+ * `tmp` is a second buffer of buffer_cells doubles. */
+int  gdsp_sort_genome (gdsp_ctx* ctx, const gdsp_layout* lay, double* sig,
+                       double* tmp, uint64_t buffer_cells);
+
+/* ---- clump ---------------------------------------------------------------- */
+/* clump_search, clump.c:494-736 (above=1 clump, 0 anticlump); in place.
+ * `work` = device buffer of gdsp_clump_work_bytes(buffer_cells). */
+size_t gdsp_clump_work_bytes (uint64_t buffer_cells);
+int  gdsp_clump (gdsp_ctx* ctx, const gdsp_layout* lay, double* sig,
+                 uint64_t buffer_cells, void* work, double average,
+                 uint32_t min_length, double relative_length, int above,
+                 double one_val, double zero_val);
+
+/* ---- run-length output ------------------------------------------------------
+ * report_intervals, genodsp.c:1561-1691: maximal runs of raw-equal values
+ * (every cell its own run when collapse==0); runs of value 0 are dropped
+ * unless show_uncovered==1.  Runs are produced in layout order; seg_first[s]
+ * (nseg+1 entries, host) receives the index of segment s's first run.
+ * Returns GDSP_ERR_CAPACITY (and the needed count in *n_runs) when cap is too
+ * small.  starts/ends are chromosome coordinates (0-based, end exclusive). */
+int  gdsp_runs (gdsp_ctx* ctx, const gdsp_layout* lay, const double* sig,
+                int collapse, int show_uncovered,
+                uint32_t* d_start, uint32_t* d_end, double* d_val, uint64_t cap,
+                uint64_t* h_n_runs, uint64_t* h_seg_first);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GDSP_B200_H */

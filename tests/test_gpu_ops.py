@@ -1,0 +1,319 @@
+"""GPU parity tests: every operator runs through the C-ABI (libgdsp_b200.so) on a
+multi-chromosome genome and is compared with the plain-C oracle on the same seeded
+inputs.  Bit-exact unless a tolerance is written in the test."""
+import numpy as np
+import pytest
+
+from checkers import Oracle
+
+pytestmark = pytest.mark.gpu
+
+# lengths chosen to hit tile edges: exact tile multiples, tiny, odd
+CHROMS = [("chr1", 70001), ("chr2", 8192), ("chr3", 4096), ("chr4", 4097), ("chr5", 1), ("chr6", 63), ("chr7", 130000)]
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return Oracle()
+
+
+@pytest.fixture()
+def genome():
+    from genodsp_b200.genome import Genome
+    g = Genome(CHROMS)
+    yield g
+    g.close()
+
+
+def signal(rng, n, kind):
+    if kind == "int":
+        return rng.poisson(5, n).astype(np.float64)
+    if kind == "sparse":
+        v = np.zeros(n)
+        for _ in range(max(1, n // 200)):
+            s = rng.integers(0, n); L = rng.integers(1, 150)
+            v[s:s + L] += rng.integers(1, 4)
+        return v
+    if kind == "dyadic":
+        return rng.integers(-4096, 4096, n).astype(np.float64) / 1024.0
+    return rng.normal(0, 3, n)
+
+
+KINDS = ["int", "sparse", "dyadic", "real"]
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float64).view(np.uint64)
+
+
+def load(genome, rng, kind):
+    inputs = {}
+    for name, n in CHROMS:
+        inputs[name] = signal(rng, n, kind)
+        genome.set_chrom(name, inputs[name])
+    return inputs
+
+
+def compare(genome, inputs, fn, exact=True, rtol=0.0, what=""):
+    for name, n in CHROMS:
+        want = fn(inputs[name].copy())
+        got = genome.get_chrom(name)
+        if exact:
+            bad = np.nonzero(bits(got) != bits(want))[0]
+            assert bad.size == 0, "%s %s: %d mismatches, first at %d: got %r want %r" % (
+                what, name, bad.size, bad[0], got[bad[0]], want[bad[0]])
+        else:
+            scale = np.maximum(np.abs(want), 1.0)
+            err = np.max(np.abs(got - want) / scale) if n else 0.0
+            assert err <= rtol, "%s %s: rel err %g > %g" % (what, name, err, rtol)
+
+
+def test_fill_and_roundtrip(genome):
+    genome.fill(3.5)
+    for name, n in CHROMS:
+        assert np.all(genome.get_chrom(name) == 3.5)
+
+
+@pytest.mark.parametrize("novalue", [True, False])
+def test_accumulate(genome, orc, novalue):
+    rng = np.random.default_rng(1)
+    m = 20000
+    seg = rng.integers(0, genome.nseg, m).astype(np.uint32)
+    lens = np.array([genome.segs[k][5] for k in seg])
+    start = (rng.random(m) * lens).astype(np.uint32)
+    end = np.minimum(lens, start + rng.integers(0, 300, m)).astype(np.uint32)
+    val = None if novalue else rng.integers(-8, 9, m).astype(np.float64) / 4.0
+    genome.fill(0.0)
+    genome.accumulate(seg, start, end, val)
+    for k in range(genome.nseg):
+        name, n = genome.chroms[genome.seg_chrom[k]]
+        sel = seg == k
+        v = np.zeros(n)
+        orc.accumulate(v, start[sel], end[sel], None if novalue else val[sel])
+        got = genome.get_chrom(name)
+        assert np.array_equal(bits(got), bits(v)), name
+    # adding on top of an existing signal (add operator path)
+    before = {name: genome.get_chrom(name) for name, _ in CHROMS}
+    genome.accumulate(seg, start, end, val, add=True)
+    for name, n in CHROMS:
+        assert np.array_equal(genome.get_chrom(name), 2 * before[name])
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("W", [3, 100, 101, 1000, 5000])
+def test_sliding_sum(genome, orc, kind, W):
+    inputs = load(genome, np.random.default_rng(W), kind)
+    genome.slidingsum(W, denom=float(W) if W == 100 else 1.0)
+    d = float(W) if W == 100 else 1.0
+    # integer / dyadic signals: every partial sum is exact, so any association order gives the
+    # reference's bits; general reals: 1e-12 relative (BASELINE.json north_star)
+    compare(genome, inputs, lambda v: orc.sliding_sum(v, W, d), exact=(kind != "real"), rtol=1e-12,
+            what="slidingsum W=%d" % W)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("W", [3, 100, 101, 4096, 5000])
+def test_block_sum(genome, orc, kind, W):
+    inputs = load(genome, np.random.default_rng(W + 7), kind)
+    genome.sum(W, denom=1.0, denom_actual=(W == 101), zero=-1.0 if W == 3 else 0.0)
+    exact = (kind != "real") or W <= 4096       # W<=4096 folds each block in the reference's order
+    compare(genome, inputs, lambda v: orc.block_sum(v, W, 1.0, W == 101, -1.0 if W == 3 else 0.0),
+            exact=exact, rtol=1e-12, what="sum W=%d" % W)
+
+
+@pytest.mark.parametrize("kind", ["int", "real"])
+def test_block_sum_whole_chromosome(genome, orc, kind):
+    inputs = load(genome, np.random.default_rng(3), kind)
+    genome.sum(window_is_chromosome=True)
+    compare(genome, inputs, lambda v: orc.block_sum(v, v.size), exact=(kind == "int"), rtol=1e-12, what="sum chrom")
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("W", [3, 11, 101, 513, 1001])
+def test_smooth_bit_exact(genome, orc, kind, W):
+    inputs = load(genome, np.random.default_rng(W), kind)
+    genome.smooth(W)
+    # chromosomes shorter than the window hit the reference's u32 wrap (sum.c:657); the oracle defines them
+    compare(genome, inputs, lambda v: orc.smooth(v, W), exact=True, what="smooth W=%d" % W)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_cumulative_sum(genome, orc, kind):
+    inputs = load(genome, np.random.default_rng(5), kind)
+    genome.cumulativesum()
+    compare(genome, inputs, orc.cumulative, exact=(kind != "real"), rtol=1e-12, what="cumulativesum")
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("N", [3, 11, 101, 2049, 3001])
+def test_local_extrema(genome, orc, kind, N):
+    inputs = load(genome, np.random.default_rng(N), kind)
+    genome.localmax(N, zero=-2.0)
+    compare(genome, inputs, lambda v: orc.local_extrema(v, N, True, -2.0), what="localmax N=%d" % N)
+    inputs = load(genome, np.random.default_rng(N + 1), kind)
+    genome.localmin(N)
+    compare(genome, inputs, lambda v: orc.local_extrema(v, N, False, np.finfo(np.float64).max), what="localmin N=%d" % N)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("W", [3, 4, 100, 101, 1000, 2050, 6145])
+def test_best_extrema(genome, orc, kind, W):
+    inputs = load(genome, np.random.default_rng(W), kind)
+    genome.bestmax(W)
+    compare(genome, inputs, lambda v: orc.best_extrema(v, W, True), what="bestmax W=%d" % W)
+    inputs = load(genome, np.random.default_rng(W + 1), kind)
+    genome.bestmin(W)
+    compare(genome, inputs, lambda v: orc.best_extrema(v, W, False), what="bestmin W=%d" % W)
+
+
+def test_best_extrema_very_wide(orc):
+    from genodsp_b200.genome import Genome
+    g = Genome([("a", 30000), ("b", 100)])
+    rng = np.random.default_rng(0)
+    ins = {"a": signal(rng, 30000, "real"), "b": signal(rng, 100, "real")}
+    for k, v in ins.items():
+        g.set_chrom(k, v)
+    g.bestmax(8001)
+    for k, v in ins.items():
+        assert np.array_equal(g.get_chrom(k), orc.best_extrema(v.copy(), 8001, True))
+    g.close()
+
+
+@pytest.mark.parametrize("kind", ["int", "sparse", "real"])
+@pytest.mark.parametrize("L", [1, 2, 5, 31, 32, 33, 101, 1001, 20000])
+def test_morphology(genome, orc, kind, L):
+    T = {"int": 5.0, "sparse": 0.0, "real": 0.5}[kind]
+    left, right = L // 2, L - L // 2
+    inputs = load(genome, np.random.default_rng(L), kind)
+    genome.close_(L, T)
+    compare(genome, inputs, lambda v: orc.close(v, L, T), what="close %d" % L)
+    inputs = load(genome, np.random.default_rng(L + 1), kind)
+    genome.open_(L, T, one=2.0, zero=-1.0)
+    compare(genome, inputs, lambda v: orc.open(v, L, T, 2.0, -1.0), what="open %d" % L)
+    inputs = load(genome, np.random.default_rng(L + 2), kind)
+    genome.dilate(L, threshold=T)
+    compare(genome, inputs, lambda v: orc.dilate(v, left, right, T), what="dilate %d" % L)
+    inputs = load(genome, np.random.default_rng(L + 3), kind)
+    genome.dilate(left=3, right=9, threshold=T)
+    compare(genome, inputs, lambda v: orc.dilate(v, 3, 9, T), what="dilate 3/9")
+    inputs = load(genome, np.random.default_rng(L + 4), kind)
+    genome.erode(L, threshold=T)
+    compare(genome, inputs, lambda v: orc.erode(v, left, right, T), what="erode %d" % L)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_pointwise_single_ops(genome, orc, kind):
+    G = type(genome)
+    cases = [
+        ([G.op_binarize(3.0)], lambda v: orc.binarize(v, 3.0)),
+        ([G.op_binarize(3.0, True, 5.0, -5.0)], lambda v: orc.binarize(v, 3.0, True, 5.0, -5.0)),
+        ([G.op_addconst(2.5)], lambda v: orc.addconst(v, 2.5)),
+        ([G.op_abs()], orc.abs),
+        ([G.op_clip(1.0, 4.0)], lambda v: orc.clip(v, 1.0, 4.0)),
+        ([G.op_clip(1.0, None)], lambda v: orc.clip(v, 1.0, None)),
+        ([G.op_clip(None, 2.0)], lambda v: orc.clip(v, None, 2.0)),
+        ([G.op_erase(1.0, 4.0)], lambda v: orc.erase(v, 1.0, 4.0)),
+        ([G.op_erase(1.0, 4.0, True, -1.0)], lambda v: orc.erase(v, 1.0, 4.0, True, -1.0)),
+        ([G.op_erase(2.0, None)], lambda v: orc.erase(v, 2.0, None)),
+        ([G.op_erase(None, 2.0, True)], lambda v: orc.erase(v, None, 2.0, True)),
+        ([G.op_invert(1.25)], lambda v: orc.invert(v, 1.25)),
+    ]
+    for i, (ops, fn) in enumerate(cases):
+        inputs = load(genome, np.random.default_rng(100 + i), kind)
+        genome.pointwise(ops)
+        compare(genome, inputs, fn, what="pointwise case %d" % i)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_pointwise_fused_chain_equals_sequence(genome, orc, kind):
+    G = type(genome)
+    inputs = load(genome, np.random.default_rng(77), kind)
+    genome.pointwise([G.op_addconst(-1.5), G.op_abs(), G.op_clip(0.5, 6.0), G.op_invert(2.0), G.op_binarize(-1.0)])
+    compare(genome, inputs,
+            lambda v: orc.binarize(orc.invert(orc.clip(orc.abs(orc.addconst(v, -1.5)), 0.5, 6.0), 2.0), -1.0),
+            what="fused chain")
+
+
+def test_invert_auto_mid(genome, orc):
+    inputs = load(genome, np.random.default_rng(8), "real")
+    allv = np.concatenate(list(inputs.values()))
+    lo, hi, n = genome.minmax()
+    assert (lo, hi, n) == (allv.min(), allv.max(), allv.size)
+    genome.invert()
+    mid = (allv.min() + allv.max()) / 2.0
+    compare(genome, inputs, lambda v: orc.invert(v, mid), what="invert")
+
+
+def _sorted_disjoint(rng, genome, skip=()):
+    seg, s, e, val = [], [], [], []
+    for k in range(genome.nseg):
+        name, n = genome.chroms[genome.seg_chrom[k]]
+        if name in skip:
+            continue
+        pos = int(rng.integers(0, 50))
+        while pos < n:
+            L = int(rng.integers(1, 300)); end = min(n, pos + L)
+            seg.append(k); s.append(pos); e.append(end); val.append(float(rng.integers(1, 7)) / 2.0 * (-1) ** int(rng.integers(0, 2)))
+            pos = end + int(rng.integers(0, 200))
+    return np.array(seg, np.uint32), np.array(s, np.uint32), np.array(e, np.uint32), np.array(val)
+
+
+@pytest.mark.parametrize("op", ["multiply", "divide", "masknot", "and", "mask", "or", "add", "subtract"])
+def test_interval_table_ops(genome, orc, op):
+    from genodsp_b200 import capi
+    rng = np.random.default_rng(len(op))
+    seg, s, e, val = _sorted_disjoint(rng, genome, skip=("chr3",))
+    table = genome.interval_table(seg, s, e, val)
+    inputs = load(genome, rng, "real")
+    big = np.finfo(np.float64).max
+    prog = {
+        "multiply": [(capi.PW_IVL_MUL, 0.0, 0, 0, 0, table)],
+        "divide": [(capi.PW_IVL_DIV, big, 0, 0, 0, table)],
+        "masknot": [(capi.PW_IVL_SET_OUTSIDE, -2.0, 0, 0, 0, table)],
+        "and": [(capi.PW_NONZERO_TO_ONE, 0.0), (capi.PW_IVL_SET_OUTSIDE, 0.0, 0, 0, 0, table)],
+        "mask": [(capi.PW_IVL_SET, -3.0, 0, 0, 0, table)],
+        "or": [(capi.PW_NONZERO_TO_ONE, 0.0), (capi.PW_IVL_SET, 1.0, 0, 0, 0, table)],
+        "add": [(capi.PW_IVL_ADD, 0.0, 0, 0, 0, table)],
+        "subtract": [(capi.PW_IVL_SUB, 0.0, 0, 0, 0, table)],
+    }[op]
+    genome.pointwise(prog)
+    for k in range(genome.nseg):
+        name, n = genome.chroms[genome.seg_chrom[k]]
+        sel = seg == k
+        v = inputs[name].copy()
+        if op == "multiply":
+            orc.sorted_intervals(v, s[sel], e[sel], val[sel], 0, 0.0)
+        elif op == "divide":
+            orc.sorted_intervals(v, s[sel], e[sel], val[sel], 1, big)
+        elif op == "masknot":
+            orc.sorted_intervals(v, s[sel], e[sel], val[sel], 2, -2.0)
+        elif op == "and":
+            orc.sorted_intervals(orc.logical_prep(v), s[sel], e[sel], val[sel], 3, 0.0)
+        elif op == "mask":
+            orc.mask_intervals(v, s[sel], e[sel], -3.0)
+        elif op == "or":
+            orc.or_intervals(orc.logical_prep(v), s[sel], e[sel], val[sel])
+        elif op == "add":
+            orc.add_intervals(v, s[sel], e[sel], val[sel], 1.0)
+        else:
+            orc.add_intervals(v, s[sel], e[sel], val[sel], -1.0)
+        got = genome.get_chrom(name)
+        assert np.array_equal(bits(got), bits(v)), (op, name)
+    table.close()
+
+
+@pytest.mark.parametrize("collapse", [True, False])
+@pytest.mark.parametrize("show", [0, 1])
+@pytest.mark.parametrize("kind", ["sparse", "int", "real"])
+def test_runs(genome, orc, collapse, show, kind):
+    inputs = load(genome, np.random.default_rng(40), kind)
+    for name, n in CHROMS:
+        if n > 100:
+            v = inputs[name]; v[0:3] = 0.0; v[50:60] = 2.0; v[n - 4:] = 0.0
+            genome.set_chrom(name, v)
+    got = genome.runs(collapse, show, cap=1000)       # small cap: exercises the capacity retry
+    for name, n in CHROMS:
+        rs, re, rv = orc.runs(inputs[name], collapse, show)
+        gs, ge, gv = got[name]
+        assert np.array_equal(gs, rs) and np.array_equal(ge, re), (name, collapse, show)
+        assert np.array_equal(bits(gv), bits(rv)), (name, collapse, show)
