@@ -77,8 +77,8 @@ SIGNATURES = {
     "gdsp_ivl_table_destroy": (None, [_vp]),
     "gdsp_pointwise": (_i, [_vp, _vp, _vp, _vp, C.POINTER(PwOp), _i]),
     "gdsp_minmax": (_i, [_vp, _vp, _vp, _u32, _d, _d, _dp, _dp, _u64p]),
-    "gdsp_select_ranks": (_i, [_vp, _vp, _vp, _u32, _d, _d, _u64p, _i, _dp, _u64p]),
-    "gdsp_sort_genome": (_i, [_vp, _vp, _vp, _vp, _u64]),
+    "gdsp_percentiles": (_i, [_vp, _vp, _vp, _vp, _u64, _u32, _d, _d, _u32p, _i, _dp, _u64p]),
+    "gdsp_sort_genome": (_i, [_vp, _vp, _vp, _vp, _u64, C.POINTER(_i)]),
     "gdsp_clump_work_bytes": (_sz, [_u64]),
     "gdsp_clump": (_i, [_vp, _vp, _vp, _u64, _vp, _d, _u32, _d, _i, _d, _d]),
     "gdsp_runs": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _u64, _u64p, _u64p]),

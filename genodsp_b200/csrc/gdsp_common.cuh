@@ -93,6 +93,9 @@ struct gdsp_ctx
 	size_t       pinned_bytes;
 	cudaEvent_t  pinned_ev[2];
 	cudaEvent_t  t0, t1;
+	double*      taps_host;           // last taps uploaded by gdsp_smooth (host copy) ...
+	double*      taps_dev;            // ... and their device copy, reused while unchanged
+	uint32_t     taps_n;
 	};
 
 // grow-only device scratch (slot 0..GDSP_NUM_WS-1); contents undefined

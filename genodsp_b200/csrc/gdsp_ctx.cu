@@ -50,7 +50,7 @@ extern "C" int gdsp_ctx_create (int device, void* stream, gdsp_ctx** out)
 	c->cc_major   = prop.major;
 	c->cc_minor   = prop.minor;
 	c->smem_optin = prop.sharedMemPerBlockOptin;
-	if (stream != NULL) { c->stream = (cudaStream_t) stream;  c->owns_stream = false; }
+	if (stream != GDSP_STREAM_PRIVATE) { c->stream = (cudaStream_t) stream;  c->owns_stream = false; }
 	else
 		{
 		GDSP_CUDA (cudaStreamCreateWithFlags (&c->stream, cudaStreamNonBlocking));
@@ -71,6 +71,8 @@ extern "C" void gdsp_ctx_destroy (gdsp_ctx* c)
 	cudaStreamSynchronize (c->stream);
 	for (int i = 0; i < GDSP_NUM_WS; i++) if (c->ws[i] != NULL) cudaFree (c->ws[i]);
 	for (int i = 0; i < 2; i++) if (c->pinned[i] != NULL) cudaFreeHost (c->pinned[i]);
+	if (c->taps_dev != NULL) cudaFree (c->taps_dev);
+	if (c->taps_host != NULL) free (c->taps_host);
 	cudaEventDestroy (c->t0);  cudaEventDestroy (c->t1);
 	cudaEventDestroy (c->pinned_ev[0]);  cudaEventDestroy (c->pinned_ev[1]);
 	if (c->owns_stream) cudaStreamDestroy (c->stream);
@@ -82,7 +84,7 @@ extern "C" int gdsp_ctx_set_stream (gdsp_ctx* c, void* stream)
 	GDSP_REQUIRE (c != NULL, "gdsp_ctx_set_stream: ctx is NULL");
 	GDSP_CUDA (cudaStreamSynchronize (c->stream));
 	if (c->owns_stream) { cudaStreamDestroy (c->stream);  c->owns_stream = false; }
-	if (stream != NULL) c->stream = (cudaStream_t) stream;
+	if (stream != GDSP_STREAM_PRIVATE) c->stream = (cudaStream_t) stream;
 	else
 		{
 		GDSP_CUDA (cudaStreamCreateWithFlags (&c->stream, cudaStreamNonBlocking));

@@ -1,0 +1,765 @@
+// gdsp_sort.cu -- percentile selection and the percentile operator's post-state.
+//
+// Replaces op_percentile_apply (percentile.c:392-751).  The reference collects
+// the qualifying samples, qsorts every chromosome and bubble-merges the
+// chromosomes pairwise (percentile.c:611-651, O(m^2 n log n)); here
+//
+//   gdsp_percentiles : exact order statistics WITHOUT sorting the genome.
+//       (1) a hashed sample of the qualifying cells is sorted and gives, for
+//           every requested percentile, a value window [lo,hi] that contains
+//           the wanted rank with overwhelming probability;
+//       (2) ONE streaming pass (8 B/bp) counts the cells in every region
+//           delimited by the window bounds and compacts the (few) cells that
+//           fall strictly inside a window;
+//       (3) the wanted rank is located from the exact region counts; it is
+//           either a window bound itself (heavy ties) or an element of the
+//           small sorted candidate set.  If a rank falls outside its window the
+//           pass is repeated on the exact bracket learned from the counts, so
+//           the result is always exact.
+//   gdsp_sort_genome : LSD radix sort (8-bit digits, stable, single pass per
+//       digit with decoupled look-back; digits on which all keys agree are
+//       skipped) -- the globally sorted genome the reference leaves behind.
+#include <algorithm>
+#include <cmath>
+#include "gdsp_common.cuh"
+
+#define SORT_THREADS 256
+#define SORT_WARPS   8
+#define SORT_ROUNDS  16
+#define SORT_TILE    (SORT_WARPS * SORT_ROUNDS * 32)     // 4096 keys
+
+#define ST_EMPTY 0ull
+#define ST_AGG   1ull
+#define ST_INCL  2ull
+#define ST_SHIFT 62
+#define ST_MASK  ((1ull << ST_SHIFT) - 1)
+
+// output position -> buffer cell (segmented destination), or identity
+struct OutMap
+	{
+	int             nseg;          // 0 = linear
+	const uint64_t* prefix;        // nseg+1: owned cells before segment s
+	const SegDev*   segs;
+	};
+
+__device__ __forceinline__ uint64_t out_cell (const OutMap& om, uint64_t pos)
+	{
+	if (om.nseg == 0) return pos;
+	int lo = 0, hi = om.nseg - 1;
+	while (lo < hi)
+		{
+		int mid = (lo + hi + 1) >> 1;
+		if (om.prefix[mid] <= pos) lo = mid; else hi = mid - 1;
+		}
+	return om.segs[lo].lo + (pos - om.prefix[lo]);
+	}
+
+// ---------------------------------------------------------------------------
+// bitwise OR / AND of all keys: a digit on which OR and AND agree is constant
+// ---------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256)
+k_sort_orand (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg, uint64_t ntiles,
+              const double* __restrict__ in, unsigned long long* __restrict__ res)
+	{
+	unsigned long long o = 0ull, a = ~0ull;
+	for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x)
+		{
+		int seg;  uint64_t tis;
+		tile_to_seg (base, nseg, t, seg, tis);
+		const SegDev sd = segs[seg];
+		const uint64_t t0 = sd.lo + tis * SORT_TILE;
+		uint64_t t1 = t0 + SORT_TILE;  if (t1 > sd.hi) t1 = sd.hi;
+		for (uint64_t i = t0 + threadIdx.x; i < t1; i += 256)
+			{
+			unsigned long long k = f64_key (in[i]);
+			o |= k;  a &= k;
+			}
+		}
+	#pragma unroll
+	for (int d = 16; d > 0; d >>= 1)
+		{
+		o |= __shfl_xor_sync (0xffffffffu, o, d);
+		a &= __shfl_xor_sync (0xffffffffu, a, d);
+		}
+	if ((threadIdx.x & 31) == 0) { atomicOr (&res[0], o);  atomicAnd (&res[1], a); }
+	}
+
+// ---------------------------------------------------------------------------
+// histogram of one digit (warp-private counters, match.any ranking: no
+// same-address shared-memory atomics however skewed the data)
+// ---------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(SORT_THREADS)
+k_sort_hist (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg, uint64_t ntiles,
+             const double* __restrict__ in, int shift, unsigned long long* __restrict__ hist)
+	{
+	__shared__ unsigned int s_cnt[SORT_WARPS][256];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	for (int i = threadIdx.x; i < SORT_WARPS * 256; i += SORT_THREADS) (&s_cnt[0][0])[i] = 0;
+	__syncthreads ();
+	for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x)
+		{
+		int seg;  uint64_t tis;
+		tile_to_seg (base, nseg, t, seg, tis);
+		const SegDev sd = segs[seg];
+		const uint64_t t0 = sd.lo + tis * SORT_TILE;
+		const uint32_t n  = (uint32_t) ((sd.hi - t0 < SORT_TILE) ? (sd.hi - t0) : SORT_TILE);
+		for (int r = 0; r < SORT_ROUNDS; r++)
+			{
+			const uint32_t idx = warp * (SORT_ROUNDS * 32) + r * 32 + lane;
+			const bool valid = idx < n;
+			const unsigned vm = __ballot_sync (0xffffffffu, valid);
+			if (valid)
+				{
+				const unsigned d = (unsigned) ((f64_key (in[t0 + idx]) >> shift) & 255ull);
+				const unsigned peers = __match_any_sync (vm, d);
+				if (lane == __ffs (peers) - 1) s_cnt[warp][d] += __popc (peers);
+				}
+			__syncwarp ();
+			}
+		}
+	__syncthreads ();
+	unsigned int tot = 0;
+	for (int w = 0; w < SORT_WARPS; w++) tot += s_cnt[w][threadIdx.x];
+	if (tot) atomicAdd (&hist[threadIdx.x], (unsigned long long) tot);
+	}
+
+// exclusive prefix over the 256 bins (one warp)
+__global__ void k_sort_binstart (const unsigned long long* __restrict__ hist, unsigned long long* __restrict__ binStart)
+	{
+	const int lane = threadIdx.x;
+	unsigned long long carry = 0;
+	for (int c = 0; c < 8; c++)
+		{
+		unsigned long long v = hist[c * 32 + lane], inc = v;
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+			{
+			unsigned long long up = __shfl_up_sync (0xffffffffu, inc, d);
+			if (lane >= d) inc += up;
+			}
+		binStart[c * 32 + lane] = carry + inc - v;
+		carry += __shfl_sync (0xffffffffu, inc, 31);
+		}
+	}
+
+// ---------------------------------------------------------------------------
+// one stable counting-sort pass on digit `shift`
+// ---------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(SORT_THREADS)
+k_sort_scatter (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
+                const double* __restrict__ in, double* __restrict__ out, OutMap om, int shift,
+                const unsigned long long* __restrict__ binStart,
+                unsigned long long* __restrict__ status /* [ntiles][256] */,
+                unsigned int* __restrict__ ticket)
+	{
+	__shared__ unsigned int       s_cnt[SORT_WARPS][256];
+	__shared__ unsigned long long s_off[256];
+	__shared__ unsigned int       s_ticket;
+
+	if (threadIdx.x == 0) s_ticket = atomicAdd (ticket, 1u);
+	for (int i = threadIdx.x; i < SORT_WARPS * 256; i += SORT_THREADS) (&s_cnt[0][0])[i] = 0;
+	__syncthreads ();
+	const uint64_t tile = s_ticket;
+	int seg;  uint64_t tis;
+	tile_to_seg (base, nseg, tile, seg, tis);
+	const SegDev sd = segs[seg];
+	const uint64_t t0 = sd.lo + tis * SORT_TILE;
+	const uint32_t n  = (uint32_t) ((sd.hi - t0 < SORT_TILE) ? (sd.hi - t0) : SORT_TILE);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+	unsigned long long key[SORT_ROUNDS];
+	unsigned short     rank[SORT_ROUNDS];
+	#pragma unroll
+	for (int r = 0; r < SORT_ROUNDS; r++)
+		{
+		const uint32_t idx = warp * (SORT_ROUNDS * 32) + r * 32 + lane;
+		key[r] = (idx < n) ? f64_key (in[t0 + idx]) : ~0ull;
+		}
+	#pragma unroll
+	for (int r = 0; r < SORT_ROUNDS; r++)
+		{
+		const uint32_t idx = warp * (SORT_ROUNDS * 32) + r * 32 + lane;
+		const bool valid = idx < n;
+		const unsigned vm = __ballot_sync (0xffffffffu, valid);
+		if (valid)
+			{
+			const unsigned d = (unsigned) ((key[r] >> shift) & 255ull);
+			const unsigned peers = __match_any_sync (vm, d);
+			const int leader = __ffs (peers) - 1;
+			unsigned pre = 0;
+			if (lane == leader) { pre = s_cnt[warp][d];  s_cnt[warp][d] = pre + __popc (peers); }
+			pre = __shfl_sync (peers, pre, leader);
+			rank[r] = (unsigned short) (pre + __popc (peers & ((1u << lane) - 1u)));
+			}
+		__syncwarp ();
+		}
+	__syncthreads ();
+
+	// thread d owns digit d: per-warp exclusive offsets, tile count, look-back
+	{
+	const int d = threadIdx.x;
+	unsigned int tot = 0;
+	#pragma unroll
+	for (int w = 0; w < SORT_WARPS; w++) { unsigned int t = s_cnt[w][d];  s_cnt[w][d] = tot;  tot += t; }
+	unsigned long long* st = status + tile * 256 + d;
+	unsigned long long excl = 0;
+	if (tile == 0)
+		*(volatile unsigned long long*) st = (ST_INCL << ST_SHIFT) | (unsigned long long) tot;
+	else
+		{
+		*(volatile unsigned long long*) st = (ST_AGG << ST_SHIFT) | (unsigned long long) tot;
+		for (uint64_t j = tile - 1; ; j--)
+			{
+			unsigned long long s;
+			do { s = *(volatile unsigned long long*) (status + j * 256 + d); } while ((s >> ST_SHIFT) == ST_EMPTY);
+			excl += s & ST_MASK;
+			if ((s >> ST_SHIFT) == ST_INCL) break;
+			}
+		*(volatile unsigned long long*) st = (ST_INCL << ST_SHIFT) | (excl + tot);
+		}
+	s_off[d] = binStart[d] + excl;
+	}
+	__syncthreads ();
+
+	#pragma unroll
+	for (int r = 0; r < SORT_ROUNDS; r++)
+		{
+		const uint32_t idx = warp * (SORT_ROUNDS * 32) + r * 32 + lane;
+		if (idx < n)
+			{
+			const unsigned d = (unsigned) ((key[r] >> shift) & 255ull);
+			const unsigned long long pos = s_off[d] + s_cnt[warp][d] + rank[r];
+			out[out_cell (om, pos)] = key_f64 (key[r]);
+			}
+		}
+	}
+
+// ---------------------------------------------------------------------------
+// host driver of the radix sort
+// ---------------------------------------------------------------------------
+
+struct SortPlan
+	{
+	// input view: either the caller's layout or a linear pseudo-layout over `n` cells
+	const SegDev*   segs;
+	const uint64_t* base;
+	int             nseg;
+	uint64_t        ntiles;
+	};
+
+// device scratch for the sorter, carved from workspace slot 4
+struct SortScratch
+	{
+	unsigned long long* orand;      // 2
+	unsigned long long* hist;       // 256
+	unsigned long long* binStart;   // 256
+	unsigned int*       ticket;     // 1
+	SegDev*             linSeg;     // 1 pseudo segment
+	uint64_t*           linBase;    // 2
+	uint64_t*           prefix;     // nseg+1 (segmented destination)
+	unsigned long long* status;     // ntiles*256
+	};
+
+static int sort_scratch (gdsp_ctx* c, uint64_t ntilesMax, int nseg, SortScratch* s)
+	{
+	size_t small = 8192 + sizeof (uint64_t) * (nseg + 8);
+	size_t bytes = small + ntilesMax * 256 * sizeof (unsigned long long);
+	void* ws;
+	GDSP_TRY (gdsp_ws (c, 4, bytes, &ws));
+	char* p = (char*) ws;
+	s->orand = (unsigned long long*) p;        p += 64;
+	s->hist = (unsigned long long*) p;         p += 2048;
+	s->binStart = (unsigned long long*) p;     p += 2048;
+	s->ticket = (unsigned int*) p;             p += 64;
+	s->linSeg = (SegDev*) p;                   p += 64;
+	s->linBase = (uint64_t*) p;                p += 64;
+	s->prefix = (uint64_t*) p;                 p += ((sizeof (uint64_t) * (nseg + 1) + 255) / 256) * 256;
+	p = (char*) ws + small;
+	s->status = (unsigned long long*) p;
+	return GDSP_OK;
+	}
+
+// Sort the `n` owned cells of `src` (viewed through plan `in`) ascending.
+// Buffers a and b ping-pong; src may be a.  The result lands in *resultBuf
+// (a or b), laid out through `finalMap` (segmented) or linearly.
+static int radix_sort (gdsp_ctx* c, const SortPlan& inPlan, const SortPlan& linPlan, const double* src,
+                       double* a, double* b, const OutMap& finalMap, const SortScratch& sc,
+                       double** resultBuf, int* passesRun)
+	{
+	unsigned long long init[2] = { 0ull, ~0ull };
+	GDSP_CUDA (cudaMemcpyAsync (sc.orand, init, sizeof (init), cudaMemcpyHostToDevice, c->stream));
+	int grid = c->sm_count * 8;
+	if ((uint64_t) grid > inPlan.ntiles) grid = (int) inPlan.ntiles;
+	k_sort_orand<<<grid, 256, 0, c->stream>>> (inPlan.segs, inPlan.base, inPlan.nseg, inPlan.ntiles, src, sc.orand);
+	GDSP_KERNEL_CHECK ();
+	unsigned long long oa[2];
+	GDSP_CUDA (cudaMemcpyAsync (oa, sc.orand, sizeof (oa), cudaMemcpyDeviceToHost, c->stream));
+	GDSP_CUDA (cudaStreamSynchronize (c->stream));
+	int shifts[8], k = 0;
+	for (int d = 0; d < 8; d++)
+		if ((((oa[0] ^ oa[1]) >> (8 * d)) & 255ull) != 0) shifts[k++] = 8 * d;
+	*passesRun = k;
+	if (k == 0)
+		{
+		// all keys identical: the data is already sorted where it lies
+		*resultBuf = (double*) src;
+		return GDSP_OK;
+		}
+	const double* cur = src;
+	SortPlan plan = inPlan;
+	OutMap lin;  lin.nseg = 0;  lin.prefix = NULL;  lin.segs = NULL;
+	for (int p = 0; p < k; p++)
+		{
+		double* dst = (cur == a) ? b : a;
+		const bool last = (p == k - 1);
+		GDSP_CUDA (cudaMemsetAsync (sc.hist, 0, 2048, c->stream));
+		GDSP_CUDA (cudaMemsetAsync (sc.ticket, 0, 4, c->stream));
+		GDSP_CUDA (cudaMemsetAsync (sc.status, 0, plan.ntiles * 256 * sizeof (unsigned long long), c->stream));
+		int g = c->sm_count * 8;
+		if ((uint64_t) g > plan.ntiles) g = (int) plan.ntiles;
+		k_sort_hist<<<g, SORT_THREADS, 0, c->stream>>> (plan.segs, plan.base, plan.nseg, plan.ntiles, cur, shifts[p], sc.hist);
+		GDSP_KERNEL_CHECK ();
+		k_sort_binstart<<<1, 32, 0, c->stream>>> (sc.hist, sc.binStart);
+		GDSP_KERNEL_CHECK ();
+		k_sort_scatter<<<(unsigned) plan.ntiles, SORT_THREADS, 0, c->stream>>> (plan.segs, plan.base, plan.nseg, cur, dst,
+		        last ? finalMap : lin, shifts[p], sc.binStart, sc.status, sc.ticket);
+		GDSP_KERNEL_CHECK ();
+		cur = dst;
+		plan = linPlan;
+		}
+	*resultBuf = (double*) cur;
+	return GDSP_OK;
+	}
+
+static int make_lin_plan (gdsp_ctx* c, const SortScratch& sc, uint64_t n, SortPlan* out)
+	{
+	SegDev ls;  ls.lo = ls.dlo = 0;  ls.hi = ls.dhi = n;  ls.pos0 = 0;  ls.chromLen = (uint32_t) (n > 0xffffffffull ? 0xffffffffu : n);
+	uint64_t lb[2] = { 0, (n + SORT_TILE - 1) / SORT_TILE };
+	GDSP_CUDA (cudaMemcpyAsync (sc.linSeg, &ls, sizeof (ls), cudaMemcpyHostToDevice, c->stream));
+	GDSP_CUDA (cudaMemcpyAsync (sc.linBase, lb, sizeof (lb), cudaMemcpyHostToDevice, c->stream));
+	GDSP_CUDA (cudaStreamSynchronize (c->stream));
+	out->segs = sc.linSeg;  out->base = sc.linBase;  out->nseg = 1;  out->ntiles = lb[1];
+	return GDSP_OK;
+	}
+
+extern "C" int gdsp_sort_genome (gdsp_ctx* c, const gdsp_layout* L_, double* sig, double* tmp, uint64_t buffer_cells,
+                                 int* h_result_in_tmp)
+	{
+	gdsp_layout* L = (gdsp_layout*) L_;
+	GDSP_REQUIRE (c && L && sig && tmp && h_result_in_tmp, "gdsp_sort_genome: NULL argument");
+	GDSP_REQUIRE (sig != tmp, "gdsp_sort_genome: sig and tmp must be different buffers");
+	GDSP_REQUIRE (L->cells <= buffer_cells, "gdsp_sort_genome: buffer smaller than the layout");
+	TileMap tm;
+	GDSP_TRY (gdsp_layout_tilemap (L, SORT_TILE, &tm));
+	SortScratch sc;
+	GDSP_TRY (sort_scratch (c, tm.ntiles, L->nseg, &sc));
+	std::vector<uint64_t> prefix (L->nseg + 1);
+	uint64_t acc = 0;
+	for (int s = 0; s < L->nseg; s++) { prefix[s] = acc;  acc += L->h[s].hi - L->h[s].lo; }
+	prefix[L->nseg] = acc;
+	GDSP_CUDA (cudaMemcpyAsync (sc.prefix, prefix.data (), sizeof (uint64_t) * (L->nseg + 1), cudaMemcpyHostToDevice, c->stream));
+	SortPlan inPlan;  inPlan.segs = L->d;  inPlan.base = tm.d_base;  inPlan.nseg = L->nseg;  inPlan.ntiles = tm.ntiles;
+	SortPlan linPlan;
+	GDSP_TRY (make_lin_plan (c, sc, L->cells, &linPlan));
+	OutMap fm;  fm.nseg = L->nseg;  fm.prefix = sc.prefix;  fm.segs = L->d;
+	double* res = NULL;  int passes = 0;
+	GDSP_TRY (radix_sort (c, inPlan, linPlan, sig, sig, tmp, fm, sc, &res, &passes));
+	*h_result_in_tmp = (res == tmp) ? 1 : 0;
+	return GDSP_OK;
+	}
+
+// ---------------------------------------------------------------------------
+// percentile selection
+// ---------------------------------------------------------------------------
+
+#define PCT_MAXB    256                 // window bounds handled per pass
+#define PCT_SAMPLES (1u << 20)
+
+struct SampleSpace
+	{
+	int             nseg;
+	const uint64_t* sprefix;            // nseg+1: sample slots before segment s
+	const SegDev*   segs;
+	uint32_t        stride;
+	};
+
+// cell of the j-th sampled position of the genome (positions 0,stride,2*stride,.. of
+// every chromosome, percentile.c:559), or ~0 if the slot is outside this piece
+__device__ __forceinline__ uint64_t sample_cell (const SampleSpace& sp, uint64_t j)
+	{
+	int lo = 0, hi = sp.nseg - 1;
+	while (lo < hi)
+		{
+		int mid = (lo + hi + 1) >> 1;
+		if (sp.sprefix[mid] <= j) lo = mid; else hi = mid - 1;
+		}
+	const SegDev sd = sp.segs[lo];
+	const uint64_t first = ((uint64_t) sd.pos0 + sp.stride - 1) / sp.stride * sp.stride;   // first multiple of stride >= pos0
+	const uint64_t coord = first + (j - sp.sprefix[lo]) * sp.stride;
+	return sd.lo + (coord - sd.pos0);
+	}
+
+__global__ void __launch_bounds__(256)
+k_pct_sample (SampleSpace sp, uint64_t nslots, const double* __restrict__ sig, double mn, double mx,
+              unsigned long long keyLo, unsigned long long keyHi, uint32_t m, unsigned long long seed,
+              double* __restrict__ out, unsigned int* __restrict__ count)
+	{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= m) return;
+	// splitmix64 of (seed + i): slot index
+	unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (i + 1);
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+	z ^= z >> 31;
+	const uint64_t j = __umul64hi (z, nslots);
+	const double v = sig[sample_cell (sp, j)];
+	const unsigned long long k = f64_key (v);
+	const bool keep = !(v < mn) && !(v > mx) && k >= keyLo && k <= keyHi;
+	const unsigned act = __activemask ();
+	const unsigned km = __ballot_sync (act, keep);
+	if (km == 0) return;
+	const int lane = threadIdx.x & 31, leader = __ffs (km) - 1;
+	unsigned int b0 = 0;
+	if (lane == leader) b0 = atomicAdd (count, (unsigned int) __popc (km));
+	b0 = __shfl_sync (act, b0, leader);
+	if (keep) out[b0 + __popc (km & ((1u << lane) - 1u))] = v;
+	}
+
+struct PctBounds
+	{
+	int                nb;                 // number of distinct bounds (ascending keys)
+	unsigned long long key[PCT_MAXB];
+	unsigned char      compact[PCT_MAXB + 1];   // open region r (before bound r / after the last): compact its cells?
+	};
+
+// region of key k: 2*(#bounds < k) + (k equals a bound)
+__device__ __forceinline__ int pct_region (const unsigned long long* __restrict__ b, int nb, unsigned long long k, bool& isBound)
+	{
+	int lo = 0, hi = nb;                       // first bound >= k
+	while (lo < hi)
+		{
+		int mid = (lo + hi) >> 1;
+		if (b[mid] < k) lo = mid + 1; else hi = mid;
+		}
+	isBound = (lo < nb) && (b[lo] == k);
+	return 2 * lo + (isBound ? 1 : 0);
+	}
+
+#define PCT_TILE 8192
+
+// counts[2*nb+1] region populations; cand: compacted cells of the flagged open regions
+template <bool SMALL>
+__global__ void __launch_bounds__(256)
+k_pct_pass (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg, uint64_t ntiles,
+            const double* __restrict__ sig, uint32_t stride, double mn, double mx,
+            const __grid_constant__ PctBounds B, unsigned long long* __restrict__ counts,
+            double* __restrict__ cand, unsigned long long cap, unsigned long long* __restrict__ ncand)
+	{
+	__shared__ unsigned long long s_key[PCT_MAXB];
+	__shared__ unsigned int       s_cnt[2 * PCT_MAXB + 1];
+	const int nb = B.nb, nreg = 2 * nb + 1;
+	for (int i = threadIdx.x; i < nb; i += 256) s_key[i] = B.key[i];
+	for (int i = threadIdx.x; i < nreg; i += 256) s_cnt[i] = 0;
+	__syncthreads ();
+	const int lane = threadIdx.x & 31;
+
+	unsigned int mine[5] = { 0, 0, 0, 0, 0 };         // SMALL: nb <= 2 -> at most 5 regions, counted in registers
+
+	for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x)
+		{
+		int seg;  uint64_t tis;
+		tile_to_seg (base, nseg, t, seg, tis);
+		const SegDev sd = segs[seg];
+		const uint64_t t0 = sd.lo + tis * PCT_TILE;
+		uint64_t t1 = t0 + PCT_TILE;  if (t1 > sd.hi) t1 = sd.hi;
+		for (uint64_t i0 = t0; i0 < t1; i0 += 256)
+			{
+			const uint64_t i = i0 + threadIdx.x;
+			bool q = (i < t1);
+			double v = 0.0;
+			if (q && stride > 1) q = (((uint64_t) sd.pos0 + (i - sd.lo)) % stride) == 0;
+			if (q) { v = sig[i];  q = !(v < mn) && !(v > mx); }
+			int reg = 0;  bool isB = false;
+			if (q) reg = pct_region (s_key, nb, f64_key (v), isB);
+			if (SMALL)
+				{
+				if (q)
+					{
+					#pragma unroll
+					for (int r = 0; r < 5; r++) mine[r] += (reg == r);
+					}
+				}
+			else
+				{
+				const unsigned qm = __ballot_sync (0xffffffffu, q);
+				if (q)
+					{
+					const unsigned peers = __match_any_sync (qm, reg);
+					if (lane == __ffs (peers) - 1) atomicAdd (&s_cnt[reg], __popc (peers));
+					}
+				}
+			const bool c = q && !isB && B.compact[reg >> 1];
+			const unsigned cm = __ballot_sync (0xffffffffu, c);
+			if (cm)
+				{
+				unsigned long long b0 = 0;
+				if (lane == __ffs (cm) - 1) b0 = atomicAdd (ncand, (unsigned long long) __popc (cm));
+				b0 = __shfl_sync (0xffffffffu, b0, __ffs (cm) - 1);
+				if (c)
+					{
+					const unsigned long long slot = b0 + __popc (cm & ((1u << lane) - 1u));
+					if (slot < cap) cand[slot] = v;
+					}
+				}
+			}
+		}
+	if (SMALL)
+		{
+		#pragma unroll
+		for (int r = 0; r < 5; r++)
+			{
+			unsigned int x = mine[r];
+			#pragma unroll
+			for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync (0xffffffffu, x, d);
+			if (lane == 0 && x && r < nreg) atomicAdd (&s_cnt[r], x);
+			}
+		}
+	__syncthreads ();
+	for (int i = threadIdx.x; i < nreg; i += 256)
+		if (s_cnt[i]) atomicAdd (&counts[i], (unsigned long long) s_cnt[i]);
+	}
+
+static inline unsigned long long host_key (double v)
+	{
+	unsigned long long b;  memcpy (&b, &v, 8);
+	return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+	}
+static inline double host_unkey (unsigned long long k)
+	{
+	unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+	double d;  memcpy (&d, &b, 8);  return d;
+	}
+
+struct PctJob
+	{
+	uint32_t pMilli;
+	bool     done;
+	double   value;
+	// exact bracket learned so far: the wanted element has key in [keyLo,keyHi];
+	// `below` samples have keys < keyLo and `inside` samples lie in the bracket
+	// (both exact, known once a pass has run: haveCounts)
+	unsigned long long keyLo, keyHi;
+	unsigned long long below, inside;
+	bool     haveCounts;
+	};
+
+extern "C" int gdsp_percentiles (gdsp_ctx* c, const gdsp_layout* L_, const double* sig, double* tmp,
+                                 uint64_t buffer_cells, uint32_t stride, double mn, double mx,
+                                 const uint32_t* h_p_milli, int np, double* h_values, uint64_t* h_num_samples)
+	{
+	gdsp_layout* L = (gdsp_layout*) L_;
+	GDSP_REQUIRE (c && L && sig && tmp && h_num_samples, "gdsp_percentiles: NULL argument");
+	GDSP_REQUIRE (np == 0 || (h_p_milli && h_values), "gdsp_percentiles: NULL percentile arrays");
+	GDSP_REQUIRE (sig != tmp, "gdsp_percentiles: sig and tmp must be different buffers");
+	if (stride == 0) stride = 1;
+	GDSP_REQUIRE (buffer_cells >= 1024, "gdsp_percentiles: tmp buffer must hold at least 1024 cells");
+
+	// sample-slot prefix (every stride-th chromosome coordinate owned by this piece)
+	std::vector<uint64_t> sprefix (L->nseg + 1);
+	uint64_t nslots = 0;
+	for (int s = 0; s < L->nseg; s++)
+		{
+		const gdsp_seg& g = L->h[s];
+		uint64_t p0 = g.pos0, p1 = p0 + (g.hi - g.lo);
+		uint64_t first = (p0 + stride - 1) / stride * stride;
+		sprefix[s] = nslots;
+		if (first < p1) nslots += (p1 - 1 - first) / stride + 1;
+		}
+	sprefix[L->nseg] = nslots;
+
+	TileMap tmSort, tmPct;
+	GDSP_TRY (gdsp_layout_tilemap (L, SORT_TILE, &tmSort));
+	GDSP_TRY (gdsp_layout_tilemap (L, PCT_TILE, &tmPct));
+	const uint64_t candCapTotal = buffer_cells / 2 - 64;         // tmp = [candidates | sort ping-pong]
+	SortScratch sc;
+	GDSP_TRY (sort_scratch (c, (candCapTotal + SORT_TILE - 1) / SORT_TILE + 1, L->nseg, &sc));
+	void* wsv;
+	GDSP_TRY (gdsp_ws (c, 5, 64 + sizeof (unsigned long long) * (2 * PCT_MAXB + 8) + sizeof (uint64_t) * (L->nseg + 1), &wsv));
+	unsigned long long* d_ncand  = (unsigned long long*) wsv;
+	unsigned int*       d_scount = (unsigned int*) ((char*) wsv + 16);
+	unsigned long long* d_counts = (unsigned long long*) ((char*) wsv + 64);
+	uint64_t*           d_sprefix = (uint64_t*) (d_counts + 2 * PCT_MAXB + 8);
+	GDSP_CUDA (cudaMemcpyAsync (d_sprefix, sprefix.data (), sizeof (uint64_t) * (L->nseg + 1), cudaMemcpyHostToDevice, c->stream));
+	GDSP_CUDA (cudaStreamSynchronize (c->stream));
+
+	double* bufA = tmp;                                  // candidates / samples
+	double* bufB = tmp + buffer_cells / 2;               // sort ping-pong partner
+	SampleSpace sp;  sp.nseg = L->nseg;  sp.sprefix = d_sprefix;  sp.segs = L->d;  sp.stride = stride;
+
+	std::vector<PctJob> jobs (np);
+	for (int i = 0; i < np; i++) { jobs[i].pMilli = h_p_milli[i];  jobs[i].done = false;  jobs[i].value = 0;  jobs[i].keyLo = 0;  jobs[i].keyHi = ~0ull;  jobs[i].below = jobs[i].inside = 0;  jobs[i].haveCounts = false; }
+
+	uint64_t numSamples = 0;
+	bool haveCount = false;
+	if (nslots == 0) { *h_num_samples = 0;  return GDSP_OK; }
+
+	std::vector<double> hs;                              // sorted sample (host copy)
+	for (int iter = 0; iter < 80; iter++)
+		{
+		// jobs still open in this iteration (at most PCT_MAXB/2 at a time)
+		std::vector<int> open;
+		for (int i = 0; i < np && (int) open.size () < PCT_MAXB / 2; i++) if (!jobs[i].done) open.push_back (i);
+		if (open.empty () && haveCount) break;
+
+		// ---- (1) sample inside the union bracket of the open jobs, sort it
+		unsigned long long bLo = ~0ull, bHi = 0ull;
+		for (int i : open) { if (jobs[i].keyLo < bLo) bLo = jobs[i].keyLo;  if (jobs[i].keyHi > bHi) bHi = jobs[i].keyHi; }
+		if (open.empty ()) { bLo = 0;  bHi = ~0ull; }
+		GDSP_CUDA (cudaMemsetAsync (d_scount, 0, 4, c->stream));
+		const uint32_t m = (uint32_t) std::min<uint64_t> (PCT_SAMPLES, std::max<uint64_t> (64, buffer_cells / 8));
+		k_pct_sample<<<(m + 255) / 256, 256, 0, c->stream>>> (sp, nslots, sig, mn, mx, bLo, bHi, m,
+		        0x243F6A8885A308D3ull + 0x9E37ull * iter, bufA, d_scount);
+		GDSP_KERNEL_CHECK ();
+		unsigned int scount = 0;
+		GDSP_CUDA (cudaMemcpyAsync (&scount, d_scount, 4, cudaMemcpyDeviceToHost, c->stream));
+		GDSP_CUDA (cudaStreamSynchronize (c->stream));
+		hs.resize (scount);
+		if (scount > 0)
+			{
+			SortPlan lp;
+			GDSP_TRY (make_lin_plan (c, sc, scount, &lp));
+			OutMap lin;  lin.nseg = 0;  lin.prefix = NULL;  lin.segs = NULL;
+			double* res = NULL;  int passes = 0;
+			GDSP_TRY (radix_sort (c, lp, lp, bufA, bufA, bufB, lin, sc, &res, &passes));
+			GDSP_CUDA (cudaMemcpyAsync (hs.data (), res, sizeof (double) * scount, cudaMemcpyDeviceToHost, c->stream));
+			GDSP_CUDA (cudaStreamSynchronize (c->stream));
+			}
+
+		// ---- (2) window bounds for every open job: the sample quantiles around the fraction of the
+		// job's bracket that lies below the wanted rank (+-6 sigma of the binomial sampling error)
+		PctBounds B;  memset (&B, 0, sizeof (B));
+		std::vector<unsigned long long> bounds;
+		std::vector<std::pair<unsigned long long, unsigned long long> > win (np);
+		for (int i : open)
+			{
+			unsigned long long lo = jobs[i].keyLo, hi = jobs[i].keyHi;
+			// the part of the sorted sample that lies inside this job's bracket
+			size_t a = std::lower_bound (hs.begin (), hs.end (), lo,
+			               [] (double x, unsigned long long k) { return host_key (x) < k; }) - hs.begin ();
+			size_t b = std::upper_bound (hs.begin (), hs.end (), hi,
+			               [] (unsigned long long k, double x) { return k < host_key (x); }) - hs.begin ();
+			const size_t ns = b - a;
+			double f = -1;
+			if (!jobs[i].haveCounts) f = (jobs[i].pMilli >= 100000) ? 1.0 : jobs[i].pMilli / 100000.0;
+			else if (jobs[i].inside > 0)
+				{
+				const uint32_t nv = (uint32_t) numSamples;
+				unsigned long long rank = (jobs[i].pMilli >= 100000) ? numSamples - 1
+				                        : (unsigned long long) (uint32_t) (((uint64_t) nv) * jobs[i].pMilli / (100.0 * 1000));
+				f = ((double) (rank - jobs[i].below) + 0.5) / (double) jobs[i].inside;
+				}
+			if (ns >= 64 && f >= 0)
+				{
+				if (f > 1) f = 1;
+				double sdv = sqrt (f * (1 - f) / ns);
+				double dl = 6 * sdv + 2.0 / ns;
+				long long il = (long long) floor ((f - dl) * ns) - 1, ih = (long long) ceil ((f + dl) * ns) + 1;
+				if (il >= 0 && il < (long long) ns) { unsigned long long k = host_key (hs[a + il]);  if (k > lo) lo = k; }
+				if (ih >= 0 && ih < (long long) ns) { unsigned long long k = host_key (hs[a + ih]);  if (k < hi) hi = k; }
+				}
+			win[i] = std::make_pair (lo, hi);
+			bounds.push_back (lo);  bounds.push_back (hi);
+			}
+		std::sort (bounds.begin (), bounds.end ());
+		bounds.erase (std::unique (bounds.begin (), bounds.end ()), bounds.end ());
+		B.nb = (int) bounds.size ();
+		for (int k = 0; k < B.nb; k++) B.key[k] = bounds[k];
+		// open region r lies between bound r-1 and bound r; compact it if some job's window spans it
+		for (int i : open)
+			for (int r = 1; r < B.nb; r++)
+				if (bounds[r - 1] >= win[i].first && bounds[r] <= win[i].second) B.compact[r] = 1;
+
+		// ---- (3) the counting / compaction pass
+		const int nreg = 2 * B.nb + 1;
+		GDSP_CUDA (cudaMemsetAsync (d_counts, 0, sizeof (unsigned long long) * nreg, c->stream));
+		GDSP_CUDA (cudaMemsetAsync (d_ncand, 0, 8, c->stream));
+		int grid = c->sm_count * 8;
+		if ((uint64_t) grid > tmPct.ntiles) grid = (int) tmPct.ntiles;
+		if (B.nb <= 2)
+			k_pct_pass<true><<<grid, 256, 0, c->stream>>> (L->d, tmPct.d_base, L->nseg, tmPct.ntiles, sig, stride, mn, mx,
+			        B, d_counts, bufA, candCapTotal, d_ncand);
+		else
+			k_pct_pass<false><<<grid, 256, 0, c->stream>>> (L->d, tmPct.d_base, L->nseg, tmPct.ntiles, sig, stride, mn, mx,
+			        B, d_counts, bufA, candCapTotal, d_ncand);
+		GDSP_KERNEL_CHECK ();
+		std::vector<unsigned long long> counts (nreg);
+		unsigned long long ncand = 0;
+		GDSP_CUDA (cudaMemcpyAsync (counts.data (), d_counts, sizeof (unsigned long long) * nreg, cudaMemcpyDeviceToHost, c->stream));
+		GDSP_CUDA (cudaMemcpyAsync (&ncand, d_ncand, 8, cudaMemcpyDeviceToHost, c->stream));
+		GDSP_CUDA (cudaStreamSynchronize (c->stream));
+		unsigned long long total = 0;
+		for (int r = 0; r < nreg; r++) total += counts[r];
+		numSamples = total;  haveCount = true;
+		if (total == 0 || np == 0) break;
+
+		// sort the candidates (if they fit)
+		const bool candOk = (ncand <= candCapTotal);
+		double* sortedCand = NULL;
+		if (candOk && ncand > 0)
+			{
+			SortPlan lp;
+			GDSP_TRY (make_lin_plan (c, sc, ncand, &lp));
+			OutMap lin;  lin.nseg = 0;  lin.prefix = NULL;  lin.segs = NULL;
+			int passes = 0;
+			GDSP_TRY (radix_sort (c, lp, lp, bufA, bufA, bufB, lin, sc, &sortedCand, &passes));
+			}
+		// candidate offset of each compacted open region
+		std::vector<unsigned long long> candBefore (B.nb + 2, 0);
+		{
+		unsigned long long acc = 0;
+		for (int r = 0; r <= B.nb; r++) { candBefore[r] = acc;  if (B.compact[r]) acc += counts[2 * r]; }
+		}
+
+		// ---- (4) locate every open job's rank
+		for (int i : open)
+			{
+			// rank exactly as percentile.c:588/:686 computes it (numValues is a u32 there)
+			const uint32_t nv = (uint32_t) total;
+			unsigned long long rank;
+			if (jobs[i].pMilli >= 100000) rank = total - 1;
+			else
+				{
+				rank = (uint32_t) (((uint64_t) nv) * jobs[i].pMilli / (100.0 * 1000));
+				if (rank >= total) rank = total - 1;
+				}
+			unsigned long long cum = 0;
+			int reg = 0;
+			for (reg = 0; reg < nreg; reg++) { if (rank < cum + counts[reg]) break;  cum += counts[reg]; }
+			if (reg & 1) { jobs[i].value = host_unkey (bounds[reg >> 1]);  jobs[i].done = true;  continue; }
+			const int r = reg >> 1;
+			if (B.compact[r] && candOk)
+				{
+				double v;
+				GDSP_CUDA (cudaMemcpyAsync (&v, sortedCand + candBefore[r] + (rank - cum), 8, cudaMemcpyDeviceToHost, c->stream));
+				GDSP_CUDA (cudaStreamSynchronize (c->stream));
+				jobs[i].value = v;  jobs[i].done = true;
+				continue;
+				}
+			// missed: the wanted key lies strictly inside open region r; if the region is small
+			// enough, the next pass compacts all of it
+			jobs[i].keyLo = (r > 0) ? bounds[r - 1] + 1 : 0ull;
+			jobs[i].keyHi = (r < B.nb) ? bounds[r] - 1 : ~0ull;
+			jobs[i].below = cum;  jobs[i].inside = counts[reg];  jobs[i].haveCounts = true;
+			}
+		}
+	for (int i = 0; i < np; i++)
+		{
+		GDSP_REQUIRE (jobs[i].done || numSamples == 0, "gdsp_percentiles: selection did not converge for percentile %u", jobs[i].pMilli);
+		h_values[i] = jobs[i].value;
+		}
+	*h_num_samples = numSamples;
+	return GDSP_OK;
+	}

@@ -426,10 +426,21 @@ extern "C" int gdsp_smooth (gdsp_ctx* c, const gdsp_layout* L_, const double* in
 	GDSP_REQUIRE (c && L && in && out && h_taps, "gdsp_smooth: NULL argument");
 	GDSP_REQUIRE (in != out, "gdsp_smooth: in and out must be different buffers");
 	GDSP_REQUIRE (W >= 1, "gdsp_smooth: window must be positive");
-	void* dt;
-	GDSP_TRY (gdsp_ws (c, 2, sizeof (double) * W, &dt));
-	GDSP_CUDA (cudaMemcpyAsync (dt, h_taps, sizeof (double) * W, cudaMemcpyHostToDevice, c->stream));
-	GDSP_CUDA (cudaStreamSynchronize (c->stream));          // h_taps belongs to the caller
+	// the taps are uploaded once and reused while the caller keeps passing the same window
+	if (c->taps_n != W || c->taps_host == NULL || memcmp (c->taps_host, h_taps, sizeof (double) * W) != 0)
+		{
+		GDSP_CUDA (cudaStreamSynchronize (c->stream));
+		if (c->taps_dev)  { cudaFree (c->taps_dev);  c->taps_dev = NULL; }
+		if (c->taps_host) { free (c->taps_host);     c->taps_host = NULL; }
+		c->taps_n = 0;
+		c->taps_host = (double*) malloc (sizeof (double) * W);
+		GDSP_REQUIRE (c->taps_host != NULL, "gdsp_smooth: out of host memory");
+		memcpy (c->taps_host, h_taps, sizeof (double) * W);
+		GDSP_CUDA (cudaMalloc (&c->taps_dev, sizeof (double) * W));
+		GDSP_CUDA (cudaMemcpyAsync (c->taps_dev, c->taps_host, sizeof (double) * W, cudaMemcpyHostToDevice, c->stream));
+		c->taps_n = W;
+		}
+	void* dt = c->taps_dev;
 	TileMap tm;
 	GDSP_TRY (gdsp_layout_tilemap (L, SM_TILE, &tm));
 	k_smooth<<<(unsigned) tm.ntiles, SM_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, in, out, W, (const double*) dt);

@@ -357,21 +357,15 @@ class Genome:
             self.variables.update(out)
             return out
         ps = list(range(plo, phi + 1, pstep))
-        ranks = (C.c_uint64 * len(ps))()
+        pm = (C.c_uint32 * len(ps))(*ps)
         vals = (C.c_double * len(ps))()
         n = C.c_uint64()
-        # first call with rank 0 placeholders just to learn the sample count is avoided:
-        # the library returns the count, ranks are recomputed by a second cheap call if needed
-        check(self.lib.gdsp_select_ranks(self.ctx, self.layout, self._p(self.sig), int(window), float(mn), float(mx),
-                                         ranks, 0, vals, C.byref(n)))
-        nv = int(n.value)
-        if nv == 0:
+        check(self.lib.gdsp_percentiles(self.ctx, self.layout, self._p(self.sig), self._p(self.tmp), self.buffer_cells,
+                                        int(window), float(mn), float(mx), pm, len(ps), vals, C.byref(n)))
+        self.launches += 4
+        self.num_samples = int(n.value)
+        if self.num_samples == 0:
             return out
-        for i, p in enumerate(ps):
-            r = percentile_rank(nv, p)
-            ranks[i] = nv - 1 if (p == 100000 or r >= nv) else r     # percentile.c:690-707
-        check(self.lib.gdsp_select_ranks(self.ctx, self.layout, self._p(self.sig), int(window), float(mn), float(mx),
-                                         ranks, len(ps), vals, C.byref(n)))
         for i, p in enumerate(ps):
             out[percentile_name(p)] = vals[i]
         self.variables.update(out)
@@ -380,7 +374,14 @@ class Genome:
         return out
 
     def sort_genome(self):
-        check(self.lib.gdsp_sort_genome(self.ctx, self.layout, self._p(self.sig), self._p(self.tmp), self.buffer_cells))
+        """the reference's post-percentile state for the all-qualifying case: genome globally sorted
+        in chromsSorted order (percentile.c:611-651)"""
+        flag = C.c_int()
+        check(self.lib.gdsp_sort_genome(self.ctx, self.layout, self._p(self.sig), self._p(self.tmp), self.buffer_cells,
+                                        C.byref(flag)))
+        if flag.value:
+            self._swap()
+        self.launches += 8
 
     # ------------------------------------------------------------------ clump.c
     def clump(self, average=0.0, length=100, relative_length=0.0, above=True, one=1.0, zero=0.0):

@@ -61,7 +61,10 @@ typedef struct gdsp_seg
 
 /* ---- context, memory, layout ------------------------------------------- */
 
-/* `stream` is a cudaStream_t (or NULL for a private non-blocking stream). */
+/* `stream` is a cudaStream_t: NULL is the legacy default stream (what
+ * torch.cuda.current_stream() reports as 0); GDSP_STREAM_PRIVATE asks the
+ * library to create and own a non-blocking stream. */
+#define GDSP_STREAM_PRIVATE ((void*) (intptr_t) -1)
 int  gdsp_ctx_create   (int device, void* stream, gdsp_ctx** out);
 void gdsp_ctx_destroy  (gdsp_ctx* ctx);
 int  gdsp_ctx_set_stream (gdsp_ctx* ctx, void* stream);
@@ -233,20 +236,23 @@ int  gdsp_minmax (gdsp_ctx* ctx, const gdsp_layout* lay, const double* sig,
 /* ---- percentile -------------------------------------------------------------
  * op_percentile_apply, percentile.c:392-751.  Order statistics of the samples
  * v[ix], ix = 0,stride,2*stride,.. of every chromosome with
- * min_allowed <= v <= max_allowed.  ranks[] are 0-based indices into the
- * ascending order of the samples (computed on the host exactly as
- * percentile.c:588,686 do); values[] receives the order statistics.
- * Non-destructive. */
-int  gdsp_select_ranks (gdsp_ctx* ctx, const gdsp_layout* lay, const double* sig,
-                        uint32_t stride, double min_allowed, double max_allowed,
-                        const uint64_t* h_ranks, int nranks, double* h_values,
-                        uint64_t* h_num_samples);
+ * min_allowed <= v <= max_allowed.  p_milli[] are percentiles in thousandths
+ * of a percent; the rank of each is (u32)((u64)n*p/100000.0) as in
+ * percentile.c:588,686 (p = 100000 -> the largest sample, :690-707).
+ * Non-destructive and exact (selection, no sorting of the genome).
+ * `tmp` is a scratch buffer of buffer_cells doubles (>= 1024). */
+int  gdsp_percentiles (gdsp_ctx* ctx, const gdsp_layout* lay, const double* sig,
+                       double* tmp, uint64_t buffer_cells, uint32_t stride,
+                       double min_allowed, double max_allowed,
+                       const uint32_t* h_p_milli, int np, double* h_values,
+                       uint64_t* h_num_samples);
 /* The reference's percentile is destructive; with every cell qualifying and
  * the last requested rank in the last two chromosomes the genome ends up
- * globally sorted in layout order (percentile.c:611-651; SURVEY §7 #3).
- * `tmp` is a second buffer of buffer_cells doubles. */
+ * globally sorted in layout order (percentile.c:611-651; SURVEY 7 #3).
+ * `tmp` is a second buffer of buffer_cells doubles; the sorted genome lands
+ * in sig (*h_result_in_tmp = 0) or in tmp (= 1): the caller swaps its buffers. */
 int  gdsp_sort_genome (gdsp_ctx* ctx, const gdsp_layout* lay, double* sig,
-                       double* tmp, uint64_t buffer_cells);
+                       double* tmp, uint64_t buffer_cells, int* h_result_in_tmp);
 
 /* ---- clump ---------------------------------------------------------------- */
 /* clump_search, clump.c:494-736 (above=1 clump, 0 anticlump); in place.

@@ -54,7 +54,11 @@ def load(genome, rng, kind):
     return inputs
 
 
-def compare(genome, inputs, fn, exact=True, rtol=0.0, what=""):
+def compare(genome, inputs, fn, exact=True, rtol=0.0, what="", scale_fn=None, exact_fn=None):
+    """exact: bit-for-bit.  Otherwise |got-want| <= rtol * scale, where scale is the magnitude of
+    the summands feeding each output (the same operator applied to |v|): the reference's own
+    running sums drift by ~eps*sqrt(steps)*|summands| from the true value, so an error relative to a
+    cancelling result would measure the reference's drift, not ours."""
     for name, n in CHROMS:
         want = fn(inputs[name].copy())
         got = genome.get_chrom(name)
@@ -63,9 +67,29 @@ def compare(genome, inputs, fn, exact=True, rtol=0.0, what=""):
             assert bad.size == 0, "%s %s: %d mismatches, first at %d: got %r want %r" % (
                 what, name, bad.size, bad[0], got[bad[0]], want[bad[0]])
         else:
-            scale = np.maximum(np.abs(want), 1.0)
-            err = np.max(np.abs(got - want) / scale) if n else 0.0
+            scale = np.maximum(np.abs(want), 1e-300)
+            if scale_fn is not None:
+                scale = np.maximum(scale, np.abs(scale_fn(np.abs(inputs[name]))))
+            drift = 0.0
+            if exact_fn is not None:
+                # the reference's sequential running sums drift from the exact (extended precision) sum by
+                # ~eps*sqrt(steps)*|summands|; we must be within rtol of the exact value, and within
+                # rtol + that drift of the reference
+                truth = exact_fn(inputs[name])
+                err_true = np.max(np.abs(got - truth) / scale) if n else 0.0
+                assert err_true <= rtol, "%s %s: rel err vs exact sum %g > %g" % (what, name, err_true, rtol)
+                drift = np.abs(want - truth)
+            err = np.max(np.maximum(np.abs(got - want) - drift, 0.0) / scale) if n else 0.0
             assert err <= rtol, "%s %s: rel err %g > %g" % (what, name, err, rtol)
+
+
+def _exact_sliding_sum(v, W, d):
+    """sliding sum in extended precision (np.longdouble prefix sums), rounded once"""
+    n = v.size; h = (W - 1) // 2
+    c = np.concatenate([[np.longdouble(0)], np.cumsum(v.astype(np.longdouble))])
+    i = np.arange(n)
+    hi = np.minimum(n, i + h + 1); lo = np.maximum(0, i + h - W + 1)
+    return ((c[hi] - c[lo]) / np.longdouble(d)).astype(np.float64)
 
 
 def test_fill_and_roundtrip(genome):
@@ -108,7 +132,8 @@ def test_sliding_sum(genome, orc, kind, W):
     # integer / dyadic signals: every partial sum is exact, so any association order gives the
     # reference's bits; general reals: 1e-12 relative (BASELINE.json north_star)
     compare(genome, inputs, lambda v: orc.sliding_sum(v, W, d), exact=(kind != "real"), rtol=1e-12,
-            what="slidingsum W=%d" % W)
+            what="slidingsum W=%d" % W, scale_fn=lambda a: orc.sliding_sum(a, W, d),
+            exact_fn=lambda v: _exact_sliding_sum(v, W, d))
 
 
 @pytest.mark.parametrize("kind", KINDS)
@@ -118,14 +143,16 @@ def test_block_sum(genome, orc, kind, W):
     genome.sum(W, denom=1.0, denom_actual=(W == 101), zero=-1.0 if W == 3 else 0.0)
     exact = (kind != "real") or W <= 4096       # W<=4096 folds each block in the reference's order
     compare(genome, inputs, lambda v: orc.block_sum(v, W, 1.0, W == 101, -1.0 if W == 3 else 0.0),
-            exact=exact, rtol=1e-12, what="sum W=%d" % W)
+            exact=exact, rtol=1e-12, what="sum W=%d" % W,
+            scale_fn=lambda a: orc.block_sum(a, W, 1.0, W == 101, 0.0))
 
 
 @pytest.mark.parametrize("kind", ["int", "real"])
 def test_block_sum_whole_chromosome(genome, orc, kind):
     inputs = load(genome, np.random.default_rng(3), kind)
     genome.sum(window_is_chromosome=True)
-    compare(genome, inputs, lambda v: orc.block_sum(v, v.size), exact=(kind == "int"), rtol=1e-12, what="sum chrom")
+    compare(genome, inputs, lambda v: orc.block_sum(v, v.size), exact=(kind == "int"), rtol=1e-12, what="sum chrom",
+            scale_fn=lambda a: orc.block_sum(a, a.size))
 
 
 @pytest.mark.parametrize("kind", KINDS)
@@ -141,7 +168,8 @@ def test_smooth_bit_exact(genome, orc, kind, W):
 def test_cumulative_sum(genome, orc, kind):
     inputs = load(genome, np.random.default_rng(5), kind)
     genome.cumulativesum()
-    compare(genome, inputs, orc.cumulative, exact=(kind != "real"), rtol=1e-12, what="cumulativesum")
+    compare(genome, inputs, orc.cumulative, exact=(kind != "real"), rtol=1e-12, what="cumulativesum",
+            scale_fn=orc.cumulative)
 
 
 @pytest.mark.parametrize("kind", KINDS)
@@ -317,3 +345,88 @@ def test_runs(genome, orc, collapse, show, kind):
         gs, ge, gv = got[name]
         assert np.array_equal(gs, rs) and np.array_equal(ge, re), (name, collapse, show)
         assert np.array_equal(bits(gv), bits(rv)), (name, collapse, show)
+
+
+@pytest.mark.parametrize("kind", ["int", "sparse", "dyadic"])
+@pytest.mark.parametrize("L", [1, 10, 100, 1000, 5000])
+def test_clump(genome, orc, kind, L):
+    T = {"int": 5.5, "sparse": 0.5, "dyadic": 0.25}[kind]
+    inputs = load(genome, np.random.default_rng(L), kind)
+    genome.clump(T, L)
+    compare(genome, inputs, lambda v: orc.clump(v, T, L, True), what="clump L=%d" % L)
+    inputs = load(genome, np.random.default_rng(L + 1), kind)
+    genome.anticlump(T, L, one=3.0, zero=-1.0)
+    compare(genome, inputs, lambda v: orc.clump(v, T, L, False, 3.0, -1.0), what="anticlump L=%d" % L)
+
+
+def test_clump_all_below_and_relative_length(genome, orc):
+    inputs = load(genome, np.random.default_rng(0), "int")
+    genome.clump(1000.0, 10)
+    compare(genome, inputs, lambda v: orc.clump(v, 1000.0, 10, True), what="clump all below")
+    inputs = load(genome, np.random.default_rng(1), "int")
+    genome.clump(5.5, 0, relative_length=0.001)
+    compare(genome, inputs, lambda v: orc.clump(v, 5.5, max(0, int(0.001 * v.size)), True), what="clump CL*0.001")
+
+
+def _sorted_post_state(genome, inputs):
+    names = [genome.chroms[i][0] for i in genome.order]
+    allv = np.sort(np.concatenate([inputs[n] for n in names]))
+    out, pos = {}, 0
+    for n in names:
+        out[n] = allv[pos:pos + inputs[n].size]; pos += inputs[n].size
+    return out
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_percentile_values_and_sorted_post_state(genome, orc, kind):
+    inputs = load(genome, np.random.default_rng(17), kind)
+    names = [genome.chroms[i][0] for i in genome.order]
+    srt = orc.sort(np.concatenate([orc.percentile_collect(inputs[n]) for n in names]).copy())
+    got = genome.percentile(1.0, 99.0, step=7.0, destructive=False)
+    for p in range(1000, 99001, 7000):
+        want = srt[orc.percentile_rank(srt.size, p)]
+        name = "percentile%d" % (p // 1000)
+        assert np.float64(got[name]).view(np.uint64) == np.float64(want).view(np.uint64), (kind, p)
+    compare(genome, inputs, lambda v: v, what="percentile must not modify the signal")
+    for p_str, p in (("99", 99000), ("99.5", 99500), ("12.345", 12345), ("100", 100000), ("0", 0)):
+        got = genome.percentile(float(p_str), destructive=False)
+        want = srt[-1] if p == 100000 else srt[orc.percentile_rank(srt.size, p)]
+        assert got["percentile" + p_str] == want, (kind, p_str)
+    genome.percentile(99.0, destructive=True)
+    post = _sorted_post_state(genome, inputs)
+    for name, n in CHROMS:
+        assert np.array_equal(genome.get_chrom(name), post[name]), (kind, name)
+
+
+@pytest.mark.parametrize("W", [2, 5, 100])
+def test_percentile_window_and_range(genome, orc, W):
+    inputs = load(genome, np.random.default_rng(W), "int")
+    names = [genome.chroms[i][0] for i in genome.order]
+    srt = orc.sort(np.concatenate([orc.percentile_collect(inputs[n], W, 2.0, 9.0) for n in names]).copy())
+    got = genome.percentile(10.0, 90.0, step=20.0, window=W, mn=2.0, mx=9.0, destructive=False)
+    assert genome.num_samples == srt.size
+    for p in (10, 30, 50, 70, 90):
+        assert got["percentile%d" % p] == srt[orc.percentile_rank(srt.size, p * 1000)], (W, p)
+
+
+def test_percentile_many_and_heavy_ties(genome, orc):
+    rng = np.random.default_rng(3)
+    inputs = {}
+    for name, n in CHROMS:
+        v = np.where(rng.random(n) < 0.7, 4.0, rng.integers(0, 3, n).astype(np.float64))   # 70 % ties
+        inputs[name] = v; genome.set_chrom(name, v)
+    names = [genome.chroms[i][0] for i in genome.order]
+    srt = np.sort(np.concatenate([inputs[n] for n in names]))
+    got = genome.percentile(0.5, 99.5, step=0.5, destructive=False)           # 199 percentiles
+    for p in range(500, 99501, 500):
+        want = srt[orc.percentile_rank(srt.size, p)]
+        key = "percentile%d" % (p // 1000) if p % 1000 == 0 else "percentile%.1f" % (p / 1000.0)
+        assert got[key] == want, p
+
+
+def test_sort_genome_real_values(genome):
+    inputs = load(genome, np.random.default_rng(23), "real")
+    genome.sort_genome()
+    post = _sorted_post_state(genome, inputs)
+    for name, n in CHROMS:
+        assert np.array_equal(genome.get_chrom(name), post[name]), name
