@@ -139,9 +139,11 @@ k_scan_tiles (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base
 		tileAgg += t;
 		}
 
-	if (threadIdx.x == 0)
-		s_excl = scan_lookback<T> (st, tile, tis == 0, tileAgg, (T) 0,
-		                           [] (T a, T b) { return a + b; });
+	if (threadIdx.x < 32)
+		{
+		const T e = scan_lookback<T> (st, tile, tis == 0, tileAgg, (T) 0, [] (T a, T b) { return a + b; });
+		if (threadIdx.x == 0) s_excl = e;
+		}
 	__syncthreads ();
 	const T add = s_excl + warpExcl;
 

@@ -136,10 +136,14 @@ k_clump_a (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, i
 
 	double warpExcl, tileAgg;
 	tile_scan<double> (x, 0.0, [] (double a, double b) { return a + b; }, s_warp, warpExcl, tileAgg);
-	if (threadIdx.x == 0)
+	if (threadIdx.x < 32)
 		{
-		s_carry[0] = scan_lookback<double> (stSum, tile, tis == 0, tileAgg, 0.0, [] (double a, double b) { return a + b; });
-		if (s_anyNonNeg) atomicAnd (&wk.segAllNeg[seg], 0);
+		const double e = scan_lookback<double> (stSum, tile, tis == 0, tileAgg, 0.0, [] (double a, double b) { return a + b; });
+		if (threadIdx.x == 0)
+			{
+			s_carry[0] = e;
+			if (s_anyNonNeg) atomicAnd (&wk.segAllNeg[seg], 0);
+			}
 		}
 	__syncthreads ();
 	const double addP = s_carry[0] + warpExcl;
@@ -157,9 +161,12 @@ k_clump_a (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, i
 	double wExM, tAggM;
 	tile_scan<double> (m, __longlong_as_double (0x7ff0000000000000ll), [] (double a, double b) { return fmin (a, b); },
 	                   s_warp, wExM, tAggM);
-	if (threadIdx.x == 0)
-		s_carry[1] = scan_lookback<double> (stMin, tile, tis == 0, tAggM, __longlong_as_double (0x7ff0000000000000ll),
-		                                    [] (double a, double b) { return fmin (a, b); });
+	if (threadIdx.x < 32)
+		{
+		const double e = scan_lookback<double> (stMin, tile, tis == 0, tAggM, __longlong_as_double (0x7ff0000000000000ll),
+		                                        [] (double a, double b) { return fmin (a, b); });
+		if (threadIdx.x == 0) s_carry[1] = e;
+		}
 	__syncthreads ();
 	const double carryM = fmin (fmin (s_carry[1], wExM), 0.0);        // P[-1] = 0 takes part in every prefix minimum
 
@@ -249,8 +256,11 @@ k_clump_b (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, i
 
 	double wEx, tAgg;
 	tile_scan<double> (q, NEG, [] (double a, double b) { return fmax (a, b); }, s_warp, wEx, tAgg);
-	if (threadIdx.x == 0)
-		s_carryD = scan_lookback<double> (stMax, ticket, firstOfScan, tAgg, NEG, [] (double a, double b) { return fmax (a, b); });
+	if (threadIdx.x < 32)
+		{
+		const double e = scan_lookback<double> (stMax, ticket, firstOfScan, tAgg, NEG, [] (double a, double b) { return fmax (a, b); });
+		if (threadIdx.x == 0) s_carryD = e;
+		}
 	__syncthreads ();
 	const double carryQ = fmax (s_carryD, wEx);
 
@@ -269,8 +279,11 @@ k_clump_b (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, i
 			}
 	int wExI, tAggI;
 	tile_scan<int> (st, 0, [] (int a, int b) { return seg_or (a, b); }, s_warpI, wExI, tAggI);
-	if (threadIdx.x == 0)
-		s_carryI = scan_lookback<int> (stOr, ticket, firstOfScan, tAggI, 0, [] (int a, int b) { return seg_or (a, b); });
+	if (threadIdx.x < 32)
+		{
+		const int e = scan_lookback<int> (stOr, ticket, firstOfScan, tAggI, 0, [] (int a, int b) { return seg_or (a, b); });
+		if (threadIdx.x == 0) s_carryI = e;
+		}
 	__syncthreads ();
 	const int carryI = seg_or (s_carryI, wExI);
 
@@ -323,8 +336,11 @@ k_clump_c (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, i
 		}
 	int wExI, tAggI;
 	tile_scan<int> (st, 0, [] (int a, int b) { return seg_or (a, b); }, s_warpI, wExI, tAggI);
-	if (threadIdx.x == 0)
-		s_carryI = scan_lookback<int> (stOr, tile, tis == 0, tAggI, 0, [] (int a, int b) { return seg_or (a, b); });
+	if (threadIdx.x < 32)
+		{
+		const int e = scan_lookback<int> (stOr, tile, tis == 0, tAggI, 0, [] (int a, int b) { return seg_or (a, b); });
+		if (threadIdx.x == 0) s_carryI = e;
+		}
 	__syncthreads ();
 	const int carryI = seg_or (s_carryI, wExI);
 

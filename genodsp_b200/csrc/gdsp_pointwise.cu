@@ -92,6 +92,7 @@ __device__ __forceinline__ double pw_apply (const PwProgram& P, double v, uint64
 					case GDSP_PW_IVL_DIV: v = inside ? __ddiv_rn (v, op.val[k]) : ((v >= 0) ? op.a : -op.a);  break;
 					case GDSP_PW_IVL_SET: if (inside) v = op.a;  break;
 					case GDSP_PW_IVL_SET_OUTSIDE: if (!inside) v = op.a;  break;
+					case GDSP_PW_IVL_ASSIGN: if (inside) v = op.val[k];  break;
 					}
 				}
 			}
@@ -271,7 +272,7 @@ extern "C" int gdsp_pointwise (gdsp_ctx* c, const gdsp_layout* L_, const double*
 	P.nops = nops;
 	for (int i = 0; i < nops; i++)
 		{
-		GDSP_REQUIRE (ops[i].code >= GDSP_PW_BINARIZE_GT && ops[i].code <= GDSP_PW_IVL_SET_OUTSIDE,
+		GDSP_REQUIRE (ops[i].code >= GDSP_PW_BINARIZE_GT && ops[i].code <= GDSP_PW_IVL_ASSIGN,
 		              "gdsp_pointwise: operator %d has unknown code %d", i, ops[i].code);
 		P.ops[i].code = ops[i].code;  P.ops[i].flags = ops[i].flags;
 		P.ops[i].a = ops[i].a;  P.ops[i].b = ops[i].b;  P.ops[i].c = ops[i].c;

@@ -95,13 +95,16 @@ k_runs (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int 
 		if (w < warp) warpExcl += t;
 		tileTot += t;
 		}
-	if (threadIdx.x == 0)
+	if (threadIdx.x < 32)
 		{
 		unsigned long long ex = scan_lookback<unsigned long long> (st, tile, tile == 0, (unsigned long long) tileTot, 0ull,
 		                            [] (unsigned long long a, unsigned long long b) { return a + b; });
-		s_excl = ex;
-		if (tis == 0) segFirst[seg] = ex;
-		if (tile == ntiles - 1) segFirst[nseg] = ex + tileTot;
+		if (threadIdx.x == 0)
+			{
+			s_excl = ex;
+			if (tis == 0) segFirst[seg] = ex;
+			if (tile == ntiles - 1) segFirst[nseg] = ex + tileTot;
+			}
 		}
 	__syncthreads ();
 

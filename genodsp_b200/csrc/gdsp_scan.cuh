@@ -55,37 +55,90 @@ static inline size_t scan_status_clear_bytes (uint64_t ntiles)
 template <typename T> __device__ __forceinline__ T ld_vol (const T* p) { return *(const volatile T*) p; }
 template <typename T> __device__ __forceinline__ void st_vol (T* p, T v) { *(volatile T*) p = v; }
 
-// Called by ONE thread of the block.  `myAgg` is this tile's aggregate; returns
-// the aggregate of all earlier tiles of the same segment (identity for the
-// first tile) and publishes this tile's inclusive value.  op(a,b) combines an
-// earlier aggregate a with a later aggregate b.
+// Warp-cooperative look-back: called by ALL 32 lanes of ONE warp of the block
+// (every lane passes the same arguments).  `myAgg` is this tile's aggregate; the
+// function publishes it, inspects the 32 preceding tiles at a time (one per lane),
+// folds their aggregates in tile order until a tile with a published inclusive
+// value is met, publishes this tile's inclusive value and returns the aggregate of
+// all earlier tiles of the segment (identity for the first tile) in every lane.
+// op(a,b) combines an earlier aggregate a with a later aggregate b and may be
+// non-commutative.
+template <typename T> struct LbShfl;
+template <> struct LbShfl<double>
+	{ static __device__ __forceinline__ double down (double v, int d) { return shfl_down_f64 (v, d); }
+	  static __device__ __forceinline__ double idx  (double v, int s) { return shfl_idx_f64 (v, s); } };
+template <> struct LbShfl<int>
+	{ static __device__ __forceinline__ int down (int v, int d) { return __shfl_down_sync (0xffffffffu, v, d); }
+	  static __device__ __forceinline__ int idx  (int v, int s) { return __shfl_sync (0xffffffffu, v, s); } };
+template <> struct LbShfl<unsigned long long>
+	{ static __device__ __forceinline__ unsigned long long down (unsigned long long v, int d) { return __shfl_down_sync (0xffffffffu, v, d); }
+	  static __device__ __forceinline__ unsigned long long idx  (unsigned long long v, int s) { return __shfl_sync (0xffffffffu, v, s); } };
+
 template <typename T, typename Op>
 __device__ T scan_lookback (const ScanStatus<T>& st, uint64_t tile, bool firstOfSeg,
                             T myAgg, T identity, Op op)
 	{
+	const int lane = threadIdx.x & 31;
 	if (firstOfSeg)
 		{
-		st_vol (&st.incl[tile], myAgg);
-		__threadfence ();
-		st_vol (&st.flag[tile], SCAN_FLAG_INCL);
+		if (lane == 0)
+			{
+			st_vol (&st.incl[tile], myAgg);
+			__threadfence ();
+			st_vol (&st.flag[tile], SCAN_FLAG_INCL);
+			}
 		return identity;
 		}
-	st_vol (&st.agg[tile], myAgg);
-	__threadfence ();
-	st_vol (&st.flag[tile], SCAN_FLAG_AGG);
+	if (lane == 0)
+		{
+		st_vol (&st.agg[tile], myAgg);
+		__threadfence ();
+		st_vol (&st.flag[tile], SCAN_FLAG_AGG);
+		}
 
 	T excl = identity;
-	for (uint64_t j = tile - 1; ; j--)
+	bool haveExcl = false;
+	uint64_t j0 = tile;                       // the window covers tiles j0-1 .. j0-32
+	while (true)
 		{
-		uint32_t f;
-		do { f = ld_vol (&st.flag[j]); } while (f == SCAN_FLAG_EMPTY);
+		// lane l looks at tile j0-1-l; tiles before the segment's first tile are never reached
+		// because that first tile always publishes an inclusive value
+		const bool inRange = (j0 >= (uint64_t) lane + 1);
+		const uint64_t j = inRange ? j0 - 1 - lane : 0;
+		uint32_t f = SCAN_FLAG_EMPTY;
+		unsigned inclMask, emptyMask;
+		do  {
+			if (inRange) f = ld_vol (&st.flag[j]);
+			inclMask  = __ballot_sync (0xffffffffu, inRange && f == SCAN_FLAG_INCL);
+			emptyMask = __ballot_sync (0xffffffffu, inRange && f == SCAN_FLAG_EMPTY);
+			// spin only while a tile NEARER than the first inclusive one is still empty
+			const unsigned need = inclMask ? ((1u << (__ffs (inclMask) - 1)) - 1u) | (1u << (__ffs (inclMask) - 1)) : 0xffffffffu;
+			emptyMask &= need;
+			} while (emptyMask != 0);
 		__threadfence ();
-		if (f == SCAN_FLAG_INCL) { excl = op (ld_vol (&st.incl[j]), excl);  break; }
-		excl = op (ld_vol (&st.agg[j]), excl);
+		const int last = inclMask ? (__ffs (inclMask) - 1) : 31;          // farthest lane that takes part
+		T v = identity;
+		const bool part = inRange && lane <= last;
+		if (part) v = (f == SCAN_FLAG_INCL) ? ld_vol (&st.incl[j]) : ld_vol (&st.agg[j]);
+		// ordered fold: lane l+d holds an EARLIER tile than lane l
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+			{
+			T o = LbShfl<T>::down (v, d);
+			if (lane + d <= last) v = op (o, v);
+			}
+		const T w = LbShfl<T>::idx (v, 0);
+		excl = haveExcl ? op (w, excl) : w;
+		haveExcl = true;
+		if (inclMask) break;
+		j0 -= 32;
 		}
-	st_vol (&st.incl[tile], op (excl, myAgg));
-	__threadfence ();
-	st_vol (&st.flag[tile], SCAN_FLAG_INCL);
+	if (lane == 0)
+		{
+		st_vol (&st.incl[tile], op (excl, myAgg));
+		__threadfence ();
+		st_vol (&st.flag[tile], SCAN_FLAG_INCL);
+		}
 	return excl;
 	}
 

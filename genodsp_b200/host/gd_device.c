@@ -1,0 +1,246 @@
+/* gd_device.c -- device state of the host layer: one context, the packed genome
+ * buffer (replacing the per-chromosome callocs of main, genodsp.c:865-878, and
+ * the scratch-vector pool, genodsp.c:1904-2037) and interval-file loading. */
+#include <stdlib.h>
+#include <stdio.h>
+#include <string.h>
+#include "gd_device.h"
+
+gdev gd;
+
+void gd_check (int status, const char* who)
+	{
+	if (status == GDSP_OK) return;
+	fprintf (stderr, "[%s] GPU failure: %s\n", who, gdsp_last_error ());
+	exit (EXIT_FAILURE);
+	}
+
+void gd_device_open (void)
+	{
+	int n = 0;
+	while (chromsSorted[n] != NULL) n++;
+	memset (&gd, 0, sizeof (gd));
+	gd.nchrom = n;
+	gd_check (gdsp_ctx_create (0, GDSP_STREAM_PRIVATE, &gd.ctx), "genodsp");
+
+	u32* lens = (u32*) malloc (n * sizeof (u32));
+	gd.segs   = (gdsp_seg*) malloc (n * sizeof (gdsp_seg));
+	gd.single = (gdsp_layout**) malloc (n * sizeof (gdsp_layout*));
+	for (int i = 0; i < n; i++)
+		{
+		lens[i] = chromsSorted[i]->length;
+		if (lens[i] > gd.maxLength) gd.maxLength = lens[i];
+		}
+	u64 total;
+	gd_check (gdsp_layout_pack (lens, n, gd.segs, &total), "genodsp");
+	gd.cells = total;
+	gd_check (gdsp_layout_create (gd.ctx, gd.segs, n, &gd.genome), "genodsp");
+	for (int i = 0; i < n; i++)
+		gd_check (gdsp_layout_create (gd.ctx, &gd.segs[i], 1, &gd.single[i]), "genodsp");
+	void* p;
+	gd_check (gdsp_malloc (gd.ctx, total * sizeof (double), &p), "genodsp");  gd.sig = (double*) p;
+	gd_check (gdsp_malloc (gd.ctx, total * sizeof (double), &p), "genodsp");  gd.tmp = (double*) p;
+	gd_check (gdsp_fill (gd.ctx, gd.genome, gd.sig, 0.0), "genodsp");
+	for (int i = 0; i < n; i++) chromsSorted[i]->valVector = gd.sig + gd.segs[i].lo;
+	free (lens);
+	}
+
+void gd_device_close (void)
+	{
+	if (gd.ctx == NULL) return;
+	gdsp_sync (gd.ctx);
+	for (int i = 0; i < gd.nchrom; i++) gdsp_layout_destroy (gd.single[i]);
+	gdsp_layout_destroy (gd.genome);
+	gdsp_free (gd.ctx, gd.sig);  gdsp_free (gd.ctx, gd.tmp);
+	if (gd.work) gdsp_free (gd.ctx, gd.work);
+	gdsp_ctx_destroy (gd.ctx);
+	free (gd.segs);  free (gd.single);
+	memset (&gd, 0, sizeof (gd));
+	}
+
+void gd_swap (void)
+	{
+	double* t = gd.sig;  gd.sig = gd.tmp;  gd.tmp = t;
+	for (int i = 0; i < gd.nchrom; i++) chromsSorted[i]->valVector = gd.sig + gd.segs[i].lo;
+	}
+
+void* gd_work (size_t bytes)
+	{
+	if (bytes > gd.work_bytes)
+		{
+		if (gd.work) gd_check (gdsp_free (gd.ctx, gd.work), "genodsp");
+		gd.work = NULL;  gd.work_bytes = 0;
+		void* p;
+		gd_check (gdsp_malloc (gd.ctx, bytes, &p), "genodsp");
+		gd.work = p;  gd.work_bytes = bytes;
+		}
+	return gd.work;
+	}
+
+int gd_sorted_index (spec* c)
+	{
+	for (int i = 0; i < gd.nchrom; i++) if (chromsSorted[i] == c) return i;
+	return -1;
+	}
+
+const gdsp_layout* gd_layout_for (valtype* v, int* sortedIx)
+	{
+	if (v == NULL) { if (sortedIx) *sortedIx = -1;  return gd.genome; }
+	for (int i = 0; i < gd.nchrom; i++)
+		if (chromsSorted[i]->valVector == v) { if (sortedIx) *sortedIx = i;  return gd.single[i]; }
+	fprintf (stderr, "internal error: apply called with a vector that is not a chromosome\n");
+	exit (EXIT_FAILURE);
+	}
+
+void gd_commit_tmp (valtype* v, int sortedIx)
+	{
+	if (v == NULL) { gd_swap ();  return; }
+	const gdsp_seg* s = &gd.segs[sortedIx];
+	gd_check (gdsp_d2d (gd.ctx, gd.sig + s->lo, gd.tmp + s->lo, (s->hi - s->lo) * sizeof (double)), "genodsp");
+	}
+
+/* ---- interval lists -------------------------------------------------------- */
+
+void ivlist_init (ivlist* l) { memset (l, 0, sizeof (*l)); }
+
+void ivlist_free (ivlist* l)
+	{
+	free (l->seg);  free (l->start);  free (l->end);  free (l->val);
+	memset (l, 0, sizeof (*l));
+	}
+
+void ivlist_push (ivlist* l, u32 seg, u32 start, u32 end, double val)
+	{
+	if (l->n == l->cap)
+		{
+		u64 nc = l->cap ? 2 * l->cap : (1u << 16);
+		l->seg   = (u32*) realloc (l->seg,   nc * sizeof (u32));
+		l->start = (u32*) realloc (l->start, nc * sizeof (u32));
+		l->end   = (u32*) realloc (l->end,   nc * sizeof (u32));
+		l->val   = (double*) realloc (l->val, nc * sizeof (double));
+		if (!l->seg || !l->start || !l->end || !l->val)
+			{ fprintf (stderr, "out of memory holding %llu intervals\n", (unsigned long long) nc);  exit (EXIT_FAILURE); }
+		l->cap = nc;
+		}
+	l->seg[l->n] = seg;  l->start[l->n] = start;  l->end[l->n] = end;  l->val[l->n] = val;
+	l->n++;
+	}
+
+static ivlist* sortTarget;
+static int iv_cmp (const void* a, const void* b)
+	{
+	u64 i = *(const u64*) a, j = *(const u64*) b;
+	if (sortTarget->seg[i]   != sortTarget->seg[j])   return (sortTarget->seg[i]   < sortTarget->seg[j])   ? -1 : 1;
+	if (sortTarget->start[i] != sortTarget->start[j]) return (sortTarget->start[i] < sortTarget->start[j]) ? -1 : 1;
+	return (i < j) ? -1 : (i > j);            /* stable */
+	}
+
+void ivlist_sort (ivlist* l)
+	{
+	if (l->n < 2) return;
+	int sorted = true;
+	for (u64 k = 1; k < l->n && sorted; k++)
+		if (l->seg[k] < l->seg[k-1] || (l->seg[k] == l->seg[k-1] && l->start[k] < l->start[k-1])) sorted = false;
+	if (sorted) return;
+	u64* perm = (u64*) malloc (l->n * sizeof (u64));
+	for (u64 k = 0; k < l->n; k++) perm[k] = k;
+	sortTarget = l;
+	qsort (perm, l->n, sizeof (u64), iv_cmp);
+	u32* seg = (u32*) malloc (l->n * sizeof (u32));  u32* st = (u32*) malloc (l->n * sizeof (u32));
+	u32* en  = (u32*) malloc (l->n * sizeof (u32));  double* va = (double*) malloc (l->n * sizeof (double));
+	for (u64 k = 0; k < l->n; k++)
+		{ seg[k] = l->seg[perm[k]];  st[k] = l->start[perm[k]];  en[k] = l->end[perm[k]];  va[k] = l->val[perm[k]]; }
+	free (l->seg);  free (l->start);  free (l->end);  free (l->val);  free (perm);
+	l->seg = seg;  l->start = st;  l->end = en;  l->val = va;  l->cap = l->n;
+	}
+
+void ivlist_union (ivlist* l)
+	{
+	ivlist_sort (l);
+	u64 o = 0;
+	for (u64 k = 0; k < l->n; k++)
+		{
+		if (l->start[k] >= l->end[k]) continue;
+		if (o > 0 && l->seg[o-1] == l->seg[k] && l->start[k] <= l->end[o-1])
+			{ if (l->end[k] > l->end[o-1]) l->end[o-1] = l->end[k];  continue; }
+		l->seg[o] = l->seg[k];  l->start[o] = l->start[k];  l->end[o] = l->end[k];  l->val[o] = 1.0;
+		o++;
+		}
+	l->n = o;
+	}
+
+void ivlist_read_file (ivlist* l, const char* opName, const char* filename,
+                       int valCol, int originOne, int skipZeroVal, int requireSorted)
+	{
+	FILE* f = fopen (filename, "rt");
+	if (f == NULL)
+		{ fprintf (stderr, "[%s] can't open \"%s\" for reading\n", opName, filename);  exit (EXIT_FAILURE); }
+
+	char   line[1001], prevChrom[1001];
+	char*  chrom;
+	u32    start, end, prevEnd = 0;
+	double val;
+	spec*  cs = NULL;
+	int    segIx = -1;
+	u32    o = originOne ? 1 : 0;
+
+	for (int i = 0; i < gd.nchrom; i++) chromsSorted[i]->flag = false;
+	prevChrom[0] = 0;
+	while (read_interval (f, line, sizeof (line), valCol, &chrom, &start, &end, &val))
+		{
+		if (skipZeroVal && val == 0.0) continue;
+		if (strcmp (chrom, prevChrom) != 0)
+			{
+			cs = find_chromosome_spec (chrom);
+			segIx = (cs != NULL) ? gd_sorted_index (cs) : -1;
+			if (cs != NULL && requireSorted)
+				{
+				prevEnd = 0;
+				if (cs->flag)
+					{
+					fprintf (stderr, "[%s] in \"%s\", not all intervals on %s are together (%d..%d begins new group)\n",
+					         opName, filename, chrom, start, end);
+					exit (EXIT_FAILURE);
+					}
+				}
+			safe_strncpy (prevChrom, chrom, sizeof (prevChrom) - 1);
+			}
+		if (cs == NULL) continue;
+		if (!cs->flag)
+			{
+			if (trackOperations) fprintf (stderr, "%s(%s)\n", opName, chrom);
+			cs->flag = true;
+			}
+		start -= o;
+		u32 a = start, b = end;
+		if (cs->start == 0)
+			{
+			if (end > cs->length)
+				{
+				fprintf (stderr, "[%s] in \"%s\", %s %d %d is beyond the end of the chromosome (L=%d)\n",
+				         opName, filename, chrom, start, end, cs->length);
+				exit (EXIT_FAILURE);
+				}
+			}
+		else
+			{
+			if (end <= cs->start) continue;
+			b = end - cs->start;
+			a = (start <= cs->start) ? 0 : start - cs->start;
+			if (a >= cs->length) continue;
+			if (b >= cs->length) b = cs->length;
+			}
+		if (requireSorted)
+			{
+			if (a < prevEnd)
+				{
+				fprintf (stderr, "[%s] in \"%s\", intervals on %s are not sorted (%d..%d after %d)\n",
+				         opName, filename, chrom, start, end, cs->start + prevEnd);
+				exit (EXIT_FAILURE);
+				}
+			prevEnd = b;
+			}
+		ivlist_push (l, (u32) segIx, a, b, val);
+		}
+	fclose (f);
+	}

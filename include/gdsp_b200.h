@@ -191,8 +191,10 @@ typedef enum gdsp_pw_code
 	GDSP_PW_IVL_DIV,          /* inside v/=val, gap +-a     multiply.c:586-787*/
 	GDSP_PW_IVL_SET,          /* inside v=a                 mask.c:295-296,
 	                                                        logical.c:or      */
-	GDSP_PW_IVL_SET_OUTSIDE   /* gap v=a                    mask.c:483-668,
+	GDSP_PW_IVL_SET_OUTSIDE,  /* gap v=a                    mask.c:483-668,
 	                                                        logical.c:and     */
+	GDSP_PW_IVL_ASSIGN        /* inside v=val (input --overlap=min/max after the
+	                             host reduced the overlaps, genodsp.c:1307-1322) */
 	} gdsp_pw_code;
 
 #define GDSP_PW_ERASE_HAVE_MIN    1u

@@ -1,0 +1,171 @@
+"""Drop-in check of the host CLI: genodsp_b200/bin/genodsp (C host + CUDA library) must write
+byte-identical stdout (and the same variable / threshold messages on stderr) as the unmodified
+reference binary oracle/_ref/genodsp for the same command line and input."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from checkers import REF_BIN, ROOT, have_ref
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not have_ref(), reason="oracle/_ref/genodsp not built")]
+
+OURS = os.path.join(ROOT, "genodsp_b200", "bin", "genodsp")
+CHROMS = [("chrA", 300000), ("chrB", 150000), ("chrC", 70000), ("chrD", 1234)]
+
+
+@pytest.fixture(scope="module")
+def data(tmp_path_factory):
+    d = tmp_path_factory.mktemp("cli")
+    rng = np.random.default_rng(5)
+    with open(d / "g.chroms", "w") as f:
+        for n, l in CHROMS:
+            f.write("%s %d\n" % (n, l))
+    # coverage-like reads, mean depth ~5, a few unknown chromosomes, comments and a track line
+    with open(d / "reads.iv", "w") as f:
+        f.write("track name=reads\n# a comment\n\n")
+        for n, l in CHROMS:
+            m = l * 5 // 100
+            s = rng.integers(0, max(1, l - 150), m)
+            ln = rng.integers(50, 151, m)
+            for a, b in zip(s, ln):
+                f.write("%s\t%d\t%d\n" % (n, a, min(l, a + b)))
+        f.write("chrUn\t5\t10\n")
+    # valued intervals (dyadic values), column 4 and a 5th column
+    with open(d / "vals.iv", "w") as f:
+        for n, l in CHROMS:
+            m = l // 300
+            s = np.sort(rng.integers(0, l - 400, m))
+            for a in s:
+                f.write("%s %d %d %s %s\n" % (n, a, a + int(rng.integers(1, 400)), repr(float(rng.integers(-8, 9)) / 4),
+                                              repr(float(rng.integers(0, 5)))))
+    # sorted disjoint second track (~50 % covered), values k/1024; chrC absent
+    with open(d / "trackB.iv", "w") as f:
+        for n, l in CHROMS:
+            if n == "chrC":
+                continue
+            pos = int(rng.integers(0, 100))
+            while pos < l:
+                e = min(l, pos + int(rng.integers(1, 600)))
+                f.write("%s\t%d\t%d\t%s\n" % (n, pos, e, repr(float(rng.integers(1, 4096)) / 1024)))
+                pos = e + int(rng.integers(1, 600))
+    # unsorted, overlapping mask intervals
+    with open(d / "maskM.iv", "w") as f:
+        for _ in range(400):
+            n, l = CHROMS[int(rng.integers(0, 3))]
+            a = int(rng.integers(0, l - 2000))
+            f.write("%s\t%d\t%d\n" % (n, a, a + int(rng.integers(1, 2000))))
+    return d
+
+
+def run(binary, args, stdin_path, cwd):
+    with open(stdin_path, "rb") as fin:
+        p = subprocess.run([binary] + args, stdin=fin, capture_output=True, cwd=cwd, timeout=600)
+    return p.returncode, p.stdout, p.stderr
+
+
+def both(data, args, stdin="reads.iv"):
+    a = run(REF_BIN, args, data / stdin, data)
+    b = run(OURS, args, data / stdin, data)
+    return a, b
+
+
+def assert_same(data, args, stdin="reads.iv", stderr_too=True):
+    (rc_r, out_r, err_r), (rc_o, out_o, err_o) = both(data, args, stdin)
+    assert rc_r == 0, err_r.decode()[-500:]
+    assert rc_o == 0, err_o.decode()[-2000:]
+    if out_r != out_o:
+        lr, lo = out_r.split(b"\n"), out_o.split(b"\n")
+        for i, (x, y) in enumerate(zip(lr, lo)):
+            assert x == y, "stdout differs at line %d: ref %r ours %r (args %s)" % (i + 1, x, y, args)
+        assert len(lr) == len(lo), "stdout has %d lines, reference %d (args %s)" % (len(lo), len(lr), args)
+    if stderr_too:
+        assert err_r == err_o, "stderr differs:\nref:  %r\nours: %r" % (err_r[-400:], err_o[-400:])
+
+
+C = ["--chromosomes=g.chroms"]
+
+
+def test_cfg1_depth_sum_localmax(data):
+    assert_same(data, C + ["--novalue", "=", "sum", "--window=101", "=", "localmax", "--neighborhood=11"])
+
+
+def test_cfg2_depth_smooth(data):
+    assert_same(data, C + ["--novalue", "--precision=12", "=", "smooth", "--window=101"])
+
+
+def test_cfg3_percentile_pipeline(data):
+    assert_same(data, C + ["--novalue", "=", "sum", "--window=100", "--denom=100", "=", "percentile", "99",
+                           "--precision=3", "=", "binarize", "--threshold=percentile99"])
+
+
+def test_five_stage_target_pipeline(data):
+    assert_same(data, C + ["--novalue", "--precision=9", "=", "smooth", "--window=101", "=", "localmax",
+                           "--neighborhood=11", "=", "percentile", "99", "--precision=6", "=", "binarize",
+                           "--threshold=percentile99"])
+
+
+def test_cfg4_morphology_clump(data):
+    assert_same(data, C + ["--novalue", "=", "binarize", "6", "=", "open", "101", "=", "close", "1001", "=", "clump",
+                           "0.5", "--length=1000"])
+    assert_same(data, C + ["--novalue", "=", "dilate", "31", "--threshold=8", "=", "erode", "11"])
+    assert_same(data, C + ["--novalue", "=", "anticlump", "3", "--length=200", "--one=2"])
+
+
+def test_cfg5_multi_signal_fused_chain(data):
+    assert_same(data, C + ["--novalue", "--precision=6", "=", "add", "trackB.iv", "=", "multiply", "trackB.iv", "=", "mask",
+                           "maskM.iv", "--mask=0", "=", "and", "trackB.iv", "=", "binarize", "0.5"])
+    assert_same(data, C + ["--novalue", "--precision=6", "=", "subtract", "trackB.iv", "=", "divide", "trackB.iv",
+                           "--infinity=1000", "=", "masknot", "trackB.iv", "--mask=-1", "=", "abs", "=", "addconst", "0.25"])
+    assert_same(data, C + ["--novalue", "=", "erase", "--min=3", "--max=5", "=", "or", "maskM.iv", "--novalue"])
+
+
+def test_pointwise_and_window_ops(data):
+    assert_same(data, C + ["--novalue", "--precision=4", "=", "slidingsum", "--window=100", "--denom=W", "=", "clip",
+                           "--min=2", "--max=6.5", "=", "invert", "=", "bestmax", "--window=31", "=", "localmin",
+                           "--neighborhood=5", "--infinity=99"])
+    assert_same(data, C + ["--novalue", "=", "cumulativesum", "=", "bestmin", "W=4", "=", "invert", "one"])
+    assert_same(data, C + ["--window=50", "--novalue", "=", "sum", "--denom=actual", "--zero=-1", "=", "erase", "--max=2",
+                           "--keep:inside"])
+    assert_same(data, C + ["--novalue", "=", "sum", "--window=chromosome"])
+
+
+def test_valued_input_and_output_options(data):
+    assert_same(data, C + ["--precision=2"], stdin="vals.iv")
+    assert_same(data, C + ["--value=5", "--precision=1", "--uncovered:show"], stdin="vals.iv")
+    assert_same(data, C + ["--novalue", "--uncovered:NA", "--origin=one"])
+    assert_same(data, C + ["--novalue", "--nocollapse", "--nooutputvalue", "=", "binarize", "9"])
+    assert_same(data, ["chrA:300000", "chrB:1000:50000", "--novalue", "--cliptochromosome"])
+
+
+def test_input_output_variables_operators(data):
+    args = C + ["=", "input", "vals.iv", "--missing=-3", "=", "output", "mid.out", "--precision=3", "--uncovered:show", "=",
+                "percentile", "10..90by20", "--quiet", "--preserve=scratch.tmp", "=", "variables", "=", "input", "reads.iv",
+                "--novalue", "--overlap=max", "=", "percentile", "0..100"]
+    (rc_r, out_r, err_r), _ = both(data, args)
+    mid_ref = open(data / "mid.out", "rb").read()
+    (rc_o, out_o, err_o) = run(OURS, args, data / "reads.iv", data)
+    mid_ours = open(data / "mid.out", "rb").read()
+    assert rc_r == 0 and rc_o == 0, (err_r[-300:], err_o[-1000:])
+    assert out_r == out_o
+    assert mid_ref == mid_ours
+    assert err_r == err_o
+    assert_same(data, C + ["=", "input", "vals.iv", "--overlap=min", "--missing=2"])
+
+
+def test_progress_protocol(data):
+    assert_same(data, C + ["--novalue", "--progress=operations", "=", "addconst", "1", "=", "abs", "=", "percentile", "50",
+                           "--quiet", "=", "binarize", "--threshold=percentile50"])
+
+
+def test_errors_match(data):
+    for args in (C + ["=", "nosuchop"], C + ["--novalue", "=", "smooth", "--window=0"], C + ["--bogus"],
+                 C + ["--novalue", "=", "binarize", "--threshold=nosuchvar"]):
+        (rc_r, out_r, err_r), (rc_o, out_o, err_o) = both(data, args)
+        assert rc_r != 0 and rc_o != 0, args
+        assert err_r.split(b"\n")[0] == err_o.split(b"\n")[0], (args, err_r[:200], err_o[:200])
+    with open(data / "bad.iv", "w") as f:
+        f.write("chrD\t1000\t2000\n")
+    (rc_r, _, err_r), (rc_o, _, err_o) = both(data, C + ["--novalue"], stdin="bad.iv")
+    assert rc_r != 0 and rc_o != 0 and err_r == err_o
