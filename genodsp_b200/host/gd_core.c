@@ -839,24 +839,20 @@ static void parse_options (int _argc, char** _argv)
 dspop* gd_pipeline_head (void) { return pipeline; }
 int    gd_output_inhibited (void) { return inhibitOutput; }
 
-static void run_pipeline (void)
+/* run the operators [first, stop): consecutive pointwise ones as a single fused launch */
+static void exec_range (dspop* first, dspop* stop)
 	{
-	dspop* op = pipeline;
-	while (op != NULL)
+	dspop* op = first;
+	while (op != stop)
 		{
-		/* maximal run of fusable pointwise operators */
 		gdsp_pw_op prog[GDSP_MAX_POINTWISE];
 		gd_pw_resources res[GDSP_MAX_POINTWISE];
-		int n = 0;
+		int n = 0, k = 0;
 		dspop* scan = op;
-		while (scan != NULL && n < GDSP_MAX_POINTWISE && gd_is_pointwise (scan))
+		while (scan != stop && k < GDSP_MAX_POINTWISE && gd_is_pointwise (scan))
 			{
-			if (trackOperations)
-				{
-				if (scan->atRandom) tracking_report ("%s(*)\n", scan->name);
-				else for (int i = 0; i < gd.nchrom; i++) fprintf (stderr, "%s(%s)\n", scan->name, chromsSorted[i]->chrom);
-				}
-			n += gd_pointwise_descriptor (scan, &prog[n], &res[n]);     /* 0 when the operator is a no-op */
+			int got = gd_pointwise_descriptor (scan, &prog[n], &res[n]);     /* 0 when the operator is a no-op */
+			n += got;  k++;
 			scan = scan->next;
 			}
 		if (scan != op)
@@ -867,24 +863,41 @@ static void run_pipeline (void)
 			continue;
 			}
 		if (op->atRandom || gd_is_genome_capable (op))
-			{
-			if (trackOperations)
-				{
-				if (op->atRandom) tracking_report ("%s(*)\n", op->name);
-				else for (int i = 0; i < gd.nchrom; i++) fprintf (stderr, "%s(%s)\n", op->name, chromsSorted[i]->chrom);
-				}
 			(*op->funcApply) (op, "*", gd.maxLength, NULL);
-			}
 		else
-			{
 			/* an operator written against the reference contract: one chromosome vector at a time */
 			for (int i = 0; i < gd.nchrom; i++)
-				{
-				if (trackOperations) fprintf (stderr, "%s(%s)\n", op->name, chromsSorted[i]->chrom);
 				(*op->funcApply) (op, chromsSorted[i]->chrom, chromsSorted[i]->length, chromsSorted[i]->valVector);
-				}
-			}
 		op = op->next;
+		}
+	}
+
+static void run_pipeline (void)
+	{
+	if (!trackOperations) { exec_range (pipeline, NULL);  return; }
+
+	/* --progress=operations: reproduce the reference's trace (genodsp.c:900-936): a group of
+	 * per-chromosome operators is listed chromosome by chromosome, variables are resolved (and
+	 * announced) when an operator first meets a chromosome, whole-genome operators print op(*) */
+	dspop* first = pipeline;
+	while (first != NULL)
+		{
+		dspop* stop = first;
+		while (stop != NULL && !stop->atRandom) stop = stop->next;
+		if (stop != first)
+			{
+			for (int i = 0; i < gd.nchrom; i++)
+				for (dspop* op = first; op != stop; op = op->next)
+					{
+					fprintf (stderr, "%s(%s)\n", op->name, chromsSorted[i]->chrom);
+					if (i == 0) gd_resolve_variables (op);
+					}
+			exec_range (first, stop);
+			}
+		if (stop == NULL) break;
+		tracking_report ("%s(*)\n", stop->name);
+		exec_range (stop, stop->next);
+		first = stop->next;
 		}
 	}
 

@@ -59,6 +59,10 @@ int  gd_is_pointwise         (dspop* op);
  * order); returns 1, or 0 when the operator turns out to be a no-op */
 int  gd_pointwise_descriptor (dspop* op, gdsp_pw_op* out, gd_pw_resources* res);
 void gd_pw_release           (gd_pw_resources* res);
+/* resolve (and announce on stderr) the named variables an operator refers to, now */
+void gd_resolve_variables    (dspop* op);
+void gd_resolve_pointwise    (dspop* op);      /* gd_ops_pointwise.c */
+void gd_resolve_morph        (dspop* op);      /* gd_ops_morph.c     */
 
 /* helpers shared between files */
 void gd_set_outside   (ivlist* unionList, valtype value);                /* v = value outside the intervals */

@@ -106,7 +106,7 @@ static void morph_usage (char* name, FILE* f, char* indent, int kind)
 	fprintf (f, "%s  --zero=<value>           (Z=) value written for \"out\" (default is 0.0)\n", indent);
 	}
 
-static void morph_apply (dspop* _op, valtype* v)
+static void morph_resolve (dspop* _op)
 	{
 	dspop_morph* op = (dspop_morph*) _op;
 	if (op->thresholdVarName != NULL)
@@ -119,6 +119,12 @@ static void morph_apply (dspop* _op, valtype* v)
 		fprintf (stderr, "[%s] using %s = " valtypeFmt " as threshold\n", _op->name, op->thresholdVarName, op->threshold);
 		free (op->thresholdVarName);  op->thresholdVarName = NULL;
 		}
+	}
+
+static void morph_apply (dspop* _op, valtype* v)
+	{
+	dspop_morph* op = (dspop_morph*) _op;
+	morph_resolve (_op);
 	u32 left = op->left, right = op->right;
 	if (op->kind >= GDSP_MORPH_DILATE && left == 0 && right == 0)
 		{
@@ -258,7 +264,7 @@ static void clump_usage (char* name, FILE* f, char* indent, int above)
 	fprintf (f, "%s  --zero=<value>           (Z=) value for other positions (default 0.0)\n", indent);
 	}
 
-static void clump_apply (dspop* _op, valtype* v, int above)
+static void clump_resolve (dspop* _op)
 	{
 	dspop_clump* op = (dspop_clump*) _op;
 	if (op->averageVarName != NULL)
@@ -271,6 +277,12 @@ static void clump_apply (dspop* _op, valtype* v, int above)
 		fprintf (stderr, "[%s] using %s = " valtypeFmt " as threshold\n", _op->name, op->averageVarName, op->average);
 		free (op->averageVarName);  op->averageVarName = NULL;
 		}
+	}
+
+static void clump_apply (dspop* _op, valtype* v, int above)
+	{
+	dspop_clump* op = (dspop_clump*) _op;
+	clump_resolve (_op);
 	void* work = gd_work (gdsp_clump_work_bytes (gd.cells));
 	gd_check (gdsp_clump (gd.ctx, gd_layout_for (v, NULL), gd.sig, gd.cells, work, op->average, op->minLength,
 	                      op->relativeLength, above, op->oneVal, op->zeroVal), _op->name);
@@ -294,3 +306,10 @@ void   op_skimp_usage (char* name, FILE* f, char* indent) { clump_usage (name, f
 dspop* op_skimp_parse (char* name, int argc, char** argv) { return clump_parse (name, argc, argv); }
 void   op_skimp_free  (dspop* op) { clump_free (op); }
 void   op_skimp_apply (dspop* op, arg_dont_complain(char* n), arg_dont_complain(u32 l), valtype* v) { clump_apply (op, v, false); }
+
+void gd_resolve_morph (dspop* op)
+	{
+	if (op->funcApply == op_close_apply || op->funcApply == op_open_apply
+	 || op->funcApply == op_dilate_apply || op->funcApply == op_erode_apply) morph_resolve (op);
+	else if (op->funcApply == op_clump_apply || op->funcApply == op_skimp_apply) clump_resolve (op);
+	}

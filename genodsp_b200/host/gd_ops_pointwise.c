@@ -36,6 +36,12 @@ static void pw_register (opfunc_apply apply, int kind)
 	pwKinds[nPw].apply = apply;  pwKinds[nPw].kind = kind;  nPw++;
 	}
 
+int gd_is_pw_family (dspop* op);
+int gd_is_pw_family (dspop* op)
+	{
+	return op->funcApply == op_binarize_apply || op->funcApply == op_clip_apply || op->funcApply == op_erase_apply;
+	}
+
 int gd_is_pointwise (dspop* op)
 	{
 	for (int i = 0; i < nPw; i++)
@@ -114,6 +120,20 @@ void gd_set_outside (ivlist* u, valtype value)
 
 void gd_pw_release (gd_pw_resources* res)
 	{ if (res->table != NULL) { gdsp_ivl_table_destroy (res->table);  res->table = NULL; } }
+
+void gd_resolve_pointwise (dspop* _op)
+	{
+	dspop_pw* op = (dspop_pw*) _op;
+	switch (op->kind)
+		{
+		case PK_BINARIZE: resolve (_op, &op->varA, &op->a, "threshold", "threshold");  break;
+		case PK_CLIP: case PK_ERASE:
+			resolve (_op, &op->varA, &op->a, "minimum limit", "minimum");
+			resolve (_op, &op->varB, &op->b, "maximum limit", "maximum");
+			break;
+		default: break;
+		}
+	}
 
 /* ---- descriptor ----------------------------------------------------------------- */
 

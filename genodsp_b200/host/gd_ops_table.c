@@ -101,3 +101,10 @@ void* op_alloc (char* name, size_t bytes)
 
 void bad_arg (char* name, char* arg)
 	{ chastise ("[%s] Can't understand \"%s\"\n", name, arg); }
+
+int gd_is_pw_family (dspop* op);
+void gd_resolve_variables (dspop* op)
+	{
+	if (gd_is_pw_family (op)) gd_resolve_pointwise (op);
+	else gd_resolve_morph (op);
+	}

@@ -1,0 +1,92 @@
+#!/usr/bin/env python
+"""Regenerates the golden fixtures from the UNMODIFIED reference binary.
+
+    make -C oracle ref && python tests/golden/make_golden.py
+
+Inputs (g.chroms, reads.iv, vals.iv, trackB.iv) are generated from a fixed seed;
+every case in CASES is run through oracle/_ref/genodsp and its stdout/stderr are
+stored as <case>.out / <case>.err.  The reference ships no test vectors of its
+own; these files, produced by its own binary, are what pins parity on
+machines where /root/reference is absent.
+"""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.path.join(ROOT, "oracle", "_ref", "genodsp")
+
+CHROMS = [("chrA", 3000), ("chrB", 7000), ("chrC", 1100)]
+
+C = ["--chromosomes=g.chroms"]
+CASES = {
+    "depth": (C + ["--novalue"], "reads.iv"),
+    "depth_show_nocollapse": (C + ["--novalue", "--uncovered:show", "--nocollapse"], "reads.iv"),
+    "depth_NA_origin1": (C + ["--novalue", "--uncovered:NA", "--origin=one"], "reads.iv"),
+    "cfg1_sum_localmax": (C + ["--novalue", "=", "sum", "--window=101", "=", "localmax", "--neighborhood=11"], "reads.iv"),
+    "slidingsum": (C + ["--novalue", "--precision=4", "=", "slidingsum", "--window=100", "--denom=W"], "reads.iv"),
+    "smooth101": (C + ["--novalue", "--precision=15", "=", "smooth", "--window=101"], "reads.iv"),
+    "bestmax_localmin": (C + ["--novalue", "=", "bestmax", "--window=31", "=", "localmin", "--neighborhood=5", "--infinity=99"], "reads.iv"),
+    "cumulative": (C + ["--novalue", "=", "cumulativesum"], "reads.iv"),
+    "percentile_binarize": (C + ["--novalue", "=", "sum", "--window=100", "--denom=100", "=", "percentile", "99", "--precision=3",
+                                 "=", "binarize", "--threshold=percentile99"], "reads.iv"),
+    "five_stage": (C + ["--novalue", "--precision=9", "=", "smooth", "--window=101", "=", "localmax", "--neighborhood=11", "=",
+                        "percentile", "99", "--precision=6", "=", "binarize", "--threshold=percentile99"], "reads.iv"),
+    "morphology": (C + ["--novalue", "=", "binarize", "6", "=", "open", "31", "=", "close", "201", "=", "clump", "0.5",
+                        "--length=300"], "reads.iv"),
+    "dilate_erode": (C + ["--novalue", "=", "dilate", "31", "--threshold=8", "=", "erode", "11"], "reads.iv"),
+    "anticlump": (C + ["--novalue", "=", "anticlump", "3", "--length=200", "--one=2"], "reads.iv"),
+    "valued": (C + ["--precision=2"], "vals.iv"),
+    "multi_signal": (C + ["--novalue", "--precision=6", "=", "add", "trackB.iv", "=", "multiply", "trackB.iv", "=", "and",
+                          "trackB.iv", "=", "binarize", "0.5"], "reads.iv"),
+    "pointwise": (C + ["--novalue", "--precision=3", "=", "addconst", "-4.5", "=", "abs", "=", "clip", "--min=1", "--max=3.5",
+                       "=", "invert", "=", "erase", "--min=2", "--max=3"], "reads.iv"),
+}
+
+
+def write_inputs():
+    rng = np.random.default_rng(20261018)
+    with open(os.path.join(HERE, "g.chroms"), "w") as f:
+        for n, l in CHROMS:
+            f.write("%s %d\n" % (n, l))
+    with open(os.path.join(HERE, "reads.iv"), "w") as f:
+        f.write("track name=golden\n# reads\n")
+        for n, l in CHROMS:
+            m = l * 5 // 100
+            s = rng.integers(0, l - 150, m)
+            ln = rng.integers(50, 151, m)
+            for a, b in zip(s, ln):
+                f.write("%s\t%d\t%d\n" % (n, a, a + b))
+    with open(os.path.join(HERE, "vals.iv"), "w") as f:
+        for n, l in CHROMS:
+            for a in np.sort(rng.integers(0, l - 400, l // 300)):
+                f.write("%s %d %d %s\n" % (n, a, a + int(rng.integers(1, 400)), repr(float(rng.integers(-8, 9)) / 4)))
+    with open(os.path.join(HERE, "trackB.iv"), "w") as f:
+        for n, l in CHROMS[:2]:
+            pos = int(rng.integers(0, 100))
+            while pos < l:
+                e = min(l, pos + int(rng.integers(1, 600)))
+                f.write("%s\t%d\t%d\t%s\n" % (n, pos, e, repr(float(rng.integers(1, 4096)) / 1024)))
+                pos = e + int(rng.integers(1, 600))
+
+
+def main():
+    if not os.path.exists(REF):
+        sys.exit("build the reference first: make -C oracle ref")
+    write_inputs()
+    for name, (args, stdin) in CASES.items():
+        with open(os.path.join(HERE, stdin), "rb") as fin:
+            p = subprocess.run([REF] + args, stdin=fin, capture_output=True, cwd=HERE)
+        assert p.returncode == 0, (name, p.stderr)
+        open(os.path.join(HERE, name + ".out"), "wb").write(p.stdout)
+        open(os.path.join(HERE, name + ".err"), "wb").write(p.stderr)
+    json.dump({k: {"args": v[0], "stdin": v[1]} for k, v in CASES.items()}, open(os.path.join(HERE, "cases.json"), "w"), indent=1)
+    print("wrote %d golden cases" % len(CASES))
+
+
+if __name__ == "__main__":
+    main()
