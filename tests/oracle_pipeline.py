@@ -1,0 +1,203 @@
+"""A tiny interpreter of genodsp command lines on top of the plain-C oracle (CPU).  Test
+infrastructure only: it lets the CPU test-suite check the oracle against the golden fixtures
+(tests/golden/, produced by the reference binary) on machines without /root/reference."""
+import math
+import os
+
+import numpy as np
+
+from checkers import Oracle
+
+DBL_MAX = float(np.finfo(np.float64).max)
+
+
+def _num(s):
+    return {"inf": DBL_MAX, "+inf": DBL_MAX, "-inf": -DBL_MAX}.get(s, None) if s in ("inf", "+inf", "-inf") else float(s)
+
+
+def _unit(s):
+    mult = {"K": 1000, "M": 1000000, "G": 1000000000}.get(s[-1].upper(), 1)
+    return int(float(s[:-1]) * mult + 0.5) if mult != 1 else int(s)
+
+
+def fmt(v, precision):
+    return "%.*f" % (precision, v)
+
+
+class Pipeline:
+    def __init__(self, cwd):
+        self.cwd = cwd
+        self.orc = Oracle()
+        self.vars = {}
+        self.stderr = []
+
+    def read_chroms(self, path):
+        self.chroms = []
+        for line in open(os.path.join(self.cwd, path)):
+            f = line.split()
+            if f and not f[0].startswith("#"):
+                self.chroms.append((f[0], int(f[1])))
+        self.sorted = sorted(range(len(self.chroms)), key=lambda i: -self.chroms[i][1])
+        self.v = {n: np.zeros(l) for n, l in self.chroms}
+
+    def read_intervals(self, path, val_col, origin=0):
+        by = {n: ([], [], []) for n, _ in self.chroms}
+        for line in open(os.path.join(self.cwd, path)):
+            if line.startswith("track ") or not line.strip() or line.lstrip().startswith("#"):
+                continue
+            f = line.split()
+            if f[0] in by:
+                by[f[0]][0].append(int(f[1]) - origin); by[f[0]][1].append(int(f[2]))
+                by[f[0]][2].append(1.0 if val_col < 0 else float(f[val_col]))
+        return by
+
+    def per_chrom(self, fn):
+        for i in self.sorted:
+            n = self.chroms[i][0]
+            fn(self.v[n])
+
+    def run(self, argv, stdin):
+        opts = {"val_col": 3, "precision": 0, "collapse": True, "show": 0, "origin": 0, "window": None}
+        ops, cur = [], None
+        for a in argv:
+            if a == "=":
+                cur = []; ops.append(cur)
+            elif cur is not None:
+                cur.append(a)
+            elif a.startswith("--chromosomes="):
+                self.read_chroms(a.split("=", 1)[1])
+            elif a == "--novalue":
+                opts["val_col"] = -1
+            elif a.startswith("--precision="):
+                opts["precision"] = int(a.split("=")[1])
+            elif a == "--nocollapse":
+                opts["collapse"] = False
+            elif a == "--uncovered:show":
+                opts["show"] = 1
+            elif a == "--uncovered:NA":
+                opts["show"] = -1
+            elif a == "--origin=one":
+                opts["origin"] = 1
+            else:
+                raise ValueError(a)
+        iv = self.read_intervals(stdin, opts["val_col"], opts["origin"])
+        for n, _ in self.chroms:
+            s, e, val = iv[n]
+            self.orc.accumulate(self.v[n], s, e, None if opts["val_col"] < 0 else val)
+        for op in ops:
+            self.apply(op, opts)
+        return self.report(opts)
+
+    def kw(self, args, names, default=None):
+        for a in args:
+            for nm in names:
+                if a.startswith(nm):
+                    return a[len(nm):]
+        return default
+
+    def apply(self, op, opts):
+        name, args = op[0], op[1:]
+        o = self.orc
+        pos = [a for a in args if not a.startswith("--")]
+        if name == "sum":
+            W = _unit(self.kw(args, ["--window="], "100"))
+            d = self.kw(args, ["--denom="], "1")
+            self.per_chrom(lambda v: o.block_sum(v, W, float(W) if d in ("W", "window") else float(d), d == "actual", 0.0))
+        elif name == "slidingsum":
+            W = _unit(self.kw(args, ["--window="], "100"))
+            d = self.kw(args, ["--denom="], "1")
+            self.per_chrom(lambda v: o.sliding_sum(v, W, float(W) if d in ("W", "window") else float(d)))
+        elif name == "smooth":
+            W = _unit(self.kw(args, ["--window="], "101")); W += (W % 2 == 0)
+            self.per_chrom(lambda v: o.smooth(v, W))
+        elif name == "cumulativesum":
+            self.per_chrom(o.cumulative)
+        elif name in ("localmax", "localmin"):
+            N = _unit(self.kw(args, ["--neighborhood="], "3"))
+            fill = float(self.kw(args, ["--zero=", "--infinity="], "0" if name == "localmax" else repr(DBL_MAX)))
+            self.per_chrom(lambda v: o.local_extrema(v, N, name == "localmax", fill))
+        elif name in ("bestmax", "bestmin"):
+            W = _unit(self.kw(args, ["--window="], "100"))
+            self.per_chrom(lambda v: o.best_extrema(v, W, name == "bestmax"))
+        elif name == "binarize":
+            var = self.kw(args, ["--threshold="])
+            if var is not None:
+                T = self.vars[var]
+                self.stderr.append("[binarize] using %s = %f as threshold" % (var, T))
+            else:
+                T = float(pos[0]) if pos else 0.0
+            self.per_chrom(lambda v: o.binarize(v, T))
+        elif name == "addconst":
+            c = float(args[0])
+            self.per_chrom(lambda v: o.addconst(v, c))
+        elif name == "abs":
+            self.per_chrom(o.abs)
+        elif name == "clip":
+            mn, mx = self.kw(args, ["--min="]), self.kw(args, ["--max="])
+            self.per_chrom(lambda v: o.clip(v, None if mn is None else float(mn), None if mx is None else float(mx)))
+        elif name == "erase":
+            mn, mx = self.kw(args, ["--min="]), self.kw(args, ["--max="])
+            self.per_chrom(lambda v: o.erase(v, None if mn is None else float(mn), None if mx is None else float(mx),
+                                             "--keep:inside" in args, 0.0))
+        elif name == "invert":
+            if pos:
+                mid = float(pos[0])
+            else:
+                allv = np.concatenate([self.v[n] for n, _ in self.chroms])
+                mid = (allv.min() + allv.max()) / 2.0
+            self.per_chrom(lambda v: o.invert(v, mid))
+        elif name in ("open", "close", "dilate", "erode"):
+            L = _unit(pos[0]); T = float(self.kw(args, ["--threshold="], "0"))
+            if name == "open":
+                self.per_chrom(lambda v: o.open(v, L, T))
+            elif name == "close":
+                self.per_chrom(lambda v: o.close(v, L, T))
+            elif name == "dilate":
+                self.per_chrom(lambda v: o.dilate(v, L // 2, L - L // 2, T))
+            else:
+                self.per_chrom(lambda v: o.erode(v, L // 2, L - L // 2, T))
+        elif name in ("clump", "anticlump"):
+            T = float(pos[0]); L = _unit(self.kw(args, ["--length="], "100"))
+            one = float(self.kw(args, ["--one="], "1"))
+            self.per_chrom(lambda v: o.clump(v, T, L, name == "clump", one, 0.0))
+        elif name == "percentile":
+            p = pos[0]
+            prec = int(self.kw(args, ["--precision="], str(opts["precision"])))
+            names = [self.chroms[i][0] for i in self.sorted]
+            srt = np.sort(np.concatenate([self.v[n] for n in names]))
+            pm = int(round(float(p) * 1000))
+            val = srt[o.percentile_rank(srt.size, pm)]
+            self.vars["percentile" + p] = val
+            self.stderr.append("percentile %.3f is %s" % (float(p), fmt(val, prec)))
+            at = 0                          # the reference's post-state: globally sorted genome
+            for n in names:
+                self.v[n] = srt[at:at + self.v[n].size].copy(); at += self.v[n].size
+        elif name in ("add", "multiply", "and"):
+            iv = self.read_intervals(pos[0], 3)
+            for n, _ in self.chroms:
+                s, e, val = iv[n]
+                keep = [i for i, x in enumerate(val) if x != 0.0]
+                s = [s[i] for i in keep]; e = [e[i] for i in keep]; val = [val[i] for i in keep]
+                if name == "add":
+                    o.add_intervals(self.v[n], s, e, val, 1.0)
+                elif name == "multiply":
+                    o.sorted_intervals(self.v[n], s, e, val, 0, 0.0)
+                else:
+                    o.sorted_intervals(o.logical_prep(self.v[n]), s, e, val, 3, 0.0)
+        else:
+            raise ValueError("oracle pipeline: operator %s not supported" % name)
+
+    def report(self, opts):
+        out = []
+        o = opts["origin"]
+        for n, l in self.chroms:
+            rs, re, rv = self.orc.runs(np.ascontiguousarray(self.v[n]), opts["collapse"], opts["show"])
+            prev = 0
+            for s, e, x in zip(rs, re, rv):
+                if opts["show"] == -1 and s != prev:
+                    out.append("%s\t%d\t%d\tNA" % (n, prev + o, s))
+                out.append("%s\t%d\t%d\t%s" % (n, s + o, e, fmt(x, opts["precision"])))
+                prev = int(e)
+            if opts["show"] == -1 and prev != l:
+                out.append("%s\t%d\t%d\tNA" % (n, prev + o, l))
+        return "\n".join(out) + ("\n" if out else "")

@@ -1,0 +1,148 @@
+"""CPU-only tests (run with -m "not gpu"): the oracle against the golden fixtures produced by the
+reference binary, the host-side helpers, the slab partition with a world_size-2 gloo exchange, and the
+C-ABI library's exported symbols (no compute calls: there is no GPU here)."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from checkers import Oracle, ROOT
+from oracle_pipeline import Pipeline
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+CASES = json.load(open(os.path.join(GOLD, "cases.json")))
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_oracle_matches_golden(case):
+    p = Pipeline(GOLD)
+    got = p.run(CASES[case]["args"], CASES[case]["stdin"])
+    want = open(os.path.join(GOLD, case + ".out")).read()
+    if got != want:
+        g, w = got.split("\n"), want.split("\n")
+        for i, (a, b) in enumerate(zip(g, w)):
+            assert a == b, "%s: line %d: oracle %r, reference %r" % (case, i + 1, a, b)
+        assert len(g) == len(w)
+    err = open(os.path.join(GOLD, case + ".err")).read().strip().split("\n")
+    assert [e for e in err if e] == p.stderr, case
+
+
+def test_hann_taps_match_oracle():
+    from genodsp_b200.genome import hann_taps
+    orc = Oracle()
+    for W in (3, 11, 101, 1001):
+        assert np.array_equal(hann_taps(W).view(np.uint64), orc.hann_taps(W).view(np.uint64))
+
+
+def test_percentile_rank_and_name():
+    from genodsp_b200.genome import percentile_name, percentile_rank
+    orc = Oracle()
+    for n in (1, 7, 1000, 3088269832, 4294967295):
+        for p in (1, 500, 12345, 50000, 99000, 99999):
+            assert percentile_rank(n, p) == orc.percentile_rank(n, p)
+    assert percentile_name(99000) == "percentile99"
+    assert percentile_name(99500) == "percentile99.5"
+    assert percentile_name(99720) == "percentile99.72"
+    assert percentile_name(12345) == "percentile12.345"
+
+
+def test_library_exports_every_declared_symbol():
+    """include/gdsp_b200.h is the C-ABI contract: every function it declares must be exported by the built
+    library and bound (with the same name) by the ctypes mirror."""
+    from genodsp_b200 import capi
+    hdr = open(os.path.join(ROOT, "include", "gdsp_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(gdsp_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 35
+    lib = C.CDLL(capi.LIB_PATH)
+    for n in sorted(names):
+        assert hasattr(lib, n), "libgdsp_b200.so does not export %s" % n
+        assert n in capi.SIGNATURES, "capi.py does not bind %s" % n
+    assert set(capi.SIGNATURES) <= names
+    capi.load()
+
+
+def test_no_cpu_fallback_without_device():
+    """without a CUDA device the library must refuse, not fall back"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from genodsp_b200 import capi
+    lib = capi.load()
+    ctx = C.c_void_p()
+    assert lib.gdsp_ctx_create(0, None, C.byref(ctx)) == -5
+    assert b"no CPU path" in lib.gdsp_last_error()
+    with pytest.raises(capi.GdspError):
+        from genodsp_b200.genome import Genome
+        Genome([("a", 10)])
+
+
+def test_product_never_touches_the_oracle():
+    """only tests/, bench.py (cpu_baseline / --impl reference) and __graft_entry__.smoke may use oracle/"""
+    for d, _, files in os.walk(os.path.join(ROOT, "genodsp_b200")):
+        for f in files:
+            if f.endswith((".py", ".c", ".h", ".cu", ".cuh")) or f == "Makefile":
+                txt = open(os.path.join(d, f), errors="ignore").read()
+                assert "gdsp_oracle" not in txt and "oracle/" not in txt and "checkers" not in txt, os.path.join(d, f)
+
+
+# ---------------------------------------------------------------------------------------- slabs
+HG38 = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 156040895, 145138636,
+        138394717, 135086622, 133797422, 133275309, 114364328, 107043718, 101991189, 90338345, 83257441, 80373285,
+        64444167, 58617616, 57227415, 50818468, 46709983]
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+def test_slab_partition_covers_genome_once(world):
+    from genodsp_b200 import slab
+    owned = {}
+    sizes = []
+    for r in range(world):
+        segs, cells = slab.partition(HG38, world, r, 50)
+        sizes.append(sum(hi - lo for _, lo, hi, _, _, _ in segs))
+        prev_end = 0
+        for si, lo, hi, dlo, dhi, pos0 in segs:
+            assert lo % 64 == 0 and dlo >= prev_end and dlo <= lo and hi <= dhi <= cells
+            prev_end = dhi
+            owned.setdefault(si, []).append((pos0, pos0 + hi - lo))
+    assert sum(sizes) == sum(HG38) and max(sizes) - min(sizes) <= 1
+    for si, pieces in owned.items():
+        pieces.sort()
+        assert pieces[0][0] == 0 and pieces[-1][1] == HG38[si]
+        for a, b in zip(pieces, pieces[1:]):
+            assert a[1] == b[0]
+
+
+def _gloo_worker(rank, world, port, lengths, halo, out):
+    import torch
+    import torch.distributed as dist
+    from genodsp_b200 import slab
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    segs, cells = slab.partition(lengths, world, rank, halo)
+    buf = torch.full((cells,), -1.0, dtype=torch.float64)
+    g0 = [0]
+    for l in lengths:
+        g0.append(g0[-1] + l)
+    for si, lo, hi, dlo, dhi, pos0 in segs:       # cell value = its genome coordinate
+        buf[lo:hi] = torch.arange(g0[si] + pos0, g0[si] + pos0 + (hi - lo), dtype=torch.float64)
+    slab.exchange_halos(buf, slab.halo_plan(lengths, world, rank, halo), dist)
+    ok = True
+    for si, lo, hi, dlo, dhi, pos0 in segs:       # halo cells must hold the neighbour's coordinates
+        want = torch.arange(g0[si] + pos0 - (lo - dlo), g0[si] + pos0 + (hi - lo) + (dhi - hi), dtype=torch.float64)
+        ok = ok and bool(torch.equal(buf[dlo:dhi], want))
+    out[rank] = ok
+    dist.destroy_process_group()
+
+
+def test_halo_exchange_world2_gloo():
+    import torch.multiprocessing as mp
+    lengths = [5000, 3000, 1200, 300]
+    for world in (2, 3):
+        mgr = mp.Manager()
+        out = mgr.dict()
+        port = 29500 + world + (os.getpid() % 1000)
+        mp.spawn(_gloo_worker, args=(world, port, lengths, 37, out), nprocs=world, join=True)
+        assert all(out[r] for r in range(world)), dict(out)
