@@ -28,12 +28,6 @@
 #define SORT_ROUNDS  16
 #define SORT_TILE    (SORT_WARPS * SORT_ROUNDS * 32)     // 4096 keys
 
-#define ST_EMPTY 0ull
-#define ST_AGG   1ull
-#define ST_INCL  2ull
-#define ST_SHIFT 62
-#define ST_MASK  ((1ull << ST_SHIFT) - 1)
-
 // output position -> buffer cell (segmented destination), or identity
 struct OutMap
 	{
@@ -86,153 +80,250 @@ k_sort_orand (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base
 	}
 
 // ---------------------------------------------------------------------------
-// histogram of one digit (warp-private counters, match.any ranking: no
-// same-address shared-memory atomics however skewed the data)
+// One stable counting-sort pass on an 8-bit digit = three chain-free kernels:
+//   k_sort_hist     per-tile digit histograms (warp-private counters ranked with
+//                   match.any: no same-address atomics however skewed the data)
+//   k_tab_*         exclusive prefix over the digit-major table [digit][tile]:
+//                   entry (d,t) becomes the output position of tile t's first key
+//                   with digit d
+//   k_sort_scatter  re-reads the tile, ranks its keys the same way and writes
+//                   them to their final positions
+// Traffic: 24 B per key per pass (+ the table, ~1 B per key).
 // ---------------------------------------------------------------------------
+
+#define SORT_HB 8      // consecutive tiles handled by one histogram block
+#define SORT_SB 4      // consecutive tiles handled by one scatter block
+
+// rank the valid keys of one round inside the warp; returns the digit
+__device__ __forceinline__ unsigned sort_rank_round (unsigned long long key, int shift, bool valid, int lane,
+                                                     unsigned int* warpCnt, unsigned short& rank)
+	{
+	const unsigned vm = __ballot_sync (0xffffffffu, valid);
+	unsigned d = 0;
+	if (valid)
+		{
+		d = (unsigned) ((key >> shift) & 255ull);
+		const unsigned peers = __match_any_sync (vm, d);
+		const int leader = __ffs (peers) - 1;
+		unsigned pre = 0;
+		if (lane == leader) { pre = warpCnt[d];  warpCnt[d] = pre + __popc (peers); }
+		pre = __shfl_sync (peers, pre, leader);
+		rank = (unsigned short) (pre + __popc (peers & ((1u << lane) - 1u)));
+		}
+	__syncwarp ();
+	return d;
+	}
 
 __global__ void __launch_bounds__(SORT_THREADS)
 k_sort_hist (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg, uint64_t ntiles,
-             const double* __restrict__ in, int shift, unsigned long long* __restrict__ hist)
+             uint64_t ntilesPad, const double* __restrict__ in, int shift, unsigned int* __restrict__ tileHist)
 	{
 	__shared__ unsigned int s_cnt[SORT_WARPS][256];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	for (int i = threadIdx.x; i < SORT_WARPS * 256; i += SORT_THREADS) (&s_cnt[0][0])[i] = 0;
-	__syncthreads ();
-	for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x)
+	const uint64_t tFirst = (uint64_t) blockIdx.x * SORT_HB;
+	unsigned int mine[SORT_HB];
+	#pragma unroll
+	for (int k = 0; k < SORT_HB; k++)
 		{
+		mine[k] = 0;
+		const uint64_t t = tFirst + k;
+		if (t >= ntiles) continue;                           // uniform across the block
+		for (int i = threadIdx.x; i < SORT_WARPS * 256; i += SORT_THREADS) (&s_cnt[0][0])[i] = 0;
+		__syncthreads ();
 		int seg;  uint64_t tis;
 		tile_to_seg (base, nseg, t, seg, tis);
 		const SegDev sd = segs[seg];
 		const uint64_t t0 = sd.lo + tis * SORT_TILE;
 		const uint32_t n  = (uint32_t) ((sd.hi - t0 < SORT_TILE) ? (sd.hi - t0) : SORT_TILE);
+		#pragma unroll 4
 		for (int r = 0; r < SORT_ROUNDS; r++)
 			{
 			const uint32_t idx = warp * (SORT_ROUNDS * 32) + r * 32 + lane;
 			const bool valid = idx < n;
-			const unsigned vm = __ballot_sync (0xffffffffu, valid);
-			if (valid)
-				{
-				const unsigned d = (unsigned) ((f64_key (in[t0 + idx]) >> shift) & 255ull);
-				const unsigned peers = __match_any_sync (vm, d);
-				if (lane == __ffs (peers) - 1) s_cnt[warp][d] += __popc (peers);
-				}
-			__syncwarp ();
+			const unsigned long long key = valid ? f64_key (in[t0 + idx]) : 0ull;
+			unsigned short rk;
+			sort_rank_round (key, shift, valid, lane, s_cnt[warp], rk);
 			}
+		__syncthreads ();
+		unsigned int tot = 0;
+		#pragma unroll
+		for (int w = 0; w < SORT_WARPS; w++) tot += s_cnt[w][threadIdx.x];
+		mine[k] = tot;
+		__syncthreads ();
 		}
-	__syncthreads ();
-	unsigned int tot = 0;
-	for (int w = 0; w < SORT_WARPS; w++) tot += s_cnt[w][threadIdx.x];
-	if (tot) atomicAdd (&hist[threadIdx.x], (unsigned long long) tot);
+	// thread d owns digit d: SORT_HB consecutive table entries = one 32-byte sector
+	uint4* dst = reinterpret_cast<uint4*> (tileHist + (uint64_t) threadIdx.x * ntilesPad + tFirst);
+	dst[0] = make_uint4 (mine[0], mine[1], mine[2], mine[3]);
+	dst[1] = make_uint4 (mine[4], mine[5], mine[6], mine[7]);
 	}
 
-// exclusive prefix over the 256 bins (one warp)
-__global__ void k_sort_binstart (const unsigned long long* __restrict__ hist, unsigned long long* __restrict__ binStart)
+// ---- exclusive prefix over the table (u32 counts -> u64 positions) ------------------
+#define TAB_CHUNK 8192
+
+__global__ void __launch_bounds__(256)
+k_tab_reduce (const unsigned int* __restrict__ tab, uint64_t n, unsigned long long* __restrict__ partial)
 	{
-	const int lane = threadIdx.x;
-	unsigned long long carry = 0;
-	for (int c = 0; c < 8; c++)
+	__shared__ unsigned long long s_red[8];
+	const uint64_t c0 = (uint64_t) blockIdx.x * TAB_CHUNK;
+	unsigned long long t = 0;
+	for (uint32_t i = threadIdx.x * 4; i < TAB_CHUNK; i += 256 * 4)
+		if (c0 + i < n)
+			{
+			uint4 v = *reinterpret_cast<const uint4*> (tab + c0 + i);        // n is a multiple of 8
+			t += (unsigned long long) v.x + v.y + v.z + v.w;
+			}
+	#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync (0xffffffffu, t, d);
+	if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = t;
+	__syncthreads ();
+	if (threadIdx.x == 0)
 		{
-		unsigned long long v = hist[c * 32 + lane], inc = v;
+		unsigned long long a = 0;
+		for (int w = 0; w < 8; w++) a += s_red[w];
+		partial[blockIdx.x] = a;
+		}
+	}
+
+// one block: in-place exclusive scan of the chunk totals
+__global__ void __launch_bounds__(1024)
+k_tab_scan_partials (unsigned long long* __restrict__ partial, uint64_t nchunks)
+	{
+	__shared__ unsigned long long s_w[32];
+	__shared__ unsigned long long s_carry;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (threadIdx.x == 0) s_carry = 0;
+	__syncthreads ();
+	for (uint64_t c0 = 0; c0 < nchunks; c0 += 1024)
+		{
+		const uint64_t i = c0 + threadIdx.x;
+		unsigned long long v = (i < nchunks) ? partial[i] : 0ull, inc = v;
 		#pragma unroll
 		for (int d = 1; d < 32; d <<= 1)
 			{
 			unsigned long long up = __shfl_up_sync (0xffffffffu, inc, d);
 			if (lane >= d) inc += up;
 			}
-		binStart[c * 32 + lane] = carry + inc - v;
-		carry += __shfl_sync (0xffffffffu, inc, 31);
+		if (lane == 31) s_w[warp] = inc;
+		__syncthreads ();
+		unsigned long long wex = 0, tot = 0;
+		for (int w = 0; w < 32; w++) { if (w < warp) wex += s_w[w];  tot += s_w[w]; }
+		const unsigned long long carry = s_carry;
+		if (i < nchunks) partial[i] = carry + wex + inc - v;
+		__syncthreads ();
+		if (threadIdx.x == 0) s_carry = carry + tot;
+		__syncthreads ();
 		}
 	}
 
-// ---------------------------------------------------------------------------
-// one stable counting-sort pass on digit `shift`
-// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_tab_apply (const unsigned int* __restrict__ tab, uint64_t n, const unsigned long long* __restrict__ partial,
+             unsigned long long* __restrict__ off)
+	{
+	__shared__ unsigned long long s_w[8];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint64_t c0 = (uint64_t) blockIdx.x * TAB_CHUNK;
+	// thread owns 32 consecutive entries
+	const uint64_t i0 = c0 + (uint64_t) threadIdx.x * 32;
+	unsigned int v[32];
+	unsigned long long tot = 0;
+	#pragma unroll
+	for (int q = 0; q < 8; q++)
+		{
+		uint4 x = (i0 + q * 4 < n) ? *reinterpret_cast<const uint4*> (tab + i0 + q * 4) : make_uint4 (0, 0, 0, 0);
+		v[q*4+0] = x.x;  v[q*4+1] = x.y;  v[q*4+2] = x.z;  v[q*4+3] = x.w;
+		tot += (unsigned long long) x.x + x.y + x.z + x.w;
+		}
+	unsigned long long inc = tot;
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1)
+		{
+		unsigned long long up = __shfl_up_sync (0xffffffffu, inc, d);
+		if (lane >= d) inc += up;
+		}
+	if (lane == 31) s_w[warp] = inc;
+	__syncthreads ();
+	unsigned long long run = partial[blockIdx.x] + inc - tot;
+	for (int w = 0; w < warp; w++) run += s_w[w];
+	if (i0 < n)
+		{
+		#pragma unroll
+		for (int q = 0; q < 32; q += 2)
+			{
+			ulonglong2 o;
+			o.x = run;  run += v[q];
+			o.y = run;  run += v[q+1];
+			*reinterpret_cast<ulonglong2*> (off + i0 + q) = o;
+			}
+		}
+	}
 
 __global__ void __launch_bounds__(SORT_THREADS)
-k_sort_scatter (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
-                const double* __restrict__ in, double* __restrict__ out, OutMap om, int shift,
-                const unsigned long long* __restrict__ binStart,
-                unsigned long long* __restrict__ status /* [ntiles][256] */,
-                unsigned int* __restrict__ ticket)
+k_sort_scatter (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg, uint64_t ntiles,
+                uint64_t ntilesPad, const double* __restrict__ in, double* __restrict__ out, OutMap om, int shift,
+                const unsigned long long* __restrict__ tileOff)
 	{
 	__shared__ unsigned int       s_cnt[SORT_WARPS][256];
 	__shared__ unsigned long long s_off[256];
-	__shared__ unsigned int       s_ticket;
-
-	if (threadIdx.x == 0) s_ticket = atomicAdd (ticket, 1u);
-	for (int i = threadIdx.x; i < SORT_WARPS * 256; i += SORT_THREADS) (&s_cnt[0][0])[i] = 0;
-	__syncthreads ();
-	const uint64_t tile = s_ticket;
-	int seg;  uint64_t tis;
-	tile_to_seg (base, nseg, tile, seg, tis);
-	const SegDev sd = segs[seg];
-	const uint64_t t0 = sd.lo + tis * SORT_TILE;
-	const uint32_t n  = (uint32_t) ((sd.hi - t0 < SORT_TILE) ? (sd.hi - t0) : SORT_TILE);
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint64_t tFirst = (uint64_t) blockIdx.x * SORT_SB;
 
-	unsigned long long key[SORT_ROUNDS];
-	unsigned short     rank[SORT_ROUNDS];
-	#pragma unroll
-	for (int r = 0; r < SORT_ROUNDS; r++)
-		{
-		const uint32_t idx = warp * (SORT_ROUNDS * 32) + r * 32 + lane;
-		key[r] = (idx < n) ? f64_key (in[t0 + idx]) : ~0ull;
-		}
-	#pragma unroll
-	for (int r = 0; r < SORT_ROUNDS; r++)
-		{
-		const uint32_t idx = warp * (SORT_ROUNDS * 32) + r * 32 + lane;
-		const bool valid = idx < n;
-		const unsigned vm = __ballot_sync (0xffffffffu, valid);
-		if (valid)
-			{
-			const unsigned d = (unsigned) ((key[r] >> shift) & 255ull);
-			const unsigned peers = __match_any_sync (vm, d);
-			const int leader = __ffs (peers) - 1;
-			unsigned pre = 0;
-			if (lane == leader) { pre = s_cnt[warp][d];  s_cnt[warp][d] = pre + __popc (peers); }
-			pre = __shfl_sync (peers, pre, leader);
-			rank[r] = (unsigned short) (pre + __popc (peers & ((1u << lane) - 1u)));
-			}
-		__syncwarp ();
-		}
-	__syncthreads ();
-
-	// thread d owns digit d: per-warp exclusive offsets, tile count, look-back
+	// thread d: positions of digit d for the SORT_SB tiles of this block (one 32-byte sector)
+	unsigned long long myOff[SORT_SB];
 	{
-	const int d = threadIdx.x;
-	unsigned int tot = 0;
-	#pragma unroll
-	for (int w = 0; w < SORT_WARPS; w++) { unsigned int t = s_cnt[w][d];  s_cnt[w][d] = tot;  tot += t; }
-	unsigned long long* st = status + tile * 256 + d;
-	unsigned long long excl = 0;
-	if (tile == 0)
-		*(volatile unsigned long long*) st = (ST_INCL << ST_SHIFT) | (unsigned long long) tot;
-	else
-		{
-		*(volatile unsigned long long*) st = (ST_AGG << ST_SHIFT) | (unsigned long long) tot;
-		for (uint64_t j = tile - 1; ; j--)
-			{
-			unsigned long long s;
-			do { s = *(volatile unsigned long long*) (status + j * 256 + d); } while ((s >> ST_SHIFT) == ST_EMPTY);
-			excl += s & ST_MASK;
-			if ((s >> ST_SHIFT) == ST_INCL) break;
-			}
-		*(volatile unsigned long long*) st = (ST_INCL << ST_SHIFT) | (excl + tot);
-		}
-	s_off[d] = binStart[d] + excl;
+	const ulonglong2* src = reinterpret_cast<const ulonglong2*> (tileOff + (uint64_t) threadIdx.x * ntilesPad + tFirst);
+	ulonglong2 a = src[0], b = src[1];
+	myOff[0] = a.x;  myOff[1] = a.y;  myOff[2] = b.x;  myOff[3] = b.y;
 	}
-	__syncthreads ();
 
-	#pragma unroll
-	for (int r = 0; r < SORT_ROUNDS; r++)
+	#pragma unroll 1
+	for (int k = 0; k < SORT_SB; k++)
 		{
-		const uint32_t idx = warp * (SORT_ROUNDS * 32) + r * 32 + lane;
-		if (idx < n)
+		const uint64_t t = tFirst + k;
+		if (t >= ntiles) break;
+		__syncthreads ();
+		for (int i = threadIdx.x; i < SORT_WARPS * 256; i += SORT_THREADS) (&s_cnt[0][0])[i] = 0;
+		s_off[threadIdx.x] = (k == 0) ? myOff[0] : (k == 1) ? myOff[1] : (k == 2) ? myOff[2] : myOff[3];
+		__syncthreads ();
+		int seg;  uint64_t tis;
+		tile_to_seg (base, nseg, t, seg, tis);
+		const SegDev sd = segs[seg];
+		const uint64_t t0 = sd.lo + tis * SORT_TILE;
+		const uint32_t n  = (uint32_t) ((sd.hi - t0 < SORT_TILE) ? (sd.hi - t0) : SORT_TILE);
+
+		unsigned long long key[SORT_ROUNDS];
+		unsigned short     rank[SORT_ROUNDS];
+		#pragma unroll
+		for (int r = 0; r < SORT_ROUNDS; r++)
 			{
-			const unsigned d = (unsigned) ((key[r] >> shift) & 255ull);
-			const unsigned long long pos = s_off[d] + s_cnt[warp][d] + rank[r];
-			out[out_cell (om, pos)] = key_f64 (key[r]);
+			const uint32_t idx = warp * (SORT_ROUNDS * 32) + r * 32 + lane;
+			key[r] = (idx < n) ? f64_key (in[t0 + idx]) : ~0ull;
+			}
+		#pragma unroll
+		for (int r = 0; r < SORT_ROUNDS; r++)
+			{
+			const uint32_t idx = warp * (SORT_ROUNDS * 32) + r * 32 + lane;
+			rank[r] = 0;
+			sort_rank_round (key[r], shift, idx < n, lane, s_cnt[warp], rank[r]);
+			}
+		__syncthreads ();
+		// per-warp exclusive offsets of every digit
+		{
+		const int d = threadIdx.x;
+		unsigned int tot = 0;
+		#pragma unroll
+		for (int w = 0; w < SORT_WARPS; w++) { unsigned int c = s_cnt[w][d];  s_cnt[w][d] = tot;  tot += c; }
+		}
+		__syncthreads ();
+		#pragma unroll
+		for (int r = 0; r < SORT_ROUNDS; r++)
+			{
+			const uint32_t idx = warp * (SORT_ROUNDS * 32) + r * 32 + lane;
+			if (idx < n)
+				{
+				const unsigned d = (unsigned) ((key[r] >> shift) & 255ull);
+				const unsigned long long pos = s_off[d] + s_cnt[warp][d] + rank[r];
+				out[out_cell (om, pos)] = key_f64 (key[r]);
+				}
 			}
 		}
 	}
@@ -254,35 +345,40 @@ struct SortPlan
 struct SortScratch
 	{
 	unsigned long long* orand;      // 2
-	unsigned long long* hist;       // 256
-	unsigned long long* binStart;   // 256
-	unsigned int*       ticket;     // 1
 	SegDev*             linSeg;     // 1 pseudo segment
 	uint64_t*           linBase;    // 2
 	uint64_t*           prefix;     // nseg+1 (segmented destination)
-	unsigned long long* status;     // ntiles*256
+	unsigned int*       tileHist;   // 256 * ntilesPad
+	unsigned long long* tileOff;    // 256 * ntilesPad
+	unsigned long long* partial;    // chunks
+	uint64_t            ntilesPadMax;
 	};
+
+static inline uint64_t pad8 (uint64_t x) { return (x + 7) / 8 * 8; }
 
 static int sort_scratch (gdsp_ctx* c, uint64_t ntilesMax, int nseg, SortScratch* s)
 	{
-	size_t small = 8192 + sizeof (uint64_t) * (nseg + 8);
-	size_t bytes = small + ntilesMax * 256 * sizeof (unsigned long long);
+	const uint64_t tp = pad8 (ntilesMax);
+	const uint64_t entries = 256 * tp;
+	const uint64_t chunks = (entries + TAB_CHUNK - 1) / TAB_CHUNK + 8;
+	size_t small = 4096 + ((sizeof (uint64_t) * (nseg + 8) + 255) / 256) * 256;
+	size_t bytes = small + entries * 4 + 256 + entries * 8 + 256 + chunks * 8;
 	void* ws;
 	GDSP_TRY (gdsp_ws (c, 4, bytes, &ws));
 	char* p = (char*) ws;
-	s->orand = (unsigned long long*) p;        p += 64;
-	s->hist = (unsigned long long*) p;         p += 2048;
-	s->binStart = (unsigned long long*) p;     p += 2048;
-	s->ticket = (unsigned int*) p;             p += 64;
-	s->linSeg = (SegDev*) p;                   p += 64;
-	s->linBase = (uint64_t*) p;                p += 64;
-	s->prefix = (uint64_t*) p;                 p += ((sizeof (uint64_t) * (nseg + 1) + 255) / 256) * 256;
+	s->orand = (unsigned long long*) p;        p += 256;
+	s->linSeg = (SegDev*) p;                   p += 256;
+	s->linBase = (uint64_t*) p;                p += 256;
+	s->prefix = (uint64_t*) p;
 	p = (char*) ws + small;
-	s->status = (unsigned long long*) p;
+	s->tileHist = (unsigned int*) p;           p += entries * 4 + 256;
+	s->tileOff = (unsigned long long*) p;      p += entries * 8 + 256;
+	s->partial = (unsigned long long*) p;
+	s->ntilesPadMax = tp;
 	return GDSP_OK;
 	}
 
-// Sort the `n` owned cells of `src` (viewed through plan `in`) ascending.
+// Sort the owned cells of `src` (viewed through plan `inPlan`) ascending.
 // Buffers a and b ping-pong; src may be a.  The result lands in *resultBuf
 // (a or b), laid out through `finalMap` (segmented) or linearly.
 static int radix_sort (gdsp_ctx* c, const SortPlan& inPlan, const SortPlan& linPlan, const double* src,
@@ -315,17 +411,21 @@ static int radix_sort (gdsp_ctx* c, const SortPlan& inPlan, const SortPlan& linP
 		{
 		double* dst = (cur == a) ? b : a;
 		const bool last = (p == k - 1);
-		GDSP_CUDA (cudaMemsetAsync (sc.hist, 0, 2048, c->stream));
-		GDSP_CUDA (cudaMemsetAsync (sc.ticket, 0, 4, c->stream));
-		GDSP_CUDA (cudaMemsetAsync (sc.status, 0, plan.ntiles * 256 * sizeof (unsigned long long), c->stream));
-		int g = c->sm_count * 8;
-		if ((uint64_t) g > plan.ntiles) g = (int) plan.ntiles;
-		k_sort_hist<<<g, SORT_THREADS, 0, c->stream>>> (plan.segs, plan.base, plan.nseg, plan.ntiles, cur, shifts[p], sc.hist);
+		const uint64_t tp = pad8 (plan.ntiles);
+		GDSP_REQUIRE (tp <= sc.ntilesPadMax, "radix_sort: scratch too small");
+		const uint64_t entries = 256 * tp;
+		const unsigned chunks = (unsigned) ((entries + TAB_CHUNK - 1) / TAB_CHUNK);
+		k_sort_hist<<<(unsigned) (tp / SORT_HB), SORT_THREADS, 0, c->stream>>> (plan.segs, plan.base, plan.nseg, plan.ntiles, tp,
+		        cur, shifts[p], sc.tileHist);
 		GDSP_KERNEL_CHECK ();
-		k_sort_binstart<<<1, 32, 0, c->stream>>> (sc.hist, sc.binStart);
+		k_tab_reduce<<<chunks, 256, 0, c->stream>>> (sc.tileHist, entries, sc.partial);
 		GDSP_KERNEL_CHECK ();
-		k_sort_scatter<<<(unsigned) plan.ntiles, SORT_THREADS, 0, c->stream>>> (plan.segs, plan.base, plan.nseg, cur, dst,
-		        last ? finalMap : lin, shifts[p], sc.binStart, sc.status, sc.ticket);
+		k_tab_scan_partials<<<1, 1024, 0, c->stream>>> (sc.partial, chunks);
+		GDSP_KERNEL_CHECK ();
+		k_tab_apply<<<chunks, 256, 0, c->stream>>> (sc.tileHist, entries, sc.partial, sc.tileOff);
+		GDSP_KERNEL_CHECK ();
+		k_sort_scatter<<<(unsigned) ((plan.ntiles + SORT_SB - 1) / SORT_SB), SORT_THREADS, 0, c->stream>>> (plan.segs, plan.base,
+		        plan.nseg, plan.ntiles, tp, cur, dst, last ? finalMap : lin, shifts[p], sc.tileOff);
 		GDSP_KERNEL_CHECK ();
 		cur = dst;
 		plan = linPlan;

@@ -1,0 +1,105 @@
+#!/usr/bin/env python
+"""Per-stage throughput of the operator kernels on an hg38-shaped genome (or hg38/--scale).
+
+Every stage is timed with CUDA events on the stream the kernels run on, after warm-up, on a
+signal much larger than L2.  Prints one JSON object: stage -> ms, Gbp/s, algorithmic GB/s and the
+fraction of the measured HBM peak (MEASURED_PEAKS.json)."""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scale", type=int, default=1)
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--stages", default="all")
+    args = ap.parse_args()
+    import torch
+    from genodsp_b200.genome import Genome
+    chroms = bench.scaled_genome(args.scale)
+    g = Genome(chroms)
+    order = sorted(range(len(chroms)), key=lambda i: -chroms[i][1])
+    seg, st, en = bench.synth_intervals(torch, g.device, [chroms[i] for i in order])
+    N = g.cells
+    peak, _ = bench.measured_hbm_peak()
+    G = type(g)
+    depth = None
+
+    def reset():
+        g.sig.copy_(depth)
+
+    def timed(fn, setup=None):
+        best = None
+        for r in range(args.reps + 1):
+            if setup:
+                setup()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ms = a.elapsed_time(b)
+            if r > 0:
+                best = ms if best is None else min(best, ms)
+        return best
+
+    out = {}
+
+    def rec(name, ms, bytes_per_bp, extra_bytes=0):
+        gbs = (bytes_per_bp * N + extra_bytes) / (ms / 1e3) / 1e9
+        out[name] = {"ms": round(ms, 3), "gbp_s": round(N / (ms / 1e3) / 1e9, 2), "alg_bytes_per_bp": bytes_per_bp,
+                     "achieved_gbs": round(gbs, 1), "frac_hbm": round(gbs / peak, 3)}
+        print(name, out[name], flush=True)
+
+    want = None if args.stages == "all" else set(args.stages.split(","))
+
+    def on(name):
+        return want is None or name in want
+
+    ms = timed(lambda: g.accumulate(seg, st, en, host=False))
+    rec("depth_accumulate", ms, 16, 28 * int(seg.shape[0]))
+    depth = g.sig.clone()
+    if on("slidingsum"):
+        rec("slidingsum_w101", timed(lambda: g.slidingsum(101), reset), 16)
+    if on("sum"):
+        rec("sum_w100", timed(lambda: g.sum(100, denom=100.0), reset), 16)
+    if on("smooth"):
+        rec("smooth_w101", timed(lambda: g.smooth(101), reset), 16)
+    if on("localmax"):
+        rec("localmax_n11", timed(lambda: g.localmax(11), reset), 16)
+    if on("bestmax"):
+        rec("bestmax_w101", timed(lambda: g.bestmax(101), reset), 16)
+    if on("binarize"):
+        rec("binarize", timed(lambda: g.binarize(6.0), reset), 16)
+        rec("pointwise_chain5", timed(lambda: g.pointwise([G.op_addconst(-1.5), G.op_abs(), G.op_clip(0.5, 6.0), G.op_invert(2.0),
+                                                           G.op_binarize(-1.0)]), reset), 16)
+    if on("cumulativesum"):
+        rec("cumulativesum", timed(lambda: g.cumulativesum(), reset), 16)
+    if on("percentile"):
+        rec("percentile99_select", timed(lambda: g.percentile(99.0, destructive=False), reset), 8)
+        rec("percentile_1to99by1_select", timed(lambda: g.percentile(1.0, 99.0, 1.0, destructive=False), reset), 8)
+    if on("sort"):
+        rec("sort_genome_depth", timed(lambda: g.sort_genome(), reset), 16)
+        def smooth_setup():
+            reset(); g.smooth(101)
+        rec("percentile99_select_smoothed", timed(lambda: g.percentile(99.0, destructive=False), smooth_setup), 8)
+        rec("sort_genome_smoothed", timed(lambda: g.sort_genome(), smooth_setup), 16)
+    if on("morph"):
+        rec("open_1001", timed(lambda: g.open_(1001, 6.0), reset), 16)
+        rec("close_1001", timed(lambda: g.close_(1001, 6.0), reset), 16)
+        rec("dilate_1001", timed(lambda: g.dilate(1001, threshold=6.0), reset), 16)
+    if on("clump"):
+        rec("clump_L1000", timed(lambda: g.clump(6.5, 1000), reset), 16)
+    if on("runs"):
+        def bin_setup():
+            reset(); g.binarize(9.0)
+        rec("runs_binarized", timed(lambda: g.runs(cap=max(1024, N // 8)), bin_setup), 8)
+    print(json.dumps({"scale": args.scale, "bases": N, "hbm_peak_gbs": peak, "stages": out}))
+
+
+if __name__ == "__main__":
+    main()
