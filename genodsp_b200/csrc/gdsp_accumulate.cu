@@ -20,13 +20,20 @@
 #define SCAN_ROWS    4
 #define SCAN_TILE    (SCAN_WARPS * SCAN_ROWS * 128)      // 4096 cells
 
+template <typename T> __device__ __forceinline__ T warp_shfl_up (T v, int d);
+template <typename T> __device__ __forceinline__ T warp_shfl_idx (T v, int s);
+
 // ---------------------------------------------------------------------------
 // K1: difference array
 // ---------------------------------------------------------------------------
 
+// Besides the difference array, every interval also updates the SUM of its tile of the difference
+// array (tileSum, a few MB that stay in L2): the prefix over those sums gives every tile of the scan
+// its starting value up front, so the scan below needs no inter-block chain at all.
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_diff (const SegDev* __restrict__ segs, int nseg, T* __restrict__ diff,
+k_diff (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg, T* __restrict__ diff,
+        T* __restrict__ tileSum,
         const uint32_t* __restrict__ iseg, const uint32_t* __restrict__ istart,
         const uint32_t* __restrict__ iend, const double* __restrict__ ival, uint64_t n)
 	{
@@ -44,7 +51,52 @@ k_diff (const SegDev* __restrict__ segs, int nseg, T* __restrict__ diff,
 	uint64_t b = ((uint64_t) e < p1 ? (uint64_t) e : p1) - p0;
 	T w = (ival != NULL) ? (T) ival[k] : (T) 1;
 	atomicAdd (diff + sd.lo + a, w);
-	if (b < len) atomicAdd (diff + sd.lo + b, (T) (-w));
+	const uint64_t ta = a / SCAN_TILE;
+	if (b < len)
+		{
+		atomicAdd (diff + sd.lo + b, (T) (-w));
+		const uint64_t tb = b / SCAN_TILE;
+		if (tb != ta)                              // same tile: the two updates cancel in the tile sum
+			{
+			atomicAdd (tileSum + base[sg] + ta, w);
+			atomicAdd (tileSum + base[sg] + tb, (T) (-w));
+			}
+		}
+	else atomicAdd (tileSum + base[sg] + ta, w);
+	}
+
+// exclusive prefix of the tile sums inside every segment (one block per segment)
+template <typename T>
+__global__ void __launch_bounds__(1024)
+k_tile_prefix (const uint64_t* __restrict__ base, const T* __restrict__ tileSum, T* __restrict__ tilePrefix)
+	{
+	__shared__ T s_w[32];
+	__shared__ T s_carry;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint64_t t0 = base[blockIdx.x], t1 = base[blockIdx.x + 1];
+	if (threadIdx.x == 0) s_carry = (T) 0;
+	__syncthreads ();
+	for (uint64_t c0 = t0; c0 < t1; c0 += 1024)
+		{
+		const uint64_t i = c0 + threadIdx.x;
+		const T v = (i < t1) ? tileSum[i] : (T) 0;
+		T inc = v;
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+			{
+			T up = warp_shfl_up<T> (inc, d);
+			if (lane >= d) inc += up;
+			}
+		if (lane == 31) s_w[warp] = inc;
+		__syncthreads ();
+		T wex = (T) 0, tot = (T) 0;
+		for (int w = 0; w < 32; w++) { if (w < warp) wex += s_w[w];  tot += s_w[w]; }
+		const T carry = s_carry;
+		if (i < t1) tilePrefix[i] = carry + wex + inc - v;
+		__syncthreads ();
+		if (threadIdx.x == 0) s_carry = carry + tot;
+		__syncthreads ();
+		}
 	}
 
 // ---------------------------------------------------------------------------
@@ -63,23 +115,24 @@ template <> struct Vec4<double>
 		{ double2 a = ldg_stream (p), b = ldg_stream (p + 2);  x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; }
 	};
 
-template <typename T> __device__ __forceinline__ T warp_shfl_up (T v, int d);
 template <> __device__ __forceinline__ int    warp_shfl_up<int>    (int v, int d)    { return __shfl_up_sync (0xffffffffu, v, d); }
 template <> __device__ __forceinline__ double warp_shfl_up<double> (double v, int d) { return shfl_up_f64 (v, d); }
-template <typename T> __device__ __forceinline__ T warp_shfl_idx (T v, int s);
 template <> __device__ __forceinline__ int    warp_shfl_idx<int>    (int v, int s)    { return __shfl_sync (0xffffffffu, v, s); }
 template <> __device__ __forceinline__ double warp_shfl_idx<double> (double v, int s) { return shfl_idx_f64 (v, s); }
 
 // MODE 0: out = scan ; MODE 1: out += scan
-template <typename T, int MODE>
+// CHAINED: the tile's starting value comes from the decoupled look-back (generic input);
+// otherwise it is read from tilePrefix (accumulate: known from the intervals themselves)
+template <typename T, int MODE, bool CHAINED>
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_scan_tiles (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
-              const T* __restrict__ in, double* __restrict__ out, ScanStatus<T> st)
+              const T* __restrict__ in, double* __restrict__ out, ScanStatus<T> st,
+              const T* __restrict__ tilePrefix)
 	{
 	__shared__ T s_warp[SCAN_WARPS];
 	__shared__ T s_excl;
 
-	const uint32_t tile = scan_take_ticket (st.ticket);
+	const uint32_t tile = CHAINED ? scan_take_ticket (st.ticket) : blockIdx.x;
 	int seg;  uint64_t tis;
 	tile_to_seg (base, nseg, tile, seg, tis);
 	const SegDev sd = segs[seg];
@@ -139,13 +192,19 @@ k_scan_tiles (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base
 		tileAgg += t;
 		}
 
-	if (threadIdx.x < 32)
+	T tileExcl;
+	if (CHAINED)
 		{
-		const T e = scan_lookback<T> (st, tile, tis == 0, tileAgg, (T) 0, [] (T a, T b) { return a + b; });
-		if (threadIdx.x == 0) s_excl = e;
+		if (threadIdx.x < 32)
+			{
+			const T e = scan_lookback<T> (st, tile, tis == 0, tileAgg, (T) 0, [] (T a, T b) { return a + b; });
+			if (threadIdx.x == 0) s_excl = e;
+			}
+		__syncthreads ();
+		tileExcl = s_excl;
 		}
-	__syncthreads ();
-	const T add = s_excl + warpExcl;
+	else tileExcl = tilePrefix[tile];
+	const T add = tileExcl + warpExcl;
 
 	#pragma unroll
 	for (int r = 0; r < SCAN_ROWS; r++)
@@ -183,8 +242,22 @@ static int launch_scan (gdsp_ctx* c, gdsp_layout* L, const T* in, double* out, i
 	GDSP_TRY (gdsp_ws (c, 0, scan_status_bytes<T> (tm.ntiles), &ws));
 	ScanStatus<T> st = scan_status_carve<T> (ws, tm.ntiles);
 	GDSP_CUDA (cudaMemsetAsync (ws, 0, scan_status_clear_bytes<T> (tm.ntiles), c->stream));
-	if (addTo) k_scan_tiles<T, 1><<<(unsigned) tm.ntiles, SCAN_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, in, out, st);
-	else       k_scan_tiles<T, 0><<<(unsigned) tm.ntiles, SCAN_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, in, out, st);
+	if (addTo) k_scan_tiles<T, 1, true><<<(unsigned) tm.ntiles, SCAN_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, in, out, st, NULL);
+	else       k_scan_tiles<T, 0, true><<<(unsigned) tm.ntiles, SCAN_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, in, out, st, NULL);
+	GDSP_KERNEL_CHECK ();
+	return GDSP_OK;
+	}
+
+// accumulate: tile sums (slot 0) were filled by k_diff
+template <typename T>
+static int launch_scan_prefixed (gdsp_ctx* c, gdsp_layout* L, const T* in, double* out, int addTo,
+                                 const TileMap& tm, T* tileSum, T* tilePrefix)
+	{
+	k_tile_prefix<T><<<L->nseg, 1024, 0, c->stream>>> (tm.d_base, tileSum, tilePrefix);
+	GDSP_KERNEL_CHECK ();
+	ScanStatus<T> st;  st.ticket = NULL;  st.rec = NULL;
+	if (addTo) k_scan_tiles<T, 1, false><<<(unsigned) tm.ntiles, SCAN_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, in, out, st, tilePrefix);
+	else       k_scan_tiles<T, 0, false><<<(unsigned) tm.ntiles, SCAN_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, in, out, st, tilePrefix);
 	GDSP_KERNEL_CHECK ();
 	return GDSP_OK;
 	}
@@ -199,31 +272,42 @@ extern "C" size_t gdsp_accumulate_work_bytes (const gdsp_layout* L, uint64_t buf
 	return (size_t) buffer_cells * (mode == GDSP_ACC_I32 ? sizeof (int) : sizeof (double));
 	}
 
-static int accumulate_begin (gdsp_ctx* c, uint64_t buffer_cells, void* work, int mode)
+struct AccTiles { TileMap tm;  void* tileSum;  void* tilePrefix; };
+
+static int accumulate_begin (gdsp_ctx* c, gdsp_layout* L, uint64_t buffer_cells, void* work, int mode, AccTiles* at)
 	{
-	size_t bytes = (size_t) buffer_cells * (mode == GDSP_ACC_I32 ? sizeof (int) : sizeof (double));
-	GDSP_CUDA (cudaMemsetAsync (work, 0, bytes, c->stream));
+	const size_t esz = (mode == GDSP_ACC_I32) ? sizeof (int) : sizeof (double);
+	GDSP_CUDA (cudaMemsetAsync (work, 0, (size_t) buffer_cells * esz, c->stream));
+	GDSP_TRY (gdsp_layout_tilemap (L, SCAN_TILE, &at->tm));
+	const size_t tb = ((at->tm.ntiles * esz + 255) / 256) * 256;
+	void* ws;
+	GDSP_TRY (gdsp_ws (c, 0, 2 * tb, &ws));
+	at->tileSum = ws;  at->tilePrefix = (char*) ws + tb;
+	GDSP_CUDA (cudaMemsetAsync (ws, 0, tb, c->stream));
 	return GDSP_OK;
 	}
 
-static int accumulate_chunk (gdsp_ctx* c, gdsp_layout* L, void* work, const uint32_t* d_seg,
+static int accumulate_chunk (gdsp_ctx* c, gdsp_layout* L, void* work, const AccTiles& at, const uint32_t* d_seg,
                              const uint32_t* d_start, const uint32_t* d_end, const double* d_val,
                              uint64_t n, int mode)
 	{
 	if (n == 0) return GDSP_OK;
 	unsigned blocks = (unsigned) ((n + 255) / 256);
 	if (mode == GDSP_ACC_I32)
-		k_diff<int><<<blocks, 256, 0, c->stream>>> (L->d, L->nseg, (int*) work, d_seg, d_start, d_end, d_val, n);
+		k_diff<int><<<blocks, 256, 0, c->stream>>> (L->d, at.tm.d_base, L->nseg, (int*) work, (int*) at.tileSum,
+		                                            d_seg, d_start, d_end, d_val, n);
 	else
-		k_diff<double><<<blocks, 256, 0, c->stream>>> (L->d, L->nseg, (double*) work, d_seg, d_start, d_end, d_val, n);
+		k_diff<double><<<blocks, 256, 0, c->stream>>> (L->d, at.tm.d_base, L->nseg, (double*) work, (double*) at.tileSum,
+		                                               d_seg, d_start, d_end, d_val, n);
 	GDSP_KERNEL_CHECK ();
 	return GDSP_OK;
 	}
 
-static int accumulate_finish (gdsp_ctx* c, gdsp_layout* L, double* sig, void* work, int mode, int addTo)
+static int accumulate_finish (gdsp_ctx* c, gdsp_layout* L, double* sig, void* work, const AccTiles& at, int mode, int addTo)
 	{
-	if (mode == GDSP_ACC_I32) return launch_scan<int>    (c, L, (const int*) work,    sig, addTo);
-	else                      return launch_scan<double> (c, L, (const double*) work, sig, addTo);
+	if (mode == GDSP_ACC_I32)
+		return launch_scan_prefixed<int> (c, L, (const int*) work, sig, addTo, at.tm, (int*) at.tileSum, (int*) at.tilePrefix);
+	return launch_scan_prefixed<double> (c, L, (const double*) work, sig, addTo, at.tm, (double*) at.tileSum, (double*) at.tilePrefix);
 	}
 
 extern "C" int gdsp_accumulate_dev (gdsp_ctx* c, const gdsp_layout* L_, double* sig, uint64_t buffer_cells,
@@ -235,9 +319,10 @@ extern "C" int gdsp_accumulate_dev (gdsp_ctx* c, const gdsp_layout* L_, double* 
 	GDSP_REQUIRE (c && L && sig && work, "gdsp_accumulate_dev: NULL argument");
 	GDSP_REQUIRE (mode == GDSP_ACC_I32 || mode == GDSP_ACC_F64, "gdsp_accumulate_dev: bad mode %d", mode);
 	GDSP_REQUIRE (n == 0 || (d_seg && d_start && d_end), "gdsp_accumulate_dev: NULL interval arrays");
-	GDSP_TRY (accumulate_begin (c, buffer_cells, work, mode));
-	GDSP_TRY (accumulate_chunk (c, L, work, d_seg, d_start, d_end, d_val, n, mode));
-	return accumulate_finish (c, L, sig, work, mode, addTo);
+	AccTiles at;
+	GDSP_TRY (accumulate_begin (c, L, buffer_cells, work, mode, &at));
+	GDSP_TRY (accumulate_chunk (c, L, work, at, d_seg, d_start, d_end, d_val, n, mode));
+	return accumulate_finish (c, L, sig, work, at, mode, addTo);
 	}
 
 // host arrays: streamed through the context's two pinned staging buffers (or
@@ -251,7 +336,8 @@ extern "C" int gdsp_accumulate_host (gdsp_ctx* c, const gdsp_layout* L_, double*
 	GDSP_REQUIRE (c && L && sig && work, "gdsp_accumulate_host: NULL argument");
 	GDSP_REQUIRE (mode == GDSP_ACC_I32 || mode == GDSP_ACC_F64, "gdsp_accumulate_host: bad mode %d", mode);
 	GDSP_REQUIRE (n == 0 || (h_seg && h_start && h_end), "gdsp_accumulate_host: NULL interval arrays");
-	GDSP_TRY (accumulate_begin (c, buffer_cells, work, mode));
+	AccTiles at;
+	GDSP_TRY (accumulate_begin (c, L, buffer_cells, work, mode, &at));
 
 	const uint64_t CHUNK = 8u << 20;                        // intervals per chunk
 	const size_t   rec   = 3 * sizeof (uint32_t) + (h_val ? sizeof (double) : 0);
@@ -262,8 +348,8 @@ extern "C" int gdsp_accumulate_host (gdsp_ctx* c, const gdsp_layout* L_, double*
 	void* dws;
 	GDSP_TRY (gdsp_ws (c, 1, 2 * cbytes, &dws));
 
-	cudaPointerAttributes at;
-	bool pinnedSrc = (cudaPointerGetAttributes (&at, h_seg) == cudaSuccess) && (at.type == cudaMemoryTypeHost);
+	cudaPointerAttributes pattr;
+	bool pinnedSrc = (cudaPointerGetAttributes (&pattr, h_seg) == cudaSuccess) && (pattr.type == cudaMemoryTypeHost);
 	cudaGetLastError ();
 	if (!pinnedSrc && c->pinned_bytes < cbytes)
 		{
@@ -306,9 +392,9 @@ extern "C" int gdsp_accumulate_host (gdsp_ctx* c, const gdsp_layout* L_, double*
 			GDSP_CUDA (cudaMemcpyAsync (dbase, hp, tot, cudaMemcpyHostToDevice, c->stream));
 			GDSP_CUDA (cudaEventRecord (c->pinned_ev[buf], c->stream));
 			}
-		GDSP_TRY (accumulate_chunk (c, L, work, d_seg, d_start, d_end, d_val, m, mode));
+		GDSP_TRY (accumulate_chunk (c, L, work, at, d_seg, d_start, d_end, d_val, m, mode));
 		}
-	return accumulate_finish (c, L, sig, work, mode, addTo);
+	return accumulate_finish (c, L, sig, work, at, mode, addTo);
 	}
 
 extern "C" int gdsp_cumulative_sum (gdsp_ctx* c, const gdsp_layout* L_, const double* in, double* out)

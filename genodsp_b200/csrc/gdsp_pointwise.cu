@@ -53,51 +53,93 @@ __device__ __forceinline__ int64_t ivl_find (const uint64_t* __restrict__ start,
 	return lo - 1;
 	}
 
-__device__ __forceinline__ double pw_apply (const PwProgram& P, double v, uint64_t g,
-                                            const int64_t* s_klo, const int64_t* s_khi)
+// Apply the whole program to PW_VEC cells held in registers.  The operator
+// loop is the OUTER loop, so the opcode dispatch (a warp-uniform switch) is paid
+// once per PW_VEC cells instead of once per cell.
+#define PW_VEC 8
+
+__device__ __forceinline__ void pw_apply_vec (const PwProgram& P, double (&v)[PW_VEC], const uint64_t (&g)[PW_VEC],
+                                              const int64_t* s_klo, const int64_t* s_khi)
 	{
 	for (int i = 0; i < P.nops; i++)
 		{
 		const PwOpDev& op = P.ops[i];
+		const double a = op.a, b = op.b, c = op.c;
 		switch (op.code)
 			{
-			case GDSP_PW_BINARIZE_GT:  v = (v >  op.a) ? op.b : op.c;  break;
-			case GDSP_PW_BINARIZE_GE:  v = (v >= op.a) ? op.b : op.c;  break;
-			case GDSP_PW_ADDCONST:     v = __dadd_rn (v, op.a);        break;
-			case GDSP_PW_ABS:          if (v < 0) v = -v;              break;
-			case GDSP_PW_CLIP_MIN:     if (v < op.a) v = op.a;         break;
-			case GDSP_PW_CLIP_MAX:     if (v > op.a) v = op.a;         break;
-			case GDSP_PW_CLIP_BOTH:    if (v < op.a) v = op.a; else if (v > op.b) v = op.b;  break;
+			case GDSP_PW_BINARIZE_GT:
+				#pragma unroll
+				for (int e = 0; e < PW_VEC; e++) v[e] = (v[e] >  a) ? b : c;
+				break;
+			case GDSP_PW_BINARIZE_GE:
+				#pragma unroll
+				for (int e = 0; e < PW_VEC; e++) v[e] = (v[e] >= a) ? b : c;
+				break;
+			case GDSP_PW_ADDCONST:
+				#pragma unroll
+				for (int e = 0; e < PW_VEC; e++) v[e] = __dadd_rn (v[e], a);
+				break;
+			case GDSP_PW_ABS:
+				#pragma unroll
+				for (int e = 0; e < PW_VEC; e++) if (v[e] < 0) v[e] = -v[e];
+				break;
+			case GDSP_PW_CLIP_MIN:
+				#pragma unroll
+				for (int e = 0; e < PW_VEC; e++) if (v[e] < a) v[e] = a;
+				break;
+			case GDSP_PW_CLIP_MAX:
+				#pragma unroll
+				for (int e = 0; e < PW_VEC; e++) if (v[e] > a) v[e] = a;
+				break;
+			case GDSP_PW_CLIP_BOTH:
+				#pragma unroll
+				for (int e = 0; e < PW_VEC; e++) { if (v[e] < a) v[e] = a; else if (v[e] > b) v[e] = b; }
+				break;
 			case GDSP_PW_ERASE:
 				{
 				const bool hmin = op.flags & GDSP_PW_ERASE_HAVE_MIN, hmax = op.flags & GDSP_PW_ERASE_HAVE_MAX;
-				bool kill;
-				if (op.flags & GDSP_PW_ERASE_KEEP_INSIDE) kill = (hmin && v < op.a) || (hmax && v > op.b);
-				else                                      kill = (!hmin || v >= op.a) && (!hmax || v <= op.b);
-				if (kill) v = op.c;
+				const bool keepIn = op.flags & GDSP_PW_ERASE_KEEP_INSIDE;
+				#pragma unroll
+				for (int e = 0; e < PW_VEC; e++)
+					{
+					bool kill;
+					if (keepIn) kill = (hmin && v[e] < a) || (hmax && v[e] > b);
+					else        kill = (!hmin || v[e] >= a) && (!hmax || v[e] <= b);
+					if (kill) v[e] = c;
+					}
 				break;
 				}
-			case GDSP_PW_INVERT:         v = __dsub_rn (op.a, v);      break;
-			case GDSP_PW_NONZERO_TO_ONE: if (v != 0.0) v = 1.0;        break;
+			case GDSP_PW_INVERT:
+				#pragma unroll
+				for (int e = 0; e < PW_VEC; e++) v[e] = __dsub_rn (a, v[e]);
+				break;
+			case GDSP_PW_NONZERO_TO_ONE:
+				#pragma unroll
+				for (int e = 0; e < PW_VEC; e++) if (v[e] != 0.0) v[e] = 1.0;
+				break;
 			default:
 				{
-				// interval-table operators
-				int64_t k = ivl_find (op.start, s_klo[i], s_khi[i], g);
-				bool inside = (k >= s_klo[i]) && (g < op.end[k]);
-				switch (op.code)
+				// interval-table operators: one search per cell inside the tile's slice of the table
+				const int64_t klo = s_klo[i], khi = s_khi[i];
+				#pragma unroll
+				for (int e = 0; e < PW_VEC; e++)
 					{
-					case GDSP_PW_IVL_ADD: if (inside) v = __dadd_rn (v, op.val[k]);  break;
-					case GDSP_PW_IVL_SUB: if (inside) v = __dsub_rn (v, op.val[k]);  break;
-					case GDSP_PW_IVL_MUL: v = inside ? __dmul_rn (v, op.val[k]) : op.a;  break;
-					case GDSP_PW_IVL_DIV: v = inside ? __ddiv_rn (v, op.val[k]) : ((v >= 0) ? op.a : -op.a);  break;
-					case GDSP_PW_IVL_SET: if (inside) v = op.a;  break;
-					case GDSP_PW_IVL_SET_OUTSIDE: if (!inside) v = op.a;  break;
-					case GDSP_PW_IVL_ASSIGN: if (inside) v = op.val[k];  break;
+					const int64_t k = ivl_find (op.start, klo, khi, g[e]);
+					const bool inside = (k >= klo) && (g[e] < op.end[k]);
+					switch (op.code)
+						{
+						case GDSP_PW_IVL_ADD: if (inside) v[e] = __dadd_rn (v[e], op.val[k]);  break;
+						case GDSP_PW_IVL_SUB: if (inside) v[e] = __dsub_rn (v[e], op.val[k]);  break;
+						case GDSP_PW_IVL_MUL: v[e] = inside ? __dmul_rn (v[e], op.val[k]) : a;  break;
+						case GDSP_PW_IVL_DIV: v[e] = inside ? __ddiv_rn (v[e], op.val[k]) : ((v[e] >= 0) ? a : -a);  break;
+						case GDSP_PW_IVL_SET: if (inside) v[e] = a;  break;
+						case GDSP_PW_IVL_SET_OUTSIDE: if (!inside) v[e] = a;  break;
+						case GDSP_PW_IVL_ASSIGN: if (inside) v[e] = op.val[k];  break;
+						}
 					}
 				}
 			}
 		}
-	return v;
 	}
 
 __global__ void __launch_bounds__(PW_THREADS)
@@ -126,18 +168,31 @@ k_pointwise (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base,
 		__syncthreads ();
 		}
 
-	// t0 is even (segment starts are 64-aligned): 128-bit accesses on whole pairs
-	for (uint64_t i = t0 + 2 * threadIdx.x; i < t1; i += 2 * PW_THREADS)
+	// PW_TILE = PW_THREADS * 16: every thread owns PW_VEC/2 pairs per half tile, pair p of the
+	// warp-wide access q at cell t0 + 2*(q*PW_THREADS + tid): 128-bit coalesced accesses
+	#pragma unroll 1
+	for (uint32_t half = 0; half < PW_TILE / (PW_THREADS * PW_VEC); half++)
 		{
-		if (i + 1 < t1)
+		double   v[PW_VEC];
+		uint64_t g[PW_VEC];
+		const uint64_t h0 = t0 + (uint64_t) half * (PW_THREADS * PW_VEC);
+		if (h0 >= t1) break;
+		#pragma unroll
+		for (int q = 0; q < PW_VEC / 2; q++)
 			{
-			double2 v = ldg_stream (in + i);
-			v.x = pw_apply (P, v.x, i,     s_klo, s_khi);
-			v.y = pw_apply (P, v.y, i + 1, s_klo, s_khi);
-			stg_stream (out + i, v);
+			const uint64_t i = h0 + 2 * ((uint64_t) q * PW_THREADS + threadIdx.x);
+			g[2*q] = i;  g[2*q+1] = i + 1;
+			if (i + 1 < t1) { double2 x = ldg_stream (in + i);  v[2*q] = x.x;  v[2*q+1] = x.y; }
+			else            { v[2*q] = (i < t1) ? in[i] : 0.0;  v[2*q+1] = 0.0; }
 			}
-		else
-			out[i] = pw_apply (P, in[i], i, s_klo, s_khi);
+		pw_apply_vec (P, v, g, s_klo, s_khi);
+		#pragma unroll
+		for (int q = 0; q < PW_VEC / 2; q++)
+			{
+			const uint64_t i = g[2*q];
+			if (i + 1 < t1) stg_stream (out + i, make_double2 (v[2*q], v[2*q+1]));
+			else if (i < t1) out[i] = v[2*q];
+			}
 		}
 	}
 
