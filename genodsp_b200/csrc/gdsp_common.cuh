@@ -168,6 +168,45 @@ __device__ __forceinline__ void stg_stream (double* p, double2 v)
 	              :: "l"(p), "d"(v.x), "d"(v.y) : "memory");
 	}
 
+// Stage cells [g0, g0+count) of `in` into shared memory (index j -> smem[j + (j >> PADSHIFT)], or
+// smem[j] when PADSHIFT == 0); cells outside the readable range [dlo,dhi) get `neutral`.
+// Interior tiles (the whole range readable -- all but the first/last tile of a chromosome) take a
+// branch-free path with 128-bit loads; edge tiles check every cell.
+template <int PADSHIFT>
+__device__ __forceinline__ uint32_t stage_idx (uint32_t j) { return PADSHIFT ? j + (j >> PADSHIFT) : j; }
+
+template <int PADSHIFT>
+__device__ __forceinline__ void stage_tile (double* smem, const double* __restrict__ in, int64_t g0, uint32_t count,
+                                            uint64_t dlo, uint64_t dhi, double neutral)
+	{
+	const uint32_t tid = threadIdx.x, nt = blockDim.x;
+	if (g0 >= (int64_t) dlo && g0 + (int64_t) count <= (int64_t) dhi)
+		{
+		const double* p = in + g0;
+		const uint32_t j0 = (uint32_t) (g0 & 1);                 // first cell on a 16-byte boundary
+		const uint32_t npair = (count - j0) >> 1;
+		if (j0 && tid == 0) smem[stage_idx<PADSHIFT> (0)] = __ldg (p);
+		for (uint32_t q = tid; q < npair; q += nt)
+			{
+			const uint32_t j = j0 + 2 * q;
+			const double2 v = __ldg (reinterpret_cast<const double2*> (p + j));
+			smem[stage_idx<PADSHIFT> (j)]     = v.x;
+			smem[stage_idx<PADSHIFT> (j + 1)] = v.y;
+			}
+		if (((count - j0) & 1) && tid == nt - 1) smem[stage_idx<PADSHIFT> (count - 1)] = __ldg (p + count - 1);
+		}
+	else
+		{
+		for (uint32_t j = tid; j < count; j += nt)
+			{
+			const int64_t g = g0 + (int64_t) j;
+			double v = neutral;
+			if (g >= (int64_t) dlo && g < (int64_t) dhi) v = __ldg (in + g);
+			smem[stage_idx<PADSHIFT> (j)] = v;
+			}
+		}
+	}
+
 // order-preserving 64-bit key of a double: a<b  <=>  key(a)<key(b) for all
 // non-NaN a,b (with -0.0 just below +0.0)
 __device__ __forceinline__ uint64_t f64_key (double v)

@@ -51,13 +51,8 @@ k_extrema (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, i
 	const uint32_t count = nOut + Wn - 1;
 	const int64_t  g0   = (int64_t) t0 - (int64_t) reachL;
 
-	for (uint32_t j = threadIdx.x; j < SCAP; j += MM_THREADS)
-		{
-		double v = NEUTRAL;
-		int64_t g = g0 + (int64_t) j;
-		if (j < count && g >= (int64_t) sd.dlo && g < (int64_t) sd.dhi) v = __ldg (in + g);
-		A[mm_pad<LOGE> (j)] = v;
-		}
+	stage_tile<LOGE> (A, in, g0, count, sd.dlo, sd.dhi, NEUTRAL);
+	for (uint32_t j = count + threadIdx.x; j < SCAP; j += MM_THREADS) A[mm_pad<LOGE> (j)] = NEUTRAL;
 	__syncthreads ();
 
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -191,13 +186,7 @@ k_extrema_small (const SegDev* __restrict__ segs, const uint64_t* __restrict__ b
 	const uint32_t nOut = (uint32_t) ((sd.hi - t0 < MS_TILE) ? (sd.hi - t0) : MS_TILE);
 	const int64_t  g0   = (int64_t) t0 - (int64_t) reachL;      // staged cell j <-> in[g0 + j]
 
-	for (uint32_t j = threadIdx.x; j < XN; j += MS_THREADS)
-		{
-		const int64_t g = g0 + (int64_t) j;
-		double v = NEUTRAL;
-		if (g >= (int64_t) sd.dlo && g < (int64_t) sd.dhi) v = __ldg (in + g);
-		s_x[ms_pad (j)] = v;
-		}
+	stage_tile<3> (s_x, in, g0, XN, sd.dlo, sd.dhi, NEUTRAL);
 	__syncthreads ();
 
 	// A[j] for the 8 cells of this thread, by doubling
@@ -219,18 +208,18 @@ k_extrema_small (const SegDev* __restrict__ segs, const uint64_t* __restrict__ b
 	__syncthreads ();
 
 	const uint32_t shift = Wn - P;                              // 0 <= shift < P <= MS_MARGIN
-	for (uint32_t c = 2 * threadIdx.x; c < nOut; c += 2 * MS_THREADS)
+	// consecutive lanes take consecutive outputs: conflict-free table reads, 256-byte coalesced stores
+	double* o = out + t0;
+	#pragma unroll 4
+	for (uint32_t c = threadIdx.x; c < nOut; c += MS_THREADS)
 		{
-		double w0 = ext<WANT_MAX> (s_a[ms_pad (c)],     s_a[ms_pad (c + shift)]);
-		double w1 = ext<WANT_MAX> (s_a[ms_pad (c + 1)], s_a[ms_pad (c + 1 + shift)]);
+		double w = ext<WANT_MAX> (s_a[ms_pad (c)], s_a[ms_pad (c + shift)]);
 		if (MODE == 1)
 			{
-			const double v0 = s_x[ms_pad (c + reachL)], v1 = s_x[ms_pad (c + 1 + reachL)];
-			w0 = (WANT_MAX ? (w0 > v0) : (w0 < v0)) ? fill : v0;
-			w1 = (WANT_MAX ? (w1 > v1) : (w1 < v1)) ? fill : v1;
+			const double v = s_x[ms_pad (c + reachL)];
+			w = (WANT_MAX ? (w > v) : (w < v)) ? fill : v;
 			}
-		if (c + 1 < nOut) stg_stream (out + t0 + c, make_double2 (w0, w1));
-		else              out[t0 + c] = w0;
+		o[c] = w;
 		}
 	}
 

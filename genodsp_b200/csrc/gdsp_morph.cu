@@ -49,13 +49,15 @@ k_morph_pack (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base
 
 	long long first = -1, last = -1;
 	// warp `warp` packs words warp, warp+8, ... of the tile
+	// every warp packs MO_WORDS/8 = 32 words; the 32 loads of a lane are independent
+	#pragma unroll 8
 	for (uint32_t w = warp; w < MO_WORDS; w += MO_THREADS / 32)
 		{
 		const uint32_t c = w * 32 + lane;
 		bool mark = false;
 		if (c < n)
 			{
-			const double v = sig[t0 + c];
+			const double v = __ldg (sig + t0 + c);
 			if      (kind == GDSP_MORPH_CLOSE)  mark = !(v <= T);
 			else if (kind == GDSP_MORPH_DILATE) mark = (sd.pos0 == 0 && t0 + c == sd.lo) ? (v > T) : !(v <= T);
 			else                                mark = !(v > T);

@@ -575,43 +575,54 @@ k_pct_pass (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, 
 		const SegDev sd = segs[seg];
 		const uint64_t t0 = sd.lo + tis * PCT_TILE;
 		uint64_t t1 = t0 + PCT_TILE;  if (t1 > sd.hi) t1 = sd.hi;
-		for (uint64_t i0 = t0; i0 < t1; i0 += 256)
+		for (uint64_t i0 = t0; i0 < t1; i0 += 256 * 4)
 			{
-			const uint64_t i = i0 + threadIdx.x;
-			bool q = (i < t1);
-			double v = 0.0;
-			if (q && stride > 1) q = (((uint64_t) sd.pos0 + (i - sd.lo)) % stride) == 0;
-			if (q) { v = sig[i];  q = !(v < mn) && !(v > mx); }
-			int reg = 0;  bool isB = false;
-			if (q) reg = pct_region (s_key, nb, f64_key (v), isB);
-			if (SMALL)
+			// four independent loads per thread before any of the warp votes below
+			double vv[4];  bool qq[4];
+			#pragma unroll
+			for (int u = 0; u < 4; u++)
 				{
-				if (q)
-					{
-					#pragma unroll
-					for (int r = 0; r < 5; r++) mine[r] += (reg == r);
-					}
+				const uint64_t i = i0 + (uint64_t) u * 256 + threadIdx.x;
+				qq[u] = (i < t1);
+				if (qq[u] && stride > 1) qq[u] = (((uint64_t) sd.pos0 + (i - sd.lo)) % stride) == 0;
+				vv[u] = qq[u] ? sig[i] : 0.0;
 				}
-			else
+			#pragma unroll
+			for (int u = 0; u < 4; u++)
 				{
-				const unsigned qm = __ballot_sync (0xffffffffu, q);
-				if (q)
+				const double v = vv[u];
+				bool q = qq[u] && !(v < mn) && !(v > mx);
+				int reg = 0;  bool isB = false;
+				if (q) reg = pct_region (s_key, nb, f64_key (v), isB);
+				if (SMALL)
 					{
-					const unsigned peers = __match_any_sync (qm, reg);
-					if (lane == __ffs (peers) - 1) atomicAdd (&s_cnt[reg], __popc (peers));
+					if (q)
+						{
+						#pragma unroll
+						for (int r = 0; r < 5; r++) mine[r] += (reg == r);
+						}
 					}
-				}
-			const bool c = q && !isB && B.compact[reg >> 1];
-			const unsigned cm = __ballot_sync (0xffffffffu, c);
-			if (cm)
-				{
-				unsigned long long b0 = 0;
-				if (lane == __ffs (cm) - 1) b0 = atomicAdd (ncand, (unsigned long long) __popc (cm));
-				b0 = __shfl_sync (0xffffffffu, b0, __ffs (cm) - 1);
-				if (c)
+				else
 					{
-					const unsigned long long slot = b0 + __popc (cm & ((1u << lane) - 1u));
-					if (slot < cap) cand[slot] = v;
+					const unsigned qm = __ballot_sync (0xffffffffu, q);
+					if (q)
+						{
+						const unsigned peers = __match_any_sync (qm, reg);
+						if (lane == __ffs (peers) - 1) atomicAdd (&s_cnt[reg], __popc (peers));
+						}
+					}
+				const bool c = q && !isB && B.compact[reg >> 1];
+				const unsigned cm = __ballot_sync (0xffffffffu, c);
+				if (cm)
+					{
+					unsigned long long b0 = 0;
+					if (lane == __ffs (cm) - 1) b0 = atomicAdd (ncand, (unsigned long long) __popc (cm));
+					b0 = __shfl_sync (0xffffffffu, b0, __ffs (cm) - 1);
+					if (c)
+						{
+						const unsigned long long slot = b0 + __popc (cm & ((1u << lane) - 1u));
+						if (slot < cap) cand[slot] = v;
+						}
 					}
 				}
 			}

@@ -61,7 +61,7 @@ k_sliding_sum (const SegDev* __restrict__ segs, const uint64_t* __restrict__ bas
 	const uint32_t reachL = W - 1 - h;
 	const uint32_t count  = n + W - 1;
 
-	stage_zero_padded<0> (P, in, (int64_t) t0 - (int64_t) reachL, count, sd.dlo, sd.dhi);
+	stage_tile<0> (P, in, (int64_t) t0 - (int64_t) reachL, count, sd.dlo, sd.dhi, 0.0);
 	__syncthreads ();
 
 	// each thread owns `strip` consecutive cells (strip is odd: conflict-free 64-bit accesses)
@@ -268,8 +268,7 @@ k_smooth (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, in
 		__syncthreads ();
 		for (uint32_t k = threadIdx.x; k < kn; k += blockDim.x) s_w[k] = taps[kc + k];
 		// staged cell j  <->  input index t0 - h + kc + j ; need j in [0, SM_TILE + kn - 1 + 8)
-		stage_zero_padded<3> (s_x, in, (int64_t) t0 - (int64_t) h + (int64_t) kc,
-		                      SM_TILE + kn + 8, sd.dlo, sd.dhi);
+		stage_tile<3> (s_x, in, (int64_t) t0 - (int64_t) h + (int64_t) kc, SM_TILE + kn + 8, sd.dlo, sd.dhi, 0.0);
 		__syncthreads ();
 
 		double x[SM_R], y[SM_R];
