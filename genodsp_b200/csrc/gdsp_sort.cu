@@ -52,11 +52,14 @@ __device__ __forceinline__ uint64_t out_cell (const OutMap& om, uint64_t pos)
 // bitwise OR / AND of all keys: a digit on which OR and AND agree is constant
 // ---------------------------------------------------------------------------
 
+#define ZERO_KEY 0x8000000000000000ull          // f64_key(+0.0)
+
+// res[0] |= keys, res[1] &= keys, res[2] += #(+0.0), res[3] += #(keys below +0.0)
 __global__ void __launch_bounds__(256)
 k_sort_orand (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg, uint64_t ntiles,
               const double* __restrict__ in, unsigned long long* __restrict__ res)
 	{
-	unsigned long long o = 0ull, a = ~0ull;
+	unsigned long long o = 0ull, a = ~0ull, nz = 0ull, nneg = 0ull;
 	for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x)
 		{
 		int seg;  uint64_t tis;
@@ -68,6 +71,7 @@ k_sort_orand (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base
 			{
 			unsigned long long k = f64_key (in[i]);
 			o |= k;  a &= k;
+			nz += (k == ZERO_KEY);  nneg += (k < ZERO_KEY);
 			}
 		}
 	#pragma unroll
@@ -75,8 +79,74 @@ k_sort_orand (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base
 		{
 		o |= __shfl_xor_sync (0xffffffffu, o, d);
 		a &= __shfl_xor_sync (0xffffffffu, a, d);
+		nz   += __shfl_xor_sync (0xffffffffu, nz, d);
+		nneg += __shfl_xor_sync (0xffffffffu, nneg, d);
 		}
-	if ((threadIdx.x & 31) == 0) { atomicOr (&res[0], o);  atomicAnd (&res[1], a); }
+	if ((threadIdx.x & 31) == 0)
+		{
+		atomicOr (&res[0], o);  atomicAnd (&res[1], a);
+		if (nz)   atomicAdd (&res[2], nz);
+		if (nneg) atomicAdd (&res[3], nneg);
+		}
+	}
+
+// copy every cell that is not +0.0 to out[] (any order; they get sorted next)
+__global__ void __launch_bounds__(256)
+k_sort_compact_nonzero (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg, uint64_t ntiles,
+                        const double* __restrict__ in, double* __restrict__ out, unsigned long long* __restrict__ counter)
+	{
+	const int lane = threadIdx.x & 31;
+	for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x)
+		{
+		int seg;  uint64_t tis;
+		tile_to_seg (base, nseg, t, seg, tis);
+		const SegDev sd = segs[seg];
+		const uint64_t t0 = sd.lo + tis * SORT_TILE;
+		uint64_t t1 = t0 + SORT_TILE;  if (t1 > sd.hi) t1 = sd.hi;
+		for (uint64_t i0 = t0; i0 < t1; i0 += 256 * 4)
+			{
+			double v[4];  bool keep[4];
+			#pragma unroll
+			for (int u = 0; u < 4; u++)
+				{
+				const uint64_t i = i0 + (uint64_t) u * 256 + threadIdx.x;
+				v[u] = (i < t1) ? in[i] : 0.0;
+				keep[u] = (i < t1) && (f64_key (v[u]) != ZERO_KEY);
+				}
+			#pragma unroll
+			for (int u = 0; u < 4; u++)
+				{
+				const unsigned m = __ballot_sync (0xffffffffu, keep[u]);
+				if (m == 0) continue;
+				unsigned long long b0 = 0;
+				if (lane == __ffs (m) - 1) b0 = atomicAdd (counter, (unsigned long long) __popc (m));
+				b0 = __shfl_sync (0xffffffffu, b0, __ffs (m) - 1);
+				if (keep[u]) out[b0 + __popc (m & ((1u << lane) - 1u))] = v[u];
+				}
+			}
+		}
+	}
+
+// sorted genome = [negatives (sorted)] [+0.0 x nZero] [positives (sorted)]: cell at sorted position p
+__global__ void __launch_bounds__(256)
+k_sort_fill_with_zeros (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
+                        const uint64_t* __restrict__ prefix, const double* __restrict__ sorted,
+                        unsigned long long nNeg, unsigned long long nZero, double* __restrict__ out)
+	{
+	int seg;  uint64_t tis;
+	tile_to_seg (base, nseg, blockIdx.x, seg, tis);
+	const SegDev sd = segs[seg];
+	const uint64_t t0 = sd.lo + tis * SORT_TILE;
+	uint64_t t1 = t0 + SORT_TILE;  if (t1 > sd.hi) t1 = sd.hi;
+	const uint64_t p0 = prefix[seg] + (t0 - sd.lo);
+	for (uint64_t i = t0 + threadIdx.x; i < t1; i += 256)
+		{
+		const uint64_t p = p0 + (i - t0);
+		double v = 0.0;
+		if (p < nNeg) v = sorted[p];
+		else if (p >= nNeg + nZero) v = sorted[p - nZero];
+		out[i] = v;
+		}
 	}
 
 // ---------------------------------------------------------------------------
@@ -385,7 +455,7 @@ static int radix_sort (gdsp_ctx* c, const SortPlan& inPlan, const SortPlan& linP
                        double* a, double* b, const OutMap& finalMap, const SortScratch& sc,
                        double** resultBuf, int* passesRun)
 	{
-	unsigned long long init[2] = { 0ull, ~0ull };
+	unsigned long long init[4] = { 0ull, ~0ull, 0ull, 0ull };
 	GDSP_CUDA (cudaMemcpyAsync (sc.orand, init, sizeof (init), cudaMemcpyHostToDevice, c->stream));
 	int grid = c->sm_count * 8;
 	if ((uint64_t) grid > inPlan.ntiles) grid = (int) inPlan.ntiles;
@@ -462,6 +532,39 @@ extern "C" int gdsp_sort_genome (gdsp_ctx* c, const gdsp_layout* L_, double* sig
 	prefix[L->nseg] = acc;
 	GDSP_CUDA (cudaMemcpyAsync (sc.prefix, prefix.data (), sizeof (uint64_t) * (L->nseg + 1), cudaMemcpyHostToDevice, c->stream));
 	SortPlan inPlan;  inPlan.segs = L->d;  inPlan.base = tm.d_base;  inPlan.nseg = L->nseg;  inPlan.ntiles = tm.ntiles;
+
+	// Genomic signals are often mostly zeros (uncovered bases, thresholded or peak-picked tracks).
+	// One pass counts the cells that are exactly +0.0; when they are the majority only the other
+	// cells are sorted and the zeros are written back as a block.
+	unsigned long long init[4] = { 0ull, ~0ull, 0ull, 0ull }, st[4];
+	GDSP_CUDA (cudaMemcpyAsync (sc.orand, init, sizeof (init), cudaMemcpyHostToDevice, c->stream));
+	int grid = c->sm_count * 8;
+	if ((uint64_t) grid > tm.ntiles) grid = (int) tm.ntiles;
+	k_sort_orand<<<grid, 256, 0, c->stream>>> (L->d, tm.d_base, L->nseg, tm.ntiles, sig, sc.orand);
+	GDSP_KERNEL_CHECK ();
+	GDSP_CUDA (cudaMemcpyAsync (st, sc.orand, sizeof (st), cudaMemcpyDeviceToHost, c->stream));
+	GDSP_CUDA (cudaStreamSynchronize (c->stream));
+	const uint64_t nZero = st[2], nNeg = st[3], nOther = L->cells - nZero;
+	if (nZero * 2 >= L->cells && 2 * nOther + 64 <= buffer_cells)
+		{
+		*h_result_in_tmp = 0;
+		if (nOther == 0) return GDSP_OK;                      // all zeros: already sorted
+		unsigned long long* d_counter = sc.orand + 8;
+		GDSP_CUDA (cudaMemsetAsync (d_counter, 0, 8, c->stream));
+		k_sort_compact_nonzero<<<grid, 256, 0, c->stream>>> (L->d, tm.d_base, L->nseg, tm.ntiles, sig, tmp, d_counter);
+		GDSP_KERNEL_CHECK ();
+		SortPlan lp;
+		GDSP_TRY (make_lin_plan (c, sc, nOther, &lp));
+		OutMap lin;  lin.nseg = 0;  lin.prefix = NULL;  lin.segs = NULL;
+		double* sorted = NULL;  int passes = 0;
+		double* bufB = tmp + ((nOther + 63) / 64) * 64;
+		GDSP_TRY (radix_sort (c, lp, lp, tmp, tmp, bufB, lin, sc, &sorted, &passes));
+		k_sort_fill_with_zeros<<<(unsigned) tm.ntiles, 256, 0, c->stream>>> (L->d, tm.d_base, L->nseg, sc.prefix, sorted,
+		        nNeg, nZero, sig);
+		GDSP_KERNEL_CHECK ();
+		return GDSP_OK;
+		}
+
 	SortPlan linPlan;
 	GDSP_TRY (make_lin_plan (c, sc, L->cells, &linPlan));
 	OutMap fm;  fm.nseg = L->nseg;  fm.prefix = sc.prefix;  fm.segs = L->d;

@@ -330,6 +330,170 @@ k_smooth (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, in
 	}
 
 // ---------------------------------------------------------------------------
+// k_smooth_pipe: the same FIR for W <= SP_MAXW as a PERSISTENT kernel whose
+// tiles arrive through the TMA engine.  Each CTA loops over tiles; while it
+// computes tile i from one shared-memory buffer, one thread has already issued
+// a 1-D bulk async copy (cp.async.bulk.shared::cluster.global with an mbarrier
+// transaction count; SASS UBLKCP) of tile i+1 into the other buffer, so the
+// FP64 pipe never waits for global memory.  The staged layout is linear (what a
+// bulk copy produces); every thread owns SP_R = 9 consecutive outputs, an ODD
+// strip, which makes the stride-9 window loads bank-conflict free without
+// padding.  Tiles that touch a chromosome end (or the buffer start) are staged
+// by hand with zero fill instead.
+// ---------------------------------------------------------------------------
+
+#define SP_THREADS 128
+#define SP_R       9
+#define SP_TILE    (SP_THREADS * SP_R)           // 1152 outputs per tile
+#define SP_MAXW    513
+#define SP_BUF     ((SP_TILE + SP_MAXW + 2 * SP_R + 17) & ~15)   // cells per staging buffer (multiple of 16: 128-byte aligned buffers)
+
+__global__ void __launch_bounds__(SP_THREADS)
+k_smooth_pipe (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg, uint64_t ntiles,
+               const double* __restrict__ in, double* __restrict__ out,
+               uint32_t W, const double* __restrict__ taps)
+	{
+	__shared__ __align__(128) double s_buf[2][SP_BUF];
+	__shared__ double s_w[SP_MAXW + SP_R];
+	__shared__ __align__(8) uint64_t s_bar[2];
+
+	const uint32_t h = (W - 1) / 2;
+	const uint32_t need = SP_TILE + W - 1 + SP_R;          // staged cells a tile reads (incl. the look-ahead loads)
+
+	for (uint32_t k = threadIdx.x; k < W + SP_R; k += SP_THREADS) s_w[k] = (k < W) ? taps[k] : 0.0;
+	if (threadIdx.x == 0)
+		{
+		mbar_init (&s_bar[0], 1);
+		mbar_init (&s_bar[1], 1);
+		mbar_fence_init ();
+		}
+	__syncthreads ();
+
+	// stage tile t into buffer b: returns (through shared state) how it was staged
+	// kind 0 = bulk copy in flight on s_bar[b]; kind 1 = staged by hand (already complete after the sync)
+	auto tile_geom = [&] (uint64_t t, SegDev& sd, uint64_t& t0, uint32_t& n, int64_t& g0, bool& interior)
+		{
+		int seg;  uint64_t tis;
+		tile_to_seg (base, nseg, t, seg, tis);
+		sd = segs[seg];
+		t0 = sd.lo + tis * SP_TILE;
+		n  = (uint32_t) ((sd.hi - t0 < SP_TILE) ? (sd.hi - t0) : SP_TILE);
+		g0 = (int64_t) t0 - (int64_t) h;
+		interior = (g0 >= (int64_t) sd.dlo) && (g0 + (int64_t) need + 1 <= (int64_t) sd.dhi);
+		};
+
+	uint32_t phase[2] = { 0, 0 };
+	uint64_t t = blockIdx.x;
+	if (t >= ntiles) return;
+
+	// prologue: first tile into buffer 0
+	{
+	SegDev sd;  uint64_t t0;  uint32_t n;  int64_t g0;  bool interior;
+	tile_geom (t, sd, t0, n, g0, interior);
+	if (interior && threadIdx.x == 0)
+		{
+		const int64_t ga = g0 & ~1ll;
+		const uint32_t bytes = (uint32_t) (((need + (uint32_t) (g0 - ga) + 1) & ~1u) * sizeof (double));
+		mbar_expect_tx (&s_bar[0], bytes);
+		bulk_g2s (&s_buf[0][0], in + ga, bytes, &s_bar[0]);
+		}
+	}
+
+	for (int it = 0; ; it++)
+		{
+		const int cur = it & 1;
+		SegDev sd;  uint64_t t0;  uint32_t n;  int64_t g0;  bool interior;
+		tile_geom (t, sd, t0, n, g0, interior);
+
+		// prefetch the next tile into the other buffer (its previous contents were consumed before the
+		// __syncthreads that ended the previous iteration)
+		const uint64_t tn = t + gridDim.x;
+		if (tn < ntiles && threadIdx.x == 0)
+			{
+			SegDev sdn;  uint64_t t0n;  uint32_t nn;  int64_t g0n;  bool intn;
+			tile_geom (tn, sdn, t0n, nn, g0n, intn);
+			if (intn)
+				{
+				const int64_t ga = g0n & ~1ll;
+				const uint32_t bytes = (uint32_t) (((need + (uint32_t) (g0n - ga) + 1) & ~1u) * sizeof (double));
+				asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");
+				mbar_expect_tx (&s_bar[cur ^ 1], bytes);
+				bulk_g2s (&s_buf[cur ^ 1][0], in + ga, bytes, &s_bar[cur ^ 1]);
+				}
+			}
+
+		uint32_t shift;                           // staged cell j <-> in[g0 + j] lives at s_buf[cur][j + shift]
+		if (interior)
+			{
+			shift = (uint32_t) (g0 & 1);
+			mbar_wait (&s_bar[cur], phase[cur]);
+			phase[cur] ^= 1;
+			}
+		else
+			{
+			shift = 0;
+			stage_tile<0> (&s_buf[cur][0], in, g0, need, sd.dlo, sd.dhi, 0.0);
+			__syncthreads ();
+			}
+		const double* X = &s_buf[cur][shift];
+
+		double acc[SP_R];
+		#pragma unroll
+		for (int r = 0; r < SP_R; r++) acc[r] = 0.0;
+		const uint32_t i0 = threadIdx.x * SP_R;
+		double x[SP_R], y[SP_R];
+		#pragma unroll
+		for (int m = 0; m < SP_R; m++) x[m] = X[i0 + m];
+		for (uint32_t k0 = 0; k0 < W; k0 += SP_R)
+			{
+			#pragma unroll
+			for (int m = 0; m < SP_R; m++) y[m] = X[i0 + k0 + SP_R + m];
+			if (k0 + SP_R <= W)
+				{
+				#pragma unroll
+				for (int u = 0; u < SP_R; u++)
+					{
+					const double w = s_w[k0 + u];
+					#pragma unroll
+					for (int r = 0; r < SP_R; r++)
+						{
+						const double xv = (u + r < SP_R) ? x[u + r] : y[u + r - SP_R];
+						acc[r] = __dadd_rn (acc[r], __dmul_rn (w, xv));
+						}
+					}
+				}
+			else
+				{
+				#pragma unroll
+				for (int u = 0; u < SP_R; u++)
+					{
+					if (k0 + u < W)
+						{
+						const double w = s_w[k0 + u];
+						#pragma unroll
+						for (int r = 0; r < SP_R; r++)
+							{
+							const double xv = (u + r < SP_R) ? x[u + r] : y[u + r - SP_R];
+							acc[r] = __dadd_rn (acc[r], __dmul_rn (w, xv));
+							}
+						}
+					}
+				}
+			#pragma unroll
+			for (int m = 0; m < SP_R; m++) x[m] = y[m];
+			}
+
+		double* o = out + t0 + i0;
+		#pragma unroll
+		for (int r = 0; r < SP_R; r++) if (i0 + r < n) o[r] = acc[r];
+
+		__syncthreads ();                         // everyone is done with s_buf[cur]
+		t = tn;
+		if (t >= ntiles) break;
+		}
+	}
+
+// ---------------------------------------------------------------------------
 // C-ABI
 // ---------------------------------------------------------------------------
 
@@ -441,6 +605,19 @@ extern "C" int gdsp_smooth (gdsp_ctx* c, const gdsp_layout* L_, const double* in
 		}
 	void* dt = c->taps_dev;
 	TileMap tm;
+	if (W <= SP_MAXW)
+		{
+		// persistent CTAs fed by TMA bulk copies: as many CTAs as fit on the device at once
+		GDSP_TRY (gdsp_layout_tilemap (L, SP_TILE, &tm));
+		int perSM = 0;
+		GDSP_CUDA (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&perSM, k_smooth_pipe, SP_THREADS, 0));
+		if (perSM < 1) perSM = 1;
+		uint64_t grid = (uint64_t) c->sm_count * perSM;
+		if (grid > tm.ntiles) grid = tm.ntiles;
+		k_smooth_pipe<<<(unsigned) grid, SP_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, tm.ntiles, in, out, W, (const double*) dt);
+		GDSP_KERNEL_CHECK ();
+		return GDSP_OK;
+		}
 	GDSP_TRY (gdsp_layout_tilemap (L, SM_TILE, &tm));
 	k_smooth<<<(unsigned) tm.ntiles, SM_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, in, out, W, (const double*) dt);
 	GDSP_KERNEL_CHECK ();

@@ -430,3 +430,38 @@ def test_sort_genome_real_values(genome):
     post = _sorted_post_state(genome, inputs)
     for name, n in CHROMS:
         assert np.array_equal(genome.get_chrom(name), post[name]), name
+
+
+def test_smooth_many_tiles_per_cta(orc):
+    """more tiles than resident CTAs: exercises the double-buffered TMA pipeline of k_smooth_pipe"""
+    from genodsp_b200.genome import Genome
+    chroms = [("big", 2500000), ("mid", 1300000 + 7), ("tiny", 50)]
+    g = Genome(chroms)
+    rng = np.random.default_rng(99)
+    ins = {n: signal(rng, l, "real" if n != "mid" else "int") for n, l in chroms}
+    for W in (101, 11, 513):
+        for n, v in ins.items():
+            g.set_chrom(n, v)
+        g.smooth(W)
+        for n, v in ins.items():
+            want = orc.smooth(v.copy(), W)
+            got = g.get_chrom(n)
+            bad = np.nonzero(bits(got) != bits(want))[0]
+            assert bad.size == 0, (W, n, bad[:5])
+    g.close()
+
+
+def test_sort_genome_mostly_zeros(genome):
+    """zero-majority shortcut of gdsp_sort_genome (negatives, -0.0 and +0.0 included)"""
+    rng = np.random.default_rng(31)
+    inputs = {}
+    for name, n in CHROMS:
+        v = np.where(rng.random(n) < 0.93, 0.0, rng.normal(0, 3, n))
+        if n > 10:
+            v[3] = -0.0
+        inputs[name] = v; genome.set_chrom(name, v)
+    genome.sort_genome()
+    post = _sorted_post_state(genome, inputs)
+    for name, n in CHROMS:
+        got = genome.get_chrom(name)
+        assert np.array_equal(got, post[name]), name      # (-0.0 == +0.0: their relative order is unspecified in the reference too)
