@@ -107,18 +107,30 @@ int gdsp_ws (gdsp_ctx* ctx, int slot, size_t bytes, void** out);
 
 #ifdef __CUDACC__
 
-// which segment does tile `t` belong to, and which tile of that segment is it
+// Which segment does tile `t` belong to, and which tile of that segment is it?
+// Warp-cooperative: all 32 lanes of the calling warp must call it with the same t.
+// Each lane inspects one entry of the tile-count prefix (one coalesced load for up
+// to 32 segments) and a vote finds the last entry <= t -- one memory round trip
+// instead of a chain of dependent bisection loads at the head of every block.
 __device__ __forceinline__ void tile_to_seg (const uint64_t* __restrict__ base, int nseg,
                                              uint64_t t, int& seg, uint64_t& tileInSeg)
 	{
-	int lo = 0, hi = nseg - 1;
-	while (lo < hi)
+	const int lane = threadIdx.x & 31;
+	int s = 0;
+	uint64_t b = 0;
+	for (int s0 = 0; s0 < nseg; s0 += 32)
 		{
-		int mid = (lo + hi + 1) >> 1;
-		if (base[mid] <= t) lo = mid; else hi = mid - 1;
+		const int idx = s0 + lane;
+		const uint64_t v = (idx < nseg) ? __ldg (base + idx) : ~0ull;
+		const unsigned m = __ballot_sync (0xffffffffu, v <= t);
+		if (m == 0) break;
+		const int cnt = __popc (m);
+		s = s0 + cnt - 1;
+		b = __shfl_sync (0xffffffffu, v, cnt - 1);
+		if (cnt < 32) break;
 		}
-	seg = lo;
-	tileInSeg = t - base[lo];
+	seg = s;
+	tileInSeg = t - b;
 	}
 
 __device__ __forceinline__ double shfl_up_f64 (double v, int delta)

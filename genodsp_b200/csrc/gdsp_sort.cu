@@ -977,3 +977,117 @@ extern "C" int gdsp_percentiles (gdsp_ctx* c, const gdsp_layout* L_, const doubl
 	*h_num_samples = numSamples;
 	return GDSP_OK;
 	}
+
+// ---------------------------------------------------------------------------
+// Building blocks of the percentile selection, for slab-sharded runs: every rank
+// samples, counts and compacts its own slab; the host layer (genodsp_b200/slab.py)
+// combines samples, region counts and candidates across ranks with all-gather /
+// all-reduce and repeats gdsp_percentiles' decision logic.
+// ---------------------------------------------------------------------------
+
+static int pct_sample_space (gdsp_ctx* c, gdsp_layout* L, uint32_t stride, uint64_t** d_sprefix, uint64_t* nslots)
+	{
+	std::vector<uint64_t> sprefix (L->nseg + 1);
+	uint64_t n = 0;
+	for (int s = 0; s < L->nseg; s++)
+		{
+		const gdsp_seg& g = L->h[s];
+		uint64_t p0 = g.pos0, p1 = p0 + (g.hi - g.lo);
+		uint64_t first = (p0 + stride - 1) / stride * stride;
+		sprefix[s] = n;
+		if (first < p1) n += (p1 - 1 - first) / stride + 1;
+		}
+	sprefix[L->nseg] = n;
+	void* ws;
+	GDSP_TRY (gdsp_ws (c, 5, 64 + sizeof (unsigned long long) * (2 * PCT_MAXB + 8) + sizeof (uint64_t) * (L->nseg + 1), &ws));
+	*d_sprefix = (uint64_t*) ((char*) ws + 64 + sizeof (unsigned long long) * (2 * PCT_MAXB + 8));
+	GDSP_CUDA (cudaMemcpyAsync (*d_sprefix, sprefix.data (), sizeof (uint64_t) * (L->nseg + 1), cudaMemcpyHostToDevice, c->stream));
+	GDSP_CUDA (cudaStreamSynchronize (c->stream));
+	*nslots = n;
+	return GDSP_OK;
+	}
+
+extern "C" int gdsp_pct_sample (gdsp_ctx* c, const gdsp_layout* L_, const double* sig, uint32_t stride,
+                                double mn, double mx, uint64_t key_lo, uint64_t key_hi, uint32_t m, uint64_t seed,
+                                double* d_out, uint32_t* h_count, uint64_t* h_slots)
+	{
+	gdsp_layout* L = (gdsp_layout*) L_;
+	GDSP_REQUIRE (c && L && sig && d_out && h_count, "gdsp_pct_sample: NULL argument");
+	if (stride == 0) stride = 1;
+	uint64_t* d_sprefix;  uint64_t nslots;
+	GDSP_TRY (pct_sample_space (c, L, stride, &d_sprefix, &nslots));
+	if (h_slots) *h_slots = nslots;
+	*h_count = 0;
+	if (nslots == 0 || m == 0) return GDSP_OK;
+	void* ws;
+	GDSP_TRY (gdsp_ws (c, 5, 64, &ws));
+	unsigned int* d_scount = (unsigned int*) ((char*) ws + 16);
+	GDSP_CUDA (cudaMemsetAsync (d_scount, 0, 4, c->stream));
+	SampleSpace sp;  sp.nseg = L->nseg;  sp.sprefix = d_sprefix;  sp.segs = L->d;  sp.stride = stride;
+	k_pct_sample<<<(m + 255) / 256, 256, 0, c->stream>>> (sp, nslots, sig, mn, mx, key_lo, key_hi, m, seed, d_out, d_scount);
+	GDSP_KERNEL_CHECK ();
+	GDSP_CUDA (cudaMemcpyAsync (h_count, d_scount, 4, cudaMemcpyDeviceToHost, c->stream));
+	GDSP_CUDA (cudaStreamSynchronize (c->stream));
+	return GDSP_OK;
+	}
+
+extern "C" int gdsp_sort_array (gdsp_ctx* c, double* d_a, double* d_b, uint64_t n, int* h_result_in_b)
+	{
+	GDSP_REQUIRE (c && d_a && d_b && h_result_in_b, "gdsp_sort_array: NULL argument");
+	*h_result_in_b = 0;
+	if (n < 2) return GDSP_OK;
+	SortScratch sc;
+	GDSP_TRY (sort_scratch (c, (n + SORT_TILE - 1) / SORT_TILE + 1, 1, &sc));
+	SortPlan lp;
+	GDSP_TRY (make_lin_plan (c, sc, n, &lp));
+	OutMap lin;  lin.nseg = 0;  lin.prefix = NULL;  lin.segs = NULL;
+	double* res = NULL;  int passes = 0;
+	GDSP_TRY (radix_sort (c, lp, lp, d_a, d_a, d_b, lin, sc, &res, &passes));
+	*h_result_in_b = (res == d_b) ? 1 : 0;
+	return GDSP_OK;
+	}
+
+extern "C" int gdsp_pct_count (gdsp_ctx* c, const gdsp_layout* L_, const double* sig, uint32_t stride,
+                               double mn, double mx, const uint64_t* h_bound_keys, int nb, const uint8_t* h_compact,
+                               uint64_t* h_counts, double* d_cand, uint64_t cap, uint64_t* h_ncand)
+	{
+	gdsp_layout* L = (gdsp_layout*) L_;
+	GDSP_REQUIRE (c && L && sig && h_counts && h_ncand, "gdsp_pct_count: NULL argument");
+	GDSP_REQUIRE (nb >= 0 && nb <= PCT_MAXB, "gdsp_pct_count: at most %d bounds per pass", PCT_MAXB);
+	GDSP_REQUIRE (nb == 0 || (h_bound_keys && h_compact), "gdsp_pct_count: NULL bounds");
+	if (stride == 0) stride = 1;
+	PctBounds B;  memset (&B, 0, sizeof (B));
+	B.nb = nb;
+	for (int k = 0; k < nb; k++)
+		{
+		GDSP_REQUIRE (k == 0 || h_bound_keys[k] > h_bound_keys[k-1], "gdsp_pct_count: bounds must be strictly ascending");
+		B.key[k] = h_bound_keys[k];
+		}
+	for (int k = 0; k <= nb; k++) B.compact[k] = (h_compact != NULL && h_compact[k]) ? 1 : 0;
+	TileMap tmPct;
+	GDSP_TRY (gdsp_layout_tilemap (L, PCT_TILE, &tmPct));
+	void* ws;
+	GDSP_TRY (gdsp_ws (c, 5, 64 + sizeof (unsigned long long) * (2 * PCT_MAXB + 8), &ws));
+	unsigned long long* d_ncand  = (unsigned long long*) ws;
+	unsigned long long* d_counts = (unsigned long long*) ((char*) ws + 64);
+	const int nreg = 2 * nb + 1;
+	GDSP_CUDA (cudaMemsetAsync (d_counts, 0, sizeof (unsigned long long) * nreg, c->stream));
+	GDSP_CUDA (cudaMemsetAsync (d_ncand, 0, 8, c->stream));
+	int grid = c->sm_count * 8;
+	if ((uint64_t) grid > tmPct.ntiles) grid = (int) tmPct.ntiles;
+	if (nb <= 2)
+		k_pct_pass<true><<<grid, 256, 0, c->stream>>> (L->d, tmPct.d_base, L->nseg, tmPct.ntiles, sig, stride, mn, mx,
+		        B, d_counts, d_cand, cap, d_ncand);
+	else
+		k_pct_pass<false><<<grid, 256, 0, c->stream>>> (L->d, tmPct.d_base, L->nseg, tmPct.ntiles, sig, stride, mn, mx,
+		        B, d_counts, d_cand, cap, d_ncand);
+	GDSP_KERNEL_CHECK ();
+	std::vector<unsigned long long> counts (nreg);
+	unsigned long long ncand = 0;
+	GDSP_CUDA (cudaMemcpyAsync (counts.data (), d_counts, sizeof (unsigned long long) * nreg, cudaMemcpyDeviceToHost, c->stream));
+	GDSP_CUDA (cudaMemcpyAsync (&ncand, d_ncand, 8, cudaMemcpyDeviceToHost, c->stream));
+	GDSP_CUDA (cudaStreamSynchronize (c->stream));
+	for (int r = 0; r < nreg; r++) h_counts[r] = counts[r];
+	*h_ncand = ncand;
+	return GDSP_OK;
+	}

@@ -330,166 +330,112 @@ k_smooth (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, in
 	}
 
 // ---------------------------------------------------------------------------
-// k_smooth_pipe: the same FIR for W <= SP_MAXW as a PERSISTENT kernel whose
-// tiles arrive through the TMA engine.  Each CTA loops over tiles; while it
-// computes tile i from one shared-memory buffer, one thread has already issued
-// a 1-D bulk async copy (cp.async.bulk.shared::cluster.global with an mbarrier
-// transaction count; SASS UBLKCP) of tile i+1 into the other buffer, so the
-// FP64 pipe never waits for global memory.  The staged layout is linear (what a
-// bulk copy produces); every thread owns SP_R = 9 consecutive outputs, an ODD
-// strip, which makes the stride-9 window loads bank-conflict free without
-// padding.  Tiles that touch a chromosome end (or the buffer start) are staged
-// by hand with zero fill instead.
+// k_smooth_ct: the same FIR for W <= SC_MAXW with the taps passed BY VALUE as a
+// __grid_constant__ kernel parameter.  The tap of step k is the same for every
+// thread, so it is read through the uniform datapath straight from the constant
+// bank (SASS: LDCU.64 UR, c[0x0][UR+off]; DMUL R, R, UR) and costs no
+// shared-memory load; the only LDS left in the inner loop is the one new input
+// cell per 2*R FP64 instructions.  scripts/micro/fp64_peak.cu measures what
+// that buys on this part: 1.745e13 DMUL+DADD/s with constant-bank taps against
+// 1.673e13 with a broadcast LDS per tap (nominal 64 lanes * 148 SMs * 1.965 GHz
+// = 1.861e13).
+// (A persistent variant fed by 1-D bulk async copies (cp.async.bulk + mbarrier)
+// was measured at 43.9 ms on hg38 against 39.9 ms for k_smooth: the kernel is
+// FP64-issue bound, so hiding the global-load latency buys nothing and the
+// per-tile bookkeeping costs issue slots.  It was removed.)
 // ---------------------------------------------------------------------------
 
-#define SP_THREADS 128
-#define SP_R       9
-#define SP_TILE    (SP_THREADS * SP_R)           // 1152 outputs per tile
-#define SP_MAXW    513
-#define SP_BUF     ((SP_TILE + SP_MAXW + 2 * SP_R + 17) & ~15)   // cells per staging buffer (multiple of 16: 128-byte aligned buffers)
+#define SC_MAXW    1024
+#define SC_LOGR    4            // 16 outputs per thread: hg38 W=101 35.3 ms; 8 per thread 37.1 ms
+struct SmoothTaps { double w[SC_MAXW]; };
 
-__global__ void __launch_bounds__(SP_THREADS)
-k_smooth_pipe (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg, uint64_t ntiles,
-               const double* __restrict__ in, double* __restrict__ out,
-               uint32_t W, const double* __restrict__ taps)
+template <int LOGR>
+__global__ void __launch_bounds__(SM_THREADS)
+k_smooth_ct (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
+             const double* __restrict__ in, double* __restrict__ out,
+             uint32_t W, const __grid_constant__ SmoothTaps tp)
 	{
-	__shared__ __align__(128) double s_buf[2][SP_BUF];
-	__shared__ double s_w[SP_MAXW + SP_R];
-	__shared__ __align__(8) uint64_t s_bar[2];
+	constexpr int      R    = 1 << LOGR;
+	constexpr uint32_t TILE = SM_THREADS * R;
+	__shared__ double s_x[(TILE + SM_KC + 2 * R) + ((TILE + SM_KC + 2 * R) >> LOGR) + 2];
 
-	const uint32_t h = (W - 1) / 2;
-	const uint32_t need = SP_TILE + W - 1 + SP_R;          // staged cells a tile reads (incl. the look-ahead loads)
+	int seg;  uint64_t tis;
+	tile_to_seg (base, nseg, blockIdx.x, seg, tis);
+	const SegDev sd = segs[seg];
+	const uint64_t t0 = sd.lo + tis * TILE;
+	const uint32_t n  = (uint32_t) ((sd.hi - t0 < TILE) ? (sd.hi - t0) : TILE);
+	const uint32_t h  = (W - 1) / 2;
 
-	for (uint32_t k = threadIdx.x; k < W + SP_R; k += SP_THREADS) s_w[k] = (k < W) ? taps[k] : 0.0;
-	if (threadIdx.x == 0)
+	double acc[R];
+	#pragma unroll
+	for (int r = 0; r < R; r++) acc[r] = 0.0;
+
+	const uint32_t i0 = threadIdx.x * R;
+	// padded position of staged cell i0 + q*R + m  (0 <= m < R)  is  (threadIdx.x + q) * (R + 1) + m
+	const double* xrow = s_x + (size_t) threadIdx.x * (R + 1);
+
+	for (uint32_t kc = 0; kc < W; kc += SM_KC)
 		{
-		mbar_init (&s_bar[0], 1);
-		mbar_init (&s_bar[1], 1);
-		mbar_fence_init ();
-		}
-	__syncthreads ();
+		const uint32_t kn = (W - kc < SM_KC) ? (W - kc) : SM_KC;      // taps in this chunk
+		if (kc) __syncthreads ();
+		stage_tile<LOGR> (s_x, in, (int64_t) t0 - (int64_t) h + (int64_t) kc, TILE + kn + R, sd.dlo, sd.dhi, 0.0);
+		__syncthreads ();
 
-	// stage tile t into buffer b: returns (through shared state) how it was staged
-	// kind 0 = bulk copy in flight on s_bar[b]; kind 1 = staged by hand (already complete after the sync)
-	auto tile_geom = [&] (uint64_t t, SegDev& sd, uint64_t& t0, uint32_t& n, int64_t& g0, bool& interior)
-		{
-		int seg;  uint64_t tis;
-		tile_to_seg (base, nseg, t, seg, tis);
-		sd = segs[seg];
-		t0 = sd.lo + tis * SP_TILE;
-		n  = (uint32_t) ((sd.hi - t0 < SP_TILE) ? (sd.hi - t0) : SP_TILE);
-		g0 = (int64_t) t0 - (int64_t) h;
-		interior = (g0 >= (int64_t) sd.dlo) && (g0 + (int64_t) need + 1 <= (int64_t) sd.dhi);
-		};
-
-	uint32_t phase[2] = { 0, 0 };
-	uint64_t t = blockIdx.x;
-	if (t >= ntiles) return;
-
-	// prologue: first tile into buffer 0
-	{
-	SegDev sd;  uint64_t t0;  uint32_t n;  int64_t g0;  bool interior;
-	tile_geom (t, sd, t0, n, g0, interior);
-	if (interior && threadIdx.x == 0)
-		{
-		const int64_t ga = g0 & ~1ll;
-		const uint32_t bytes = (uint32_t) (((need + (uint32_t) (g0 - ga) + 1) & ~1u) * sizeof (double));
-		mbar_expect_tx (&s_bar[0], bytes);
-		bulk_g2s (&s_buf[0][0], in + ga, bytes, &s_bar[0]);
-		}
-	}
-
-	for (int it = 0; ; it++)
-		{
-		const int cur = it & 1;
-		SegDev sd;  uint64_t t0;  uint32_t n;  int64_t g0;  bool interior;
-		tile_geom (t, sd, t0, n, g0, interior);
-
-		// prefetch the next tile into the other buffer (its previous contents were consumed before the
-		// __syncthreads that ended the previous iteration)
-		const uint64_t tn = t + gridDim.x;
-		if (tn < ntiles && threadIdx.x == 0)
-			{
-			SegDev sdn;  uint64_t t0n;  uint32_t nn;  int64_t g0n;  bool intn;
-			tile_geom (tn, sdn, t0n, nn, g0n, intn);
-			if (intn)
-				{
-				const int64_t ga = g0n & ~1ll;
-				const uint32_t bytes = (uint32_t) (((need + (uint32_t) (g0n - ga) + 1) & ~1u) * sizeof (double));
-				asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");
-				mbar_expect_tx (&s_bar[cur ^ 1], bytes);
-				bulk_g2s (&s_buf[cur ^ 1][0], in + ga, bytes, &s_bar[cur ^ 1]);
-				}
-			}
-
-		uint32_t shift;                           // staged cell j <-> in[g0 + j] lives at s_buf[cur][j + shift]
-		if (interior)
-			{
-			shift = (uint32_t) (g0 & 1);
-			mbar_wait (&s_bar[cur], phase[cur]);
-			phase[cur] ^= 1;
-			}
-		else
-			{
-			shift = 0;
-			stage_tile<0> (&s_buf[cur][0], in, g0, need, sd.dlo, sd.dhi, 0.0);
-			__syncthreads ();
-			}
-		const double* X = &s_buf[cur][shift];
-
-		double acc[SP_R];
+		double x[R], y[R];
 		#pragma unroll
-		for (int r = 0; r < SP_R; r++) acc[r] = 0.0;
-		const uint32_t i0 = threadIdx.x * SP_R;
-		double x[SP_R], y[SP_R];
-		#pragma unroll
-		for (int m = 0; m < SP_R; m++) x[m] = X[i0 + m];
-		for (uint32_t k0 = 0; k0 < W; k0 += SP_R)
+		for (int m = 0; m < R; m++) x[m] = xrow[m];
+
+		uint32_t k0 = 0;
+		const double* yrow = xrow + (R + 1);
+		for (; k0 + R <= kn; k0 += R, yrow += R + 1)
 			{
 			#pragma unroll
-			for (int m = 0; m < SP_R; m++) y[m] = X[i0 + k0 + SP_R + m];
-			if (k0 + SP_R <= W)
+			for (int m = 0; m < R; m++) y[m] = yrow[m];
+			#pragma unroll
+			for (int u = 0; u < R; u++)
 				{
+				const double w = tp.w[kc + k0 + u];
 				#pragma unroll
-				for (int u = 0; u < SP_R; u++)
+				for (int r = 0; r < R; r++)
 					{
-					const double w = s_w[k0 + u];
+					const double xv = (u + r < R) ? x[u + r] : y[u + r - R];
+					acc[r] = __dadd_rn (acc[r], __dmul_rn (w, xv));
+					}
+				}
+			#pragma unroll
+			for (int m = 0; m < R; m++) x[m] = y[m];
+			}
+		if (k0 < kn)
+			{
+			#pragma unroll
+			for (int m = 0; m < R; m++) y[m] = yrow[m];
+			#pragma unroll
+			for (int u = 0; u < R; u++)
+				{
+				if (k0 + u < kn)
+					{
+					const double w = tp.w[kc + k0 + u];
 					#pragma unroll
-					for (int r = 0; r < SP_R; r++)
+					for (int r = 0; r < R; r++)
 						{
-						const double xv = (u + r < SP_R) ? x[u + r] : y[u + r - SP_R];
+						const double xv = (u + r < R) ? x[u + r] : y[u + r - R];
 						acc[r] = __dadd_rn (acc[r], __dmul_rn (w, xv));
 						}
 					}
 				}
-			else
-				{
-				#pragma unroll
-				for (int u = 0; u < SP_R; u++)
-					{
-					if (k0 + u < W)
-						{
-						const double w = s_w[k0 + u];
-						#pragma unroll
-						for (int r = 0; r < SP_R; r++)
-							{
-							const double xv = (u + r < SP_R) ? x[u + r] : y[u + r - SP_R];
-							acc[r] = __dadd_rn (acc[r], __dmul_rn (w, xv));
-							}
-						}
-					}
-				}
-			#pragma unroll
-			for (int m = 0; m < SP_R; m++) x[m] = y[m];
 			}
+		}
 
-		double* o = out + t0 + i0;
+	double* o = out + t0 + i0;
+	if (i0 + R <= n)
+		{
 		#pragma unroll
-		for (int r = 0; r < SP_R; r++) if (i0 + r < n) o[r] = acc[r];
-
-		__syncthreads ();                         // everyone is done with s_buf[cur]
-		t = tn;
-		if (t >= ntiles) break;
+		for (int r = 0; r < R; r += 2) stg_stream (o + r, make_double2 (acc[r], acc[r + 1]));
+		}
+	else
+		{
+		#pragma unroll
+		for (int r = 0; r < R; r++) if (i0 + r < n) o[r] = acc[r];
 		}
 	}
 
@@ -589,6 +535,16 @@ extern "C" int gdsp_smooth (gdsp_ctx* c, const gdsp_layout* L_, const double* in
 	GDSP_REQUIRE (c && L && in && out && h_taps, "gdsp_smooth: NULL argument");
 	GDSP_REQUIRE (in != out, "gdsp_smooth: in and out must be different buffers");
 	GDSP_REQUIRE (W >= 1, "gdsp_smooth: window must be positive");
+	TileMap tm;
+	if (W <= SC_MAXW)
+		{
+		SmoothTaps tp;                          // by-value kernel parameter (copied at launch)
+		memcpy (tp.w, h_taps, sizeof (double) * W);
+		GDSP_TRY (gdsp_layout_tilemap (L, SM_THREADS << SC_LOGR, &tm));
+		k_smooth_ct<SC_LOGR><<<(unsigned) tm.ntiles, SM_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, in, out, W, tp);
+		GDSP_KERNEL_CHECK ();
+		return GDSP_OK;
+		}
 	// the taps are uploaded once and reused while the caller keeps passing the same window
 	if (c->taps_n != W || c->taps_host == NULL || memcmp (c->taps_host, h_taps, sizeof (double) * W) != 0)
 		{
@@ -604,20 +560,6 @@ extern "C" int gdsp_smooth (gdsp_ctx* c, const gdsp_layout* L_, const double* in
 		c->taps_n = W;
 		}
 	void* dt = c->taps_dev;
-	TileMap tm;
-	if (W <= SP_MAXW)
-		{
-		// persistent CTAs fed by TMA bulk copies: as many CTAs as fit on the device at once
-		GDSP_TRY (gdsp_layout_tilemap (L, SP_TILE, &tm));
-		int perSM = 0;
-		GDSP_CUDA (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&perSM, k_smooth_pipe, SP_THREADS, 0));
-		if (perSM < 1) perSM = 1;
-		uint64_t grid = (uint64_t) c->sm_count * perSM;
-		if (grid > tm.ntiles) grid = tm.ntiles;
-		k_smooth_pipe<<<(unsigned) grid, SP_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, tm.ntiles, in, out, W, (const double*) dt);
-		GDSP_KERNEL_CHECK ();
-		return GDSP_OK;
-		}
 	GDSP_TRY (gdsp_layout_tilemap (L, SM_TILE, &tm));
 	k_smooth<<<(unsigned) tm.ntiles, SM_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, in, out, W, (const double*) dt);
 	GDSP_KERNEL_CHECK ();

@@ -248,6 +248,24 @@ int  gdsp_percentiles (gdsp_ctx* ctx, const gdsp_layout* lay, const double* sig,
                        double min_allowed, double max_allowed,
                        const uint32_t* h_p_milli, int np, double* h_values,
                        uint64_t* h_num_samples);
+/* Building blocks of gdsp_percentiles for slab-sharded runs (one rank = one
+ * slab): sample the qualifying cells whose order-preserving key lies in
+ * [key_lo,key_hi] (unsorted, into d_out, capacity m); sort a plain device
+ * array; count the cells in the regions delimited by ascending key bounds
+ * (region 2k = keys below bound k and above bound k-1, region 2k+1 = equal to
+ * bound k; 2*nb+1 regions) while compacting the cells of the open regions whose
+ * h_compact[k] is set.  The host combines the per-rank results with
+ * all-gather / all-reduce (genodsp_b200/slab.py).  The key of a double is its
+ * bit pattern with the sign bit flipped for non-negatives and all bits flipped
+ * for negatives. */
+int  gdsp_pct_sample  (gdsp_ctx* ctx, const gdsp_layout* lay, const double* sig, uint32_t stride,
+                       double min_allowed, double max_allowed, uint64_t key_lo, uint64_t key_hi,
+                       uint32_t m, uint64_t seed, double* d_out, uint32_t* h_count, uint64_t* h_slots);
+int  gdsp_sort_array  (gdsp_ctx* ctx, double* d_a, double* d_b, uint64_t n, int* h_result_in_b);
+int  gdsp_pct_count   (gdsp_ctx* ctx, const gdsp_layout* lay, const double* sig, uint32_t stride,
+                       double min_allowed, double max_allowed, const uint64_t* h_bound_keys, int nb,
+                       const uint8_t* h_compact, uint64_t* h_counts, double* d_cand, uint64_t cap,
+                       uint64_t* h_ncand);
 /* The reference's percentile is destructive; with every cell qualifying and
  * the last requested rank in the last two chromosomes the genome ends up
  * globally sorted in layout order (percentile.c:611-651).
