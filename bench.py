@@ -35,6 +35,9 @@ HG38 = [("chr1", 248956422), ("chr2", 242193529), ("chr3", 198295559), ("chr4", 
 WINDOW = 101
 DEPTH = 5
 READ_MIN, READ_MAX = 50, 150
+FP64_NOMINAL = 148 * 64 * 1.965e9      # FP64 lanes * SMs * max SM clock (instructions/s)
+FP64_MEASURED = 1.745e13               # scripts/micro/fp64_peak.cu on this pool's B200 (gpurun, round 1)
+SMOOTH_TRAFFIC_BYTES_PER_BASE = None   # dram read+write per base of k_smooth_ct from ncu --set full (profiles/)
 METRIC = "Gbp/s, hg38 depth accumulation + smooth --window=101 (fp64)"
 
 
@@ -282,8 +285,10 @@ def run_gpu_arm(args):
     t_begin, t_end = ev(), ev()
     barrier()
     t_begin.record()
+    launches0 = g.launches
     for k in range(args.steps):
         step_resident(stage_ev[k])
+    timed_launches = g.launches - launches0
     t_end.record()
     barrier()
     total_ms = t_begin.elapsed_time(t_end)
@@ -328,6 +333,7 @@ def run_gpu_arm(args):
         peak, peak_src = measured_hbm_peak()
         per_gpu_bases = total_bases / world
         smooth_gbs = 16.0 * per_gpu_bases / (smo_ms / 1e3) / 1e9
+        fp64_rate = 2.0 * WINDOW * per_gpu_bases / (smo_ms / 1e3)
         acc_bytes = 16.0 * per_gpu_bases + 28.0 * n_iv_total / world
         line = {
             "metric": METRIC, "value": total_bases / (ms_per_step / 1e3) / 1e9, "unit": "Gbp/s",
@@ -345,7 +351,7 @@ def run_gpu_arm(args):
                     "h2d_bytes_per_step": 12 * n_iv_total, "d2h_bytes_per_step": 8 * int(g.buffer_cells) * world,
                     "ms_per_step": e2e_ms,
                     "what": "gdsp_accumulate_host(pinned seg/start/end) + gdsp_smooth + D2H of the fp64 signal"},
-            "gpu_launches": 3 * args.steps,
+            "gpu_launches": timed_launches,
             "stages": {"accumulate": {"ms": acc_ms, "gbp_s": total_bases / (acc_ms / 1e3) / 1e9,
                                       "achieved_gbs": acc_bytes / (acc_ms / 1e3) / 1e9,
                                       "frac_hbm": acc_bytes / (acc_ms / 1e3) / 1e9 / peak},
@@ -354,10 +360,15 @@ def run_gpu_arm(args):
                                   "achieved_gbs": smooth_gbs, "frac_hbm": smooth_gbs / peak,
                                   "fp64_instr_per_base": 2 * WINDOW,
                                   "fp64_lane_ops_per_s": 2 * WINDOW * per_gpu_bases / (smo_ms / 1e3)}},
-            "roofline": {"kernel": "k_smooth", "bound": "hbm", "achieved": smooth_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": smooth_gbs / peak, "traffic": None, "peak_source": peak_src,
-                         "note": "16 B/bp algorithmic; the exact-order FIR needs 2*W=202 FP64 instructions per base, "
-                                 "so FP64 issue (64 lanes/SM), not HBM, is the binding limit for W=101"},
+            "roofline": {"kernel": "k_smooth_ct", "bound": "hbm", "achieved": smooth_gbs, "peak": peak, "unit": "GB/s",
+                         "frac": smooth_gbs / peak, "traffic": SMOOTH_TRAFFIC_BYTES_PER_BASE * per_gpu_bases if SMOOTH_TRAFFIC_BYTES_PER_BASE else None,
+                         "peak_source": peak_src,
+                         "binding_limit": {"kind": "fp64_issue", "achieved": fp64_rate, "unit": "FP64 instr/s",
+                                           "peak_nominal": FP64_NOMINAL, "frac_nominal": fp64_rate / FP64_NOMINAL,
+                                           "peak_measured": FP64_MEASURED, "frac_measured": fp64_rate / FP64_MEASURED,
+                                           "peak_measured_source": "scripts/micro/fp64_peak.cu (DMUL+DADD, constant-bank operand)"},
+                         "note": "16 B/bp algorithmic; the exact-order FIR needs 2*W=202 separately rounded FP64 "
+                                 "instructions per base, so FP64 issue (64 lanes/SM), not HBM, is the binding limit for W=101"},
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_single()

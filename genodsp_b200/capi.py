@@ -44,6 +44,7 @@ SIGNATURES = {
     "gdsp_ctx_set_stream": (_i, [_vp, _vp]),
     "gdsp_sync": (_i, [_vp]),
     "gdsp_last_error": (C.c_char_p, []),
+    "gdsp_launch_count": (C.c_uint64, []),
     "gdsp_version": (C.c_char_p, []),
     "gdsp_device_info": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_sz), C.POINTER(_sz)]),
     "gdsp_malloc": (_i, [_vp, _sz, C.POINTER(_vp)]),

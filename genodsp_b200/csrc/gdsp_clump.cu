@@ -180,10 +180,8 @@ k_clump_a (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, i
 		for (int c = 0; c < 4; c++) mm[c] = fmin (carryM, m[r][c]);
 		if (e0 + 4 <= n)
 			{
-			stg_stream (wk.P + t0 + e0,     make_double2 (x[r][0], x[r][1]));
-			stg_stream (wk.P + t0 + e0 + 2, make_double2 (x[r][2], x[r][3]));
-			stg_stream (wk.M + t0 + e0,     make_double2 (mm[0], mm[1]));
-			stg_stream (wk.M + t0 + e0 + 2, make_double2 (mm[2], mm[3]));
+			stg_stream4 (wk.P + t0 + e0, x[r][0], x[r][1], x[r][2], x[r][3]);
+			stg_stream4 (wk.M + t0 + e0, mm[0], mm[1], mm[2], mm[3]);
 			}
 		else
 			for (int c = 0; c < 4 && e0 + c < n; c++) { wk.P[t0 + e0 + c] = x[r][c];  wk.M[t0 + e0 + c] = mm[c]; }
@@ -359,8 +357,7 @@ k_clump_c (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, i
 			}
 		if (e0 + 4 <= n)
 			{
-			stg_stream (sig + t0 + e0,     make_double2 (y[0], y[1]));
-			stg_stream (sig + t0 + e0 + 2, make_double2 (y[2], y[3]));
+			stg_stream4 (sig + t0 + e0, y[0], y[1], y[2], y[3]);
 			}
 		else
 			for (int c = 0; c < 4 && e0 + c < n; c++) sig[t0 + e0 + c] = y[c];
@@ -384,6 +381,7 @@ extern "C" int gdsp_clump (gdsp_ctx* c, const gdsp_layout* L_, double* sig, uint
 	{
 	gdsp_layout* L = (gdsp_layout*) L_;
 	GDSP_REQUIRE (c && L && sig && work, "gdsp_clump: NULL argument");
+	GDSP_REQUIRE_ALIGNED (sig, "gdsp_clump");  GDSP_REQUIRE_ALIGNED (work, "gdsp_clump");
 	GDSP_REQUIRE (L->nseg <= 65536, "gdsp_clump: more than 65536 segments");
 	for (int s = 0; s < L->nseg; s++)
 		GDSP_REQUIRE (L->h[s].pos0 == 0 && L->h[s].hi - L->h[s].lo == L->h[s].chrom_len,

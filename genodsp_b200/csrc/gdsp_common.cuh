@@ -32,12 +32,19 @@ void gdsp_set_error (const char* fmt, ...);
 			}                                                                  \
 	} while (0)
 
-#define GDSP_KERNEL_CHECK()  GDSP_CUDA (cudaGetLastError ())
+// every kernel launch of the library goes through this macro; the count is what bench.py reports
+extern unsigned long long g_gdsp_launches;
+#define GDSP_KERNEL_CHECK()                                                    \
+	do { __atomic_fetch_add (&g_gdsp_launches, 1ull, __ATOMIC_RELAXED);  GDSP_CUDA (cudaGetLastError ()); } while (0)
 
 #define GDSP_REQUIRE(cond, ...)                                                \
 	do {                                                                       \
 		if (!(cond)) { gdsp_set_error (__VA_ARGS__); return GDSP_ERR_ARG; }    \
 	} while (0)
+
+// signal buffers are accessed with 256-bit vector loads/stores
+#define GDSP_REQUIRE_ALIGNED(p, what)                                          \
+	GDSP_REQUIRE ((((uintptr_t) (p)) & 31u) == 0, what ": signal buffers must be 32-byte aligned")
 
 #define GDSP_TRY(call)                                                         \
 	do { int s__ = (call); if (s__ != GDSP_OK) return s__; } while (0)
@@ -96,10 +103,14 @@ struct gdsp_ctx
 	double*      taps_host;           // last taps uploaded by gdsp_smooth (host copy) ...
 	double*      taps_dev;            // ... and their device copy, reused while unchanged
 	uint32_t     taps_n;
+	void*        host_small;          // page-locked scratch for small device->host results (percentile samples)
+	size_t       host_small_bytes;
 	};
 
 // grow-only device scratch (slot 0..GDSP_NUM_WS-1); contents undefined
 int gdsp_ws (gdsp_ctx* ctx, int slot, size_t bytes, void** out);
+// grow-only page-locked host scratch; contents undefined
+int gdsp_host_scratch (gdsp_ctx* ctx, size_t bytes, void** out);
 
 // ---------------------------------------------------------------------------
 // device helpers
@@ -180,6 +191,23 @@ __device__ __forceinline__ void stg_stream (double* p, double2 v)
 	              :: "l"(p), "d"(v.x), "d"(v.y) : "memory");
 	}
 
+// 256-bit accesses (sm_100): one lane moves a whole 32-byte sector.  A lane that owns 4 consecutive
+// cells must NOT use two 128-bit accesses instead: each of them touches half of every sector, and
+// the L1 forwards every half-filled sector to the crossbar separately (ncu: l1tex2xbar write bytes
+// = 2x the stored bytes, the crossbar port -- not HBM -- then bounds the kernel).
+// p must be 32-byte aligned.
+__device__ __forceinline__ void stg_stream4 (double* p, double a, double b, double c, double d)
+	{
+	asm volatile ("st.global.L1::no_allocate.v4.f64 [%0], {%1,%2,%3,%4};"
+	              :: "l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+	}
+
+__device__ __forceinline__ void ldg_stream4 (const double* p, double& a, double& b, double& c, double& d)
+	{
+	asm volatile ("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+	              : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+	}
+
 // Stage cells [g0, g0+count) of `in` into shared memory (index j -> smem[j + (j >> PADSHIFT)], or
 // smem[j] when PADSHIFT == 0); cells outside the readable range [dlo,dhi) get `neutral`.
 // Interior tiles (the whole range readable -- all but the first/last tile of a chromosome) take a
@@ -218,6 +246,16 @@ __device__ __forceinline__ void stage_tile (double* smem, const double* __restri
 			}
 		}
 	}
+
+// exact int32 -> double without the I2F.F64 conversion unit (a 16-per-clock-per-SM path that caps a
+// whole-genome kernel at ~5 ms): build 2^52 + (x + 2^31) from its bit pattern and subtract the bias
+// with one FP64 add (exact: both operands and the result are integers below 2^53)
+__device__ __forceinline__ double i32_to_f64 (int x)
+	{
+	return __dadd_rn (__hiloint2double (0x43300000, x ^ (int) 0x80000000), -4503601774854144.0);
+	}
+__device__ __forceinline__ double to_f64 (int x)    { return i32_to_f64 (x); }
+__device__ __forceinline__ double to_f64 (double x) { return x; }
 
 // order-preserving 64-bit key of a double: a<b  <=>  key(a)<key(b) for all
 // non-NaN a,b (with -0.0 just below +0.0)

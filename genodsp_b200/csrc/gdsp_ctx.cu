@@ -17,6 +17,11 @@ void gdsp_set_error (const char* fmt, ...)
 	va_end (ap);
 	}
 
+unsigned long long g_gdsp_launches = 0;
+
+extern "C" uint64_t gdsp_launch_count (void)
+	{ return __atomic_load_n (&g_gdsp_launches, __ATOMIC_RELAXED); }
+
 extern "C" const char* gdsp_last_error (void) { return g_err; }
 extern "C" const char* gdsp_version (void) { return "genodsp-b200 0.1 (sm_100a)"; }
 
@@ -73,6 +78,7 @@ extern "C" void gdsp_ctx_destroy (gdsp_ctx* c)
 	for (int i = 0; i < 2; i++) if (c->pinned[i] != NULL) cudaFreeHost (c->pinned[i]);
 	if (c->taps_dev != NULL) cudaFree (c->taps_dev);
 	if (c->taps_host != NULL) free (c->taps_host);
+	if (c->host_small != NULL) cudaFreeHost (c->host_small);
 	cudaEventDestroy (c->t0);  cudaEventDestroy (c->t1);
 	cudaEventDestroy (c->pinned_ev[0]);  cudaEventDestroy (c->pinned_ev[1]);
 	if (c->owns_stream) cudaStreamDestroy (c->stream);
@@ -114,6 +120,20 @@ extern "C" int gdsp_device_info (gdsp_ctx* c, int* sm, int* maj, int* min, size_
 		if (fre) *fre = f;
 		if (tot) *tot = t;
 		}
+	return GDSP_OK;
+	}
+
+int gdsp_host_scratch (gdsp_ctx* c, size_t bytes, void** out)
+	{
+	if (c->host_small_bytes < bytes)
+		{
+		GDSP_CUDA (cudaStreamSynchronize (c->stream));
+		if (c->host_small) { cudaFreeHost (c->host_small);  c->host_small = NULL;  c->host_small_bytes = 0; }
+		const size_t want = (bytes + ((size_t) 1 << 20) - 1) & ~(((size_t) 1 << 20) - 1);
+		GDSP_CUDA (cudaMallocHost (&c->host_small, want));
+		c->host_small_bytes = want;
+		}
+	*out = c->host_small;
 	return GDSP_OK;
 	}
 

@@ -19,8 +19,16 @@
 #define MM_THREADS 512
 #define MM_WARPS   (MM_THREADS / 32)
 
-template <bool WANT_MAX> __device__ __forceinline__ double ext (double a, double b)
+// fmax/fmin ignore a NaN operand, which is what the reference's `if (v[j] > best)` scans do with a NaN
+// neighbour; but they compile to ~8 instructions per call.  The tiled kernels therefore replace NaN by
+// the neutral element once, when a staged cell enters registers (sanitize), and use the
+// 3-instruction compare-select below; only a window made ENTIRELY of NaN differs (neutral instead of
+// NaN), which localmax/localmin never show because they output the untouched centre value.
+template <bool WANT_MAX> __device__ __forceinline__ double ext_ieee (double a, double b)
 	{ return WANT_MAX ? fmax (a, b) : fmin (a, b); }
+template <bool WANT_MAX> __device__ __forceinline__ double ext (double a, double b)
+	{ return WANT_MAX ? ((b > a) ? b : a) : ((b < a) ? b : a); }
+__device__ __forceinline__ double sanitize (double v, double neutral) { return (v == v) ? v : neutral; }
 
 template <int LOGE> __device__ __forceinline__ uint32_t mm_pad (uint32_t j) { return j + (j >> LOGE); }
 
@@ -59,7 +67,7 @@ k_extrema (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, i
 	const uint32_t j0 = threadIdx.x * E;
 	double a[E];
 	#pragma unroll
-	for (int e = 0; e < E; e++) a[e] = A[mm_pad<LOGE> (j0 + e)];
+	for (int e = 0; e < E; e++) a[e] = sanitize (A[mm_pad<LOGE> (j0 + e)], NEUTRAL);
 	const uint32_t m0 = j0 % Wn;
 
 	// ---------------- forward: blocks restart where j % Wn == 0 ----------------
@@ -193,7 +201,7 @@ k_extrema_small (const SegDev* __restrict__ segs, const uint64_t* __restrict__ b
 	const uint32_t j0 = threadIdx.x * MS_STRIP;
 	double x[MS_STRIP + P - 1];
 	#pragma unroll
-	for (int e = 0; e < MS_STRIP + P - 1; e++) x[e] = s_x[ms_pad (j0 + e)];
+	for (int e = 0; e < MS_STRIP + P - 1; e++) x[e] = sanitize (s_x[ms_pad (j0 + e)], NEUTRAL);
 	#pragma unroll
 	for (int lev = 0; lev < LOGP; lev++)
 		{
@@ -208,18 +216,33 @@ k_extrema_small (const SegDev* __restrict__ segs, const uint64_t* __restrict__ b
 	__syncthreads ();
 
 	const uint32_t shift = Wn - P;                              // 0 <= shift < P <= MS_MARGIN
-	// consecutive lanes take consecutive outputs: conflict-free table reads, 256-byte coalesced stores
-	double* o = out + t0;
-	#pragma unroll 4
-	for (uint32_t c = threadIdx.x; c < nOut; c += MS_THREADS)
+	// every thread finishes its own 8 outputs: A[c] is still in registers, A[c+shift] and the centre
+	// value come from the padded tables at a lane stride of 9 cells (conflict-free), and the 64 bytes
+	// of results leave as two full-sector 256-bit stores
+	if (j0 < nOut)
 		{
-		double w = ext<WANT_MAX> (s_a[ms_pad (c)], s_a[ms_pad (c + shift)]);
-		if (MODE == 1)
+		double w[MS_STRIP];
+		#pragma unroll
+		for (int e = 0; e < MS_STRIP; e++)
 			{
-			const double v = s_x[ms_pad (c + reachL)];
-			w = (WANT_MAX ? (w > v) : (w < v)) ? fill : v;
+			w[e] = ext<WANT_MAX> (x[e], s_a[ms_pad (j0 + e + shift)]);
+			if (MODE == 1)
+				{
+				const double v = s_x[ms_pad (j0 + e + reachL)];
+				w[e] = (WANT_MAX ? (w[e] > v) : (w[e] < v)) ? fill : v;
+				}
 			}
-		o[c] = w;
+		double* o = out + t0 + j0;
+		if (j0 + MS_STRIP <= nOut)
+			{
+			stg_stream4 (o,     w[0], w[1], w[2], w[3]);
+			stg_stream4 (o + 4, w[4], w[5], w[6], w[7]);
+			}
+		else
+			{
+			#pragma unroll
+			for (int e = 0; e < MS_STRIP; e++) if (j0 + e < nOut) o[e] = w[e];
+			}
 		}
 	}
 
@@ -250,7 +273,7 @@ k_extrema_wide (const SegDev* __restrict__ segs, const uint64_t* __restrict__ ba
 	uint64_t a = (i - sd.dlo > reachL) ? i - reachL : sd.dlo;
 	uint64_t b = (sd.dhi - 1 - i > reachR) ? i + reachR : sd.dhi - 1;
 	double w = in[a];
-	for (uint64_t j = a + 1; j <= b; j++) w = ext<WANT_MAX> (w, in[j]);
+	for (uint64_t j = a + 1; j <= b; j++) w = ext_ieee<WANT_MAX> (w, in[j]);
 	if (MODE == 0) out[i] = w;
 	else
 		{
@@ -307,6 +330,7 @@ extern "C" int gdsp_local_extrema (gdsp_ctx* c, const gdsp_layout* L_, const dou
 	gdsp_layout* L = (gdsp_layout*) L_;
 	GDSP_REQUIRE (c && L && in && out, "gdsp_local_extrema: NULL argument");
 	GDSP_REQUIRE (in != out, "gdsp_local_extrema: in and out must be different buffers");
+	GDSP_REQUIRE_ALIGNED (out, "gdsp_local_extrema");
 	GDSP_REQUIRE (neighborhood >= 1, "gdsp_local_extrema: neighborhood must be positive");
 	uint32_t h = (neighborhood - 1) / 2;
 	return wantMax ? launch_extrema<true, 1>  (c, L, in, out, h, h, fill)
@@ -319,6 +343,7 @@ extern "C" int gdsp_best_extrema (gdsp_ctx* c, const gdsp_layout* L_, const doub
 	gdsp_layout* L = (gdsp_layout*) L_;
 	GDSP_REQUIRE (c && L && in && out, "gdsp_best_extrema: NULL argument");
 	GDSP_REQUIRE (in != out, "gdsp_best_extrema: in and out must be different buffers");
+	GDSP_REQUIRE_ALIGNED (out, "gdsp_best_extrema");
 	GDSP_REQUIRE (window >= 1, "gdsp_best_extrema: window must be positive");
 	uint32_t l = (window - 1) / 2, r = (window - 1) - l;
 	return wantMax ? launch_extrema<true, 0>  (c, L, in, out, l, r, 0.0)

@@ -746,6 +746,182 @@ k_pct_pass (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, 
 		if (s_cnt[i]) atomicAdd (&counts[i], (unsigned long long) s_cnt[i]);
 	}
 
+// ---------------------------------------------------------------------------
+// k_pct_pass_small<NB>: the same counting / compaction pass for NB <= 2 bounds (one open
+// percentile, the common case), written for issue rate: a lane reads 4 consecutive cells with one
+// 256-bit load, the region counts are kept as four CUMULATIVE per-thread counters (key < k0,
+// key <= k0, key < k1, key <= k1 -- two integer compares and a predicated add each) and the
+// compaction branch is taken only by warps that actually hold a candidate.  Edge tiles (shorter
+// than PCT_TILE) and stride > 1 take a scalar path.
+// ---------------------------------------------------------------------------
+
+struct PctSmall
+	{
+	unsigned long long k0, k1;
+	unsigned int       cmask;          // bit o: compact open region o
+	int                limits;         // 0: every value qualifies (no --min/--max)
+	};
+
+template <int NB>
+struct PctAcc
+	{
+	unsigned int tot, lt0, le0, lt1, le1;
+	__device__ __forceinline__ void clear () { tot = lt0 = le0 = lt1 = le1 = 0; }
+	// returns true when the cell must be compacted
+	__device__ __forceinline__ bool add (const PctSmall& P, double v, bool q)
+		{
+		const unsigned long long k = f64_key (v);
+		tot += q;
+		bool a0 = false, b0 = false, a1 = false, b1 = false;
+		if (NB >= 1) { a0 = q && (k < P.k0);  b0 = q && (k <= P.k0);  lt0 += a0;  le0 += b0; }
+		if (NB >= 2) { a1 = q && (k < P.k1);  b1 = q && (k <= P.k1);  lt1 += a1;  le1 += b1; }
+		int  o   = 0;
+		bool isB = false;
+		if (NB >= 1) { o = b0 ? 0 : 1;  isB = b0 && !a0; }
+		if (NB >= 2) { o += b1 ? 0 : 1; isB = isB || (b1 && !a1); }
+		return q && !isB && ((P.cmask >> o) & 1u);
+		}
+	};
+
+__device__ __forceinline__ void pct_compact (bool c, double v, double* __restrict__ cand, unsigned long long cap,
+                                             unsigned long long* __restrict__ ncand)
+	{
+	const int lane = threadIdx.x & 31;
+	const unsigned cm = __ballot_sync (0xffffffffu, c);
+	if (cm)
+		{
+		unsigned long long b0 = 0;
+		if (lane == __ffs (cm) - 1) b0 = atomicAdd (ncand, (unsigned long long) __popc (cm));
+		b0 = __shfl_sync (0xffffffffu, b0, __ffs (cm) - 1);
+		if (c)
+			{
+			const unsigned long long slot = b0 + __popc (cm & ((1u << lane) - 1u));
+			if (slot < cap) cand[slot] = v;
+			}
+		}
+	}
+
+template <int NB>
+__global__ void __launch_bounds__(256)
+k_pct_pass_small (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg, uint64_t ntiles,
+                  const double* __restrict__ sig, uint32_t stride, double mn, double mx,
+                  const PctSmall P, unsigned long long* __restrict__ counts,
+                  double* __restrict__ cand, unsigned long long cap, unsigned long long* __restrict__ ncand)
+	{
+	__shared__ unsigned int s_cnt[5];
+	if (threadIdx.x < 5) s_cnt[threadIdx.x] = 0;
+	__syncthreads ();
+	PctAcc<NB> A;  A.clear ();
+
+	for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x)
+		{
+		int seg;  uint64_t tis;
+		tile_to_seg (base, nseg, t, seg, tis);
+		const SegDev sd = segs[seg];
+		const uint64_t t0 = sd.lo + tis * PCT_TILE;
+		const uint32_t n  = (uint32_t) ((sd.hi - t0 < PCT_TILE) ? (sd.hi - t0) : PCT_TILE);
+		const double* p = sig + t0;
+		if (n == PCT_TILE && stride == 1)
+			{
+			// 8 rounds of 256 lanes x 4 cells, two rounds in flight
+			#pragma unroll 1
+			for (uint32_t j0 = 0; j0 < PCT_TILE; j0 += 2048)
+				{
+				double v[8];
+				ldg_stream4 (p + j0 + 4 * threadIdx.x,        v[0], v[1], v[2], v[3]);
+				ldg_stream4 (p + j0 + 1024 + 4 * threadIdx.x, v[4], v[5], v[6], v[7]);
+				bool cc[8];  bool any = false;
+				#pragma unroll
+				for (int u = 0; u < 8; u++)
+					{
+					const bool q = P.limits ? (!(v[u] < mn) && !(v[u] > mx)) : true;
+					cc[u] = A.add (P, v[u], q);
+					any = any || cc[u];
+					}
+				if (__any_sync (0xffffffffu, any))
+					{
+					#pragma unroll
+					for (int u = 0; u < 8; u++) pct_compact (cc[u], v[u], cand, cap, ncand);
+					}
+				}
+			}
+		else
+			{
+			for (uint32_t j0 = 0; j0 < n; j0 += 256)
+				{
+				const uint32_t j = j0 + threadIdx.x;
+				bool q = (j < n);
+				if (q && stride > 1) q = (((uint64_t) sd.pos0 + (t0 - sd.lo) + j) % stride) == 0;
+				const double v = q ? p[j] : 0.0;
+				q = q && !(v < mn) && !(v > mx);
+				const bool c = A.add (P, v, q);
+				pct_compact (c, v, cand, cap, ncand);
+				}
+			}
+		}
+
+	unsigned int x[5] = { A.tot, A.lt0, A.le0, A.lt1, A.le1 };
+	#pragma unroll
+	for (int r = 0; r < 5; r++)
+		{
+		#pragma unroll
+		for (int d = 16; d > 0; d >>= 1) x[r] += __shfl_xor_sync (0xffffffffu, x[r], d);
+		if ((threadIdx.x & 31) == 0 && x[r]) atomicAdd (&s_cnt[r], x[r]);
+		}
+	__syncthreads ();
+	if (threadIdx.x == 0)
+		{
+		// cumulative counts -> region populations (region 2i+1 = "equals bound i")
+		const unsigned long long tot = s_cnt[0], lt0 = s_cnt[1], le0 = s_cnt[2], lt1 = s_cnt[3], le1 = s_cnt[4];
+		if (NB == 0) { if (tot) atomicAdd (&counts[0], tot); }
+		if (NB == 1)
+			{
+			if (lt0)       atomicAdd (&counts[0], lt0);
+			if (le0 - lt0) atomicAdd (&counts[1], le0 - lt0);
+			if (tot - le0) atomicAdd (&counts[2], tot - le0);
+			}
+		if (NB == 2)
+			{
+			if (lt0)       atomicAdd (&counts[0], lt0);
+			if (le0 - lt0) atomicAdd (&counts[1], le0 - lt0);
+			if (lt1 - le0) atomicAdd (&counts[2], lt1 - le0);
+			if (le1 - lt1) atomicAdd (&counts[3], le1 - lt1);
+			if (tot - le1) atomicAdd (&counts[4], tot - le1);
+			}
+		}
+	}
+
+// one counting / compaction pass over the layout (d_counts, d_ncand already zeroed)
+static int pct_launch_pass (gdsp_ctx* c, gdsp_layout* L, const TileMap& tmPct, const double* sig, uint32_t stride,
+                            double mn, double mx, const PctBounds& B, unsigned long long* d_counts,
+                            double* d_cand, unsigned long long cap, unsigned long long* d_ncand)
+	{
+	int grid = c->sm_count * 8;
+	if ((uint64_t) grid > tmPct.ntiles) grid = (int) tmPct.ntiles;
+	if (B.nb <= 2 && (((uintptr_t) sig) & 31u) == 0)
+		{
+		PctSmall P;
+		P.k0 = (B.nb >= 1) ? B.key[0] : 0;  P.k1 = (B.nb >= 2) ? B.key[1] : 0;
+		P.cmask = 0;
+		for (int r = 0; r <= B.nb; r++) if (B.compact[r]) P.cmask |= 1u << r;
+		P.limits = !(mn == -HUGE_VAL && mx == HUGE_VAL);
+		// persistent grid: exactly the blocks that are resident at once (a larger grid runs a ragged second wave)
+		int perSM = 0;
+		GDSP_CUDA (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&perSM, k_pct_pass_small<2>, 256, 0));
+		grid = c->sm_count * (perSM > 0 ? perSM : 1);
+		if ((uint64_t) grid > tmPct.ntiles) grid = (int) tmPct.ntiles;
+		if (B.nb == 0)      k_pct_pass_small<0><<<grid, 256, 0, c->stream>>> (L->d, tmPct.d_base, L->nseg, tmPct.ntiles, sig, stride, mn, mx, P, d_counts, d_cand, cap, d_ncand);
+		else if (B.nb == 1) k_pct_pass_small<1><<<grid, 256, 0, c->stream>>> (L->d, tmPct.d_base, L->nseg, tmPct.ntiles, sig, stride, mn, mx, P, d_counts, d_cand, cap, d_ncand);
+		else                k_pct_pass_small<2><<<grid, 256, 0, c->stream>>> (L->d, tmPct.d_base, L->nseg, tmPct.ntiles, sig, stride, mn, mx, P, d_counts, d_cand, cap, d_ncand);
+		}
+	else if (B.nb <= 2)
+		k_pct_pass<true><<<grid, 256, 0, c->stream>>> (L->d, tmPct.d_base, L->nseg, tmPct.ntiles, sig, stride, mn, mx, B, d_counts, d_cand, cap, d_ncand);
+	else
+		k_pct_pass<false><<<grid, 256, 0, c->stream>>> (L->d, tmPct.d_base, L->nseg, tmPct.ntiles, sig, stride, mn, mx, B, d_counts, d_cand, cap, d_ncand);
+	GDSP_KERNEL_CHECK ();
+	return GDSP_OK;
+	}
+
 static inline unsigned long long host_key (double v)
 	{
 	unsigned long long b;  memcpy (&b, &v, 8);
@@ -820,7 +996,9 @@ extern "C" int gdsp_percentiles (gdsp_ctx* c, const gdsp_layout* L_, const doubl
 	bool haveCount = false;
 	if (nslots == 0) { *h_num_samples = 0;  return GDSP_OK; }
 
-	std::vector<double> hs;                              // sorted sample (host copy)
+	double* hs = NULL;                                   // sorted sample (page-locked host copy)
+	size_t  nhs = 0;
+	{ void* hp;  GDSP_TRY (gdsp_host_scratch (c, sizeof (double) * PCT_SAMPLES, &hp));  hs = (double*) hp; }
 	for (int iter = 0; iter < 80; iter++)
 		{
 		// jobs still open in this iteration (at most PCT_MAXB/2 at a time)
@@ -840,7 +1018,7 @@ extern "C" int gdsp_percentiles (gdsp_ctx* c, const gdsp_layout* L_, const doubl
 		unsigned int scount = 0;
 		GDSP_CUDA (cudaMemcpyAsync (&scount, d_scount, 4, cudaMemcpyDeviceToHost, c->stream));
 		GDSP_CUDA (cudaStreamSynchronize (c->stream));
-		hs.resize (scount);
+		nhs = scount;
 		if (scount > 0)
 			{
 			SortPlan lp;
@@ -848,7 +1026,7 @@ extern "C" int gdsp_percentiles (gdsp_ctx* c, const gdsp_layout* L_, const doubl
 			OutMap lin;  lin.nseg = 0;  lin.prefix = NULL;  lin.segs = NULL;
 			double* res = NULL;  int passes = 0;
 			GDSP_TRY (radix_sort (c, lp, lp, bufA, bufA, bufB, lin, sc, &res, &passes));
-			GDSP_CUDA (cudaMemcpyAsync (hs.data (), res, sizeof (double) * scount, cudaMemcpyDeviceToHost, c->stream));
+			GDSP_CUDA (cudaMemcpyAsync (hs, res, sizeof (double) * scount, cudaMemcpyDeviceToHost, c->stream));
 			GDSP_CUDA (cudaStreamSynchronize (c->stream));
 			}
 
@@ -861,10 +1039,10 @@ extern "C" int gdsp_percentiles (gdsp_ctx* c, const gdsp_layout* L_, const doubl
 			{
 			unsigned long long lo = jobs[i].keyLo, hi = jobs[i].keyHi;
 			// the part of the sorted sample that lies inside this job's bracket
-			size_t a = std::lower_bound (hs.begin (), hs.end (), lo,
-			               [] (double x, unsigned long long k) { return host_key (x) < k; }) - hs.begin ();
-			size_t b = std::upper_bound (hs.begin (), hs.end (), hi,
-			               [] (unsigned long long k, double x) { return k < host_key (x); }) - hs.begin ();
+			size_t a = std::lower_bound (hs, hs + nhs, lo,
+			               [] (double x, unsigned long long k) { return host_key (x) < k; }) - hs;
+			size_t b = std::upper_bound (hs, hs + nhs, hi,
+			               [] (unsigned long long k, double x) { return k < host_key (x); }) - hs;
 			const size_t ns = b - a;
 			double f = -1;
 			if (!jobs[i].haveCounts) f = (jobs[i].pMilli >= 100000) ? 1.0 : jobs[i].pMilli / 100000.0;
@@ -900,15 +1078,7 @@ extern "C" int gdsp_percentiles (gdsp_ctx* c, const gdsp_layout* L_, const doubl
 		const int nreg = 2 * B.nb + 1;
 		GDSP_CUDA (cudaMemsetAsync (d_counts, 0, sizeof (unsigned long long) * nreg, c->stream));
 		GDSP_CUDA (cudaMemsetAsync (d_ncand, 0, 8, c->stream));
-		int grid = c->sm_count * 8;
-		if ((uint64_t) grid > tmPct.ntiles) grid = (int) tmPct.ntiles;
-		if (B.nb <= 2)
-			k_pct_pass<true><<<grid, 256, 0, c->stream>>> (L->d, tmPct.d_base, L->nseg, tmPct.ntiles, sig, stride, mn, mx,
-			        B, d_counts, bufA, candCapTotal, d_ncand);
-		else
-			k_pct_pass<false><<<grid, 256, 0, c->stream>>> (L->d, tmPct.d_base, L->nseg, tmPct.ntiles, sig, stride, mn, mx,
-			        B, d_counts, bufA, candCapTotal, d_ncand);
-		GDSP_KERNEL_CHECK ();
+		GDSP_TRY (pct_launch_pass (c, L, tmPct, sig, stride, mn, mx, B, d_counts, bufA, candCapTotal, d_ncand));
 		std::vector<unsigned long long> counts (nreg);
 		unsigned long long ncand = 0;
 		GDSP_CUDA (cudaMemcpyAsync (counts.data (), d_counts, sizeof (unsigned long long) * nreg, cudaMemcpyDeviceToHost, c->stream));
@@ -1073,15 +1243,7 @@ extern "C" int gdsp_pct_count (gdsp_ctx* c, const gdsp_layout* L_, const double*
 	const int nreg = 2 * nb + 1;
 	GDSP_CUDA (cudaMemsetAsync (d_counts, 0, sizeof (unsigned long long) * nreg, c->stream));
 	GDSP_CUDA (cudaMemsetAsync (d_ncand, 0, 8, c->stream));
-	int grid = c->sm_count * 8;
-	if ((uint64_t) grid > tmPct.ntiles) grid = (int) tmPct.ntiles;
-	if (nb <= 2)
-		k_pct_pass<true><<<grid, 256, 0, c->stream>>> (L->d, tmPct.d_base, L->nseg, tmPct.ntiles, sig, stride, mn, mx,
-		        B, d_counts, d_cand, cap, d_ncand);
-	else
-		k_pct_pass<false><<<grid, 256, 0, c->stream>>> (L->d, tmPct.d_base, L->nseg, tmPct.ntiles, sig, stride, mn, mx,
-		        B, d_counts, d_cand, cap, d_ncand);
-	GDSP_KERNEL_CHECK ();
+	GDSP_TRY (pct_launch_pass (c, L, tmPct, sig, stride, mn, mx, B, d_counts, d_cand, cap, d_ncand));
 	std::vector<unsigned long long> counts (nreg);
 	unsigned long long ncand = 0;
 	GDSP_CUDA (cudaMemcpyAsync (counts.data (), d_counts, sizeof (unsigned long long) * nreg, cudaMemcpyDeviceToHost, c->stream));

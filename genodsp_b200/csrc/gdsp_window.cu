@@ -320,7 +320,7 @@ k_smooth (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, in
 	if (i0 + SM_R <= n)
 		{
 		#pragma unroll
-		for (int r = 0; r < SM_R; r += 2) stg_stream (o + r, make_double2 (acc[r], acc[r + 1]));
+		for (int r = 0; r < SM_R; r += 4) stg_stream4 (o + r, acc[r], acc[r + 1], acc[r + 2], acc[r + 3]);
 		}
 	else
 		{
@@ -430,7 +430,7 @@ k_smooth_ct (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base,
 	if (i0 + R <= n)
 		{
 		#pragma unroll
-		for (int r = 0; r < R; r += 2) stg_stream (o + r, make_double2 (acc[r], acc[r + 1]));
+		for (int r = 0; r < R; r += 4) stg_stream4 (o + r, acc[r], acc[r + 1], acc[r + 2], acc[r + 3]);
 		}
 	else
 		{
@@ -534,6 +534,7 @@ extern "C" int gdsp_smooth (gdsp_ctx* c, const gdsp_layout* L_, const double* in
 	gdsp_layout* L = (gdsp_layout*) L_;
 	GDSP_REQUIRE (c && L && in && out && h_taps, "gdsp_smooth: NULL argument");
 	GDSP_REQUIRE (in != out, "gdsp_smooth: in and out must be different buffers");
+	GDSP_REQUIRE_ALIGNED (out, "gdsp_smooth");
 	GDSP_REQUIRE (W >= 1, "gdsp_smooth: window must be positive");
 	TileMap tm;
 	if (W <= SC_MAXW)

@@ -100,9 +100,14 @@ class Genome:
         self.tmp = torch.zeros(self.buffer_cells, dtype=torch.float64, device=self.device)
         self._work = None
         self.cells = int(self.lib.gdsp_layout_cells(self.layout))
-        self.launches = 0
+        self._launch0 = self.lib.gdsp_launch_count()
 
     # ------------------------------------------------------------------ plumbing
+    @property
+    def launches(self):
+        """kernels launched by the library since this genome was created (gdsp_launch_count)"""
+        return int(self.lib.gdsp_launch_count() - self._launch0)
+
     def close(self):
         if getattr(self, "layout", None):
             self.lib.gdsp_layout_destroy(self.layout); self.layout = None
@@ -149,7 +154,7 @@ class Genome:
         return self.sig[lo:hi].cpu().numpy()
 
     def fill(self, value=0.0):
-        check(self.lib.gdsp_fill(self.ctx, self.layout, self._p(self.sig), float(value))); self.launches += 1
+        check(self.lib.gdsp_fill(self.ctx, self.layout, self._p(self.sig), float(value)))
 
     # ------------------------------------------------------------------ input
     def accumulate(self, seg, start, end, val=None, mode=None, add=False, host=True):
@@ -176,7 +181,6 @@ class Genome:
             check(self.lib.gdsp_accumulate_dev(self.ctx, self.layout, self._p(self.sig), self.buffer_cells,
                                                self._p(work), self._p(seg), self._p(start), self._p(end),
                                                vp, n, mode, int(add)))
-        self.launches += 3
 
     def accumulate_pinned(self, seg, start, end, val=None, mode=None, add=False):
         """like accumulate(host=True) for torch CPU tensors in pinned memory"""
@@ -188,18 +192,16 @@ class Genome:
         check(self.lib.gdsp_accumulate_host(self.ctx, self.layout, self._p(self.sig), self.buffer_cells,
                                             self._p(work), C.c_void_p(seg.data_ptr()), C.c_void_p(start.data_ptr()),
                                             C.c_void_p(end.data_ptr()), vp, int(seg.shape[0]), mode, int(add)))
-        self.launches += 3
 
     # ------------------------------------------------------------------ sum.c
     def sum(self, window=100, denom=1.0, denom_actual=False, zero=0.0, window_is_chromosome=False):
         check(self.lib.gdsp_block_sum(self.ctx, self.layout, self._p(self.sig), int(window),
                                       int(window_is_chromosome), float(denom), int(denom_actual), float(zero)))
-        self.launches += 1
 
     def slidingsum(self, window=100, denom=1.0):
         check(self.lib.gdsp_sliding_sum(self.ctx, self.layout, self._p(self.sig), self._p(self.tmp),
                                         int(window), float(denom)))
-        self._swap(); self.launches += 1
+        self._swap()
 
     def smooth(self, window=101):
         W = int(window)
@@ -208,11 +210,10 @@ class Genome:
         taps = hann_taps(W)
         check(self.lib.gdsp_smooth(self.ctx, self.layout, self._p(self.sig), self._p(self.tmp), W,
                                    taps.ctypes.data_as(C.POINTER(C.c_double))))
-        self._swap(); self.launches += 1
+        self._swap()
 
     def cumulativesum(self):
         check(self.lib.gdsp_cumulative_sum(self.ctx, self.layout, self._p(self.sig), self._p(self.sig)))
-        self.launches += 1
 
     # ------------------------------------------------------------------ minmax.c
     @staticmethod
@@ -223,20 +224,20 @@ class Genome:
     def localmax(self, neighborhood=3, zero=0.0):
         check(self.lib.gdsp_local_extrema(self.ctx, self.layout, self._p(self.sig), self._p(self.tmp),
                                           self._odd3(neighborhood), 1, float(zero)))
-        self._swap(); self.launches += 1
+        self._swap()
 
     def localmin(self, neighborhood=3, infinity=DBL_MAX):
         check(self.lib.gdsp_local_extrema(self.ctx, self.layout, self._p(self.sig), self._p(self.tmp),
                                           self._odd3(neighborhood), 0, float(infinity)))
-        self._swap(); self.launches += 1
+        self._swap()
 
     def bestmax(self, window=100):
         check(self.lib.gdsp_best_extrema(self.ctx, self.layout, self._p(self.sig), self._p(self.tmp), int(window), 1))
-        self._swap(); self.launches += 1
+        self._swap()
 
     def bestmin(self, window=100):
         check(self.lib.gdsp_best_extrema(self.ctx, self.layout, self._p(self.sig), self._p(self.tmp), int(window), 0))
-        self._swap(); self.launches += 1
+        self._swap()
 
     # ------------------------------------------------------------------ morphology.c
     def _morph(self, kind, length, left, right, threshold, one, zero):
@@ -245,7 +246,6 @@ class Genome:
         check(self.lib.gdsp_morphology(self.ctx, self.layout, self._p(self.sig), self.buffer_cells, self._p(work),
                                        kind, float(length), int(left), int(right), float(threshold),
                                        float(one), float(zero)))
-        self.launches += 3
 
     def close_(self, length, threshold=0.0, one=1.0, zero=0.0):
         self._morph(capi.MORPH_CLOSE, length, 0, 0, threshold, one, zero)
@@ -273,7 +273,6 @@ class Genome:
             arr[i].code, arr[i].a, arr[i].b, arr[i].c, arr[i].flags = int(op[0]), float(op[1]), float(op[2]), float(op[3]), int(op[4])
             arr[i].table = op[5].handle if op[5] is not None else None
         check(self.lib.gdsp_pointwise(self.ctx, self.layout, self._p(self.sig), self._p(self.sig), arr, len(ops)))
-        self.launches += 1
 
     @staticmethod
     def op_binarize(threshold=0.0, ties_above=False, one=1.0, zero=0.0):
@@ -325,7 +324,6 @@ class Genome:
         a, b, n = C.c_double(), C.c_double(), C.c_uint64()
         check(self.lib.gdsp_minmax(self.ctx, self.layout, self._p(self.sig), int(stride), float(mn), float(mx),
                                    C.byref(a), C.byref(b), C.byref(n)))
-        self.launches += 1
         return a.value, b.value, int(n.value)
 
     def invert(self, mid=None):
@@ -362,7 +360,6 @@ class Genome:
         n = C.c_uint64()
         check(self.lib.gdsp_percentiles(self.ctx, self.layout, self._p(self.sig), self._p(self.tmp), self.buffer_cells,
                                         int(window), float(mn), float(mx), pm, len(ps), vals, C.byref(n)))
-        self.launches += 4
         self.num_samples = int(n.value)
         if self.num_samples == 0:
             return out
@@ -381,7 +378,6 @@ class Genome:
                                         C.byref(flag)))
         if flag.value:
             self._swap()
-        self.launches += 8
 
     # ------------------------------------------------------------------ clump.c
     def clump(self, average=0.0, length=100, relative_length=0.0, above=True, one=1.0, zero=0.0):
@@ -408,7 +404,6 @@ class Genome:
             first = (C.c_uint64 * (self.nseg + 1))()
             st = self.lib.gdsp_runs(self.ctx, self.layout, self._p(self.sig), int(collapse), int(show_uncovered),
                                     self._p(s), self._p(e), self._p(v), cap, C.byref(n), first)
-            self.launches += 1
             if st == capi.ERR_CAPACITY:
                 cap = int(n.value) + 16
                 continue

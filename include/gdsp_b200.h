@@ -70,6 +70,8 @@ void gdsp_ctx_destroy  (gdsp_ctx* ctx);
 int  gdsp_ctx_set_stream (gdsp_ctx* ctx, void* stream);
 int  gdsp_sync         (gdsp_ctx* ctx);
 const char* gdsp_last_error (void);
+/* number of kernels this library has launched in the calling process (all contexts) */
+uint64_t gdsp_launch_count (void);
 const char* gdsp_version    (void);
 int  gdsp_device_info  (gdsp_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor,
                         size_t* free_bytes, size_t* total_bytes);

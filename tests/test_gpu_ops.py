@@ -123,6 +123,62 @@ def test_accumulate(genome, orc, novalue):
         assert np.array_equal(genome.get_chrom(name), 2 * before[name])
 
 
+@pytest.mark.parametrize("path", ["host", "dev"])
+@pytest.mark.parametrize("force_diff", [False, True])
+@pytest.mark.parametrize("shape", ["uniform", "sorted_pileup", "long", "edges"])
+def test_accumulate_unit_paths(genome, orc, monkeypatch, path, force_diff, shape):
+    """unit-weight depth: the binned path (events bucketed per 16384-cell tile, counts in shared
+    memory) and the difference-array path must both give the reference loop's result
+    (genodsp.c:1325-1329), from host arrays and from device arrays"""
+    import torch
+    if force_diff:
+        monkeypatch.setenv("GDSP_ACCUMULATE_DIFF", "1")
+    rng = np.random.default_rng({"uniform": 11, "sorted_pileup": 12, "long": 13, "edges": 14}[shape])
+    m = 30000
+    seg = rng.integers(0, genome.nseg, m).astype(np.uint32)
+    lens = np.array([genome.segs[k][5] for k in seg])
+    if shape == "uniform":
+        start = (rng.random(m) * lens).astype(np.uint32)
+        end = np.minimum(lens, start + rng.integers(0, 300, m)).astype(np.uint32)
+    elif shape == "sorted_pileup":
+        # position-sorted reads with heavy duplicates: whole warps hit one bucket / one cell
+        seg = np.sort(seg); lens = np.array([genome.segs[k][5] for k in seg])
+        start = ((rng.integers(0, 40, m) / 40.0) * lens).astype(np.uint32)
+        order = np.lexsort((start, seg)); seg, start, lens = seg[order], start[order], lens[order]
+        end = np.minimum(lens, start + 100).astype(np.uint32)
+    elif shape == "long":
+        # intervals much longer than a tile, many reaching the chromosome end
+        start = (rng.random(m) * lens * 0.5).astype(np.uint32)
+        end = np.minimum(lens, start + rng.integers(0, 200000, m)).astype(np.uint32)
+    else:
+        # empty intervals, whole-chromosome intervals, single cells at both ends, unknown segment ids
+        start = np.where(rng.random(m) < 0.5, 0, np.maximum(lens, 1) - 1).astype(np.uint32)
+        end = np.where(rng.random(m) < 0.3, start, np.where(rng.random(m) < 0.5, lens, np.minimum(lens, start + 1))).astype(np.uint32)
+        seg[::97] = genome.nseg + 3
+    genome.fill(7.0)                        # must be overwritten, not added to
+    if path == "host":
+        genome.accumulate(seg, start, end)
+    else:
+        dev = torch.device("cuda", 0)
+        t = [torch.from_numpy(a.astype(np.int64)).to(dev).to(torch.int32) for a in (seg, start, end)]
+        genome.accumulate(t[0], t[1], t[2], host=False)
+        torch.cuda.synchronize()
+    for k in range(genome.nseg):
+        name, n = genome.chroms[genome.seg_chrom[k]]
+        sel = seg == k
+        v = np.zeros(n)
+        orc.accumulate(v, start[sel], end[sel], None)
+        got = genome.get_chrom(name)
+        assert np.array_equal(bits(got), bits(v)), (name, np.nonzero(got != v)[0][:5])
+    before = {name: genome.get_chrom(name) for name, _ in CHROMS}
+    if path == "host":
+        genome.accumulate(seg, start, end, add=True)
+    else:
+        genome.accumulate(t[0], t[1], t[2], host=False, add=True)
+    for name, n in CHROMS:
+        assert np.array_equal(genome.get_chrom(name), 2 * before[name])
+
+
 @pytest.mark.parametrize("kind", KINDS)
 @pytest.mark.parametrize("W", [3, 100, 101, 1000, 5000])
 def test_sliding_sum(genome, orc, kind, W):
