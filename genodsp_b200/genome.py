@@ -109,6 +109,9 @@ class Genome:
         return int(self.lib.gdsp_launch_count() - self._launch0)
 
     def close(self):
+        for lay in getattr(self, "_piece_layouts", None) or []:
+            self.lib.gdsp_layout_destroy(lay)
+        self._piece_layouts = None
         if getattr(self, "layout", None):
             self.lib.gdsp_layout_destroy(self.layout); self.layout = None
         if getattr(self, "ctx", None):
@@ -211,6 +214,41 @@ class Genome:
         check(self.lib.gdsp_smooth(self.ctx, self.layout, self._p(self.sig), self._p(self.tmp), W,
                                    taps.ctypes.data_as(C.POINTER(C.c_double))))
         self._swap()
+
+    def smooth_to_host(self, window, out_host):
+        """smooth + device->host delivery of the result, pipelined per chromosome piece: while piece
+        k is on its way to `out_host` (a pinned float64 tensor of buffer_cells) on a copy stream, the
+        FIR of piece k+1 runs.  Same arithmetic as smooth(); returns the bytes copied."""
+        t = self.torch
+        W = int(window)
+        if W % 2 == 0:
+            W += 1
+        taps = hann_taps(W)
+        if getattr(self, "_piece_layouts", None) is None:
+            self._piece_layouts = []
+            for k in range(self.nseg):
+                one = (capi.Seg * 1)()
+                lo, hi, dlo, dhi, pos0, clen = self.segs[k]
+                one[0].lo, one[0].hi, one[0].dlo, one[0].dhi, one[0].pos0, one[0].chrom_len = lo, hi, dlo, dhi, pos0, clen
+                lay = C.c_void_p()
+                check(self.lib.gdsp_layout_create(self.ctx, one, 1, C.byref(lay)))
+                self._piece_layouts.append(lay)
+            self._copy_stream = t.cuda.Stream(device=self.device)
+        main = t.cuda.current_stream(self.device)
+        copied = 0
+        for k in range(self.nseg):
+            lo, hi = self.segs[k][0], self.segs[k][1]
+            check(self.lib.gdsp_smooth(self.ctx, self._piece_layouts[k], self._p(self.sig), self._p(self.tmp), W,
+                                       taps.ctypes.data_as(C.POINTER(C.c_double))))
+            done = t.cuda.Event(); done.record(main)
+            self._copy_stream.wait_event(done)
+            with t.cuda.stream(self._copy_stream):
+                out_host[lo:hi].copy_(self.tmp[lo:hi], non_blocking=True)
+            copied += 8 * (hi - lo)
+        fin = t.cuda.Event(); fin.record(self._copy_stream)
+        main.wait_event(fin)
+        self._swap()
+        return copied
 
     def cumulativesum(self):
         check(self.lib.gdsp_cumulative_sum(self.ctx, self.layout, self._p(self.sig), self._p(self.sig)))

@@ -98,6 +98,47 @@ def main():
         def bin_setup():
             reset(); g.binarize(9.0)
         rec("runs_binarized", timed(lambda: g.runs(cap=max(1024, N // 8)), bin_setup), 8)
+    # whole pipelines: wall time of the chain, with per-operator CUDA-event splits
+    def chain(name, ops):
+        evs = None
+        best = None
+        for r in range(args.reps + 1):
+            torch.cuda.synchronize()
+            marks = [torch.cuda.Event(enable_timing=True) for _ in range(len(ops) + 1)]
+            marks[0].record()
+            for k, (_, fn) in enumerate(ops):
+                fn(); marks[k + 1].record()
+            torch.cuda.synchronize()
+            ms = marks[0].elapsed_time(marks[-1])
+            if r > 0 and (best is None or ms < best):
+                best = ms; evs = [marks[k].elapsed_time(marks[k + 1]) for k in range(len(ops))]
+        out[name] = {"ms": round(best, 3), "gbp_s": round(N / (best / 1e3) / 1e9, 2),
+                     "ops": {ops[k][0]: round(evs[k], 3) for k in range(len(ops))}}
+        print(name, out[name], flush=True)
+
+    if on("pipe5"):
+        chain("pipe5_depth_smooth_localmax_percentile_binarize", [
+            ("depth", lambda: g.accumulate(seg, st, en, host=False)),
+            ("smooth101", lambda: g.smooth(101)),
+            ("localmax11", lambda: g.localmax(11)),
+            ("percentile99", lambda: g.percentile(99.0)),
+            ("binarize", lambda: g.binarize(g.variables["percentile99"])),
+            ("runs", lambda: g.runs(cap=max(1024, N // 8)))])
+    if on("cfg3"):
+        chain("cfg3_depth_sum100_percentile99_binarize", [
+            ("depth", lambda: g.accumulate(seg, st, en, host=False)),
+            ("sum100", lambda: g.sum(100, denom=100.0)),
+            ("percentile99", lambda: g.percentile(99.0)),
+            ("binarize", lambda: g.binarize(g.variables["percentile99"])),
+            ("runs", lambda: g.runs(cap=max(1024, N // 8)))])
+    if on("cfg4"):
+        chain("cfg4_depth_binarize_open_close_clump", [
+            ("depth", lambda: g.accumulate(seg, st, en, host=False)),
+            ("binarize6", lambda: g.binarize(6.0)),
+            ("open1001", lambda: g.open_(1001, 0.5)),
+            ("close1001", lambda: g.close_(1001, 0.5)),
+            ("clump", lambda: g.clump(0.5, 1000)),
+            ("runs", lambda: g.runs(cap=max(1024, N // 8)))])
     print(json.dumps({"scale": args.scale, "bases": N, "hbm_peak_gbs": peak, "stages": out}))
 
 

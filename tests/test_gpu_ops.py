@@ -192,6 +192,23 @@ def test_sliding_sum(genome, orc, kind, W):
             exact_fn=lambda v: _exact_sliding_sum(v, W, d))
 
 
+def test_smooth_to_host_matches_smooth(genome, orc):
+    """the pipelined smooth + device->host delivery used by bench.py's e2e leg: same bits as smooth()"""
+    import torch
+    inputs = load(genome, np.random.default_rng(77), "real")
+    out_h = torch.empty(genome.buffer_cells, dtype=torch.float64, pin_memory=True)
+    copied = genome.smooth_to_host(101, out_h)
+    torch.cuda.synchronize()
+    assert copied == 8 * sum(n for _, n in CHROMS)
+    host = out_h.numpy()
+    for k in range(genome.nseg):
+        name, n = genome.chroms[genome.seg_chrom[k]]
+        lo, hi = genome.segs[k][0], genome.segs[k][1]
+        want = orc.smooth(inputs[name].copy(), 101)
+        assert np.array_equal(bits(host[lo:hi]), bits(want)), name
+        assert np.array_equal(bits(genome.get_chrom(name)), bits(want)), name
+
+
 @pytest.mark.parametrize("kind", KINDS)
 @pytest.mark.parametrize("W", [3, 100, 101, 4096, 5000])
 def test_block_sum(genome, orc, kind, W):
