@@ -37,7 +37,7 @@ DEPTH = 5
 READ_MIN, READ_MAX = 50, 150
 FP64_NOMINAL = 148 * 64 * 1.965e9      # FP64 lanes * SMs * max SM clock (instructions/s)
 FP64_MEASURED = 1.745e13               # scripts/micro/fp64_peak.cu on this pool's B200 (gpurun, round 1)
-SMOOTH_TRAFFIC_BYTES_PER_BASE = None   # dram read+write per base of k_smooth_ct from ncu --set full (profiles/)
+SMOOTH_TRAFFIC_BYTES_PER_BASE = 15.99   # (24.71 GB read + 24.67 GB written) / 3,088,269,832 bases: ncu --set full, profiles/r1_bench_kernels_ncu_full.csv
 METRIC = "Gbp/s, hg38 depth accumulation + smooth --window=101 (fp64)"
 
 
