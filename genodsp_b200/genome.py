@@ -215,15 +215,8 @@ class Genome:
                                    taps.ctypes.data_as(C.POINTER(C.c_double))))
         self._swap()
 
-    def smooth_to_host(self, window, out_host):
-        """smooth + device->host delivery of the result, pipelined per chromosome piece: while piece
-        k is on its way to `out_host` (a pinned float64 tensor of buffer_cells) on a copy stream, the
-        FIR of piece k+1 runs.  Same arithmetic as smooth(); returns the bytes copied."""
-        t = self.torch
-        W = int(window)
-        if W % 2 == 0:
-            W += 1
-        taps = hann_taps(W)
+    def _ensure_piece_layouts(self):
+        """one single-segment layout per owned chromosome piece (for per-piece calls)"""
         if getattr(self, "_piece_layouts", None) is None:
             self._piece_layouts = []
             for k in range(self.nseg):
@@ -233,6 +226,57 @@ class Genome:
                 lay = C.c_void_p()
                 check(self.lib.gdsp_layout_create(self.ctx, one, 1, C.byref(lay)))
                 self._piece_layouts.append(lay)
+        return self._piece_layouts
+
+    # ------------------------------------------------------------------ per-rank pieces of the slab-sharded operators
+    def piece_add_constant(self, k, value):
+        """v += value on owned piece k only (carry fix-up of slab-sharded scans)"""
+        lay = self._ensure_piece_layouts()[k]
+        arr = (capi.PwOp * 1)()
+        arr[0].code, arr[0].a, arr[0].b, arr[0].c, arr[0].flags, arr[0].table = capi.PW_ADDCONST, float(value), 0.0, 0.0, 0, None
+        check(self.lib.gdsp_pointwise(self.ctx, lay, self._p(self.sig), self._p(self.sig), arr, 1))
+
+    def piece_last_values(self):
+        """value of the last owned cell of every piece (host floats)"""
+        idx = self.torch.tensor([hi - 1 for (lo, hi, *_r) in self.segs], dtype=self.torch.int64, device=self.device)
+        return self.sig[idx].cpu().numpy()
+
+    def pct_sample(self, m, stride=1, mn=-DBL_MAX, mx=DBL_MAX, key_lo=0, key_hi=2 ** 64 - 1, seed=1):
+        """gdsp_pct_sample -> (numpy samples, number of sample slots this rank owns)"""
+        m = int(m)
+        if self.tmp.numel() < m:
+            raise ValueError("sample larger than the scratch buffer")
+        cnt, slots = C.c_uint32(), C.c_uint64()
+        check(self.lib.gdsp_pct_sample(self.ctx, self.layout, self._p(self.sig), int(stride), float(mn), float(mx),
+                                       int(key_lo), int(key_hi), m, int(seed), self._p(self.tmp), C.byref(cnt), C.byref(slots)))
+        return self.tmp[:int(cnt.value)].cpu().numpy(), int(slots.value)
+
+    def pct_count(self, bound_keys, compact, stride=1, mn=-DBL_MAX, mx=DBL_MAX, cap=None):
+        """gdsp_pct_count -> (region counts numpy u64[2*nb+1], candidates numpy or None if over cap)"""
+        nb = len(bound_keys)
+        cap = int(cap) if cap else int(self.tmp.numel())
+        cap = min(cap, int(self.tmp.numel()))
+        bk = (C.c_uint64 * max(nb, 1))(*[int(k) for k in bound_keys])
+        cp = (C.c_uint8 * (nb + 1))(*[int(bool(x)) for x in compact])
+        counts = (C.c_uint64 * (2 * nb + 1))()
+        ncand = C.c_uint64()
+        check(self.lib.gdsp_pct_count(self.ctx, self.layout, self._p(self.sig), int(stride), float(mn), float(mx),
+                                      bk, nb, cp, counts, self._p(self.tmp), cap, C.byref(ncand)))
+        n = int(ncand.value)
+        cand = self.tmp[:n].cpu().numpy() if n <= cap else None
+        return np.array(list(counts), dtype=np.uint64), cand
+
+    def smooth_to_host(self, window, out_host):
+        """smooth + device->host delivery of the result, pipelined per chromosome piece: while piece
+        k is on its way to `out_host` (a pinned float64 tensor of buffer_cells) on a copy stream, the
+        FIR of piece k+1 runs.  Same arithmetic as smooth(); returns the bytes copied."""
+        t = self.torch
+        W = int(window)
+        if W % 2 == 0:
+            W += 1
+        taps = hann_taps(W)
+        self._ensure_piece_layouts()
+        if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = t.cuda.Stream(device=self.device)
         main = t.cuda.current_stream(self.device)
         copied = 0

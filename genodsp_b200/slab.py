@@ -78,3 +78,219 @@ def exchange_halos(buf, plan, dist):
         ops.append(dist.P2POp(dist.irecv, buf[r_lo:r_hi], peer))
     for req in dist.batch_isend_irecv(ops):
         req.wait()
+
+
+# ----------------------------------------------------------------------------------------------
+# Operators that need more than a halo: the carry / reduction layer of SURVEY 8(e).
+#
+# Every function below is written once for two drivers:
+#   * real ranks: `parts` = [this rank's Genome], `gather` = all_gather_object over torch.distributed
+#     (`dist_gather(dist)`), so every rank sees the list of all ranks' local values in rank order;
+#   * virtual ranks (tests on one GPU): `parts` = all the rank Genomes, `gather` = identity.
+# All decisions are taken from gathered values only, so every rank takes the same ones.
+# ----------------------------------------------------------------------------------------------
+
+import numpy as _np
+
+_KEY_MAX = (1 << 64) - 1
+_SIGN = _np.uint64(1 << 63)
+
+
+def dist_gather(dist):
+    """gather(local_values) for real ranks: local_values has ONE entry (this rank's)"""
+    def gather(local_values):
+        out = [None] * dist.get_world_size()
+        dist.all_gather_object(out, local_values[0])
+        return out
+    return gather
+
+
+def virtual_gather(local_values):
+    return list(local_values)
+
+
+def f64_keys(a):
+    """order-preserving u64 keys of doubles (the kernels' f64_key): -0.0 just below +0.0"""
+    b = _np.ascontiguousarray(a, _np.float64).view(_np.uint64)
+    neg = (b & _SIGN) != 0
+    return _np.where(neg, ~b, b | _SIGN)
+
+
+def key_f64(k):
+    k = _np.uint64(k)
+    b = (k & ~_SIGN) if (k & _SIGN) else ~k
+    return float(_np.array([b], dtype=_np.uint64).view(_np.float64)[0])
+
+
+def _pct_rank(n, p_milli):
+    # (u32)((u64) numValues * p / 100000.0), percentile.c:588/:686; p = 100 % -> the largest sample
+    if p_milli >= 100000:
+        return n - 1
+    r = int(_np.uint32(_np.float64(_np.uint64(_np.uint32(n)) * _np.uint64(p_milli)) / _np.float64(100000.0)))
+    return min(r, n - 1)
+
+
+def slab_minmax(parts, gather, stride=1, mn=-1.7976931348623157e308, mx=1.7976931348623157e308):
+    """(min, max, count) over all slabs (invert's default centre, percentile 0/100)"""
+    allv = gather([g.minmax(stride, mn, mx) for g in parts])
+    have = [v for v in allv if v[2] > 0]
+    if not have:
+        return 0.0, 0.0, 0
+    return min(v[0] for v in have), max(v[1] for v in have), sum(v[2] for v in allv)
+
+
+def slab_invert(parts, gather, mid=None):
+    if mid is None:                                   # add.c:907-926: (globalMin + globalMax) / 2
+        lo, hi, _ = slab_minmax(parts, gather)
+        mid = (lo + hi) / 2.0
+    for g in parts:
+        g.pointwise([g.op_invert(mid)])
+    return mid
+
+
+def slab_cumulativesum(parts, gather):
+    """op_cumulative_sum_apply (sum.c:776-792) on a slab-sharded genome: local scan, then every piece
+    adds the totals of the pieces of its chromosome that lie to its left (exact for integer and dyadic
+    signals, 1e-12 relative otherwise -- the same statement as for one GPU)."""
+    local = []
+    for g in parts:
+        g.cumulativesum()
+        lasts = g.piece_last_values()
+        local.append([(g.seg_chrom[k], g.segs[k][4], float(lasts[k])) for k in range(g.nseg)])
+    pieces = sorted(p for rank in gather(local) for p in rank)        # (chromosome, pos0, total)
+    for g in parts:
+        for k in range(g.nseg):
+            ci, pos0 = g.seg_chrom[k], g.segs[k][4]
+            off = 0.0
+            for c, p0, tot in pieces:
+                if c == ci and p0 < pos0:
+                    off = off + tot
+            if pos0 > 0:
+                g.piece_add_constant(k, off)
+
+
+def merge_runs(chunks, collapse=True):
+    """chunks: [(pos0, (start, end, value))] pieces of ONE chromosome -> merged (start, end, value).
+    Pure host logic (numpy)."""
+    chunks = sorted(chunks, key=lambda c: c[0])
+    s = _np.concatenate([c[1][0] for c in chunks]) if chunks else _np.zeros(0, _np.uint32)
+    e = _np.concatenate([c[1][1] for c in chunks]) if chunks else _np.zeros(0, _np.uint32)
+    v = _np.concatenate([c[1][2] for c in chunks]) if chunks else _np.zeros(0, _np.float64)
+    if not collapse or s.size < 2:
+        return s, e, v
+    # the first run of a piece continues the run before it when it starts exactly at the slab cut,
+    # right where that run ended, with an equal value (at most world-1 such places)
+    first = _np.cumsum([0] + [c[1][0].size for c in chunks])
+    keep = _np.ones(s.size, bool)
+    e = e.copy()
+    for c in range(1, len(chunks)):
+        k = int(first[c])
+        if chunks[c][1][0].size == 0 or k == 0:
+            continue
+        if int(s[k]) == int(chunks[c][0]) and e[k - 1] == s[k] and v[k - 1] == v[k]:
+            h = k - 1
+            while not keep[h]:
+                h -= 1
+            e[h] = e[k]
+            keep[k] = False
+    return s[keep], e[keep], v[keep]
+
+
+def slab_runs(parts, gather, collapse=True, show_uncovered=0):
+    """report_intervals run detection over all slabs: {chromosome: (start, end, value)}; a run cut by a
+    slab boundary is merged back when both halves hold the same value (`==`, genodsp.c:1640)."""
+    local = []
+    for g in parts:
+        r = g.runs(collapse=collapse, show_uncovered=show_uncovered)
+        local.append({name: (min(g.segs[k][4] for k in g.seg_index(name)), r[name]) for name in r})
+    per_chrom = {}
+    for d in gather(local):
+        for name, chunk in d.items():
+            per_chrom.setdefault(name, []).append(chunk)
+    return {name: merge_runs(chunks, collapse) for name, chunks in per_chrom.items()}
+
+
+def slab_percentiles(parts, gather, p_milli, stride=1, mn=-1.7976931348623157e308, mx=1.7976931348623157e308,
+                     sample_per_rank=1 << 16, cand_cap=None, max_iter=60):
+    """op_percentile_apply's order statistics (percentile.c:392-751) over all slabs, exact, without
+    moving the signal: every rank samples its slab, the combined sample brackets each wanted rank
+    between two keys, one counting pass per rank (gdsp_pct_count) gives the exact population of every
+    key region (summed over ranks) and compacts the cells between the brackets, whose combined sorted
+    list holds the wanted element.  Regions are narrowed and the pass repeated when a bracket
+    misses.  -> (values, number of samples); identical on every rank."""
+    jobs = [{"p": int(p), "done": False, "value": 0.0, "lo": 0, "hi": _KEY_MAX, "below": 0, "inside": None}
+            for p in p_milli]
+    total = None
+    for it in range(max_iter):
+        open_jobs = [j for j in jobs if not j["done"]][:128]
+        if not open_jobs and total is not None:
+            break
+        b_lo = min([j["lo"] for j in open_jobs], default=0)
+        b_hi = max([j["hi"] for j in open_jobs], default=_KEY_MAX)
+        local = [g.pct_sample(sample_per_rank, stride, mn, mx, b_lo, b_hi, seed=0x243F6A88 + 7919 * it)[0] for g in parts]
+        ks = _np.sort(_np.concatenate([f64_keys(a) for a in gather(local)] + [_np.zeros(0, _np.uint64)]))
+        bounds, win = [], {}
+        for j in open_jobs:
+            lo, hi = j["lo"], j["hi"]
+            a = int(_np.searchsorted(ks, _np.uint64(lo), "left")); b = int(_np.searchsorted(ks, _np.uint64(hi), "right"))
+            ns = b - a
+            f = -1.0
+            if j["inside"] is None:
+                f = 1.0 if j["p"] >= 100000 else j["p"] / 100000.0
+            elif j["inside"] > 0:
+                f = ((_pct_rank(total, j["p"]) - j["below"]) + 0.5) / float(j["inside"])
+            if ns >= 64 and f >= 0:
+                f = min(f, 1.0)
+                sd = (f * (1 - f) / ns) ** 0.5
+                dl = 6 * sd + 2.0 / ns
+                il = int(_np.floor((f - dl) * ns)) - 1; ih = int(_np.ceil((f + dl) * ns)) + 1
+                if 0 <= il < ns:
+                    lo = max(lo, int(ks[a + il]))
+                if 0 <= ih < ns:
+                    hi = min(hi, int(ks[a + ih]))
+            win[id(j)] = (lo, hi)
+            bounds += [lo, hi]
+        bounds = sorted(set(bounds))
+        nb = len(bounds)
+        compact = [0] * (nb + 1)
+        for j in open_jobs:
+            lo, hi = win[id(j)]
+            for r in range(1, nb):
+                if bounds[r - 1] >= lo and bounds[r] <= hi:
+                    compact[r] = 1
+        local = [g.pct_count(bounds, compact, stride, mn, mx, cand_cap) for g in parts]
+        allr = gather(local)
+        counts = _np.sum([_np.asarray(c[0], dtype=_np.uint64) for c in allr], axis=0, dtype=_np.uint64)
+        total = int(counts.sum())
+        if total == 0 or not jobs:
+            break
+        cand_ok = all(c[1] is not None for c in allr)
+        sorted_cand = None
+        if cand_ok:
+            allc = _np.concatenate([c[1] for c in allr] + [_np.zeros(0)])
+            sorted_cand = allc[_np.argsort(f64_keys(allc), kind="stable")]
+        cand_before, acc = [0] * (nb + 2), 0
+        for r in range(nb + 1):
+            cand_before[r] = acc
+            if compact[r]:
+                acc += int(counts[2 * r])
+        for j in open_jobs:
+            rank = _pct_rank(total, j["p"])
+            cum, reg = 0, 0
+            for reg in range(2 * nb + 1):
+                if rank < cum + int(counts[reg]):
+                    break
+                cum += int(counts[reg])
+            if reg & 1:
+                j["value"], j["done"] = key_f64(bounds[reg >> 1]), True
+                continue
+            r = reg >> 1
+            if compact[r] and cand_ok:
+                j["value"], j["done"] = float(sorted_cand[cand_before[r] + (rank - cum)]), True
+                continue
+            j["lo"] = bounds[r - 1] + 1 if r > 0 else 0
+            j["hi"] = bounds[r] - 1 if r < nb else _KEY_MAX
+            j["below"], j["inside"] = cum, int(counts[reg])
+    if total and any(not j["done"] for j in jobs):
+        raise RuntimeError("slab_percentiles: selection did not converge")
+    return [j["value"] for j in jobs], (total or 0)

@@ -146,3 +146,112 @@ def test_halo_exchange_world2_gloo():
         port = 29500 + world + (os.getpid() % 1000)
         mp.spawn(_gloo_worker, args=(world, port, lengths, 37, out), nprocs=world, join=True)
         assert all(out[r] for r in range(world)), dict(out)
+
+
+# ----------------------------------------------------------------------------- slab-level operators
+def _slab_signal(chroms, seed):
+    rng = np.random.default_rng(seed)
+    sig = {}
+    for name, n in chroms:
+        v = np.repeat(rng.integers(0, 6, n // 7 + 1), 7)[:n].astype(np.float64)      # runs of 7 equal cells
+        sig[name] = v
+    return sig
+
+
+def _slab_expected(chroms, sig, plist):
+    order = sorted(range(len(chroms)), key=lambda i: -chroms[i][1])
+    allv = np.sort(np.concatenate([sig[chroms[i][0]] for i in order]))
+    n = allv.size
+    from genodsp_b200 import slab
+    want_p = [float(allv[slab._pct_rank(n, p)]) for p in plist]
+    want_c = {name: np.cumsum(sig[name]) for name, _ in chroms}
+    want_r = {}
+    for name, _ in chroms:
+        v = sig[name]
+        head = np.concatenate([[True], v[1:] != v[:-1]])
+        st = np.nonzero(head)[0]; en = np.concatenate([st[1:], [v.size]]); val = v[st]
+        keep = val != 0
+        want_r[name] = (st[keep], en[keep], val[keep])
+    return want_p, want_c, want_r
+
+
+def _slab_ops_check(parts, gather, chroms, sig, plist):
+    from genodsp_b200 import slab
+    want_p, want_c, want_r = _slab_expected(chroms, sig, plist)
+    got_p, n = slab.slab_percentiles(parts, gather, plist, sample_per_rank=512)
+    assert n == sum(l for _, l in chroms) and got_p == want_p, (got_p, want_p)
+    lo, hi, cnt = slab.slab_minmax(parts, gather)
+    assert (lo, hi, cnt) == (min(v.min() for v in sig.values()), max(v.max() for v in sig.values()), n)
+    runs = slab.slab_runs(parts, gather)
+    for name, _ in chroms:
+        if want_r[name][0].size == 0:
+            continue
+        for a, b in zip(runs[name], want_r[name]):
+            assert np.array_equal(np.asarray(a, np.float64), np.asarray(b, np.float64)), name
+    slab.slab_cumulativesum(parts, gather)
+    for g in parts:
+        for k in range(g.nseg):
+            name = g.chroms[g.seg_chrom[k]][0]
+            pos0 = g.segs[k][4]
+            assert np.array_equal(g.piece[k], want_c[name][pos0:pos0 + g.piece[k].size]), name
+    return True
+
+
+def _host_parts(chroms, world, ranks, sig):
+    from genodsp_b200 import slab
+    from host_genome import HostGenome
+    order = sorted(range(len(chroms)), key=lambda i: -chroms[i][1])
+    lengths = [chroms[i][1] for i in order]
+    parts = []
+    for r in ranks:
+        segs_s, _ = slab.partition(lengths, world, r, 0)
+        parts.append(HostGenome(chroms, [(order[si], lo, hi, dlo, dhi, pos0) for si, lo, hi, dlo, dhi, pos0 in segs_s], sig))
+    return parts
+
+
+SLAB_CHROMS = [("chrA", 9001), ("chrB", 20000), ("chrC", 313), ("chrD", 4500)]
+SLAB_PCTS = [0, 1000, 50000, 99000, 99900, 100000]
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 5])
+def test_slab_operators_virtual_ranks(world):
+    """cross-rank logic of slab_percentiles / slab_cumulativesum / slab_runs / slab_minmax with every
+    rank's piece held by a numpy stand-in (tests/host_genome.py)"""
+    from genodsp_b200 import slab
+    sig = _slab_signal(SLAB_CHROMS, 5)
+    parts = _host_parts(SLAB_CHROMS, world, range(world), sig)
+    assert _slab_ops_check(parts, slab.virtual_gather, SLAB_CHROMS, sig, SLAB_PCTS)
+
+
+def _slab_gloo_worker(rank, world, port, out):
+    import sys
+    import torch.distributed as dist
+    from genodsp_b200 import slab
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    sig = _slab_signal(SLAB_CHROMS, 5)
+    parts = _host_parts(SLAB_CHROMS, world, [rank], sig)
+    try:
+        out[rank] = _slab_ops_check(parts, slab.dist_gather(dist), SLAB_CHROMS, sig, SLAB_PCTS)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_slab_operators_world2_gloo():
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 29700 + (os.getpid() % 1000)
+    mp.spawn(_slab_gloo_worker, args=(2, port, out), nprocs=2, join=True)
+    assert all(out[r] for r in range(2)), dict(out)
+
+
+def test_merge_runs_chain_across_several_cuts():
+    from genodsp_b200 import slab
+    u = lambda *a: np.array(a, np.uint32)
+    chunks = [(0, (u(0, 10), u(5, 20), np.array([1., 2.]))), (20, (u(20), u(40), np.array([2.]))),
+              (40, (u(40, 50), u(45, 51), np.array([2., 3.])))]
+    s, e, v = slab.merge_runs(chunks)
+    assert s.tolist() == [0, 10, 50] and e.tolist() == [5, 45, 51] and v.tolist() == [1., 2., 3.]
+    s, e, v = slab.merge_runs(chunks, collapse=False)
+    assert s.size == 5

@@ -123,3 +123,61 @@ def test_slab_pipeline_matches_whole_chromosomes(world):
     finally:
         for g in ranks:
             g.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("kind", ["depth", "real"])
+def test_slab_operators_on_virtual_ranks(world, kind):
+    """percentile selection, cumulative sum, invert (global min/max) and run-length output over a
+    slab-sharded genome: the per-rank CUDA calls (gdsp_pct_sample / gdsp_pct_count / gdsp_minmax /
+    gdsp_cumulative_sum / gdsp_runs) combined by genodsp_b200.slab, against the whole-genome answers"""
+    from genodsp_b200 import slab
+    rng = np.random.default_rng(world + (7 if kind == "real" else 0))
+    ranks, order = make_ranks(world, halo=0)
+    try:
+        sig = {}
+        for name, n in CHROMS:
+            if kind == "depth":
+                sig[name] = np.repeat(rng.poisson(3, n // 5 + 1), 5)[:n].astype(np.float64)
+            else:
+                sig[name] = rng.normal(0, 3, n)
+        scatter_signal(ranks, sig)
+        allv = np.sort(np.concatenate([sig[CHROMS[i][0]] for i in order]))
+        plist = [0, 500, 25000, 50000, 99000, 99990, 100000]
+        got, n = slab.slab_percentiles(ranks, slab.virtual_gather, plist, sample_per_rank=4096)
+        assert n == allv.size
+        want = [float(allv[slab._pct_rank(allv.size, p)]) for p in plist]
+        assert got == want, (got, want)
+        # strided samples with limits (percentile --window / --min / --max)
+        sel = np.concatenate([sig[CHROMS[i][0]][::3] for i in order]); sel = np.sort(sel[(sel >= 1.0) & (sel <= 6.0)])
+        got, n = slab.slab_percentiles(ranks, slab.virtual_gather, [50000, 99000], stride=3, mn=1.0, mx=6.0, sample_per_rank=4096)
+        assert n == sel.size and got == [float(sel[slab._pct_rank(sel.size, p)]) for p in (50000, 99000)]
+        # run-length output: runs cut by a slab boundary are merged back
+        runs = slab.slab_runs(ranks, slab.virtual_gather)
+        for name, _ in CHROMS:
+            v = sig[name]
+            head = np.concatenate([[True], v[1:] != v[:-1]])
+            st = np.nonzero(head)[0]; en = np.concatenate([st[1:], [v.size]]); val = v[st]
+            keep = val != 0
+            assert np.array_equal(runs[name][0], st[keep]) and np.array_equal(runs[name][1], en[keep]), name
+            assert np.array_equal(bits(runs[name][2]), bits(val[keep])), name
+        # invert about the global (min+max)/2
+        mid = slab.slab_invert(ranks, slab.virtual_gather)
+        assert mid == (allv[0] + allv[-1]) / 2.0
+        got = gather_signal(ranks)
+        for name, _ in CHROMS:
+            assert np.array_equal(bits(got[name]), bits(2 * mid - sig[name])), name
+        # cumulative sum with carries across the cuts
+        scatter_signal(ranks, sig)
+        slab.slab_cumulativesum(ranks, slab.virtual_gather)
+        got = gather_signal(ranks)
+        for name, _ in CHROMS:
+            want = np.cumsum(sig[name])
+            if kind == "depth":
+                assert np.array_equal(bits(got[name]), bits(want)), name
+            else:
+                scale = np.cumsum(np.abs(sig[name]))
+                assert np.max(np.abs(got[name] - want) / scale) <= 1e-12, name
+    finally:
+        for g in ranks:
+            g.close()
