@@ -80,6 +80,7 @@ SIGNATURES = {
     "gdsp_minmax": (_i, [_vp, _vp, _vp, _u32, _d, _d, _dp, _dp, _u64p]),
     "gdsp_percentiles": (_i, [_vp, _vp, _vp, _vp, _u64, _u32, _d, _d, _u32p, _i, _dp, _u64p]),
     "gdsp_sort_genome": (_i, [_vp, _vp, _vp, _vp, _u64, C.POINTER(_i)]),
+    "gdsp_text_roundtrip": (_i, [_vp, _vp, _vp, _i]),
     "gdsp_pct_sample": (_i, [_vp, _vp, _vp, _u32, _d, _d, _u64, _u64, _u32, _u64, _vp, _u32p, _u64p]),
     "gdsp_sort_array": (_i, [_vp, _vp, _vp, _u64, C.POINTER(_i)]),
     "gdsp_pct_count": (_i, [_vp, _vp, _vp, _u32, _d, _d, _u64p, _i, C.POINTER(C.c_uint8), _u64p, _vp, _u64, _u64p]),

@@ -376,3 +376,90 @@ extern "C" int gdsp_minmax (gdsp_ctx* c, const gdsp_layout* L_, const double* si
 	if (h_max) *h_max = (res[0] == ~0ull && res[1] == 0ull) ? -DBL_MAX : unkey (res[1]);
 	return GDSP_OK;
 	}
+
+// ---------------------------------------------------------------------------
+// percentile --preserve: the reference saves the signal as text with 10 decimals
+// (write_all_chromosomes, genodsp.c:1754-1775: report_intervals, precision 10, zero
+// runs hidden) and reads it back after the percentile (read_all_chromosomes,
+// genodsp.c:1717-1742: read_intervals with clear), so every value comes back as
+//     strtod (printf ("%.10f", v))            -- and every zero as +0.0.
+// k_text_roundtrip computes exactly that without any text: with |v| = m * 2^-k,
+// q = round-half-even (m * 10^10 / 2^k) is what glibc prints (exact arithmetic on the
+// binary value), and the nearest double to q / 10^10 (ties to even) is what strtod
+// returns.  All of it in 128-bit integers.  inf comes back as DBL_MAX ("inf" goes
+// through string_to_double, utilities.c:350-352), NaN as the default quiet NaN.
+// ---------------------------------------------------------------------------
+
+__device__ __forceinline__ int bitlen128 (unsigned __int128 x)
+	{
+	const unsigned long long hi = (unsigned long long) (x >> 64), lo = (unsigned long long) x;
+	return hi ? 128 - __clzll ((long long) hi) : 64 - __clzll ((long long) lo);
+	}
+
+__device__ double text_roundtrip10 (double v)
+	{
+	if (v == 0.0) return 0.0;
+	const unsigned long long SIGN = 0x8000000000000000ull;
+	const unsigned long long b = (unsigned long long) __double_as_longlong (v);
+	const unsigned long long sign = b & SIGN, ab = b & ~SIGN;
+	const int ex = (int) (ab >> 52);
+	const unsigned long long frac = ab & 0x000fffffffffffffull;
+	if (ex == 0x7ff)
+		return __longlong_as_double ((long long) (sign | (frac ? 0x7ff8000000000000ull : 0x7fefffffffffffffull)));
+	unsigned long long m;  int e;
+	if (ex == 0) { m = frac;  e = -1074; } else { m = frac | 0x0010000000000000ull;  e = ex - 1075; }
+	if (e >= 0) return v;                                       // an integer: printed exactly
+	const int k = -e;                                           // |v| = m / 2^k
+	if (k <= 52 && (m & ((1ull << k) - 1ull)) == 0ull) return v;   // still an integer
+	const double zero = __longlong_as_double ((long long) sign);   // "-0.0000000000" reads back as -0.0
+	if (k >= 120) return zero;
+	const unsigned long long D = 10000000000ull;
+	const unsigned __int128 P = (unsigned __int128) m * D;      // < 2^87
+	unsigned __int128 q = P >> k;
+	const unsigned __int128 rem = P & ((((unsigned __int128) 1) << k) - 1), half = ((unsigned __int128) 1) << (k - 1);
+	if (rem > half || (rem == half && (q & 1))) q += 1;
+	if (q == 0) return zero;
+	// nearest double to q / D: scale q to 89 bits so the quotient has 55 or 56 bits
+	const int s = 89 - bitlen128 (q);
+	const unsigned __int128 N = q << s;
+	// long division by D (34 bits) in 16-bit limbs: the running remainder stays below 2^50
+	unsigned long long r = 0;
+	unsigned __int128 Q = 0;
+	#pragma unroll
+	for (int limb = 5; limb >= 0; limb--)
+		{
+		const unsigned long long t = (r << 16) | (unsigned long long) ((N >> (16 * limb)) & 0xffffu);
+		const unsigned long long qd = t / D;
+		r = t - qd * D;
+		Q = (Q << 16) | qd;
+		}
+	const int drop = bitlen128 (Q) - 53;                        // 2 or 3
+	unsigned long long Qm = (unsigned long long) (Q >> drop);
+	const unsigned long long low = (unsigned long long) Q & ((1ull << drop) - 1ull), hq = 1ull << (drop - 1);
+	if (low > hq || (low == hq && (r != 0 || (Qm & 1ull)))) Qm += 1;
+	const double res = ldexp ((double) Qm, drop - s);           // Qm <= 2^53: exact; the scaling is exact too
+	return sign ? -res : res;
+	}
+
+__global__ void __launch_bounds__(256)
+k_text_roundtrip (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg, double* __restrict__ sig)
+	{
+	int seg;  uint64_t tis;
+	tile_to_seg (base, nseg, blockIdx.x, seg, tis);
+	const SegDev sd = segs[seg];
+	const uint64_t t0 = sd.lo + tis * 2048;
+	uint64_t t1 = t0 + 2048;  if (t1 > sd.hi) t1 = sd.hi;
+	for (uint64_t i = t0 + threadIdx.x; i < t1; i += 256) sig[i] = text_roundtrip10 (sig[i]);
+	}
+
+extern "C" int gdsp_text_roundtrip (gdsp_ctx* c, const gdsp_layout* L_, double* sig, int decimals)
+	{
+	gdsp_layout* L = (gdsp_layout*) L_;
+	GDSP_REQUIRE (c && L && sig, "gdsp_text_roundtrip: NULL argument");
+	GDSP_REQUIRE (decimals == 10, "gdsp_text_roundtrip: only the 10 decimals of write_all_chromosomes are implemented");
+	TileMap tm;
+	GDSP_TRY (gdsp_layout_tilemap (L, 2048, &tm));
+	k_text_roundtrip<<<(unsigned) tm.ntiles, 256, 0, c->stream>>> (L->d, tm.d_base, L->nseg, sig);
+	GDSP_KERNEL_CHECK ();
+	return GDSP_OK;
+	}

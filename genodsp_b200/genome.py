@@ -452,6 +452,10 @@ class Genome:
             self.sort_genome()
         return out
 
+    def text_roundtrip(self):
+        """percentile --preserve's write_all/read_all round trip (10 decimals), genodsp.c:1717-1775"""
+        check(self.lib.gdsp_text_roundtrip(self.ctx, self.layout, self._p(self.sig), 10))
+
     def sort_genome(self):
         """the reference's post-percentile state for the all-qualifying case: genome globally sorted
         in chromsSorted order (percentile.c:611-651)"""

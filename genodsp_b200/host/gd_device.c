@@ -243,4 +243,9 @@ void ivlist_read_file (ivlist* l, const char* opName, const char* filename,
 		ivlist_push (l, (u32) segIx, a, b, val);
 		}
 	fclose (f);
+	/* the sorted-file operators then treat every chromosome the file never mentioned
+	 * (multiply.c:343-355, :737-749, logical.c:884-896, mask.c:622-634) */
+	if (requireSorted && trackOperations)
+		for (int i = 0; i < gd.nchrom; i++)
+			if (!chromsSorted[i]->flag) fprintf (stderr, "%s(%s,absent)\n", opName, chromsSorted[i]->chrom);
 	}

@@ -192,6 +192,15 @@ void op_percentile_apply (dspop* _op, arg_dont_complain(char* vName), arg_dont_c
 		return;
 		}
 
+	/* --preserve (percentile.c:534-535): the reference writes the vectors to the scratch file here ... */
+	if (op->preserveFilename != NULL)
+		{
+		FILE* f = fopen (op->preserveFilename, "wt");
+		if (f == NULL) { fprintf (stderr, "can't open \"%s\" for writing\n", op->preserveFilename);  exit (EXIT_FAILURE); }
+		fclose (f);
+		if (trackOperations) fprintf (stderr, "write_all(%s)\n", op->preserveFilename);
+		}
+
 	FILE* mapF = (op->mapFilename != NULL) ? fopen (op->mapFilename, "wt") : NULL;
 
 	u32 np = 0;
@@ -229,6 +238,10 @@ void op_percentile_apply (dspop* _op, arg_dont_complain(char* vName), arg_dont_c
 	/* the reference leaves the genome permuted; reproduce that state only if someone will look */
 	if (op->preserveFilename != NULL)
 		{
+		/* ... and reads them back here (percentile.c:717-725): every value returns as the double nearest
+		 * to its 10-decimal text, every zero as +0.0.  gdsp_text_roundtrip does that on the device. */
+		if (trackOperations) fprintf (stderr, "read_all(%s)\n", op->preserveFilename);
+		gd_check (gdsp_text_roundtrip (gd.ctx, gd.genome, gd.sig, 10), _op->name);
 		FILE* f = fopen (op->preserveFilename, "wb");      /* the reference leaves an empty scratch file */
 		if (f != NULL) fclose (f);
 		return;

@@ -237,6 +237,12 @@ int  gdsp_minmax (gdsp_ctx* ctx, const gdsp_layout* lay, const double* sig,
                   uint32_t stride, double min_allowed, double max_allowed,
                   double* h_min, double* h_max, uint64_t* h_count);
 
+/* percentile --preserve: what write_all_chromosomes + read_all_chromosomes
+ * (genodsp.c:1717-1775) leave in the vectors: every value v != 0 becomes
+ * strtod(printf("%.10f", v)) (inf -> DBL_MAX), every zero +0.0.  Exact integer
+ * arithmetic on the device, no text.  decimals must be 10.  In place. */
+int  gdsp_text_roundtrip (gdsp_ctx* ctx, const gdsp_layout* lay, double* sig, int decimals);
+
 /* ---- percentile -------------------------------------------------------------
  * op_percentile_apply, percentile.c:392-751.  Order statistics of the samples
  * v[ix], ix = 0,stride,2*stride,.. of every chromosome with

@@ -8,6 +8,7 @@
  *
  * Every function cites the reference file:line it restates.
  */
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
@@ -112,6 +113,24 @@ void gdo_smooth (double* v, u32 n, u32 W)
 	}
 
 /* op_cumulative_sum_apply, sum.c:776-792 */
+/* percentile --preserve (percentile.c:534-535, :717-725): the vectors are written as text by
+ * write_all_chromosomes (genodsp.c:1754-1775: report_intervals with precision 10, runs of zero not
+ * shown) and read back by read_all_chromosomes (genodsp.c:1717-1742: read_intervals, value column 4,
+ * clear to 0.0).  Per cell: a zero comes back as +0.0; anything else as what read_interval makes of
+ * its "%.10f" text, i.e. string_to_double (utilities.c:334-370): "inf" -> DBL_MAX, else sscanf %lf. */
+void gdo_text_roundtrip10 (double* v, u32 n)
+	{
+	char buf[512];
+	for (u32 i = 0; i < n; i++)
+		{
+		if (v[i] == 0.0) { v[i] = 0.0;  continue; }
+		snprintf (buf, sizeof (buf), "%.10f", v[i]);
+		if      (strcmp (buf, "inf")  == 0) v[i] =  DBL_MAX;
+		else if (strcmp (buf, "-inf") == 0) v[i] = -DBL_MAX;
+		else { double x = 0;  char extra;  if (sscanf (buf, "%lf%c", &x, &extra) == 1) v[i] = x; }
+		}
+	}
+
 void gdo_cumulative (double* v, u32 n)
 	{
 	double run = 0.0;

@@ -26,6 +26,8 @@ void gdo_sliding_sum (double* v, uint32_t n, uint32_t W, double denom);
 void gdo_hann_taps   (double* w, uint32_t W);
 void gdo_smooth      (double* v, uint32_t n, uint32_t W);
 void gdo_cumulative  (double* v, uint32_t n);
+/* percentile --preserve: write_all_chromosomes + read_all_chromosomes (genodsp.c:1717-1775) */
+void gdo_text_roundtrip10 (double* v, uint32_t n);
 /* minmax.c */
 void gdo_local_extrema (double* v, uint32_t n, uint32_t N, int wantMax, double fill);
 void gdo_best_extrema  (double* v, uint32_t n, uint32_t W, int wantMax);

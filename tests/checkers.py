@@ -47,6 +47,7 @@ class Oracle:
             "gdo_hann_taps": [c_dp, u32],
             "gdo_smooth": [c_dp, u32, u32],
             "gdo_cumulative": [c_dp, u32],
+            "gdo_text_roundtrip10": [c_dp, u32],
             "gdo_local_extrema": [c_dp, u32, u32, i, d],
             "gdo_best_extrema": [c_dp, u32, u32, i],
             "gdo_close": [c_dp, u32, d, d, d, d],
@@ -109,6 +110,9 @@ class Oracle:
 
     def cumulative(self, v):
         self.lib.gdo_cumulative(*self._v(v)); return v
+
+    def text_roundtrip10(self, v):
+        self.lib.gdo_text_roundtrip10(*self._v(v)); return v
 
     def local_extrema(self, v, N, want_max=True, fill=0.0):
         self.lib.gdo_local_extrema(*self._v(v), N, int(want_max), fill); return v

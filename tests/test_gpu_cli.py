@@ -169,3 +169,16 @@ def test_errors_match(data):
         f.write("chrD\t1000\t2000\n")
     (rc_r, _, err_r), (rc_o, _, err_o) = both(data, C + ["--novalue"], stdin="bad.iv")
     assert rc_r != 0 and rc_o != 0 and err_r == err_o
+
+
+def test_percentile_preserve_roundtrip(data):
+    """--preserve: the reference writes the vectors with 10 decimals and reads them back, so the signal
+    that continues down the pipeline is the 10-decimal rounding of the smoothed track (and the trace
+    shows write_all/read_all); window/min/max percentiles are fine with --preserve"""
+    assert_same(data, C + ["--novalue", "--precision=17", "--progress=operations",
+                           "=", "smooth", "--window=31",
+                           "=", "percentile", "90", "--preserve=scratch.pres", "--precision=12",
+                           "=", "multiply", "trackB.iv",
+                           "=", "percentile", "10..90by20", "--window=7", "--min=0.25", "--preserve=scratch2.pres",
+                           "=", "clip", "--max=percentile90"])
+    assert os.path.getsize(data / "scratch.pres") == 0

@@ -192,6 +192,30 @@ def test_sliding_sum(genome, orc, kind, W):
             exact_fn=lambda v: _exact_sliding_sum(v, W, d))
 
 
+def test_text_roundtrip_is_printf_strtod(genome, orc):
+    """gdsp_text_roundtrip (percentile --preserve) == strtod(printf("%.10f")) per cell, computed with
+    integer arithmetic on the device: random magnitudes, exact ties at the 11th decimal (odd/2048),
+    values that round to +-0, integers, infinities, huge values"""
+    rng = np.random.default_rng(10)
+    inputs = {}
+    for name, n in CHROMS:
+        parts = [rng.normal(0, 3, n), rng.integers(-5, 9, n).astype(np.float64), (2 * rng.integers(0, 4096, n) + 1) / 2048.0,
+                 rng.normal(0, 1e-9, n), rng.normal(0, 1e-11, n), rng.normal(0, 1e7, n), rng.normal(0, 1e-3, n)]
+        v = np.choose(rng.integers(0, len(parts), n), parts)
+        special = np.array([0.0, -0.0, np.inf, -np.inf, 1e300, 5e-11, -5e-11, 2.5e-11, 7.5e-11, 123456.78901234567,
+                            4.9e-324, -2.2250738585072014e-308, 0.1, 1e-10, 1.5e-10, 0.99999999995, 4503599627370495.5])
+        k = min(n, special.size)
+        v[:k] = special[:k]
+        inputs[name] = v
+        genome.set_chrom(name, v)
+    genome.text_roundtrip()
+    for name, n in CHROMS:
+        want = orc.text_roundtrip10(inputs[name].copy())
+        got = genome.get_chrom(name)
+        bad = np.nonzero(bits(got) != bits(want))[0]
+        assert bad.size == 0, (name, inputs[name][bad[:5]], got[bad[:5]], want[bad[:5]])
+
+
 def test_smooth_to_host_matches_smooth(genome, orc):
     """the pipelined smooth + device->host delivery used by bench.py's e2e leg: same bits as smooth()"""
     import torch

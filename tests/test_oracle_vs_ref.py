@@ -432,3 +432,19 @@ def test_runs(orc, tmp_path, collapse, show):
             assert lines == ref.get(name, []), (name, collapse, show)
     finally:
         g.close()
+
+
+def test_preserve_roundtrip_matches_reference(tmp_path):
+    """oracle gdo_text_roundtrip10 == what `percentile --preserve` leaves in the reference's vectors
+    (write_all_chromosomes + read_all_chromosomes, genodsp.c:1717-1775)"""
+    rng = np.random.default_rng(3)
+    n = 20000
+    v = np.concatenate([rng.normal(0, 3, n), rng.integers(-5, 9, n).astype(float), (2 * rng.integers(0, 4096, n) + 1) / 2048.0,
+                        rng.normal(0, 1e-9, n), rng.normal(0, 1e-11, n), rng.normal(0, 1e7, n),
+                        [0.0, -0.0, np.inf, -np.inf, 1e300, 5e-11, -5e-11, 2.5e-11, 7.5e-11, 123456.78901234567]])
+    want = Oracle().text_roundtrip10(v.copy())
+    g = RefGenome([("chrT", v.size)])
+    g.vec["chrT"][:] = v
+    g.apply("percentile", "50", "--quiet", "--preserve=" + str(tmp_path / "scratch"))
+    got = g.vec["chrT"].copy()
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
