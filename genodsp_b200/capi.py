@@ -27,7 +27,7 @@ class PwOp(C.Structure):
 # gdsp_pw_code
 PW_BINARIZE_GT, PW_BINARIZE_GE, PW_ADDCONST, PW_ABS, PW_CLIP_MIN, PW_CLIP_MAX, PW_CLIP_BOTH, PW_ERASE, \
     PW_INVERT, PW_NONZERO_TO_ONE, PW_IVL_ADD, PW_IVL_SUB, PW_IVL_MUL, PW_IVL_DIV, PW_IVL_SET, \
-    PW_IVL_SET_OUTSIDE, PW_IVL_ASSIGN = range(1, 18)
+    PW_IVL_SET_OUTSIDE, PW_IVL_ASSIGN, PW_IVL_MIN, PW_IVL_MAX, PW_IVL_KEEP_AT = range(1, 21)
 PW_ERASE_HAVE_MIN, PW_ERASE_HAVE_MAX, PW_ERASE_KEEP_INSIDE = 1, 2, 4
 ACC_I32, ACC_F64 = 0, 1
 MORPH_CLOSE, MORPH_OPEN, MORPH_DILATE, MORPH_ERODE = 0, 1, 2, 3
@@ -80,6 +80,8 @@ SIGNATURES = {
     "gdsp_minmax": (_i, [_vp, _vp, _vp, _u32, _d, _d, _dp, _dp, _u64p]),
     "gdsp_percentiles": (_i, [_vp, _vp, _vp, _vp, _u64, _u32, _d, _d, _u32p, _i, _dp, _u64p]),
     "gdsp_sort_genome": (_i, [_vp, _vp, _vp, _vp, _u64, C.POINTER(_i)]),
+    "gdsp_ivl_arg_extrema": (_i, [_vp, _vp, _vp, _vp, _i]),
+    "gdsp_map_values": (_i, [_vp, _vp, _vp, _dp, _dp, _i]),
     "gdsp_text_roundtrip": (_i, [_vp, _vp, _vp, _i]),
     "gdsp_pct_sample": (_i, [_vp, _vp, _vp, _u32, _d, _d, _u64, _u64, _u32, _u64, _vp, _u32p, _u64p]),
     "gdsp_sort_array": (_i, [_vp, _vp, _vp, _u64, C.POINTER(_i)]),

@@ -135,6 +135,9 @@ __device__ __forceinline__ void pw_apply_vec (const PwProgram& P, double (&v)[PW
 						case GDSP_PW_IVL_SET: if (inside) v[e] = a;  break;
 						case GDSP_PW_IVL_SET_OUTSIDE: if (!inside) v[e] = a;  break;
 						case GDSP_PW_IVL_ASSIGN: if (inside) v[e] = op.val[k];  break;
+						case GDSP_PW_IVL_MIN: if (inside) { const double w = op.val[k];  if (w < v[e]) v[e] = w; }  break;
+						case GDSP_PW_IVL_MAX: if (inside) { const double w = op.val[k];  if (w > v[e]) v[e] = w; }  break;
+						case GDSP_PW_IVL_KEEP_AT: if (!(inside && (double) g[e] == op.val[k])) v[e] = a;  break;
 						}
 					}
 				}
@@ -327,7 +330,7 @@ extern "C" int gdsp_pointwise (gdsp_ctx* c, const gdsp_layout* L_, const double*
 	P.nops = nops;
 	for (int i = 0; i < nops; i++)
 		{
-		GDSP_REQUIRE (ops[i].code >= GDSP_PW_BINARIZE_GT && ops[i].code <= GDSP_PW_IVL_ASSIGN,
+		GDSP_REQUIRE (ops[i].code >= GDSP_PW_BINARIZE_GT && ops[i].code <= GDSP_PW_IVL_KEEP_AT,
 		              "gdsp_pointwise: operator %d has unknown code %d", i, ops[i].code);
 		P.ops[i].code = ops[i].code;  P.ops[i].flags = ops[i].flags;
 		P.ops[i].a = ops[i].a;  P.ops[i].b = ops[i].b;  P.ops[i].c = ops[i].c;
@@ -460,6 +463,140 @@ extern "C" int gdsp_text_roundtrip (gdsp_ctx* c, const gdsp_layout* L_, double* 
 	TileMap tm;
 	GDSP_TRY (gdsp_layout_tilemap (L, 2048, &tm));
 	k_text_roundtrip<<<(unsigned) tm.ntiles, 256, 0, c->stream>>> (L->d, tm.d_base, L->nseg, sig);
+	GDSP_KERNEL_CHECK ();
+	return GDSP_OK;
+	}
+
+// ---------------------------------------------------------------------------
+// minover / maxover (minmax.c:322-343, :725-746): for every interval of a sorted, disjoint table the
+// cell holding the extremum; among equal values the one farthest from both interval ends
+// (inset = min (ix-start, end-ix)), the earliest of those.  One warp per interval; the winning
+// buffer cell index is stored (as a double) in the table's value column, which
+// GDSP_PW_IVL_KEEP_AT then compares with every cell's own index.
+// ---------------------------------------------------------------------------
+
+struct ArgBest { double v;  uint64_t inset, idx;  bool has; };
+
+template <bool WANT_MAX>
+__device__ __forceinline__ bool arg_better (const ArgBest& a, const ArgBest& b)      // is a better than b?
+	{
+	if (!a.has) return false;
+	if (!b.has) return true;
+	if (WANT_MAX ? (a.v > b.v) : (a.v < b.v)) return true;
+	if (WANT_MAX ? (a.v < b.v) : (a.v > b.v)) return false;
+	if (a.inset != b.inset) return a.inset > b.inset;
+	return a.idx < b.idx;
+	}
+
+template <bool WANT_MAX>
+__global__ void __launch_bounds__(256)
+k_ivl_arg_extrema (const double* __restrict__ sig, const uint64_t* __restrict__ start, const uint64_t* __restrict__ end,
+                   double* __restrict__ val, uint64_t n)
+	{
+	const int lane = threadIdx.x & 31;
+	const uint64_t warp = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t) gridDim.x * blockDim.x) >> 5;
+	for (uint64_t k = warp; k < n; k += nwarps)
+		{
+		const uint64_t s = start[k], e = end[k];
+		ArgBest best;  best.has = false;  best.v = 0;  best.inset = 0;  best.idx = 0;
+		for (uint64_t i = s + lane; i < e; i += 32)
+			{
+			ArgBest c;  c.has = true;  c.v = sig[i];  c.idx = i;
+			c.inset = (i - s < e - i) ? (i - s) : (e - i);
+			if (arg_better<WANT_MAX> (c, best)) best = c;
+			}
+		#pragma unroll
+		for (int d = 16; d > 0; d >>= 1)
+			{
+			ArgBest o;
+			o.v = shfl_xor_f64 (best.v, d);
+			o.inset = __shfl_xor_sync (0xffffffffu, best.inset, d);
+			o.idx   = __shfl_xor_sync (0xffffffffu, best.idx, d);
+			o.has   = __shfl_xor_sync (0xffffffffu, (int) best.has, d) != 0;
+			if (arg_better<WANT_MAX> (o, best)) best = o;
+			}
+		if (lane == 0) val[k] = best.has ? (double) best.idx : -1.0;
+		}
+	}
+
+extern "C" int gdsp_ivl_arg_extrema (gdsp_ctx* c, const gdsp_layout* L, const double* sig, gdsp_ivl_table* t, int wantMax)
+	{
+	GDSP_REQUIRE (c && L && sig && t, "gdsp_ivl_arg_extrema: NULL argument");
+	if (t->n == 0) return GDSP_OK;
+	uint64_t blocks = (t->n + 7) / 8;
+	if (blocks > (uint64_t) c->sm_count * 32) blocks = (uint64_t) c->sm_count * 32;
+	if (wantMax) k_ivl_arg_extrema<true><<<(unsigned) blocks, 256, 0, c->stream>>> (sig, t->d_start, t->d_end, t->d_val, t->n);
+	else         k_ivl_arg_extrema<false><<<(unsigned) blocks, 256, 0, c->stream>>> (sig, t->d_start, t->d_end, t->d_val, t->n);
+	GDSP_KERNEL_CHECK ();
+	return GDSP_OK;
+	}
+
+// ---------------------------------------------------------------------------
+// map (map.c:263-357): piecewise-linear function through breakpoints (in[k], out[k]), in[] strictly
+// ascending.  v <= in[0] -> out[0]; v >= in[n-1] -> out[n-1]; a breakpoint maps to its output; anything
+// else on piece k to  out[k] + (v - in[k]) * (out[k+1] - out[k]) / (in[k+1] - in[k])  evaluated in
+// the reference's order (product first, then the quotient, then the sum; no FMA).
+// ---------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256)
+k_map_values (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg, double* __restrict__ sig,
+              const double* __restrict__ bin, const double* __restrict__ bout, int n)
+	{
+	extern __shared__ double s_map[];              // [in | out] when they fit
+	const double* xin = bin;  const double* xout = bout;
+	if (n <= 2048)
+		{
+		for (int i = threadIdx.x; i < n; i += 256) { s_map[i] = bin[i];  s_map[n + i] = bout[i]; }
+		__syncthreads ();
+		xin = s_map;  xout = s_map + n;
+		}
+	int seg;  uint64_t tis;
+	tile_to_seg (base, nseg, blockIdx.x, seg, tis);
+	const SegDev sd = segs[seg];
+	const uint64_t t0 = sd.lo + tis * 4096;
+	uint64_t t1 = t0 + 4096;  if (t1 > sd.hi) t1 = sd.hi;
+	const double minIn = xin[0], maxIn = xin[n - 1], outMin = xout[0], outMax = xout[n - 1];
+	for (uint64_t i = t0 + threadIdx.x; i < t1; i += 256)
+		{
+		const double x = sig[i];
+		double y;
+		if (x <= minIn) y = outMin;
+		else if (x >= maxIn) y = outMax;
+		else if (!(x == x)) y = x;                 // NaN: the reference's search is undefined here
+		else
+			{
+			int lo = 0, hi = n - 1;                // in[lo] <= x < in[hi]
+			while (lo + 1 < hi)
+				{
+				const int mid = (lo + hi) >> 1;
+				if (x < xin[mid]) hi = mid; else lo = mid;
+				}
+			const double pLo = xin[lo], pHi = xin[lo + 1], oLo = xout[lo], oHi = xout[lo + 1];
+			if (x == pLo) y = oLo;
+			else if (x == pHi) y = oHi;
+			else y = __dadd_rn (oLo, __ddiv_rn (__dmul_rn (__dsub_rn (x, pLo), __dsub_rn (oHi, oLo)), __dsub_rn (pHi, pLo)));
+			}
+		sig[i] = y;
+		}
+	}
+
+extern "C" int gdsp_map_values (gdsp_ctx* c, const gdsp_layout* L_, double* sig, const double* h_in, const double* h_out, int n)
+	{
+	gdsp_layout* L = (gdsp_layout*) L_;
+	GDSP_REQUIRE (c && L && sig && h_in && h_out, "gdsp_map_values: NULL argument");
+	GDSP_REQUIRE (n >= 1 && n <= (1 << 24), "gdsp_map_values: %d breakpoints (1..16777216 allowed)", n);
+	for (int k = 1; k < n; k++)
+		GDSP_REQUIRE (h_in[k] > h_in[k-1], "gdsp_map_values: input values must be strictly ascending (entry %d)", k);
+	void* ws;
+	GDSP_TRY (gdsp_ws (c, 6, 2 * sizeof (double) * (size_t) n, &ws));
+	double* d_in = (double*) ws;  double* d_out = d_in + n;
+	GDSP_CUDA (cudaMemcpyAsync (d_in, h_in, sizeof (double) * n, cudaMemcpyHostToDevice, c->stream));
+	GDSP_CUDA (cudaMemcpyAsync (d_out, h_out, sizeof (double) * n, cudaMemcpyHostToDevice, c->stream));
+	GDSP_CUDA (cudaStreamSynchronize (c->stream));          // h_in/h_out may be host temporaries
+	TileMap tm;
+	GDSP_TRY (gdsp_layout_tilemap (L, 4096, &tm));
+	const size_t smem = (n <= 2048) ? 2 * sizeof (double) * (size_t) n : 0;
+	k_map_values<<<(unsigned) tm.ntiles, 256, smem, c->stream>>> (L->d, tm.d_base, L->nseg, sig, d_in, d_out, n);
 	GDSP_KERNEL_CHECK ();
 	return GDSP_OK;
 	}

@@ -417,6 +417,23 @@ class Genome:
     def interval_table(self, seg, start, end, val=None):
         return IntervalTable(self, seg, start, end, val)
 
+    def minover(self, table, infinity=DBL_MAX):
+        """op_min_in_interval_apply (minmax.c:197-419): keep the trough of every interval, `infinity` elsewhere"""
+        check(self.lib.gdsp_ivl_arg_extrema(self.ctx, self.layout, self._p(self.sig), table.handle, 0))
+        self.pointwise([(capi.PW_IVL_KEEP_AT, infinity, 0, 0, 0, table)])
+
+    def maxover(self, table, zero=0.0):
+        """op_max_in_interval_apply (minmax.c:600-822): keep the peak of every interval, `zero` elsewhere"""
+        check(self.lib.gdsp_ivl_arg_extrema(self.ctx, self.layout, self._p(self.sig), table.handle, 1))
+        self.pointwise([(capi.PW_IVL_KEEP_AT, zero, 0, 0, 0, table)])
+
+    def map_values(self, vin, vout):
+        """op_map_apply (map.c:194-385) for strictly ascending breakpoints"""
+        vin = np.ascontiguousarray(vin, np.float64); vout = np.ascontiguousarray(vout, np.float64)
+        dp = C.POINTER(C.c_double)
+        check(self.lib.gdsp_map_values(self.ctx, self.layout, self._p(self.sig), vin.ctypes.data_as(dp),
+                                       vout.ctypes.data_as(dp), int(vin.size)))
+
     # ------------------------------------------------------------------ percentile.c
     def percentile(self, lo, hi=None, step=1.0, window=1, mn=-DBL_MAX, mx=DBL_MAX, destructive=True):
         """op_percentile_apply (percentile.c:392-751): sets self.variables['percentile<p>'].

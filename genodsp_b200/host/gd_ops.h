@@ -67,6 +67,7 @@ void gd_resolve_morph        (dspop* op);      /* gd_ops_morph.c     */
 /* helpers shared between files */
 void gd_set_outside   (ivlist* unionList, valtype value);                /* v = value outside the intervals */
 void gd_input_minmax  (ivlist* l, int overlapOp, int clear, valtype missingVal);
+void gd_paint_extreme (ivlist* l, int wantMax, ivlist* out);
 void gd_run_pointwise_now (dspop* op);                                   /* apply path of a pointwise operator */
 void op_short_line (char* name, int nameWidth, FILE* f, char* indent, const char* text);
 dspop* gd_pipeline_head (void);

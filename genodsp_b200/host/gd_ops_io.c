@@ -99,14 +99,14 @@ static int mm_by_value (const void* a, const void* b)
 static int u32_cmp (const void* a, const void* b)
 	{ u32 x = *(const u32*) a, y = *(const u32*) b;  return (x > y) - (x < y); }
 
-void gd_input_minmax (ivlist* l, int overlapOp, arg_dont_complain(int clear), valtype missingVal)
+/* reduce overlapping intervals to disjoint pieces that hold, for every covered position, the smallest
+ * (largest) value among the intervals covering it; pieces come out in layout order */
+void gd_paint_extreme (ivlist* l, int wantMax, ivlist* outp)
 	{
-	gd_check (gdsp_fill (gd.ctx, gd.genome, gd.sig, missingVal), "input");
 	if (l->n == 0) return;
-	ivlist out;  ivlist_init (&out);
 	u64* order = (u64*) malloc (l->n * sizeof (u64));
 	for (u64 k = 0; k < l->n; k++) order[k] = k;
-	mmList = l;  mmWantMax = (overlapOp == ri_overlapMax);
+	mmList = l;  mmWantMax = wantMax;
 	qsort (order, l->n, sizeof (u64), mm_by_value);
 
 	for (int seg = 0; seg < gd.nchrom; seg++)
@@ -148,10 +148,18 @@ void gd_input_minmax (ivlist* l, int overlapOp, arg_dont_complain(int clear), va
 				}
 			}
 		for (u64 p = 0; p < npiece; p++)
-			if (painted[p]) ivlist_push (&out, (u32) seg, bp[p], bp[p+1], pv[p]);
+			if (painted[p]) ivlist_push (outp, (u32) seg, bp[p], bp[p+1], pv[p]);
 		free (bp);  free (next);  free (pv);  free (painted);
 		}
 	free (order);
+	}
+
+void gd_input_minmax (ivlist* l, int overlapOp, arg_dont_complain(int clear), valtype missingVal)
+	{
+	gd_check (gdsp_fill (gd.ctx, gd.genome, gd.sig, missingVal), "input");
+	if (l->n == 0) return;
+	ivlist out;  ivlist_init (&out);
+	gd_paint_extreme (l, overlapOp == ri_overlapMax, &out);
 	gdsp_ivl_table* t;
 	gd_check (gdsp_ivl_table_create (gd.ctx, gd.genome, out.seg, out.start, out.end, out.val, out.n, &t), "input");
 	gdsp_pw_op p;  memset (&p, 0, sizeof (p));
@@ -257,41 +265,124 @@ void op_show_variables_apply (arg_dont_complain(dspop* op), arg_dont_complain(ch
 	report_named_globals (stderr, "  ");
 	}
 
-/* ==== minover, maxover, minwith, maxwith, map: not on this build's hot path ==== */
 
-typedef struct dspop_later { dspop common;  char* filename; } dspop_later;
+/* ======================================================================== map
+ * op_map_* (map.c:44-385): a piecewise-linear function read from a two-column text file (blank and
+ * '#' lines skipped, any order, sorted by input value with qsort as map.c:461).  The reference applies
+ * it chromosome by chromosome and re-reads the file for every chromosome; so does this operator when
+ * it is handed one chromosome, and once when it is handed the whole genome.  Breakpoints that share
+ * an input value make the reference's result depend on its piece cache: refused. */
 
-static dspop* later_parse (char* name, int argc, char** argv)
+typedef struct dspop_map { dspop common;  char* filename;  int destroyFile, debug, applied; } dspop_map;
+
+void op_map_short (char* name, int w, FILE* f, char* indent)
+	{ op_short_line (name, w, f, indent, "map values according to a piecewise-linear function"); }
+
+void op_map_usage (char* name, FILE* f, char* indent)
 	{
-	dspop_later* op = (dspop_later*) op_alloc (name, sizeof (dspop_later));
-	op->common.atRandom = true;
+	if (indent == NULL) indent = "";
+	fprintf (f, "%sMap every value through a piecewise-linear function read from a file: two\n", indent);
+	fprintf (f, "%snumbers per line, an input value and the output it maps to. Values between two\n", indent);
+	fprintf (f, "%slisted inputs are interpolated linearly; values beyond the smallest or largest\n", indent);
+	fprintf (f, "%slisted input take that end's output.\n%s\n", indent, indent);
+	fprintf (f, "%susage: %s <filename> [options]\n", indent, name);
+	fprintf (f, "%s  --destroy                delete the file after reading it\n", indent);
+	}
+
+dspop* op_map_parse (char* name, int argc, char** argv)
+	{
+	dspop_map* op = (dspop_map*) op_alloc (name, sizeof (dspop_map));
+	op->common.atRandom = false;
 	for (; argc > 0; argv++, argc--)
-		if (strcmp_prefix (argv[0], "--") != 0 && op->filename == NULL) op->filename = copy_string (argv[0]);
+		{
+		char* arg = argv[0];
+		if (strcmp (arg, "--destroy") == 0) op->destroyFile = true;
+		else if (strcmp (arg, "--debug") == 0) op->debug = true;
+		else if (strcmp_prefix (arg, "--") == 0) bad_arg (name, arg);
+		else if (op->filename == NULL) op->filename = copy_string (arg);
+		else bad_arg (name, arg);
+		}
 	if (op->filename == NULL) { fprintf (stderr, "[%s] no filename was provided\n", name);  exit (EXIT_FAILURE); }
 	return (dspop*) op;
 	}
-static void later_free (dspop* _op) { dspop_later* op = (dspop_later*) _op;  free (op->filename);  free (op); }
-static void later_apply (dspop* op)
+
+void op_map_free (dspop* _op) { dspop_map* op = (dspop_map*) _op;  free (op->filename);  free (op); }
+
+typedef struct mapel { double vIn, vOut; } mapel;
+static int mapel_ascending (const void* a, const void* b)
+	{ const mapel* x = (const mapel*) a;  const mapel* y = (const mapel*) b;  return (x->vIn > y->vIn) - (x->vIn < y->vIn); }
+
+static u32 mapLineNumber = 0;          /* the reference's counter is a function static: it keeps counting across files */
+
+static int read_value_pair (FILE* f, double* v1, double* v2)
 	{
-	fprintf (stderr, "[%s] this operator has no GPU implementation in this build (and there is no CPU fallback)\n", op->name);
-	exit (EXIT_FAILURE);
-	}
-static void later_usage (char* name, FILE* f, char* indent, const char* what)
-	{
-	if (indent == NULL) indent = "";
-	fprintf (f, "%s%s\n%s(accepted on the command line; not implemented on the GPU in this build)\n%s\n", indent, what, indent, indent);
-	fprintf (f, "%susage: %s <filename> [options]\n", indent, name);
+	char line[1000];
+	static int missingEol = false;
+	while (fgets (line, sizeof (line), f) != NULL)
+		{
+		mapLineNumber++;
+		if (missingEol)
+			{ fprintf (stderr, "problem at line %u, line is longer than internal buffer\n", mapLineNumber - 1);  exit (EXIT_FAILURE); }
+		size_t len = strlen (line);
+		if (len != 0) missingEol = (line[len-1] != '\n');
+		char* scan = skip_whitespace (line);
+		if (*scan == 0 || *scan == '#') continue;
+		if (line[0] == ' ')
+			{ fprintf (stderr, "problem at line %u, line contains no first value\n", mapLineNumber);  exit (EXIT_FAILURE); }
+		char* field = line;
+		char* mark = skip_darkspace (field);
+		scan = skip_whitespace (mark);
+		if (*mark != 0) *mark = 0;
+		*v1 = string_to_valtype (field);
+		if (*scan == 0)
+			{ fprintf (stderr, "problem at line %u, line contains no second value\n", mapLineNumber);  exit (EXIT_FAILURE); }
+		field = scan;
+		mark = skip_darkspace (field);
+		if (*mark != 0) *mark = 0;
+		*v2 = string_to_valtype (field);
+		return true;
+		}
+	return false;
 	}
 
-#define LATER_GROUP(fn, text, what) \
-void   fn##_short (char* name, int w, FILE* f, char* indent) { op_short_line (name, w, f, indent, text); } \
-void   fn##_usage (char* name, FILE* f, char* indent) { later_usage (name, f, indent, what); } \
-dspop* fn##_parse (char* name, int argc, char** argv) { return later_parse (name, argc, argv); } \
-void   fn##_free  (dspop* op) { later_free (op); } \
-void   fn##_apply (dspop* op, arg_dont_complain(char* n), arg_dont_complain(u32 l), arg_dont_complain(valtype* v)) { later_apply (op); }
-
-LATER_GROUP (op_max_in_interval, "find the maximum value in each of a set of intervals read from a file", "Keep, in each interval of a file, only the position holding the maximum.")
-LATER_GROUP (op_min_in_interval, "find the minimum value in each of a set of intervals read from a file", "Keep, in each interval of a file, only the position holding the minimum.")
-LATER_GROUP (op_min_with, "take the minimum of the current set of interval values and values read from a file", "Position-wise minimum of the signal and the intervals of a file.")
-LATER_GROUP (op_max_with, "take the maximum of the current set of interval values and values read from a file", "Position-wise maximum of the signal and the intervals of a file.")
-LATER_GROUP (op_map, "map the current set of interval values to new values", "Map values through a piecewise-linear table read from a file.")
+void op_map_apply (dspop* _op, arg_dont_complain(char* vName), arg_dont_complain(u32 vLen), valtype* v)
+	{
+	dspop_map* op = (dspop_map*) _op;
+	FILE* f = fopen (op->filename, "rt");
+	if (f == NULL) { fprintf (stderr, "[%s] can't open \"%s\" for reading\n", _op->name, op->filename);  exit (EXIT_FAILURE); }
+	u32 n = 0, cap = 64;
+	mapel* m = (mapel*) malloc (cap * sizeof (mapel));
+	double a, b;
+	/* the reference reads the file twice (count, then fill: map.c:429-455); line numbers in messages follow */
+	while (read_value_pair (f, &a, &b)) n++;
+	rewind (f);
+	if (n > cap) { cap = n;  m = (mapel*) realloc (m, cap * sizeof (mapel)); }
+	n = 0;
+	while (read_value_pair (f, &a, &b)) { m[n].vIn = a;  m[n].vOut = b;  n++; }
+	fclose (f);
+	if (op->destroyFile) remove (op->filename);
+	if (n == 0) { fprintf (stderr, "[%s] problem with mapping file \"%s\"\n", _op->name, op->filename);  exit (EXIT_FAILURE); }
+	qsort (m, n, sizeof (mapel), mapel_ascending);
+	double* in = (double*) malloc (n * sizeof (double));  double* out = (double*) malloc (n * sizeof (double));
+	for (u32 k = 0; k < n; k++)
+		{
+		if (k > 0 && m[k].vIn == m[k-1].vIn)
+			{
+			fprintf (stderr, "[%s] \"%s\" lists the input value " valtypeFmt " more than once; the reference's result then\n"
+			                 "depends on the order in which it meets the data, which this build does not reproduce\n",
+			         _op->name, op->filename, m[k].vIn);
+			exit (EXIT_FAILURE);
+			}
+		in[k] = m[k].vIn;  out[k] = m[k].vOut;
+		}
+	const gdsp_layout* lay = gd_layout_for (v, NULL);
+	gd_check (gdsp_map_values (gd.ctx, lay, gd.sig, in, out, (int) n), _op->name);
+	free (m);  free (in);  free (out);
+	if (v == NULL && op->destroyFile && gd.nchrom > 1)
+		{
+		/* handed the whole genome at once; the reference would now fail to re-open the file it just
+		 * deleted for the second chromosome (map.c:211-212) */
+		fprintf (stderr, "[%s] can't open \"%s\" for reading\n", _op->name, op->filename);
+		exit (EXIT_FAILURE);
+		}
+	}

@@ -11,7 +11,8 @@
 #include "gd_ops.h"
 
 enum { PK_BINARIZE, PK_ADDCONST, PK_ABS, PK_INVERT, PK_CLIP, PK_ERASE,
-       PK_ADD, PK_SUBTRACT, PK_MULTIPLY, PK_DIVIDE, PK_MASK, PK_MASKNOT, PK_OR, PK_AND };
+       PK_ADD, PK_SUBTRACT, PK_MULTIPLY, PK_DIVIDE, PK_MASK, PK_MASKNOT, PK_OR, PK_AND,
+       PK_MINOVER, PK_MAXOVER, PK_MINWITH, PK_MAXWITH };
 
 typedef struct dspop_pw
 	{
@@ -210,7 +211,7 @@ int gd_pointwise_descriptor (dspop* _op, gdsp_pw_op* out, gd_pw_resources* res)
 /* or / and need two descriptors (non-zero -> 1, then the interval rule); add / subtract go through
  * the accumulate kernels: those four run on their own from their apply function */
 static int fusable_kind (int kind)
-	{ return kind != PK_OR && kind != PK_AND && kind != PK_ADD && kind != PK_SUBTRACT; }
+	{ return kind != PK_OR && kind != PK_AND && kind != PK_ADD && kind != PK_SUBTRACT && kind < PK_MINOVER; }
 
 static void pw_apply (dspop* _op, arg_dont_complain(char* vName), arg_dont_complain(u32 vLen), valtype* v)
 	{
@@ -231,6 +232,29 @@ static void pw_apply (dspop* _op, arg_dont_complain(char* vName), arg_dont_compl
 		prog[1].table = res.table;
 		n = 2;
 		}
+	else if (op->kind == PK_MINOVER || op->kind == PK_MAXOVER)
+		{
+		/* minmax.c:197-419, :600-822: the extremum cell of every interval survives, everything else
+		 * (rest of the interval, gaps, chromosomes absent from the file) takes the fill value */
+		res.table = table_from_file (op, -1, true, true, false);
+		gd_check (gdsp_ivl_arg_extrema (gd.ctx, lay, gd.sig, res.table, op->kind == PK_MAXOVER), _op->name);
+		prog[0].code = GDSP_PW_IVL_KEEP_AT;  prog[0].a = op->a;  prog[0].table = res.table;
+		n = 1;
+		}
+	else if (op->kind == PK_MINWITH || op->kind == PK_MAXWITH)
+		{
+		/* minmax.c:1979-1982, :2265-2268: intervals in any order, overlaps allowed; the host reduces
+		 * them to disjoint pieces holding the smallest (largest) covering value */
+		ivlist l, pieces;
+		ivlist_init (&l);  ivlist_init (&pieces);
+		ivlist_read_file (&l, _op->name, op->filename, op->valColumn, op->originOne, false, false);
+		gd_paint_extreme (&l, op->kind == PK_MAXWITH, &pieces);
+		gd_check (gdsp_ivl_table_create (gd.ctx, gd.genome, pieces.seg, pieces.start, pieces.end, pieces.val, pieces.n, &res.table), _op->name);
+		ivlist_free (&l);  ivlist_free (&pieces);
+		prog[0].code = (op->kind == PK_MINWITH) ? GDSP_PW_IVL_MIN : GDSP_PW_IVL_MAX;  prog[0].table = res.table;
+		n = 1;
+		if (op->destroyFile) remove (op->filename);
+		}
 	else n = gd_pointwise_descriptor (_op, &prog[0], &res);
 	if (n > 0) gd_check (gdsp_pointwise (gd.ctx, lay, gd.sig, gd.sig, prog, n), _op->name);
 	gd_pw_release (&res);
@@ -241,6 +265,7 @@ static void pw_apply (dspop* _op, arg_dont_complain(char* vName), arg_dont_compl
 PW_APPLY (op_binarize)  PW_APPLY (op_add_constant)  PW_APPLY (op_absolute_value)  PW_APPLY (op_invert)
 PW_APPLY (op_clip)      PW_APPLY (op_erase)         PW_APPLY (op_add)             PW_APPLY (op_subtract)
 PW_APPLY (op_multiply)  PW_APPLY (op_divide)        PW_APPLY (op_mask)            PW_APPLY (op_mask_not)
+PW_APPLY (op_min_in_interval)  PW_APPLY (op_max_in_interval)  PW_APPLY (op_min_with)  PW_APPLY (op_max_with)
 PW_APPLY (op_or)        PW_APPLY (op_and)
 
 static dspop_pw* pw_new (char* name, int kind, opfunc_apply apply, int atRandom)
@@ -443,10 +468,9 @@ static void file_usage (char* name, FILE* f, char* indent, const char* what, int
 	fprintf (f, "%s%s\n%s\n", indent, what, indent);
 	fprintf (f, "%susage: %s <filename> [options]\n", indent, name);
 	if (hasValue)
-		{
 		fprintf (f, "%s  --value=<col>            column of the file that holds the value (default 4)\n", indent);
+	if (hasValue == 1)
 		fprintf (f, "%s  --novalue                the file has no value column (every value is 1)\n", indent);
-		}
 	fprintf (f, "%s  --origin=one             the file's intervals are origin-one, closed\n", indent);
 	fprintf (f, "%s  --origin=zero            the file's intervals are origin-zero, half-open\n", indent);
 	if (extra != NULL) fprintf (f, "%s%s\n", indent, extra);
@@ -459,12 +483,13 @@ static dspop* file_parse (char* name, int argc, char** argv, int kind, opfunc_ap
 	dspop_pw* op = pw_new (name, kind, apply, true);
 	op->valColumn = (int) get_named_global ("valColumn", 4-1);
 	op->originOne = (int) get_named_global ("originOne", false);
-	if (kind == PK_DIVIDE) op->a = valtypeMax;
+	if (kind == PK_DIVIDE || kind == PK_MINOVER) op->a = valtypeMax;
+	if (kind == PK_MAXOVER) op->a = 0.0;
 	for (; argc > 0; argv++, argc--)
 		{
 		char* arg = argv[0];
 		char* argVal = strchr (arg, '=');  if (argVal != NULL) argVal++;
-		if (valueOpts && (strcmp (arg, "--novalue") == 0 || strcmp (arg, "--novalues") == 0 || strcmp (arg, "--value=none") == 0))
+		if (valueOpts == 1 && (strcmp (arg, "--novalue") == 0 || strcmp (arg, "--novalues") == 0 || strcmp (arg, "--value=none") == 0))
 			op->valColumn = -1;
 		else if (valueOpts && strcmp_prefix (arg, "--value=") == 0)
 			{
@@ -477,8 +502,9 @@ static dspop* file_parse (char* name, int argc, char** argv, int kind, opfunc_ap
 		else if (strcmp (arg, "--origin=one") == 0 || strcmp (arg, "--origin=1") == 0)  op->originOne = true;
 		else if (strcmp (arg, "--origin=zero") == 0 || strcmp (arg, "--origin=0") == 0) op->originOne = false;
 		else if (destroyOpt && strcmp (arg, "--destroy") == 0) op->destroyFile = true;
-		else if (kind == PK_DIVIDE && strcmp_prefix (arg, "--infinity=") == 0) op->a = string_to_valtype (argVal);
-		else if ((kind == PK_MULTIPLY || kind == PK_DIVIDE) && strcmp (arg, "--debug") == 0) op->debug = true;
+		else if ((kind == PK_DIVIDE || kind == PK_MINOVER) && strcmp_prefix (arg, "--infinity=") == 0) op->a = string_to_valtype (argVal);
+		else if (kind == PK_MAXOVER && is_opt (arg, "--zero=", "Z=", "--Z=")) op->a = string_to_valtype (argVal);
+		else if ((kind == PK_MULTIPLY || kind == PK_DIVIDE || kind == PK_MINOVER || kind == PK_MAXOVER) && strcmp (arg, "--debug") == 0) op->debug = true;
 		else if ((kind == PK_MASK || kind == PK_MASKNOT) && is_opt (arg, "--mask=", "M=", "--M="))
 			{
 			if (op->haveA)
@@ -522,3 +548,16 @@ FILE_GROUP (op_or,       PK_OR,       "perform logical OR of the current set of 
             "Logical OR: non-zero positions become 1, and so do the positions covered by\n  the file's intervals (intervals whose value is 0 are ignored).", 1, 0, NULL)
 FILE_GROUP (op_and,      PK_AND,      "perform logical AND of the current set of interval values with intervals read from a file",
             "Logical AND: non-zero positions become 1, and positions not covered by the\n  file's intervals become 0. The file must be sorted along each chromosome and\n  its intervals must not overlap.", 1, 0, NULL)
+
+FILE_GROUP (op_min_in_interval, PK_MINOVER, "find the minimum value in each of a set of intervals read from a file",
+            "Keep, in every interval of a file, only the position holding the minimum; all\n  other positions (inside and outside the intervals) become infinity. Ties go to\n  the position nearest the centre of the interval. The file must be sorted along\n  each chromosome and its intervals must not overlap.", 0, 0,
+            "  --infinity=<value>       value given to every other position (default is the largest double)")
+FILE_GROUP (op_max_in_interval, PK_MAXOVER, "find the maximum value in each of a set of intervals read from a file",
+            "Keep, in every interval of a file, only the position holding the maximum; all\n  other positions (inside and outside the intervals) become zero. Ties go to the\n  position nearest the centre of the interval. The file must be sorted along\n  each chromosome and its intervals must not overlap.", 0, 0,
+            "  --zero=<value>           (Z=) value given to every other position (default 0.0)")
+FILE_GROUP (op_min_with, PK_MINWITH, "take the minimum of the current set of interval values and values read from a file",
+            "Position by position, keep the smaller of the signal and the values of the\n  intervals of a file covering that position.", 2, 1,
+            "  --destroy                delete the file after reading it")
+FILE_GROUP (op_max_with, PK_MAXWITH, "take the maximum of the current set of interval values and values read from a file",
+            "Position by position, keep the larger of the signal and the values of the\n  intervals of a file covering that position.", 2, 1,
+            "  --destroy                delete the file after reading it")

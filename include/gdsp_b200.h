@@ -195,8 +195,13 @@ typedef enum gdsp_pw_code
 	                                                        logical.c:or      */
 	GDSP_PW_IVL_SET_OUTSIDE,  /* gap v=a                    mask.c:483-668,
 	                                                        logical.c:and     */
-	GDSP_PW_IVL_ASSIGN        /* inside v=val (input --overlap=min/max after the
+	GDSP_PW_IVL_ASSIGN,       /* inside v=val (input --overlap=min/max after the
 	                             host reduced the overlaps, genodsp.c:1307-1322) */
+	GDSP_PW_IVL_MIN,          /* inside v=min(v,val)        minmax.c:1979-1982 (minwith; the host
+	                             reduces overlapping intervals to their minimum first) */
+	GDSP_PW_IVL_MAX,          /* inside v=max(v,val)        minmax.c:2265-2268 (maxwith) */
+	GDSP_PW_IVL_KEEP_AT       /* v=a everywhere except at the one cell of every interval that
+	                             gdsp_ivl_arg_extrema chose  minmax.c:345-348, :748-751 (minover/maxover) */
 	} gdsp_pw_code;
 
 #define GDSP_PW_ERASE_HAVE_MIN    1u
@@ -242,6 +247,18 @@ int  gdsp_minmax (gdsp_ctx* ctx, const gdsp_layout* lay, const double* sig,
  * strtod(printf("%.10f", v)) (inf -> DBL_MAX), every zero +0.0.  Exact integer
  * arithmetic on the device, no text.  decimals must be 10.  In place. */
 int  gdsp_text_roundtrip (gdsp_ctx* ctx, const gdsp_layout* lay, double* sig, int decimals);
+
+/* minover / maxover, minmax.c:322-343 / :725-746: for every interval of the table find
+ * the cell holding the minimum (maximum); ties go to the cell farthest from both ends of
+ * its interval, then to the earliest.  The chosen buffer cell index replaces the table's
+ * value column (device side); apply GDSP_PW_IVL_KEEP_AT with the same table next. */
+int  gdsp_ivl_arg_extrema (gdsp_ctx* ctx, const gdsp_layout* lay, const double* sig,
+                           gdsp_ivl_table* table, int want_max);
+
+/* map, map.c:263-357: piecewise-linear function through n breakpoints (h_in strictly
+ * ascending); values at or beyond the ends take the end outputs.  In place. */
+int  gdsp_map_values (gdsp_ctx* ctx, const gdsp_layout* lay, double* sig,
+                      const double* h_in, const double* h_out, int n);
 
 /* ---- percentile -------------------------------------------------------------
  * op_percentile_apply, percentile.c:392-751.  Order statistics of the samples

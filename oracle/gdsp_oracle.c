@@ -131,6 +131,69 @@ void gdo_text_roundtrip10 (double* v, u32 n)
 		}
 	}
 
+/* minover / maxover, minmax.c:322-348 and :725-751.  One pass over each interval keeps the best
+ * value, its index and that index's inset (distance to the nearer interval end); an equal value
+ * replaces the incumbent only with a strictly larger inset.  Then the interval is filled except at
+ * the winner; gaps before, between and after the intervals are filled too (minmax.c:312-320,
+ * :354-363). */
+void gdo_over_intervals (double* v, u32 n, const u32* s, const u32* e, u32 m, int want_max, double fill)
+	{
+	u32 prevEnd = 0;
+	for (u32 k = 0; k < m; k++)
+		{
+		for (u32 ix = prevEnd; ix < s[k]; ix++) v[ix] = fill;
+		double best = v[s[k]];
+		u32 bestIx = s[k], bestInset = 0;
+		for (u32 ix = s[k] + 1; ix < e[k]; ix++)
+			{
+			int worse  = want_max ? (v[ix] < best) : (v[ix] > best);
+			int better = want_max ? (v[ix] > best) : (v[ix] < best);
+			if (worse) continue;
+			u32 inset = (ix - s[k] < e[k] - ix) ? ix - s[k] : e[k] - ix;
+			if (better) { best = v[ix];  bestIx = ix;  bestInset = inset; }
+			else if (inset > bestInset) { bestIx = ix;  bestInset = inset; }
+			}
+		for (u32 ix = s[k]; ix < e[k]; ix++) if (ix != bestIx) v[ix] = fill;
+		prevEnd = e[k];
+		}
+	for (u32 ix = prevEnd; ix < n; ix++) v[ix] = fill;
+	}
+
+/* minwith / maxwith, minmax.c:1979-1982 and :2265-2268 */
+void gdo_with_intervals (double* v, u32 n, const u32* s, const u32* e, const double* val, u32 m, int want_max)
+	{
+	(void) n;
+	for (u32 k = 0; k < m; k++)
+		for (u32 ix = s[k]; ix < e[k]; ix++)
+			{
+			if (want_max) { if (val[k] > v[ix]) v[ix] = val[k]; }
+			else          { if (val[k] < v[ix]) v[ix] = val[k]; }
+			}
+	}
+
+/* map, map.c:263-357, for breakpoints with distinct inputs (then the reference's piece cache does
+ * not influence the result): clamp at the ends, exact hits return the listed output, otherwise
+ * outLo + (x - inLo) * outDiff / inDiff in that evaluation order (map.c:340). */
+void gdo_map (double* v, u32 n, const double* in, const double* out, u32 len)
+	{
+	for (u32 i = 0; i < n; i++)
+		{
+		double x = v[i];
+		if (x <= in[0])       { v[i] = out[0];        continue; }
+		if (x >= in[len - 1]) { v[i] = out[len - 1];  continue; }
+		u32 lo = 0, hi = len - 1;
+		while (lo + 1 < hi)
+			{
+			u32 mid = (lo + hi) / 2;
+			if (x < in[mid]) hi = mid; else lo = mid;
+			}
+		double inDiff = in[lo + 1] - in[lo], outDiff = out[lo + 1] - out[lo];
+		if      (x == in[lo])     v[i] = out[lo];
+		else if (x == in[lo + 1]) v[i] = out[lo + 1];
+		else                      v[i] = out[lo] + (x - in[lo]) * outDiff / inDiff;
+		}
+	}
+
 void gdo_cumulative (double* v, u32 n)
 	{
 	double run = 0.0;

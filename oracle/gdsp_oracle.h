@@ -26,6 +26,12 @@ void gdo_sliding_sum (double* v, uint32_t n, uint32_t W, double denom);
 void gdo_hann_taps   (double* w, uint32_t W);
 void gdo_smooth      (double* v, uint32_t n, uint32_t W);
 void gdo_cumulative  (double* v, uint32_t n);
+/* minover / maxover on one chromosome (minmax.c:322-348, :725-751): s/e sorted, disjoint */
+void gdo_over_intervals (double* v, uint32_t n, const uint32_t* s, const uint32_t* e, uint32_t m, int want_max, double fill);
+/* minwith / maxwith (minmax.c:1979-1982, :2265-2268): any order, overlaps allowed */
+void gdo_with_intervals (double* v, uint32_t n, const uint32_t* s, const uint32_t* e, const double* val, uint32_t m, int want_max);
+/* map (map.c:263-357), breakpoints sorted ascending by input */
+void gdo_map (double* v, uint32_t n, const double* in, const double* out, uint32_t len);
 /* percentile --preserve: write_all_chromosomes + read_all_chromosomes (genodsp.c:1717-1775) */
 void gdo_text_roundtrip10 (double* v, uint32_t n);
 /* minmax.c */

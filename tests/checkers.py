@@ -48,6 +48,9 @@ class Oracle:
             "gdo_smooth": [c_dp, u32, u32],
             "gdo_cumulative": [c_dp, u32],
             "gdo_text_roundtrip10": [c_dp, u32],
+            "gdo_over_intervals": [c_dp, u32, c_u32p, c_u32p, u32, C.c_int, C.c_double],
+            "gdo_with_intervals": [c_dp, u32, c_u32p, c_u32p, c_dp, u32, C.c_int],
+            "gdo_map": [c_dp, u32, c_dp, c_dp, u32],
             "gdo_local_extrema": [c_dp, u32, u32, i, d],
             "gdo_best_extrema": [c_dp, u32, u32, i],
             "gdo_close": [c_dp, u32, d, d, d, d],
@@ -110,6 +113,21 @@ class Oracle:
 
     def cumulative(self, v):
         self.lib.gdo_cumulative(*self._v(v)); return v
+
+    def over_intervals(self, v, s, e, want_max, fill):
+        s = np.ascontiguousarray(s, np.uint32); e = np.ascontiguousarray(e, np.uint32)
+        self.lib.gdo_over_intervals(*self._v(v), s.ctypes.data_as(c_u32p), e.ctypes.data_as(c_u32p), s.size, int(want_max), fill)
+        return v
+
+    def with_intervals(self, v, s, e, val, want_max):
+        s = np.ascontiguousarray(s, np.uint32); e = np.ascontiguousarray(e, np.uint32); val = np.ascontiguousarray(val, np.float64)
+        self.lib.gdo_with_intervals(*self._v(v), s.ctypes.data_as(c_u32p), e.ctypes.data_as(c_u32p), val.ctypes.data_as(c_dp), s.size, int(want_max))
+        return v
+
+    def map_values(self, v, vin, vout):
+        vin = np.ascontiguousarray(vin, np.float64); vout = np.ascontiguousarray(vout, np.float64)
+        self.lib.gdo_map(*self._v(v), vin.ctypes.data_as(c_dp), vout.ctypes.data_as(c_dp), vin.size)
+        return v
 
     def text_roundtrip10(self, v):
         self.lib.gdo_text_roundtrip10(*self._v(v)); return v

@@ -182,3 +182,21 @@ def test_percentile_preserve_roundtrip(data):
                            "=", "percentile", "10..90by20", "--window=7", "--min=0.25", "--preserve=scratch2.pres",
                            "=", "clip", "--max=percentile90"])
     assert os.path.getsize(data / "scratch.pres") == 0
+
+
+def test_file_extrema_and_map_operators(data):
+    """minover / maxover / minwith / maxwith / map through the CLI"""
+    rng = np.random.default_rng(77)
+    with open(data / "curve.map", "w") as f:
+        f.write("# depth -> score\n")
+        for x, y in [(0, 0), (6, 1.5), (2, 0.25), (12, 1.75), (40, -3)]:
+            f.write("%d %r\n" % (x, y))
+    with open(data / "loose.iv", "w") as f:          # unsorted, overlapping, valued
+        for _ in range(600):
+            n, l = CHROMS[int(rng.integers(0, 4))]
+            a = int(rng.integers(0, max(1, l - 900)))
+            f.write("%s\t%d\t%d\t%s\n" % (n, a, min(l, a + int(rng.integers(1, 900))), repr(float(rng.integers(0, 13)) / 2)))
+    assert_same(data, C + ["--novalue", "--progress=operations", "=", "maxover", "trackB.iv"])
+    assert_same(data, C + ["--novalue", "=", "slidingsum", "--window=25", "=", "minover", "trackB.iv", "--infinity=99.5"])
+    assert_same(data, C + ["--novalue", "--progress=operations", "=", "minwith", "loose.iv", "=", "maxwith", "trackB.iv"])
+    assert_same(data, C + ["--novalue", "--precision=12", "=", "map", "curve.map", "=", "maxwith", "loose.iv", "--value=4"])

@@ -427,6 +427,63 @@ def test_interval_table_ops(genome, orc, op):
     table.close()
 
 
+@pytest.mark.parametrize("op", ["minover", "maxover"])
+@pytest.mark.parametrize("kind", ["int", "real"])
+def test_over_intervals(genome, orc, op, kind):
+    """minover / maxover: gdsp_ivl_arg_extrema + GDSP_PW_IVL_KEEP_AT vs the reference loop (ties by
+    inset, then earliest), fill everywhere else incl. a chromosome the table never mentions"""
+    rng = np.random.default_rng(5 + len(op))
+    seg, s, e, val = _sorted_disjoint(rng, genome, skip=("chr3",))
+    # a few long intervals (more than one warp stride) and single-cell ones
+    table = genome.interval_table(seg, s, e, None)
+    inputs = load(genome, rng, kind)
+    if kind == "int":
+        for name in inputs:
+            inputs[name] = np.floor(inputs[name] / 3.0); genome.set_chrom(name, inputs[name])
+    fill = -2.5
+    (genome.minover if op == "minover" else genome.maxover)(table, fill)
+    for k in range(genome.nseg):
+        name, n = genome.chroms[genome.seg_chrom[k]]
+        sel = seg == k
+        want = orc.over_intervals(inputs[name].copy(), s[sel], e[sel], op == "maxover", fill)
+        got = genome.get_chrom(name)
+        bad = np.nonzero(bits(got) != bits(want))[0]
+        assert bad.size == 0, (op, name, bad[:5], got[bad[:5]], want[bad[:5]])
+    table.close()
+
+
+@pytest.mark.parametrize("op", ["minwith", "maxwith"])
+def test_with_intervals(genome, orc, op):
+    from genodsp_b200 import capi
+    rng = np.random.default_rng(31)
+    seg, s, e, val = _sorted_disjoint(rng, genome, skip=("chr2",))
+    table = genome.interval_table(seg, s, e, val)
+    inputs = load(genome, rng, "real")
+    genome.pointwise([(capi.PW_IVL_MIN if op == "minwith" else capi.PW_IVL_MAX, 0.0, 0, 0, 0, table)])
+    for k in range(genome.nseg):
+        name, n = genome.chroms[genome.seg_chrom[k]]
+        sel = seg == k
+        want = orc.with_intervals(inputs[name].copy(), s[sel], e[sel], val[sel], op == "maxwith")
+        assert np.array_equal(bits(genome.get_chrom(name)), bits(want)), (op, name)
+    table.close()
+
+
+@pytest.mark.parametrize("npoints", [1, 2, 23, 5000])
+def test_map_values(genome, orc, npoints):
+    rng = np.random.default_rng(npoints)
+    vin = np.sort(rng.choice(np.arange(-40000, 40001), npoints, replace=False)) / 4096.0
+    vout = rng.normal(0, 5, npoints)
+    inputs = load(genome, rng, "real")
+    for name, n in CHROMS:                 # exact hits and both clamped ends
+        k = min(n, npoints)
+        inputs[name][:k] = vin[:k]
+        if n > k + 2:
+            inputs[name][k] = vin[0] - 1; inputs[name][k + 1] = vin[-1] + 1
+        genome.set_chrom(name, inputs[name])
+    genome.map_values(vin, vout)
+    compare(genome, inputs, lambda v: orc.map_values(v, vin, vout), what="map %d" % npoints)
+
+
 @pytest.mark.parametrize("collapse", [True, False])
 @pytest.mark.parametrize("show", [0, 1])
 @pytest.mark.parametrize("kind", ["sparse", "int", "real"])

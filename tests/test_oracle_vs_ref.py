@@ -448,3 +448,65 @@ def test_preserve_roundtrip_matches_reference(tmp_path):
     g.apply("percentile", "50", "--quiet", "--preserve=" + str(tmp_path / "scratch"))
     got = g.vec["chrT"].copy()
     assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+
+
+def _write_intervals(path, name, s, e, val=None):
+    with open(path, "w") as f:
+        for k in range(len(s)):
+            if val is None:
+                f.write("%s %d %d\n" % (name, s[k], e[k]))
+            else:
+                f.write("%s %d %d %r\n" % (name, s[k], e[k], float(val[k])))
+
+
+@pytest.mark.parametrize("op", ["minover", "maxover"])
+def test_over_intervals_matches_reference(tmp_path, op):
+    """oracle gdo_over_intervals == op_min/max_in_interval_apply (minmax.c:197-419, :600-822), ties included"""
+    rng = np.random.default_rng(11)
+    n = 50000
+    v = rng.integers(0, 4, n).astype(np.float64)            # many ties
+    s, e, pos = [], [], int(rng.integers(0, 30))
+    while pos < n:
+        end = min(n, pos + int(rng.integers(1, 200)))
+        s.append(pos); e.append(end); pos = end + int(rng.integers(0, 100))
+    _write_intervals(tmp_path / "iv", "chrT", s, e)
+    g = RefGenome([("chrT", n), ("chrU", 100)])
+    g.vec["chrT"][:] = v; g.vec["chrU"][:] = 3.0
+    fill = -7.5
+    g.apply(op, str(tmp_path / "iv"), ("--infinity=%r" if op == "minover" else "--zero=%r") % fill)
+    want = Oracle().over_intervals(v.copy(), s, e, op == "maxover", fill)
+    assert np.array_equal(g.vec["chrT"].view(np.uint64), want.view(np.uint64))
+    assert np.all(g.vec["chrU"] == fill)                    # absent chromosome
+
+
+@pytest.mark.parametrize("op", ["minwith", "maxwith"])
+def test_with_intervals_matches_reference(tmp_path, op):
+    rng = np.random.default_rng(12)
+    n = 30000
+    v = rng.normal(0, 2, n)
+    m = 800
+    s = rng.integers(0, n - 500, m); e = s + rng.integers(1, 500, m); val = rng.integers(-8, 9, m) / 4.0
+    _write_intervals(tmp_path / "iv", "chrT", s, e, val)
+    g = RefGenome([("chrT", n)])
+    g.vec["chrT"][:] = v
+    g.apply(op, str(tmp_path / "iv"))
+    want = Oracle().with_intervals(v.copy(), s, e, val, op == "maxwith")
+    assert np.array_equal(g.vec["chrT"].view(np.uint64), want.view(np.uint64))
+
+
+def test_map_matches_reference(tmp_path):
+    """oracle gdo_map == op_map_apply (map.c:194-385) for distinct breakpoints, incl. exact hits and both ends"""
+    rng = np.random.default_rng(13)
+    n = 40000
+    vin = np.sort(rng.choice(np.arange(-40, 41), 23, replace=False)) / 4.0
+    vout = rng.normal(0, 5, vin.size)
+    with open(tmp_path / "map", "w") as f:
+        f.write("# a comment\n\n")
+        for k in rng.permutation(vin.size):
+            f.write("%r %r\n" % (float(vin[k]), float(vout[k])))
+    v = np.concatenate([rng.normal(0, 6, n), vin, [vin[0] - 1, vin[-1] + 1]])
+    g = RefGenome([("chrT", v.size)])
+    g.vec["chrT"][:] = v
+    g.apply("map", str(tmp_path / "map"))
+    want = Oracle().map_values(v.copy(), vin, vout)
+    assert np.array_equal(g.vec["chrT"].view(np.uint64), want.view(np.uint64))
