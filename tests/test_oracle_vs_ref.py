@@ -450,7 +450,7 @@ def test_preserve_roundtrip_matches_reference(tmp_path):
     assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
 
 
-def _write_intervals(path, name, s, e, val=None):
+def _write_chrom_intervals(path, name, s, e, val=None):
     with open(path, "w") as f:
         for k in range(len(s)):
             if val is None:
@@ -469,7 +469,7 @@ def test_over_intervals_matches_reference(tmp_path, op):
     while pos < n:
         end = min(n, pos + int(rng.integers(1, 200)))
         s.append(pos); e.append(end); pos = end + int(rng.integers(0, 100))
-    _write_intervals(tmp_path / "iv", "chrT", s, e)
+    _write_chrom_intervals(tmp_path / "iv", "chrT", s, e)
     g = RefGenome([("chrT", n), ("chrU", 100)])
     g.vec["chrT"][:] = v; g.vec["chrU"][:] = 3.0
     fill = -7.5
@@ -486,7 +486,7 @@ def test_with_intervals_matches_reference(tmp_path, op):
     v = rng.normal(0, 2, n)
     m = 800
     s = rng.integers(0, n - 500, m); e = s + rng.integers(1, 500, m); val = rng.integers(-8, 9, m) / 4.0
-    _write_intervals(tmp_path / "iv", "chrT", s, e, val)
+    _write_chrom_intervals(tmp_path / "iv", "chrT", s, e, val)
     g = RefGenome([("chrT", n)])
     g.vec["chrT"][:] = v
     g.apply(op, str(tmp_path / "iv"))
