@@ -43,6 +43,8 @@ SIGNATURES = {
     "gdsp_ctx_destroy": (None, [_vp]),
     "gdsp_ctx_set_stream": (_i, [_vp, _vp]),
     "gdsp_sync": (_i, [_vp]),
+    "gdsp_malloc_host": (_i, [C.c_size_t, C.POINTER(_vp)]),
+    "gdsp_free_host": (_i, [_vp]),
     "gdsp_last_error": (C.c_char_p, []),
     "gdsp_launch_count": (C.c_uint64, []),
     "gdsp_version": (C.c_char_p, []),
@@ -82,6 +84,8 @@ SIGNATURES = {
     "gdsp_sort_genome": (_i, [_vp, _vp, _vp, _vp, _u64, C.POINTER(_i)]),
     "gdsp_ivl_arg_extrema": (_i, [_vp, _vp, _vp, _vp, _i]),
     "gdsp_map_values": (_i, [_vp, _vp, _vp, _dp, _dp, _i]),
+    "gdsp_format_runs_max_bytes": (C.c_size_t, [_u64, C.c_char_p]),
+    "gdsp_format_runs": (_i, [_vp, _vp, _vp, _vp, _u64, C.c_char_p, _u32, _u32, _i, _i, _vp, _u64, _u64p, C.POINTER(_i)]),
     "gdsp_text_roundtrip": (_i, [_vp, _vp, _vp, _i]),
     "gdsp_pct_sample": (_i, [_vp, _vp, _vp, _u32, _d, _d, _u64, _u64, _u32, _u64, _vp, _u32p, _u64p]),
     "gdsp_sort_array": (_i, [_vp, _vp, _vp, _u64, C.POINTER(_i)]),

@@ -123,6 +123,20 @@ extern "C" int gdsp_device_info (gdsp_ctx* c, int* sm, int* maj, int* min, size_
 	return GDSP_OK;
 	}
 
+// page-locked host memory for callers that stream results out (text output of the CLI)
+extern "C" int gdsp_malloc_host (size_t bytes, void** out)
+	{
+	GDSP_REQUIRE (out != NULL, "gdsp_malloc_host: out is NULL");
+	GDSP_CUDA (cudaMallocHost (out, bytes ? bytes : 1));
+	return GDSP_OK;
+	}
+
+extern "C" int gdsp_free_host (void* p)
+	{
+	if (p != NULL) GDSP_CUDA (cudaFreeHost (p));
+	return GDSP_OK;
+	}
+
 int gdsp_host_scratch (gdsp_ctx* c, size_t bytes, void** out)
 	{
 	if (c->host_small_bytes < bytes)

@@ -524,6 +524,24 @@ class Genome:
         return out
 
 
+def format_runs(genome, name, start, end, val, precision, add_start=0, add_end=0, with_value=True):
+    """gdsp_format_runs on numpy run arrays -> bytes (None if the device declined: NaN/inf/huge values)"""
+    t = genome.torch
+    n = int(len(start))
+    ds = t.from_numpy(np.ascontiguousarray(start, np.uint32).view(np.int32)).to(genome.device)
+    de = t.from_numpy(np.ascontiguousarray(end, np.uint32).view(np.int32)).to(genome.device)
+    dv = t.from_numpy(np.ascontiguousarray(val, np.float64)).to(genome.device)
+    cap = int(genome.lib.gdsp_format_runs_max_bytes(n, name.encode())) + 16
+    text = t.empty(cap, dtype=t.uint8, device=genome.device)
+    nbytes, unsupported = C.c_uint64(), C.c_int()
+    check(genome.lib.gdsp_format_runs(genome.ctx, genome._p(ds), genome._p(de), genome._p(dv), n, name.encode(),
+                                      int(add_start), int(add_end), int(with_value), int(precision), genome._p(text), cap,
+                                      C.byref(nbytes), C.byref(unsupported)))
+    if unsupported.value:
+        return None
+    return bytes(text[:int(nbytes.value)].cpu().numpy().tobytes())
+
+
 class IntervalTable:
     """sorted, disjoint interval table on the device (gdsp_ivl_table)"""
 

@@ -347,6 +347,46 @@ static void free_scratch_vectors (void)
 static u64 riLineNumber = 0;         /* never reset, like the reference's static counter */
 static int riMissingEol = false;
 
+/* fgets with the same contract (at most len-1 characters, stops after a newline, NULL at end of
+ * file with nothing read) fed from 1 MB blocks: the locked per-call stdio path costs more than the
+ * parsing of a 25-character line. */
+#define LR_CAP (1u << 20)
+static struct { FILE* f;  char* buf;  size_t pos, len;  int eof; } lr;
+
+static char* gd_fgets (char* dst, int dstLen, FILE* f)
+	{
+	if (lr.f != f)
+		{
+		lr.f = f;  lr.pos = lr.len = 0;  lr.eof = false;
+		if (lr.buf == NULL) lr.buf = (char*) malloc (LR_CAP);
+		}
+	int n = 0;
+	while (n < dstLen - 1)
+		{
+		if (lr.pos == lr.len)
+			{
+			if (lr.eof) break;
+			lr.len = fread (lr.buf, 1, LR_CAP, f);  lr.pos = 0;
+			if (lr.len == 0) { lr.eof = true;  break; }
+			}
+		size_t avail = lr.len - lr.pos, room = (size_t) (dstLen - 1 - n);
+		size_t take = (avail < room) ? avail : room;
+		char* nl = (char*) memchr (lr.buf + lr.pos, '\n', take);
+		if (nl != NULL) take = (size_t) (nl - (lr.buf + lr.pos)) + 1;
+		memcpy (dst + n, lr.buf + lr.pos, take);
+		n += (int) take;  lr.pos += take;
+		if (nl != NULL) break;
+		}
+	if (n == 0) { lr.f = NULL;  return NULL; }          /* the FILE may be closed and its address reused */
+	dst[n] = 0;
+	return dst;
+	}
+
+/* same classification as isspace() in the C locale, without the call */
+static inline int is_ws (char c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
+static inline char* ws_skip   (char* s) { while (*s != 0 &&  is_ws (*s)) s++;  return s; }
+static inline char* dark_skip (char* s) { while (*s != 0 && !is_ws (*s)) s++;  return s; }
+
 static inline int fast_u32 (const char* s, u32* out)
 	{
 	u64 v = 0;
@@ -379,7 +419,7 @@ int read_interval (FILE* f, char* buffer, int bufferLen, int valCol,
 
 	while (true)
 		{
-		if (fgets (buffer, bufferLen, f) == NULL) return false;
+		if (gd_fgets (buffer, bufferLen, f) == NULL) return false;
 		riLineNumber++;
 		if (riMissingEol)
 			{
@@ -389,11 +429,11 @@ int read_interval (FILE* f, char* buffer, int bufferLen, int valCol,
 		int len = (int) strlen (buffer);
 		if (len != 0) riMissingEol = (buffer[len-1] != '\n');
 		if (dbgInput) fprintf (stderr, "input = \"%s\"\n", buffer);
-		if (strcmp_prefix (buffer, "track ") == 0) continue;
+		if (buffer[0] == 't' && strcmp_prefix (buffer, "track ") == 0) continue;
 
 		int progressNow = (reportInputProgress != 0)
 		               && (riLineNumber == 1 || riLineNumber % reportInputProgress == 0);
-		scan = skip_whitespace (buffer);
+		scan = ws_skip (buffer);
 		if (*scan == 0)
 			{
 			if (progressNow) fprintf (stderr, "progress: input line %s\n", ucommatize (riLineNumber));
@@ -415,14 +455,14 @@ int read_interval (FILE* f, char* buffer, int bufferLen, int valCol,
 		fprintf (stderr, "problem at line %s, line contains no chromosome or begins with whitespace\n", ucommatize (riLineNumber));
 		exit (EXIT_FAILURE);
 		}
-	mark = skip_darkspace (scan);  scan = skip_whitespace (mark);  if (*mark != 0) *mark = 0;
+	mark = dark_skip (scan);  scan = ws_skip (mark);  if (*mark != 0) *mark = 0;
 	if (*scan == 0)
 		{
 		fprintf (stderr, "problem at line %s, line contains no interval start\n"
 		                 "(expected \"chromosome start end ...\", but there are fewer than 2 fields)\n", ucommatize (riLineNumber));
 		exit (EXIT_FAILURE);
 		}
-	field = scan;  mark = skip_darkspace (scan);  scan = skip_whitespace (mark);  if (*mark != 0) *mark = 0;
+	field = scan;  mark = dark_skip (scan);  scan = ws_skip (mark);  if (*mark != 0) *mark = 0;
 	if (!fast_u32 (field, &start)) start = (u32) string_to_u32 (field);
 	if (*scan == 0)
 		{
@@ -430,7 +470,7 @@ int read_interval (FILE* f, char* buffer, int bufferLen, int valCol,
 		                 "(expected \"chromosome start end ...\", but there are fewer than 3 fields)\n", ucommatize (riLineNumber));
 		exit (EXIT_FAILURE);
 		}
-	field = scan;  mark = skip_darkspace (scan);  scan = skip_whitespace (mark);  if (*mark != 0) *mark = 0;
+	field = scan;  mark = dark_skip (scan);  scan = ws_skip (mark);  if (*mark != 0) *mark = 0;
 	if (!fast_u32 (field, &end)) end = (u32) string_to_u32 (field);
 
 	if (valCol == -1 || _val == NULL) val = 1.0;
@@ -444,7 +484,7 @@ int read_interval (FILE* f, char* buffer, int bufferLen, int valCol,
 				                 "(expected \"chromosome start end value\", but there are fewer than 4 fields)\n", ucommatize (riLineNumber));
 				exit (EXIT_FAILURE);
 				}
-			field = scan;  mark = skip_darkspace (scan);  scan = skip_whitespace (mark);
+			field = scan;  mark = dark_skip (scan);  scan = ws_skip (mark);
 			}
 		if (*mark != 0) *mark = 0;
 		val = parse_value (field);
@@ -585,6 +625,8 @@ void report_intervals (FILE* f, int precision, int noOutVals, int collapse, int 
 	u64 cap = 1u << 20;
 	u32 *hS = NULL, *hE = NULL;  valtype* hV = NULL;  u64 hCap = 0;
 	void *dS = NULL, *dE = NULL, *dV = NULL;  u64 dCap = 0;
+	void *dText = NULL, *hText = NULL;  size_t dTextCap = 0, hTextCap = 0;
+	u64 hostFirst = 0;
 
 	for (spec* cs = chromsOfInterest; cs != NULL; cs = cs->next)
 		{
@@ -607,6 +649,45 @@ void report_intervals (FILE* f, int precision, int noOutVals, int collapse, int 
 			gd_check (st, "output");
 			break;
 			}
+		/* device formatter (gdsp_format_runs): the text of the chromosome is produced on the GPU chunk by
+		 * chunk and only copied out and written here.  NA gap lines and values the device declines
+		 * (NaN, infinities, >= 2^63) take the host loop below. */
+		if (nRuns && showUncov != uncovered_NA && !getenv ("GENODSP_HOST_FORMAT"))
+			{
+			const u64 CHUNK = 4u << 20;
+			int declined = false;
+			u64 done = 0;
+			for (; done < nRuns && !declined; )
+				{
+				u64 m = (nRuns - done < CHUNK) ? nRuns - done : CHUNK;
+				size_t need = gdsp_format_runs_max_bytes (m, cs->chrom);
+				if (dTextCap < need)
+					{
+					if (dText) gdsp_free (gd.ctx, dText);
+					gd_check (gdsp_malloc (gd.ctx, need, &dText), "output");
+					dTextCap = need;
+					}
+				u64 bytes = 0;
+				gd_check (gdsp_format_runs (gd.ctx, (u32*) dS + done, (u32*) dE + done, (double*) dV + done, m, cs->chrom,
+				                            cs->start + o, cs->start, !noOutVals, precision, (char*) dText, dTextCap,
+				                            &bytes, &declined), "output");
+				if (declined) break;
+				if (hTextCap < bytes)
+					{
+					if (hText) gdsp_free_host (hText);
+					hTextCap = bytes + (bytes >> 2) + (1u << 20);
+					gd_check (gdsp_malloc_host (hTextCap, &hText), "output");
+					}
+				gd_check (gdsp_d2h (gd.ctx, hText, dText, bytes), "output");
+				out_flush (f);
+				fwrite (hText, 1, bytes, f);
+				done += m;
+				}
+			if (!declined) continue;
+			/* the host formats what is left of this chromosome */
+			hostFirst = done;
+			}
+		else hostFirst = 0;
 		if (hCap < nRuns)
 			{
 			free (hS);  free (hE);  free (hV);
@@ -621,7 +702,8 @@ void report_intervals (FILE* f, int precision, int noOutVals, int collapse, int 
 			}
 		size_t cl = strlen (cs->chrom);
 		u32 prevEnd = 0;
-		for (u64 r = 0; r < nRuns; r++)
+		if (hostFirst > 0 && hostFirst <= nRuns) prevEnd = cs->start + hE[hostFirst - 1];
+		for (u64 r = hostFirst; r < nRuns; r++)
 			{
 			u32 s = cs->start + hS[r], e = cs->start + hE[r];
 			if (showUncov == uncovered_NA && s != prevEnd) out_line (f, cs->chrom, cl, prevEnd + o, s, 2, 0, 0.0);
@@ -634,6 +716,8 @@ void report_intervals (FILE* f, int precision, int noOutVals, int collapse, int 
 	out_flush (f);
 	if (trackOperations) tracking_report ("output(--done--)\n");
 	if (dS) { gdsp_free (gd.ctx, dS);  gdsp_free (gd.ctx, dE);  gdsp_free (gd.ctx, dV); }
+	if (dText) gdsp_free (gd.ctx, dText);
+	if (hText) gdsp_free_host (hText);
 	free (hS);  free (hE);  free (hV);
 	}
 
@@ -901,8 +985,24 @@ static void run_pipeline (void)
 		}
 	}
 
+/* GENODSP_TIMING=1: wall clock of the program's phases on stderr (not part of the reference's output) */
+#include <time.h>
+static double phase_clock (void)
+	{ struct timespec t;  clock_gettime (CLOCK_MONOTONIC, &t);  return t.tv_sec + 1e-9 * t.tv_nsec; }
+static double phaseT0;
+static void phase_mark (const char* what)
+	{
+	static int on = -1;
+	if (on < 0) on = (getenv ("GENODSP_TIMING") != NULL);
+	if (!on) return;
+	double now = phase_clock ();
+	if (what != NULL) fprintf (stderr, "[timing] %-12s %.3f s\n", what, now - phaseT0);
+	phaseT0 = now;
+	}
+
 int main (int argc, char** argv)
 	{
+	phase_mark (NULL);
 	set_named_global ("valColumn",     (valtype) valColumn);
 	set_named_global ("valPrecision",  (valtype) valPrecision);
 	set_named_global ("collapseRuns",  (valtype) collapseRuns);
@@ -918,16 +1018,23 @@ int main (int argc, char** argv)
 	if (trackOperations)
 		for (int i = 0; chromsSorted[i] != NULL; i++)
 			tracking_report ("allocate(%s / %s bytes)\n", chromsSorted[i]->chrom, ucommatize (chromsSorted[i]->length));
+	phase_mark ("parse args");
 	gd_device_open ();
 	if (trackOperations) tracking_report ("allocate(--done--)\n");
+	phase_mark ("device open");
 
 	if (pipeline == NULL || strcmp (pipeline->name, "input") != 0)
 		read_intervals (stdin, valColumn, originOne, ri_overlapSum, false, 0.0);
+	if (getenv ("GENODSP_TIMING") != NULL) gdsp_sync (gd.ctx);
+	phase_mark ("input");
 
 	run_pipeline ();
+	if (getenv ("GENODSP_TIMING") != NULL) gdsp_sync (gd.ctx);
+	phase_mark ("operators");
 
 	if (!inhibitOutput)
 		report_intervals (stdout, valPrecision, noOutputValues, collapseRuns, showUncovered, originOne);
+	phase_mark ("output");
 
 	gdsp_sync (gd.ctx);
 	free_scratch_vectors ();

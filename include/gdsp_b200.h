@@ -69,6 +69,9 @@ int  gdsp_ctx_create   (int device, void* stream, gdsp_ctx** out);
 void gdsp_ctx_destroy  (gdsp_ctx* ctx);
 int  gdsp_ctx_set_stream (gdsp_ctx* ctx, void* stream);
 int  gdsp_sync         (gdsp_ctx* ctx);
+/* page-locked host memory (device<->host copies from it run at full PCIe speed) */
+int  gdsp_malloc_host (size_t bytes, void** out);
+int  gdsp_free_host   (void* p);
 const char* gdsp_last_error (void);
 /* number of kernels this library has launched in the calling process (all contexts) */
 uint64_t gdsp_launch_count (void);
@@ -298,6 +301,22 @@ int  gdsp_pct_count   (gdsp_ctx* ctx, const gdsp_layout* lay, const double* sig,
  * in sig (*h_result_in_tmp = 0) or in tmp (= 1): the caller swaps its buffers. */
 int  gdsp_sort_genome (gdsp_ctx* ctx, const gdsp_layout* lay, double* sig,
                        double* tmp, uint64_t buffer_cells, int* h_result_in_tmp);
+
+/* ---- text output -----------------------------------------------------------
+ * The fprintf loop of report_intervals (genodsp.c:1606-1678) on the device: run r
+ * becomes the line  chrom TAB start[r]+add_start TAB end[r]+add_end [TAB "%.*f"
+ * of val[r]] NEWLINE  in d_text (device memory, capacity cap bytes); *h_bytes is
+ * the length of the text.  The value is printed exactly as glibc does (round
+ * half even on the binary value, "-0.000" for negative values that round to
+ * zero).  *h_unsupported = 1 (and nothing written) when some value is NaN,
+ * infinite or >= 2^63, the precision is above 17 or the name longer than 255:
+ * the caller then formats those runs itself.  GDSP_ERR_CAPACITY if cap is too
+ * small (*h_bytes = needed).  gdsp_format_runs_max_bytes bounds the text of n runs. */
+size_t gdsp_format_runs_max_bytes (uint64_t n, const char* chrom);
+int  gdsp_format_runs (gdsp_ctx* ctx, const uint32_t* d_start, const uint32_t* d_end,
+                       const double* d_val, uint64_t n, const char* chrom,
+                       uint32_t add_start, uint32_t add_end, int with_value, int precision,
+                       char* d_text, uint64_t cap, uint64_t* h_bytes, int* h_unsupported);
 
 /* ---- clump ---------------------------------------------------------------- */
 /* clump_search, clump.c:494-736 (above=1 clump, 0 anticlump); in place.

@@ -216,6 +216,38 @@ def test_text_roundtrip_is_printf_strtod(genome, orc):
         assert bad.size == 0, (name, inputs[name][bad[:5]], got[bad[:5]], want[bad[:5]])
 
 
+@pytest.mark.parametrize("precision", [0, 1, 3, 10, 17])
+def test_format_runs_matches_printf(genome, precision):
+    """gdsp_format_runs: device-side "%s\\t%u\\t%u\\t%.*f\\n" of run lists == C printf (Python's % uses the same
+    correctly rounded conversion): ties at the last printed digit, negatives rounding to zero, -0.0,
+    subnormals, integers up to 2^62, many magnitudes"""
+    from genodsp_b200.genome import format_runs
+    rng = np.random.default_rng(precision)
+    n = 20000
+    parts = [rng.normal(0, 3, n), rng.integers(-50, 90, n).astype(np.float64), (2 * rng.integers(0, 4096, n) + 1) / 2048.0,
+             rng.normal(0, 1e-9, n), rng.normal(0, 1e7, n), rng.normal(0, 1e-3, n), rng.integers(0, 2 ** 40, n) / 1024.0,
+             rng.integers(-1000, 1000, n) / 8.0]
+    val = np.choose(rng.integers(0, len(parts), n), parts)
+    special = np.array([0.0, -0.0, 0.5, 1.5, 2.5, -0.5, 0.05, 0.15, 0.25, 1e-300, -1e-300, 4.9e-324, 2.0 ** 62, -(2.0 ** 62),
+                        0.0005, -0.0004, 123456789.987654321, 9.999999999999999e15, 0.99999999999999989, 1e15 + 0.5])
+    val[:special.size] = special
+    start = np.sort(rng.integers(0, 2 ** 31, n)).astype(np.uint32)
+    end = (start + rng.integers(1, 1000, n)).astype(np.uint32)
+    for with_value in (True, False):
+        got = format_runs(genome, "chr12_random", start, end, val, precision, add_start=1, add_end=0, with_value=with_value)
+        assert got is not None
+        want = "".join("chr12_random\t%d\t%d%s\n" % (int(start[k]) + 1, int(end[k]), ("\t%.*f" % (precision, val[k])) if with_value else "")
+                       for k in range(n)).encode()
+        if got != want:
+            gl, wl = got.split(b"\n"), want.split(b"\n")
+            for k, (a, b) in enumerate(zip(gl, wl)):
+                assert a == b, (k, val[k], a, b)
+        assert got == want
+    # values the device declines: the caller must fall back
+    val[7] = np.inf
+    assert format_runs(genome, "c", start, end, val, precision) is None
+
+
 def test_smooth_to_host_matches_smooth(genome, orc):
     """the pipelined smooth + device->host delivery used by bench.py's e2e leg: same bits as smooth()"""
     import torch
