@@ -124,7 +124,7 @@ template <> __device__ __forceinline__ double warp_shfl_idx<double> (double v, i
 // CHAINED: the tile's starting value comes from the decoupled look-back (generic input);
 // otherwise it is read from tilePrefix (accumulate: known from the intervals themselves)
 template <typename T, int MODE, bool CHAINED>
-__global__ void __launch_bounds__(SCAN_THREADS)
+__global__ void __launch_bounds__(SCAN_THREADS, 4)
 k_scan_tiles (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
               const T* __restrict__ in, double* __restrict__ out, ScanStatus<T> st,
               const T* __restrict__ tilePrefix)

@@ -97,7 +97,7 @@ struct ClumpWork
 // ---------------------------------------------------------------------------
 // pass A
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(CL_THREADS)
+__global__ void __launch_bounds__(CL_THREADS, 3)
 k_clump_a (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
            const double* __restrict__ sig, double T, int above, ClumpWork wk,
            ScanStatus<double> stSum, ScanStatus<double> stMin)
@@ -191,7 +191,7 @@ k_clump_a (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, i
 // ---------------------------------------------------------------------------
 // pass B (backward: tile element e <-> cell t1-1-e)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(CL_THREADS)
+__global__ void __launch_bounds__(CL_THREADS, 3)
 k_clump_b (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg, uint64_t ntiles,
            const double* __restrict__ sig, double T, int above, uint32_t minLength, double relLength,
            ClumpWork wk, ScanStatus<double> stMax, ScanStatus<int> stOr)
@@ -301,7 +301,7 @@ k_clump_b (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, i
 // ---------------------------------------------------------------------------
 // pass C (forward)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(CL_THREADS)
+__global__ void __launch_bounds__(CL_THREADS, 3)
 k_clump_c (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
            double* __restrict__ sig, double oneVal, double zeroVal, ClumpWork wk, ScanStatus<int> stOr)
 	{

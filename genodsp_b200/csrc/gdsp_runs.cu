@@ -21,7 +21,7 @@
 
 __device__ __forceinline__ uint32_t run_pad (uint32_t j) { return j + (j >> 4); }
 
-__global__ void __launch_bounds__(RUN_THREADS)
+__global__ void __launch_bounds__(RUN_THREADS, 4)
 k_runs (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
         const double* __restrict__ sig, int collapse, int show,
         uint32_t* __restrict__ oStart, uint32_t* __restrict__ oEnd, double* __restrict__ oVal,
@@ -39,6 +39,59 @@ k_runs (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int 
 	const uint64_t t0 = sd.lo + tis * RUN_TILE;
 	const uint32_t n  = (uint32_t) ((sd.hi - t0 < RUN_TILE) ? (sd.hi - t0) : RUN_TILE);
 
+	const uint32_t c0 = threadIdx.x * RUN_PER;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t heads = 0, tails = 0;
+	double   myv[RUN_PER];                    // FULL tiles keep their cells in registers (no staging)
+	const bool fullTile = (n == RUN_TILE);
+
+	if (fullTile)
+		{
+		// 16 consecutive cells per thread straight from global memory (four 256-bit loads); the cell
+		// before and after the strip come from the neighbouring lanes, across warps through shared
+		// memory, across the tile edge from global memory
+		const double* p = sig + t0 + c0;
+		#pragma unroll
+		for (int q = 0; q < RUN_PER / 4; q++) ldg_stream4 (p + 4 * q, myv[4*q], myv[4*q+1], myv[4*q+2], myv[4*q+3]);
+		__shared__ double s_first[RUN_THREADS / 32], s_last[RUN_THREADS / 32];
+		__shared__ double s_edge[2];
+		if (lane == 0)  s_first[warp] = myv[0];
+		if (lane == 31) s_last[warp]  = myv[RUN_PER - 1];
+		const bool segFirstCell = (t0 == sd.lo), segLastCell = (t0 + RUN_TILE == sd.hi);
+		if (threadIdx.x == 0) s_edge[0] = segFirstCell ? 0.0 : sig[t0 - 1];
+		if (threadIdx.x == 1) s_edge[1] = segLastCell  ? 0.0 : sig[t0 + RUN_TILE];
+		__syncthreads ();
+		double before = shfl_up_f64 (myv[RUN_PER - 1], 1), after = shfl_down_f64 (myv[0], 1);
+		if (lane == 0)  before = (warp == 0) ? s_edge[0] : s_last[warp - 1];
+		if (lane == 31) after  = (warp == RUN_THREADS / 32 - 1) ? s_edge[1] : s_first[warp + 1];
+		const bool isFirst = segFirstCell && threadIdx.x == 0;                 // cell 0 of the chromosome piece
+		const bool isLast  = segLastCell  && threadIdx.x == RUN_THREADS - 1;   // its last cell
+
+		// pr: printable, ne: differs from the cell before
+		uint32_t pr = 0, ne = 0;
+		#pragma unroll
+		for (int k = 0; k < RUN_PER; k++)
+			{
+			const double pv = (k == 0) ? before : myv[k - 1];
+			if (show || myv[k] != 0) pr |= 1u << k;
+			if (myv[k] != pv)        ne |= 1u << k;
+			}
+		const uint32_t prBefore = (!isFirst && (show || before != 0)) ? 1u : 0u;
+		const uint32_t prAfter  = (!isLast  && (show || after  != 0)) ? 1u : 0u;
+		const uint32_t neAfter  = (after != myv[RUN_PER - 1]) ? 1u : 0u;
+		const uint32_t prPrev = ((pr << 1) | prBefore) & 0xffffu;              // printable(c-1), 0 at the piece start
+		const uint32_t prNext = (pr >> 1) | (prAfter << (RUN_PER - 1));        // printable(c+1), 0 at the piece end
+		const uint32_t neNext = (ne >> 1) | (neAfter << (RUN_PER - 1));        // v[c+1] != v[c]
+		if (collapse)
+			{
+			heads = pr & (~prPrev | ne | (isFirst ? 1u : 0u));
+			tails = pr & (~prNext | neNext | (isLast ? (1u << (RUN_PER - 1)) : 0u));
+			}
+		else heads = tails = pr;
+		heads &= 0xffffu;  tails &= 0xffffu;
+		}
+	else
+		{
 	// staged cell j <-> sig[t0 - 1 + j], j in [0, n+2); cells outside [lo,hi) are never compared
 	for (uint32_t j = threadIdx.x; j < n + 2; j += RUN_THREADS)
 		{
@@ -49,8 +102,6 @@ k_runs (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int 
 		}
 	__syncthreads ();
 
-	const uint32_t c0 = threadIdx.x * RUN_PER;
-	uint32_t heads = 0, tails = 0;
 	if (c0 < n)
 		{
 		double prev = s_v[run_pad (c0)];           // cell c0-1
@@ -75,9 +126,9 @@ k_runs (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int 
 			prev = cur;  cur = next;
 			}
 		}
+		}
 
 	// block exclusive scan of head counts
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	unsigned int cnt = __popc (heads), inc = cnt;
 	#pragma unroll
 	for (int d = 1; d < 32; d <<= 1)
@@ -111,16 +162,26 @@ k_runs (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int 
 	unsigned long long idx = s_excl + warpExcl + (inc - cnt);      // slot of this thread's first head
 	if (c0 < n && (heads | tails))
 		{
-		#pragma unroll
-		for (int k = 0; k < RUN_PER; k++)
+		// walk the set bits in cell order; a head and a tail on the same cell: head first
+		uint32_t both = heads | tails;
+		while (both)
 			{
+			const int k = __ffs (both) - 1;
+			both &= both - 1;
 			const uint32_t c = c0 + k;
+			const uint32_t coord = sd.pos0 + (uint32_t) (t0 + c - sd.lo);
 			if (heads & (1u << k))
 				{
 				if (idx < cap)
 					{
-					double v = s_v[run_pad (c + 1)];
-					const uint32_t coord = sd.pos0 + (uint32_t) (t0 + c - sd.lo);
+					double v;
+					if (fullTile)
+						{
+						v = myv[0];
+						#pragma unroll
+						for (int q = 1; q < RUN_PER; q++) if (q == k) v = myv[q];
+						}
+					else v = s_v[run_pad (c + 1)];
 					// the reference's state machine starts with val=+0.0 (genodsp.c:1590): a collapsed
 					// run of zeros that begins at base 0 reports that +0.0, not v[0]
 					if (coord == 0 && collapse && v == 0) v = 0.0;
@@ -129,11 +190,8 @@ k_runs (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int 
 					}
 				idx++;
 				}
-			if (tails & (1u << k))
-				{
-				// the run this tail closes is the most recent head: slot idx-1
-				if (idx - 1 < cap) oEnd[idx - 1] = sd.pos0 + (uint32_t) (t0 + c - sd.lo) + 1;
-				}
+			// the run a tail closes is the most recent head: slot idx-1
+			if ((tails & (1u << k)) && idx - 1 < cap) oEnd[idx - 1] = coord + 1;
 			}
 		}
 	}
@@ -145,6 +203,7 @@ extern "C" int gdsp_runs (gdsp_ctx* c, const gdsp_layout* L_, const double* sig,
 	gdsp_layout* L = (gdsp_layout*) L_;
 	GDSP_REQUIRE (c && L && sig && h_n_runs, "gdsp_runs: NULL argument");
 	GDSP_REQUIRE (cap == 0 || (d_start && d_end && d_val), "gdsp_runs: NULL output arrays");
+	GDSP_REQUIRE_ALIGNED (sig, "gdsp_runs");
 	TileMap tm;
 	GDSP_TRY (gdsp_layout_tilemap (L, RUN_TILE, &tm));
 	void* ws;  void* wseg;

@@ -72,7 +72,7 @@ __device__ __forceinline__ void scan_rec_load (const ScanRec* p, unsigned long l
 __device__ __forceinline__ unsigned long long shfl_down_u64 (unsigned long long v, int d)
 	{ return __shfl_down_sync (0xffffffffu, v, d); }
 
-#define SCAN_SUBW 4        // sub-windows of 32 tiles inspected per look-back step
+#define SCAN_SUBW 1        // sub-windows of 32 tiles inspected per look-back step
 
 // Warp-cooperative look-back: called by ALL 32 lanes of ONE warp of the block
 // (every lane passes the same arguments).  `myAgg` is this tile's aggregate; the

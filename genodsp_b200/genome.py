@@ -494,6 +494,16 @@ class Genome:
         self.clump(average, length, relative_length, False, one, zero)
 
     # ------------------------------------------------------------------ output
+    def runs_device(self, bufs, collapse=True, show_uncovered=0):
+        """gdsp_runs into caller-provided device tensors (start i32, end i32, value f64 of equal length):
+        -> (number of runs, per-segment first-run offsets); nothing is copied to the host"""
+        s, e, v = bufs
+        n = C.c_uint64()
+        first = (C.c_uint64 * (self.nseg + 1))()
+        check(self.lib.gdsp_runs(self.ctx, self.layout, self._p(self.sig), int(collapse), int(show_uncovered),
+                                 self._p(s), self._p(e), self._p(v), int(s.numel()), C.byref(n), first))
+        return int(n.value), list(first)
+
     def runs(self, collapse=True, show_uncovered=0, cap=None):
         """report_intervals run detection (genodsp.c:1589-1678) -> {chrom: (start, end, val)} numpy
         arrays, chromosome coordinates, 0-based half-open."""

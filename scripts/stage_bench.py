@@ -97,7 +97,22 @@ def main():
     if on("runs"):
         def bin_setup():
             reset(); g.binarize(9.0)
-        rec("runs_binarized", timed(lambda: g.runs(cap=max(1024, N // 8)), bin_setup), 8)
+        # kernel only: results stay on the device (the CLI formats them there, gdsp_format_runs)
+        capr = max(1024, N // 4)
+        bufs = (torch.empty(capr, dtype=torch.int32, device=g.device), torch.empty(capr, dtype=torch.int32, device=g.device),
+                torch.empty(capr, dtype=torch.float64, device=g.device))
+        nr = [0]
+        def do_runs():
+            nr[0] = g.runs_device(bufs)[0]
+        ms = timed(do_runs, bin_setup)
+        rec("runs_binarized", ms, 8, 16 * nr[0])
+        out["runs_binarized"]["runs"] = nr[0]
+        def few_setup():
+            reset(); g.binarize(14.0)
+        ms = timed(do_runs, few_setup)
+        rec("runs_sparse", ms, 8, 16 * nr[0])
+        out["runs_sparse"]["runs"] = nr[0]
+        del bufs
     # whole pipelines: wall time of the chain, with per-operator CUDA-event splits
     def chain(name, ops):
         evs = None
