@@ -47,34 +47,68 @@ k_morph_pack (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base
 	const bool endsChrom = ((uint64_t) sd.pos0 + (sd.hi - sd.lo) == (uint64_t) sd.chromLen);
 	const bool complement = (kind == GDSP_MORPH_OPEN || kind == GDSP_MORPH_ERODE);
 
+	// thread t owns word t of the tile: 32 consecutive cells (256 bytes) read with 256-bit loads, the
+	// marker bits assembled in a register -- no warp votes, and the word store is coalesced
 	long long first = -1, last = -1;
-	// warp `warp` packs words warp, warp+8, ... of the tile
-	// every warp packs MO_WORDS/8 = 32 words; the 32 loads of a lane are independent
-	#pragma unroll 8
-	for (uint32_t w = warp; w < MO_WORDS; w += MO_THREADS / 32)
+	const uint32_t c0 = threadIdx.x * 32;
+	const uint32_t nRound = (n + 31u) & ~31u;
+	uint32_t word = 0;
+	if (c0 + 32 <= n)
 		{
-		const uint32_t c = w * 32 + lane;
-		bool mark = false;
-		if (c < n)
+		const double* p = sig + t0 + c0;
+		#pragma unroll
+		for (int h = 0; h < 2; h++)
 			{
-			const double v = __ldg (sig + t0 + c);
-			if      (kind == GDSP_MORPH_CLOSE)  mark = !(v <= T);
-			else if (kind == GDSP_MORPH_DILATE) mark = (sd.pos0 == 0 && t0 + c == sd.lo) ? (v > T) : !(v <= T);
-			else                                mark = !(v > T);
-			}
-		else if (complement && endsChrom && c < ((n + 31u) & ~31u))
-			mark = true;                 // cells past the chromosome end bound every run
-		const uint32_t word = __ballot_sync (0xffffffffu, mark);
-		if (w * 32 < ((n + 31u) & ~31u))
-			{
-			if (lane == 0) wk.words[(t0 >> 5) + w] = word;
-			if (word != 0)
+			double v[16];
+			#pragma unroll
+			for (int q = 0; q < 4; q++) ldg_stream4 (p + 16 * h + 4 * q, v[4*q], v[4*q+1], v[4*q+2], v[4*q+3]);
+			#pragma unroll
+			for (int k = 0; k < 16; k++)
 				{
-				const long long c0 = (long long) sd.pos0 + (long long) (t0 - sd.lo) + (long long) w * 32;
-				if (first < 0) first = c0 + (__ffs (word) - 1);
-				last = c0 + (31 - __clz (word));
+				const bool mark = complement ? !(v[k] > T) : !(v[k] <= T);
+				word |= (mark ? 1u : 0u) << (16 * h + k);
 				}
 			}
+		if (kind == GDSP_MORPH_DILATE && sd.pos0 == 0 && t0 == sd.lo && threadIdx.x == 0)
+			{
+			const double v0 = __ldg (sig + t0);                      // the reference tests the first cell with v > T
+			word = (word & ~1u) | ((v0 > T) ? 1u : 0u);
+			}
+		}
+	else if (c0 < nRound)
+		{
+		for (uint32_t k = 0; k < 32; k++)
+			{
+			const uint32_t c = c0 + k;
+			bool mark = false;
+			if (c < n)
+				{
+				const double v = __ldg (sig + t0 + c);
+				if      (kind == GDSP_MORPH_CLOSE)  mark = !(v <= T);
+				else if (kind == GDSP_MORPH_DILATE) mark = (sd.pos0 == 0 && t0 + c == sd.lo) ? (v > T) : !(v <= T);
+				else                                mark = !(v > T);
+				}
+			else if (complement && endsChrom) mark = true;        // cells past the chromosome end bound every run
+			word |= (mark ? 1u : 0u) << k;
+			}
+		}
+	if (c0 < nRound)
+		{
+		wk.words[(t0 >> 5) + threadIdx.x] = word;
+		if (word != 0)
+			{
+			const long long cc = (long long) sd.pos0 + (long long) (t0 - sd.lo) + (long long) c0;
+			first = cc + (__ffs (word) - 1);
+			last  = cc + (31 - __clz (word));
+			}
+		}
+	// first marker = smallest, last = largest over the warp
+	#pragma unroll
+	for (int d = 16; d > 0; d >>= 1)
+		{
+		const long long f2 = __shfl_xor_sync (0xffffffffu, first, d), l2 = __shfl_xor_sync (0xffffffffu, last, d);
+		if (f2 >= 0 && (first < 0 || f2 < first)) first = f2;
+		if (l2 > last) last = l2;
 		}
 	if (lane == 0) { s_first[warp] = first;  s_last[warp] = last; }
 	__syncthreads ();
@@ -175,47 +209,60 @@ k_morph_apply (const SegDev* __restrict__ segs, const uint64_t* __restrict__ bas
 	const long long carryPrev = s_carry[0], carryNext = s_carry[1];
 	const long long chromEnd  = (long long) sd.chromLen;
 
-	for (uint32_t c = threadIdx.x; c < n; c += MO_THREADS)
+	// thread t decides the 32 cells of word t: the nearest markers outside the word are looked up once,
+	// the ones inside come from clz/ffs on the word; 256 bytes of results leave as 256-bit stores
+	const uint32_t w = threadIdx.x;
+	const uint32_t c0 = w * 32;
+	if (c0 >= n) return;
+	const uint32_t word = s_word[w];
+	long long prevOut, nextOut;                       // nearest marker before / after this word (chromosome coordinates)
+	{
+	const int pw = (w > 0) ? s_prevW[w - 1] : -1;
+	prevOut = (pw >= 0) ? coord0 + (long long) (pw * 32 + 31 - __clz (s_word[pw])) : carryPrev;
+	const int nwd = (w + 1 < MO_WORDS) ? s_nextW[w + 1] : -1;
+	nextOut = (nwd >= 0) ? coord0 + (long long) (nwd * 32 + __ffs (s_word[nwd]) - 1) : carryNext;
+	}
+	const long long cw = coord0 + c0;                 // coordinate of the word's first cell
+	double* o = sig + t0 + c0;
+	#pragma unroll
+	for (int g = 0; g < 8; g++)
 		{
-		const uint32_t w = c >> 5;                    // uniform across the warp
-		const uint32_t word = s_word[w];
-		const long long cp = coord0 + c;
-
-		// nearest marker at or before c  /  at or after c   (chromosome coordinates, -1 = none in reach)
-		long long prevM, nextM;
-		uint32_t m = word & (0xffffffffu >> (31 - lane));
-		if (m) prevM = coord0 + (long long) (w * 32 + 31 - __clz (m));
-		else
+		double y[4];
+		#pragma unroll
+		for (int q = 0; q < 4; q++)
 			{
-			int pw = (w > 0) ? s_prevW[w - 1] : -1;
-			prevM = (pw >= 0) ? coord0 + (long long) (pw * 32 + 31 - __clz (s_word[pw])) : carryPrev;
-			}
-		m = word & (0xffffffffu << lane);
-		if (m) nextM = coord0 + (long long) (w * 32 + __ffs (m) - 1);
-		else
-			{
-			int nwd = (w + 1 < MO_WORDS) ? s_nextW[w + 1] : -1;
-			nextM = (nwd >= 0) ? coord0 + (long long) (nwd * 32 + __ffs (s_word[nwd]) - 1) : carryNext;
-			}
-
-		bool one;
-		if (kind == GDSP_MORPH_DILATE)
-			one = (prevM >= 0 && cp - prevM <= right) || (nextM >= 0 && nextM - cp <= left);
-		else if (kind == GDSP_MORPH_CLOSE)
-			one = (prevM == cp) || (prevM >= 0 && nextM >= 0 && !((double) (nextM - prevM - 1) > L));
-		else
-			{
-			// markers are the cells outside the set; a marker at cp means cp itself is outside
-			if (prevM == cp) one = false;
+			const int bit = 4 * g + q;
+			const long long cp = cw + bit;
+			uint32_t m = word & (0xffffffffu >> (31 - bit));
+			const long long prevM = m ? cw + (31 - __clz (m)) : prevOut;
+			m = word & (0xffffffffu << bit);
+			const long long nextM = m ? cw + (__ffs (m) - 1) : nextOut;
+			bool one;
+			if (kind == GDSP_MORPH_DILATE)
+				one = (prevM >= 0 && cp - prevM <= right) || (nextM >= 0 && nextM - cp <= left);
+			else if (kind == GDSP_MORPH_CLOSE)
+				one = (prevM == cp) || (prevM >= 0 && nextM >= 0 && !((double) (nextM - prevM - 1) > L));
 			else
 				{
-				const long long s = prevM + 1;                           // prevM == -1 -> run starts at coordinate 0
-				const long long e = (nextM >= 0) ? nextM : chromEnd;
-				if (kind == GDSP_MORPH_OPEN) one = ((double) (e - s) > L);
-				else                         one = (cp >= s + right) && (cp < e - left);
+				// markers are the cells outside the set; a marker at cp means cp itself is outside
+				if (prevM == cp) one = false;
+				else
+					{
+					const long long rs = prevM + 1;                          // prevM == -1 -> run starts at coordinate 0
+					const long long re = (nextM >= 0) ? nextM : chromEnd;
+					if (kind == GDSP_MORPH_OPEN) one = ((double) (re - rs) > L);
+					else                         one = (cp >= rs + right) && (cp < re - left);
+					}
 				}
+			y[q] = one ? oneVal : zeroVal;
 			}
-		sig[t0 + c] = one ? oneVal : zeroVal;
+		const uint32_t c = c0 + 4 * g;
+		if (c + 4 <= n) stg_stream4 (o + 4 * g, y[0], y[1], y[2], y[3]);
+		else
+			{
+			#pragma unroll
+			for (int q = 0; q < 4; q++) if (c + q < n) o[4 * g + q] = y[q];
+			}
 		}
 	}
 
@@ -233,6 +280,7 @@ extern "C" int gdsp_morphology (gdsp_ctx* c, const gdsp_layout* L_, double* sig,
 	gdsp_layout* L = (gdsp_layout*) L_;
 	GDSP_REQUIRE (c && L && sig && work, "gdsp_morphology: NULL argument");
 	GDSP_REQUIRE (kind >= GDSP_MORPH_CLOSE && kind <= GDSP_MORPH_ERODE, "gdsp_morphology: bad kind %d", kind);
+	GDSP_REQUIRE_ALIGNED (sig, "gdsp_morphology");
 	for (int s = 0; s < L->nseg; s++)
 		GDSP_REQUIRE (L->h[s].pos0 == 0 && L->h[s].hi - L->h[s].lo == L->h[s].chrom_len,
 		              "gdsp_morphology: slab-sharded chromosomes need the carry variant (not in this build)");
