@@ -131,18 +131,41 @@ k_block_sum (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base,
 	// cell index of chromosome coordinate c:  sd.lo + (c - pos0)   (may precede sd.lo: halo / dlo)
 	const int64_t  g0     = (int64_t) sd.lo + ((int64_t) c0 - (int64_t) sd.pos0);
 
-	for (uint32_t j = threadIdx.x; j < count; j += blockDim.x)
+	// (row, offset) of staged cell j = tid + k*BS_THREADS, advanced without dividing per cell
+	const uint32_t dq = BS_THREADS / W, dr = BS_THREADS % W;
+	const bool readable = (g0 >= (int64_t) sd.dlo) && (g0 + (int64_t) count <= (int64_t) sd.dhi);
+	const bool owned    = (g0 >= (int64_t) sd.lo)  && (g0 + (int64_t) count <= (int64_t) sd.hi);
+	{
+	uint32_t r = threadIdx.x / W, off = threadIdx.x - r * W;
+	const double* src = sig + g0;
+	// four loads in flight per thread (a loop with one load per trip leaves the memory system idle)
+	for (uint32_t j = threadIdx.x; j < count; j += 4 * BS_THREADS)
 		{
-		int64_t g = g0 + (int64_t) j;
-		double v = 0.0;
-		if (g >= (int64_t) sd.dlo && g < (int64_t) sd.dhi) v = sig[g];
-		uint32_t r = j / W;
-		sm[r * rowS + (j - r * W)] = v;
+		double v[4];
+		#pragma unroll
+		for (int u = 0; u < 4; u++)
+			{
+			const uint32_t ju = j + u * BS_THREADS;
+			if (readable) v[u] = (ju < count) ? __ldg (src + ju) : 0.0;
+			else
+				{
+				const int64_t g = g0 + (int64_t) ju;
+				v[u] = (ju < count && g >= (int64_t) sd.dlo && g < (int64_t) sd.dhi) ? sig[g] : 0.0;
+				}
+			}
+		#pragma unroll
+		for (int u = 0; u < 4; u++)
+			{
+			if (j + u * BS_THREADS < count) sm[r * rowS + off] = v[u];
+			off += dr;  r += dq;
+			if (off >= W) { off -= W;  r++; }
+			}
 		}
+	}
 	__syncthreads ();
 
 	const uint32_t nblk = (count + W - 1) / W;
-	for (uint32_t b = threadIdx.x; b < nblk; b += blockDim.x)
+	for (uint32_t b = threadIdx.x; b < nblk; b += BS_THREADS)
 		{
 		uint32_t bl = (b * W + W <= count) ? W : count - b * W;
 		const double* row = sm + b * rowS;
@@ -153,13 +176,22 @@ k_block_sum (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base,
 	__syncthreads ();
 
 	// write back only cells this piece owns
-	for (uint32_t j = threadIdx.x; j < count; j += blockDim.x)
+	{
+	uint32_t r = threadIdx.x / W, off = threadIdx.x - r * W;
+	double* dst = sig + g0;
+	for (uint32_t j = threadIdx.x; j < count; j += BS_THREADS)
 		{
-		int64_t g = g0 + (int64_t) j;
-		if (g < (int64_t) sd.lo || g >= (int64_t) sd.hi) continue;
-		uint32_t r = j / W;
-		sig[g] = (j == r * W) ? sm[r * rowS] : zeroVal;
+		const double y = (off == 0) ? sm[r * rowS] : zeroVal;
+		if (owned) dst[j] = y;
+		else
+			{
+			const int64_t g = g0 + (int64_t) j;
+			if (g >= (int64_t) sd.lo && g < (int64_t) sd.hi) sig[g] = y;
+			}
+		off += dr;  r += dq;
+		if (off >= W) { off -= W;  r++; }
 		}
+	}
 	(void) len;
 	}
 
