@@ -90,14 +90,36 @@ k_sort_orand (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base
 		}
 	}
 
-// copy every cell that is not +0.0 to out[] (any order; they get sorted next)
+// copy every cell that is not +0.0 to out[] (any order; they get sorted next).
+// The survivors are collected in a shared-memory buffer and flushed with ONE global atomic per
+// ~1000 cells: with a global atomic per warp vote (the first version) 15 M same-address atomics
+// made this 24.7 GB read take 22 ms.
+#define CNZ_CAP 5120          // buffer entries; a tile adds at most SORT_TILE = 4096
 __global__ void __launch_bounds__(256)
 k_sort_compact_nonzero (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg, uint64_t ntiles,
                         const double* __restrict__ in, double* __restrict__ out, unsigned long long* __restrict__ counter)
 	{
+	__shared__ double s_buf[CNZ_CAP];
+	__shared__ unsigned int s_cnt;
+	__shared__ unsigned long long s_base;
 	const int lane = threadIdx.x & 31;
-	for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x)
+	if (threadIdx.x == 0) s_cnt = 0;
+	__syncthreads ();
+	for (uint64_t t = blockIdx.x; ; t += gridDim.x)
 		{
+		// flush when the next tile might not fit (or at the end)
+		const bool more = (t < ntiles);
+		if (!more || s_cnt + SORT_TILE > CNZ_CAP)
+			{
+			const unsigned int cnt = s_cnt;
+			if (threadIdx.x == 0 && cnt) s_base = atomicAdd (counter, (unsigned long long) cnt);
+			__syncthreads ();
+			for (unsigned int i = threadIdx.x; i < cnt; i += 256) out[s_base + i] = s_buf[i];
+			__syncthreads ();
+			if (threadIdx.x == 0) s_cnt = 0;
+			__syncthreads ();
+			}
+		if (!more) break;
 		int seg;  uint64_t tis;
 		tile_to_seg (base, nseg, t, seg, tis);
 		const SegDev sd = segs[seg];
@@ -118,12 +140,13 @@ k_sort_compact_nonzero (const SegDev* __restrict__ segs, const uint64_t* __restr
 				{
 				const unsigned m = __ballot_sync (0xffffffffu, keep[u]);
 				if (m == 0) continue;
-				unsigned long long b0 = 0;
-				if (lane == __ffs (m) - 1) b0 = atomicAdd (counter, (unsigned long long) __popc (m));
+				unsigned int b0 = 0;
+				if (lane == __ffs (m) - 1) b0 = atomicAdd (&s_cnt, (unsigned int) __popc (m));
 				b0 = __shfl_sync (0xffffffffu, b0, __ffs (m) - 1);
-				if (keep[u]) out[b0 + __popc (m & ((1u << lane) - 1u))] = v[u];
+				if (keep[u]) s_buf[b0 + __popc (m & ((1u << lane) - 1u))] = v[u];
 				}
 			}
+		__syncthreads ();
 		}
 	}
 

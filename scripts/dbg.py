@@ -1,13 +1,15 @@
-# scratch: phase timing of the CLI on cfg1 and hg38/16
-import os, sys, subprocess, tempfile
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-import cli_bench as cb, bench
-for name, chroms, cmd in [("cfg1", [("chr1", 10000000)], ["--chromosomes=g.chroms", "--novalue", "=", "sum", "--window=101", "=", "localmax", "--neighborhood=11"]),
-                          ("div16", bench.scaled_genome(16), ["--chromosomes=g.chroms", "--novalue", "--precision=3", "=", "smooth", "--window=101"])]:
-    with tempfile.TemporaryDirectory() as d:
-        reads = cb.write_case(d, chroms, 1)
-        env = dict(os.environ, GENODSP_TIMING="1")
-        for rep in range(2):
-            with open(reads, "rb") as fin:
-                p = subprocess.run([cb.OURS] + cmd, stdin=fin, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, cwd=d, env=env)
-            print(name, rep, p.stderr.decode().replace("\n", " | "), flush=True)
+# scratch: pipe5 up to localmax, then percentile(destructive) once -- for an ncu launch list of the post-state path
+import os, sys
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import torch, bench
+from genodsp_b200.genome import Genome
+chroms = bench.scaled_genome(1)
+g = Genome(chroms)
+order = sorted(range(len(chroms)), key=lambda i: -chroms[i][1])
+seg, st, en = bench.synth_intervals(torch, g.device, [chroms[i] for i in order])
+g.accumulate(seg, st, en, host=False); g.smooth(101); g.localmax(11)
+torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record(); out = g.percentile(99.0); b.record(); torch.cuda.synchronize()
+print(out, a.elapsed_time(b), "ms", flush=True)
+nz = int((g.sig != 0).sum().item()); print("nonzero cells", nz, "of", g.cells)
