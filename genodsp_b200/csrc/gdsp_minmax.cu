@@ -16,8 +16,6 @@
 // cells in registers; strip aggregates are combined with warp shuffles.
 #include "gdsp_common.cuh"
 
-#define MM_THREADS 512
-#define MM_WARPS   (MM_THREADS / 32)
 
 // fmax/fmin ignore a NaN operand, which is what the reference's `if (v[j] > best)` scans do with a NaN
 // neighbour; but they compile to ~8 instructions per call.  The tiled kernels therefore replace NaN by
@@ -34,13 +32,14 @@ template <int LOGE> __device__ __forceinline__ uint32_t mm_pad (uint32_t j) { re
 
 // MODE 0: out = window extremum (bestmax/bestmin)
 // MODE 1: out = in unless the window extremum beats it, then fill (localmax/localmin)
-template <int LOGE, bool WANT_MAX, int MODE>
+template <int LOGE, int MM_THREADS, bool WANT_MAX, int MODE>
 __global__ void __launch_bounds__(MM_THREADS)
 k_extrema (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
            const double* __restrict__ in, double* __restrict__ out,
            uint32_t reachL, uint32_t Wn, uint32_t tileOut, double fill)
 	{
 	constexpr int      E    = 1 << LOGE;
+	constexpr int      MM_WARPS = MM_THREADS / 32;
 	constexpr uint32_t SCAP = (uint32_t) E * MM_THREADS;
 	constexpr uint32_t PADN = SCAP + (SCAP >> LOGE) + 2;
 	extern __shared__ double sm[];
@@ -283,7 +282,7 @@ k_extrema_wide (const SegDev* __restrict__ segs, const uint64_t* __restrict__ ba
 		}
 	}
 
-template <int LOGE, bool WANT_MAX, int MODE>
+template <int LOGE, int MM_THREADS, bool WANT_MAX, int MODE>
 static int launch_extrema_t (gdsp_ctx* c, gdsp_layout* L, const double* in, double* out,
                              uint32_t reachL, uint32_t Wn, double fill)
 	{
@@ -294,8 +293,8 @@ static int launch_extrema_t (gdsp_ctx* c, gdsp_layout* L, const double* in, doub
 	size_t smem = 2 * (size_t) PADN * sizeof (double);
 	TileMap tm;
 	GDSP_TRY (gdsp_layout_tilemap (L, tileOut, &tm));
-	GDSP_CUDA (cudaFuncSetAttribute (k_extrema<LOGE, WANT_MAX, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-	k_extrema<LOGE, WANT_MAX, MODE><<<(unsigned) tm.ntiles, MM_THREADS, smem, c->stream>>>
+	GDSP_CUDA (cudaFuncSetAttribute (k_extrema<LOGE, MM_THREADS, WANT_MAX, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	k_extrema<LOGE, MM_THREADS, WANT_MAX, MODE><<<(unsigned) tm.ntiles, MM_THREADS, smem, c->stream>>>
 		(L->d, tm.d_base, L->nseg, in, out, reachL, Wn, tileOut, fill);
 	GDSP_KERNEL_CHECK ();
 	return GDSP_OK;
@@ -315,8 +314,8 @@ static int launch_extrema (gdsp_ctx* c, gdsp_layout* L, const double* in, double
 		if (Wn < 32) return launch_extrema_small_t<4, WANT_MAX, MODE> (c, L, in, out, reachL, Wn, fill);
 		return launch_extrema_small_t<5, WANT_MAX, MODE> (c, L, in, out, reachL, Wn, fill);
 		}
-	if (Wn64 <= 2049) return launch_extrema_t<3, WANT_MAX, MODE> (c, L, in, out, reachL, (uint32_t) Wn64, fill);
-	if (Wn64 <= 6145) return launch_extrema_t<4, WANT_MAX, MODE> (c, L, in, out, reachL, (uint32_t) Wn64, fill);
+	if (Wn64 <= 2049) return launch_extrema_t<4, 256, WANT_MAX, MODE> (c, L, in, out, reachL, (uint32_t) Wn64, fill);
+	if (Wn64 <= 6145) return launch_extrema_t<4, 512, WANT_MAX, MODE> (c, L, in, out, reachL, (uint32_t) Wn64, fill);
 	TileMap tm;
 	GDSP_TRY (gdsp_layout_tilemap (L, 256, &tm));
 	k_extrema_wide<WANT_MAX, MODE><<<(unsigned) tm.ntiles, 256, 0, c->stream>>> (L->d, tm.d_base, L->nseg, in, out, reachL, reachR, fill);
