@@ -18,6 +18,8 @@
 //                     neighbouring tiles' summaries.
 // Algorithmic bytes: 16 B/bp (+ 0.16 B/bp of bit traffic).
 #include "gdsp_common.cuh"
+#include <algorithm>
+#include <vector>
 
 #define MO_TILE    8192
 #define MO_WORDS   (MO_TILE / 32)        // 256
@@ -125,6 +127,37 @@ k_morph_pack (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base
 		}
 	}
 
+// Slab pieces: marker bits of the readable halo cells [dlo,lo) and [hi,dhi) of every piece, so that
+// the search for the nearest marker can continue past the piece into its neighbour's data.
+// blockIdx.x = 2*segment + side.  Whole halo words are stored; the word shared with the owned tail
+// (hi not a multiple of 32) is OR-ed.
+__global__ void __launch_bounds__(256)
+k_morph_pack_halo (const SegDev* __restrict__ segs, const double* __restrict__ sig, int kind, double T, MorphWork wk)
+	{
+	const SegDev sd = segs[blockIdx.x >> 1];
+	const bool right = (blockIdx.x & 1) != 0;
+	const uint64_t a = right ? sd.hi : sd.dlo, b = right ? sd.dhi : sd.lo;       // halo cells [a,b)
+	if (a >= b) return;
+	const bool complement = (kind == GDSP_MORPH_OPEN || kind == GDSP_MORPH_ERODE);
+	const int lane = threadIdx.x & 31;
+	const uint64_t w0 = a >> 5, w1 = (b + 31) >> 5;
+	for (uint64_t w = w0 + (threadIdx.x >> 5); w < w1; w += 256 / 32)
+		{
+		const uint64_t cell = w * 32 + lane;
+		bool mark = false;
+		if (cell >= a && cell < b)
+			{
+			const double v = __ldg (sig + cell);
+			mark = complement ? !(v > T) : !(v <= T);
+			}
+		const uint32_t word = __ballot_sync (0xffffffffu, mark);
+		if (lane == 0)
+			{
+			if (word) atomicOr (wk.words + w, word);             // the array was cleared; a word may hold owned cells too
+			}
+		}
+	}
+
 __global__ void __launch_bounds__(MO_THREADS)
 k_morph_apply (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
                double* __restrict__ sig, int kind, double L, long long left, long long right,
@@ -190,6 +223,24 @@ k_morph_apply (const SegDev* __restrict__ segs, const uint64_t* __restrict__ bas
 			unsigned m = __ballot_sync (0xffffffffu, v >= 0);
 			if (m) found = __shfl_sync (0xffffffffu, v, __ffs (m) - 1);
 			}
+		// ran out of tiles of this piece: the piece's left halo (slab layouts) holds the neighbour's cells
+		if (found < 0 && tis < (uint64_t) maxTileSearch && sd.dlo < sd.lo)
+			{
+			const long long wTop = (long long) (sd.lo >> 5) - 1, wBot = (long long) (sd.dlo >> 5);
+			for (long long wb = wTop; wb >= wBot && found < 0; wb -= 32)
+				{
+				const long long wi = wb - lane;
+				const uint32_t word = (wi >= wBot) ? wk.words[wi] : 0u;
+				const unsigned m = __ballot_sync (0xffffffffu, word != 0u);
+				if (m)
+					{
+					const int src = __ffs (m) - 1;
+					const uint32_t wsel = __shfl_sync (0xffffffffu, word, src);
+					const long long cell = (wb - src) * 32 + (31 - __clz (wsel));
+					found = (long long) sd.pos0 - ((long long) sd.lo - cell);
+					}
+				}
+			}
 		if (lane == 0) s_carry[0] = found;
 		}
 	else if (warp == 1)
@@ -202,6 +253,23 @@ k_morph_apply (const SegDev* __restrict__ segs, const uint64_t* __restrict__ bas
 			long long v = (k <= after && k <= maxTileSearch) ? wk.tileFirst[blockIdx.x + k] : -1;
 			unsigned m = __ballot_sync (0xffffffffu, v >= 0);
 			if (m) found = __shfl_sync (0xffffffffu, v, __ffs (m) - 1);
+			}
+		if (found < 0 && after < (uint64_t) maxTileSearch && sd.dhi > sd.hi)
+			{
+			const long long wBot = (long long) ((sd.hi + 31) >> 5), wTop = (long long) ((sd.dhi + 31) >> 5);   // [wBot, wTop)
+			for (long long wb = wBot; wb < wTop && found < 0; wb += 32)
+				{
+				const long long wi = wb + lane;
+				const uint32_t word = (wi < wTop) ? wk.words[wi] : 0u;
+				const unsigned m = __ballot_sync (0xffffffffu, word != 0u);
+				if (m)
+					{
+					const int src = __ffs (m) - 1;
+					const uint32_t wsel = __shfl_sync (0xffffffffu, word, src);
+					const long long cell = (wb + src) * 32 + (__ffs (wsel) - 1);
+					found = (long long) sd.pos0 + (cell - (long long) sd.lo);
+					}
+				}
 			}
 		if (lane == 0) s_carry[1] = found;
 		}
@@ -281,9 +349,33 @@ extern "C" int gdsp_morphology (gdsp_ctx* c, const gdsp_layout* L_, double* sig,
 	GDSP_REQUIRE (c && L && sig && work, "gdsp_morphology: NULL argument");
 	GDSP_REQUIRE (kind >= GDSP_MORPH_CLOSE && kind <= GDSP_MORPH_ERODE, "gdsp_morphology: bad kind %d", kind);
 	GDSP_REQUIRE_ALIGNED (sig, "gdsp_morphology");
+	// how far can a neighbouring marker matter?  (cells)
+	double reach;
+	if      (kind == GDSP_MORPH_DILATE || kind == GDSP_MORPH_ERODE) reach = (double) ((left > right) ? left : right) + 1;
+	else    reach = length + 2;
+	// slab pieces: the readable halo on a side where the chromosome continues must cover that reach
+	bool anyHalo = false;
 	for (int s = 0; s < L->nseg; s++)
-		GDSP_REQUIRE (L->h[s].pos0 == 0 && L->h[s].hi - L->h[s].lo == L->h[s].chrom_len,
-		              "gdsp_morphology: slab-sharded chromosomes need the carry variant (not in this build)");
+		{
+		const gdsp_seg& g = L->h[s];
+		const bool startsChrom = (g.pos0 == 0), endsChrom = ((uint64_t) g.pos0 + (g.hi - g.lo) == (uint64_t) g.chrom_len);
+		GDSP_REQUIRE (startsChrom || (double) (g.lo - g.dlo) >= reach || (uint64_t) (g.lo - g.dlo) == (uint64_t) g.pos0,
+		              "gdsp_morphology: piece %d needs a left halo of %.0f cells (has %llu)", s, reach, (unsigned long long) (g.lo - g.dlo));
+		GDSP_REQUIRE (endsChrom || (double) (g.dhi - g.hi) >= reach
+		              || (uint64_t) (g.dhi - g.hi) == (uint64_t) g.chrom_len - ((uint64_t) g.pos0 + (g.hi - g.lo)),
+		              "gdsp_morphology: piece %d needs a right halo of %.0f cells (has %llu)", s, reach, (unsigned long long) (g.dhi - g.hi));
+		if (g.dlo < g.lo || g.dhi > g.hi) anyHalo = true;
+		}
+	if (anyHalo)
+		{
+		// the marker bits of two pieces must not meet in one 32-cell word
+		std::vector<std::pair<uint64_t, uint64_t> > span;
+		for (int s = 0; s < L->nseg; s++) span.push_back (std::make_pair ((uint64_t) L->h[s].dlo, (uint64_t) L->h[s].dhi));
+		std::sort (span.begin (), span.end ());
+		for (size_t k = 1; k < span.size (); k++)
+			GDSP_REQUIRE ((span[k].first >> 5) >= ((span[k-1].second + 31) >> 5),
+			              "gdsp_morphology: pieces %zu and %zu share a 32-cell word; leave 32 spare cells between pieces", k - 1, k);
+		}
 	TileMap tm;
 	GDSP_TRY (gdsp_layout_tilemap (L, MO_TILE, &tm));
 	uint64_t words = (buffer_cells + 31) / 32 + 64;
@@ -295,15 +387,17 @@ extern "C" int gdsp_morphology (gdsp_ctx* c, const gdsp_layout* L_, double* sig,
 	wk.tileFirst = (long long*) p;             p += ((tilesCap * 8 + 255) / 256) * 256;
 	wk.tileLast  = (long long*) p;
 
-	// how far can a neighbouring marker matter?  (cells) -> tiles
-	double reach;
-	if      (kind == GDSP_MORPH_DILATE || kind == GDSP_MORPH_ERODE) reach = (double) ((left > right) ? left : right) + 1;
-	else    reach = length + 2;
 	double tilesD = reach / MO_TILE + 2;
 	uint32_t maxTileSearch = (tilesD > 4.0e9) ? 0xffffffffu : (uint32_t) tilesD;
 
+	if (anyHalo) GDSP_CUDA (cudaMemsetAsync (wk.words, 0, words * 4, c->stream));     // halo words are OR-ed in
 	k_morph_pack<<<(unsigned) tm.ntiles, MO_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, sig, kind, threshold, wk);
 	GDSP_KERNEL_CHECK ();
+	if (anyHalo)
+		{
+		k_morph_pack_halo<<<2 * L->nseg, 256, 0, c->stream>>> (L->d, sig, kind, threshold, wk);
+		GDSP_KERNEL_CHECK ();
+		}
 	k_morph_apply<<<(unsigned) tm.ntiles, MO_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, sig, kind, length,
 	        (long long) left, (long long) right, oneVal, zeroVal, maxTileSearch, wk);
 	GDSP_KERNEL_CHECK ();

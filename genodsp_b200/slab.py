@@ -36,7 +36,9 @@ def partition(sorted_lengths, world, rank, halo):
             right = halo if (pos0 + (b - a)) < length else 0  # ... on rank+1
             left = min(left, pos0)
             right = min(right, length - (pos0 + (b - a)))
-            lo = _round_up(pos + left, ALIGN)
+            # 32 spare cells after the previous piece's readable range: no two pieces share a 32-cell
+            # word of the bit-packed morphology masks
+            lo = _round_up(pos + left + 32, ALIGN)
             hi = lo + (b - a)
             segs.append((si, lo, hi, lo - left, hi + right, pos0))
             pos = hi + right

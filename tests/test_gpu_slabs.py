@@ -181,3 +181,47 @@ def test_slab_operators_on_virtual_ranks(world, kind):
     finally:
         for g in ranks:
             g.close()
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_slab_morphology_with_halos(world):
+    """open / close / dilate / erode on slab pieces: the marker search continues into the halo cells the
+    neighbouring rank supplied (halo >= the operator's reach), so the owned cells equal the
+    whole-chromosome result"""
+    orc = Oracle()
+    rng = np.random.default_rng(40 + world)
+    ranks, order = make_ranks(world, halo=HALO)
+    try:
+        sig = {}
+        for name, n in CHROMS:
+            v = np.zeros(n)
+            pos = 0
+            while pos < n:                                   # runs and gaps of 1..400 cells
+                L = int(rng.integers(1, 400)); v[pos:pos + L] = float(rng.integers(0, 2)) * float(rng.integers(1, 9)); pos += L
+            sig[name] = v
+        cases = [
+            ("open 150", lambda g: g.open_(150, 0.5), lambda v: orc.open(v, 150, 0.5)),
+            ("close 150", lambda g: g.close_(150, 0.5), lambda v: orc.close(v, 150, 0.5)),
+            ("close 598", lambda g: g.close_(598, 0.5), lambda v: orc.close(v, 598, 0.5)),
+            ("dilate 301", lambda g: g.dilate(301, threshold=0.5), lambda v: orc.dilate(v, 150, 151, 0.5)),
+            ("erode 77", lambda g: g.erode(77, threshold=0.5), lambda v: orc.erode(v, 38, 39, 0.5)),
+        ]
+        for label, gpu_fn, cpu_fn in cases:
+            scatter_signal(ranks, sig)
+            exchange(ranks)
+            for g in ranks:
+                gpu_fn(g)
+            got = gather_signal(ranks)
+            for name, _ in CHROMS:
+                want = cpu_fn(sig[name].copy())
+                bad = np.nonzero(bits(got[name]) != bits(want))[0]
+                assert bad.size == 0, (label, world, name, bad[:8], got[name][bad[:8]], want[bad[:8]])
+        # a reach larger than the halo must be refused, not silently wrong
+        from genodsp_b200 import capi
+        scatter_signal(ranks, sig)
+        with pytest.raises(capi.GdspError):
+            for g in ranks:
+                g.open_(5000, 0.5)
+    finally:
+        for g in ranks:
+            g.close()
