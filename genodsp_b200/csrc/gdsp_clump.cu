@@ -97,7 +97,7 @@ struct ClumpWork
 // ---------------------------------------------------------------------------
 // pass A
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(CL_THREADS, 3)
+__global__ void __launch_bounds__(CL_THREADS, 4)
 k_clump_a (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
            const double* __restrict__ sig, double T, int above, ClumpWork wk,
            ScanStatus<double> stSum, ScanStatus<double> stMin)
@@ -159,12 +159,12 @@ k_clump_a (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, i
 			m[r][c] = (e < n) ? x[r][c] : __longlong_as_double (0x7ff0000000000000ll);
 			}
 	double wExM, tAggM;
-	tile_scan<double> (m, __longlong_as_double (0x7ff0000000000000ll), [] (double a, double b) { return fmin (a, b); },
+	tile_scan<double> (m, __longlong_as_double (0x7ff0000000000000ll), [] (double a, double b) { return (b < a) ? b : a; },
 	                   s_warp, wExM, tAggM);
 	if (threadIdx.x < 32)
 		{
 		const double e = scan_lookback<double> (stMin, tile, tis == 0, tAggM, __longlong_as_double (0x7ff0000000000000ll),
-		                                        [] (double a, double b) { return fmin (a, b); });
+		                                        [] (double a, double b) { return (b < a) ? b : a; });
 		if (threadIdx.x == 0) s_carry[1] = e;
 		}
 	__syncthreads ();
@@ -191,7 +191,7 @@ k_clump_a (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, i
 // ---------------------------------------------------------------------------
 // pass B (backward: tile element e <-> cell t1-1-e)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(CL_THREADS, 3)
+__global__ void __launch_bounds__(CL_THREADS, 4)
 k_clump_b (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg, uint64_t ntiles,
            const double* __restrict__ sig, double T, int above, uint32_t minLength, double relLength,
            ClumpWork wk, ScanStatus<double> stMax, ScanStatus<int> stOr)
@@ -253,10 +253,10 @@ k_clump_b (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, i
 			}
 
 	double wEx, tAgg;
-	tile_scan<double> (q, NEG, [] (double a, double b) { return fmax (a, b); }, s_warp, wEx, tAgg);
+	tile_scan<double> (q, NEG, [] (double a, double b) { return (b > a) ? b : a; }, s_warp, wEx, tAgg);
 	if (threadIdx.x < 32)
 		{
-		const double e = scan_lookback<double> (stMax, ticket, firstOfScan, tAgg, NEG, [] (double a, double b) { return fmax (a, b); });
+		const double e = scan_lookback<double> (stMax, ticket, firstOfScan, tAgg, NEG, [] (double a, double b) { return (b > a) ? b : a; });
 		if (threadIdx.x == 0) s_carryD = e;
 		}
 	__syncthreads ();
@@ -287,21 +287,33 @@ k_clump_b (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, i
 
 	#pragma unroll
 	for (int r = 0; r < CL_ROWS; r++)
+		{
+		const uint32_t e0 = cl_elem (warp, lane, r, 0);
+		if (e0 >= n) continue;
+		unsigned int fb[4];
 		#pragma unroll
 		for (int c = 0; c < 4; c++)
 			{
-			const uint32_t e = cl_elem (warp, lane, r, c);
-			if (e >= n) continue;
 			const int s = seg_or (carryI, st[r][c]);
 			const int marked = (ql[r][c] >> 2) & 1;
-			wk.F[t1 - 1 - e] = (unsigned char) (marked | ((marked & s & 1) << 1) | ((ql[r][c] & 1) << 2));
+			fb[c] = (unsigned int) (marked | ((marked & s & 1) << 1) | ((ql[r][c] & 1) << 2));
 			}
+		// elements e0..e0+3 are the cells t1-1-e0 down to t1-4-e0: one 32-bit store when that group is
+		// whole and 4-aligned (byte stores cost a 32-byte sector transaction each)
+		if (e0 + 4 <= n && ((t1 - e0) & 3) == 0)
+			*reinterpret_cast<unsigned int*> (wk.F + (t1 - 4 - e0)) = fb[3] | (fb[2] << 8) | (fb[1] << 16) | (fb[0] << 24);
+		else
+			{
+			#pragma unroll
+			for (int c = 0; c < 4; c++) if (e0 + c < n) wk.F[t1 - 1 - (e0 + c)] = (unsigned char) fb[c];
+			}
+		}
 	}
 
 // ---------------------------------------------------------------------------
 // pass C (forward)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(CL_THREADS, 3)
+__global__ void __launch_bounds__(CL_THREADS, 4)
 k_clump_c (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
            double* __restrict__ sig, double oneVal, double zeroVal, ClumpWork wk, ScanStatus<int> stOr)
 	{
