@@ -15,20 +15,17 @@
 #include "gdsp_common.cuh"
 #include "gdsp_scan.cuh"
 
-#define RUN_THREADS 256
+#define RUN_THREADS 512
 #define RUN_PER     16
-#define RUN_TILE    (RUN_THREADS * RUN_PER)      // 4096
+#define RUN_TILE    (RUN_THREADS * RUN_PER)      // 8192
 
-__device__ __forceinline__ uint32_t run_pad (uint32_t j) { return j + (j >> 4); }
-
-__global__ void __launch_bounds__(RUN_THREADS, 4)
+__global__ void __launch_bounds__(RUN_THREADS, 3)
 k_runs (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
         const double* __restrict__ sig, int collapse, int show,
         uint32_t* __restrict__ oStart, uint32_t* __restrict__ oEnd, double* __restrict__ oVal,
         uint64_t cap, unsigned long long* __restrict__ segFirst, uint64_t ntiles,
         ScanStatus<unsigned long long> st)
 	{
-	__shared__ double s_v[RUN_TILE + 2 + ((RUN_TILE + 2) >> 4) + 2];
 	__shared__ unsigned int s_warp[RUN_THREADS / 32];
 	__shared__ unsigned long long s_excl;
 
@@ -92,40 +89,28 @@ k_runs (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int 
 		}
 	else
 		{
-	// staged cell j <-> sig[t0 - 1 + j], j in [0, n+2); cells outside [lo,hi) are never compared
-	for (uint32_t j = threadIdx.x; j < n + 2; j += RUN_THREADS)
-		{
-		int64_t g = (int64_t) t0 - 1 + (int64_t) j;
-		double v = 0.0;
-		if (g >= (int64_t) sd.lo && g < (int64_t) sd.hi) v = sig[g];
-		s_v[run_pad (j)] = v;
-		}
-	__syncthreads ();
-
-	if (c0 < n)
-		{
-		double prev = s_v[run_pad (c0)];           // cell c0-1
-		double cur  = s_v[run_pad (c0 + 1)];
-		#pragma unroll
-		for (int k = 0; k < RUN_PER; k++)
+		// edge tile (shorter than RUN_TILE): cells and their neighbours straight from global memory
+		if (c0 < n)
 			{
-			const uint32_t c = c0 + k;
-			double next = s_v[run_pad (c + 2)];
-			if (c < n)
+			#pragma unroll 4
+			for (int k = 0; k < RUN_PER; k++)
 				{
+				const uint32_t c = c0 + k;
+				if (c >= n) break;
 				const bool first = (t0 + c == sd.lo), last = (t0 + c + 1 == sd.hi);
+				const double cur = sig[t0 + c];
 				const bool pr = show || (cur != 0);
 				if (pr)
 					{
+					const double prev = first ? 0.0 : sig[t0 + c - 1];
+					const double next = last  ? 0.0 : sig[t0 + c + 1];
 					const bool prPrev = !first && (show || prev != 0);
 					const bool prNext = !last  && (show || next != 0);
 					if (first || !collapse || !prPrev || cur != prev)  heads |= 1u << k;
 					if (last  || !collapse || !prNext || next != cur)  tails |= 1u << k;
 					}
 				}
-			prev = cur;  cur = next;
 			}
-		}
 		}
 
 	// block exclusive scan of head counts
@@ -174,14 +159,8 @@ k_runs (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int 
 				{
 				if (idx < cap)
 					{
-					double v;
-					if (fullTile)
-						{
-						v = myv[0];
-						#pragma unroll
-						for (int q = 1; q < RUN_PER; q++) if (q == k) v = myv[q];
-						}
-					else v = s_v[run_pad (c + 1)];
+					double v = __ldg (sig + t0 + c);         // re-read (L2): keeping 16 cells per thread in
+					                                           // registers until here halves the occupancy
 					// the reference's state machine starts with val=+0.0 (genodsp.c:1590): a collapsed
 					// run of zeros that begins at base 0 reports that +0.0, not v[0]
 					if (coord == 0 && collapse && v == 0) v = 0.0;
