@@ -233,17 +233,127 @@ k_scan_tiles (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base
 		}
 	}
 
-template <typename T>
-static int launch_scan (gdsp_ctx* c, gdsp_layout* L, const T* in, double* out, int addTo)
+// ---------------------------------------------------------------------------
+// Cumulative sum (chained).  A chained tile waits for its predecessors between reading and writing,
+// so what bounds the kernel is how many tiles an SM keeps in flight, i.e. registers per thread.
+// k_cumsum therefore reads its tile twice: once to form the tile's sum (published at once), and --
+// after the look-back -- row by row from L2 to scan and write, holding 4 cells at a time instead of
+// 16 (32 registers of data).  DRAM traffic is unchanged (the second read hits L2).
+// ---------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(SCAN_THREADS, 8)
+k_cumsum (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
+          const double* __restrict__ in, double* __restrict__ out, ScanStatus<double> st)
+	{
+	__shared__ double s_warp[SCAN_WARPS];
+	__shared__ double s_excl;
+	const uint32_t tile = scan_take_ticket (st.ticket);
+	int seg;  uint64_t tis;
+	tile_to_seg (base, nseg, tile, seg, tis);
+	const SegDev sd = segs[seg];
+	const uint64_t t0 = sd.lo + tis * SCAN_TILE;
+	const uint32_t n  = (uint32_t) ((sd.hi - t0 < SCAN_TILE) ? (sd.hi - t0) : SCAN_TILE);
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+	// phase 1: the warp's total, rows in order, lanes in order (the same association as phase 2)
+	double x[SCAN_ROWS][4];
+	#pragma unroll
+	for (int r = 0; r < SCAN_ROWS; r++)
+		{
+		const uint32_t off = warp * (SCAN_ROWS * 128) + r * 128 + lane * 4;
+		if (off + 4 <= n) ldg_stream4 (in + t0 + off, x[r][0], x[r][1], x[r][2], x[r][3]);
+		else
+			{
+			#pragma unroll
+			for (int c = 0; c < 4; c++) x[r][c] = (off + c < n) ? in[t0 + off + c] : 0.0;
+			}
+		}
+	double warpTot = 0.0;
+	#pragma unroll
+	for (int r = 0; r < SCAN_ROWS; r++)
+		{
+		double g = ((x[r][0] + x[r][1]) + x[r][2]) + x[r][3];
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+			{
+			const double up = shfl_up_f64 (g, d);
+			if (lane >= d) g += up;
+			}
+		warpTot += shfl_idx_f64 (g, 31);
+		}
+	if (lane == 0) s_warp[warp] = warpTot;
+	__syncthreads ();
+	double warpExcl = 0.0, tileAgg = 0.0;
+	#pragma unroll
+	for (int w = 0; w < SCAN_WARPS; w++) { const double t = s_warp[w];  if (w < warp) warpExcl += t;  tileAgg += t; }
+	if (threadIdx.x < 32)
+		{
+		const double e = scan_lookback<double> (st, tile, tis == 0, tileAgg, 0.0, [] (double a, double b) { return a + b; });
+		if (threadIdx.x == 0) s_excl = e;
+		}
+	__syncthreads ();
+
+	// phase 2: row by row from L2
+	double run = s_excl + warpExcl;
+	#pragma unroll 1
+	for (int r = 0; r < SCAN_ROWS; r++)
+		{
+		const uint32_t off = warp * (SCAN_ROWS * 128) + r * 128 + lane * 4;
+		double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+		if (off + 4 <= n)
+			{
+			const double2 p = *reinterpret_cast<const double2*> (in + t0 + off), q = *reinterpret_cast<const double2*> (in + t0 + off + 2);
+			a0 = p.x;  a1 = p.y;  a2 = q.x;  a3 = q.y;
+			}
+		else
+			{
+			if (off     < n) a0 = in[t0 + off];
+			if (off + 1 < n) a1 = in[t0 + off + 1];
+			if (off + 2 < n) a2 = in[t0 + off + 2];
+			}
+		a1 += a0;  a2 += a1;  a3 += a2;
+		double g = a3;
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+			{
+			const double up = shfl_up_f64 (g, d);
+			if (lane >= d) g += up;
+			}
+		double ex = shfl_up_f64 (g, 1);
+		if (lane == 0) ex = 0.0;
+		ex += run;
+		run += shfl_idx_f64 (g, 31);
+		if (off >= n) continue;
+		double y0 = a0 + ex, y1 = a1 + ex, y2 = a2 + ex, y3 = a3 + ex;
+		double* o = out + t0 + off;
+		if (off + 4 <= n)
+			{
+			if (MODE == 1)
+				{
+				double b0, b1, b2, b3;
+				ldg_stream4 (o, b0, b1, b2, b3);
+				y0 += b0;  y1 += b1;  y2 += b2;  y3 += b3;
+				}
+			stg_stream4 (o, y0, y1, y2, y3);
+			}
+		else
+			{
+			const double y[4] = { y0, y1, y2, y3 };
+			for (int c = 0; c < 4 && off + c < n; c++) o[c] = (MODE == 1) ? o[c] + y[c] : y[c];
+			}
+		}
+	}
+
+static int launch_scan (gdsp_ctx* c, gdsp_layout* L, const double* in, double* out, int addTo)
 	{
 	TileMap tm;
 	GDSP_TRY (gdsp_layout_tilemap (L, SCAN_TILE, &tm));
 	void* ws;
-	GDSP_TRY (gdsp_ws (c, 0, scan_status_bytes<T> (tm.ntiles), &ws));
-	ScanStatus<T> st = scan_status_carve<T> (ws, tm.ntiles);
-	GDSP_CUDA (cudaMemsetAsync (ws, 0, scan_status_clear_bytes<T> (tm.ntiles), c->stream));
-	if (addTo) k_scan_tiles<T, 1, true><<<(unsigned) tm.ntiles, SCAN_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, in, out, st, NULL);
-	else       k_scan_tiles<T, 0, true><<<(unsigned) tm.ntiles, SCAN_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, in, out, st, NULL);
+	GDSP_TRY (gdsp_ws (c, 0, scan_status_bytes<double> (tm.ntiles), &ws));
+	ScanStatus<double> st = scan_status_carve<double> (ws, tm.ntiles);
+	GDSP_CUDA (cudaMemsetAsync (ws, 0, scan_status_clear_bytes<double> (tm.ntiles), c->stream));
+	if (addTo) k_cumsum<1><<<(unsigned) tm.ntiles, SCAN_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, in, out, st);
+	else       k_cumsum<0><<<(unsigned) tm.ntiles, SCAN_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, in, out, st);
 	GDSP_KERNEL_CHECK ();
 	return GDSP_OK;
 	}
@@ -773,5 +883,5 @@ extern "C" int gdsp_cumulative_sum (gdsp_ctx* c, const gdsp_layout* L_, const do
 	gdsp_layout* L = (gdsp_layout*) L_;
 	GDSP_REQUIRE (c && L && in && out, "gdsp_cumulative_sum: NULL argument");
 	GDSP_REQUIRE_ALIGNED (in, "gdsp_cumulative_sum");  GDSP_REQUIRE_ALIGNED (out, "gdsp_cumulative_sum");
-	return launch_scan<double> (c, L, in, out, 0);
+	return launch_scan (c, L, in, out, 0);
 	}
