@@ -255,3 +255,49 @@ def test_merge_runs_chain_across_several_cuts():
     assert s.tolist() == [0, 10, 50] and e.tolist() == [5, 45, 51] and v.tolist() == [1., 2., 3.]
     s, e, v = slab.merge_runs(chunks, collapse=False)
     assert s.size == 5
+
+
+# ----------------------------------------------------------------------------- host CLI without a GPU
+OURS_BIN = os.path.join(ROOT, "genodsp_b200", "bin", "genodsp")
+
+
+def _run_cli(binary, args, stdin=b"chr1 1 5\n", cwd=None):
+    import subprocess
+    return subprocess.run([binary] + args, input=stdin, capture_output=True, cwd=cwd, timeout=60)
+
+
+@pytest.mark.skipif(not os.path.exists(OURS_BIN), reason="host CLI not built")
+def test_cli_parser_errors_match_reference_without_gpu(tmp_path):
+    """command-line parsing happens before the device is opened: wrong arguments produce the reference's
+    first message line and exit status (the usage text that follows is worded independently)"""
+    from checkers import REF_BIN, have_ref
+    (tmp_path / "g.chroms").write_text("chr1 100\nchr2 50\n")
+    cases = [
+        ["--chromosomes=g.chroms", "=", "binarize", "--bogus"],
+        ["--chromosomes=g.chroms", "=", "nosuchoperator"],
+        ["--chromosomes=g.chroms", "=", "smooth", "--window=abc"],
+        ["--chromosomes=g.chroms", "=", "multiply"],
+        ["--chromosomes=g.chroms", "=", "minover"],
+        ["--chromosomes=g.chroms", "=", "map"],
+        ["--chromosomes=nosuchfile"],
+        ["--value=2"],
+    ]
+    for args in cases:
+        ours = _run_cli(OURS_BIN, args, cwd=tmp_path)
+        assert ours.returncode != 0, args
+        if have_ref():
+            ref = _run_cli(REF_BIN, args, cwd=tmp_path)
+            assert ref.returncode == ours.returncode, (args, ref.returncode, ours.returncode)
+            first = lambda b: b.decode(errors="replace").splitlines()[0] if b.strip() else ""
+            assert first(ours.stderr) == first(ref.stderr), (args, ours.stderr[:200], ref.stderr[:200])
+
+
+@pytest.mark.skipif(not os.path.exists(OURS_BIN), reason="host CLI not built")
+def test_cli_refuses_to_run_without_a_device(tmp_path):
+    """no CPU fallback: with no CUDA device the program stops with a message and a failure status"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    (tmp_path / "g.chroms").write_text("chr1 100\n")
+    p = _run_cli(OURS_BIN, ["--chromosomes=g.chroms", "=", "binarize"], cwd=tmp_path)
+    assert p.returncode != 0 and b"no CUDA device" in p.stderr and p.stdout == b""
