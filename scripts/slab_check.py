@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """N-GPU check of the slab-sharded pipeline with REAL ranks (NCCL):
-  depth -> smooth 101 -> localmax 11 -> percentile 99 -> binarize -> run-length output
+  depth -> smooth 101 -> localmax 11 -> percentile 99 -> binarize -> dilate 150 -> close 200 -> run-length output
 on hg38/--scale, one process per GPU, against the same pipeline on one whole-genome Genome on rank 0.
 Launch:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
          --master-port 29533 scripts/slab_check.py --scale 16
@@ -33,7 +33,7 @@ def main():
     order = sorted(range(len(chroms)), key=lambda i: -chroms[i][1])
     sorted_chroms = [chroms[i] for i in order]
     lengths = [l for _, l in sorted_chroms]
-    HALO = 50
+    HALO = 256
     segs_s, cells = slab.partition(lengths, world, rank, HALO)
     segs = [(order[si], lo, hi, dlo, dhi, pos0) for si, lo, hi, dlo, dhi, pos0 in segs_s]
     g = Genome(chroms, device=local, segs=segs, buffer_cells=cells)
@@ -54,6 +54,10 @@ def main():
     g.localmax(11)
     (p99,), n = slab.slab_percentiles([g], gather, [99000])
     g.binarize(p99)
+    slab.exchange_halos(g.sig, plan, dist)
+    g.dilate(150, threshold=0.5)                   # reach 76 cells: inside the halo
+    slab.exchange_halos(g.sig, plan, dist)
+    g.close_(200, 0.5)                             # reach 202 cells
     runs = slab.slab_runs([g], gather)
     total_cum = None
     # cumulative sum of the binary track: the last cell of every chromosome = number of ones
@@ -73,6 +77,7 @@ def main():
         w.smooth(101); w.localmax(11)
         want = w.percentile(99.0, destructive=False)["percentile99"]
         w.binarize(want)
+        w.dilate(150, threshold=0.5); w.close_(200, 0.5)
         wr = w.runs()
         print("percentile99 slabs=%r whole=%r samples=%d" % (p99, want, n), flush=True)
         ok = ok and (p99 == want) and n == sum(lengths)
