@@ -27,7 +27,7 @@ class PwOp(C.Structure):
 # gdsp_pw_code
 PW_BINARIZE_GT, PW_BINARIZE_GE, PW_ADDCONST, PW_ABS, PW_CLIP_MIN, PW_CLIP_MAX, PW_CLIP_BOTH, PW_ERASE, \
     PW_INVERT, PW_NONZERO_TO_ONE, PW_IVL_ADD, PW_IVL_SUB, PW_IVL_MUL, PW_IVL_DIV, PW_IVL_SET, \
-    PW_IVL_SET_OUTSIDE, PW_IVL_ASSIGN, PW_IVL_MIN, PW_IVL_MAX, PW_IVL_KEEP_AT = range(1, 21)
+    PW_IVL_SET_OUTSIDE, PW_IVL_ASSIGN, PW_IVL_MIN, PW_IVL_MAX, PW_IVL_KEEP_AT, PW_IVL_ACCUM_CLEAR = range(1, 22)
 PW_ERASE_HAVE_MIN, PW_ERASE_HAVE_MAX, PW_ERASE_KEEP_INSIDE = 1, 2, 4
 ACC_I32, ACC_F64 = 0, 1
 MORPH_CLOSE, MORPH_OPEN, MORPH_DILATE, MORPH_ERODE = 0, 1, 2, 3

@@ -138,6 +138,7 @@ __device__ __forceinline__ void pw_apply_vec (const PwProgram& P, double (&v)[PW
 						case GDSP_PW_IVL_MIN: if (inside) { const double w = op.val[k];  if (w < v[e]) v[e] = w; }  break;
 						case GDSP_PW_IVL_MAX: if (inside) { const double w = op.val[k];  if (w > v[e]) v[e] = w; }  break;
 						case GDSP_PW_IVL_KEEP_AT: if (!(inside && (double) g[e] == op.val[k])) v[e] = a;  break;
+						case GDSP_PW_IVL_ACCUM_CLEAR: if (inside) v[e] = (v[e] == a) ? op.val[k] : __dadd_rn (v[e], op.val[k]);  break;
 						}
 					}
 				}
@@ -330,7 +331,7 @@ extern "C" int gdsp_pointwise (gdsp_ctx* c, const gdsp_layout* L_, const double*
 	P.nops = nops;
 	for (int i = 0; i < nops; i++)
 		{
-		GDSP_REQUIRE (ops[i].code >= GDSP_PW_BINARIZE_GT && ops[i].code <= GDSP_PW_IVL_KEEP_AT,
+		GDSP_REQUIRE (ops[i].code >= GDSP_PW_BINARIZE_GT && ops[i].code <= GDSP_PW_IVL_ACCUM_CLEAR,
 		              "gdsp_pointwise: operator %d has unknown code %d", i, ops[i].code);
 		P.ops[i].code = ops[i].code;  P.ops[i].flags = ops[i].flags;
 		P.ops[i].a = ops[i].a;  P.ops[i].b = ops[i].b;  P.ops[i].c = ops[i].c;

@@ -563,6 +563,10 @@ void read_intervals (FILE* f, int valCol, int originOne_, int overlapOp, int cle
 		 * (genodsp.c:1327).  For missingVal==0 that is a plain sum; otherwise the uncovered cells are
 		 * set to missingVal afterwards through the union of the intervals. */
 		int mode = (valCol == -1 || (allInt && sumAbs < 2.0e9)) ? GDSP_ACC_I32 : GDSP_ACC_F64;
+		/* real (non-integer) values: every cell must see the reference's additions in file order */
+		if (mode == GDSP_ACC_F64
+		 && gd_apply_intervals_exact (&l, clear ? GD_EXACT_CLEAR : GD_EXACT_ADD, missingVal, "input"))
+			{ ivlist_free (&l);  return; }
 		void* work = gd_work (gdsp_accumulate_work_bytes (gd.genome, gd.cells, mode));
 		gd_check (gdsp_accumulate_host (gd.ctx, gd.genome, gd.sig, gd.cells, work, l.seg, l.start, l.end,
 		                                (valCol == -1) ? NULL : l.val, l.n, mode, clear ? 0 : 1), "input");

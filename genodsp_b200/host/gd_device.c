@@ -249,3 +249,131 @@ void ivlist_read_file (ivlist* l, const char* opName, const char* filename,
 		for (int i = 0; i < gd.nchrom; i++)
 			if (!chromsSorted[i]->flag) fprintf (stderr, "%s(%s,absent)\n", opName, chromsSorted[i]->chrom);
 	}
+
+/* ---- exact application of valued intervals --------------------------------------------------
+ * The reference adds every interval's value to every cell it covers, one interval after the other
+ * in file order (genodsp.c:1325-1329, add.c:280-281).  For integer and dyadic values any order gives
+ * the same bits and the difference-array kernels are used; for other real values (bedGraph-like
+ * decimals, abutting or overlapping intervals, NaN / infinity) a difference array is NOT exact --
+ * v + (-a + b) is not b -- so the intervals are cut into elementary pieces, every piece keeps the
+ * values of the intervals covering it IN FILE ORDER, and layer k (the k-th value of every piece) is
+ * applied by one pointwise launch: each cell receives exactly the reference's sequence of additions.
+ * Disjoint input (the common case) is a single launch.  Returns false (nothing done) when some piece
+ * is covered by more than GD_EXACT_MAX_DEPTH intervals or the piece lists would not fit in memory;
+ * the caller then falls back to the difference array (1e-12 relative). */
+#define GD_EXACT_MAX_DEPTH 4096
+
+static int ex_by_pos (const void* a, const void* b)
+	{
+	u32 x = *(const u32*) a, y = *(const u32*) b;
+	return (x > y) - (x < y);
+	}
+
+typedef struct exseg { u32* bp;  u64 np;  u32* cnt;  u64* off;  double* vals;  u32 maxDepth; } exseg;
+
+int gd_apply_intervals_exact (ivlist* l, int mode, valtype missing, const char* opName)
+	{
+	if (l->n == 0)
+		{
+		if (mode == GD_EXACT_CLEAR) gd_check (gdsp_fill (gd.ctx, gd.genome, gd.sig, missing), opName);
+		return true;
+		}
+	/* per chromosome (segment): intervals grouped, file order kept */
+	u64* segCount = (u64*) calloc ((size_t) gd.nchrom + 1, sizeof (u64));
+	for (u64 k = 0; k < l->n; k++) segCount[l->seg[k] + 1]++;
+	for (int s = 0; s < gd.nchrom; s++) segCount[s + 1] += segCount[s];
+	u64* order = (u64*) malloc (l->n * sizeof (u64));
+	{
+	u64* cur = (u64*) malloc ((size_t) gd.nchrom * sizeof (u64));
+	for (int s = 0; s < gd.nchrom; s++) cur[s] = segCount[s];
+	for (u64 k = 0; k < l->n; k++) order[cur[l->seg[k]]++] = k;           /* stable: file order inside a segment */
+	free (cur);
+	}
+
+	/* phase 1 (host only): elementary pieces of every chromosome and their value lists in file order */
+	exseg* ex = (exseg*) calloc ((size_t) gd.nchrom, sizeof (exseg));
+	int ok = true;
+	/* piece-value slots we are willing to hold: an interval that spans p elementary pieces takes p slots */
+	u64 budget = 64 * l->n + (1u << 20);
+	if (budget > 1000000000ull) budget = 1000000000ull;
+	for (int s = 0; s < gd.nchrom && ok; s++)
+		{
+		u64 a = segCount[s], b = segCount[s + 1], m = b - a;
+		if (m == 0) continue;
+		u32* bp = (u32*) malloc (2 * m * sizeof (u32));
+		u64 nb = 0;
+		for (u64 q = a; q < b; q++) { u64 k = order[q];  if (l->start[k] < l->end[k]) { bp[nb++] = l->start[k];  bp[nb++] = l->end[k]; } }
+		if (nb == 0) { free (bp);  continue; }
+		qsort (bp, nb, sizeof (u32), ex_by_pos);
+		u64 u = 0;
+		for (u64 k = 0; k < nb; k++) if (u == 0 || bp[k] != bp[u-1]) bp[u++] = bp[k];
+		nb = u;
+		u64 np = nb - 1;                                                    /* pieces [bp[p], bp[p+1]) */
+		u32* cnt = (u32*) calloc (np + 1, sizeof (u32));
+		/* depth of every piece through a difference array over piece indices (integers: exact) */
+		int64_t* d = (int64_t*) calloc (np + 2, sizeof (int64_t));
+		for (u64 q = a; q < b; q++)
+			{
+			u64 k = order[q];
+			if (l->start[k] >= l->end[k]) continue;
+			u32* ps = (u32*) bsearch (&l->start[k], bp, nb, sizeof (u32), ex_by_pos);
+			u32* pe = (u32*) bsearch (&l->end[k],   bp, nb, sizeof (u32), ex_by_pos);
+			d[ps - bp] += 1;  d[pe - bp] -= 1;
+			}
+		int64_t run = 0;  u64 total = 0;  u32 maxDepth = 0;
+		for (u64 p = 0; p < np; p++)
+			{
+			run += d[p];  cnt[p] = (u32) run;  total += (u64) run;
+			if (run > GD_EXACT_MAX_DEPTH) ok = false;
+			if ((u32) run > maxDepth) maxDepth = (u32) run;
+			}
+		free (d);
+		if (total > budget) ok = false; else budget -= total;
+		ex[s].bp = bp;  ex[s].np = np;  ex[s].cnt = cnt;  ex[s].maxDepth = maxDepth;
+		if (!ok) break;
+		u64* off = (u64*) malloc ((np + 1) * sizeof (u64));
+		off[0] = 0;
+		for (u64 p = 0; p < np; p++) off[p + 1] = off[p] + cnt[p];
+		double* vals = (double*) malloc ((off[np] + 1) * sizeof (double));
+		u32* fill = (u32*) calloc (np + 1, sizeof (u32));
+		for (u64 q = a; q < b; q++)                                           /* file order */
+			{
+			u64 k = order[q];
+			if (l->start[k] >= l->end[k]) continue;
+			u64 p0 = (u64) ((u32*) bsearch (&l->start[k], bp, nb, sizeof (u32), ex_by_pos) - bp);
+			u64 p1 = (u64) ((u32*) bsearch (&l->end[k],   bp, nb, sizeof (u32), ex_by_pos) - bp);
+			for (u64 p = p0; p < p1; p++) vals[off[p] + fill[p]++] = l->val[k];
+			}
+		free (fill);
+		ex[s].off = off;  ex[s].vals = vals;
+		}
+	free (segCount);  free (order);
+	if (getenv ("GENODSP_TIMING") != NULL)
+		fprintf (stderr, "[timing] exact interval application: %s\n", ok ? "yes" : "no (difference array)");
+
+	/* phase 2 (only if every chromosome fits): layer k of chromosome s = one pointwise launch over s */
+	if (ok)
+		{
+		if (mode == GD_EXACT_CLEAR) gd_check (gdsp_fill (gd.ctx, gd.genome, gd.sig, missing), opName);
+		ivlist layer;
+		ivlist_init (&layer);
+		for (int s = 0; s < gd.nchrom; s++)
+			for (u32 k = 0; k < ex[s].maxDepth; k++)
+				{
+				layer.n = 0;
+				for (u64 p = 0; p < ex[s].np; p++)
+					if (ex[s].cnt[p] > k) ivlist_push (&layer, 0, ex[s].bp[p], ex[s].bp[p + 1], ex[s].vals[ex[s].off[p] + k]);
+				gdsp_ivl_table* t;
+				gd_check (gdsp_ivl_table_create (gd.ctx, gd.single[s], layer.seg, layer.start, layer.end, layer.val, layer.n, &t), opName);
+				gdsp_pw_op p;  memset (&p, 0, sizeof (p));
+				p.code = (mode == GD_EXACT_CLEAR) ? GDSP_PW_IVL_ACCUM_CLEAR : (mode == GD_EXACT_SUB) ? GDSP_PW_IVL_SUB : GDSP_PW_IVL_ADD;
+				p.a = missing;  p.table = t;
+				gd_check (gdsp_pointwise (gd.ctx, gd.single[s], gd.sig, gd.sig, &p, 1), opName);
+				gdsp_ivl_table_destroy (t);
+				}
+		ivlist_free (&layer);
+		}
+	for (int s = 0; s < gd.nchrom; s++) { free (ex[s].bp);  free (ex[s].cnt);  free (ex[s].off);  free (ex[s].vals); }
+	free (ex);
+	return ok;
+	}

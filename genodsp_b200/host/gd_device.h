@@ -48,6 +48,12 @@ typedef struct ivlist
 	double* val;
 	} ivlist;
 
+/* exact (file-order) application of valued intervals, gd_device.c; false = too deep, nothing done */
+#define GD_EXACT_ADD   0
+#define GD_EXACT_SUB   1
+#define GD_EXACT_CLEAR 2
+int  gd_apply_intervals_exact (ivlist* l, int mode, valtype missing, const char* opName);
+
 void ivlist_init    (ivlist* l);
 void ivlist_push    (ivlist* l, u32 seg, u32 start, u32 end, double val);
 void ivlist_free    (ivlist* l);

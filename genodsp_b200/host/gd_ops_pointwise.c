@@ -85,11 +85,18 @@ static void add_file_now (dspop_pw* op, double sign)
 	double sumAbs = 0.0;
 	for (u64 k = 0; k < l.n; k++)
 		{
-		if (sign < 0) l.val[k] = -l.val[k];
 		if (l.val[k] != floor (l.val[k]) || fabs (l.val[k]) > 1e6) allInt = false;
 		sumAbs += fabs (l.val[k]);
 		}
 	int mode = (allInt && sumAbs < 2.0e9) ? GDSP_ACC_I32 : GDSP_ACC_F64;
+	/* real values: the reference's additions (subtractions) cell by cell in file order */
+	if (mode == GDSP_ACC_F64 && gd_apply_intervals_exact (&l, sign < 0 ? GD_EXACT_SUB : GD_EXACT_ADD, 0.0, op->common.name))
+		{
+		ivlist_free (&l);
+		if (op->destroyFile) remove (op->filename);
+		return;
+		}
+	if (sign < 0) for (u64 k = 0; k < l.n; k++) l.val[k] = -l.val[k];
 	void* work = gd_work (gdsp_accumulate_work_bytes (gd.genome, gd.cells, mode));
 	gd_check (gdsp_accumulate_host (gd.ctx, gd.genome, gd.sig, gd.cells, work, l.seg, l.start, l.end, l.val, l.n, mode, 1),
 	          op->common.name);

@@ -203,8 +203,10 @@ typedef enum gdsp_pw_code
 	GDSP_PW_IVL_MIN,          /* inside v=min(v,val)        minmax.c:1979-1982 (minwith; the host
 	                             reduces overlapping intervals to their minimum first) */
 	GDSP_PW_IVL_MAX,          /* inside v=max(v,val)        minmax.c:2265-2268 (maxwith) */
-	GDSP_PW_IVL_KEEP_AT       /* v=a everywhere except at the one cell of every interval that
+	GDSP_PW_IVL_KEEP_AT,      /* v=a everywhere except at the one cell of every interval that
 	                             gdsp_ivl_arg_extrema chose  minmax.c:345-348, :748-751 (minover/maxover) */
+	GDSP_PW_IVL_ACCUM_CLEAR   /* inside v = (v==a) ? val : v+val   the `clear` accumulate of
+	                             read_intervals, genodsp.c:1325-1329 (a = the missing value) */
 	} gdsp_pw_code;
 
 #define GDSP_PW_ERASE_HAVE_MIN    1u

@@ -200,3 +200,39 @@ def test_file_extrema_and_map_operators(data):
     assert_same(data, C + ["--novalue", "=", "slidingsum", "--window=25", "=", "minover", "trackB.iv", "--infinity=99.5"])
     assert_same(data, C + ["--novalue", "--progress=operations", "=", "minwith", "loose.iv", "=", "maxwith", "trackB.iv"])
     assert_same(data, C + ["--novalue", "--precision=12", "=", "map", "curve.map", "=", "maxwith", "loose.iv", "--value=4"])
+
+
+def test_output_values_the_device_formatter_declines(data):
+    """NaN and values of 2^63 and beyond are not formatted on the GPU: the chromosome that holds them is
+    written by the host loop (glibc printf), the others by gdsp_format_runs -- byte-identical either way"""
+    with open(data / "odd.iv", "w") as f:
+        f.write("chrA 10 20 nan\nchrA 30 40 1e300\nchrA 50 60 -2.5\nchrB 5 9 0.125\nchrC 1 2 9223372036854775808\n"
+                "chrC 7 9 9223372036854774784\nchrD 0 3 -0.0004\n")
+    for prec in ("0", "3", "17"):
+        assert_same(data, C + ["--precision=" + prec], stdin="odd.iv")
+        assert_same(data, C + ["--precision=" + prec, "--uncovered:show", "--origin=one", "--nocollapse"], stdin="odd.iv")
+
+
+def test_real_valued_intervals_are_applied_in_file_order(data):
+    """decimal (non-dyadic) values: abutting bedGraph-like intervals, overlapping ones, NaN and huge
+    values next to small ones -- the reference adds interval after interval per cell, and so must we
+    (a difference array would be off in the last bits, or poisoned by NaN / 1e300)"""
+    rng = np.random.default_rng(123)
+    with open(data / "bedgraph.iv", "w") as f:                 # abutting, disjoint, decimals
+        for n, l in CHROMS:
+            pos = 0
+            while pos < l:
+                e = min(l, pos + int(rng.integers(1, 300)))
+                f.write("%s\t%d\t%d\t%s\n" % (n, pos, e, repr(round(float(rng.normal(0, 3)), 3))))
+                pos = e
+    with open(data / "overlap.iv", "w") as f:                  # unsorted, overlapping, decimals and extremes
+        for _ in range(3000):
+            n, l = CHROMS[int(rng.integers(0, 4))]
+            a = int(rng.integers(0, max(1, l - 700)))
+            v = [repr(round(float(rng.normal(0, 1)), 4)), "0.1", "1e300", "-1e300", "nan", "1e-300"][int(rng.integers(0, 12)) % 6 if rng.random() < 0.2 else 0]
+            f.write("%s\t%d\t%d\t%s\n" % (n, a, min(l, a + int(rng.integers(1, 700))), v))
+    P = ["--precision=17", "--uncovered:show"]
+    assert_same(data, C + P, stdin="bedgraph.iv")
+    assert_same(data, C + P, stdin="overlap.iv")
+    assert_same(data, C + P + ["=", "add", "bedgraph.iv", "=", "subtract", "overlap.iv"], stdin="bedgraph.iv")
+    assert_same(data, C + P + ["=", "input", "overlap.iv", "--missing=-1.5", "=", "add", "overlap.iv"], stdin="bedgraph.iv")
