@@ -4,14 +4,21 @@
 // Replaces the accumulate loops of read_intervals (genodsp.c:1307-1330, sum
 // overlap) and op_cumulative_sum_apply (sum.c:776-792).
 //
-// K1  k_diff_*      one thread per interval: +w at the interval start, -w at
-//                   its end (clipped to the owned piece of the chromosome)
-// K2  k_scan_tiles  segmented inclusive prefix sum, single pass with decoupled
-//                   look-back; reads the difference array (int32 or fp64) and
-//                   writes fp64 depth
+// Unit-weight intervals (the `--novalue` depth case, the benchmark path):
+//   k_bin_count / k_bin_offsets / k_bin_scatter / k_bin_final -- every interval becomes one 32-bit
+//   record in the bucket of the 8192-cell tile it starts in; one block per tile turns its records
+//   into depth with shared-memory counters and writes fp64 once (no difference array in HBM).
+// Intervals with integer or dyadic values (`add`, `subtract`, valued `input`):
+//   K1  k_diff_*      one thread per interval: +w at the interval start, -w at
+//                     its end (clipped to the owned piece of the chromosome)
+//   K2  k_scan_tiles  segmented inclusive prefix sum of the difference array (int32 or fp64),
+//                     chain-free: k_diff also maintains the tile sums
+// (other real values are applied exactly, in file order, by the host's layered pointwise launches:
+// genodsp_b200/host/gd_device.c, gd_apply_intervals_exact)
+// Cumulative sum: k_cumsum, a chained (decoupled look-back) two-phase tile scan.
 //
-// Algorithmic bytes: int32 path 4 B/bp zero + 4 B/bp read + 8 B/bp
-// write + 28 B/interval; fp64 path 8+8+8 B/bp + 52 B/interval.
+// Algorithmic bytes: 16 B/bp + 28 B/interval (binned and int32 paths), 24 B/bp +
+// 52 B/interval (fp64 difference array), 16 B/bp (cumulative sum).
 #include "gdsp_common.cuh"
 #include "gdsp_scan.cuh"
 
