@@ -493,6 +493,15 @@ class Genome:
     def anticlump(self, average=0.0, length=100, relative_length=0.0, one=1.0, zero=0.0):
         self.clump(average, length, relative_length, False, one, zero)
 
+    def clump_piece(self, k, average=0.0, length=100, relative_length=0.0, above=True, one=1.0, zero=0.0):
+        """clump on owned piece k alone (it must be a whole chromosome)"""
+        lay = self._ensure_piece_layouts()[k]
+        wb = self.lib.gdsp_clump_work_bytes(self.buffer_cells)
+        work = self.work(wb)
+        check(self.lib.gdsp_clump(self.ctx, lay, self._p(self.sig), self.buffer_cells, self._p(work),
+                                  float(average), int(length), float(relative_length), int(above),
+                                  float(one), float(zero)))
+
     # ------------------------------------------------------------------ output
     def runs_device(self, bufs, collapse=True, show_uncovered=0):
         """gdsp_runs into caller-provided device tensors (start i32, end i32, value f64 of equal length):

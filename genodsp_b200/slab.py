@@ -296,3 +296,88 @@ def slab_percentiles(parts, gather, p_milli, stride=1, mn=-1.7976931348623157e30
     if total and any(not j["done"] for j in jobs):
         raise RuntimeError("slab_percentiles: selection did not converge")
     return [j["value"] for j in jobs], (total or 0)
+
+
+# ----------------------------------------------------------------------------------------------
+# clump / anticlump on slabs.  The search has no bounded reach (prefix sums, prefix minima and a
+# suffix maximum over a whole chromosome), so a chromosome that a slab boundary cuts is put back
+# together on the rank that owns its largest piece: the other pieces travel there (NCCL send/recv
+# over NVLink, or a device copy between virtual ranks), the single-GPU kernels run on the whole
+# chromosome, and every piece of the result travels back.  At most world-1 chromosomes are cut.
+# ----------------------------------------------------------------------------------------------
+
+class VirtualTransport:
+    """all rank Genomes live in this process: a transfer is a device copy"""
+    def __init__(self, parts):
+        self.parts = parts
+        self.rank_of = {id(g): r for r, g in enumerate(parts)}
+
+    def local_ranks(self):
+        return list(range(len(self.parts)))
+
+    def genome(self, rank):
+        return self.parts[rank]
+
+    def move(self, src_rank, src_view_fn, dst_rank, dst_view_fn):
+        dst_view_fn(self.parts[dst_rank]).copy_(src_view_fn(self.parts[src_rank]))
+
+
+class DistTransport:
+    """one Genome per process (torch.distributed, NCCL on GPUs)"""
+    def __init__(self, genome, dist):
+        self.g, self.dist, self.rank = genome, dist, dist.get_rank()
+
+    def local_ranks(self):
+        return [self.rank]
+
+    def genome(self, rank):
+        return self.g
+
+    def move(self, src_rank, src_view_fn, dst_rank, dst_view_fn):
+        if src_rank == dst_rank:
+            if self.rank == src_rank:
+                dst_view_fn(self.g).copy_(src_view_fn(self.g))
+        elif self.rank == src_rank:
+            self.dist.send(src_view_fn(self.g).contiguous(), dst_rank)
+        elif self.rank == dst_rank:
+            self.dist.recv(dst_view_fn(self.g), src_rank)
+
+
+def slab_clump(transport, gather, genome_factory, average=0.0, length=100, relative_length=0.0, above=True,
+               one=1.0, zero=0.0):
+    """clump_search (clump.c:494-736) on a slab-sharded genome.  genome_factory(name, length, rank) builds a
+    whole-chromosome Genome on that rank's device (called only on the rank that reassembles it)."""
+    local = transport.local_ranks()
+    # who owns which piece of which chromosome: (chromosome, pos0, length, rank, piece index)
+    mine = []
+    for r in local:
+        g = transport.genome(r)
+        mine.append([(g.seg_chrom[k], g.segs[k][4], g.segs[k][1] - g.segs[k][0], r, k) for k in range(g.nseg)])
+    pieces = sorted(p for per_rank in gather(mine) for p in per_rank)
+    by_chrom = {}
+    for p in pieces:
+        by_chrom.setdefault(p[0], []).append(p)
+    for r in local:
+        g = transport.genome(r)
+        for k in range(g.nseg):
+            if len(by_chrom[g.seg_chrom[k]]) == 1:              # whole chromosome on this rank
+                g.clump_piece(k, average, length, relative_length, above, one, zero)
+    for ci in sorted(c for c, ps in by_chrom.items() if len(ps) > 1):
+        ps = by_chrom[ci]
+        owner = max(ps, key=lambda p: (p[2], -p[3]))[3]
+        whole = None
+        if owner in local:
+            g0 = transport.genome(owner)
+            name, clen = g0.chroms[ci]
+            whole = genome_factory(name, clen, owner)
+        for (c, pos0, ln, r, k) in ps:                             # pieces -> owner
+            transport.move(r, (lambda g, k=k: g.sig[g.segs[k][0]:g.segs[k][1]]),
+                           owner, (lambda g, pos0=pos0, ln=ln: whole.sig[whole.segs[0][0] + pos0:whole.segs[0][0] + pos0 + ln]))
+        if whole is not None:
+            whole.clump(average, length, relative_length, above, one, zero)
+        for (c, pos0, ln, r, k) in ps:                             # results -> pieces
+            transport.move(owner, (lambda g, pos0=pos0, ln=ln: whole.sig[whole.segs[0][0] + pos0:whole.segs[0][0] + pos0 + ln]),
+                           r, (lambda g, k=k: g.sig[g.segs[k][0]:g.segs[k][1]]))
+        if whole is not None:
+            whole.torch.cuda.synchronize()
+            whole.close()

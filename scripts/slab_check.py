@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """N-GPU check of the slab-sharded pipeline with REAL ranks (NCCL):
-  depth -> smooth 101 -> localmax 11 -> percentile 99 -> binarize -> dilate 150 -> close 200 -> run-length output
+  depth -> smooth 101 -> localmax 11 -> percentile 99 -> binarize -> dilate 150 -> close 200 -> clump -> run-length output
 on hg38/--scale, one process per GPU, against the same pipeline on one whole-genome Genome on rank 0.
 Launch:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
          --master-port 29533 scripts/slab_check.py --scale 16
@@ -58,6 +58,9 @@ def main():
     g.dilate(150, threshold=0.5)                   # reach 76 cells: inside the halo
     slab.exchange_halos(g.sig, plan, dist)
     g.close_(200, 0.5)                             # reach 202 cells
+    # clump has no bounded reach: chromosomes cut by a slab boundary are reassembled on one rank
+    slab.slab_clump(slab.DistTransport(g, dist), gather, lambda name, clen, r: Genome([(name, clen)], device=local),
+                    average=0.97, length=300)
     runs = slab.slab_runs([g], gather)
     total_cum = None
     # cumulative sum of the binary track: the last cell of every chromosome = number of ones
@@ -78,6 +81,7 @@ def main():
         want = w.percentile(99.0, destructive=False)["percentile99"]
         w.binarize(want)
         w.dilate(150, threshold=0.5); w.close_(200, 0.5)
+        w.clump(0.97, 300)
         wr = w.runs()
         print("percentile99 slabs=%r whole=%r samples=%d" % (p99, want, n), flush=True)
         ok = ok and (p99 == want) and n == sum(lengths)

@@ -225,3 +225,29 @@ def test_slab_morphology_with_halos(world):
     finally:
         for g in ranks:
             g.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_clump_reassembles_cut_chromosomes(world):
+    """clump / anticlump on slab pieces: chromosomes cut by a slab boundary are put back together on one
+    rank (slab_clump), whole ones run in place; the result equals the whole-chromosome oracle"""
+    from genodsp_b200 import slab
+    from genodsp_b200.genome import Genome
+    orc = Oracle()
+    rng = np.random.default_rng(70 + world)
+    ranks, order = make_ranks(world, halo=0)
+    try:
+        sig = {name: rng.poisson(4, n).astype(np.float64) for name, n in CHROMS}
+        factory = lambda name, clen, rank: Genome([(name, clen)])
+        for above in (True, False):
+            scatter_signal(ranks, sig)
+            slab.slab_clump(slab.VirtualTransport(ranks), slab.virtual_gather, factory, average=4.5, length=40,
+                            above=above)
+            got = gather_signal(ranks)
+            for name, _ in CHROMS:
+                want = orc.clump(sig[name].copy(), 4.5, 40, above)
+                bad = np.nonzero(bits(got[name]) != bits(want))[0]
+                assert bad.size == 0, (world, above, name, bad[:8])
+    finally:
+        for g in ranks:
+            g.close()
