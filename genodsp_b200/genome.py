@@ -243,9 +243,7 @@ class Genome:
 
     def pct_sample(self, m, stride=1, mn=-DBL_MAX, mx=DBL_MAX, key_lo=0, key_hi=2 ** 64 - 1, seed=1):
         """gdsp_pct_sample -> (numpy samples, number of sample slots this rank owns)"""
-        m = int(m)
-        if self.tmp.numel() < m:
-            raise ValueError("sample larger than the scratch buffer")
+        m = min(int(m), int(self.tmp.numel()))          # the scratch buffer bounds the sample
         cnt, slots = C.c_uint32(), C.c_uint64()
         check(self.lib.gdsp_pct_sample(self.ctx, self.layout, self._p(self.sig), int(stride), float(mn), float(mx),
                                        int(key_lo), int(key_hi), m, int(seed), self._p(self.tmp), C.byref(cnt), C.byref(slots)))

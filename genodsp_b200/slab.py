@@ -381,3 +381,48 @@ def slab_clump(transport, gather, genome_factory, average=0.0, length=100, relat
         if whole is not None:
             whole.torch.cuda.synchronize()
             whole.close()
+
+
+def slab_percentile_then_binarize(parts, gather, p_milli, ties_above=False, one=1.0, zero=0.0):
+    """`percentile <p> = binarize --threshold=percentile<p>` on a slab-sharded genome.
+
+    The reference's percentile leaves the genome globally sorted (chromsSorted order,
+    percentile.c:611-651) and binarize then thresholds that sorted array: the result is `zero` on the
+    first K cells of the concatenated genome and `one` on the rest, K = the number of cells that do
+    not pass the threshold.  No distributed sort is needed: K comes from the summed region counts of
+    one more counting pass.  (NaN cells would sort to the ends and break the step shape: refused.)
+    -> (threshold, K)"""
+    (thr,), n = slab_percentiles(parts, gather, [int(p_milli)])
+    key = int(f64_keys(_np.array([thr]))[0])
+    neg_inf, pos_inf = int(f64_keys(_np.array([-_np.inf]))[0]), int(f64_keys(_np.array([_np.inf]))[0])
+    bounds = sorted({neg_inf, key, pos_inf})
+    local = [g.pct_count(bounds, [0] * (len(bounds) + 1), 1, -_np.inf, _np.inf)[0] for g in parts]
+    counts = _np.sum([_np.asarray(c, dtype=_np.uint64) for c in gather(local)], axis=0, dtype=_np.uint64)
+    if int(counts[0]) or int(counts[-1]):
+        raise ValueError("slab_percentile_then_binarize: the signal holds NaN")
+    kpos = bounds.index(key)
+    below = int(sum(int(c) for c in counts[:2 * kpos + 1]))          # keys strictly below the threshold
+    equal = int(counts[2 * kpos + 1])
+    K = below if ties_above else below + equal                         # binarize: v > T (or >= T) -> one
+    # cells before K in the concatenated chromsSorted genome are zero; every piece knows its offset there
+    for g in parts:
+        lengths = {}
+        for ci, (name, ln) in enumerate(g.chroms):
+            lengths[ci] = ln
+        order = sorted(range(len(g.chroms)), key=lambda i: -g.chroms[i][1])
+        before, acc = {}, 0
+        for ci in order:
+            before[ci] = acc; acc += lengths[ci]
+        g.fill(one)
+        seg, start, end = [], [], []
+        for k in range(g.nseg):
+            ci, pos0, ln = g.seg_chrom[k], g.segs[k][4], g.segs[k][1] - g.segs[k][0]
+            z_end = min(pos0 + ln, max(pos0, K - before[ci]))         # chromosome coordinates [pos0, z_end) are zero
+            if z_end > pos0:
+                seg.append(k); start.append(pos0); end.append(z_end)
+        if seg:
+            from . import capi
+            table = g.interval_table(_np.array(seg, _np.uint32), _np.array(start, _np.uint32), _np.array(end, _np.uint32))
+            g.pointwise([(capi.PW_IVL_SET, zero, 0, 0, 0, table)])
+            table.close()
+    return thr, K

@@ -251,3 +251,27 @@ def test_slab_clump_reassembles_cut_chromosomes(world):
     finally:
         for g in ranks:
             g.close()
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_slab_percentile_then_binarize(world):
+    """cfg3's `percentile 99 = binarize --threshold=percentile99` on slabs: the reference's sorted
+    post-state thresholded = a step at K, computed from region counts instead of a distributed sort"""
+    from genodsp_b200 import slab
+    rng = np.random.default_rng(5 + world)
+    ranks, order = make_ranks(world, halo=0)
+    try:
+        sig = {name: np.floor(rng.gamma(2.0, 2.0, n)) / 4.0 for name, n in CHROMS}
+        scatter_signal(ranks, sig)
+        allv = np.sort(np.concatenate([sig[CHROMS[i][0]] for i in order]))
+        for p, ties in ((99000, False), (50000, True), (10, False)):
+            scatter_signal(ranks, sig)
+            thr, K = slab.slab_percentile_then_binarize(ranks, slab.virtual_gather, p, ties_above=ties, one=2.0, zero=-1.0)
+            assert thr == allv[slab._pct_rank(allv.size, p)]
+            want_sorted = np.where((allv >= thr) if ties else (allv > thr), 2.0, -1.0)
+            got = gather_signal(ranks)
+            cat = np.concatenate([got[CHROMS[i][0]] for i in order])
+            assert np.array_equal(cat, want_sorted), (world, p, K)
+    finally:
+        for g in ranks:
+            g.close()
