@@ -58,9 +58,14 @@ __device__ __forceinline__ int64_t ivl_find (const uint64_t* __restrict__ start,
 // once per PW_VEC cells instead of once per cell.
 #define PW_VEC 8
 
+template <bool HAS_IVL>
 __device__ __forceinline__ void pw_apply_vec (const PwProgram& P, double (&v)[PW_VEC], const uint64_t (&g)[PW_VEC],
                                               const int64_t* s_klo, const int64_t* s_khi)
 	{
+	const uint64_t* cachedStart = NULL;          // table whose search results are in kc[]
+	int kc[PW_VEC];                              // k - klo of the last search (same klo for the same table)
+	#pragma unroll
+	for (int e = 0; e < PW_VEC; e++) kc[e] = -1;
 	for (int i = 0; i < P.nops; i++)
 		{
 		const PwOpDev& op = P.ops[i];
@@ -118,13 +123,18 @@ __device__ __forceinline__ void pw_apply_vec (const PwProgram& P, double (&v)[PW
 				for (int e = 0; e < PW_VEC; e++) if (v[e] != 0.0) v[e] = 1.0;
 				break;
 			default:
+				if (HAS_IVL)
 				{
-				// interval-table operators: one search per cell inside the tile's slice of the table
+				// interval-table operators: one search per cell inside the tile's slice of the table;
+				// consecutive operators on the SAME table (add B = multiply B = and B ...) reuse it
 				const int64_t klo = s_klo[i], khi = s_khi[i];
+				const bool reuse = (op.start == cachedStart);
+				cachedStart = op.start;
 				#pragma unroll
 				for (int e = 0; e < PW_VEC; e++)
 					{
-					const int64_t k = ivl_find (op.start, klo, khi, g[e]);
+					const int64_t k = reuse ? klo + kc[e] : ivl_find (op.start, klo, khi, g[e]);
+					kc[e] = (int) (k - klo);
 					const bool inside = (k >= klo) && (g[e] < op.end[k]);
 					switch (op.code)
 						{
@@ -146,7 +156,10 @@ __device__ __forceinline__ void pw_apply_vec (const PwProgram& P, double (&v)[PW
 		}
 	}
 
-__global__ void __launch_bounds__(PW_THREADS)
+// HAS_IVL = false: programs without interval-table operators get a kernel without the table code
+// (fewer registers: the plain chains run at the HBM rate)
+template <bool HAS_IVL>
+__global__ void __launch_bounds__(PW_THREADS, 3)
 k_pointwise (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
              const double* __restrict__ in, double* __restrict__ out, const __grid_constant__ PwProgram P)
 	{
@@ -157,7 +170,7 @@ k_pointwise (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base,
 	const uint64_t t0 = sd.lo + tis * PW_TILE;
 	uint64_t t1 = t0 + PW_TILE;  if (t1 > sd.hi) t1 = sd.hi;
 
-	if (P.hasIvl)
+	if (HAS_IVL)
 		{
 		// range of table entries that can touch [t0,t1): the last entry starting
 		// at or before t0 (it may cover t0) up to the last entry starting before t1
@@ -189,7 +202,7 @@ k_pointwise (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base,
 			if (i + 1 < t1) { double2 x = ldg_stream (in + i);  v[2*q] = x.x;  v[2*q+1] = x.y; }
 			else            { v[2*q] = (i < t1) ? in[i] : 0.0;  v[2*q+1] = 0.0; }
 			}
-		pw_apply_vec (P, v, g, s_klo, s_khi);
+		pw_apply_vec<HAS_IVL> (P, v, g, s_klo, s_khi);
 		#pragma unroll
 		for (int q = 0; q < PW_VEC / 2; q++)
 			{
@@ -345,7 +358,8 @@ extern "C" int gdsp_pointwise (gdsp_ctx* c, const gdsp_layout* L_, const double*
 		}
 	TileMap tm;
 	GDSP_TRY (gdsp_layout_tilemap (L, PW_TILE, &tm));
-	k_pointwise<<<(unsigned) tm.ntiles, PW_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, in, out, P);
+	if (P.hasIvl) k_pointwise<true><<<(unsigned) tm.ntiles, PW_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, in, out, P);
+	else          k_pointwise<false><<<(unsigned) tm.ntiles, PW_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, in, out, P);
 	GDSP_KERNEL_CHECK ();
 	return GDSP_OK;
 	}

@@ -213,13 +213,15 @@ def slab_runs(parts, gather, collapse=True, show_uncovered=0):
 
 
 def slab_percentiles(parts, gather, p_milli, stride=1, mn=-1.7976931348623157e308, mx=1.7976931348623157e308,
-                     sample_per_rank=1 << 16, cand_cap=None, max_iter=60):
+                     sample_per_rank=1 << 18, cand_cap=1 << 18, max_iter=60):
     """op_percentile_apply's order statistics (percentile.c:392-751) over all slabs, exact, without
     moving the signal: every rank samples its slab, the combined sample brackets each wanted rank
     between two keys, one counting pass per rank (gdsp_pct_count) gives the exact population of every
     key region (summed over ranks) and compacts the cells between the brackets, whose combined sorted
     list holds the wanted element.  Regions are narrowed and the pass repeated when a bracket
-    misses.  -> (values, number of samples); identical on every rank."""
+    misses.  Candidates are only gathered while a rank holds at most `cand_cap` of them (they travel
+    through the host); a wider bracket is narrowed by another counting pass instead.
+    -> (values, number of samples); identical on every rank."""
     jobs = [{"p": int(p), "done": False, "value": 0.0, "lo": 0, "hi": _KEY_MAX, "below": 0, "inside": None}
             for p in p_milli]
     total = None
