@@ -19,6 +19,7 @@
 // result is bit-identical to the reference there (the reference's P is a
 // sequentially rounded sum; for general reals the comparison P[j]<=P[i] can
 // differ at ties within rounding -- BASELINE.json's stated tolerance class).
+#include <stdlib.h>
 #include "gdsp_common.cuh"
 #include "gdsp_scan.cuh"
 
@@ -376,6 +377,522 @@ k_clump_c (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, i
 		}
 	}
 
+// ===========================================================================
+// Fast path (every chromosome's minimum length <= CLF_MAX_HALO): the prefix arrays
+// P and M are never stored.  Pass A2 keeps only one {P,M} carry per 128-cell group
+// (0.125 B/bp); pass B2 rebuilds P and M of its tile and of the `Lmin` cells before
+// it from those carries (the halo is the tail of the previous tile: L2 hits), needs
+// ONE chained scan (the suffix maximum) and leaves two bits per cell (marked,
+// marked-and-qualifying); the trimming of every marked run to its first..last
+// qualifying cell is carry propagation on those bit words -- `fill upwards from the
+// seeds through the mask` is  (M & ~(M + S)) | S  on a 32-cell word, a word passes a
+// carry on like a full adder's generate/propagate pair, and the pairs are folded per
+// tile (k_clump_tilesum), per chromosome (k_clump_tilecarry) and per word
+// (k_clump_emit), in both directions.  DRAM traffic: 8 + 8 + 8 = 24.6 B/bp instead of
+// 66, one look-back chain per pass instead of two.
+// ===========================================================================
+#define CLF_MAX_HALO 4096                 // cells; larger minimum lengths take the stored-prefix passes above
+#define CLF_GROUPS   (CL_TILE / 128)      // 32 carry groups per tile
+#define CLF_WORDS    (CL_TILE / 32)       // 128 bit words per tile
+
+struct ClumpFast
+	{
+	double2*       carry;      // per group (tile*32 + row): x = P before the group, y = M before it (0 at a chromosome start)
+	uint32_t*      Bm;         // per word (tile*128 + w): marked
+	uint32_t*      Bq;         // marked and qualifying (v >= T, <= T for anticlump)
+	unsigned char* tsum;       // per tile: bit0/1 generate/propagate upwards, bit2/3 downwards
+	unsigned char* tcin;       // per tile: bit0 carry entering from below, bit1 from above
+	int*           segAllNeg;
+	};
+
+#define CLF_INF (__longlong_as_double (0x7ff0000000000000ll))
+
+// Inclusive prefix sums inside the 128-cell group a warp row holds (lane l: cells 4l..4l+3).  Passes
+// A2 and B2 both use exactly this association, so B2 reproduces A2's prefix sums bit for bit.
+__device__ __forceinline__ void group_sum_scan (double x[4], double& total)
+	{
+	const int lane = threadIdx.x & 31;
+	x[1] = x[0] + x[1];  x[2] = x[1] + x[2];  x[3] = x[2] + x[3];
+	double g = x[3];
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1)
+		{
+		const double up = shfl_up_f64 (g, d);
+		if (lane >= d) g = up + g;
+		}
+	double ex = shfl_up_f64 (g, 1);
+	if (lane == 0) ex = 0.0;
+	#pragma unroll
+	for (int c = 0; c < 4; c++) x[c] = ex + x[c];
+	total = shfl_idx_f64 (g, 31);
+	}
+
+__device__ __forceinline__ double dmin2 (double a, double b) { return (b < a) ? b : a; }
+__device__ __forceinline__ double dmax2 (double a, double b) { return (b > a) ? b : a; }
+
+// loads the 4 cells of a lane (cells past `n` read as 0 and are flagged invalid)
+__device__ __forceinline__ void clf_load4 (const double* __restrict__ sig, uint64_t t0, uint32_t e0, uint32_t n, double v[4])
+	{
+	if (e0 + 4 <= n) ldg_stream4 (sig + t0 + e0, v[0], v[1], v[2], v[3]);
+	else
+		{
+		#pragma unroll
+		for (int c = 0; c < 4; c++) v[c] = (e0 + c < n) ? sig[t0 + e0 + c] : 0.0;
+		}
+	}
+
+// ---- pass A2: group carries ------------------------------------------------
+__global__ void __launch_bounds__(CL_THREADS, 4)
+k_clump_carry (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
+               const double* __restrict__ sig, double T, int above, ClumpFast wk,
+               ScanStatus<double> stSum, ScanStatus<double> stMin)
+	{
+	__shared__ double s_warp[CL_WARPS];
+	__shared__ double s_carry[2];
+	__shared__ int    s_anyNonNeg;
+	const uint32_t tile = scan_take_ticket (stSum.ticket);
+	int seg;  uint64_t tis;
+	tile_to_seg (base, nseg, tile, seg, tis);
+	const SegDev sd = segs[seg];
+	const uint64_t t0 = sd.lo + tis * CL_TILE;
+	const uint32_t n  = (uint32_t) ((sd.hi - t0 < CL_TILE) ? (sd.hi - t0) : CL_TILE);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (threadIdx.x == 0) s_anyNonNeg = 0;
+	__syncthreads ();
+
+	double x[CL_ROWS][4], tot[CL_ROWS];
+	bool nonNeg = false;
+	#pragma unroll
+	for (int r = 0; r < CL_ROWS; r++)
+		{
+		const uint32_t e0 = cl_elem (warp, lane, r, 0);
+		double v[4];
+		clf_load4 (sig, t0, e0, n, v);
+		#pragma unroll
+		for (int c = 0; c < 4; c++)
+			{
+			double d = 0.0;
+			if (e0 + c < n)
+				{
+				d = above ? __dsub_rn (v[c], T) : __dsub_rn (T, v[c]);
+				if (d >= 0.0) nonNeg = true;
+				}
+			x[r][c] = d;
+			}
+		group_sum_scan (x[r], tot[r]);
+		}
+	if (nonNeg) s_anyNonNeg = 1;
+
+	// sums of the rows before row r inside this warp, of the warps before this one, of the tiles before this one
+	double rc[CL_ROWS];
+	rc[0] = 0.0;
+	#pragma unroll
+	for (int r = 1; r < CL_ROWS; r++) rc[r] = rc[r - 1] + tot[r - 1];
+	if (lane == 0) s_warp[warp] = rc[CL_ROWS - 1] + tot[CL_ROWS - 1];
+	__syncthreads ();
+	double warpExcl = 0.0, tileAgg = 0.0;
+	#pragma unroll
+	for (int w = 0; w < CL_WARPS; w++)
+		{
+		const double t = s_warp[w];
+		if (w < warp) warpExcl = warpExcl + t;
+		tileAgg = tileAgg + t;
+		}
+	if (threadIdx.x < 32)
+		{
+		const double e = scan_lookback<double> (stSum, tile, tis == 0, tileAgg, 0.0, [] (double a, double b) { return a + b; });
+		if (threadIdx.x == 0)
+			{
+			s_carry[0] = e;
+			if (s_anyNonNeg) atomicAnd (&wk.segAllNeg[seg], 0);
+			}
+		}
+	__syncthreads ();                                  // also: every warp has read s_warp
+	const double addP = s_carry[0] + warpExcl;
+
+	// minimum of the prefix sums of every group
+	double gP[CL_ROWS], rowMin[CL_ROWS];
+	#pragma unroll
+	for (int r = 0; r < CL_ROWS; r++)
+		{
+		gP[r] = addP + rc[r];
+		const uint32_t e0 = cl_elem (warp, lane, r, 0);
+		double m = CLF_INF;
+		#pragma unroll
+		for (int c = 0; c < 4; c++)
+			if (e0 + c < n) m = dmin2 (m, gP[r] + x[r][c]);
+		#pragma unroll
+		for (int d = 16; d >= 1; d >>= 1) m = dmin2 (m, shfl_xor_f64 (m, d));
+		rowMin[r] = m;
+		}
+	double rm[CL_ROWS];
+	rm[0] = CLF_INF;
+	#pragma unroll
+	for (int r = 1; r < CL_ROWS; r++) rm[r] = dmin2 (rm[r - 1], rowMin[r - 1]);
+	if (lane == 0) s_warp[warp] = dmin2 (rm[CL_ROWS - 1], rowMin[CL_ROWS - 1]);
+	__syncthreads ();
+	double wExM = CLF_INF, tAggM = CLF_INF;
+	#pragma unroll
+	for (int w = 0; w < CL_WARPS; w++)
+		{
+		const double t = s_warp[w];
+		if (w < warp) wExM = dmin2 (wExM, t);
+		tAggM = dmin2 (tAggM, t);
+		}
+	if (threadIdx.x < 32)
+		{
+		const double e = scan_lookback<double> (stMin, tile, tis == 0, tAggM, CLF_INF, [] (double a, double b) { return (b < a) ? b : a; });
+		if (threadIdx.x == 0) s_carry[1] = e;
+		}
+	__syncthreads ();
+	const double addM = dmin2 (dmin2 (s_carry[1], wExM), 0.0);      // P[-1] = 0 takes part in every prefix minimum
+
+	if (lane < CL_ROWS)
+		{
+		double p = gP[0], m = rm[0];
+		#pragma unroll
+		for (int r = 1; r < CL_ROWS; r++) if (lane == r) { p = gP[r];  m = rm[r]; }
+		wk.carry[(uint64_t) tile * CLF_GROUPS + warp * CL_ROWS + lane] = make_double2 (p, dmin2 (addM, m));
+		}
+	}
+
+// ---- pass B2: marks ----------------------------------------------------------
+// shared-memory slot of the prefix minimum of the cell `jj` cells after the first halo cell: row-major
+// groups of 128, cell 4l+c of a group at c*32+l (64-bit accesses of a warp are then conflict-free both
+// when a row is written and when it is read back shifted by Lmin)
+__device__ __forceinline__ uint32_t clf_slot (uint32_t jj) { return (jj & ~127u) | ((jj & 3u) << 5) | ((jj & 127u) >> 2); }
+
+__global__ void __launch_bounds__(CL_THREADS, 4)
+k_clump_mark (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg, uint64_t ntiles,
+              const double* __restrict__ sig, double T, int above, uint32_t minLength, double relLength,
+              ClumpFast wk, ScanStatus<double> stMax)
+	{
+	extern __shared__ double s_M[];                    // (hrows + 32) * 128 prefix minima
+	__shared__ double s_warp[CL_WARPS];
+	__shared__ double s_carryD;
+	// reversed tile order: ticket k handles the k-th tile from the END of the launch, so that every tile a
+	// block waits on (the tiles to its right) has already started
+	const uint32_t ticket = scan_take_ticket (stMax.ticket);
+	const uint64_t tile = ntiles - 1 - ticket;
+	int seg;  uint64_t tis;
+	tile_to_seg (base, nseg, tile, seg, tis);
+	const SegDev sd = segs[seg];
+	const uint64_t tilesInSeg = base[seg + 1] - base[seg];
+	const uint64_t t0 = sd.lo + tis * CL_TILE;
+	const uint32_t n  = (uint32_t) ((sd.hi - t0 < CL_TILE) ? (sd.hi - t0) : CL_TILE);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const double NEG = -CLF_INF;
+	const bool firstOfScan = (tis == tilesInSeg - 1);
+
+	uint32_t Lmin = minLength;
+	if (relLength > 0.0)
+		{
+		uint32_t rl = (uint32_t) (relLength * sd.chromLen);       // clump.c:516-522
+		if (rl > Lmin) Lmin = rl;
+		}
+	const uint32_t reach = (Lmin > 0) ? Lmin : 1;                 // M[p-1] is needed even when Lmin is 0
+	const uint32_t hrows = (reach + 127) >> 7;                    // <= CLF_MAX_HALO / 128 (the host checked)
+	const uint32_t hcells = hrows << 7;
+
+	// prefix minima of the halo rows (the tail of the previous tile(s) of this chromosome)
+	for (uint32_t h = warp; h < hrows; h += CL_WARPS)
+		{
+		const uint64_t back = (uint64_t) (hrows - h) * 128;       // cells between the row's first cell and t0
+		if (back > tis * CL_TILE) continue;                       // before the chromosome's first cell
+		const uint64_t c0 = t0 - back + lane * 4;
+		double x[4], tot;
+		ldg_stream4 (sig + c0, x[0], x[1], x[2], x[3]);
+		#pragma unroll
+		for (int c = 0; c < 4; c++) x[c] = above ? __dsub_rn (x[c], T) : __dsub_rn (T, x[c]);
+		group_sum_scan (x, tot);
+		const double2 cr = wk.carry[tile * CLF_GROUPS - (hrows - h)];
+		double m = CLF_INF;
+		#pragma unroll
+		for (int c = 0; c < 4; c++) { m = dmin2 (m, cr.x + x[c]);  x[c] = m; }     // thread-local prefix minima
+		double g = m;
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+			{
+			const double up = shfl_up_f64 (g, d);
+			if (lane >= d) g = dmin2 (up, g);
+			}
+		double ex = shfl_up_f64 (g, 1);
+		if (lane == 0) ex = CLF_INF;
+		ex = dmin2 (ex, cr.y);
+		#pragma unroll
+		for (int c = 0; c < 4; c++) s_M[h * 128 + c * 32 + lane] = dmin2 (ex, x[c]);
+		}
+
+	// own rows: P stays in registers, M goes to shared memory
+	double P[CL_ROWS][4];
+	unsigned qualNib[CL_ROWS];
+	#pragma unroll
+	for (int r = 0; r < CL_ROWS; r++)
+		{
+		const uint32_t e0 = cl_elem (warp, lane, r, 0);
+		double v[4], tot;
+		clf_load4 (sig, t0, e0, n, v);
+		unsigned qn = 0;
+		#pragma unroll
+		for (int c = 0; c < 4; c++)
+			{
+			const bool in = (e0 + c < n);
+			if (in && (above ? (v[c] >= T) : (v[c] <= T))) qn |= 1u << c;
+			P[r][c] = in ? (above ? __dsub_rn (v[c], T) : __dsub_rn (T, v[c])) : 0.0;
+			}
+		qualNib[r] = qn;
+		group_sum_scan (P[r], tot);
+		const double2 cr = wk.carry[tile * CLF_GROUPS + warp * CL_ROWS + r];
+		double x[4], m = CLF_INF;
+		#pragma unroll
+		for (int c = 0; c < 4; c++)
+			{
+			P[r][c] = cr.x + P[r][c];
+			if (e0 + c < n) m = dmin2 (m, P[r][c]);
+			x[c] = m;
+			}
+		double g = m;
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+			{
+			const double up = shfl_up_f64 (g, d);
+			if (lane >= d) g = dmin2 (up, g);
+			}
+		double ex = shfl_up_f64 (g, 1);
+		if (lane == 0) ex = CLF_INF;
+		ex = dmin2 (ex, cr.y);
+		#pragma unroll
+		for (int c = 0; c < 4; c++) s_M[hcells + (warp * CL_ROWS + r) * 128 + c * 32 + lane] = dmin2 (ex, x[c]);
+		}
+	__syncthreads ();
+
+	// q = P where the cell is a valid end, -inf elsewhere
+	#pragma unroll
+	for (int r = 0; r < CL_ROWS; r++)
+		#pragma unroll
+		for (int c = 0; c < 4; c++)
+			{
+			const uint32_t e = cl_elem (warp, lane, r, c);
+			double qq = NEG;
+			if (e < n)
+				{
+				const uint64_t i = tis * CL_TILE + e;                    // index inside the chromosome
+				if (i + 1 >= (uint64_t) Lmin)
+					{
+					const double mj = (i >= (uint64_t) Lmin) ? s_M[clf_slot (hcells + e - Lmin)] : 0.0;     // M[i-Lmin], M[-1] = 0
+					if (mj <= P[r][c]) qq = P[r][c];
+					}
+				}
+			P[r][c] = qq;
+			}
+
+	// suffix maximum of q: inside the thread, the row, the warp (rows 3..0), the tile (warps 7..0), the chromosome
+	double rowTot[CL_ROWS];
+	#pragma unroll
+	for (int r = 0; r < CL_ROWS; r++)
+		{
+		P[r][2] = dmax2 (P[r][2], P[r][3]);  P[r][1] = dmax2 (P[r][1], P[r][2]);  P[r][0] = dmax2 (P[r][0], P[r][1]);
+		double g = P[r][0];
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+			{
+			const double dn = shfl_down_f64 (g, d);
+			if (lane + d < 32) g = dmax2 (g, dn);
+			}
+		double ex = shfl_down_f64 (g, 1);
+		if (lane == 31) ex = NEG;
+		#pragma unroll
+		for (int c = 0; c < 4; c++) P[r][c] = dmax2 (P[r][c], ex);
+		rowTot[r] = shfl_idx_f64 (g, 0);
+		}
+	double rcar[CL_ROWS];
+	rcar[CL_ROWS - 1] = NEG;
+	#pragma unroll
+	for (int r = CL_ROWS - 2; r >= 0; r--) rcar[r] = dmax2 (rcar[r + 1], rowTot[r + 1]);
+	if (lane == 0) s_warp[warp] = dmax2 (rcar[0], rowTot[0]);
+	__syncthreads ();
+	double wEx = NEG, tAgg = NEG;
+	#pragma unroll
+	for (int w = 0; w < CL_WARPS; w++)
+		{
+		const double t = s_warp[w];
+		if (w > warp) wEx = dmax2 (wEx, t);
+		tAgg = dmax2 (tAgg, t);
+		}
+	if (threadIdx.x < 32)
+		{
+		const double e = scan_lookback<double> (stMax, ticket, firstOfScan, tAgg, NEG, [] (double a, double b) { return (b > a) ? b : a; });
+		if (threadIdx.x == 0) s_carryD = e;
+		}
+	__syncthreads ();
+	const double carryQ = dmax2 (s_carryD, wEx);
+
+	// two bits per cell, 32 cells per word (8 lanes of a row share a word)
+	#pragma unroll
+	for (int r = 0; r < CL_ROWS; r++)
+		{
+		const uint32_t e0 = cl_elem (warp, lane, r, 0);
+		const double cq = dmax2 (carryQ, rcar[r]);
+		unsigned mk = 0;
+		#pragma unroll
+		for (int c = 0; c < 4; c++)
+			if (e0 + c < n)
+				{
+				const double mp = (tis == 0 && e0 + c == 0) ? 0.0 : s_M[clf_slot (hcells + e0 + c - 1)];      // M[p-1], M[-1] = 0
+				if (dmax2 (cq, P[r][c]) >= mp) mk |= 1u << c;
+				}
+		unsigned wm = mk << ((lane & 7) * 4), wq = (mk & qualNib[r]) << ((lane & 7) * 4);
+		#pragma unroll
+		for (int d = 1; d <= 4; d <<= 1)
+			{
+			wm |= __shfl_xor_sync (0xffffffffu, wm, d);
+			wq |= __shfl_xor_sync (0xffffffffu, wq, d);
+			}
+		if ((lane & 7) == 0)
+			{
+			const uint64_t w = tile * CLF_WORDS + (warp * CL_ROWS + r) * 4 + (lane >> 3);
+			wk.Bm[w] = wm;  wk.Bq[w] = wq;
+			}
+		}
+	}
+
+// ---- run trimming on the bit words -------------------------------------------
+// cells reached from the seeds S (a subset of M) going UP through set bits of M; `cin`: the cell below
+// bit 0 is reached
+__device__ __forceinline__ uint32_t clf_fill_up (uint32_t M, uint32_t S, uint32_t cin)
+	{
+	S |= cin & M & 1u;
+	return (M & ~(M + S)) | S;
+	}
+// bit0 = the word reaches the cell above it on its own (generate), bit1 = it passes a carry on (propagate)
+__device__ __forceinline__ int clf_gp (uint32_t M, uint32_t S)
+	{
+	return (int) (clf_fill_up (M, S, 0) >> 31) | ((M == 0xffffffffu) ? 2 : 0);
+	}
+// a then b (b is the later word in the direction of travel)
+__device__ __forceinline__ int clf_comb (int a, int b) { return ((b | ((b >> 1) & a)) & 1) | (a & b & 2); }
+__device__ __forceinline__ int clf_apply (int gp, int cin) { return (gp | ((gp >> 1) & cin)) & 1; }
+
+// one warp per tile: fold the 128 words of the tile in both directions
+__global__ void __launch_bounds__(256)
+k_clump_tilesum (uint64_t ntiles, ClumpFast wk)
+	{
+	const uint64_t tile = (uint64_t) blockIdx.x * 8 + (threadIdx.x >> 5);
+	const int lane = threadIdx.x & 31;
+	if (tile >= ntiles) return;
+	const uint4 m = *reinterpret_cast<const uint4*> (wk.Bm + tile * CLF_WORDS + lane * 4);
+	const uint4 q = *reinterpret_cast<const uint4*> (wk.Bq + tile * CLF_WORDS + lane * 4);
+	int up = clf_comb (clf_comb (clf_comb (clf_gp (m.x, q.x), clf_gp (m.y, q.y)), clf_gp (m.z, q.z)), clf_gp (m.w, q.w));
+	int dn = clf_comb (clf_comb (clf_comb (clf_gp (__brev (m.w), __brev (q.w)), clf_gp (__brev (m.z), __brev (q.z))),
+	                             clf_gp (__brev (m.y), __brev (q.y))), clf_gp (__brev (m.x), __brev (q.x)));
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1)
+		{
+		const int o = __shfl_up_sync (0xffffffffu, up, d);         // earlier lanes
+		if (lane >= d) up = clf_comb (o, up);
+		const int p = __shfl_down_sync (0xffffffffu, dn, d);       // lanes above come first going down
+		if (lane + d < 32) dn = clf_comb (p, dn);
+		}
+	const int upAll = __shfl_sync (0xffffffffu, up, 31), dnAll = __shfl_sync (0xffffffffu, dn, 0);
+	if (lane == 0) wk.tsum[tile] = (unsigned char) (upAll | (dnAll << 2));
+	}
+
+// one block per chromosome: the carry entering every tile from below and from above
+__global__ void __launch_bounds__(256)
+k_clump_tilecarry (const uint64_t* __restrict__ base, ClumpFast wk)
+	{
+	__shared__ int s_up[256], s_dn[256];
+	const uint64_t b0 = base[blockIdx.x], b1 = base[blockIdx.x + 1];
+	const uint64_t nt = b1 - b0, chunk = (nt + 255) / 256;
+	const uint64_t lo = b0 + threadIdx.x * chunk < b1 ? b0 + threadIdx.x * chunk : b1;
+	const uint64_t hi = lo + chunk < b1 ? lo + chunk : b1;
+	int up = 2, dn = 2;                                            // identity: propagate only
+	for (uint64_t t = lo; t < hi; t++) up = clf_comb (up, wk.tsum[t] & 3);
+	for (uint64_t t = hi; t > lo; t--) dn = clf_comb (dn, (wk.tsum[t - 1] >> 2) & 3);
+	s_up[threadIdx.x] = up;  s_dn[threadIdx.x] = dn;
+	__syncthreads ();
+	int cu = 0, cd = 0;                                            // nothing enters a chromosome from outside
+	for (int k = 0; k < (int) threadIdx.x; k++) cu = clf_apply (s_up[k], cu);
+	for (int k = 255; k > (int) threadIdx.x; k--) cd = clf_apply (s_dn[k], cd);
+	for (uint64_t t = lo; t < hi; t++)
+		{
+		wk.tcin[t] = (unsigned char) cu;                           // bit1 is OR-ed in below
+		cu = clf_apply (wk.tsum[t] & 3, cu);
+		}
+	for (uint64_t t = hi; t > lo; t--)
+		{
+		wk.tcin[t - 1] |= (unsigned char) (cd << 1);
+		cd = clf_apply ((wk.tsum[t - 1] >> 2) & 3, cd);
+		}
+	}
+
+// one block per tile: the words of the trimmed runs, then the one/zero cells
+__global__ void __launch_bounds__(CL_THREADS, 6)
+k_clump_emit (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
+              double* __restrict__ sig, double oneVal, double zeroVal, ClumpFast wk)
+	{
+	__shared__ uint32_t s_out[CLF_WORDS];
+	__shared__ int s_wu[4], s_wd[4];
+	const uint64_t tile = blockIdx.x;
+	int seg;  uint64_t tis;
+	tile_to_seg (base, nseg, tile, seg, tis);
+	const SegDev sd = segs[seg];
+	const uint64_t t0 = sd.lo + tis * CL_TILE;
+	const uint32_t n  = (uint32_t) ((sd.hi - t0 < CL_TILE) ? (sd.hi - t0) : CL_TILE);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const bool allNeg = wk.segAllNeg[seg] != 0;                   // clump.c:545-565: nothing can clump
+	const int tc = wk.tcin[tile];
+
+	uint32_t M = 0, S = 0;
+	int up = 2, dn = 2, upIn = 2, dnIn = 2;
+	if (warp < 4)
+		{
+		M = wk.Bm[tile * CLF_WORDS + threadIdx.x];
+		S = wk.Bq[tile * CLF_WORDS + threadIdx.x];
+		up = clf_gp (M, S);  dn = clf_gp (__brev (M), __brev (S));
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+			{
+			const int o = __shfl_up_sync (0xffffffffu, up, d);
+			if (lane >= d) up = clf_comb (o, up);
+			const int p = __shfl_down_sync (0xffffffffu, dn, d);
+			if (lane + d < 32) dn = clf_comb (p, dn);
+			}
+		upIn = __shfl_up_sync (0xffffffffu, up, 1);                // fold of the earlier words of this warp
+		if (lane == 0) upIn = 2;
+		dnIn = __shfl_down_sync (0xffffffffu, dn, 1);
+		if (lane == 31) dnIn = 2;
+		if (lane == 31) s_wu[warp] = up;
+		if (lane == 0)  s_wd[warp] = dn;
+		}
+	__syncthreads ();
+	if (warp < 4)
+		{
+		int cu = tc & 1, cd = (tc >> 1) & 1;
+		for (int w = 0; w < warp; w++) cu = clf_apply (s_wu[w], cu);
+		for (int w = 3; w > warp; w--) cd = clf_apply (s_wd[w], cd);
+		cu = clf_apply (upIn, cu);  cd = clf_apply (dnIn, cd);
+		const uint32_t fu = clf_fill_up (M, S, (uint32_t) cu);
+		const uint32_t fd = __brev (clf_fill_up (__brev (M), __brev (S), (uint32_t) cd));
+		s_out[threadIdx.x] = allNeg ? 0u : (fu & fd);
+		}
+	__syncthreads ();
+
+	#pragma unroll
+	for (int r = 0; r < CL_ROWS; r++)
+		{
+		const uint32_t e0 = cl_elem (warp, lane, r, 0);
+		if (e0 >= n) continue;
+		const uint32_t nib = s_out[e0 >> 5] >> (e0 & 31);
+		double y[4];
+		#pragma unroll
+		for (int c = 0; c < 4; c++) y[c] = ((nib >> c) & 1) ? oneVal : zeroVal;
+		if (e0 + 4 <= n) stg_stream4 (sig + t0 + e0, y[0], y[1], y[2], y[3]);
+		else
+			for (int c = 0; c < 4 && e0 + c < n; c++) sig[t0 + e0 + c] = y[c];
+		}
+	}
+
 __global__ void k_fill_int (int* p, int n, int v)
 	{
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -398,20 +915,71 @@ extern "C" int gdsp_clump (gdsp_ctx* c, const gdsp_layout* L_, double* sig, uint
 	for (int s = 0; s < L->nseg; s++)
 		GDSP_REQUIRE (L->h[s].pos0 == 0 && L->h[s].hi - L->h[s].lo == L->h[s].chrom_len,
 		              "gdsp_clump: slab-sharded chromosomes need the carry variant (not in this build)");
+	TileMap tm;
+	GDSP_TRY (gdsp_layout_tilemap (L, CL_TILE, &tm));
+
+	// two scan status blocks (reused by the passes)
+	size_t sb = scan_status_bytes<double> (tm.ntiles);
+	void* ws;
+	GDSP_TRY (gdsp_ws (c, 0, 2 * sb, &ws));
+	void* ws1 = ws;  void* ws2 = (char*) ws + sb;
+
+	// the longest minimum length of any chromosome decides the path (clump.c:516-522)
+	uint32_t maxLmin = minLength;
+	if (relLength > 0.0)
+		for (int s = 0; s < L->nseg; s++)
+			{
+			const uint32_t rl = (uint32_t) (relLength * L->h[s].chrom_len);
+			if (rl > maxLmin) maxLmin = rl;
+			}
+	const size_t fastBytes = (size_t) tm.ntiles * (CLF_GROUPS * 16 + 2 * CLF_WORDS * 4) + 2 * (((size_t) tm.ntiles + 255) / 256) * 256
+	                       + (size_t) L->nseg * 4;
+	if (maxLmin <= CLF_MAX_HALO && fastBytes <= gdsp_clump_work_bytes (buffer_cells) && !getenv ("GDSP_CLUMP_STORED"))
+		{
+		ClumpFast wf;
+		char* p = (char*) work;
+		wf.carry = (double2*) p;            p += (size_t) tm.ntiles * CLF_GROUPS * 16;
+		wf.Bm = (uint32_t*) p;              p += (size_t) tm.ntiles * CLF_WORDS * 4;
+		wf.Bq = (uint32_t*) p;              p += (size_t) tm.ntiles * CLF_WORDS * 4;
+		wf.tsum = (unsigned char*) p;       p += (((size_t) tm.ntiles + 255) / 256) * 256;
+		wf.tcin = (unsigned char*) p;       p += (((size_t) tm.ntiles + 255) / 256) * 256;
+		wf.segAllNeg = (int*) p;
+		const uint32_t reach = maxLmin ? maxLmin : 1;
+		const size_t smem = ((size_t) ((reach + 127) / 128) + CLF_GROUPS) * 128 * sizeof (double);
+		static size_t smemSet = 0;
+		if (smem > smemSet)
+			{
+			GDSP_CUDA (cudaFuncSetAttribute (k_clump_mark, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+			smemSet = smem;
+			}
+
+		k_fill_int<<<(L->nseg + 255) / 256, 256, 0, c->stream>>> (wf.segAllNeg, L->nseg, 1);
+		GDSP_KERNEL_CHECK ();
+		GDSP_CUDA (cudaMemsetAsync (ws1, 0, scan_status_clear_bytes<double> (tm.ntiles), c->stream));
+		GDSP_CUDA (cudaMemsetAsync (ws2, 0, scan_status_clear_bytes<double> (tm.ntiles), c->stream));
+		k_clump_carry<<<(unsigned) tm.ntiles, CL_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, sig, average, above ? 1 : 0, wf,
+		        scan_status_carve<double> (ws1, tm.ntiles), scan_status_carve<double> (ws2, tm.ntiles));
+		GDSP_KERNEL_CHECK ();
+		GDSP_CUDA (cudaMemsetAsync (ws1, 0, scan_status_clear_bytes<double> (tm.ntiles), c->stream));
+		k_clump_mark<<<(unsigned) tm.ntiles, CL_THREADS, smem, c->stream>>> (L->d, tm.d_base, L->nseg, tm.ntiles, sig, average, above ? 1 : 0,
+		        minLength, relLength, wf, scan_status_carve<double> (ws1, tm.ntiles));
+		GDSP_KERNEL_CHECK ();
+		k_clump_tilesum<<<(unsigned) ((tm.ntiles + 7) / 8), 256, 0, c->stream>>> (tm.ntiles, wf);
+		GDSP_KERNEL_CHECK ();
+		k_clump_tilecarry<<<L->nseg, 256, 0, c->stream>>> (tm.d_base, wf);
+		GDSP_KERNEL_CHECK ();
+		k_clump_emit<<<(unsigned) tm.ntiles, CL_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, sig, oneVal, zeroVal, wf);
+		GDSP_KERNEL_CHECK ();
+		return GDSP_OK;
+		}
+
+	// stored-prefix passes (minimum lengths beyond CLF_MAX_HALO)
 	ClumpWork wk;
 	char* p = (char*) work;
 	wk.P = (double*) p;                 p += ((buffer_cells * 8 + 255) / 256) * 256;
 	wk.M = (double*) p;                 p += ((buffer_cells * 8 + 255) / 256) * 256;
 	wk.F = (unsigned char*) p;          p += ((buffer_cells + 255) / 256) * 256;
 	wk.segAllNeg = (int*) p;
-	TileMap tm;
-	GDSP_TRY (gdsp_layout_tilemap (L, CL_TILE, &tm));
-
-	// two scan status blocks (reused by the three passes)
-	size_t sb = scan_status_bytes<double> (tm.ntiles);
-	void* ws;
-	GDSP_TRY (gdsp_ws (c, 0, 2 * sb, &ws));
-	void* ws1 = ws;  void* ws2 = (char*) ws + sb;
 
 	k_fill_int<<<(L->nseg + 255) / 256, 256, 0, c->stream>>> (wk.segAllNeg, L->nseg, 1);
 	GDSP_KERNEL_CHECK ();

@@ -545,6 +545,30 @@ def test_clump(genome, orc, kind, L):
     compare(genome, inputs, lambda v: orc.clump(v, T, L, False, 3.0, -1.0), what="anticlump L=%d" % L)
 
 
+@pytest.mark.parametrize("L", [2, 127, 128, 129, 1000, 4095, 4096, 4097])
+def test_clump_long_runs_and_halo_edges(genome, orc, L):
+    """minimum lengths either side of the 128-cell carry groups and of the 4096-cell limit of the
+    path that rebuilds the prefix sums from group carries; plateaus that span many tiles (the run
+    trimming carries cross tile and word boundaries), runs touching both chromosome ends"""
+    rng = np.random.default_rng(L)
+    inputs = load(genome, rng, "sparse")
+    for name, n in CHROMS:
+        v = inputs[name]
+        if n > 60000:
+            v[5000:5000 + 3 * 4096 + 17] = 2.0            # whole tiles above the threshold
+            v[30000:30031] = 1.0; v[30031:30063] = 0.0; v[30063:30100] = 3.0
+            v[n - 9000:] = 1.0                            # a run that ends with the chromosome
+            v[:700] = 1.0                                 # ... and one that starts with it
+            v[40960 - 1] = 1.0; v[40960] = 0.0; v[40961:40999] = 1.0
+        genome.set_chrom(name, v)
+    genome.clump(0.5, L)
+    compare(genome, inputs, lambda v: orc.clump(v, 0.5, L, True), what="clump long runs L=%d" % L)
+    for name, n in CHROMS:
+        genome.set_chrom(name, inputs[name])
+    genome.anticlump(1.5, L, one=7.0, zero=0.5)
+    compare(genome, inputs, lambda v: orc.clump(v, 1.5, L, False, 7.0, 0.5), what="anticlump long runs L=%d" % L)
+
+
 def test_clump_all_below_and_relative_length(genome, orc):
     inputs = load(genome, np.random.default_rng(0), "int")
     genome.clump(1000.0, 10)
