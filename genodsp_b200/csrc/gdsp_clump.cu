@@ -379,25 +379,37 @@ k_clump_c (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, i
 
 // ===========================================================================
 // Fast path (every chromosome's minimum length <= CLF_MAX_HALO): the prefix arrays
-// P and M are never stored.  Pass A2 keeps only one {P,M} carry per 128-cell group
-// (0.125 B/bp); pass B2 rebuilds P and M of its tile and of the `Lmin` cells before
-// it from those carries (the halo is the tail of the previous tile: L2 hits), needs
-// ONE chained scan (the suffix maximum) and leaves two bits per cell (marked,
-// marked-and-qualifying); the trimming of every marked run to its first..last
-// qualifying cell is carry propagation on those bit words -- `fill upwards from the
-// seeds through the mask` is  (M & ~(M + S)) | S  on a 32-cell word, a word passes a
-// carry on like a full adder's generate/propagate pair, and the pairs are folded per
-// tile (k_clump_tilesum), per chromosome (k_clump_tilecarry) and per word
-// (k_clump_emit), in both directions.  DRAM traffic: 8 + 8 + 8 = 24.6 B/bp instead of
-// 66, one look-back chain per pass instead of two.
+// P and M are never stored.
+//   k_clump_groups     every warp folds one 512-cell group to {sum of d, minimum of its
+//                      group-relative prefix sums} -- a pure streaming read, no chain
+//   k_clump_groupscan  one block per chromosome turns those into the carry of every group:
+//                      {P before the group, M before the group}
+//   k_clump_mark       rebuilds P and M of its tile and of the `Lmin` cells before it from
+//                      the carries (the halo is the tail of the previous tile: L2 hits),
+//                      needs ONE chained scan (the suffix maximum) and leaves two bits per
+//                      cell (marked, marked-and-qualifying)
+//   k_clump_tilesum / k_clump_tilecarry / k_clump_emit
+//                      the trimming of every marked run to its first..last qualifying cell
+//                      is carry propagation on those bit words: `fill upwards from the seeds
+//                      through the mask` is (M & ~(M + S)) | S on a 32-cell word, a word
+//                      passes a carry on like a full adder's generate/propagate pair, and
+//                      the pairs are folded per tile, per chromosome and per word, in both
+//                      directions
+// Rounding is monotone, so min_i fl(c + x_i) = fl(c + min_i x_i): the group minima published
+// by the first kernel give exactly the minima of the prefix sums the mark kernel computes
+// (P = carry + group-local prefix, the same association in both kernels).
+// DRAM traffic: 8 + 8 + 8 B/bp (+0.6 of bits and carries) instead of 66, one look-back chain
+// instead of five.
 // ===========================================================================
 #define CLF_MAX_HALO 4096                 // cells; larger minimum lengths take the stored-prefix passes above
-#define CLF_GROUPS   (CL_TILE / 128)      // 32 carry groups per tile
+#define CLF_GROUP    512                  // cells per carry group: one warp, 16 consecutive cells per lane
+#define CLF_GROUPS   (CL_TILE / CLF_GROUP)    // 8
 #define CLF_WORDS    (CL_TILE / 32)       // 128 bit words per tile
 
 struct ClumpFast
 	{
-	double2*       carry;      // per group (tile*32 + row): x = P before the group, y = M before it (0 at a chromosome start)
+	double2*       carry;      // per group (tile*8 + warp): first {group sum, group-relative prefix minimum}, then
+	                           // {P before the group, M before the group} (M includes P[-1] = 0)
 	uint32_t*      Bm;         // per word (tile*128 + w): marked
 	uint32_t*      Bq;         // marked and qualifying (v >= T, <= T for anticlump)
 	unsigned char* tsum;       // per tile: bit0/1 generate/propagate upwards, bit2/3 downwards
@@ -407,13 +419,41 @@ struct ClumpFast
 
 #define CLF_INF (__longlong_as_double (0x7ff0000000000000ll))
 
-// Inclusive prefix sums inside the 128-cell group a warp row holds (lane l: cells 4l..4l+3).  Passes
-// A2 and B2 both use exactly this association, so B2 reproduces A2's prefix sums bit for bit.
-__device__ __forceinline__ void group_sum_scan (double x[4], double& total)
+__device__ __forceinline__ double dmin2 (double a, double b) { return (b < a) ? b : a; }
+__device__ __forceinline__ double dmax2 (double a, double b) { return (b > a) ? b : a; }
+
+// d = v-T (T-v) of the 16 cells of a lane: cells [c0, c0+16) of the signal, `valid` of them inside the tile
+// (the others read as d = 0); returns the bit mask of qualifying cells
+__device__ __forceinline__ unsigned clf_load16 (const double* __restrict__ sig, uint64_t c0, int valid, double T, int above, double x[16])
+	{
+	if (valid >= 16)
+		{
+		#pragma unroll
+		for (int k = 0; k < 16; k += 4) ldg_stream4 (sig + c0 + k, x[k], x[k + 1], x[k + 2], x[k + 3]);
+		}
+	else
+		{
+		#pragma unroll
+		for (int k = 0; k < 16; k++) x[k] = (k < valid) ? sig[c0 + k] : T;
+		}
+	unsigned q = 0;
+	#pragma unroll
+	for (int k = 0; k < 16; k++)
+		{
+		if (k < valid && (above ? (x[k] >= T) : (x[k] <= T))) q |= 1u << k;
+		x[k] = (k < valid) ? (above ? __dsub_rn (x[k], T) : __dsub_rn (T, x[k])) : 0.0;
+		}
+	return q;
+	}
+
+// Inclusive prefix sums inside the 512-cell group a warp holds (lane l: cells 16l..16l+15).  The group
+// and the mark kernel both use exactly this association, so they compute the same values bit for bit.
+__device__ __forceinline__ void group_sum_scan (double x[16], double& total)
 	{
 	const int lane = threadIdx.x & 31;
-	x[1] = x[0] + x[1];  x[2] = x[1] + x[2];  x[3] = x[2] + x[3];
-	double g = x[3];
+	#pragma unroll
+	for (int k = 1; k < 16; k++) x[k] = x[k - 1] + x[k];
+	double g = x[15];
 	#pragma unroll
 	for (int d = 1; d < 32; d <<= 1)
 		{
@@ -423,151 +463,146 @@ __device__ __forceinline__ void group_sum_scan (double x[4], double& total)
 	double ex = shfl_up_f64 (g, 1);
 	if (lane == 0) ex = 0.0;
 	#pragma unroll
-	for (int c = 0; c < 4; c++) x[c] = ex + x[c];
+	for (int k = 0; k < 16; k++) x[k] = ex + x[k];
 	total = shfl_idx_f64 (g, 31);
 	}
 
-__device__ __forceinline__ double dmin2 (double a, double b) { return (b < a) ? b : a; }
-__device__ __forceinline__ double dmax2 (double a, double b) { return (b > a) ? b : a; }
-
-// loads the 4 cells of a lane (cells past `n` read as 0 and are flagged invalid)
-__device__ __forceinline__ void clf_load4 (const double* __restrict__ sig, uint64_t t0, uint32_t e0, uint32_t n, double v[4])
-	{
-	if (e0 + 4 <= n) ldg_stream4 (sig + t0 + e0, v[0], v[1], v[2], v[3]);
-	else
-		{
-		#pragma unroll
-		for (int c = 0; c < 4; c++) v[c] = (e0 + c < n) ? sig[t0 + e0 + c] : 0.0;
-		}
-	}
-
-// ---- pass A2: group carries ------------------------------------------------
+// ---- group aggregates ----------------------------------------------------------
 __global__ void __launch_bounds__(CL_THREADS, 4)
-k_clump_carry (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
-               const double* __restrict__ sig, double T, int above, ClumpFast wk,
-               ScanStatus<double> stSum, ScanStatus<double> stMin)
+k_clump_groups (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
+                const double* __restrict__ sig, double T, int above, ClumpFast wk)
 	{
-	__shared__ double s_warp[CL_WARPS];
-	__shared__ double s_carry[2];
-	__shared__ int    s_anyNonNeg;
-	const uint32_t tile = scan_take_ticket (stSum.ticket);
+	const uint64_t tile = blockIdx.x;
 	int seg;  uint64_t tis;
 	tile_to_seg (base, nseg, tile, seg, tis);
 	const SegDev sd = segs[seg];
 	const uint64_t t0 = sd.lo + tis * CL_TILE;
 	const uint32_t n  = (uint32_t) ((sd.hi - t0 < CL_TILE) ? (sd.hi - t0) : CL_TILE);
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	if (threadIdx.x == 0) s_anyNonNeg = 0;
-	__syncthreads ();
+	const uint32_t e0 = warp * CLF_GROUP + lane * 16;
+	const int valid = (e0 >= n) ? 0 : (int) ((n - e0 < 16) ? (n - e0) : 16);
 
-	double x[CL_ROWS][4], tot[CL_ROWS];
+	double x[16], total;
+	clf_load16 (sig, t0 + e0, valid, T, above, x);
 	bool nonNeg = false;
 	#pragma unroll
-	for (int r = 0; r < CL_ROWS; r++)
-		{
-		const uint32_t e0 = cl_elem (warp, lane, r, 0);
-		double v[4];
-		clf_load4 (sig, t0, e0, n, v);
-		#pragma unroll
-		for (int c = 0; c < 4; c++)
-			{
-			double d = 0.0;
-			if (e0 + c < n)
-				{
-				d = above ? __dsub_rn (v[c], T) : __dsub_rn (T, v[c]);
-				if (d >= 0.0) nonNeg = true;
-				}
-			x[r][c] = d;
-			}
-		group_sum_scan (x[r], tot[r]);
-		}
-	if (nonNeg) s_anyNonNeg = 1;
-
-	// sums of the rows before row r inside this warp, of the warps before this one, of the tiles before this one
-	double rc[CL_ROWS];
-	rc[0] = 0.0;
+	for (int k = 0; k < 16; k++) if (k < valid && x[k] >= 0.0) nonNeg = true;
+	group_sum_scan (x, total);
+	double m = CLF_INF;
 	#pragma unroll
-	for (int r = 1; r < CL_ROWS; r++) rc[r] = rc[r - 1] + tot[r - 1];
-	if (lane == 0) s_warp[warp] = rc[CL_ROWS - 1] + tot[CL_ROWS - 1];
-	__syncthreads ();
-	double warpExcl = 0.0, tileAgg = 0.0;
+	for (int k = 0; k < 16; k++) if (k < valid) m = dmin2 (m, x[k]);
 	#pragma unroll
-	for (int w = 0; w < CL_WARPS; w++)
+	for (int d = 16; d >= 1; d >>= 1) m = dmin2 (m, shfl_xor_f64 (m, d));
+	const bool any = __any_sync (0xffffffffu, nonNeg);
+	if (lane == 0)
 		{
-		const double t = s_warp[w];
-		if (w < warp) warpExcl = warpExcl + t;
-		tileAgg = tileAgg + t;
-		}
-	if (threadIdx.x < 32)
-		{
-		const double e = scan_lookback<double> (stSum, tile, tis == 0, tileAgg, 0.0, [] (double a, double b) { return a + b; });
-		if (threadIdx.x == 0)
-			{
-			s_carry[0] = e;
-			if (s_anyNonNeg) atomicAnd (&wk.segAllNeg[seg], 0);
-			}
-		}
-	__syncthreads ();                                  // also: every warp has read s_warp
-	const double addP = s_carry[0] + warpExcl;
-
-	// minimum of the prefix sums of every group
-	double gP[CL_ROWS], rowMin[CL_ROWS];
-	#pragma unroll
-	for (int r = 0; r < CL_ROWS; r++)
-		{
-		gP[r] = addP + rc[r];
-		const uint32_t e0 = cl_elem (warp, lane, r, 0);
-		double m = CLF_INF;
-		#pragma unroll
-		for (int c = 0; c < 4; c++)
-			if (e0 + c < n) m = dmin2 (m, gP[r] + x[r][c]);
-		#pragma unroll
-		for (int d = 16; d >= 1; d >>= 1) m = dmin2 (m, shfl_xor_f64 (m, d));
-		rowMin[r] = m;
-		}
-	double rm[CL_ROWS];
-	rm[0] = CLF_INF;
-	#pragma unroll
-	for (int r = 1; r < CL_ROWS; r++) rm[r] = dmin2 (rm[r - 1], rowMin[r - 1]);
-	if (lane == 0) s_warp[warp] = dmin2 (rm[CL_ROWS - 1], rowMin[CL_ROWS - 1]);
-	__syncthreads ();
-	double wExM = CLF_INF, tAggM = CLF_INF;
-	#pragma unroll
-	for (int w = 0; w < CL_WARPS; w++)
-		{
-		const double t = s_warp[w];
-		if (w < warp) wExM = dmin2 (wExM, t);
-		tAggM = dmin2 (tAggM, t);
-		}
-	if (threadIdx.x < 32)
-		{
-		const double e = scan_lookback<double> (stMin, tile, tis == 0, tAggM, CLF_INF, [] (double a, double b) { return (b < a) ? b : a; });
-		if (threadIdx.x == 0) s_carry[1] = e;
-		}
-	__syncthreads ();
-	const double addM = dmin2 (dmin2 (s_carry[1], wExM), 0.0);      // P[-1] = 0 takes part in every prefix minimum
-
-	if (lane < CL_ROWS)
-		{
-		double p = gP[0], m = rm[0];
-		#pragma unroll
-		for (int r = 1; r < CL_ROWS; r++) if (lane == r) { p = gP[r];  m = rm[r]; }
-		wk.carry[(uint64_t) tile * CLF_GROUPS + warp * CL_ROWS + lane] = make_double2 (p, dmin2 (addM, m));
+		wk.carry[tile * CLF_GROUPS + warp] = make_double2 (total, m);
+		// clump.c:545-565; the flag is read first: 6 M atomics on 24 addresses would serialise
+		if (any && *((volatile int*) &wk.segAllNeg[seg]) != 0) atomicAnd (&wk.segAllNeg[seg], 0);
 		}
 	}
 
-// ---- pass B2: marks ----------------------------------------------------------
-// shared-memory slot of the prefix minimum of the cell `jj` cells after the first halo cell: row-major
-// groups of 128, cell 4l+c of a group at c*32+l (64-bit accesses of a warp are then conflict-free both
-// when a row is written and when it is read back shifted by Lmin)
-__device__ __forceinline__ uint32_t clf_slot (uint32_t jj) { return (jj & ~127u) | ((jj & 3u) << 5) | ((jj & 127u) >> 2); }
+// ---- group carries: one block per chromosome -------------------------------------
+#define CLF_GS_THREADS 1024
+__global__ void __launch_bounds__(CLF_GS_THREADS)
+k_clump_groupscan (const uint64_t* __restrict__ base, ClumpFast wk)
+	{
+	__shared__ double s_w[32];
+	const uint64_t g0 = base[blockIdx.x] * CLF_GROUPS, g1 = base[blockIdx.x + 1] * CLF_GROUPS;
+	const uint64_t chunk = (g1 - g0 + CLF_GS_THREADS - 1) / CLF_GS_THREADS;
+	const uint64_t lo = (g0 + threadIdx.x * chunk < g1) ? g0 + threadIdx.x * chunk : g1;
+	const uint64_t hi = (lo + chunk < g1) ? lo + chunk : g1;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+	// 1: sum of the chunk, exclusive prefix over the block
+	double sum = 0.0;
+	for (uint64_t g = lo; g < hi; g++) sum = sum + wk.carry[g].x;
+	double inc = sum;
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1)
+		{
+		const double up = shfl_up_f64 (inc, d);
+		if (lane >= d) inc = up + inc;
+		}
+	if (lane == 31) s_w[warp] = inc;
+	__syncthreads ();
+	double wex = 0.0;
+	for (int w = 0; w < warp; w++) wex = wex + s_w[w];
+	double ex = shfl_up_f64 (inc, 1);
+	if (lane == 0) ex = 0.0;
+	const double run0 = wex + ex;                      // P before the chunk
+	__syncthreads ();
+
+	// 2: minimum prefix sum inside the chunk, exclusive prefix minimum over the block
+	double run = run0, mn = CLF_INF;
+	for (uint64_t g = lo; g < hi; g++)
+		{
+		const double2 a = wk.carry[g];
+		mn = dmin2 (mn, run + a.y);
+		run = run + a.x;
+		}
+	double minc = mn;
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1)
+		{
+		const double up = shfl_up_f64 (minc, d);
+		if (lane >= d) minc = dmin2 (up, minc);
+		}
+	if (lane == 31) s_w[warp] = minc;
+	__syncthreads ();
+	double mex = 0.0;                                  // P[-1] = 0 takes part in every prefix minimum
+	for (int w = 0; w < warp; w++) mex = dmin2 (mex, s_w[w]);
+	double e2 = shfl_up_f64 (minc, 1);
+	if (lane != 0) mex = dmin2 (mex, e2);
+
+	// 3: carries, in place
+	run = run0;
+	for (uint64_t g = lo; g < hi; g++)
+		{
+		const double2 a = wk.carry[g];
+		wk.carry[g] = make_double2 (run, mex);
+		mex = dmin2 (mex, run + a.y);
+		run = run + a.x;
+		}
+	}
+
+// ---- marks ---------------------------------------------------------------------
+// shared-memory slot of the prefix minimum of the cell `j` cells after the first halo cell: one pad per
+// 16 cells, so that lanes 16 cells apart are 17 slots apart (conflict-free 64-bit accesses both when a
+// lane writes its own cells and when it reads cells shifted by Lmin)
+__device__ __forceinline__ uint32_t clf_slot (uint32_t j) { return j + (j >> 4); }
+
+// prefix minima of a group's prefix sums P[k] (cells past `valid` are skipped), including the carry
+__device__ __forceinline__ void clf_group_min_store (const double P[16], int valid, double carryM, double* s_row)
+	{
+	const int lane = threadIdx.x & 31;
+	double m = CLF_INF;
+	#pragma unroll
+	for (int k = 0; k < 16; k++) if (k < valid) m = dmin2 (m, P[k]);
+	double g = m;
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1)
+		{
+		const double up = shfl_up_f64 (g, d);
+		if (lane >= d) g = dmin2 (up, g);
+		}
+	double ex = shfl_up_f64 (g, 1);
+	if (lane == 0) ex = CLF_INF;
+	m = dmin2 (ex, carryM);                            // everything before this lane's cells
+	#pragma unroll
+	for (int k = 0; k < 16; k++)
+		{
+		if (k < valid) m = dmin2 (m, P[k]);
+		s_row[lane * 17 + k] = m;
+		}
+	}
 
 __global__ void __launch_bounds__(CL_THREADS, 4)
 k_clump_mark (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg, uint64_t ntiles,
               const double* __restrict__ sig, double T, int above, uint32_t minLength, double relLength,
               ClumpFast wk, ScanStatus<double> stMax)
 	{
-	extern __shared__ double s_M[];                    // (hrows + 32) * 128 prefix minima
+	extern __shared__ double s_M[];                    // (hrows + 8) * 544 prefix minima
 	__shared__ double s_warp[CL_WARPS];
 	__shared__ double s_carryD;
 	// reversed tile order: ticket k handles the k-th tile from the END of the launch, so that every tile a
@@ -591,125 +626,63 @@ k_clump_mark (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base
 		if (rl > Lmin) Lmin = rl;
 		}
 	const uint32_t reach = (Lmin > 0) ? Lmin : 1;                 // M[p-1] is needed even when Lmin is 0
-	const uint32_t hrows = (reach + 127) >> 7;                    // <= CLF_MAX_HALO / 128 (the host checked)
-	const uint32_t hcells = hrows << 7;
+	const uint32_t hrows = (reach + CLF_GROUP - 1) / CLF_GROUP;   // <= 8 (the host checked): at most one per warp
+	const uint32_t hcells = hrows * CLF_GROUP;
 
-	// prefix minima of the halo rows (the tail of the previous tile(s) of this chromosome)
-	for (uint32_t h = warp; h < hrows; h += CL_WARPS)
+	// prefix minima of the halo groups (the tail of the previous tile of this chromosome)
+	if ((uint32_t) warp < hrows && (uint64_t) (hrows - warp) * CLF_GROUP <= tis * CL_TILE)
 		{
-		const uint64_t back = (uint64_t) (hrows - h) * 128;       // cells between the row's first cell and t0
-		if (back > tis * CL_TILE) continue;                       // before the chromosome's first cell
-		const uint64_t c0 = t0 - back + lane * 4;
-		double x[4], tot;
-		ldg_stream4 (sig + c0, x[0], x[1], x[2], x[3]);
-		#pragma unroll
-		for (int c = 0; c < 4; c++) x[c] = above ? __dsub_rn (x[c], T) : __dsub_rn (T, x[c]);
+		const uint32_t back = (hrows - warp) * CLF_GROUP;         // cells between the group's first cell and t0
+		double x[16], tot;
+		clf_load16 (sig, t0 - back + lane * 16, 16, T, above, x);
 		group_sum_scan (x, tot);
-		const double2 cr = wk.carry[tile * CLF_GROUPS - (hrows - h)];
-		double m = CLF_INF;
+		const double2 cr = wk.carry[tile * CLF_GROUPS - (hrows - warp)];
 		#pragma unroll
-		for (int c = 0; c < 4; c++) { m = dmin2 (m, cr.x + x[c]);  x[c] = m; }     // thread-local prefix minima
-		double g = m;
-		#pragma unroll
-		for (int d = 1; d < 32; d <<= 1)
-			{
-			const double up = shfl_up_f64 (g, d);
-			if (lane >= d) g = dmin2 (up, g);
-			}
-		double ex = shfl_up_f64 (g, 1);
-		if (lane == 0) ex = CLF_INF;
-		ex = dmin2 (ex, cr.y);
-		#pragma unroll
-		for (int c = 0; c < 4; c++) s_M[h * 128 + c * 32 + lane] = dmin2 (ex, x[c]);
+		for (int k = 0; k < 16; k++) x[k] = cr.x + x[k];
+		clf_group_min_store (x, 16, cr.y, s_M + warp * (CLF_GROUP / 16 * 17));
 		}
 
-	// own rows: P stays in registers, M goes to shared memory
-	double P[CL_ROWS][4];
-	unsigned qualNib[CL_ROWS];
-	#pragma unroll
-	for (int r = 0; r < CL_ROWS; r++)
+	// own group: P stays in registers, M goes to shared memory
+	const uint32_t e0 = warp * CLF_GROUP + lane * 16;
+	const int valid = (e0 >= n) ? 0 : (int) ((n - e0 < 16) ? (n - e0) : 16);
+	double P[16];
+	unsigned qual;
 		{
-		const uint32_t e0 = cl_elem (warp, lane, r, 0);
-		double v[4], tot;
-		clf_load4 (sig, t0, e0, n, v);
-		unsigned qn = 0;
+		double tot;
+		qual = clf_load16 (sig, t0 + e0, valid, T, above, P);
+		group_sum_scan (P, tot);
+		const double2 cr = wk.carry[tile * CLF_GROUPS + warp];
 		#pragma unroll
-		for (int c = 0; c < 4; c++)
-			{
-			const bool in = (e0 + c < n);
-			if (in && (above ? (v[c] >= T) : (v[c] <= T))) qn |= 1u << c;
-			P[r][c] = in ? (above ? __dsub_rn (v[c], T) : __dsub_rn (T, v[c])) : 0.0;
-			}
-		qualNib[r] = qn;
-		group_sum_scan (P[r], tot);
-		const double2 cr = wk.carry[tile * CLF_GROUPS + warp * CL_ROWS + r];
-		double x[4], m = CLF_INF;
-		#pragma unroll
-		for (int c = 0; c < 4; c++)
-			{
-			P[r][c] = cr.x + P[r][c];
-			if (e0 + c < n) m = dmin2 (m, P[r][c]);
-			x[c] = m;
-			}
-		double g = m;
-		#pragma unroll
-		for (int d = 1; d < 32; d <<= 1)
-			{
-			const double up = shfl_up_f64 (g, d);
-			if (lane >= d) g = dmin2 (up, g);
-			}
-		double ex = shfl_up_f64 (g, 1);
-		if (lane == 0) ex = CLF_INF;
-		ex = dmin2 (ex, cr.y);
-		#pragma unroll
-		for (int c = 0; c < 4; c++) s_M[hcells + (warp * CL_ROWS + r) * 128 + c * 32 + lane] = dmin2 (ex, x[c]);
+		for (int k = 0; k < 16; k++) P[k] = cr.x + P[k];
+		clf_group_min_store (P, valid, cr.y, s_M + (hrows + warp) * (CLF_GROUP / 16 * 17));
 		}
 	__syncthreads ();
 
-	// q = P where the cell is a valid end, -inf elsewhere
+	// q = P where the cell is a valid end, -inf elsewhere; then its suffix maximum inside the lane
+	const uint64_t i0 = tis * CL_TILE + e0;                       // index of the lane's first cell inside the chromosome
 	#pragma unroll
-	for (int r = 0; r < CL_ROWS; r++)
-		#pragma unroll
-		for (int c = 0; c < 4; c++)
-			{
-			const uint32_t e = cl_elem (warp, lane, r, c);
-			double qq = NEG;
-			if (e < n)
-				{
-				const uint64_t i = tis * CL_TILE + e;                    // index inside the chromosome
-				if (i + 1 >= (uint64_t) Lmin)
-					{
-					const double mj = (i >= (uint64_t) Lmin) ? s_M[clf_slot (hcells + e - Lmin)] : 0.0;     // M[i-Lmin], M[-1] = 0
-					if (mj <= P[r][c]) qq = P[r][c];
-					}
-				}
-			P[r][c] = qq;
-			}
-
-	// suffix maximum of q: inside the thread, the row, the warp (rows 3..0), the tile (warps 7..0), the chromosome
-	double rowTot[CL_ROWS];
-	#pragma unroll
-	for (int r = 0; r < CL_ROWS; r++)
+	for (int k = 0; k < 16; k++)
 		{
-		P[r][2] = dmax2 (P[r][2], P[r][3]);  P[r][1] = dmax2 (P[r][1], P[r][2]);  P[r][0] = dmax2 (P[r][0], P[r][1]);
-		double g = P[r][0];
-		#pragma unroll
-		for (int d = 1; d < 32; d <<= 1)
+		double qq = NEG;
+		if (k < valid && i0 + k + 1 >= (uint64_t) Lmin)
 			{
-			const double dn = shfl_down_f64 (g, d);
-			if (lane + d < 32) g = dmax2 (g, dn);
+			const double mj = (i0 + k >= (uint64_t) Lmin) ? s_M[clf_slot (hcells + e0 + k - Lmin)] : 0.0;     // M[i-Lmin], M[-1] = 0
+			if (mj <= P[k]) qq = P[k];
 			}
-		double ex = shfl_down_f64 (g, 1);
-		if (lane == 31) ex = NEG;
-		#pragma unroll
-		for (int c = 0; c < 4; c++) P[r][c] = dmax2 (P[r][c], ex);
-		rowTot[r] = shfl_idx_f64 (g, 0);
+		P[k] = qq;
 		}
-	double rcar[CL_ROWS];
-	rcar[CL_ROWS - 1] = NEG;
 	#pragma unroll
-	for (int r = CL_ROWS - 2; r >= 0; r--) rcar[r] = dmax2 (rcar[r + 1], rowTot[r + 1]);
-	if (lane == 0) s_warp[warp] = dmax2 (rcar[0], rowTot[0]);
+	for (int k = 14; k >= 0; k--) P[k] = dmax2 (P[k], P[k + 1]);
+	double g = P[0];
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1)
+		{
+		const double dn = shfl_down_f64 (g, d);
+		if (lane + d < 32) g = dmax2 (g, dn);
+		}
+	double ex = shfl_down_f64 (g, 1);
+	if (lane == 31) ex = NEG;
+	if (lane == 0) s_warp[warp] = g;
 	__syncthreads ();
 	double wEx = NEG, tAgg = NEG;
 	#pragma unroll
@@ -725,34 +698,24 @@ k_clump_mark (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base
 		if (threadIdx.x == 0) s_carryD = e;
 		}
 	__syncthreads ();
-	const double carryQ = dmax2 (s_carryD, wEx);
+	const double cq = dmax2 (dmax2 (s_carryD, wEx), ex);          // everything after this lane's cells
 
-	// two bits per cell, 32 cells per word (8 lanes of a row share a word)
+	// two bits per cell; a 32-cell word is shared by two lanes
+	unsigned mk = 0;
 	#pragma unroll
-	for (int r = 0; r < CL_ROWS; r++)
+	for (int k = 0; k < 16; k++)
+		if (k < valid)
+			{
+			const double mp = (i0 + k == 0) ? 0.0 : s_M[clf_slot (hcells + e0 + k - 1)];      // M[p-1], M[-1] = 0
+			if (dmax2 (cq, P[k]) >= mp) mk |= 1u << k;
+			}
+	unsigned wm = mk << ((lane & 1) * 16), wq = (mk & qual) << ((lane & 1) * 16);
+	wm |= __shfl_xor_sync (0xffffffffu, wm, 1);
+	wq |= __shfl_xor_sync (0xffffffffu, wq, 1);
+	if ((lane & 1) == 0)
 		{
-		const uint32_t e0 = cl_elem (warp, lane, r, 0);
-		const double cq = dmax2 (carryQ, rcar[r]);
-		unsigned mk = 0;
-		#pragma unroll
-		for (int c = 0; c < 4; c++)
-			if (e0 + c < n)
-				{
-				const double mp = (tis == 0 && e0 + c == 0) ? 0.0 : s_M[clf_slot (hcells + e0 + c - 1)];      // M[p-1], M[-1] = 0
-				if (dmax2 (cq, P[r][c]) >= mp) mk |= 1u << c;
-				}
-		unsigned wm = mk << ((lane & 7) * 4), wq = (mk & qualNib[r]) << ((lane & 7) * 4);
-		#pragma unroll
-		for (int d = 1; d <= 4; d <<= 1)
-			{
-			wm |= __shfl_xor_sync (0xffffffffu, wm, d);
-			wq |= __shfl_xor_sync (0xffffffffu, wq, d);
-			}
-		if ((lane & 7) == 0)
-			{
-			const uint64_t w = tile * CLF_WORDS + (warp * CL_ROWS + r) * 4 + (lane >> 3);
-			wk.Bm[w] = wm;  wk.Bq[w] = wq;
-			}
+		const uint64_t w = tile * CLF_WORDS + warp * (CLF_GROUP / 32) + (lane >> 1);
+		wk.Bm[w] = wm;  wk.Bq[w] = wq;
 		}
 	}
 
@@ -945,7 +908,7 @@ extern "C" int gdsp_clump (gdsp_ctx* c, const gdsp_layout* L_, double* sig, uint
 		wf.tcin = (unsigned char*) p;       p += (((size_t) tm.ntiles + 255) / 256) * 256;
 		wf.segAllNeg = (int*) p;
 		const uint32_t reach = maxLmin ? maxLmin : 1;
-		const size_t smem = ((size_t) ((reach + 127) / 128) + CLF_GROUPS) * 128 * sizeof (double);
+		const size_t smem = ((size_t) ((reach + CLF_GROUP - 1) / CLF_GROUP) + CLF_GROUPS) * (CLF_GROUP / 16 * 17) * sizeof (double);
 		static size_t smemSet = 0;
 		if (smem > smemSet)
 			{
@@ -955,10 +918,9 @@ extern "C" int gdsp_clump (gdsp_ctx* c, const gdsp_layout* L_, double* sig, uint
 
 		k_fill_int<<<(L->nseg + 255) / 256, 256, 0, c->stream>>> (wf.segAllNeg, L->nseg, 1);
 		GDSP_KERNEL_CHECK ();
-		GDSP_CUDA (cudaMemsetAsync (ws1, 0, scan_status_clear_bytes<double> (tm.ntiles), c->stream));
-		GDSP_CUDA (cudaMemsetAsync (ws2, 0, scan_status_clear_bytes<double> (tm.ntiles), c->stream));
-		k_clump_carry<<<(unsigned) tm.ntiles, CL_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, sig, average, above ? 1 : 0, wf,
-		        scan_status_carve<double> (ws1, tm.ntiles), scan_status_carve<double> (ws2, tm.ntiles));
+		k_clump_groups<<<(unsigned) tm.ntiles, CL_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, sig, average, above ? 1 : 0, wf);
+		GDSP_KERNEL_CHECK ();
+		k_clump_groupscan<<<L->nseg, CLF_GS_THREADS, 0, c->stream>>> (tm.d_base, wf);
 		GDSP_KERNEL_CHECK ();
 		GDSP_CUDA (cudaMemsetAsync (ws1, 0, scan_status_clear_bytes<double> (tm.ntiles), c->stream));
 		k_clump_mark<<<(unsigned) tm.ntiles, CL_THREADS, smem, c->stream>>> (L->d, tm.d_base, L->nseg, tm.ntiles, sig, average, above ? 1 : 0,
