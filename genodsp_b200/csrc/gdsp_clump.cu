@@ -422,11 +422,13 @@ struct ClumpFast
 __device__ __forceinline__ double dmin2 (double a, double b) { return (b < a) ? b : a; }
 __device__ __forceinline__ double dmax2 (double a, double b) { return (b > a) ? b : a; }
 
-// d = v-T (T-v) of the 16 cells of a lane: cells [c0, c0+16) of the signal, `valid` of them inside the tile
-// (the others read as d = 0); returns the bit mask of qualifying cells
-__device__ __forceinline__ unsigned clf_load16 (const double* __restrict__ sig, uint64_t c0, int valid, double T, int above, double x[16])
+// d = v-T (T-v for anticlump) of the 16 cells of a lane: cells [c0, c0+16) of the signal, `valid` of them
+// inside the tile (the others read as d = 0); returns the bit mask of qualifying cells (v >= T, resp.
+// v <= T, which is d >= 0: a difference of two distinct doubles never rounds to zero)
+template <bool FULL, bool ABOVE>
+__device__ __forceinline__ unsigned clf_load16 (const double* __restrict__ sig, uint64_t c0, int valid, double T, double x[16])
 	{
-	if (valid >= 16)
+	if (FULL || valid >= 16)
 		{
 		#pragma unroll
 		for (int k = 0; k < 16; k += 4) ldg_stream4 (sig + c0 + k, x[k], x[k + 1], x[k + 2], x[k + 3]);
@@ -440,8 +442,9 @@ __device__ __forceinline__ unsigned clf_load16 (const double* __restrict__ sig, 
 	#pragma unroll
 	for (int k = 0; k < 16; k++)
 		{
-		if (k < valid && (above ? (x[k] >= T) : (x[k] <= T))) q |= 1u << k;
-		x[k] = (k < valid) ? (above ? __dsub_rn (x[k], T) : __dsub_rn (T, x[k])) : 0.0;
+		x[k] = ABOVE ? __dsub_rn (x[k], T) : __dsub_rn (T, x[k]);
+		if (!FULL && k >= valid) x[k] = 0.0;
+		else if (x[k] >= 0.0) q |= 1u << k;
 		}
 	return q;
 	}
@@ -468,9 +471,10 @@ __device__ __forceinline__ void group_sum_scan (double x[16], double& total)
 	}
 
 // ---- group aggregates ----------------------------------------------------------
+template <bool ABOVE>
 __global__ void __launch_bounds__(CL_THREADS, 4)
 k_clump_groups (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
-                const double* __restrict__ sig, double T, int above, ClumpFast wk)
+                const double* __restrict__ sig, double T, ClumpFast wk)
 	{
 	const uint64_t tile = blockIdx.x;
 	int seg;  uint64_t tis;
@@ -483,17 +487,14 @@ k_clump_groups (const SegDev* __restrict__ segs, const uint64_t* __restrict__ ba
 	const int valid = (e0 >= n) ? 0 : (int) ((n - e0 < 16) ? (n - e0) : 16);
 
 	double x[16], total;
-	clf_load16 (sig, t0 + e0, valid, T, above, x);
-	bool nonNeg = false;
-	#pragma unroll
-	for (int k = 0; k < 16; k++) if (k < valid && x[k] >= 0.0) nonNeg = true;
+	const unsigned q = clf_load16<false, ABOVE> (sig, t0 + e0, valid, T, x);
 	group_sum_scan (x, total);
 	double m = CLF_INF;
 	#pragma unroll
 	for (int k = 0; k < 16; k++) if (k < valid) m = dmin2 (m, x[k]);
 	#pragma unroll
 	for (int d = 16; d >= 1; d >>= 1) m = dmin2 (m, shfl_xor_f64 (m, d));
-	const bool any = __any_sync (0xffffffffu, nonNeg);
+	const bool any = __any_sync (0xffffffffu, q != 0);
 	if (lane == 0)
 		{
 		wk.carry[tile * CLF_GROUPS + warp] = make_double2 (total, m);
@@ -573,12 +574,13 @@ k_clump_groupscan (const uint64_t* __restrict__ base, ClumpFast wk)
 __device__ __forceinline__ uint32_t clf_slot (uint32_t j) { return j + (j >> 4); }
 
 // prefix minima of a group's prefix sums P[k] (cells past `valid` are skipped), including the carry
+template <bool FULL>
 __device__ __forceinline__ void clf_group_min_store (const double P[16], int valid, double carryM, double* s_row)
 	{
 	const int lane = threadIdx.x & 31;
 	double m = CLF_INF;
 	#pragma unroll
-	for (int k = 0; k < 16; k++) if (k < valid) m = dmin2 (m, P[k]);
+	for (int k = 0; k < 16; k++) if (FULL || k < valid) m = dmin2 (m, P[k]);
 	double g = m;
 	#pragma unroll
 	for (int d = 1; d < 32; d <<= 1)
@@ -592,81 +594,61 @@ __device__ __forceinline__ void clf_group_min_store (const double P[16], int val
 	#pragma unroll
 	for (int k = 0; k < 16; k++)
 		{
-		if (k < valid) m = dmin2 (m, P[k]);
+		if (FULL || k < valid) m = dmin2 (m, P[k]);
 		s_row[lane * 17 + k] = m;
 		}
 	}
 
-__global__ void __launch_bounds__(CL_THREADS, 4)
-k_clump_mark (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg, uint64_t ntiles,
-              const double* __restrict__ sig, double T, int above, uint32_t minLength, double relLength,
-              ClumpFast wk, ScanStatus<double> stMax)
+// FAST: the tile is whole and at least Lmin cells away from the chromosome's first cell -- every cell is
+// valid and no index test is needed (all but the first and last tiles of a chromosome)
+template <bool FAST, bool ABOVE>
+__device__ __forceinline__ void clf_mark_tile (const double* __restrict__ sig, double T, const ClumpFast& wk, const ScanStatus<double>& stMax,
+                                               double* s_M, double* s_warp, double* s_carryD,
+                                               uint64_t tile, uint32_t ticket, bool firstOfScan, uint64_t tis, uint64_t t0, uint32_t n,
+                                               uint32_t Lmin, uint32_t hrows)
 	{
-	extern __shared__ double s_M[];                    // (hrows + 8) * 544 prefix minima
-	__shared__ double s_warp[CL_WARPS];
-	__shared__ double s_carryD;
-	// reversed tile order: ticket k handles the k-th tile from the END of the launch, so that every tile a
-	// block waits on (the tiles to its right) has already started
-	const uint32_t ticket = scan_take_ticket (stMax.ticket);
-	const uint64_t tile = ntiles - 1 - ticket;
-	int seg;  uint64_t tis;
-	tile_to_seg (base, nseg, tile, seg, tis);
-	const SegDev sd = segs[seg];
-	const uint64_t tilesInSeg = base[seg + 1] - base[seg];
-	const uint64_t t0 = sd.lo + tis * CL_TILE;
-	const uint32_t n  = (uint32_t) ((sd.hi - t0 < CL_TILE) ? (sd.hi - t0) : CL_TILE);
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const double NEG = -CLF_INF;
-	const bool firstOfScan = (tis == tilesInSeg - 1);
-
-	uint32_t Lmin = minLength;
-	if (relLength > 0.0)
-		{
-		uint32_t rl = (uint32_t) (relLength * sd.chromLen);       // clump.c:516-522
-		if (rl > Lmin) Lmin = rl;
-		}
-	const uint32_t reach = (Lmin > 0) ? Lmin : 1;                 // M[p-1] is needed even when Lmin is 0
-	const uint32_t hrows = (reach + CLF_GROUP - 1) / CLF_GROUP;   // <= 8 (the host checked): at most one per warp
 	const uint32_t hcells = hrows * CLF_GROUP;
-
-	// prefix minima of the halo groups (the tail of the previous tile of this chromosome)
-	if ((uint32_t) warp < hrows && (uint64_t) (hrows - warp) * CLF_GROUP <= tis * CL_TILE)
-		{
-		const uint32_t back = (hrows - warp) * CLF_GROUP;         // cells between the group's first cell and t0
-		double x[16], tot;
-		clf_load16 (sig, t0 - back + lane * 16, 16, T, above, x);
-		group_sum_scan (x, tot);
-		const double2 cr = wk.carry[tile * CLF_GROUPS - (hrows - warp)];
-		#pragma unroll
-		for (int k = 0; k < 16; k++) x[k] = cr.x + x[k];
-		clf_group_min_store (x, 16, cr.y, s_M + warp * (CLF_GROUP / 16 * 17));
-		}
 
 	// own group: P stays in registers, M goes to shared memory
 	const uint32_t e0 = warp * CLF_GROUP + lane * 16;
-	const int valid = (e0 >= n) ? 0 : (int) ((n - e0 < 16) ? (n - e0) : 16);
+	const int valid = FAST ? 16 : ((e0 >= n) ? 0 : (int) ((n - e0 < 16) ? (n - e0) : 16));
 	double P[16];
 	unsigned qual;
+	double* const ownRow = s_M + (hrows + warp) * (CLF_GROUP / 16 * 17) + lane * 17;
 		{
 		double tot;
-		qual = clf_load16 (sig, t0 + e0, valid, T, above, P);
+		qual = clf_load16<FAST, ABOVE> (sig, t0 + e0, valid, T, P);
 		group_sum_scan (P, tot);
 		const double2 cr = wk.carry[tile * CLF_GROUPS + warp];
 		#pragma unroll
 		for (int k = 0; k < 16; k++) P[k] = cr.x + P[k];
-		clf_group_min_store (P, valid, cr.y, s_M + (hrows + warp) * (CLF_GROUP / 16 * 17));
+		clf_group_min_store<FAST> (P, valid, cr.y, s_M + (hrows + warp) * (CLF_GROUP / 16 * 17));
 		}
 	__syncthreads ();
 
-	// q = P where the cell is a valid end, -inf elsewhere; then its suffix maximum inside the lane
+	// q = P where the cell is a valid end, -inf elsewhere; then its suffix maximum inside the lane.
+	// The cell Lmin before cell k of this lane: slot(J0 + k), J0 = hcells + e0 - Lmin = A + r0 with A a
+	// multiple of 16 and r0 = (-Lmin) mod 16 the same for every lane, so slot = slot(A) + u + (u >> 4),
+	// u = r0 + k: the per-cell part of the address is warp-uniform
+	const uint32_t r0 = (0u - Lmin) & 15u;
+	const uint32_t A = hcells + e0 - Lmin - r0;
+	const double* const shifted = s_M + A + (A >> 4);
 	const uint64_t i0 = tis * CL_TILE + e0;                       // index of the lane's first cell inside the chromosome
 	#pragma unroll
 	for (int k = 0; k < 16; k++)
 		{
 		double qq = NEG;
-		if (k < valid && i0 + k + 1 >= (uint64_t) Lmin)
+		if (FAST)
 			{
-			const double mj = (i0 + k >= (uint64_t) Lmin) ? s_M[clf_slot (hcells + e0 + k - Lmin)] : 0.0;     // M[i-Lmin], M[-1] = 0
+			const uint32_t u = r0 + k;
+			if (shifted[u + (u >> 4)] <= P[k]) qq = P[k];
+			}
+		else if (k < valid && i0 + k + 1 >= (uint64_t) Lmin)
+			{
+			const uint32_t u = r0 + k;
+			const double mj = (i0 + k >= (uint64_t) Lmin) ? shifted[u + (u >> 4)] : 0.0;     // M[i-Lmin], M[-1] = 0
 			if (mj <= P[k]) qq = P[k];
 			}
 		P[k] = qq;
@@ -695,18 +677,20 @@ k_clump_mark (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base
 	if (threadIdx.x < 32)
 		{
 		const double e = scan_lookback<double> (stMax, ticket, firstOfScan, tAgg, NEG, [] (double a, double b) { return (b > a) ? b : a; });
-		if (threadIdx.x == 0) s_carryD = e;
+		if (threadIdx.x == 0) *s_carryD = e;
 		}
 	__syncthreads ();
-	const double cq = dmax2 (dmax2 (s_carryD, wEx), ex);          // everything after this lane's cells
+	const double cq = dmax2 (dmax2 (*s_carryD, wEx), ex);         // everything after this lane's cells
 
-	// two bits per cell; a 32-cell word is shared by two lanes
+	// two bits per cell; a 32-cell word is shared by two lanes.  M[p-1] of cell k >= 1 is the slot before
+	// its own; of cell 0 it is the last slot of the previous lane's 16 (one pad in between)
 	unsigned mk = 0;
 	#pragma unroll
 	for (int k = 0; k < 16; k++)
-		if (k < valid)
+		if (FAST || k < valid)
 			{
-			const double mp = (i0 + k == 0) ? 0.0 : s_M[clf_slot (hcells + e0 + k - 1)];      // M[p-1], M[-1] = 0
+			double mp = (k == 0) ? ownRow[-2] : ownRow[k - 1];
+			if (!FAST && i0 + k == 0) mp = 0.0;                   // M[-1] = 0
 			if (dmax2 (cq, P[k]) >= mp) mk |= 1u << k;
 			}
 	unsigned wm = mk << ((lane & 1) * 16), wq = (mk & qual) << ((lane & 1) * 16);
@@ -717,6 +701,56 @@ k_clump_mark (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base
 		const uint64_t w = tile * CLF_WORDS + warp * (CLF_GROUP / 32) + (lane >> 1);
 		wk.Bm[w] = wm;  wk.Bq[w] = wq;
 		}
+	}
+
+template <bool ABOVE>
+__global__ void __launch_bounds__(CL_THREADS, 4)
+k_clump_mark (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg, uint64_t ntiles,
+              const double* __restrict__ sig, double T, uint32_t minLength, double relLength,
+              ClumpFast wk, ScanStatus<double> stMax)
+	{
+	extern __shared__ double s_M[];                    // (hrows + 8) * 544 prefix minima
+	__shared__ double s_warp[CL_WARPS];
+	__shared__ double s_carryD;
+	// reversed tile order: ticket k handles the k-th tile from the END of the launch, so that every tile a
+	// block waits on (the tiles to its right) has already started
+	const uint32_t ticket = scan_take_ticket (stMax.ticket);
+	const uint64_t tile = ntiles - 1 - ticket;
+	int seg;  uint64_t tis;
+	tile_to_seg (base, nseg, tile, seg, tis);
+	const SegDev sd = segs[seg];
+	const uint64_t tilesInSeg = base[seg + 1] - base[seg];
+	const uint64_t t0 = sd.lo + tis * CL_TILE;
+	const uint32_t n  = (uint32_t) ((sd.hi - t0 < CL_TILE) ? (sd.hi - t0) : CL_TILE);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const bool firstOfScan = (tis == tilesInSeg - 1);
+
+	uint32_t Lmin = minLength;
+	if (relLength > 0.0)
+		{
+		uint32_t rl = (uint32_t) (relLength * sd.chromLen);       // clump.c:516-522
+		if (rl > Lmin) Lmin = rl;
+		}
+	const uint32_t reach = (Lmin > 0) ? Lmin : 1;                 // M[p-1] is needed even when Lmin is 0
+	const uint32_t hrows = (reach + CLF_GROUP - 1) / CLF_GROUP;   // <= 8 (the host checked): at most one per warp
+
+	// prefix minima of the halo groups (the tail of the previous tile of this chromosome)
+	if ((uint32_t) warp < hrows && (uint64_t) (hrows - warp) * CLF_GROUP <= tis * CL_TILE)
+		{
+		const uint32_t back = (hrows - warp) * CLF_GROUP;         // cells between the group's first cell and t0
+		double x[16], tot;
+		clf_load16<true, ABOVE> (sig, t0 - back + lane * 16, 16, T, x);
+		group_sum_scan (x, tot);
+		const double2 cr = wk.carry[tile * CLF_GROUPS - (hrows - warp)];
+		#pragma unroll
+		for (int k = 0; k < 16; k++) x[k] = cr.x + x[k];
+		clf_group_min_store<true> (x, 16, cr.y, s_M + warp * (CLF_GROUP / 16 * 17));
+		}
+
+	if (n == CL_TILE && tis * CL_TILE >= (uint64_t) Lmin && tis > 0)
+		clf_mark_tile<true, ABOVE> (sig, T, wk, stMax, s_M, s_warp, &s_carryD, tile, ticket, firstOfScan, tis, t0, n, Lmin, hrows);
+	else
+		clf_mark_tile<false, ABOVE> (sig, T, wk, stMax, s_M, s_warp, &s_carryD, tile, ticket, firstOfScan, tis, t0, n, Lmin, hrows);
 	}
 
 // ---- run trimming on the bit words -------------------------------------------
@@ -912,18 +946,22 @@ extern "C" int gdsp_clump (gdsp_ctx* c, const gdsp_layout* L_, double* sig, uint
 		static size_t smemSet = 0;
 		if (smem > smemSet)
 			{
-			GDSP_CUDA (cudaFuncSetAttribute (k_clump_mark, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+			GDSP_CUDA (cudaFuncSetAttribute (k_clump_mark<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+			GDSP_CUDA (cudaFuncSetAttribute (k_clump_mark<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 			smemSet = smem;
 			}
 
 		k_fill_int<<<(L->nseg + 255) / 256, 256, 0, c->stream>>> (wf.segAllNeg, L->nseg, 1);
 		GDSP_KERNEL_CHECK ();
-		k_clump_groups<<<(unsigned) tm.ntiles, CL_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, sig, average, above ? 1 : 0, wf);
+		if (above) k_clump_groups<true><<<(unsigned) tm.ntiles, CL_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, sig, average, wf);
+		else       k_clump_groups<false><<<(unsigned) tm.ntiles, CL_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, sig, average, wf);
 		GDSP_KERNEL_CHECK ();
 		k_clump_groupscan<<<L->nseg, CLF_GS_THREADS, 0, c->stream>>> (tm.d_base, wf);
 		GDSP_KERNEL_CHECK ();
 		GDSP_CUDA (cudaMemsetAsync (ws1, 0, scan_status_clear_bytes<double> (tm.ntiles), c->stream));
-		k_clump_mark<<<(unsigned) tm.ntiles, CL_THREADS, smem, c->stream>>> (L->d, tm.d_base, L->nseg, tm.ntiles, sig, average, above ? 1 : 0,
+		if (above) k_clump_mark<true><<<(unsigned) tm.ntiles, CL_THREADS, smem, c->stream>>> (L->d, tm.d_base, L->nseg, tm.ntiles, sig, average,
+		        minLength, relLength, wf, scan_status_carve<double> (ws1, tm.ntiles));
+		else       k_clump_mark<false><<<(unsigned) tm.ntiles, CL_THREADS, smem, c->stream>>> (L->d, tm.d_base, L->nseg, tm.ntiles, sig, average,
 		        minLength, relLength, wf, scan_status_carve<double> (ws1, tm.ntiles));
 		GDSP_KERNEL_CHECK ();
 		k_clump_tilesum<<<(unsigned) ((tm.ntiles + 7) / 8), 256, 0, c->stream>>> (tm.ntiles, wf);
