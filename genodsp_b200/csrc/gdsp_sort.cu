@@ -638,6 +638,126 @@ extern "C" int gdsp_sort_genome (gdsp_ctx* c, const gdsp_layout* L_, double* sig
 	}
 
 // ---------------------------------------------------------------------------
+// percentile followed by binarize
+//
+// `percentile P = binarize --threshold=percentileP` (BASELINE configs 3 and the 5-stage pipeline) binarizes
+// the SORTED genome the reference's percentile leaves behind (percentile.c:611-651): a step function.
+// Sorting 3.1 G values only to threshold them is wasted work -- the step sits at
+// cells - #(v > T), so one counting pass and one fill give the same bytes.  NaNs sort to the ends but
+// never compare above a threshold, so a signal that holds any is left to the general path.
+// ---------------------------------------------------------------------------
+
+// res[0] += #(v > T) (v >= T with ties above), res[1] += #NaN
+__global__ void __launch_bounds__(256)
+k_count_above (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg, uint64_t ntiles,
+               const double* __restrict__ in, double T, int tiesAbove, unsigned long long* __restrict__ res)
+	{
+	unsigned int above = 0, nan = 0;                   // per thread: at most ntiles/grid * 16 cells, far below 2^32
+	for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x)
+		{
+		int seg;  uint64_t tis;
+		tile_to_seg (base, nseg, t, seg, tis);
+		const SegDev sd = segs[seg];
+		const uint64_t t0 = sd.lo + tis * SORT_TILE;
+		uint64_t t1 = t0 + SORT_TILE;  if (t1 > sd.hi) t1 = sd.hi;
+		if (t1 - t0 == SORT_TILE)
+			{
+			double v[16];
+			#pragma unroll
+			for (int r = 0; r < 4; r++)
+				ldg_stream4 (in + t0 + r * 1024 + threadIdx.x * 4, v[4 * r], v[4 * r + 1], v[4 * r + 2], v[4 * r + 3]);
+			#pragma unroll
+			for (int k = 0; k < 16; k++)
+				{
+				above += tiesAbove ? (v[k] >= T) : (v[k] > T);
+				nan   += (v[k] != v[k]);
+				}
+			}
+		else
+			for (uint64_t i = t0 + threadIdx.x; i < t1; i += 256)
+				{
+				const double v = in[i];
+				above += tiesAbove ? (v >= T) : (v > T);
+				nan   += (v != v);
+				}
+		}
+	unsigned long long a = above, b = nan;
+	#pragma unroll
+	for (int d = 16; d > 0; d >>= 1)
+		{
+		a += __shfl_xor_sync (0xffffffffu, a, d);
+		b += __shfl_xor_sync (0xffffffffu, b, d);
+		}
+	__shared__ unsigned long long s_a[8], s_b[8];
+	if ((threadIdx.x & 31) == 0) { s_a[threadIdx.x >> 5] = a;  s_b[threadIdx.x >> 5] = b; }
+	__syncthreads ();
+	if (threadIdx.x == 0)
+		{
+		for (int w = 1; w < 8; w++) { a += s_a[w];  b += s_b[w]; }
+		if (a) atomicAdd (&res[0], a);
+		if (b) atomicAdd (&res[1], b);
+		}
+	}
+
+// cell at sorted position p (layout order) = p >= step ? one : zero
+__global__ void __launch_bounds__(256)
+k_fill_step (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
+             const uint64_t* __restrict__ prefix, unsigned long long step, double one, double zero, double* __restrict__ out)
+	{
+	int seg;  uint64_t tis;
+	tile_to_seg (base, nseg, blockIdx.x, seg, tis);
+	const SegDev sd = segs[seg];
+	const uint64_t t0 = sd.lo + tis * SORT_TILE;
+	uint64_t t1 = t0 + SORT_TILE;  if (t1 > sd.hi) t1 = sd.hi;
+	const uint64_t p0 = prefix[seg] + (t0 - sd.lo);
+	if (t1 - t0 == SORT_TILE)
+		{
+		#pragma unroll
+		for (int r = 0; r < 4; r++)
+			{
+			const uint32_t e = r * 1024 + threadIdx.x * 4;
+			const uint64_t p = p0 + e;
+			stg_stream4 (out + t0 + e, (p >= step) ? one : zero, (p + 1 >= step) ? one : zero,
+			             (p + 2 >= step) ? one : zero, (p + 3 >= step) ? one : zero);
+			}
+		}
+	else
+		for (uint64_t i = t0 + threadIdx.x; i < t1; i += 256) out[i] = (p0 + (i - t0) >= step) ? one : zero;
+	}
+
+extern "C" int gdsp_sorted_binarize (gdsp_ctx* c, const gdsp_layout* L_, double* sig, double threshold, int ties_above,
+                                     double one, double zero, int* h_done)
+	{
+	gdsp_layout* L = (gdsp_layout*) L_;
+	GDSP_REQUIRE (c && L && sig && h_done, "gdsp_sorted_binarize: NULL argument");
+	GDSP_REQUIRE_ALIGNED (sig, "gdsp_sorted_binarize");
+	*h_done = 0;
+	TileMap tm;
+	GDSP_TRY (gdsp_layout_tilemap (L, SORT_TILE, &tm));
+	SortScratch sc;
+	GDSP_TRY (sort_scratch (c, tm.ntiles, L->nseg, &sc));
+	std::vector<uint64_t> prefix (L->nseg + 1);
+	uint64_t acc = 0;
+	for (int s = 0; s < L->nseg; s++) { prefix[s] = acc;  acc += L->h[s].hi - L->h[s].lo; }
+	prefix[L->nseg] = acc;
+	GDSP_CUDA (cudaMemcpyAsync (sc.prefix, prefix.data (), sizeof (uint64_t) * (L->nseg + 1), cudaMemcpyHostToDevice, c->stream));
+	unsigned long long st[2] = { 0ull, 0ull };
+	GDSP_CUDA (cudaMemsetAsync (sc.orand, 0, sizeof (st), c->stream));
+	int grid = c->sm_count * 8;
+	if ((uint64_t) grid > tm.ntiles) grid = (int) tm.ntiles;
+	if (grid < 1) return GDSP_OK;
+	k_count_above<<<grid, 256, 0, c->stream>>> (L->d, tm.d_base, L->nseg, tm.ntiles, sig, threshold, ties_above ? 1 : 0, sc.orand);
+	GDSP_KERNEL_CHECK ();
+	GDSP_CUDA (cudaMemcpyAsync (st, sc.orand, sizeof (st), cudaMemcpyDeviceToHost, c->stream));
+	GDSP_CUDA (cudaStreamSynchronize (c->stream));
+	if (st[1] != 0) return GDSP_OK;                    // NaNs: the caller sorts and binarizes
+	k_fill_step<<<(unsigned) tm.ntiles, 256, 0, c->stream>>> (L->d, tm.d_base, L->nseg, sc.prefix, L->cells - st[0], one, zero, sig);
+	GDSP_KERNEL_CHECK ();
+	*h_done = 1;
+	return GDSP_OK;
+	}
+
+// ---------------------------------------------------------------------------
 // percentile selection
 // ---------------------------------------------------------------------------
 

@@ -96,13 +96,28 @@ class Genome:
         lay = C.c_void_p()
         check(self.lib.gdsp_layout_create(self.ctx, seg_arr, self.nseg, C.byref(lay)))
         self.layout = lay
-        self.sig = torch.zeros(self.buffer_cells, dtype=torch.float64, device=self.device)
+        self._pending_sort = False
+        self._sig = torch.zeros(self.buffer_cells, dtype=torch.float64, device=self.device)
         self.tmp = torch.zeros(self.buffer_cells, dtype=torch.float64, device=self.device)
         self._work = None
         self.cells = int(self.lib.gdsp_layout_cells(self.layout))
         self._launch0 = self.lib.gdsp_launch_count()
 
     # ------------------------------------------------------------------ plumbing
+    @property
+    def sig(self):
+        """the current signal.  A destructive percentile leaves the genome notionally sorted
+        (percentile.c:611-651); the sort only runs when somebody looks -- here -- unless the next
+        operator is `binarize`, which never needs it (gdsp_sorted_binarize)."""
+        if self._pending_sort:
+            self._pending_sort = False
+            self.sort_genome()
+        return self._sig
+
+    @sig.setter
+    def sig(self, t):
+        self._sig = t
+
     @property
     def launches(self):
         """kernels launched by the library since this genome was created (gdsp_launch_count)"""
@@ -385,6 +400,14 @@ class Genome:
     def binarize(self, threshold=0.0, ties_above=False, one=1.0, zero=0.0):
         if isinstance(threshold, str):
             threshold = self.variables[threshold]     # logical.c:232-244
+        if self._pending_sort:
+            # binarizing the sorted genome = a step at cells - #(v > threshold): no sort needed
+            done = C.c_int()
+            check(self.lib.gdsp_sorted_binarize(self.ctx, self.layout, self._p(self._sig), float(threshold), int(ties_above),
+                                                float(one), float(zero), C.byref(done)))
+            if done.value:
+                self._pending_sort = False
+                return
         self.pointwise([self.op_binarize(threshold, ties_above, one, zero)])
 
     def addconst(self, value):
@@ -464,7 +487,7 @@ class Genome:
             out[percentile_name(p)] = vals[i]
         self.variables.update(out)
         if destructive:
-            self.sort_genome()
+            self._pending_sort = True                 # materialised by the next reader of self.sig
         return out
 
     def text_roundtrip(self):

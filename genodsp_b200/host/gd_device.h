@@ -19,6 +19,10 @@ typedef struct gdev
 	void*         work;          /* grow-only byte scratch                           */
 	size_t        work_bytes;
 	u32           maxLength;
+	int           pendingSorted; /* the signal is notionally the globally sorted genome a percentile leaves
+	                                behind (percentile.c:611-651) but has not been sorted: set only when the
+	                                next operator is binarize, which does not need the sort
+	                                (gdsp_sorted_binarize); cleared by gd_materialise_sorted            */
 	} gdev;
 
 extern gdev gd;
@@ -26,6 +30,7 @@ extern gdev gd;
 void  gd_device_open   (void);           /* after sort_chromosomes_by_length            */
 void  gd_device_close  (void);
 void  gd_check         (int status, const char* who);   /* fatal on error               */
+void  gd_materialise_sorted (const char* who);   /* gd_ops_percentile.c: sort now if pendingSorted */
 void  gd_swap          (void);           /* sig <-> tmp, refresh every spec->valVector  */
 void* gd_work          (size_t bytes);
 int   gd_sorted_index  (spec* chromSpec);

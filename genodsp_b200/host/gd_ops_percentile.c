@@ -173,6 +173,15 @@ static int signal_is_read_later (dspop* op)
 	return !gd_output_inhibited ();
 	}
 
+void gd_materialise_sorted (const char* who)
+	{
+	if (!gd.pendingSorted) return;
+	gd.pendingSorted = 0;
+	int inTmp = 0;
+	gd_check (gdsp_sort_genome (gd.ctx, gd.genome, gd.sig, gd.tmp, gd.cells, &inTmp), who);
+	if (inTmp) gd_swap ();
+	}
+
 void op_percentile_apply (dspop* _op, arg_dont_complain(char* vName), arg_dont_complain(u32 vLen), arg_dont_complain(valtype* v))
 	{
 	dspop_percentile* op = (dspop_percentile*) _op;
@@ -259,14 +268,18 @@ void op_percentile_apply (dspop* _op, arg_dont_complain(char* vName), arg_dont_c
 	u64 acc = 0;  int K = gd.nchrom - 1;
 	for (int i = 0; i < gd.nchrom; i++)
 		{ acc += chromsSorted[i]->length;  if (lastRank < acc) { K = i;  break; } }
-	int inTmp = 0;
 	if (K >= gd.nchrom - 2)
 		{
-		gd_check (gdsp_sort_genome (gd.ctx, gd.genome, gd.sig, gd.tmp, gd.cells, &inTmp), _op->name);
-		if (inTmp) gd_swap ();
+		/* globally sorted genome.  `percentile P = binarize ...` thresholds it straight away: a step
+		 * function that needs a count, not a sort -- leave the state pending and let binarize decide
+		 * (not under --progress=operations, whose trace interleaves binarize's messages differently) */
+		gd.pendingSorted = 1;
+		if (!(_op->next != NULL && _op->next->funcApply == op_binarize_apply && !trackOperations))
+			gd_materialise_sorted (_op->name);
 		}
 	else
 		{
+		int inTmp = 0;
 		/* the reference's bubble passes (percentile.c:623-651): chromosome c takes the smallest
 		 * len(c) values of {c, d} for every later d, in order */
 		for (int c = 0; c <= K; c++)

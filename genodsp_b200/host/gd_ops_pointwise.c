@@ -154,6 +154,15 @@ int gd_pointwise_descriptor (dspop* _op, gdsp_pw_op* out, gd_pw_resources* res)
 		{
 		case PK_BINARIZE:
 			resolve (_op, &op->varA, &op->a, "threshold", "threshold");
+			if (gd.pendingSorted)
+				{
+				/* directly after a percentile: the sorted genome it leaves is thresholded without being
+				 * sorted (gd_ops_percentile.c); this binarize is then the first operator of its chain */
+				int done = 0;
+				gd_check (gdsp_sorted_binarize (gd.ctx, gd.genome, gd.sig, op->a, op->flag, op->b, op->c, &done), _op->name);
+				if (done) { gd.pendingSorted = 0;  return 0; }
+				gd_materialise_sorted (_op->name);
+				}
 			out->code = op->flag ? GDSP_PW_BINARIZE_GE : GDSP_PW_BINARIZE_GT;
 			out->a = op->a;  out->b = op->b;  out->c = op->c;
 			return 1;

@@ -303,6 +303,12 @@ int  gdsp_pct_count   (gdsp_ctx* ctx, const gdsp_layout* lay, const double* sig,
  * in sig (*h_result_in_tmp = 0) or in tmp (= 1): the caller swaps its buffers. */
 int  gdsp_sort_genome (gdsp_ctx* ctx, const gdsp_layout* lay, double* sig,
                        double* tmp, uint64_t buffer_cells, int* h_result_in_tmp);
+/* op_binarize_apply (logical.c:216-268) applied to the post-percentile state above WITHOUT sorting:
+ * the binarized sorted genome is a step function at cells - #(v > threshold) (>= with ties above),
+ * so one counting pass and one fill produce the same bytes.  *h_done = 0 (signal untouched) when
+ * the signal holds NaNs: sort (gdsp_sort_genome) and binarize (gdsp_pointwise) instead. */
+int  gdsp_sorted_binarize (gdsp_ctx* ctx, const gdsp_layout* lay, double* sig, double threshold,
+                           int ties_above, double one, double zero, int* h_done);
 
 /* ---- text output -----------------------------------------------------------
  * The fprintf loop of report_intervals (genodsp.c:1606-1678) on the device: run r

@@ -608,6 +608,44 @@ def test_percentile_values_and_sorted_post_state(genome, orc, kind):
         assert np.array_equal(genome.get_chrom(name), post[name]), (kind, name)
 
 
+@pytest.mark.parametrize("ties_above", [False, True])
+@pytest.mark.parametrize("kind", KINDS + ["negzero", "nan"])
+def test_percentile_then_binarize_without_sorting(genome, orc, kind, ties_above):
+    """`percentile P = binarize --threshold=percentileP`: the binarized SORTED genome is a step function;
+    gdsp_sorted_binarize writes it from a count (no sort).  Must equal sort-then-binarize bit for bit --
+    also with -0.0/+0.0 around a zero threshold, and with NaNs (which fall back to the real sort)."""
+    base = "sparse" if kind in ("negzero", "nan") else kind
+    inputs = load(genome, np.random.default_rng(23), base)
+    if kind != base:
+        for name, n in CHROMS:
+            v = inputs[name]
+            v[::7] = -0.0; v[1::11] = -1.5
+            if kind == "nan" and n > 50:
+                v[13] = np.nan; v[n - 2] = -np.nan
+            genome.set_chrom(name, v)
+    launches0 = genome.launches
+    got = genome.percentile(90.0, destructive=True)
+    thr = 0.0 if kind == "negzero" else got["percentile90"]
+    genome.binarize(thr, ties_above, one=2.0, zero=-1.0)
+    fused = {name: genome.get_chrom(name) for name, _ in CHROMS}
+    fused_launches = genome.launches - launches0
+    # the explicit route: select, sort, threshold
+    for name, n in CHROMS:
+        genome.set_chrom(name, inputs[name])
+    launches0 = genome.launches
+    genome.percentile(90.0, destructive=False)
+    genome.sort_genome()
+    genome.binarize(thr, ties_above, one=2.0, zero=-1.0)
+    for name, n in CHROMS:
+        assert np.array_equal(bits(fused[name]), bits(genome.get_chrom(name))), (kind, name)
+    if kind != "nan":
+        assert fused_launches < genome.launches - launches0, "the fused route must not have sorted"
+        post = _sorted_post_state(genome, inputs)
+        for name, n in CHROMS:
+            want = np.where((post[name] >= thr) if ties_above else (post[name] > thr), 2.0, -1.0)
+            assert np.array_equal(bits(fused[name]), bits(want)), (kind, name)
+
+
 @pytest.mark.parametrize("W", [2, 5, 100])
 def test_percentile_window_and_range(genome, orc, W):
     inputs = load(genome, np.random.default_rng(W), "int")
