@@ -9,27 +9,41 @@
 //   head(i) = printable(i) && (first cell || !collapse || !printable(i-1) || v[i] != v[i-1])
 //   tail(i) = printable(i) && (last cell  || !collapse || !printable(i+1) || v[i+1] != v[i])
 // Heads and tails alternate, so the k-th head and the k-th tail bound the k-th
-// run; one exclusive scan of the head flags (single pass, decoupled look-back
-// across all tiles of the launch) gives every record its slot.
-// Algorithmic bytes: 8 B/bp read + 16 B/run written.
+// run.  Three chain-free kernels:
+//   k_runs_flags    every warp reads 512 cells (16 consecutive cells per lane, four 256-bit loads; the
+//                   cell before and after a lane's strip come from the neighbouring lanes, across
+//                   warps straight from global memory -- no block barrier at all), leaves one head
+//                   bit and one tail bit per cell and adds its counts to its tile's counters
+//   k_runs_offsets  one block: exclusive prefix of the per-tile counts (377 k tiles for hg38)
+//   k_runs_emit     tiles that hold a head or a tail (few, for thresholded tracks) walk their bit
+//                   words and write (start, value) / end records to their slots
+// The first version did all of this in one kernel with a decoupled look-back across tiles: ncu showed
+// 20 warps waiting at the block barrier per issuing warp (3.0 TB/s); the streaming pass below has no
+// barrier and no chain.
+// Algorithmic bytes: 8 B/bp read + 16 B/run written (+0.25 B/bp of flag bits).
 #include "gdsp_common.cuh"
-#include "gdsp_scan.cuh"
 
 #define RUN_THREADS 512
 #define RUN_PER     16
 #define RUN_TILE    (RUN_THREADS * RUN_PER)      // 8192
+#define RUN_WORDS   (RUN_TILE / 32)              // 256 flag words per tile
 
-__global__ void __launch_bounds__(RUN_THREADS, 3)
-k_runs (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
-        const double* __restrict__ sig, int collapse, int show,
-        uint32_t* __restrict__ oStart, uint32_t* __restrict__ oEnd, double* __restrict__ oVal,
-        uint64_t cap, unsigned long long* __restrict__ segFirst, uint64_t ntiles,
-        ScanStatus<unsigned long long> st)
+struct RunWork
 	{
-	__shared__ unsigned int s_warp[RUN_THREADS / 32];
-	__shared__ unsigned long long s_excl;
+	uint32_t*           headW;      // ntiles * 256
+	uint32_t*           tailW;
+	unsigned int*       cntH;       // ntiles: heads per tile (zeroed before k_runs_flags)
+	unsigned int*       cntT;
+	unsigned long long* offH;       // ntiles + 1: heads before tile t
+	unsigned long long* offT;
+	unsigned long long* segFirst;   // nseg + 1
+	};
 
-	const uint32_t tile = scan_take_ticket (st.ticket);
+__global__ void __launch_bounds__(RUN_THREADS, 2)
+k_runs_flags (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
+              const double* __restrict__ sig, int collapse, int show, RunWork wk)
+	{
+	const uint64_t tile = blockIdx.x;
 	int seg;  uint64_t tis;
 	tile_to_seg (base, nseg, tile, seg, tis);
 	const SegDev sd = segs[seg];
@@ -38,31 +52,20 @@ k_runs (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int 
 
 	const uint32_t c0 = threadIdx.x * RUN_PER;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t g0 = warp * 32 * RUN_PER;          // first cell of this warp's 512-cell group
 	uint32_t heads = 0, tails = 0;
-	double   myv[RUN_PER];                    // FULL tiles keep their cells in registers (no staging)
-	const bool fullTile = (n == RUN_TILE);
 
-	if (fullTile)
+	if (g0 + 32 * RUN_PER <= n)
 		{
-		// 16 consecutive cells per thread straight from global memory (four 256-bit loads); the cell
-		// before and after the strip come from the neighbouring lanes, across warps through shared
-		// memory, across the tile edge from global memory
+		double myv[RUN_PER];
 		const double* p = sig + t0 + c0;
 		#pragma unroll
 		for (int q = 0; q < RUN_PER / 4; q++) ldg_stream4 (p + 4 * q, myv[4*q], myv[4*q+1], myv[4*q+2], myv[4*q+3]);
-		__shared__ double s_first[RUN_THREADS / 32], s_last[RUN_THREADS / 32];
-		__shared__ double s_edge[2];
-		if (lane == 0)  s_first[warp] = myv[0];
-		if (lane == 31) s_last[warp]  = myv[RUN_PER - 1];
-		const bool segFirstCell = (t0 == sd.lo), segLastCell = (t0 + RUN_TILE == sd.hi);
-		if (threadIdx.x == 0) s_edge[0] = segFirstCell ? 0.0 : sig[t0 - 1];
-		if (threadIdx.x == 1) s_edge[1] = segLastCell  ? 0.0 : sig[t0 + RUN_TILE];
-		__syncthreads ();
+		const bool isFirst = (t0 + c0 == sd.lo);                       // the lane's first cell opens the chromosome piece
+		const bool isLast  = (t0 + c0 + RUN_PER == sd.hi);             // its last cell closes it
 		double before = shfl_up_f64 (myv[RUN_PER - 1], 1), after = shfl_down_f64 (myv[0], 1);
-		if (lane == 0)  before = (warp == 0) ? s_edge[0] : s_last[warp - 1];
-		if (lane == 31) after  = (warp == RUN_THREADS / 32 - 1) ? s_edge[1] : s_first[warp + 1];
-		const bool isFirst = segFirstCell && threadIdx.x == 0;                 // cell 0 of the chromosome piece
-		const bool isLast  = segLastCell  && threadIdx.x == RUN_THREADS - 1;   // its last cell
+		if (lane == 0)  before = isFirst ? 0.0 : __ldg (sig + t0 + c0 - 1);
+		if (lane == 31) after  = isLast  ? 0.0 : __ldg (sig + t0 + c0 + RUN_PER);
 
 		// pr: printable, ne: differs from the cell before
 		uint32_t pr = 0, ne = 0;
@@ -87,90 +90,142 @@ k_runs (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int 
 		else heads = tails = pr;
 		heads &= 0xffffu;  tails &= 0xffffu;
 		}
-	else
+	else if (c0 < n)
 		{
-		// edge tile (shorter than RUN_TILE): cells and their neighbours straight from global memory
-		if (c0 < n)
+		// the last, shorter group of a chromosome piece: cells and their neighbours one by one
+		#pragma unroll 4
+		for (int k = 0; k < RUN_PER; k++)
 			{
-			#pragma unroll 4
-			for (int k = 0; k < RUN_PER; k++)
+			const uint32_t c = c0 + k;
+			if (c >= n) break;
+			const bool first = (t0 + c == sd.lo), last = (t0 + c + 1 == sd.hi);
+			const double cur = sig[t0 + c];
+			const bool pr = show || (cur != 0);
+			if (pr)
 				{
-				const uint32_t c = c0 + k;
-				if (c >= n) break;
-				const bool first = (t0 + c == sd.lo), last = (t0 + c + 1 == sd.hi);
-				const double cur = sig[t0 + c];
-				const bool pr = show || (cur != 0);
-				if (pr)
-					{
-					const double prev = first ? 0.0 : sig[t0 + c - 1];
-					const double next = last  ? 0.0 : sig[t0 + c + 1];
-					const bool prPrev = !first && (show || prev != 0);
-					const bool prNext = !last  && (show || next != 0);
-					if (first || !collapse || !prPrev || cur != prev)  heads |= 1u << k;
-					if (last  || !collapse || !prNext || next != cur)  tails |= 1u << k;
-					}
+				const double prev = first ? 0.0 : sig[t0 + c - 1];
+				const double next = last  ? 0.0 : sig[t0 + c + 1];
+				const bool prPrev = !first && (show || prev != 0);
+				const bool prNext = !last  && (show || next != 0);
+				if (first || !collapse || !prPrev || cur != prev)  heads |= 1u << k;
+				if (last  || !collapse || !prNext || next != cur)  tails |= 1u << k;
 				}
 			}
 		}
 
-	// block exclusive scan of head counts
-	unsigned int cnt = __popc (heads), inc = cnt;
+	// one word per two lanes; every word of the tile is written (zeros past the end of the piece)
+	uint32_t hw = heads << ((lane & 1) * 16), tw = tails << ((lane & 1) * 16);
+	hw |= __shfl_xor_sync (0xffffffffu, hw, 1);
+	tw |= __shfl_xor_sync (0xffffffffu, tw, 1);
+	if ((lane & 1) == 0)
+		{
+		const uint64_t w = tile * RUN_WORDS + warp * 16 + (lane >> 1);
+		wk.headW[w] = hw;  wk.tailW[w] = tw;
+		}
+	const unsigned nh = __reduce_add_sync (0xffffffffu, (unsigned) __popc (heads));
+	const unsigned nt = __reduce_add_sync (0xffffffffu, (unsigned) __popc (tails));
+	if (lane == 0)
+		{
+		if (nh) atomicAdd (&wk.cntH[tile], nh);
+		if (nt) atomicAdd (&wk.cntT[tile], nt);
+		}
+	}
+
+#define RUN_OFF_THREADS 1024
+__global__ void __launch_bounds__(RUN_OFF_THREADS)
+k_runs_offsets (const uint64_t* __restrict__ base, int nseg, uint64_t ntiles, RunWork wk)
+	{
+	__shared__ unsigned long long s_h[32], s_t[32];
+	const uint64_t chunk = (ntiles + RUN_OFF_THREADS - 1) / RUN_OFF_THREADS;
+	const uint64_t lo = (threadIdx.x * chunk < ntiles) ? threadIdx.x * chunk : ntiles;
+	const uint64_t hi = (lo + chunk < ntiles) ? lo + chunk : ntiles;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	unsigned long long h = 0, t = 0;
+	for (uint64_t i = lo; i < hi; i++) { h += wk.cntH[i];  t += wk.cntT[i]; }
+	unsigned long long ih = h, it = t;
 	#pragma unroll
 	for (int d = 1; d < 32; d <<= 1)
 		{
-		unsigned int up = __shfl_up_sync (0xffffffffu, inc, d);
-		if (lane >= d) inc += up;
+		const unsigned long long uh = __shfl_up_sync (0xffffffffu, ih, d), ut = __shfl_up_sync (0xffffffffu, it, d);
+		if (lane >= d) { ih += uh;  it += ut; }
 		}
-	if (lane == 31) s_warp[warp] = inc;
+	if (lane == 31) { s_h[warp] = ih;  s_t[warp] = it; }
 	__syncthreads ();
-	unsigned int warpExcl = 0, tileTot = 0;
-	#pragma unroll
-	for (int w = 0; w < RUN_THREADS / 32; w++)
+	unsigned long long eh = ih - h, et = it - t, totH = 0, totT = 0;
+	for (int w = 0; w < 32; w++)
 		{
-		unsigned int t = s_warp[w];
-		if (w < warp) warpExcl += t;
-		tileTot += t;
+		if (w < warp) { eh += s_h[w];  et += s_t[w]; }
+		totH += s_h[w];  totT += s_t[w];
 		}
-	if (threadIdx.x < 32)
+	for (uint64_t i = lo; i < hi; i++)
 		{
-		unsigned long long ex = scan_lookback<unsigned long long> (st, tile, tile == 0, (unsigned long long) tileTot, 0ull,
-		                            [] (unsigned long long a, unsigned long long b) { return a + b; });
-		if (threadIdx.x == 0)
-			{
-			s_excl = ex;
-			if (tis == 0) segFirst[seg] = ex;
-			if (tile == ntiles - 1) segFirst[nseg] = ex + tileTot;
-			}
+		wk.offH[i] = eh;  wk.offT[i] = et;
+		eh += wk.cntH[i];  et += wk.cntT[i];
 		}
+	if (threadIdx.x == 0) { wk.offH[ntiles] = totH;  wk.offT[ntiles] = totT; }
 	__syncthreads ();
+	// first run of every chromosome piece (and the total behind the last one)
+	for (int s = threadIdx.x; s <= nseg; s += RUN_OFF_THREADS) wk.segFirst[s] = (s < nseg) ? wk.offH[base[s]] : totH;
+	}
 
-	unsigned long long idx = s_excl + warpExcl + (inc - cnt);      // slot of this thread's first head
-	if (c0 < n && (heads | tails))
+#define RUN_EMIT_THREADS 256
+__global__ void __launch_bounds__(RUN_EMIT_THREADS)
+k_runs_emit (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg, uint64_t ntiles,
+             const double* __restrict__ sig, int collapse,
+             uint32_t* __restrict__ oStart, uint32_t* __restrict__ oEnd, double* __restrict__ oVal, uint64_t cap, RunWork wk)
+	{
+	__shared__ unsigned int s_warp[RUN_EMIT_THREADS / 32];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
 		{
-		// walk the set bits in cell order; a head and a tail on the same cell: head first
+		if ((wk.cntH[tile] | wk.cntT[tile]) == 0) continue;                   // block-uniform
+		int seg;  uint64_t tis;
+		tile_to_seg (base, nseg, tile, seg, tis);
+		const SegDev sd = segs[seg];
+		const uint64_t t0 = sd.lo + tis * RUN_TILE;
+		uint32_t heads = wk.headW[tile * RUN_WORDS + threadIdx.x], tails = wk.tailW[tile * RUN_WORDS + threadIdx.x];
+		// exclusive prefix of (heads, tails) per word, packed 16:16 (a tile holds at most 8192 of each)
+		const unsigned int cnt = (unsigned) __popc (heads) | ((unsigned) __popc (tails) << 16);
+		unsigned int inc = cnt;
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+			{
+			const unsigned int up = __shfl_up_sync (0xffffffffu, inc, d);
+			if (lane >= d) inc += up;
+			}
+		__syncthreads ();                                                      // s_warp of the previous tile has been read
+		if (lane == 31) s_warp[warp] = inc;
+		__syncthreads ();
+		unsigned int ex = inc - cnt;
+		for (int w = 0; w < warp; w++) ex += s_warp[w];
+		unsigned long long ih = wk.offH[tile] + (ex & 0xffffu), it = wk.offT[tile] + (ex >> 16);
+		// walk the set bits in cell order
 		uint32_t both = heads | tails;
 		while (both)
 			{
 			const int k = __ffs (both) - 1;
 			both &= both - 1;
-			const uint32_t c = c0 + k;
+			const uint32_t c = threadIdx.x * 32 + k;
 			const uint32_t coord = sd.pos0 + (uint32_t) (t0 + c - sd.lo);
 			if (heads & (1u << k))
 				{
-				if (idx < cap)
+				if (ih < cap)
 					{
-					double v = __ldg (sig + t0 + c);         // re-read (L2): keeping 16 cells per thread in
-					                                           // registers until here halves the occupancy
+					double v = __ldg (sig + t0 + c);
 					// the reference's state machine starts with val=+0.0 (genodsp.c:1590): a collapsed
 					// run of zeros that begins at base 0 reports that +0.0, not v[0]
 					if (coord == 0 && collapse && v == 0) v = 0.0;
-					oStart[idx] = coord;
-					oVal[idx]   = v;
+					oStart[ih] = coord;
+					oVal[ih]   = v;
 					}
-				idx++;
+				ih++;
 				}
-			// the run a tail closes is the most recent head: slot idx-1
-			if ((tails & (1u << k)) && idx - 1 < cap) oEnd[idx - 1] = coord + 1;
+			// the k-th tail closes the k-th head
+			if (tails & (1u << k))
+				{
+				if (it < cap) oEnd[it] = coord + 1;
+				it++;
+				}
 			}
 		}
 	}
@@ -185,14 +240,38 @@ extern "C" int gdsp_runs (gdsp_ctx* c, const gdsp_layout* L_, const double* sig,
 	GDSP_REQUIRE_ALIGNED (sig, "gdsp_runs");
 	TileMap tm;
 	GDSP_TRY (gdsp_layout_tilemap (L, RUN_TILE, &tm));
-	void* ws;  void* wseg;
-	GDSP_TRY (gdsp_ws (c, 0, scan_status_bytes<unsigned long long> (tm.ntiles), &ws));
-	GDSP_TRY (gdsp_ws (c, 2, sizeof (unsigned long long) * (L->nseg + 1), &wseg));
-	ScanStatus<unsigned long long> st = scan_status_carve<unsigned long long> (ws, tm.ntiles);
-	GDSP_CUDA (cudaMemsetAsync (ws, 0, scan_status_clear_bytes<unsigned long long> (tm.ntiles), c->stream));
-	k_runs<<<(unsigned) tm.ntiles, RUN_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, sig, collapse ? 1 : 0,
-	        showUncovered == 1 ? 1 : 0, d_start, d_end, d_val, cap, (unsigned long long*) wseg, tm.ntiles, st);
+	if (tm.ntiles == 0) { *h_n_runs = 0;  if (h_seg_first) for (int s = 0; s <= L->nseg; s++) h_seg_first[s] = 0;  return GDSP_OK; }
+	// workspace: flag words, per-tile counts and offsets, per-piece first run
+	const size_t wordsB = (size_t) tm.ntiles * RUN_WORDS * sizeof (uint32_t);
+	const size_t cntB   = (((size_t) tm.ntiles * sizeof (unsigned int)) + 255) / 256 * 256;
+	const size_t offB   = (((size_t) (tm.ntiles + 1) * sizeof (unsigned long long)) + 255) / 256 * 256;
+	const size_t segB   = (((size_t) (L->nseg + 1) * sizeof (unsigned long long)) + 255) / 256 * 256;
+	void* ws;
+	GDSP_TRY (gdsp_ws (c, 0, 2 * wordsB + 2 * cntB + 2 * offB + segB, &ws));
+	RunWork wk;
+	char* p = (char*) ws;
+	wk.cntH = (unsigned int*) p;            p += cntB;
+	wk.cntT = (unsigned int*) p;            p += cntB;
+	wk.offH = (unsigned long long*) p;      p += offB;
+	wk.offT = (unsigned long long*) p;      p += offB;
+	wk.segFirst = (unsigned long long*) p;  p += segB;
+	wk.headW = (uint32_t*) p;               p += wordsB;
+	wk.tailW = (uint32_t*) p;
+	void* wseg = wk.segFirst;
+	GDSP_CUDA (cudaMemsetAsync (wk.cntH, 0, 2 * cntB, c->stream));
+	k_runs_flags<<<(unsigned) tm.ntiles, RUN_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, sig, collapse ? 1 : 0,
+	        showUncovered == 1 ? 1 : 0, wk);
 	GDSP_KERNEL_CHECK ();
+	k_runs_offsets<<<1, RUN_OFF_THREADS, 0, c->stream>>> (tm.d_base, L->nseg, tm.ntiles, wk);
+	GDSP_KERNEL_CHECK ();
+	if (cap > 0)
+		{
+		uint64_t grid = (uint64_t) c->sm_count * 16;
+		if (grid > tm.ntiles) grid = tm.ntiles;
+		k_runs_emit<<<(unsigned) grid, RUN_EMIT_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, tm.ntiles, sig, collapse ? 1 : 0,
+		        d_start, d_end, d_val, cap, wk);
+		GDSP_KERNEL_CHECK ();
+		}
 	std::vector<unsigned long long> sf (L->nseg + 1);
 	GDSP_CUDA (cudaMemcpyAsync (sf.data (), wseg, sizeof (unsigned long long) * (L->nseg + 1), cudaMemcpyDeviceToHost, c->stream));
 	GDSP_CUDA (cudaStreamSynchronize (c->stream));
