@@ -39,20 +39,22 @@ struct RunWork
 	unsigned long long* segFirst;   // nseg + 1
 	};
 
-__global__ void __launch_bounds__(RUN_THREADS, 2)
+// 256-thread blocks, two per tile: more, smaller blocks per SM keep loads in flight while others compute
+#define RUN_FLAG_THREADS 256
+__global__ void __launch_bounds__(RUN_FLAG_THREADS, 4)
 k_runs_flags (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
               const double* __restrict__ sig, int collapse, int show, RunWork wk)
 	{
-	const uint64_t tile = blockIdx.x;
+	const uint64_t tile = blockIdx.x >> 1;
 	int seg;  uint64_t tis;
 	tile_to_seg (base, nseg, tile, seg, tis);
 	const SegDev sd = segs[seg];
 	const uint64_t t0 = sd.lo + tis * RUN_TILE;
 	const uint32_t n  = (uint32_t) ((sd.hi - t0 < RUN_TILE) ? (sd.hi - t0) : RUN_TILE);
 
-	const uint32_t c0 = threadIdx.x * RUN_PER;
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) + (blockIdx.x & 1) * (RUN_FLAG_THREADS / 32);   // warp of the tile
 	const uint32_t g0 = warp * 32 * RUN_PER;          // first cell of this warp's 512-cell group
+	const uint32_t c0 = g0 + lane * RUN_PER;
 	uint32_t heads = 0, tails = 0;
 
 	if (g0 + 32 * RUN_PER <= n)
@@ -131,17 +133,48 @@ k_runs_flags (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base
 		}
 	}
 
+// exclusive prefix of the per-tile counts: block totals, then every block adds the totals before it
 #define RUN_OFF_THREADS 1024
+#define RUN_OFF_TILES   (RUN_OFF_THREADS * 4)
+__device__ __forceinline__ void run_load4 (const unsigned int* __restrict__ a, uint64_t i, uint64_t n, unsigned int v[4])
+	{
+	if (i + 4 <= n) { const uint4 q = *reinterpret_cast<const uint4*> (a + i);  v[0] = q.x;  v[1] = q.y;  v[2] = q.z;  v[3] = q.w; }
+	else for (int k = 0; k < 4; k++) v[k] = (i + k < n) ? a[i + k] : 0u;
+	}
+
 __global__ void __launch_bounds__(RUN_OFF_THREADS)
-k_runs_offsets (const uint64_t* __restrict__ base, int nseg, uint64_t ntiles, RunWork wk)
+k_runs_partial (uint64_t ntiles, RunWork wk, unsigned long long* __restrict__ part)
 	{
 	__shared__ unsigned long long s_h[32], s_t[32];
-	const uint64_t chunk = (ntiles + RUN_OFF_THREADS - 1) / RUN_OFF_THREADS;
-	const uint64_t lo = (threadIdx.x * chunk < ntiles) ? threadIdx.x * chunk : ntiles;
-	const uint64_t hi = (lo + chunk < ntiles) ? lo + chunk : ntiles;
+	const uint64_t i = (uint64_t) blockIdx.x * RUN_OFF_TILES + threadIdx.x * 4;
+	unsigned int a[4], b[4];
+	run_load4 (wk.cntH, i, ntiles, a);  run_load4 (wk.cntT, i, ntiles, b);
+	unsigned long long h = (unsigned long long) a[0] + a[1] + a[2] + a[3], t = (unsigned long long) b[0] + b[1] + b[2] + b[3];
+	#pragma unroll
+	for (int d = 16; d >= 1; d >>= 1) { h += __shfl_xor_sync (0xffffffffu, h, d);  t += __shfl_xor_sync (0xffffffffu, t, d); }
+	if ((threadIdx.x & 31) == 0) { s_h[threadIdx.x >> 5] = h;  s_t[threadIdx.x >> 5] = t; }
+	__syncthreads ();
+	if (threadIdx.x == 0)
+		{
+		for (int w = 1; w < 32; w++) { h += s_h[w];  t += s_t[w]; }
+		part[2 * blockIdx.x] = h;  part[2 * blockIdx.x + 1] = t;
+		}
+	}
+
+__global__ void __launch_bounds__(RUN_OFF_THREADS)
+k_runs_offsets (uint64_t ntiles, RunWork wk, const unsigned long long* __restrict__ part)
+	{
+	__shared__ unsigned long long s_h[32], s_t[32];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	unsigned long long h = 0, t = 0;
-	for (uint64_t i = lo; i < hi; i++) { h += wk.cntH[i];  t += wk.cntT[i]; }
+	// totals of the blocks before this one (a few dozen values)
+	unsigned long long bh = 0, bt = 0;
+	for (unsigned int b = lane; b < blockIdx.x; b += 32) { bh += part[2 * b];  bt += part[2 * b + 1]; }
+	#pragma unroll
+	for (int d = 16; d >= 1; d >>= 1) { bh += __shfl_xor_sync (0xffffffffu, bh, d);  bt += __shfl_xor_sync (0xffffffffu, bt, d); }
+	const uint64_t i = (uint64_t) blockIdx.x * RUN_OFF_TILES + threadIdx.x * 4;
+	unsigned int a[4], b[4];
+	run_load4 (wk.cntH, i, ntiles, a);  run_load4 (wk.cntT, i, ntiles, b);
+	const unsigned long long h = (unsigned long long) a[0] + a[1] + a[2] + a[3], t = (unsigned long long) b[0] + b[1] + b[2] + b[3];
 	unsigned long long ih = h, it = t;
 	#pragma unroll
 	for (int d = 1; d < 32; d <<= 1)
@@ -151,21 +184,22 @@ k_runs_offsets (const uint64_t* __restrict__ base, int nseg, uint64_t ntiles, Ru
 		}
 	if (lane == 31) { s_h[warp] = ih;  s_t[warp] = it; }
 	__syncthreads ();
-	unsigned long long eh = ih - h, et = it - t, totH = 0, totT = 0;
-	for (int w = 0; w < 32; w++)
-		{
-		if (w < warp) { eh += s_h[w];  et += s_t[w]; }
-		totH += s_h[w];  totT += s_t[w];
-		}
-	for (uint64_t i = lo; i < hi; i++)
-		{
-		wk.offH[i] = eh;  wk.offT[i] = et;
-		eh += wk.cntH[i];  et += wk.cntT[i];
-		}
-	if (threadIdx.x == 0) { wk.offH[ntiles] = totH;  wk.offT[ntiles] = totT; }
-	__syncthreads ();
-	// first run of every chromosome piece (and the total behind the last one)
-	for (int s = threadIdx.x; s <= nseg; s += RUN_OFF_THREADS) wk.segFirst[s] = (s < nseg) ? wk.offH[base[s]] : totH;
+	unsigned long long eh = bh + ih - h, et = bt + it - t;
+	for (int w = 0; w < warp; w++) { eh += s_h[w];  et += s_t[w]; }
+	for (int k = 0; k < 4; k++)
+		if (i + k <= ntiles)                            // entry ntiles = the totals
+			{
+			wk.offH[i + k] = eh;  wk.offT[i + k] = et;
+			eh += a[k];  et += b[k];
+			}
+	}
+
+// first run of every chromosome piece (and the total behind the last one)
+__global__ void __launch_bounds__(256)
+k_runs_segfirst (const uint64_t* __restrict__ base, int nseg, RunWork wk)
+	{
+	const int s = blockIdx.x * 256 + threadIdx.x;
+	if (s <= nseg) wk.segFirst[s] = wk.offH[base[s]];
 	}
 
 #define RUN_EMIT_THREADS 256
@@ -246,8 +280,9 @@ extern "C" int gdsp_runs (gdsp_ctx* c, const gdsp_layout* L_, const double* sig,
 	const size_t cntB   = (((size_t) tm.ntiles * sizeof (unsigned int)) + 255) / 256 * 256;
 	const size_t offB   = (((size_t) (tm.ntiles + 1) * sizeof (unsigned long long)) + 255) / 256 * 256;
 	const size_t segB   = (((size_t) (L->nseg + 1) * sizeof (unsigned long long)) + 255) / 256 * 256;
+	const size_t partB  = ((((size_t) tm.ntiles + 1) / RUN_OFF_TILES + 1) * 2 * sizeof (unsigned long long) + 255) / 256 * 256;
 	void* ws;
-	GDSP_TRY (gdsp_ws (c, 0, 2 * wordsB + 2 * cntB + 2 * offB + segB, &ws));
+	GDSP_TRY (gdsp_ws (c, 0, 2 * wordsB + 2 * cntB + 2 * offB + segB + partB, &ws));
 	RunWork wk;
 	char* p = (char*) ws;
 	wk.cntH = (unsigned int*) p;            p += cntB;
@@ -255,14 +290,20 @@ extern "C" int gdsp_runs (gdsp_ctx* c, const gdsp_layout* L_, const double* sig,
 	wk.offH = (unsigned long long*) p;      p += offB;
 	wk.offT = (unsigned long long*) p;      p += offB;
 	wk.segFirst = (unsigned long long*) p;  p += segB;
+	unsigned long long* part = (unsigned long long*) p;  p += partB;
 	wk.headW = (uint32_t*) p;               p += wordsB;
 	wk.tailW = (uint32_t*) p;
 	void* wseg = wk.segFirst;
 	GDSP_CUDA (cudaMemsetAsync (wk.cntH, 0, 2 * cntB, c->stream));
-	k_runs_flags<<<(unsigned) tm.ntiles, RUN_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, sig, collapse ? 1 : 0,
+	k_runs_flags<<<(unsigned) (2 * tm.ntiles), RUN_FLAG_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, sig, collapse ? 1 : 0,
 	        showUncovered == 1 ? 1 : 0, wk);
 	GDSP_KERNEL_CHECK ();
-	k_runs_offsets<<<1, RUN_OFF_THREADS, 0, c->stream>>> (tm.d_base, L->nseg, tm.ntiles, wk);
+	const unsigned nob = (unsigned) ((tm.ntiles + 1 + RUN_OFF_TILES - 1) / RUN_OFF_TILES);      // ntiles + 1 offsets
+	k_runs_partial<<<nob, RUN_OFF_THREADS, 0, c->stream>>> (tm.ntiles, wk, part);
+	GDSP_KERNEL_CHECK ();
+	k_runs_offsets<<<nob, RUN_OFF_THREADS, 0, c->stream>>> (tm.ntiles, wk, part);
+	GDSP_KERNEL_CHECK ();
+	k_runs_segfirst<<<(L->nseg + 1 + 255) / 256, 256, 0, c->stream>>> (tm.d_base, L->nseg, wk);
 	GDSP_KERNEL_CHECK ();
 	if (cap > 0)
 		{
