@@ -30,6 +30,7 @@ struct PwOpDev
 	const uint64_t* end;
 	const double*   val;
 	uint64_t        n;
+	const uint2*    tix;     // per tile of this launch: x = first table entry that can touch the tile, y = how many
 	};
 
 struct PwProgram
@@ -42,6 +43,120 @@ struct PwProgram
 #define PW_THREADS 256
 #define PW_TILE    4096
 
+
+// One plain (table-free) operator on N cells held in registers.  The opcode dispatch is a warp-uniform
+// switch paid once per N cells instead of once per cell.
+template <int N>
+__device__ __forceinline__ void pw_plain_op (const PwOpDev& op, double (&v)[N])
+	{
+	const double a = op.a, b = op.b, c = op.c;
+	switch (op.code)
+		{
+		case GDSP_PW_BINARIZE_GT:
+			#pragma unroll
+			for (int e = 0; e < N; e++) v[e] = (v[e] >  a) ? b : c;
+			break;
+		case GDSP_PW_BINARIZE_GE:
+			#pragma unroll
+			for (int e = 0; e < N; e++) v[e] = (v[e] >= a) ? b : c;
+			break;
+		case GDSP_PW_ADDCONST:
+			#pragma unroll
+			for (int e = 0; e < N; e++) v[e] = __dadd_rn (v[e], a);
+			break;
+		case GDSP_PW_ABS:
+			#pragma unroll
+			for (int e = 0; e < N; e++) if (v[e] < 0) v[e] = -v[e];
+			break;
+		case GDSP_PW_CLIP_MIN:
+			#pragma unroll
+			for (int e = 0; e < N; e++) if (v[e] < a) v[e] = a;
+			break;
+		case GDSP_PW_CLIP_MAX:
+			#pragma unroll
+			for (int e = 0; e < N; e++) if (v[e] > a) v[e] = a;
+			break;
+		case GDSP_PW_CLIP_BOTH:
+			#pragma unroll
+			for (int e = 0; e < N; e++) { if (v[e] < a) v[e] = a; else if (v[e] > b) v[e] = b; }
+			break;
+		case GDSP_PW_ERASE:
+			{
+			const bool hmin = op.flags & GDSP_PW_ERASE_HAVE_MIN, hmax = op.flags & GDSP_PW_ERASE_HAVE_MAX;
+			const bool keepIn = op.flags & GDSP_PW_ERASE_KEEP_INSIDE;
+			#pragma unroll
+			for (int e = 0; e < N; e++)
+				{
+				bool kill;
+				if (keepIn) kill = (hmin && v[e] < a) || (hmax && v[e] > b);
+				else        kill = (!hmin || v[e] >= a) && (!hmax || v[e] <= b);
+				if (kill) v[e] = c;
+				}
+			break;
+			}
+		case GDSP_PW_INVERT:
+			#pragma unroll
+			for (int e = 0; e < N; e++) v[e] = __dsub_rn (a, v[e]);
+			break;
+		case GDSP_PW_NONZERO_TO_ONE:
+			#pragma unroll
+			for (int e = 0; e < N; e++) if (v[e] != 0.0) v[e] = 1.0;
+			break;
+		default: break;
+		}
+	}
+
+#define PW_VEC 8
+
+// programs without interval-table operators (few registers: these chains run at the HBM rate)
+__global__ void __launch_bounds__(PW_THREADS, 3)
+k_pointwise (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
+             const double* __restrict__ in, double* __restrict__ out, const __grid_constant__ PwProgram P)
+	{
+	int seg;  uint64_t tis;
+	tile_to_seg (base, nseg, blockIdx.x, seg, tis);
+	const SegDev sd = segs[seg];
+	const uint64_t t0 = sd.lo + tis * PW_TILE;
+	uint64_t t1 = t0 + PW_TILE;  if (t1 > sd.hi) t1 = sd.hi;
+
+	// PW_TILE = PW_THREADS * 16: every thread owns PW_VEC/2 pairs per half tile, pair p of the
+	// warp-wide access q at cell t0 + 2*(q*PW_THREADS + tid): 128-bit coalesced accesses
+	#pragma unroll 1
+	for (uint32_t half = 0; half < PW_TILE / (PW_THREADS * PW_VEC); half++)
+		{
+		double v[PW_VEC];
+		const uint64_t h0 = t0 + (uint64_t) half * (PW_THREADS * PW_VEC);
+		if (h0 >= t1) break;
+		#pragma unroll
+		for (int q = 0; q < PW_VEC / 2; q++)
+			{
+			const uint64_t i = h0 + 2 * ((uint64_t) q * PW_THREADS + threadIdx.x);
+			if (i + 1 < t1) { double2 x = ldg_stream (in + i);  v[2*q] = x.x;  v[2*q+1] = x.y; }
+			else            { v[2*q] = (i < t1) ? in[i] : 0.0;  v[2*q+1] = 0.0; }
+			}
+		for (int i = 0; i < P.nops; i++) pw_plain_op<PW_VEC> (P.ops[i], v);
+		#pragma unroll
+		for (int q = 0; q < PW_VEC / 2; q++)
+			{
+			const uint64_t i = h0 + 2 * ((uint64_t) q * PW_THREADS + threadIdx.x);
+			if (i + 1 < t1) stg_stream (out + i, make_double2 (v[2*q], v[2*q+1]));
+			else if (i < t1) out[i] = v[2*q];
+			}
+		}
+	}
+
+// ---------------------------------------------------------------------------
+// Programs with interval-table operators (add/subtract/multiply/divide/mask/masknot/or/and/...).
+// The first version searched the table once per cell (two dependent global loads per step, then end[k]
+// and val[k]): a five-operator chain ran at a fifth of the plain chains' rate.  Now
+//   k_ivl_tile_index  finds, once per launch and table, the slice of table entries that can touch
+//                     every tile (all tiles in parallel, so the search latency is hidden), and
+//   k_pointwise_ivl   PAINTS the slice into a shared-memory array of one 16-bit entry index per cell
+//                     (warp per interval for sparse slices, thread per interval for dense ones) and
+//                     then reads one entry per cell -- no search; consecutive operators on the same
+//                     table (add B = multiply B = and B) share the painted array.
+// ---------------------------------------------------------------------------
+
 // index of the last interval with start <= g inside [lo,hi), or lo-1
 __device__ __forceinline__ int64_t ivl_find (const uint64_t* __restrict__ start, int64_t lo, int64_t hi, uint64_t g)
 	{
@@ -53,163 +168,126 @@ __device__ __forceinline__ int64_t ivl_find (const uint64_t* __restrict__ start,
 	return lo - 1;
 	}
 
-// Apply the whole program to PW_VEC cells held in registers.  The operator
-// loop is the OUTER loop, so the opcode dispatch (a warp-uniform switch) is paid
-// once per PW_VEC cells instead of once per cell.
-#define PW_VEC 8
-
-template <bool HAS_IVL>
-__device__ __forceinline__ void pw_apply_vec (const PwProgram& P, double (&v)[PW_VEC], const uint64_t (&g)[PW_VEC],
-                                              const int64_t* s_klo, const int64_t* s_khi)
+__global__ void __launch_bounds__(256)
+k_ivl_tile_index (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg, uint64_t ntiles,
+                  const uint64_t* __restrict__ start, uint64_t n, uint2* __restrict__ tix)
 	{
-	const uint64_t* cachedStart = NULL;          // table whose search results are in kc[]
-	int kc[PW_VEC];                              // k - klo of the last search (same klo for the same table)
-	#pragma unroll
-	for (int e = 0; e < PW_VEC; e++) kc[e] = -1;
-	for (int i = 0; i < P.nops; i++)
+	const uint64_t tile = (uint64_t) blockIdx.x * 256 + threadIdx.x;
+	if (tile >= ntiles) return;
+	int lo = 0, hi = nseg - 1;                        // segment of the tile (plain bisection: one thread per tile)
+	while (lo < hi)
 		{
-		const PwOpDev& op = P.ops[i];
-		const double a = op.a, b = op.b, c = op.c;
-		switch (op.code)
-			{
-			case GDSP_PW_BINARIZE_GT:
-				#pragma unroll
-				for (int e = 0; e < PW_VEC; e++) v[e] = (v[e] >  a) ? b : c;
-				break;
-			case GDSP_PW_BINARIZE_GE:
-				#pragma unroll
-				for (int e = 0; e < PW_VEC; e++) v[e] = (v[e] >= a) ? b : c;
-				break;
-			case GDSP_PW_ADDCONST:
-				#pragma unroll
-				for (int e = 0; e < PW_VEC; e++) v[e] = __dadd_rn (v[e], a);
-				break;
-			case GDSP_PW_ABS:
-				#pragma unroll
-				for (int e = 0; e < PW_VEC; e++) if (v[e] < 0) v[e] = -v[e];
-				break;
-			case GDSP_PW_CLIP_MIN:
-				#pragma unroll
-				for (int e = 0; e < PW_VEC; e++) if (v[e] < a) v[e] = a;
-				break;
-			case GDSP_PW_CLIP_MAX:
-				#pragma unroll
-				for (int e = 0; e < PW_VEC; e++) if (v[e] > a) v[e] = a;
-				break;
-			case GDSP_PW_CLIP_BOTH:
-				#pragma unroll
-				for (int e = 0; e < PW_VEC; e++) { if (v[e] < a) v[e] = a; else if (v[e] > b) v[e] = b; }
-				break;
-			case GDSP_PW_ERASE:
-				{
-				const bool hmin = op.flags & GDSP_PW_ERASE_HAVE_MIN, hmax = op.flags & GDSP_PW_ERASE_HAVE_MAX;
-				const bool keepIn = op.flags & GDSP_PW_ERASE_KEEP_INSIDE;
-				#pragma unroll
-				for (int e = 0; e < PW_VEC; e++)
-					{
-					bool kill;
-					if (keepIn) kill = (hmin && v[e] < a) || (hmax && v[e] > b);
-					else        kill = (!hmin || v[e] >= a) && (!hmax || v[e] <= b);
-					if (kill) v[e] = c;
-					}
-				break;
-				}
-			case GDSP_PW_INVERT:
-				#pragma unroll
-				for (int e = 0; e < PW_VEC; e++) v[e] = __dsub_rn (a, v[e]);
-				break;
-			case GDSP_PW_NONZERO_TO_ONE:
-				#pragma unroll
-				for (int e = 0; e < PW_VEC; e++) if (v[e] != 0.0) v[e] = 1.0;
-				break;
-			default:
-				if (HAS_IVL)
-				{
-				// interval-table operators: one search per cell inside the tile's slice of the table;
-				// consecutive operators on the SAME table (add B = multiply B = and B ...) reuse it
-				const int64_t klo = s_klo[i], khi = s_khi[i];
-				const bool reuse = (op.start == cachedStart);
-				cachedStart = op.start;
-				#pragma unroll
-				for (int e = 0; e < PW_VEC; e++)
-					{
-					const int64_t k = reuse ? klo + kc[e] : ivl_find (op.start, klo, khi, g[e]);
-					kc[e] = (int) (k - klo);
-					const bool inside = (k >= klo) && (g[e] < op.end[k]);
-					switch (op.code)
-						{
-						case GDSP_PW_IVL_ADD: if (inside) v[e] = __dadd_rn (v[e], op.val[k]);  break;
-						case GDSP_PW_IVL_SUB: if (inside) v[e] = __dsub_rn (v[e], op.val[k]);  break;
-						case GDSP_PW_IVL_MUL: v[e] = inside ? __dmul_rn (v[e], op.val[k]) : a;  break;
-						case GDSP_PW_IVL_DIV: v[e] = inside ? __ddiv_rn (v[e], op.val[k]) : ((v[e] >= 0) ? a : -a);  break;
-						case GDSP_PW_IVL_SET: if (inside) v[e] = a;  break;
-						case GDSP_PW_IVL_SET_OUTSIDE: if (!inside) v[e] = a;  break;
-						case GDSP_PW_IVL_ASSIGN: if (inside) v[e] = op.val[k];  break;
-						case GDSP_PW_IVL_MIN: if (inside) { const double w = op.val[k];  if (w < v[e]) v[e] = w; }  break;
-						case GDSP_PW_IVL_MAX: if (inside) { const double w = op.val[k];  if (w > v[e]) v[e] = w; }  break;
-						case GDSP_PW_IVL_KEEP_AT: if (!(inside && (double) g[e] == op.val[k])) v[e] = a;  break;
-						case GDSP_PW_IVL_ACCUM_CLEAR: if (inside) v[e] = (v[e] == a) ? op.val[k] : __dadd_rn (v[e], op.val[k]);  break;
-						}
-					}
-				}
-			}
+		const int mid = (lo + hi + 1) >> 1;
+		if (base[mid] <= tile) lo = mid; else hi = mid - 1;
 		}
+	const SegDev sd = segs[lo];
+	const uint64_t t0 = sd.lo + (tile - base[lo]) * PW_TILE;
+	uint64_t t1 = t0 + PW_TILE;  if (t1 > sd.hi) t1 = sd.hi;
+	// the last entry starting at or before t0 (it may cover t0) up to the last entry starting before t1
+	int64_t a = ivl_find (start, 0, (int64_t) n, t0);
+	const int64_t b = ivl_find (start, 0, (int64_t) n, t1 - 1);
+	if (a < 0) a = 0;
+	tix[tile] = make_uint2 ((unsigned) a, (unsigned) (b + 1 - a));
 	}
 
-// HAS_IVL = false: programs without interval-table operators get a kernel without the table code
-// (fewer registers: the plain chains run at the HBM rate)
-template <bool HAS_IVL>
+#define PW_IVL_CELLS 16         // cells per thread: the whole tile stays in registers across the program
+
 __global__ void __launch_bounds__(PW_THREADS, 3)
-k_pointwise (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
-             const double* __restrict__ in, double* __restrict__ out, const __grid_constant__ PwProgram P)
+k_pointwise_ivl (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
+                 const double* __restrict__ in, double* __restrict__ out, const __grid_constant__ PwProgram P)
 	{
-	__shared__ int64_t s_klo[GDSP_MAX_POINTWISE], s_khi[GDSP_MAX_POINTWISE];
+	__shared__ __align__(16) short s_idx[PW_TILE];    // table entry (relative to the slice) covering the cell, or -1
 	int seg;  uint64_t tis;
 	tile_to_seg (base, nseg, blockIdx.x, seg, tis);
 	const SegDev sd = segs[seg];
 	const uint64_t t0 = sd.lo + tis * PW_TILE;
 	uint64_t t1 = t0 + PW_TILE;  if (t1 > sd.hi) t1 = sd.hi;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-	if (HAS_IVL)
+	// pair q of the thread at cell t0 + 2*(q*PW_THREADS + tid): 128-bit coalesced accesses
+	double v[PW_IVL_CELLS];
+	#pragma unroll
+	for (int q = 0; q < PW_IVL_CELLS / 2; q++)
 		{
-		// range of table entries that can touch [t0,t1): the last entry starting
-		// at or before t0 (it may cover t0) up to the last entry starting before t1
-		if (threadIdx.x < P.nops && P.ops[threadIdx.x].code >= GDSP_PW_IVL_ADD)
-			{
-			const PwOpDev& op = P.ops[threadIdx.x];
-			int64_t a = ivl_find (op.start, 0, (int64_t) op.n, t0);
-			int64_t b = ivl_find (op.start, 0, (int64_t) op.n, t1 - 1);
-			s_klo[threadIdx.x] = (a < 0) ? 0 : a;
-			s_khi[threadIdx.x] = b + 1;
-			}
-		__syncthreads ();
+		const uint64_t i = t0 + 2 * ((uint64_t) q * PW_THREADS + threadIdx.x);
+		if (i + 1 < t1) { double2 x = ldg_stream (in + i);  v[2*q] = x.x;  v[2*q+1] = x.y; }
+		else            { v[2*q] = (i < t1) ? in[i] : 0.0;  v[2*q+1] = 0.0; }
 		}
 
-	// PW_TILE = PW_THREADS * 16: every thread owns PW_VEC/2 pairs per half tile, pair p of the
-	// warp-wide access q at cell t0 + 2*(q*PW_THREADS + tid): 128-bit coalesced accesses
-	#pragma unroll 1
-	for (uint32_t half = 0; half < PW_TILE / (PW_THREADS * PW_VEC); half++)
+	const uint64_t* painted = NULL;                   // table whose slice is in s_idx
+	uint32_t klo = 0;
+	for (int i = 0; i < P.nops; i++)
 		{
-		double   v[PW_VEC];
-		uint64_t g[PW_VEC];
-		const uint64_t h0 = t0 + (uint64_t) half * (PW_THREADS * PW_VEC);
-		if (h0 >= t1) break;
-		#pragma unroll
-		for (int q = 0; q < PW_VEC / 2; q++)
+		const PwOpDev& op = P.ops[i];
+		if (op.code < GDSP_PW_IVL_ADD) { pw_plain_op<PW_IVL_CELLS> (op, v);  continue; }
+		if (op.start != painted)
 			{
-			const uint64_t i = h0 + 2 * ((uint64_t) q * PW_THREADS + threadIdx.x);
-			g[2*q] = i;  g[2*q+1] = i + 1;
-			if (i + 1 < t1) { double2 x = ldg_stream (in + i);  v[2*q] = x.x;  v[2*q+1] = x.y; }
-			else            { v[2*q] = (i < t1) ? in[i] : 0.0;  v[2*q+1] = 0.0; }
+			painted = op.start;
+			__syncthreads ();                         // readers of the previous table are done
+			#pragma unroll
+			for (int j = 0; j < PW_TILE / 8 / PW_THREADS; j++)
+				reinterpret_cast<uint4*> (s_idx)[j * PW_THREADS + threadIdx.x] = make_uint4 (~0u, ~0u, ~0u, ~0u);
+			__syncthreads ();
+			const uint2 tx = op.tix[blockIdx.x];
+			klo = tx.x;
+			const uint32_t cnt = tx.y;
+			if (cnt > 128)
+				{
+				// dense slice (short intervals): one thread per entry
+				for (uint32_t j = threadIdx.x; j < cnt; j += PW_THREADS)
+					{
+					const uint64_t st = op.start[klo + j], en = op.end[klo + j];
+					const uint32_t ca = (uint32_t) ((st > t0 ? st : t0) - t0);
+					const uint32_t cb = (en <= t0) ? 0u : (uint32_t) ((en < t1 ? en : t1) - t0);
+					for (uint32_t cc = ca; cc < cb; cc++) s_idx[cc] = (short) j;
+					}
+				}
+			else
+				{
+				for (uint32_t j = warp; j < cnt; j += PW_THREADS / 32)
+					{
+					const uint64_t st = op.start[klo + j], en = op.end[klo + j];
+					const uint32_t ca = (uint32_t) ((st > t0 ? st : t0) - t0);
+					const uint32_t cb = (en <= t0) ? 0u : (uint32_t) ((en < t1 ? en : t1) - t0);
+					for (uint32_t cc = ca + lane; cc < cb; cc += 32) s_idx[cc] = (short) j;
+					}
+				}
+			__syncthreads ();
 			}
-		pw_apply_vec<HAS_IVL> (P, v, g, s_klo, s_khi);
-		#pragma unroll
-		for (int q = 0; q < PW_VEC / 2; q++)
+		const double a = op.a;
+		const double* __restrict__ val = op.val + klo;
+		// entry index of each cell (-1 outside every interval): one 32-bit shared-memory load per pair of cells
+		#define PW_EACH(body) _Pragma("unroll") for (int q = 0; q < PW_IVL_CELLS / 2; q++) \
+			{ const uint32_t pairIdx = reinterpret_cast<const uint32_t*> (s_idx)[q * PW_THREADS + threadIdx.x]; \
+			  _Pragma("unroll") for (int h = 0; h < 2; h++) \
+				{ const int e = 2 * q + h;  const int j = (int) (short) (pairIdx >> (16 * h));  const bool inside = (j >= 0);  body } }
+		switch (op.code)
 			{
-			const uint64_t i = g[2*q];
-			if (i + 1 < t1) stg_stream (out + i, make_double2 (v[2*q], v[2*q+1]));
-			else if (i < t1) out[i] = v[2*q];
+			case GDSP_PW_IVL_ADD: PW_EACH (if (inside) v[e] = __dadd_rn (v[e], val[j]);)  break;
+			case GDSP_PW_IVL_SUB: PW_EACH (if (inside) v[e] = __dsub_rn (v[e], val[j]);)  break;
+			case GDSP_PW_IVL_MUL: PW_EACH (v[e] = inside ? __dmul_rn (v[e], val[j]) : a;)  break;
+			case GDSP_PW_IVL_DIV: PW_EACH (v[e] = inside ? __ddiv_rn (v[e], val[j]) : ((v[e] >= 0) ? a : -a);)  break;
+			case GDSP_PW_IVL_SET: PW_EACH (if (inside) v[e] = a;)  break;
+			case GDSP_PW_IVL_SET_OUTSIDE: PW_EACH (if (!inside) v[e] = a;)  break;
+			case GDSP_PW_IVL_ASSIGN: PW_EACH (if (inside) v[e] = val[j];)  break;
+			case GDSP_PW_IVL_MIN: PW_EACH (if (inside) { const double w = val[j];  if (w < v[e]) v[e] = w; })  break;
+			case GDSP_PW_IVL_MAX: PW_EACH (if (inside) { const double w = val[j];  if (w > v[e]) v[e] = w; })  break;
+			case GDSP_PW_IVL_KEEP_AT:
+				PW_EACH (const uint64_t g = t0 + 2 * ((uint64_t) (e >> 1) * PW_THREADS + threadIdx.x) + (e & 1);
+				         if (!(inside && (double) g == val[j])) v[e] = a;)
+				break;
+			case GDSP_PW_IVL_ACCUM_CLEAR: PW_EACH (if (inside) v[e] = (v[e] == a) ? val[j] : __dadd_rn (v[e], val[j]);)  break;
+			default: break;
 			}
+		#undef PW_EACH
+		}
+
+	#pragma unroll
+	for (int q = 0; q < PW_IVL_CELLS / 2; q++)
+		{
+		const uint64_t i = t0 + 2 * ((uint64_t) q * PW_THREADS + threadIdx.x);
+		if (i + 1 < t1) stg_stream (out + i, make_double2 (v[2*q], v[2*q+1]));
+		else if (i < t1) out[i] = v[2*q];
 		}
 	}
 
@@ -358,8 +436,36 @@ extern "C" int gdsp_pointwise (gdsp_ctx* c, const gdsp_layout* L_, const double*
 		}
 	TileMap tm;
 	GDSP_TRY (gdsp_layout_tilemap (L, PW_TILE, &tm));
-	if (P.hasIvl) k_pointwise<true><<<(unsigned) tm.ntiles, PW_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, in, out, P);
-	else          k_pointwise<false><<<(unsigned) tm.ntiles, PW_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, in, out, P);
+	if (tm.ntiles == 0) return GDSP_OK;
+	if (!P.hasIvl)
+		{
+		k_pointwise<<<(unsigned) tm.ntiles, PW_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, in, out, P);
+		GDSP_KERNEL_CHECK ();
+		return GDSP_OK;
+		}
+	// one tile index per distinct table of the program
+	const uint64_t* distinct[GDSP_MAX_POINTWISE];
+	int nd = 0;
+	for (int i = 0; i < nops; i++)
+		if (P.ops[i].code >= GDSP_PW_IVL_ADD)
+			{
+			int d = 0;
+			while (d < nd && distinct[d] != P.ops[i].start) d++;
+			if (d == nd) distinct[nd++] = P.ops[i].start;
+			}
+	void* ws;
+	GDSP_TRY (gdsp_ws (c, 3, (size_t) nd * tm.ntiles * sizeof (uint2), &ws));
+	for (int d = 0; d < nd; d++)
+		{
+		uint2* tix = (uint2*) ws + (size_t) d * tm.ntiles;
+		uint64_t n = 0;
+		for (int i = 0; i < nops; i++)
+			if (P.ops[i].code >= GDSP_PW_IVL_ADD && P.ops[i].start == distinct[d]) { P.ops[i].tix = tix;  n = P.ops[i].n; }
+		GDSP_REQUIRE (n < 0xffffffffull, "gdsp_pointwise: interval table with 2^32 or more entries");
+		k_ivl_tile_index<<<(unsigned) ((tm.ntiles + 255) / 256), 256, 0, c->stream>>> (L->d, tm.d_base, L->nseg, tm.ntiles, distinct[d], n, tix);
+		GDSP_KERNEL_CHECK ();
+		}
+	k_pointwise_ivl<<<(unsigned) tm.ntiles, PW_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, in, out, P);
 	GDSP_KERNEL_CHECK ();
 	return GDSP_OK;
 	}
