@@ -340,7 +340,7 @@ def run_gpu_arm(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": "hg38-shaped 24 chromosomes, %d bases%s; %d intervals (reads U{50..150}, depth %d); "
-                                   "step = depth accumulation (int32 difference array + segmented scan) + smooth "
+                                   "step = depth accumulation (reads binned per 8192-cell tile, shared-memory difference + scan per tile) + smooth "
                                    "--window=%d" % (total_bases, "" if args.scale == 1 else " (lengths / %d)" % args.scale,
                                                     n_iv_total, DEPTH, WINDOW),
                        "l2": "inputs larger than L2 (%.1f GB signal per GPU)" % (8.0 * per_gpu_bases / 1e9),
