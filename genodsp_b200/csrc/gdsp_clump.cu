@@ -943,12 +943,10 @@ extern "C" int gdsp_clump (gdsp_ctx* c, const gdsp_layout* L_, double* sig, uint
 		wf.segAllNeg = (int*) p;
 		const uint32_t reach = maxLmin ? maxLmin : 1;
 		const size_t smem = ((size_t) ((reach + CLF_GROUP - 1) / CLF_GROUP) + CLF_GROUPS) * (CLF_GROUP / 16 * 17) * sizeof (double);
-		static size_t smemSet = 0;
-		if (smem > smemSet)
+		if (smem > 48 * 1024)
 			{
 			GDSP_CUDA (cudaFuncSetAttribute (k_clump_mark<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 			GDSP_CUDA (cudaFuncSetAttribute (k_clump_mark<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-			smemSet = smem;
 			}
 
 		k_fill_int<<<(L->nseg + 255) / 256, 256, 0, c->stream>>> (wf.segAllNeg, L->nseg, 1);

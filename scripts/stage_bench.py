@@ -77,6 +77,28 @@ def main():
         rec("binarize", timed(lambda: g.binarize(6.0), reset), 16)
         rec("pointwise_chain5", timed(lambda: g.pointwise([G.op_addconst(-1.5), G.op_abs(), G.op_clip(0.5, 6.0), G.op_invert(2.0),
                                                            G.op_binarize(-1.0)]), reset), 16)
+    if on("ivl"):
+        # cfg5's second track: sorted disjoint intervals covering ~50 %, values k/1024; the whole chain
+        # add B = multiply B = mask B = and B = binarize is ONE launch
+        import numpy as np
+        from genodsp_b200 import capi
+        rng = np.random.default_rng(99)
+        bs, bstart, bend, bval = [], [], [], []
+        for k, (lo, hi, dlo, dhi, pos0, clen) in enumerate(g.segs):
+            n = hi - lo
+            m = max(1, n // 2000)
+            cuts = np.sort(rng.choice(np.arange(pos0, pos0 + n, dtype=np.int64), size=min(2 * m, n), replace=False))
+            a, b = cuts[0::2], cuts[1::2]
+            m2 = min(a.size, b.size)
+            bs.append(np.full(m2, k, np.uint32)); bstart.append(a[:m2].astype(np.uint32)); bend.append(b[:m2].astype(np.uint32))
+            bval.append(rng.integers(1, 2048, m2) / 1024.0)
+        tableB = g.interval_table(np.concatenate(bs), np.concatenate(bstart), np.concatenate(bend), np.concatenate(bval))
+        chain5 = [(capi.PW_IVL_ADD, 0.0, 0, 0, 0, tableB), (capi.PW_IVL_MUL, 0.0, 0, 0, 0, tableB),
+                  (capi.PW_IVL_SET, 0.0, 0, 0, 0, tableB), (capi.PW_NONZERO_TO_ONE, 0.0),
+                  (capi.PW_IVL_SET_OUTSIDE, 0.0, 0, 0, 0, tableB), G.op_binarize(0.5)]
+        rec("ivl_chain_cfg5", timed(lambda: g.pointwise(chain5), reset), 16)
+        rec("ivl_multiply_only", timed(lambda: g.pointwise(chain5[1:2]), reset), 16)
+        tableB.close()
     if on("cumulativesum"):
         rec("cumulativesum", timed(lambda: g.cumulativesum(), reset), 16)
     if on("percentile"):

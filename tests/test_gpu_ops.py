@@ -569,6 +569,15 @@ def test_clump_long_runs_and_halo_edges(genome, orc, L):
     compare(genome, inputs, lambda v: orc.clump(v, 1.5, L, False, 7.0, 0.5), what="anticlump long runs L=%d" % L)
 
 
+def test_clump_stored_prefix_passes_on_short_lengths(genome, orc, monkeypatch):
+    """the stored-prefix passes (normally only for minimum lengths above 4096) on short ones"""
+    monkeypatch.setenv("GDSP_CLUMP_STORED", "1")
+    for L in (3, 300):
+        inputs = load(genome, np.random.default_rng(L), "int")
+        genome.clump(5.5, L)
+        compare(genome, inputs, lambda v: orc.clump(v, 5.5, L, True), what="stored-prefix clump L=%d" % L)
+
+
 def test_clump_all_below_and_relative_length(genome, orc):
     inputs = load(genome, np.random.default_rng(0), "int")
     genome.clump(1000.0, 10)
