@@ -190,6 +190,7 @@ k_ivl_tile_index (const SegDev* __restrict__ segs, const uint64_t* __restrict__ 
 	tix[tile] = make_uint2 ((unsigned) a, (unsigned) (b + 1 - a));
 	}
 
+#define PW_EARLY     64         // slice entries of the first table staged early
 #define PW_IVL_CELLS 16         // cells per thread: the whole tile stays in registers across the program
 
 __global__ void __launch_bounds__(PW_THREADS, 3)
@@ -204,6 +205,14 @@ k_pointwise_ivl (const SegDev* __restrict__ segs, const uint64_t* __restrict__ b
 	uint64_t t1 = t0 + PW_TILE;  if (t1 > sd.hi) t1 = sd.hi;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
+	// The slice of the program's FIRST table is fetched while the signal loads are in flight: its tile
+	// index entry first, then (sparse slices) the clipped bounds of its intervals into shared memory --
+	// otherwise two dependent global round trips sit between the barriers of the paint step of every tile
+	__shared__ uint32_t s_ca[PW_EARLY], s_cb[PW_EARLY];
+	int firstIvl = 0;
+	while (firstIvl < P.nops && P.ops[firstIvl].code < GDSP_PW_IVL_ADD) firstIvl++;       // < nops: the program has one
+	const uint2 tx0 = P.ops[firstIvl].tix[blockIdx.x];
+
 	// pair q of the thread at cell t0 + 2*(q*PW_THREADS + tid): 128-bit coalesced accesses
 	double v[PW_IVL_CELLS];
 	#pragma unroll
@@ -212,6 +221,12 @@ k_pointwise_ivl (const SegDev* __restrict__ segs, const uint64_t* __restrict__ b
 		const uint64_t i = t0 + 2 * ((uint64_t) q * PW_THREADS + threadIdx.x);
 		if (i + 1 < t1) { double2 x = ldg_stream (in + i);  v[2*q] = x.x;  v[2*q+1] = x.y; }
 		else            { v[2*q] = (i < t1) ? in[i] : 0.0;  v[2*q+1] = 0.0; }
+		}
+	if (tx0.y <= PW_EARLY && threadIdx.x < tx0.y)
+		{
+		const uint64_t st = P.ops[firstIvl].start[tx0.x + threadIdx.x], en = P.ops[firstIvl].end[tx0.x + threadIdx.x];
+		s_ca[threadIdx.x] = (uint32_t) ((st > t0 ? st : t0) - t0);
+		s_cb[threadIdx.x] = (en <= t0) ? 0u : (uint32_t) ((en < t1 ? en : t1) - t0);
 		}
 
 	const uint64_t* painted = NULL;                   // table whose slice is in s_idx
@@ -228,10 +243,19 @@ k_pointwise_ivl (const SegDev* __restrict__ segs, const uint64_t* __restrict__ b
 			for (int j = 0; j < PW_TILE / 8 / PW_THREADS; j++)
 				reinterpret_cast<uint4*> (s_idx)[j * PW_THREADS + threadIdx.x] = make_uint4 (~0u, ~0u, ~0u, ~0u);
 			__syncthreads ();
-			const uint2 tx = op.tix[blockIdx.x];
+			const uint2 tx = (i == firstIvl) ? tx0 : op.tix[blockIdx.x];
 			klo = tx.x;
 			const uint32_t cnt = tx.y;
-			if (cnt > 128)
+			if (i == firstIvl && cnt <= PW_EARLY)
+				{
+				// bounds already in shared memory (the barrier above ordered their stores)
+				for (uint32_t j = warp; j < cnt; j += PW_THREADS / 32)
+					{
+					const uint32_t ca = s_ca[j], cb = s_cb[j];
+					for (uint32_t cc = ca + lane; cc < cb; cc += 32) s_idx[cc] = (short) j;
+					}
+				}
+			else if (cnt > 128)
 				{
 				// dense slice (short intervals): one thread per entry
 				for (uint32_t j = threadIdx.x; j < cnt; j += PW_THREADS)
