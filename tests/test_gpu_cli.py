@@ -159,6 +159,21 @@ def test_progress_protocol(data):
                            "--quiet", "=", "binarize", "--threshold=percentile50"])
 
 
+def test_percentile_then_binarize_variants(data):
+    """the executor hands the sorted post-percentile state to `binarize` without sorting it
+    (gd_ops_percentile.c / gdsp_sorted_binarize); every variant must still print the reference's bytes"""
+    # ties above, custom one/zero, a pointwise operator behind the binarize in the same fused chain
+    assert_same(data, C + ["--novalue", "=", "percentile", "90", "=", "binarize", "--threshold=percentile90", "--ties:above",
+                           "--one=3", "--zero=-1", "=", "addconst", "2"])
+    # a literal threshold that is not the percentile, and a windowed operator behind it
+    assert_same(data, C + ["--novalue", "=", "percentile", "95", "--quiet", "=", "binarize", "4", "=", "dilate", "5"])
+    # last rank in the FIRST chromosome: the reference's bubble passes, not a global sort -- the hand-over must not fire
+    assert_same(data, C + ["--novalue", "=", "percentile", "40", "=", "binarize", "--threshold=percentile40"])
+    # several percentiles, the threshold is the lowest one; and the same under the operations trace
+    assert_same(data, C + ["--novalue", "=", "percentile", "90..99", "=", "binarize", "--threshold=percentile90"])
+    assert_same(data, C + ["--novalue", "--progress=operations", "=", "percentile", "97", "=", "binarize", "--threshold=percentile97"])
+
+
 def test_errors_match(data):
     for args in (C + ["=", "nosuchop"], C + ["--novalue", "=", "smooth", "--window=0"], C + ["--bogus"],
                  C + ["--novalue", "=", "binarize", "--threshold=nosuchvar"]):
