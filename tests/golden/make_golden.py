@@ -45,6 +45,19 @@ CASES = {
                           "trackB.iv", "=", "binarize", "0.5"], "reads.iv"),
     "pointwise": (C + ["--novalue", "--precision=3", "=", "addconst", "-4.5", "=", "abs", "=", "clip", "--min=1", "--max=3.5",
                        "=", "invert", "=", "erase", "--min=2", "--max=3"], "reads.iv"),
+    # the interval-file operators (add.c, multiply.c, mask.c, logical.c, minmax.c, map.c)
+    "subtract_divide": (C + ["--novalue", "--precision=4", "=", "subtract", "trackB.iv", "--value=4", "=", "divide", "trackB.iv",
+                             "--value=4", "--infinity=999"], "reads.iv"),
+    "or_mask_masknot": (C + ["--novalue", "=", "or", "trackB.iv", "--value=4", "=", "mask", "maskM.iv", "--mask=7", "=", "masknot",
+                             "trackB.iv", "--mask=-2"], "reads.iv"),
+    "minover": (C + ["--novalue", "=", "minover", "trackB.iv", "--infinity=99"], "reads.iv"),
+    "maxover": (C + ["--novalue", "=", "maxover", "trackB.iv", "--zero=-1"], "reads.iv"),
+    "minwith_maxwith": (C + ["--novalue", "--precision=3", "=", "minwith", "trackB.iv", "--value=4", "=", "maxwith", "vals.iv", "--value=4"], "reads.iv"),
+    "map": (C + ["--novalue", "--precision=4", "=", "map", "depth.map"], "reads.iv"),
+    # under --novalue an operator's file is read without values too (every value 1) unless it says --value=
+    "add_multiply_values": (C + ["--novalue", "--precision=5", "=", "add", "trackB.iv", "--value=4", "=", "multiply", "trackB.iv",
+                                 "--value=4"], "reads.iv"),
+    "subtract_novalue_inherited": (C + ["--novalue", "=", "subtract", "trackB.iv"], "reads.iv"),
 }
 
 
@@ -72,6 +85,16 @@ def write_inputs():
                 e = min(l, pos + int(rng.integers(1, 600)))
                 f.write("%s\t%d\t%d\t%s\n" % (n, pos, e, repr(float(rng.integers(1, 4096)) / 1024)))
                 pos = e + int(rng.integers(1, 600))
+    # (generated after the files above so that those keep their bytes)
+    with open(os.path.join(HERE, "maskM.iv"), "w") as f:           # unsorted, overlapping, no value column
+        for _ in range(60):
+            n, l = CHROMS[int(rng.integers(0, 3))]
+            a = int(rng.integers(0, l - 300))
+            f.write("%s\t%d\t%d\n" % (n, a, a + int(rng.integers(1, 300))))
+    with open(os.path.join(HERE, "depth.map"), "w") as f:          # piecewise-linear map of the depth values
+        f.write("# depth -> score\n")
+        for x in rng.permutation(np.arange(0, 26, 2)):
+            f.write("%r %r\n" % (float(x), float(rng.integers(-40, 41)) / 8))
 
 
 def main():

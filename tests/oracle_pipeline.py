@@ -98,6 +98,13 @@ class Pipeline:
     def apply(self, op, opts):
         name, args = op[0], op[1:]
         o = self.orc
+        # an operator's interval file is read with the global value column unless it says otherwise
+        # (so under --novalue every file value is 1)
+        fcol = opts["val_col"]
+        if "--novalue" in args:
+            fcol = -1
+        elif self.kw(args, ["--value="]) is not None:
+            fcol = int(self.kw(args, ["--value="])) - 1
         pos = [a for a in args if not a.startswith("--")]
         if name == "sum":
             W = _unit(self.kw(args, ["--window="], "100"))
@@ -172,18 +179,51 @@ class Pipeline:
             at = 0                          # the reference's post-state: globally sorted genome
             for n in names:
                 self.v[n] = srt[at:at + self.v[n].size].copy(); at += self.v[n].size
-        elif name in ("add", "multiply", "and"):
-            iv = self.read_intervals(pos[0], 3)
+        elif name in ("add", "subtract", "multiply", "divide", "and", "masknot"):
+            iv = self.read_intervals(pos[0], -1 if name == "masknot" else fcol)    # masknot reads no value column (mask.c:533)
             for n, _ in self.chroms:
                 s, e, val = iv[n]
-                keep = [i for i, x in enumerate(val) if x != 0.0]
+                keep = [i for i, x in enumerate(val) if x != 0.0]                  # val==0 lines are skipped
                 s = [s[i] for i in keep]; e = [e[i] for i in keep]; val = [val[i] for i in keep]
-                if name == "add":
-                    o.add_intervals(self.v[n], s, e, val, 1.0)
+                if name in ("add", "subtract"):
+                    o.add_intervals(self.v[n], s, e, val, 1.0 if name == "add" else -1.0)
                 elif name == "multiply":
                     o.sorted_intervals(self.v[n], s, e, val, 0, 0.0)
+                elif name == "divide":
+                    o.sorted_intervals(self.v[n], s, e, val, 1, _num(self.kw(args, ["--infinity="], "inf")))
+                elif name == "masknot":
+                    o.sorted_intervals(self.v[n], s, e, val, 2, float(self.kw(args, ["--mask=", "M="], "0")))
                 else:
                     o.sorted_intervals(o.logical_prep(self.v[n]), s, e, val, 3, 0.0)
+        elif name in ("mask", "or"):
+            iv = self.read_intervals(pos[0], -1 if name == "mask" else fcol)
+            for n, _ in self.chroms:
+                s, e, val = iv[n]
+                if name == "mask":
+                    o.mask_intervals(self.v[n], s, e, float(self.kw(args, ["--mask=", "M="], "0")))
+                else:
+                    o.or_intervals(o.logical_prep(self.v[n]), s, e, val)
+        elif name in ("minover", "maxover"):
+            iv = self.read_intervals(pos[0], -1)
+            fill = _num(self.kw(args, ["--infinity="], "inf")) if name == "minover" else float(self.kw(args, ["--zero="], "0"))
+            for n, _ in self.chroms:
+                s, e, _val = iv[n]
+                self.v[n] = o.over_intervals(self.v[n], s, e, name == "maxover", fill)
+        elif name in ("minwith", "maxwith"):
+            iv = self.read_intervals(pos[0], fcol)
+            for n, _ in self.chroms:
+                s, e, val = iv[n]
+                self.v[n] = o.with_intervals(self.v[n], s, e, val, name == "maxwith")
+        elif name == "map":
+            pts = []
+            for line in open(os.path.join(self.cwd, pos[0])):
+                f = line.split()
+                if f and not f[0].startswith("#"):
+                    pts.append((float(f[0]), float(f[1])))
+            pts.sort()
+            vin = np.array([a for a, _ in pts]); vout = np.array([b for _, b in pts])
+            for n, _ in self.chroms:
+                self.v[n] = o.map_values(self.v[n], vin, vout)
         else:
             raise ValueError("oracle pipeline: operator %s not supported" % name)
 

@@ -1,6 +1,7 @@
 """Drop-in check of the host CLI: genodsp_b200/bin/genodsp (C host + CUDA library) must write
 byte-identical stdout (and the same variable / threshold messages on stderr) as the unmodified
 reference binary oracle/_ref/genodsp for the same command line and input."""
+import json
 import os
 import subprocess
 
@@ -85,6 +86,27 @@ def assert_same(data, args, stdin="reads.iv", stderr_too=True):
 
 
 C = ["--chromosomes=g.chroms"]
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+with open(os.path.join(GOLDEN, "cases.json")) as _f:
+    GOLDEN_CASES = json.load(_f)
+
+
+@pytest.mark.parametrize("case", sorted(GOLDEN_CASES))
+def test_cli_matches_committed_golden(case):
+    """our CLI against the fixtures the reference binary produced (tests/golden/make_golden.py): the same
+    check as the live comparisons below, but pinned to committed bytes"""
+    spec = GOLDEN_CASES[case]
+    rc, out, err = run(OURS, spec["args"], os.path.join(GOLDEN, spec["stdin"]), GOLDEN)
+    assert rc == 0, err.decode()[-2000:]
+    want = open(os.path.join(GOLDEN, case + ".out"), "rb").read()
+    if out != want:
+        lo, lw = out.split(b"\n"), want.split(b"\n")
+        for i, (x, y) in enumerate(zip(lo, lw)):
+            assert x == y, "%s: stdout differs at line %d: ours %r golden %r" % (case, i + 1, x, y)
+        assert len(lo) == len(lw), "%s: %d lines, golden %d" % (case, len(lo), len(lw))
+    assert err == open(os.path.join(GOLDEN, case + ".err"), "rb").read(), case
+
 
 
 def test_cfg1_depth_sum_localmax(data):
