@@ -160,7 +160,7 @@ def _cpu_sample_worker(args):
     return (t1 - t0, t2 - t1, kind)
 
 
-def cpu_baseline_single(n=32_000_000):
+def cpu_baseline_single(n=160_000_000):        # 10-20 s of single-core work
     acc, smo, kind = _cpu_sample_worker((n, 1))
     tot = acc + smo
     return {"value": n / tot / 1e9, "unit": "Gbp/s", "cores": 1, "kind": kind,
