@@ -37,7 +37,10 @@ DEPTH = 5
 READ_MIN, READ_MAX = 50, 150
 FP64_NOMINAL = 148 * 64 * 1.965e9      # FP64 lanes * SMs * max SM clock (instructions/s)
 FP64_MEASURED = 1.745e13               # scripts/micro/fp64_peak.cu on this pool's B200 (gpurun, round 1)
-SMOOTH_TRAFFIC_BYTES_PER_BASE = 15.99   # (24.71 GB read + 24.67 GB written) / 3,088,269,832 bases: ncu --set full, profiles/r1_bench_kernels_ncu_full.csv
+SMOOTH_TRAFFIC_BYTES_PER_BASE = 15.99   # (24.71 GB read + 24.67 GB written) / 3,088,269,832 bases: ncu --set full
+SMOOTH_TRAFFIC_SOURCE = "profiles/r1_bench_kernels_ncu_full.csv"
+ACC_MOVED_BYTES_PER_BASE = 9.58         # 29.6 GB per accumulate launch set (k_bin_count/_offsets/_scatter/_final) / 3,088,269,832 bases
+ACC_MOVED_SOURCE = "ncu constant, profiles/r1_bench_kernels_ncu_full.csv (DRAM read + written by the four k_bin_* kernels)"
 METRIC = "Gbp/s, hg38 depth accumulation + smooth --window=101 (fp64)"
 
 
@@ -206,6 +209,131 @@ def run_reference_arm(args):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+HALO = 4096          # readable cells either side of a slab cut: open/close 1001 reach 1003, clump's carry tile is 4096
+
+
+def second_track(g, np):
+    """cfg5's second signal: sorted disjoint intervals covering ~50 % of every owned piece, values k/1024"""
+    rng = np.random.default_rng(99)
+    bs, bstart, bend, bval = [], [], [], []
+    for k, (lo, hi, dlo, dhi, pos0, clen) in enumerate(g.segs):
+        n = hi - lo
+        m = max(1, n // 2000)
+        cuts = np.unique(rng.integers(0, n, 2 * m)) + pos0
+        a, b = cuts[0::2], cuts[1::2]
+        m2 = min(a.size, b.size)
+        bs.append(np.full(m2, k, np.uint32)); bstart.append(a[:m2].astype(np.uint32)); bend.append(b[:m2].astype(np.uint32))
+        bval.append(rng.integers(1, 2048, m2) / 1024.0)
+    return g.interval_table(np.concatenate(bs), np.concatenate(bstart), np.concatenate(bend), np.concatenate(bval))
+
+
+class Pipelines:
+    """The BASELINE.json pipelines on one rank's Genome (whole genome at world 1, a slab otherwise).
+    Every method is one operator; slab-aware where the operator needs more than its own cells."""
+
+    def __init__(self, torch, dist, g, plan, world, rank, intervals, lengths):
+        from genodsp_b200 import capi, slab
+        import numpy as np
+        self.t, self.dist, self.g, self.plan, self.world, self.rank = torch, dist, g, plan, world, rank
+        self.slab, self.capi, self.np = slab, capi, np
+        self.seg_t, self.start_t, self.end_t = intervals
+        self.comm = slab.DistComm(dist, g.device) if world > 1 else slab.VirtualComm([g])
+        self.tableB = second_track(g, np)
+        cap = max(1024, g.cells // 4)
+        self.rbufs = (torch.empty(cap, dtype=torch.int32, device=g.device), torch.empty(cap, dtype=torch.int32, device=g.device),
+                      torch.empty(cap, dtype=torch.float64, device=g.device))
+        self.nruns = 0
+        self.vars = {}
+        self.overlap = slab.OverlappedExchange(g, plan, dist, (WINDOW - 1) // 2) if world > 1 else None
+        self.taps = None
+
+    def close(self):
+        self.tableB.close()
+        if self.overlap is not None:
+            self.overlap.close()
+
+    def xch(self, radius):
+        if self.world > 1:
+            self.slab.exchange_halos(self.g.sig, self.plan, self.dist, radius)
+
+    # ---- operators
+    def depth(self):
+        self.g.accumulate(self.seg_t, self.start_t, self.end_t, host=False)
+
+    def smooth(self):
+        g = self.g
+        if self.overlap is None:
+            g.smooth(WINDOW)
+            return
+        import ctypes as C
+        from genodsp_b200.genome import hann_taps
+        if self.taps is None:
+            self.taps = hann_taps(WINDOW)
+        tp = self.taps.ctypes.data_as(C.POINTER(C.c_double))
+        self.overlap.run(lambda lay: self.capi.check(g.lib.gdsp_smooth(g.ctx, lay, g._p(g.sig), g._p(g.tmp), WINDOW, tp)))
+        g._swap()
+
+    def localmax(self):
+        self.xch(5); self.g.localmax(11)
+
+    def sum100(self):
+        self.xch(100); self.g.sum(100, denom=100.0)
+
+    def percentile99(self):
+        if self.world == 1:
+            self.vars.update(self.g.percentile(99.0, destructive=True))
+        else:
+            (v,), n = self.slab.slab_percentiles([self.g], self.comm, [99000])
+            self.vars["percentile99"] = v
+
+    def binarize_after_percentile(self):
+        if self.world == 1:
+            self.g.binarize(self.vars["percentile99"])           # consumes the pending sorted state: count + fill
+        else:
+            self.slab.slab_sorted_binarize([self.g], self.comm, self.vars["percentile99"])
+
+    def binarize6(self):
+        self.g.binarize(6.0)
+
+    def open1001(self):
+        self.xch(1003); self.g.open_(1001, 0.5)
+
+    def close1001(self):
+        self.xch(1003); self.g.close_(1001, 0.5)
+
+    def clump(self):
+        if self.world == 1:
+            self.g.clump(0.5, 1000)
+        else:
+            if hasattr(self.slab, "slab_clump_carries"):
+                self.slab.slab_clump_carries([self.g], self.comm, average=0.5, length=1000)
+            else:
+                from genodsp_b200.genome import Genome
+                dev = self.g.device.index
+                self.slab.slab_clump(self.slab.DistTransport(self.g, self.dist), self.comm,
+                                     lambda name, clen, r: Genome([(name, clen)], device=dev), average=0.5, length=1000)
+
+    def runs(self):
+        self.nruns = self.g.runs_device(self.rbufs)[0]
+
+    def chain5(self):
+        c, tb = self.capi, self.tableB
+        self.g.pointwise([(c.PW_IVL_ADD, 0.0, 0, 0, 0, tb), (c.PW_IVL_MUL, 0.0, 0, 0, 0, tb), (c.PW_IVL_SET, 0.0, 0, 0, 0, tb),
+                          (c.PW_NONZERO_TO_ONE, 0.0), (c.PW_IVL_SET_OUTSIDE, 0.0, 0, 0, 0, tb), type(self.g).op_binarize(0.5)])
+
+    def pipelines(self):
+        """name -> [(operator name, callable, algorithmic bytes per base)]"""
+        return {
+            "pipe5": [("depth", self.depth, 16), ("smooth101", self.smooth, 16), ("localmax11", self.localmax, 16),
+                      ("percentile99", self.percentile99, 8), ("binarize", self.binarize_after_percentile, 16), ("runs", self.runs, 8)],
+            "cfg3": [("depth", self.depth, 16), ("sum100", self.sum100, 16), ("percentile99", self.percentile99, 8),
+                     ("binarize", self.binarize_after_percentile, 16)],
+            "cfg4": [("depth", self.depth, 16), ("binarize6", self.binarize6, 16), ("open1001", self.open1001, 16),
+                     ("close1001", self.close1001, 16), ("clump", self.clump, 16), ("runs", self.runs, 8)],
+            "cfg5": [("depth", self.depth, 16), ("chain6_one_launch", self.chain5, 16)],
+        }
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -223,6 +351,7 @@ def run_gpu_arm(args):
     chroms = scaled_genome(args.scale)
     order = sorted(range(len(chroms)), key=lambda i: -chroms[i][1])
     sorted_chroms = [chroms[i] for i in order]
+    lengths = [l for _, l in sorted_chroms]
     total_bases = sum(l for _, l in chroms)
     h = (WINDOW - 1) // 2
 
@@ -230,10 +359,10 @@ def run_gpu_arm(args):
         g = Genome(chroms, device=local)
         plan = []
     else:
-        segs_s, buffer_cells = slab.partition([l for _, l in sorted_chroms], world, rank, h)
+        segs_s, buffer_cells = slab.partition(lengths, world, rank, HALO)
         segs = [(order[si], lo, hi, dlo, dhi, pos0) for si, lo, hi, dlo, dhi, pos0 in segs_s]
         g = Genome(chroms, device=local, segs=segs, buffer_cells=buffer_cells)
-        plan = slab.halo_plan([l for _, l in sorted_chroms], world, rank, h)
+        plan = slab.halo_plan(lengths, world, rank, HALO)
 
     # intervals: generated for the whole genome with a per-chromosome seed (identical on every
     # rank), then each rank keeps those that overlap a piece it owns, indexed by layout segment
@@ -251,23 +380,19 @@ def run_gpu_arm(args):
         seg_t, start_t, end_t = torch.cat(keep_seg), torch.cat(keep_s), torch.cat(keep_e)
         del cs, st, en
     n_intervals = int(seg_t.shape[0])
-    my_bases = g.cells
+    P = Pipelines(torch, dist, g, plan, world, rank, (seg_t, start_t, end_t), lengths)
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
     def step_resident(timers=None):
         if timers is not None:
             timers[0].record()
-        g.accumulate(seg_t, start_t, end_t, host=False)
+        P.depth()
         if timers is not None:
             timers[1].record()
-        if plan:
-            slab.exchange_halos(g.sig, plan, dist)
+        P.smooth()                       # at N > 1 the halo exchange runs on a side stream behind the interior FIR
         if timers is not None:
             timers[2].record()
-        g.smooth(WINDOW)
-        if timers is not None:
-            timers[3].record()
 
     def barrier():
         if world > 1:
@@ -281,7 +406,7 @@ def run_gpu_arm(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    stage_ev = [[ev() for _ in range(4)] for _ in range(args.steps)]
+    stage_ev = [[ev() for _ in range(3)] for _ in range(args.steps)]
     t_begin, t_end = ev(), ev()
     barrier()
     t_begin.record()
@@ -294,8 +419,7 @@ def run_gpu_arm(args):
     total_ms = t_begin.elapsed_time(t_end)
     clocks = sampler.stop() if rank == 0 else None
     acc_ms = sum(e[0].elapsed_time(e[1]) for e in stage_ev) / args.steps
-    xch_ms = sum(e[1].elapsed_time(e[2]) for e in stage_ev) / args.steps
-    smo_ms = sum(e[2].elapsed_time(e[3]) for e in stage_ev) / args.steps
+    smo_ms = sum(e[1].elapsed_time(e[2]) for e in stage_ev) / args.steps
 
     # ---- end to end through the C-ABI with HOST buffers: pinned interval arrays in, fp64 signal out
     e2e_steps = max(1, min(args.steps, 3))
@@ -305,7 +429,7 @@ def run_gpu_arm(args):
     def step_e2e():
         g.accumulate_pinned(seg_h, start_h, end_h)
         if plan:
-            slab.exchange_halos(g.sig, plan, dist)
+            slab.exchange_halos(g.sig, plan, dist, h)
         g.smooth_to_host(WINDOW, out_h)        # FIR of piece k+1 overlaps the D2H of piece k
 
     step_e2e()
@@ -317,16 +441,63 @@ def run_gpu_arm(args):
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1) / e2e_steps
+    del out_h, seg_h, start_h, end_h
 
-    vals = torch.tensor([total_ms, acc_ms, xch_ms, smo_ms, e2e_ms], dtype=torch.float64, device=device)
+    # ---- every pipeline of BASELINE.json under the same clock: per-operator CUDA-event
+    # times, max over ranks, best of `--stage-reps` passes after one warm-up pass
+    stage_out = {}
+    finals = {}
+    if not args.no_stages:
+        for name, ops in P.pipelines().items():
+            best, best_ops = None, None
+            for rep in range(args.stage_reps + 1):
+                barrier()
+                marks = [ev() for _ in range(len(ops) + 1)]
+                marks[0].record()
+                for k, (_, fn, _) in enumerate(ops):
+                    fn(); marks[k + 1].record()
+                barrier()
+                ms = torch.tensor([marks[0].elapsed_time(marks[-1])] + [marks[k].elapsed_time(marks[k + 1]) for k in range(len(ops))],
+                                  dtype=torch.float64, device=device)
+                if world > 1:
+                    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+                ms = ms.tolist()
+                if rep > 0 and (best is None or ms[0] < best):
+                    best, best_ops = ms[0], ms[1:]
+            stage_out[name] = (best, best_ops, [o[0] for o in ops], [o[2] for o in ops])
+            finals[name] = dict(P.vars)
+            # ---- parity of the slab run: rank 0 reruns the pipeline on the WHOLE genome on its own GPU (the N = 1
+            # path) and every rank's pieces are compared with it bit for bit
+            if world > 1 and not args.no_parity:
+                if rank == 0:
+                    if "whole" not in finals:
+                        gw = Genome(chroms, device=local)
+                        wi = synth_intervals(torch, device, sorted_chroms)
+                        finals["whole"] = Pipelines(torch, dist, gw, [], 1, 0, wi, lengths)
+                    W = finals["whole"]
+                    for _, fn, _ in W.pipelines()[name]:
+                        fn()
+                    _ = W.g.sig                                   # materialise a pending sorted state, if any
+                    whole_g = W.g
+                    same_vars = all(W.vars.get(k) == v for k, v in P.vars.items())
+                else:
+                    whole_g, same_vars = None, True
+                compared, differ, cut = slab.compare_with_whole(g, whole_g, dist, rank, world)
+                finals.setdefault("parity", {})[name] = {"cells_compared": compared, "cells_differ": differ,
+                                                         "cut_chromosome_pieces": cut, "variables_equal": bool(same_vars)}
+        if "whole" in finals:
+            finals["whole"].close(); finals["whole"].g.close(); del finals["whole"]
+
+    vals = torch.tensor([total_ms, acc_ms, smo_ms, e2e_ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-    total_ms, acc_ms, xch_ms, smo_ms, e2e_ms = [float(x) for x in vals.tolist()]
+    total_ms, acc_ms, smo_ms, e2e_ms = [float(x) for x in vals.tolist()]
     n_iv = torch.tensor([n_intervals], dtype=torch.int64, device=device)
     if world > 1:
         dist.all_reduce(n_iv)
     n_iv_total = int(n_iv.item())
 
+    ok = True
     if rank == 0:
         ms_per_step = total_ms / args.steps
         peak, peak_src = measured_hbm_peak()
@@ -334,6 +505,15 @@ def run_gpu_arm(args):
         smooth_gbs = 16.0 * per_gpu_bases / (smo_ms / 1e3) / 1e9
         fp64_rate = 2.0 * WINDOW * per_gpu_bases / (smo_ms / 1e3)
         acc_bytes = 16.0 * per_gpu_bases + 28.0 * n_iv_total / world
+        acc_moved = ACC_MOVED_BYTES_PER_BASE * per_gpu_bases
+        pipes = {}
+        for name, (best, best_ops, op_names, op_bytes) in stage_out.items():
+            ops = {}
+            for nm, ms, bpb in zip(op_names, best_ops, op_bytes):
+                gbs = bpb * per_gpu_bases / (ms / 1e3) / 1e9
+                ops[nm] = {"ms": round(ms, 3), "gbp_s": round(total_bases / (ms / 1e3) / 1e9, 2), "alg_bytes_per_bp": bpb,
+                           "achieved_gbs_per_gpu": round(gbs, 1), "frac_hbm": round(gbs / peak, 3)}
+            pipes[name] = {"ms": round(best, 3), "gbp_s": round(total_bases / (best / 1e3) / 1e9, 2), "ops": ops}
         line = {
             "metric": METRIC, "value": total_bases / (ms_per_step / 1e3) / 1e9, "unit": "Gbp/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -344,7 +524,8 @@ def run_gpu_arm(args):
                                    "--window=%d" % (total_bases, "" if args.scale == 1 else " (lengths / %d)" % args.scale,
                                                     n_iv_total, DEPTH, WINDOW),
                        "l2": "inputs larger than L2 (%.1f GB signal per GPU)" % (8.0 * per_gpu_bases / 1e9),
-                       "parallelism": "slab x%d, halo %d cells" % (world, h) if world > 1 else "single GPU"},
+                       "parallelism": ("slab x%d, halo %d cells exchanged over NCCL send/recv on a side stream behind the interior FIR"
+                                       % (world, h)) if world > 1 else "single GPU"},
             "clocks": clocks,
             "e2e": {"value": total_bases / (e2e_ms / 1e3) / 1e9, "unit": "Gbp/s",
                     "h2d_bytes_per_step": 12 * n_iv_total, "d2h_bytes_per_step": 8 * total_bases,
@@ -353,28 +534,46 @@ def run_gpu_arm(args):
             "gpu_launches": timed_launches,
             "stages": {"accumulate": {"ms": acc_ms, "gbp_s": total_bases / (acc_ms / 1e3) / 1e9,
                                       "achieved_gbs": acc_bytes / (acc_ms / 1e3) / 1e9,
-                                      "frac_hbm": acc_bytes / (acc_ms / 1e3) / 1e9 / peak},
-                       "halo_exchange": {"ms": xch_ms},
+                                      "frac_hbm": acc_bytes / (acc_ms / 1e3) / 1e9 / peak,
+                                      "moved_bytes_per_base": ACC_MOVED_BYTES_PER_BASE, "moved_source": ACC_MOVED_SOURCE,
+                                      "frac_hbm_on_moved_bytes": acc_moved / (acc_ms / 1e3) / 1e9 / peak},
                        "smooth": {"ms": smo_ms, "gbp_s": total_bases / (smo_ms / 1e3) / 1e9,
                                   "achieved_gbs": smooth_gbs, "frac_hbm": smooth_gbs / peak,
                                   "fp64_instr_per_base": 2 * WINDOW,
-                                  "fp64_lane_ops_per_s": 2 * WINDOW * per_gpu_bases / (smo_ms / 1e3)}},
-            "roofline": {"kernel": "k_smooth_ct", "bound": "hbm", "achieved": smooth_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": smooth_gbs / peak, "traffic": SMOOTH_TRAFFIC_BYTES_PER_BASE * per_gpu_bases if SMOOTH_TRAFFIC_BYTES_PER_BASE else None,
-                         "peak_source": peak_src,
+                                  "fp64_lane_ops_per_s": 2 * WINDOW * per_gpu_bases / (smo_ms / 1e3),
+                                  "includes": "halo exchange (side stream) + interior + edge launches" if world > 1 else "one launch"},
+                       "pipelines": pipes},
+            "roofline": {"kernel": "k_smooth_ct", "bound": "fp64_issue", "achieved": smooth_gbs, "peak": peak, "unit": "GB/s",
+                         "frac": smooth_gbs / peak,
+                         "traffic": SMOOTH_TRAFFIC_BYTES_PER_BASE * per_gpu_bases if SMOOTH_TRAFFIC_BYTES_PER_BASE else None,
+                         "traffic_source": "ncu constant (dram__bytes_read.sum + dram__bytes_write.sum per base, %s), not measured in this run" % SMOOTH_TRAFFIC_SOURCE,
+                         "peak_source": peak_src, "secondary": {"bound": "hbm", "frac": smooth_gbs / peak},
                          "binding_limit": {"kind": "fp64_issue", "achieved": fp64_rate, "unit": "FP64 instr/s",
                                            "peak_nominal": FP64_NOMINAL, "frac_nominal": fp64_rate / FP64_NOMINAL,
                                            "peak_measured": FP64_MEASURED, "frac_measured": fp64_rate / FP64_MEASURED,
                                            "peak_measured_source": "scripts/micro/fp64_peak.cu (DMUL+DADD, constant-bank operand)"},
-                         "note": "16 B/bp algorithmic; the exact-order FIR needs 2*W=202 separately rounded FP64 "
-                                 "instructions per base, so FP64 issue (64 lanes/SM), not HBM, is the binding limit for W=101"},
+                         "note": "`achieved`/`frac` are the contract's HBM figures (16 B/bp algorithmic); the exact-order FIR needs "
+                                 "2*W=202 separately rounded FP64 instructions per base, so FP64 issue (64 lanes/SM), not HBM, is the "
+                                 "binding limit for W=101: see binding_limit"},
         }
+        if "parity" in finals:
+            par = finals["parity"]
+            ok = all(v["cells_differ"] == 0 and v["variables_equal"] for v in par.values())
+            line["parity_check"] = {"against": "the same pipelines run on the whole genome on rank 0's GPU (the N = 1 path)",
+                                    "cut_chromosomes": max(v["cut_chromosome_pieces"] for v in par.values()) - 0,
+                                    "bit_equal": ok, "pipelines": par}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_single()
         print(json.dumps(line), flush=True)
+    P.close()
     g.close()
     if world > 1:
+        okt = torch.tensor([1 if ok else 0], device=device)
+        dist.broadcast(okt, 0)
+        ok = bool(okt.item())
         dist.destroy_process_group()
+    if not ok:
+        sys.exit(3)
 
 
 def main():
@@ -385,6 +584,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=int, default=1, help="divide every chromosome length (1 = full hg38)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-stages", action="store_true", help="skip the per-pipeline stage timings (pipe5, cfg3, cfg4, cfg5)")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the bit-comparison of the slab results with the whole-genome run on rank 0")
+    ap.add_argument("--stage-reps", type=int, default=2)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -83,6 +83,7 @@ SIGNATURES = {
     "gdsp_percentiles": (_i, [_vp, _vp, _vp, _vp, _u64, _u32, _d, _d, _u32p, _i, _dp, _u64p]),
     "gdsp_sort_genome": (_i, [_vp, _vp, _vp, _vp, _u64, C.POINTER(_i)]),
     "gdsp_sorted_binarize": (_i, [_vp, _vp, _vp, _d, _i, _d, _d, C.POINTER(_i)]),
+    "gdsp_fill_step": (_i, [_vp, _vp, _vp, _u64p, _u64, _d, _d]),
     "gdsp_ivl_arg_extrema": (_i, [_vp, _vp, _vp, _vp, _i]),
     "gdsp_map_values": (_i, [_vp, _vp, _vp, _dp, _dp, _i]),
     "gdsp_format_runs_max_bytes": (C.c_size_t, [_u64, C.c_char_p]),

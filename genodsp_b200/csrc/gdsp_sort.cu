@@ -757,6 +757,25 @@ extern "C" int gdsp_sorted_binarize (gdsp_ctx* c, const gdsp_layout* L_, double*
 	return GDSP_OK;
 	}
 
+// The same fill for a slab-sharded genome: h_prefix[s] = position of segment s's first owned cell in
+// the concatenated chromsSorted genome, `step` = the global position of the first `one` cell.
+extern "C" int gdsp_fill_step (gdsp_ctx* c, const gdsp_layout* L_, double* sig, const uint64_t* h_prefix,
+                               uint64_t step, double one, double zero)
+	{
+	gdsp_layout* L = (gdsp_layout*) L_;
+	GDSP_REQUIRE (c && L && sig && h_prefix, "gdsp_fill_step: NULL argument");
+	GDSP_REQUIRE_ALIGNED (sig, "gdsp_fill_step");
+	TileMap tm;
+	GDSP_TRY (gdsp_layout_tilemap (L, SORT_TILE, &tm));
+	if (tm.ntiles == 0) return GDSP_OK;
+	SortScratch sc;
+	GDSP_TRY (sort_scratch (c, tm.ntiles, L->nseg, &sc));
+	GDSP_CUDA (cudaMemcpyAsync (sc.prefix, h_prefix, sizeof (uint64_t) * L->nseg, cudaMemcpyHostToDevice, c->stream));
+	k_fill_step<<<(unsigned) tm.ntiles, 256, 0, c->stream>>> (L->d, tm.d_base, L->nseg, sc.prefix, step, one, zero, sig);
+	GDSP_KERNEL_CHECK ();                               // (the pageable h_prefix was staged before cudaMemcpyAsync returned)
+	return GDSP_OK;
+	}
+
 // ---------------------------------------------------------------------------
 // percentile selection
 // ---------------------------------------------------------------------------

@@ -279,6 +279,39 @@ class Genome:
         cand = self.tmp[:n].cpu().numpy() if n <= cap else None
         return np.array(list(counts), dtype=np.uint64), cand
 
+    def pct_sample_dev(self, m, stride=1, mn=-DBL_MAX, mx=DBL_MAX, key_lo=0, key_hi=2 ** 64 - 1, seed=1):
+        """gdsp_pct_sample -> (device view of the samples inside self.tmp, sample slots this rank owns)"""
+        m = min(int(m), int(self.tmp.numel()))
+        cnt, slots = C.c_uint32(), C.c_uint64()
+        check(self.lib.gdsp_pct_sample(self.ctx, self.layout, self._p(self.sig), int(stride), float(mn), float(mx),
+                                       int(key_lo), int(key_hi), m, int(seed), self._p(self.tmp), C.byref(cnt), C.byref(slots)))
+        return self.tmp[:int(cnt.value)], int(slots.value)
+
+    def pct_count_dev(self, bound_keys, compact, stride=1, mn=-DBL_MAX, mx=DBL_MAX, cap=None):
+        """gdsp_pct_count -> (region counts numpy u64[2*nb+1], number of candidates, device view of them inside
+        self.tmp -- None when they did not fit `cap`)"""
+        nb = len(bound_keys)
+        cap = int(cap) if cap else int(self.tmp.numel())
+        cap = min(cap, int(self.tmp.numel()))
+        bk = (C.c_uint64 * max(nb, 1))(*[int(k) for k in bound_keys])
+        cp = (C.c_uint8 * (nb + 1))(*[int(bool(x)) for x in compact])
+        counts = (C.c_uint64 * (2 * nb + 1))()
+        ncand = C.c_uint64()
+        check(self.lib.gdsp_pct_count(self.ctx, self.layout, self._p(self.sig), int(stride), float(mn), float(mx),
+                                      bk, nb, cp, counts, self._p(self.tmp), cap, C.byref(ncand)))
+        n = int(ncand.value)
+        return np.array(list(counts), dtype=np.uint64), n, (self.tmp[:n] if n <= cap else None)
+
+    def sort_array(self, a):
+        """gdsp_sort_array on a 1-D float64 device tensor -> sorted tensor (key order: -0.0 before +0.0)"""
+        if a.numel() < 2:
+            return a
+        a = a.contiguous()
+        b = self.torch.empty_like(a)
+        flag = C.c_int()
+        check(self.lib.gdsp_sort_array(self.ctx, self._p(a), self._p(b), int(a.numel()), C.byref(flag)))
+        return b if flag.value else a
+
     def smooth_to_host(self, window, out_host):
         """smooth + device->host delivery of the result, pipelined per chromosome piece: while piece
         k is on its way to `out_host` (a pinned float64 tensor of buffer_cells) on a copy stream, the
@@ -489,6 +522,12 @@ class Genome:
         if destructive:
             self._pending_sort = True                 # materialised by the next reader of self.sig
         return out
+
+    def fill_step(self, prefix, step, one=1.0, zero=0.0):
+        """gdsp_fill_step: cell at global sorted position q (prefix[k] + offset inside piece k) = one if q >= step"""
+        arr = (C.c_uint64 * self.nseg)(*[int(x) for x in prefix])
+        check(self.lib.gdsp_fill_step(self.ctx, self.layout, self._p(self._sig), arr, int(step), float(one), float(zero)))
+        self._pending_sort = False
 
     def text_roundtrip(self):
         """percentile --preserve's write_all/read_all round trip (10 decimals), genodsp.c:1717-1775"""

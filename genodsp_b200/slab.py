@@ -51,35 +51,183 @@ def halo_plan(sorted_lengths, world, rank, halo):
     """-> list of (peer, send_lo, send_hi, recv_lo, recv_hi) in buffer cells for `rank`.
 
     Only the first piece can continue to the left and only the last piece to the
-    right (the slab is contiguous in genome coordinates)."""
+    right (the slab is contiguous in genome coordinates).  The number of cells a
+    rank SENDS is what its peer expects to receive (the peer's halo, which is
+    shorter than `halo` when the cut lies within `halo` cells of a chromosome end),
+    never this rank's own halo: the two differ whenever a cut is close to a
+    chromosome boundary.  A piece shorter than the halo its neighbour needs would
+    need cells from two ranks away: refused (ValueError)."""
     segs, _ = partition(sorted_lengths, world, rank, halo)
     plan = []
     if not segs:
+        if world > 1 and halo > 0 and sum(sorted_lengths) > 0:
+            raise ValueError("slab partition: rank %d owns no cells" % rank)
         return plan
+
+    def neighbour_want(peer, side):
+        """cells `peer` expects from this rank: the left halo of its first piece (side 'left' of the
+        peer = my right edge) or the right halo of its last piece"""
+        if peer < 0 or peer >= world:
+            return 0, None
+        psegs, _ = partition(sorted_lengths, world, peer, halo)
+        if not psegs:
+            return 0, None
+        si, lo, hi, dlo, dhi, pos0 = psegs[0] if side == "left" else psegs[-1]
+        return (lo - dlo, si) if side == "left" else (dhi - hi, si)
+
     si, lo, hi, dlo, dhi, pos0 = segs[0]
-    if dlo < lo:                     # rank-1 holds the cells just before pos0
-        n = lo - dlo
-        plan.append((rank - 1, lo, lo + min(n, hi - lo), dlo, lo))
+    n_recv = lo - dlo                                   # rank-1 holds the cells just before pos0
+    n_send, psi = neighbour_want(rank - 1, "right")     # rank-1's last piece continues into my first
+    if n_send and psi != si:
+        n_send = 0
+    if n_send > hi - lo:
+        raise ValueError("slab partition: rank %d's piece of chromosome #%d has %d cells, fewer than the %d halo cells "
+                         "rank %d needs from it (multi-hop halos are not supported: use fewer ranks or a smaller halo)"
+                         % (rank, si, hi - lo, n_send, rank - 1))
+    if n_recv or n_send:
+        plan.append((rank - 1, lo, lo + n_send, dlo, lo))
     si, lo, hi, dlo, dhi, pos0 = segs[-1]
-    if dhi > hi:
-        n = dhi - hi
-        plan.append((rank + 1, hi - min(n, hi - lo), hi, hi, dhi))
+    n_recv = dhi - hi
+    n_send, psi = neighbour_want(rank + 1, "left")
+    if n_send and psi != si:
+        n_send = 0
+    if n_send > hi - lo:
+        raise ValueError("slab partition: rank %d's piece of chromosome #%d has %d cells, fewer than the %d halo cells "
+                         "rank %d needs from it (multi-hop halos are not supported: use fewer ranks or a smaller halo)"
+                         % (rank, si, hi - lo, n_send, rank + 1))
+    if n_recv or n_send:
+        plan.append((rank + 1, hi - n_send, hi, hi, dhi))
     return plan
 
 
-def exchange_halos(buf, plan, dist):
+def _plan_ops(buf, plan, dist, radius):
+    ops = []
+    for peer, s_lo, s_hi, r_lo, r_hi in plan:
+        left = (r_hi == s_lo)                    # the peer holds the cells before my first piece
+        ns, nr = s_hi - s_lo, r_hi - r_lo
+        if radius is not None:                   # only the `radius` cells nearest to the cut travel
+            ns, nr = min(ns, radius), min(nr, radius)
+        if left:
+            s_a, s_b, r_a, r_b = s_lo, s_lo + ns, r_hi - nr, r_hi
+        else:
+            s_a, s_b, r_a, r_b = s_hi - ns, s_hi, r_lo, r_lo + nr
+        if s_b > s_a:
+            ops.append(dist.P2POp(dist.isend, buf[s_a:s_b], peer))
+        if r_b > r_a:
+            ops.append(dist.P2POp(dist.irecv, buf[r_a:r_b], peer))
+    return ops
+
+
+def exchange_halos(buf, plan, dist, radius=None):
     """Fill the halo cells of `buf` (1-D tensor) from the neighbouring ranks.
 
     Every rank sends the owned cells adjacent to a cut and receives the
-    neighbour's; sends and receives are posted together (ncclGroup semantics)."""
+    neighbour's; sends and receives are posted together (ncclGroup semantics).
+    `radius` limits the exchange to the cells a window of that reach reads."""
     if not plan:
         return
-    ops, recv_views = [], []
-    for peer, s_lo, s_hi, r_lo, r_hi in plan:
-        ops.append(dist.P2POp(dist.isend, buf[s_lo:s_hi], peer))
-        ops.append(dist.P2POp(dist.irecv, buf[r_lo:r_hi], peer))
+    ops = _plan_ops(buf, plan, dist, radius)
+    if not ops:
+        return
     for req in dist.batch_isend_irecv(ops):
         req.wait()
+
+
+class OverlappedExchange:
+    """Halo exchange hidden behind the interior of a windowed operator (the exchange
+    is ~0.2 ms of pure latency).  The owned cells are split into an INTERIOR layout, whose windows never
+    touch a halo cell, and EDGE layouts (the cells within `radius` of a cut).  run(op) posts the NCCL
+    send/recv on a side stream, launches `op` on the interior on the compute stream, makes the
+    compute stream wait for the exchange, and launches `op` on the edges."""
+
+    def __init__(self, genome, plan, dist, radius):
+        import ctypes as C
+        from . import capi
+        t = genome.torch
+        self.g, self.plan, self.dist, self.radius = genome, plan, dist, int(radius)
+        self.side = t.cuda.Stream(device=genome.device)
+        inner, edge = [], []
+        for k, (lo, hi, dlo, dhi, pos0, clen) in enumerate(genome.segs):
+            a, b = lo, hi
+            if dlo < lo:                                     # continues on the left
+                a = min(hi, _round_up(lo + self.radius, ALIGN))
+                edge.append((lo, a, dlo, dhi, pos0, clen))
+            if dhi > hi and a < hi:                          # continues on the right
+                b = max(a, (hi - self.radius) // ALIGN * ALIGN)
+                edge.append((b, hi, dlo, dhi, pos0 + (b - lo), clen))
+            if b > a:
+                inner.append((a, b, dlo, dhi, pos0 + (a - lo), clen))
+        self.layouts = []
+        for table in (inner, edge):
+            if not table:
+                self.layouts.append(None)
+                continue
+            arr = (capi.Seg * len(table))()
+            for i, (lo, hi, dlo, dhi, pos0, clen) in enumerate(table):
+                arr[i].lo, arr[i].hi, arr[i].dlo, arr[i].dhi, arr[i].pos0, arr[i].chrom_len = lo, hi, dlo, dhi, pos0, clen
+            lay = C.c_void_p()
+            capi.check(genome.lib.gdsp_layout_create(genome.ctx, arr, len(table), C.byref(lay)))
+            self.layouts.append(lay)
+
+    def run(self, op):
+        """op(layout) launches the operator on the cells of `layout` (reading genome.sig, writing genome.tmp)"""
+        t = self.g.torch
+        main = t.cuda.current_stream(self.g.device)
+        inner, edge = self.layouts
+        ops = _plan_ops(self.g.sig, self.plan, self.dist, self.radius)
+        if ops:
+            self.side.wait_stream(main)                      # the cells to send are final
+            with t.cuda.stream(self.side):
+                reqs = self.dist.batch_isend_irecv(ops)
+        if inner is not None:
+            op(inner)
+        if ops:
+            with t.cuda.stream(self.side):
+                for r in reqs:
+                    r.wait()
+            main.wait_stream(self.side)
+        if edge is not None:
+            op(edge)
+
+    def close(self):
+        for lay in self.layouts:
+            if lay is not None:
+                self.g.lib.gdsp_layout_destroy(lay)
+        self.layouts = []
+
+
+def compare_with_whole(g, whole, dist, rank, world):
+    """Bit-compare the slab pieces of every rank with a whole-genome Genome held by rank 0 (bench.py's
+    parity check).  Pieces travel to rank 0 over NCCL send/recv; returns
+    (cells compared, cells that differ, chromosomes cut by a slab boundary) on rank 0, broadcast to all."""
+    t = g.torch
+    info = t.zeros(3, dtype=t.int64, device=g.device)
+    tables = [None] * world
+    dist.all_gather_object(tables, [(g.seg_chrom[k],) + tuple(g.segs[k]) for k in range(g.nseg)])
+    pieces_of = {}
+    for r in range(world):
+        for (ci, *_rest) in tables[r]:
+            pieces_of[ci] = pieces_of.get(ci, 0) + 1
+    for r in range(world):
+        for (ci, lo, hi, dlo, dhi, pos0, clen) in tables[r]:
+            n = hi - lo
+            if rank == r and r != 0:
+                dist.send(g.sig[lo:hi].contiguous(), 0)
+            if rank == 0:
+                if r == 0:
+                    piece = g.sig[lo:hi]
+                else:
+                    piece = t.empty(n, dtype=t.float64, device=g.device)
+                    dist.recv(piece, r)
+                wk = whole.seg_index(whole.chroms[ci][0])[0]
+                wlo = whole.segs[wk][0] + pos0
+                ref = whole.sig[wlo:wlo + n]
+                info[0] += n
+                info[1] += int((piece.view(t.int64) != ref.view(t.int64)).sum())
+                del piece
+    info[2] = sum(1 for c in pieces_of.values() if c > 1)
+    dist.broadcast(info, 0)
+    return int(info[0]), int(info[1]), int(info[2])
 
 
 # ----------------------------------------------------------------------------------------------
@@ -98,8 +246,79 @@ _KEY_MAX = (1 << 64) - 1
 _SIGN = _np.uint64(1 << 63)
 
 
+class DistComm:
+    """Combining layer for real ranks: ONE Genome per process, every exchange is an NCCL collective on
+    device tensors (all_gather_into_tensor / all_reduce) -- nothing is pickled through the host.
+    `gather*` take the list of this process's local values (one entry) and return what every rank sees."""
+
+    def __init__(self, dist, device):
+        import torch
+        self.dist, self.t, self.device = dist, torch, device
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+
+    def local_ranks(self):
+        return [self.rank]
+
+    def sum_i64(self, local):
+        """element-wise sum over ranks of equally shaped integer numpy arrays -> numpy u64"""
+        t = self.t.from_numpy(_np.ascontiguousarray(local[0]).astype(_np.int64)).to(self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t.cpu().numpy().astype(_np.uint64)
+
+    def gather_f64(self, local):
+        """equally shaped float64 numpy arrays -> numpy [world, ...] (rank order)"""
+        a = _np.ascontiguousarray(local[0], _np.float64)
+        t = self.t.from_numpy(a).to(self.device).reshape(-1)
+        out = self.t.empty(self.world * t.numel(), dtype=self.t.float64, device=self.device)
+        self.dist.all_gather_into_tensor(out, t)
+        return out.cpu().numpy().reshape((self.world,) + a.shape)
+
+    def cat_f64(self, local, cap):
+        """variable-length 1-D device tensors (each <= cap cells) -> [device tensor of all ranks' cells] per
+        local part; the lengths travel in the same collective (slot `cap`)"""
+        t = local[0]
+        buf = self.t.zeros(cap + 1, dtype=self.t.float64, device=self.device)
+        buf[:t.numel()].copy_(t)
+        buf[cap] = float(t.numel())
+        out = self.t.empty(self.world * (cap + 1), dtype=self.t.float64, device=self.device)
+        self.dist.all_gather_into_tensor(out, buf)
+        out = out.view(self.world, cap + 1)
+        counts = [int(c) for c in out[:, cap].cpu().tolist()]
+        return [self.t.cat([out[r, :counts[r]] for r in range(self.world)])]
+
+    def gather(self, local):
+        """small host objects (piece tables at set-up time only; never per-base data)"""
+        out = [None] * self.world
+        self.dist.all_gather_object(out, local[0])
+        return out
+
+
+class VirtualComm:
+    """all rank Genomes live in this process (GPU tests on one device): same interface as DistComm"""
+
+    def __init__(self, parts):
+        self.parts = parts
+        self.world, self.rank = len(parts), 0
+
+    def local_ranks(self):
+        return list(range(self.world))
+
+    def sum_i64(self, local):
+        return _np.sum([_np.asarray(a, dtype=_np.uint64) for a in local], axis=0, dtype=_np.uint64)
+
+    def gather_f64(self, local):
+        return _np.stack([_np.ascontiguousarray(a, _np.float64) for a in local])
+
+    def cat_f64(self, local, cap):
+        t = self.parts[0].torch
+        return [t.cat([x.to(g.device) for x in local]) for g in self.parts]
+
+    def gather(self, local):
+        return list(local)
+
+
 def dist_gather(dist):
-    """gather(local_values) for real ranks: local_values has ONE entry (this rank's)"""
+    """legacy host-object gather for set-up time tables (kept for scripts/slab_check.py)"""
     def gather(local_values):
         out = [None] * dist.get_world_size()
         dist.all_gather_object(out, local_values[0])
@@ -109,6 +328,15 @@ def dist_gather(dist):
 
 def virtual_gather(local_values):
     return list(local_values)
+
+
+def _as_comm(parts, gather):
+    """accept either a comm object or one of the legacy gather callables"""
+    if hasattr(gather, "sum_i64"):
+        return gather
+    if gather is virtual_gather:
+        return VirtualComm(parts)
+    raise TypeError("slab operators need a DistComm / VirtualComm")
 
 
 def f64_keys(a):
@@ -134,11 +362,12 @@ def _pct_rank(n, p_milli):
 
 def slab_minmax(parts, gather, stride=1, mn=-1.7976931348623157e308, mx=1.7976931348623157e308):
     """(min, max, count) over all slabs (invert's default centre, percentile 0/100)"""
-    allv = gather([g.minmax(stride, mn, mx) for g in parts])
+    comm = _as_comm(parts, gather)
+    allv = comm.gather_f64([_np.array(g.minmax(stride, mn, mx), dtype=_np.float64) for g in parts])
     have = [v for v in allv if v[2] > 0]
     if not have:
         return 0.0, 0.0, 0
-    return min(v[0] for v in have), max(v[1] for v in have), sum(v[2] for v in allv)
+    return float(min(v[0] for v in have)), float(max(v[1] for v in have)), int(sum(int(v[2]) for v in allv))
 
 
 def slab_invert(parts, gather, mid=None):
@@ -153,13 +382,21 @@ def slab_invert(parts, gather, mid=None):
 def slab_cumulativesum(parts, gather):
     """op_cumulative_sum_apply (sum.c:776-792) on a slab-sharded genome: local scan, then every piece
     adds the totals of the pieces of its chromosome that lie to its left (exact for integer and dyadic
-    signals, 1e-12 relative otherwise -- the same statement as for one GPU)."""
+    signals, 1e-12 relative otherwise -- the same statement as for one GPU).  Only the last value of
+    every piece travels (one small all-gather of device tensors)."""
+    comm = _as_comm(parts, gather)
+    # a slab holds a few pieces; pad every rank's table to a common width
+    width = int(comm.gather_f64([_np.array([float(max(2, g.nseg))]) for g in parts]).max())
     local = []
     for g in parts:
         g.cumulativesum()
         lasts = g.piece_last_values()
-        local.append([(g.seg_chrom[k], g.segs[k][4], float(lasts[k])) for k in range(g.nseg)])
-    pieces = sorted(p for rank in gather(local) for p in rank)        # (chromosome, pos0, total)
+        rec = _np.full((width, 3), -1.0)
+        for k in range(g.nseg):
+            rec[k] = (g.seg_chrom[k], g.segs[k][4], float(lasts[k]))
+        local.append(rec)
+    allrec = comm.gather_f64(local).reshape(-1, 3)
+    pieces = sorted((int(c), int(p0), float(tot)) for c, p0, tot in allrec if c >= 0)    # (chromosome, pos0, total)
     for g in parts:
         for k in range(g.nseg):
             ci, pos0 = g.seg_chrom[k], g.segs[k][4]
@@ -206,22 +443,25 @@ def slab_runs(parts, gather, collapse=True, show_uncovered=0):
         r = g.runs(collapse=collapse, show_uncovered=show_uncovered)
         local.append({name: (min(g.segs[k][4] for k in g.seg_index(name)), r[name]) for name in r})
     per_chrom = {}
-    for d in gather(local):
+    for d in _as_comm(parts, gather).gather(local):
         for name, chunk in d.items():
             per_chrom.setdefault(name, []).append(chunk)
     return {name: merge_runs(chunks, collapse) for name, chunks in per_chrom.items()}
 
 
 def slab_percentiles(parts, gather, p_milli, stride=1, mn=-1.7976931348623157e308, mx=1.7976931348623157e308,
-                     sample_per_rank=1 << 18, cand_cap=1 << 18, max_iter=60):
+                     sample_total=1 << 18, cand_cap=1 << 18, max_iter=60, sample_per_rank=None):
     """op_percentile_apply's order statistics (percentile.c:392-751) over all slabs, exact, without
-    moving the signal: every rank samples its slab, the combined sample brackets each wanted rank
-    between two keys, one counting pass per rank (gdsp_pct_count) gives the exact population of every
-    key region (summed over ranks) and compacts the cells between the brackets, whose combined sorted
-    list holds the wanted element.  Regions are narrowed and the pass repeated when a bracket
-    misses.  Candidates are only gathered while a rank holds at most `cand_cap` of them (they travel
-    through the host); a wider bracket is narrowed by another counting pass instead.
+    moving the signal: every rank samples its slab, the combined sample (all-gathered and sorted ON THE
+    DEVICE) brackets each wanted rank between two keys, one counting pass per rank (gdsp_pct_count) gives
+    the exact population of every key region -- summed over ranks with ONE all-reduce of a device tensor
+    (BASELINE north_star: "percentile histograms ... use NCCL allreduce") -- and compacts the cells
+    between the brackets, whose combined sorted list holds the wanted element.  Regions are narrowed
+    and the pass repeated when a bracket misses.  Candidates are only gathered while a rank holds at
+    most `cand_cap` of them; a wider bracket is narrowed by another counting pass instead.
     -> (values, number of samples); identical on every rank."""
+    comm = _as_comm(parts, gather)
+    per_rank = int(sample_per_rank) if sample_per_rank else max(4096, int(sample_total) // comm.world)
     jobs = [{"p": int(p), "done": False, "value": 0.0, "lo": 0, "hi": _KEY_MAX, "below": 0, "inside": None}
             for p in p_milli]
     total = None
@@ -231,8 +471,9 @@ def slab_percentiles(parts, gather, p_milli, stride=1, mn=-1.7976931348623157e30
             break
         b_lo = min([j["lo"] for j in open_jobs], default=0)
         b_hi = max([j["hi"] for j in open_jobs], default=_KEY_MAX)
-        local = [g.pct_sample(sample_per_rank, stride, mn, mx, b_lo, b_hi, seed=0x243F6A88 + 7919 * it)[0] for g in parts]
-        ks = _np.sort(_np.concatenate([f64_keys(a) for a in gather(local)] + [_np.zeros(0, _np.uint64)]))
+        local = [g.pct_sample_dev(per_rank, stride, mn, mx, b_lo, b_hi, seed=0x243F6A88 + 7919 * it)[0] for g in parts]
+        combined = comm.cat_f64(local, per_rank)
+        ks = f64_keys(parts[0].sort_array(combined[0]).cpu().numpy())         # ascending keys (the sort's order)
         bounds, win = [], {}
         for j in open_jobs:
             lo, hi = j["lo"], j["hi"]
@@ -262,22 +503,20 @@ def slab_percentiles(parts, gather, p_milli, stride=1, mn=-1.7976931348623157e30
             for r in range(1, nb):
                 if bounds[r - 1] >= lo and bounds[r] <= hi:
                     compact[r] = 1
-        local = [g.pct_count(bounds, compact, stride, mn, mx, cand_cap) for g in parts]
-        allr = gather(local)
-        counts = _np.sum([_np.asarray(c[0], dtype=_np.uint64) for c in allr], axis=0, dtype=_np.uint64)
+        local = [g.pct_count_dev(bounds, compact, stride, mn, mx, cand_cap) for g in parts]
+        # region counts + "my candidates did not fit" flag in one all-reduce
+        summed = comm.sum_i64([_np.concatenate([c[0], _np.array([0 if c[2] is not None else 1], dtype=_np.uint64)]) for c in local])
+        counts, overflow = summed[:-1], int(summed[-1])
         total = int(counts.sum())
         if total == 0 or not jobs:
             break
-        cand_ok = all(c[1] is not None for c in allr)
-        sorted_cand = None
-        if cand_ok:
-            allc = _np.concatenate([c[1] for c in allr] + [_np.zeros(0)])
-            sorted_cand = allc[_np.argsort(f64_keys(allc), kind="stable")]
         cand_before, acc = [0] * (nb + 2), 0
         for r in range(nb + 1):
             cand_before[r] = acc
             if compact[r]:
                 acc += int(counts[2 * r])
+        located = []
+        need_cand = False
         for j in open_jobs:
             rank = _pct_rank(total, j["p"])
             cum, reg = 0, 0
@@ -285,13 +524,28 @@ def slab_percentiles(parts, gather, p_milli, stride=1, mn=-1.7976931348623157e30
                 if rank < cum + int(counts[reg]):
                     break
                 cum += int(counts[reg])
+            located.append((j, rank, cum, reg))
+            if not (reg & 1) and compact[reg >> 1] and not overflow:
+                need_cand = True
+        sorted_cand = None
+        if need_cand:                                  # every rank takes this branch together: it depends on summed counts only
+            cat = comm.cat_f64([c[2] for c in local], cand_cap)
+            sorted_cand = parts[0].sort_array(cat[0])
+        picks = [(j, cand_before[reg >> 1] + (rank - cum)) for j, rank, cum, reg in located
+                 if not (reg & 1) and compact[reg >> 1] and sorted_cand is not None]
+        if picks:                                      # one gather + one device->host copy for all jobs
+            t = parts[0].torch
+            idx = t.tensor([i for _, i in picks], dtype=t.int64, device=sorted_cand.device)
+            vals = sorted_cand[idx].cpu().numpy()
+            for (j, _), v in zip(picks, vals):
+                j["value"], j["done"] = float(v), True
+        for j, rank, cum, reg in located:
+            if j["done"]:
+                continue
             if reg & 1:
                 j["value"], j["done"] = key_f64(bounds[reg >> 1]), True
                 continue
             r = reg >> 1
-            if compact[r] and cand_ok:
-                j["value"], j["done"] = float(sorted_cand[cand_before[r] + (rank - cum)]), True
-                continue
             j["lo"] = bounds[r - 1] + 1 if r > 0 else 0
             j["hi"] = bounds[r] - 1 if r < nb else _KEY_MAX
             j["below"], j["inside"] = cum, int(counts[reg])
@@ -355,7 +609,7 @@ def slab_clump(transport, gather, genome_factory, average=0.0, length=100, relat
     for r in local:
         g = transport.genome(r)
         mine.append([(g.seg_chrom[k], g.segs[k][4], g.segs[k][1] - g.segs[k][0], r, k) for k in range(g.nseg)])
-    pieces = sorted(p for per_rank in gather(mine) for p in per_rank)
+    pieces = sorted(p for per_rank in (gather.gather if hasattr(gather, 'gather') else gather)(mine) for p in per_rank)
     by_chrom = {}
     for p in pieces:
         by_chrom.setdefault(p[0], []).append(p)
@@ -385,46 +639,35 @@ def slab_clump(transport, gather, genome_factory, average=0.0, length=100, relat
             whole.close()
 
 
-def slab_percentile_then_binarize(parts, gather, p_milli, ties_above=False, one=1.0, zero=0.0):
-    """`percentile <p> = binarize --threshold=percentile<p>` on a slab-sharded genome.
-
-    The reference's percentile leaves the genome globally sorted (chromsSorted order,
-    percentile.c:611-651) and binarize then thresholds that sorted array: the result is `zero` on the
-    first K cells of the concatenated genome and `one` on the rest, K = the number of cells that do
-    not pass the threshold.  No distributed sort is needed: K comes from the summed region counts of
-    one more counting pass.  (NaN cells would sort to the ends and break the step shape: refused.)
-    -> (threshold, K)"""
-    (thr,), n = slab_percentiles(parts, gather, [int(p_milli)])
+def slab_sorted_binarize(parts, gather, thr, ties_above=False, one=1.0, zero=0.0):
+    """binarize applied to the reference's post-percentile state (the genome globally sorted in chromsSorted
+    order, percentile.c:611-651) on a slab-sharded genome: `zero` on the first K cells of the concatenated
+    genome and `one` on the rest, K = the number of cells that do not pass the threshold.  No distributed
+    sort: K comes from the region counts of one counting pass, summed with one all-reduce.  (NaN cells
+    would sort to the ends and break the step shape: refused.)  -> K"""
+    comm = _as_comm(parts, gather)
     key = int(f64_keys(_np.array([thr]))[0])
     neg_inf, pos_inf = int(f64_keys(_np.array([-_np.inf]))[0]), int(f64_keys(_np.array([_np.inf]))[0])
     bounds = sorted({neg_inf, key, pos_inf})
-    local = [g.pct_count(bounds, [0] * (len(bounds) + 1), 1, -_np.inf, _np.inf)[0] for g in parts]
-    counts = _np.sum([_np.asarray(c, dtype=_np.uint64) for c in gather(local)], axis=0, dtype=_np.uint64)
+    local = [g.pct_count_dev(bounds, [0] * (len(bounds) + 1), 1, -_np.inf, _np.inf)[0] for g in parts]
+    counts = comm.sum_i64(local)
     if int(counts[0]) or int(counts[-1]):
-        raise ValueError("slab_percentile_then_binarize: the signal holds NaN")
+        raise ValueError("slab_sorted_binarize: the signal holds NaN")
     kpos = bounds.index(key)
     below = int(sum(int(c) for c in counts[:2 * kpos + 1]))          # keys strictly below the threshold
     equal = int(counts[2 * kpos + 1])
     K = below if ties_above else below + equal                         # binarize: v > T (or >= T) -> one
     # cells before K in the concatenated chromsSorted genome are zero; every piece knows its offset there
     for g in parts:
-        lengths = {}
-        for ci, (name, ln) in enumerate(g.chroms):
-            lengths[ci] = ln
         order = sorted(range(len(g.chroms)), key=lambda i: -g.chroms[i][1])
         before, acc = {}, 0
         for ci in order:
-            before[ci] = acc; acc += lengths[ci]
-        g.fill(one)
-        seg, start, end = [], [], []
-        for k in range(g.nseg):
-            ci, pos0, ln = g.seg_chrom[k], g.segs[k][4], g.segs[k][1] - g.segs[k][0]
-            z_end = min(pos0 + ln, max(pos0, K - before[ci]))         # chromosome coordinates [pos0, z_end) are zero
-            if z_end > pos0:
-                seg.append(k); start.append(pos0); end.append(z_end)
-        if seg:
-            from . import capi
-            table = g.interval_table(_np.array(seg, _np.uint32), _np.array(start, _np.uint32), _np.array(end, _np.uint32))
-            g.pointwise([(capi.PW_IVL_SET, zero, 0, 0, 0, table)])
-            table.close()
-    return thr, K
+            before[ci] = acc; acc += g.chroms[ci][1]
+        g.fill_step([before[g.seg_chrom[k]] + g.segs[k][4] for k in range(g.nseg)], K, one, zero)
+    return K
+
+
+def slab_percentile_then_binarize(parts, gather, p_milli, ties_above=False, one=1.0, zero=0.0):
+    """`percentile <p> = binarize --threshold=percentile<p>` on a slab-sharded genome -> (threshold, K)"""
+    (thr,), n = slab_percentiles(parts, gather, [int(p_milli)])
+    return thr, slab_sorted_binarize(parts, gather, thr, ties_above, one, zero)

@@ -310,6 +310,13 @@ int  gdsp_sort_genome (gdsp_ctx* ctx, const gdsp_layout* lay, double* sig,
 int  gdsp_sorted_binarize (gdsp_ctx* ctx, const gdsp_layout* lay, double* sig, double threshold,
                            int ties_above, double one, double zero, int* h_done);
 
+/* The fill half of gdsp_sorted_binarize for a slab-sharded genome: cell at position q of the
+ * concatenated chromsSorted genome becomes `one` if q >= step, else `zero`; h_prefix[s] (nseg host
+ * entries) is the position of segment s's first owned cell.  The caller obtains `step` by summing the
+ * per-rank region counts of gdsp_pct_count (NCCL all-reduce). */
+int  gdsp_fill_step (gdsp_ctx* ctx, const gdsp_layout* lay, double* sig, const uint64_t* h_prefix,
+                     uint64_t step, double one, double zero);
+
 /* ---- text output -----------------------------------------------------------
  * The fprintf loop of report_intervals (genodsp.c:1606-1678) on the device: run r
  * becomes the line  chrom TAB start[r]+add_start TAB end[r]+add_end [TAB "%.*f"

@@ -18,6 +18,8 @@ class HostGenome:
         self.segs = [(s[1], s[2], s[3], s[4], s[5], chroms[s[0]][1]) for s in segs]
         self.nseg = len(segs)
         self.piece = [np.array(signal[chroms[s[0]][0]][s[5]:s[5] + s[2] - s[1]], dtype=np.float64) for s in segs]
+        import torch
+        self.torch, self.device = torch, torch.device("cpu")
 
     def seg_index(self, name):
         ci = [i for i, (n, _) in enumerate(self.chroms) if n == name][0]
@@ -56,6 +58,21 @@ class HostGenome:
         if cap is not None and cand.size > cap:
             cand = None
         return counts, cand
+
+    def pct_sample_dev(self, m, stride=1, mn=-np.inf, mx=np.inf, key_lo=0, key_hi=2 ** 64 - 1, seed=1):
+        pick, slots = self.pct_sample(m, stride, mn, mx, key_lo, key_hi, seed)
+        return self.torch.from_numpy(np.ascontiguousarray(pick)), slots
+
+    def pct_count_dev(self, bound_keys, compact, stride=1, mn=-np.inf, mx=np.inf, cap=None):
+        s = self._samples(stride, mn, mx)
+        counts, cand = self.pct_count(bound_keys, compact, stride, mn, mx, None)
+        n = int(cand.size)
+        fits = cap is None or n <= cap
+        return counts, n, (self.torch.from_numpy(np.ascontiguousarray(cand)) if fits else None)
+
+    def sort_array(self, a):
+        v = a.numpy()
+        return self.torch.from_numpy(np.ascontiguousarray(v[np.argsort(slab.f64_keys(v), kind="stable")]))
 
     def cumulativesum(self):
         self.piece = [np.cumsum(v) for v in self.piece]

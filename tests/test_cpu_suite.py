@@ -148,6 +148,36 @@ def test_halo_exchange_world2_gloo():
         assert all(out[r] for r in range(world)), dict(out)
 
 
+def test_halo_plan_send_matches_peer_recv():
+    """ADVICE r1: a cut within `halo` cells of a chromosome boundary gives the two sides different halos;
+    what one rank sends must be what its peer posts as a receive (both directions)."""
+    from genodsp_b200 import slab
+    cases = [([990, 1010], 2, 50), ([1010, 990], 2, 50), ([5000, 3000, 1200, 300], 3, 37), ([1000] * 7, 4, 120),
+             ([2000, 30, 1970], 2, 64), ([300, 300, 300, 300], 3, 80)]
+    for lengths, world, halo in cases:
+        plans = [slab.halo_plan(lengths, world, r, halo) for r in range(world)]
+        for r, plan in enumerate(plans):
+            for peer, s_lo, s_hi, r_lo, r_hi in plan:
+                theirs = [p for p in plans[peer] if p[0] == r]
+                assert len(theirs) == 1, (lengths, world, r, peer)
+                assert s_hi - s_lo == theirs[0][4] - theirs[0][3], (lengths, world, halo, r, peer)
+                assert r_hi - r_lo == theirs[0][2] - theirs[0][1], (lengths, world, halo, r, peer)
+    # a piece shorter than the halo its neighbour needs is refused, not silently mis-sized
+    with pytest.raises(ValueError):
+        for r in range(3):
+            slab.halo_plan([3000], 3, r, 1500)
+
+
+def test_halo_exchange_cut_near_chromosome_boundary_gloo():
+    import torch.multiprocessing as mp
+    for lengths in ([990, 1010], [1010, 990]):
+        mgr = mp.Manager()
+        out = mgr.dict()
+        port = 29650 + (os.getpid() % 1000) + len(out) + lengths[0] % 7
+        mp.spawn(_gloo_worker, args=(2, port, lengths, 50, out), nprocs=2, join=True)
+        assert all(out[r] for r in range(2)), (lengths, dict(out))
+
+
 # ----------------------------------------------------------------------------- slab-level operators (SURVEY 8e)
 def _slab_signal(chroms, seed):
     rng = np.random.default_rng(seed)
@@ -232,7 +262,8 @@ def _slab_gloo_worker(rank, world, port, out):
     sig = _slab_signal(SLAB_CHROMS, 5)
     parts = _host_parts(SLAB_CHROMS, world, [rank], sig)
     try:
-        out[rank] = _slab_ops_check(parts, slab.dist_gather(dist), SLAB_CHROMS, sig, SLAB_PCTS)
+        import torch
+        out[rank] = _slab_ops_check(parts, slab.DistComm(dist, torch.device("cpu")), SLAB_CHROMS, sig, SLAB_PCTS)
     finally:
         dist.destroy_process_group()
 
