@@ -209,6 +209,7 @@ def run_reference_arm(args):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+ALIGN_CUTS = 8192    # slab cuts inside a chromosome are multiples of this in chromosome coordinates (every kernel's tile divides it)
 HALO = 4096          # readable cells either side of a slab cut: open/close 1001 reach 1003, clump's carry tile is 4096
 
 
@@ -305,13 +306,8 @@ class Pipelines:
         if self.world == 1:
             self.g.clump(0.5, 1000)
         else:
-            if hasattr(self.slab, "slab_clump_carries"):
-                self.slab.slab_clump_carries([self.g], self.comm, average=0.5, length=1000)
-            else:
-                from genodsp_b200.genome import Genome
-                dev = self.g.device.index
-                self.slab.slab_clump(self.slab.DistTransport(self.g, self.dist), self.comm,
-                                     lambda name, clen, r: Genome([(name, clen)], device=dev), average=0.5, length=1000)
+            self.xch(4096)
+            self.slab.slab_clump_carries([self.g], self.comm, average=0.5, length=1000)
 
     def runs(self):
         self.nruns = self.g.runs_device(self.rbufs)[0]
@@ -359,10 +355,10 @@ def run_gpu_arm(args):
         g = Genome(chroms, device=local)
         plan = []
     else:
-        segs_s, buffer_cells = slab.partition(lengths, world, rank, HALO)
+        segs_s, buffer_cells = slab.partition(lengths, world, rank, HALO, ALIGN_CUTS)
         segs = [(order[si], lo, hi, dlo, dhi, pos0) for si, lo, hi, dlo, dhi, pos0 in segs_s]
         g = Genome(chroms, device=local, segs=segs, buffer_cells=buffer_cells)
-        plan = slab.halo_plan(lengths, world, rank, HALO)
+        plan = slab.halo_plan(lengths, world, rank, HALO, ALIGN_CUTS)
 
     # intervals: generated for the whole genome with a per-chromosome seed (identical on every
     # rank), then each rank keeps those that overlap a piece it owns, indexed by layout segment

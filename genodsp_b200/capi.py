@@ -94,6 +94,12 @@ SIGNATURES = {
     "gdsp_pct_count": (_i, [_vp, _vp, _vp, _u32, _d, _d, _u64p, _i, C.POINTER(C.c_uint8), _u64p, _vp, _u64, _u64p]),
     "gdsp_clump_work_bytes": (_sz, [_u64]),
     "gdsp_clump": (_i, [_vp, _vp, _vp, _u64, _vp, _d, _u32, _d, _i, _d, _d]),
+    "gdsp_clump_slab_create": (_i, [_vp, _vp, _u64, _vp, _d, _u32, _d, _i, _d, _d, C.POINTER(_vp)]),
+    "gdsp_clump_slab_reduce": (_i, [_vp, _vp, _dp]),
+    "gdsp_clump_slab_mark": (_i, [_vp, _vp, _dp, _dp]),
+    "gdsp_clump_slab_trim": (_i, [_vp, _vp, _dp, C.POINTER(_i)]),
+    "gdsp_clump_slab_emit": (_i, [_vp, _vp, C.POINTER(C.c_ubyte), C.POINTER(_i)]),
+    "gdsp_clump_slab_destroy": (None, [_vp]),
     "gdsp_runs": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _u64, _u64p, _u64p]),
 }
 

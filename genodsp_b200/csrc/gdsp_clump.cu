@@ -415,6 +415,10 @@ struct ClumpFast
 	unsigned char* tsum;       // per tile: bit0/1 generate/propagate upwards, bit2/3 downwards
 	unsigned char* tcin;       // per tile: bit0 carry entering from below, bit1 from above
 	int*           segAllNeg;
+	// slab-sharded chromosomes (gdsp_clump_slab_*); all NULL for whole chromosomes
+	const double2*       segCarryIn;  // per segment: {P, M} just before the segment's first cell
+	double*              segSufMax;   // per segment: maximum valid P over the owned cells (out)
+	const unsigned char* segFlags;    // per segment: bit0 = the first tile holds the neighbour's cells (halo tile)
 	};
 
 #define CLF_INF (__longlong_as_double (0x7ff0000000000000ll))
@@ -531,7 +535,13 @@ k_clump_groupscan (const uint64_t* __restrict__ base, ClumpFast wk)
 	for (int w = 0; w < warp; w++) wex = wex + s_w[w];
 	double ex = shfl_up_f64 (inc, 1);
 	if (lane == 0) ex = 0.0;
-	const double run0 = wex + ex;                      // P before the chunk
+	double run0 = wex + ex;                            // P before the chunk
+	double mex0 = 0.0;                                 // P[-1] = 0 takes part in every prefix minimum
+	if (wk.segCarryIn != NULL)                         // a slab piece: the sums continue the left neighbour's
+		{
+		const double2 ci = wk.segCarryIn[blockIdx.x];
+		run0 = ci.x + run0;  mex0 = ci.y;
+		}
 	__syncthreads ();
 
 	// 2: minimum prefix sum inside the chunk, exclusive prefix minimum over the block
@@ -551,7 +561,7 @@ k_clump_groupscan (const uint64_t* __restrict__ base, ClumpFast wk)
 		}
 	if (lane == 31) s_w[warp] = minc;
 	__syncthreads ();
-	double mex = 0.0;                                  // P[-1] = 0 takes part in every prefix minimum
+	double mex = mex0;
 	for (int w = 0; w < warp; w++) mex = dmin2 (mex, s_w[w]);
 	double e2 = shfl_up_f64 (minc, 1);
 	if (lane != 0) mex = dmin2 (mex, e2);
@@ -604,8 +614,8 @@ __device__ __forceinline__ void clf_group_min_store (const double P[16], int val
 template <bool FAST, bool ABOVE>
 __device__ __forceinline__ void clf_mark_tile (const double* __restrict__ sig, double T, const ClumpFast& wk, const ScanStatus<double>& stMax,
                                                double* s_M, double* s_warp, double* s_carryD,
-                                               uint64_t tile, uint32_t ticket, bool firstOfScan, uint64_t tis, uint64_t t0, uint32_t n,
-                                               uint32_t Lmin, uint32_t hrows)
+                                               uint64_t tile, uint32_t ticket, bool firstOfScan, uint64_t c0, uint64_t t0, uint32_t n,
+                                               uint32_t Lmin, uint32_t hrows, double* sufMaxOut)
 	{
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const double NEG = -CLF_INF;
@@ -635,7 +645,7 @@ __device__ __forceinline__ void clf_mark_tile (const double* __restrict__ sig, d
 	const uint32_t r0 = (0u - Lmin) & 15u;
 	const uint32_t A = hcells + e0 - Lmin - r0;
 	const double* const shifted = s_M + A + (A >> 4);
-	const uint64_t i0 = tis * CL_TILE + e0;                       // index of the lane's first cell inside the chromosome
+	const uint64_t i0 = c0 + e0;                                  // index of the lane's first cell inside the chromosome
 	#pragma unroll
 	for (int k = 0; k < 16; k++)
 		{
@@ -677,7 +687,11 @@ __device__ __forceinline__ void clf_mark_tile (const double* __restrict__ sig, d
 	if (threadIdx.x < 32)
 		{
 		const double e = scan_lookback<double> (stMax, ticket, firstOfScan, tAgg, NEG, [] (double a, double b) { return (b > a) ? b : a; });
-		if (threadIdx.x == 0) *s_carryD = e;
+		if (threadIdx.x == 0)
+			{
+			*s_carryD = e;
+			if (sufMaxOut != NULL) *sufMaxOut = dmax2 (e, tAgg);   // first owned tile of a slab piece: the piece's maximum
+			}
 		}
 	__syncthreads ();
 	const double cq = dmax2 (dmax2 (*s_carryD, wEx), ex);         // everything after this lane's cells
@@ -693,7 +707,8 @@ __device__ __forceinline__ void clf_mark_tile (const double* __restrict__ sig, d
 			if (!FAST && i0 + k == 0) mp = 0.0;                   // M[-1] = 0
 			if (dmax2 (cq, P[k]) >= mp) mk |= 1u << k;
 			}
-	unsigned wm = mk << ((lane & 1) * 16), wq = (mk & qual) << ((lane & 1) * 16);
+	// Bq holds the qualifying bit of EVERY cell (the trimming kernels and the slab fix-up AND it with Bm)
+	unsigned wm = mk << ((lane & 1) * 16), wq = qual << ((lane & 1) * 16);
 	wm |= __shfl_xor_sync (0xffffffffu, wm, 1);
 	wq |= __shfl_xor_sync (0xffffffffu, wq, 1);
 	if ((lane & 1) == 0)
@@ -724,6 +739,16 @@ k_clump_mark (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base
 	const uint32_t n  = (uint32_t) ((sd.hi - t0 < CL_TILE) ? (sd.hi - t0) : CL_TILE);
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const bool firstOfScan = (tis == tilesInSeg - 1);
+	const uint64_t c0 = (uint64_t) sd.pos0 + tis * CL_TILE;       // chromosome index of the tile's first cell
+	const uint32_t haloTiles = (wk.segFlags != NULL) ? (wk.segFlags[seg] & 1u) : 0u;
+	if (tis < haloTiles)
+		{
+		// the neighbour's cells (they only supply the prefix minima of the next tile's halo): no marks, and
+		// nothing waits on this tile in the look-back chain (the tile after it in scan order starts a segment)
+		if (threadIdx.x < CLF_WORDS) { wk.Bm[tile * CLF_WORDS + threadIdx.x] = 0u;  wk.Bq[tile * CLF_WORDS + threadIdx.x] = 0u; }
+		return;
+		}
+	double* const sufMaxOut = (wk.segSufMax != NULL && tis == haloTiles) ? &wk.segSufMax[seg] : NULL;
 
 	uint32_t Lmin = minLength;
 	if (relLength > 0.0)
@@ -735,7 +760,7 @@ k_clump_mark (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base
 	const uint32_t hrows = (reach + CLF_GROUP - 1) / CLF_GROUP;   // <= 8 (the host checked): at most one per warp
 
 	// prefix minima of the halo groups (the tail of the previous tile of this chromosome)
-	if ((uint32_t) warp < hrows && (uint64_t) (hrows - warp) * CLF_GROUP <= tis * CL_TILE)
+	if ((uint32_t) warp < hrows && (uint64_t) (hrows - warp) * CLF_GROUP <= c0)
 		{
 		const uint32_t back = (hrows - warp) * CLF_GROUP;         // cells between the group's first cell and t0
 		double x[16], tot;
@@ -747,10 +772,10 @@ k_clump_mark (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base
 		clf_group_min_store<true> (x, 16, cr.y, s_M + warp * (CLF_GROUP / 16 * 17));
 		}
 
-	if (n == CL_TILE && tis * CL_TILE >= (uint64_t) Lmin && tis > 0)
-		clf_mark_tile<true, ABOVE> (sig, T, wk, stMax, s_M, s_warp, &s_carryD, tile, ticket, firstOfScan, tis, t0, n, Lmin, hrows);
+	if (n == CL_TILE && c0 >= (uint64_t) Lmin && c0 > 0)
+		clf_mark_tile<true, ABOVE> (sig, T, wk, stMax, s_M, s_warp, &s_carryD, tile, ticket, firstOfScan, c0, t0, n, Lmin, hrows, sufMaxOut);
 	else
-		clf_mark_tile<false, ABOVE> (sig, T, wk, stMax, s_M, s_warp, &s_carryD, tile, ticket, firstOfScan, tis, t0, n, Lmin, hrows);
+		clf_mark_tile<false, ABOVE> (sig, T, wk, stMax, s_M, s_warp, &s_carryD, tile, ticket, firstOfScan, c0, t0, n, Lmin, hrows, sufMaxOut);
 	}
 
 // ---- run trimming on the bit words -------------------------------------------
@@ -778,7 +803,8 @@ k_clump_tilesum (uint64_t ntiles, ClumpFast wk)
 	const int lane = threadIdx.x & 31;
 	if (tile >= ntiles) return;
 	const uint4 m = *reinterpret_cast<const uint4*> (wk.Bm + tile * CLF_WORDS + lane * 4);
-	const uint4 q = *reinterpret_cast<const uint4*> (wk.Bq + tile * CLF_WORDS + lane * 4);
+	uint4 q = *reinterpret_cast<const uint4*> (wk.Bq + tile * CLF_WORDS + lane * 4);
+	q.x &= m.x;  q.y &= m.y;  q.z &= m.z;  q.w &= m.w;
 	int up = clf_comb (clf_comb (clf_comb (clf_gp (m.x, q.x), clf_gp (m.y, q.y)), clf_gp (m.z, q.z)), clf_gp (m.w, q.w));
 	int dn = clf_comb (clf_comb (clf_comb (clf_gp (__brev (m.w), __brev (q.w)), clf_gp (__brev (m.z), __brev (q.z))),
 	                             clf_gp (__brev (m.y), __brev (q.y))), clf_gp (__brev (m.x), __brev (q.x)));
@@ -796,10 +822,17 @@ k_clump_tilesum (uint64_t ntiles, ClumpFast wk)
 
 // one block per chromosome: the carry entering every tile from below and from above
 __global__ void __launch_bounds__(256)
-k_clump_tilecarry (const uint64_t* __restrict__ base, ClumpFast wk)
+k_clump_tilecarry (const uint64_t* __restrict__ base, ClumpFast wk, const unsigned char* __restrict__ segCin)
 	{
 	__shared__ int s_up[256], s_dn[256];
-	const uint64_t b0 = base[blockIdx.x], b1 = base[blockIdx.x + 1];
+	uint64_t b0 = base[blockIdx.x];
+	const uint64_t b1 = base[blockIdx.x + 1];
+	if (wk.segFlags != NULL && (wk.segFlags[blockIdx.x] & 1u) && b0 < b1)
+		{
+		if (threadIdx.x == 0) wk.tcin[b0] = 0;                     // halo tile: not emitted
+		b0++;
+		}
+	const int cin0 = (segCin != NULL) ? segCin[blockIdx.x] : 0;   // slab piece: bit0 from the left neighbour, bit1 from the right
 	const uint64_t nt = b1 - b0, chunk = (nt + 255) / 256;
 	const uint64_t lo = b0 + threadIdx.x * chunk < b1 ? b0 + threadIdx.x * chunk : b1;
 	const uint64_t hi = lo + chunk < b1 ? lo + chunk : b1;
@@ -808,7 +841,7 @@ k_clump_tilecarry (const uint64_t* __restrict__ base, ClumpFast wk)
 	for (uint64_t t = hi; t > lo; t--) dn = clf_comb (dn, (wk.tsum[t - 1] >> 2) & 3);
 	s_up[threadIdx.x] = up;  s_dn[threadIdx.x] = dn;
 	__syncthreads ();
-	int cu = 0, cd = 0;                                            // nothing enters a chromosome from outside
+	int cu = cin0 & 1, cd = (cin0 >> 1) & 1;                       // nothing enters a whole chromosome from outside
 	for (int k = 0; k < (int) threadIdx.x; k++) cu = clf_apply (s_up[k], cu);
 	for (int k = 255; k > (int) threadIdx.x; k--) cd = clf_apply (s_dn[k], cd);
 	for (uint64_t t = lo; t < hi; t++)
@@ -839,13 +872,14 @@ k_clump_emit (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const bool allNeg = wk.segAllNeg[seg] != 0;                   // clump.c:545-565: nothing can clump
 	const int tc = wk.tcin[tile];
+	if (wk.segFlags != NULL && (wk.segFlags[seg] & 1u) && tis == 0) return;     // the neighbour's cells
 
 	uint32_t M = 0, S = 0;
 	int up = 2, dn = 2, upIn = 2, dnIn = 2;
 	if (warp < 4)
 		{
 		M = wk.Bm[tile * CLF_WORDS + threadIdx.x];
-		S = wk.Bq[tile * CLF_WORDS + threadIdx.x];
+		S = wk.Bq[tile * CLF_WORDS + threadIdx.x] & M;
 		up = clf_gp (M, S);  dn = clf_gp (__brev (M), __brev (S));
 		#pragma unroll
 		for (int d = 1; d < 32; d <<= 1)
@@ -896,6 +930,351 @@ __global__ void k_fill_int (int* p, int n, int v)
 	if (i < n) p[i] = v;
 	}
 
+// ===========================================================================
+// Slab-sharded chromosomes (one GPU owns a contiguous piece): the same kernels, with the four
+// chromosome-wide dependencies of the search exchanged as per-piece CARRIES instead of moving the
+// signal (BASELINE north_star):
+//   forward   {sum of d, minimum prefix sum} of every piece  -> {P, M} entering the next piece
+//   backward  maximum valid P of every piece                 -> suffix maximum entering the previous piece
+//   both ways generate/propagate pair of the run trimming    -> carry bits entering from either side
+// Slab cuts are multiples of CL_TILE in chromosome coordinates, so a piece's tiles and 512-cell groups
+// coincide with the whole chromosome's.  A piece that continues on the left starts one tile early
+// ("halo tile": the last CL_TILE cells of the left neighbour, supplied by the halo exchange): its groups
+// are reduced and scanned like the piece's own -- they are the Lmin-cell look-back of the first owned
+// tile -- but it is neither marked nor emitted.  A piece therefore publishes its aggregate in two parts:
+// head (all but its last tile) and tail (the last tile = the right neighbour's halo tile), so that the
+// neighbour can start its sums at the beginning of its halo tile.
+// ===========================================================================
+#define CLS_HALO   1u        // the first tile of the segment holds the left neighbour's cells
+#define CLS_CONT_R 2u        // the chromosome continues on the right neighbour
+
+struct AggSM { double S, m; };
+__device__ __forceinline__ AggSM agg_comb (AggSM a, AggSM b) { AggSM r;  r.S = a.S + b.S;  r.m = dmin2 (a.m, a.S + b.m);  return r; }
+
+// one block per segment: {sum, minimum prefix sum} of the head groups and of the tail groups, out[seg*4..]
+__global__ void __launch_bounds__(1024)
+k_clump_groupagg (const uint64_t* __restrict__ base, ClumpFast wk, double* __restrict__ out)
+	{
+	__shared__ AggSM s_w[32];
+	const unsigned fl = wk.segFlags[blockIdx.x];
+	const uint64_t g0 = (base[blockIdx.x] + (fl & CLS_HALO)) * CLF_GROUPS, g1 = base[blockIdx.x + 1] * CLF_GROUPS;
+	const uint64_t gT = ((fl & CLS_CONT_R) && g1 >= g0 + CLF_GROUPS) ? g1 - CLF_GROUPS : g1;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	for (int part = 0; part < 2; part++)
+		{
+		const uint64_t a = part ? gT : g0, b = part ? g1 : gT;
+		const uint64_t chunk = (b - a + 1023) / 1024;
+		const uint64_t lo = (a + threadIdx.x * chunk < b) ? a + threadIdx.x * chunk : b;
+		const uint64_t hi = (lo + chunk < b) ? lo + chunk : b;
+		AggSM v;  v.S = 0.0;  v.m = CLF_INF;
+		for (uint64_t g = lo; g < hi; g++)
+			{
+			const double2 r = wk.carry[g];
+			AggSM x;  x.S = r.x;  x.m = r.y;
+			v = agg_comb (v, x);
+			}
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)                           // ordered fold: lane l+d is later
+			{
+			AggSM o;  o.S = shfl_down_f64 (v.S, d);  o.m = shfl_down_f64 (v.m, d);
+			if (lane + d < 32 && ((lane & (2 * d - 1)) == 0)) v = agg_comb (v, o);
+			}
+		__syncthreads ();
+		if (lane == 0) s_w[warp] = v;
+		__syncthreads ();
+		if (threadIdx.x == 0)
+			{
+			AggSM t = s_w[0];
+			for (int w = 1; w < 32; w++) t = agg_comb (t, s_w[w]);
+			out[blockIdx.x * 4 + part * 2] = t.S;  out[blockIdx.x * 4 + part * 2 + 1] = t.m;
+			}
+		}
+	}
+
+// one block per segment: cells p of the owned part with M[p-1] <= sufIn are marked because a valid end
+// with that prefix sum lies in a piece further right.  M is non-increasing, so they form a suffix:
+// whole groups from the first group whose carry M is <= sufIn, plus a tail of the group before it.
+template <bool ABOVE>
+__global__ void __launch_bounds__(1024)
+k_clump_fixup (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, const double* __restrict__ sig, double T,
+               ClumpFast wk, const double* __restrict__ sufIn)
+	{
+	const double sIn = sufIn[blockIdx.x];
+	if (!(sIn > -CLF_INF)) return;
+	const unsigned fl = wk.segFlags[blockIdx.x];
+	const uint64_t gs = base[blockIdx.x] * CLF_GROUPS;             // first group of the (extended) segment
+	const uint64_t g0 = gs + (fl & CLS_HALO) * CLF_GROUPS, g1 = base[blockIdx.x + 1] * CLF_GROUPS;
+	uint64_t lo = g0, hi = g1;                                     // smallest g in [g0,g1) with carry[g].y <= sIn
+	while (lo < hi)
+		{
+		const uint64_t mid = (lo + hi) >> 1;
+		if (wk.carry[mid].y <= sIn) hi = mid; else lo = mid + 1;
+		}
+	const uint64_t gstar = lo;
+	for (uint64_t w = gstar * (CLF_GROUP / 32) + threadIdx.x; w < g1 * (CLF_GROUP / 32); w += 1024) wk.Bm[w] = 0xffffffffu;
+	if (gstar > g0 && threadIdx.x < 32)
+		{
+		const int lane = threadIdx.x;
+		const uint64_t g = gstar - 1;
+		const SegDev sd = segs[blockIdx.x];
+		double P[16], tot;
+		clf_load16<true, ABOVE> (sig, sd.lo + (g - gs) * CLF_GROUP + lane * 16, 16, T, P);
+		group_sum_scan (P, tot);
+		const double2 cr = wk.carry[g];
+		double m = CLF_INF;
+		#pragma unroll
+		for (int k = 0; k < 16; k++) { P[k] = cr.x + P[k];  m = dmin2 (m, P[k]); }
+		double inc = m;
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+			{
+			const double up = shfl_up_f64 (inc, d);
+			if (lane >= d) inc = dmin2 (up, inc);
+			}
+		double ex = shfl_up_f64 (inc, 1);
+		if (lane == 0) ex = CLF_INF;
+		double run = dmin2 (ex, cr.y);                             // M[p-1] of this lane's first cell
+		unsigned mk = 0;
+		#pragma unroll
+		for (int k = 0; k < 16; k++)
+			{
+			if (run <= sIn) mk |= 1u << k;
+			run = dmin2 (run, P[k]);
+			}
+		unsigned wm = mk << ((lane & 1) * 16);
+		wm |= __shfl_xor_sync (0xffffffffu, wm, 1);
+		if ((lane & 1) == 0 && wm) wk.Bm[g * (CLF_GROUP / 32) + (lane >> 1)] |= wm;
+		}
+	}
+
+// one block per segment: generate/propagate pair of the owned tiles, both directions (bits 0-1 up, 2-3 down)
+__global__ void __launch_bounds__(256)
+k_clump_seggp (const uint64_t* __restrict__ base, ClumpFast wk, int* __restrict__ out)
+	{
+	__shared__ int s_up[256], s_dn[256];
+	const uint64_t b0 = base[blockIdx.x] + (wk.segFlags[blockIdx.x] & CLS_HALO), b1 = base[blockIdx.x + 1];
+	const uint64_t nt = b1 - b0, chunk = (nt + 255) / 256;
+	const uint64_t lo = b0 + threadIdx.x * chunk < b1 ? b0 + threadIdx.x * chunk : b1;
+	const uint64_t hi = lo + chunk < b1 ? lo + chunk : b1;
+	int up = 2, dn = 2;
+	for (uint64_t t = lo; t < hi; t++) up = clf_comb (up, wk.tsum[t] & 3);
+	for (uint64_t t = hi; t > lo; t--) dn = clf_comb (dn, (wk.tsum[t - 1] >> 2) & 3);
+	s_up[threadIdx.x] = up;  s_dn[threadIdx.x] = dn;
+	__syncthreads ();
+	if (threadIdx.x == 0)
+		{
+		int u = 2, d = 2;
+		for (int k = 0; k < 256; k++) u = clf_comb (u, s_up[k]);
+		for (int k = 255; k >= 0; k--) d = clf_comb (d, s_dn[k]);
+		out[blockIdx.x] = u | (d << 2);
+		}
+	}
+
+struct gdsp_clump_slab
+	{
+	gdsp_ctx*    c;
+	gdsp_layout* E;            // the segments, each extended by its halo tile
+	int          nseg;
+	double       average, relLength, oneVal, zeroVal;
+	uint32_t     minLength;
+	int          above;
+	ClumpFast    wf;
+	TileMap      tm;
+	size_t       smem;
+	void*        ws1;
+	std::vector<unsigned char> flags;
+	char*        dev;          // one allocation holding the per-segment arrays below
+	double2*       d_carryIn;
+	double*        d_sufMax;
+	double*        d_sufIn;
+	double*        d_agg;
+	int*           d_gp;
+	unsigned char* d_flags;
+	unsigned char* d_cin;
+	};
+
+extern "C" void gdsp_clump_slab_destroy (gdsp_clump_slab* cs)
+	{
+	if (cs == NULL) return;
+	if (cs->E) gdsp_layout_destroy (cs->E);
+	if (cs->dev) cudaFree (cs->dev);
+	delete cs;
+	}
+
+extern "C" int gdsp_clump_slab_create (gdsp_ctx* c, const gdsp_layout* L_, uint64_t buffer_cells, void* work,
+                                       double average, uint32_t minLength, double relLength, int above,
+                                       double oneVal, double zeroVal, gdsp_clump_slab** out)
+	{
+	const gdsp_layout* L = L_;
+	GDSP_REQUIRE (c && L && work && out, "gdsp_clump_slab_create: NULL argument");
+	GDSP_REQUIRE_ALIGNED (work, "gdsp_clump_slab_create");
+	GDSP_REQUIRE (L->nseg <= 65536, "gdsp_clump_slab_create: more than 65536 segments");
+	uint32_t maxLmin = minLength;
+	std::vector<gdsp_seg> ext (L->nseg);
+	std::vector<unsigned char> flags (L->nseg);
+	for (int s = 0; s < L->nseg; s++)
+		{
+		gdsp_seg g = L->h[s];
+		if (relLength > 0.0)
+			{
+			const uint32_t rl = (uint32_t) (relLength * g.chrom_len);
+			if (rl > maxLmin) maxLmin = rl;
+			}
+		unsigned fl = 0;
+		if (g.pos0 > 0)
+			{
+			GDSP_REQUIRE (g.pos0 % CL_TILE == 0, "gdsp_clump_slab: a slab cut must be a multiple of 4096 in chromosome coordinates");
+			GDSP_REQUIRE (g.lo - g.dlo >= CL_TILE, "gdsp_clump_slab: needs 4096 halo cells on the left of a cut chromosome");
+			g.lo -= CL_TILE;  g.pos0 -= CL_TILE;  fl |= CLS_HALO;
+			}
+		const uint64_t endPos = (uint64_t) L->h[s].pos0 + (L->h[s].hi - L->h[s].lo);
+		if (endPos < g.chrom_len)
+			{
+			GDSP_REQUIRE (endPos % CL_TILE == 0 && L->h[s].hi - L->h[s].lo >= CL_TILE,
+			              "gdsp_clump_slab: a slab cut must be a multiple of 4096 in chromosome coordinates (and a piece at least 4096 cells)");
+			fl |= CLS_CONT_R;
+			}
+		ext[s] = g;  flags[s] = (unsigned char) fl;
+		}
+	GDSP_REQUIRE (maxLmin <= CLF_MAX_HALO, "gdsp_clump_slab: minimum lengths above 4096 are not supported on slab-sharded chromosomes");
+	gdsp_clump_slab* cs = new gdsp_clump_slab ();
+	cs->c = c;  cs->E = NULL;  cs->dev = NULL;  cs->nseg = L->nseg;  cs->flags = flags;
+	cs->average = average;  cs->relLength = relLength;  cs->oneVal = oneVal;  cs->zeroVal = zeroVal;
+	cs->minLength = minLength;  cs->above = above;
+	int st = gdsp_layout_create (c, ext.data (), L->nseg, &cs->E);
+	if (st != GDSP_OK) { delete cs;  return st; }
+	st = gdsp_layout_tilemap (cs->E, CL_TILE, &cs->tm);
+	if (st != GDSP_OK) { gdsp_clump_slab_destroy (cs);  return st; }
+	const uint64_t ntiles = cs->tm.ntiles;
+	const size_t fastBytes = (size_t) ntiles * (CLF_GROUPS * 16 + 2 * CLF_WORDS * 4) + 2 * (((size_t) ntiles + 255) / 256) * 256 + (size_t) L->nseg * 4;
+	if (fastBytes > gdsp_clump_work_bytes (buffer_cells))
+		{
+		gdsp_clump_slab_destroy (cs);
+		gdsp_set_error ("gdsp_clump_slab_create: work buffer too small");
+		return GDSP_ERR_ARG;
+		}
+	const size_t n = (size_t) L->nseg;
+	const size_t bytes = n * (16 + 8 + 8 + 32 + 4 + 1 + 1) + 256;
+	if (cudaMalloc (&cs->dev, bytes) != cudaSuccess)
+		{
+		gdsp_clump_slab_destroy (cs);
+		gdsp_set_error ("gdsp_clump_slab_create: out of device memory");
+		return GDSP_ERR_NOMEM;
+		}
+	char* q = cs->dev;
+	cs->d_carryIn = (double2*) q;  q += n * 16;
+	cs->d_agg     = (double*) q;   q += n * 32;
+	cs->d_sufMax  = (double*) q;   q += n * 8;
+	cs->d_sufIn   = (double*) q;   q += n * 8;
+	cs->d_gp      = (int*) q;      q += n * 4;
+	cs->d_flags   = (unsigned char*) q;  q += n;
+	cs->d_cin     = (unsigned char*) q;
+	cudaMemcpyAsync (cs->d_flags, flags.data (), n, cudaMemcpyHostToDevice, c->stream);
+	cudaStreamSynchronize (c->stream);
+	ClumpFast& wf = cs->wf;
+	char* p = (char*) work;
+	wf.carry = (double2*) p;            p += (size_t) ntiles * CLF_GROUPS * 16;
+	wf.Bm = (uint32_t*) p;              p += (size_t) ntiles * CLF_WORDS * 4;
+	wf.Bq = (uint32_t*) p;              p += (size_t) ntiles * CLF_WORDS * 4;
+	wf.tsum = (unsigned char*) p;       p += (((size_t) ntiles + 255) / 256) * 256;
+	wf.tcin = (unsigned char*) p;       p += (((size_t) ntiles + 255) / 256) * 256;
+	wf.segAllNeg = (int*) p;
+	wf.segCarryIn = cs->d_carryIn;  wf.segSufMax = cs->d_sufMax;  wf.segFlags = cs->d_flags;
+	const uint32_t reach = maxLmin ? maxLmin : 1;
+	cs->smem = ((size_t) ((reach + CLF_GROUP - 1) / CLF_GROUP) + CLF_GROUPS) * (CLF_GROUP / 16 * 17) * sizeof (double);
+	if (cs->smem > 48 * 1024)
+		{
+		cudaFuncSetAttribute (k_clump_mark<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) cs->smem);
+		cudaFuncSetAttribute (k_clump_mark<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) cs->smem);
+		}
+	cs->ws1 = NULL;
+	*out = cs;
+	return GDSP_OK;
+	}
+
+// phase 1: group aggregates.  h_agg[s*5..] = {head sum, head minimum prefix, tail sum, tail minimum prefix, all-negative flag}
+extern "C" int gdsp_clump_slab_reduce (gdsp_clump_slab* cs, const double* sig, double* h_agg)
+	{
+	GDSP_REQUIRE (cs && sig && h_agg, "gdsp_clump_slab_reduce: NULL argument");
+	gdsp_ctx* c = cs->c;  gdsp_layout* E = cs->E;
+	k_fill_int<<<(cs->nseg + 255) / 256, 256, 0, c->stream>>> (cs->wf.segAllNeg, cs->nseg, 1);
+	GDSP_KERNEL_CHECK ();
+	if (cs->above) k_clump_groups<true><<<(unsigned) cs->tm.ntiles, CL_THREADS, 0, c->stream>>> (E->d, cs->tm.d_base, cs->nseg, sig, cs->average, cs->wf);
+	else           k_clump_groups<false><<<(unsigned) cs->tm.ntiles, CL_THREADS, 0, c->stream>>> (E->d, cs->tm.d_base, cs->nseg, sig, cs->average, cs->wf);
+	GDSP_KERNEL_CHECK ();
+	k_clump_groupagg<<<cs->nseg, 1024, 0, c->stream>>> (cs->tm.d_base, cs->wf, cs->d_agg);
+	GDSP_KERNEL_CHECK ();
+	std::vector<double> agg ((size_t) cs->nseg * 4);
+	std::vector<int> neg (cs->nseg);
+	GDSP_CUDA (cudaMemcpyAsync (agg.data (), cs->d_agg, sizeof (double) * 4 * cs->nseg, cudaMemcpyDeviceToHost, c->stream));
+	GDSP_CUDA (cudaMemcpyAsync (neg.data (), cs->wf.segAllNeg, sizeof (int) * cs->nseg, cudaMemcpyDeviceToHost, c->stream));
+	GDSP_CUDA (cudaStreamSynchronize (c->stream));
+	for (int s = 0; s < cs->nseg; s++)
+		{
+		for (int k = 0; k < 4; k++) h_agg[s * 5 + k] = agg[(size_t) s * 4 + k];
+		h_agg[s * 5 + 4] = neg[s] ? 1.0 : 0.0;
+		}
+	return GDSP_OK;
+	}
+
+// phase 2: h_carry_in[s*2..] = {P, M} just before the first cell of segment s's halo tile (or of the segment
+// when it starts the chromosome: {0, 0}); marks; h_sufmax[s] = the maximum valid P of the owned cells
+extern "C" int gdsp_clump_slab_mark (gdsp_clump_slab* cs, const double* sig, const double* h_carry_in, double* h_sufmax)
+	{
+	GDSP_REQUIRE (cs && sig && h_carry_in && h_sufmax, "gdsp_clump_slab_mark: NULL argument");
+	gdsp_ctx* c = cs->c;  gdsp_layout* E = cs->E;
+	GDSP_TRY (gdsp_ws (c, 0, scan_status_bytes<double> (cs->tm.ntiles), &cs->ws1));
+	GDSP_CUDA (cudaMemcpyAsync (cs->d_carryIn, h_carry_in, sizeof (double) * 2 * cs->nseg, cudaMemcpyHostToDevice, c->stream));
+	k_clump_groupscan<<<cs->nseg, CLF_GS_THREADS, 0, c->stream>>> (cs->tm.d_base, cs->wf);
+	GDSP_KERNEL_CHECK ();
+	GDSP_CUDA (cudaMemsetAsync (cs->ws1, 0, scan_status_clear_bytes<double> (cs->tm.ntiles), c->stream));
+	if (cs->above) k_clump_mark<true><<<(unsigned) cs->tm.ntiles, CL_THREADS, cs->smem, c->stream>>> (E->d, cs->tm.d_base, cs->nseg, cs->tm.ntiles, sig,
+	        cs->average, cs->minLength, cs->relLength, cs->wf, scan_status_carve<double> (cs->ws1, cs->tm.ntiles));
+	else           k_clump_mark<false><<<(unsigned) cs->tm.ntiles, CL_THREADS, cs->smem, c->stream>>> (E->d, cs->tm.d_base, cs->nseg, cs->tm.ntiles, sig,
+	        cs->average, cs->minLength, cs->relLength, cs->wf, scan_status_carve<double> (cs->ws1, cs->tm.ntiles));
+	GDSP_KERNEL_CHECK ();
+	GDSP_CUDA (cudaMemcpyAsync (h_sufmax, cs->d_sufMax, sizeof (double) * cs->nseg, cudaMemcpyDeviceToHost, c->stream));
+	GDSP_CUDA (cudaStreamSynchronize (c->stream));
+	return GDSP_OK;
+	}
+
+// phase 3: h_sufmax_in[s] = maximum valid P over the pieces to the right of segment s (-inf if none); the cells
+// that maximum reaches are marked, the tile summaries of the trimming are built; h_gp[s] = generate/propagate
+// pair of the owned tiles (bits 0-1 going up, 2-3 going down)
+extern "C" int gdsp_clump_slab_trim (gdsp_clump_slab* cs, const double* sig, const double* h_sufmax_in, int* h_gp)
+	{
+	GDSP_REQUIRE (cs && sig && h_sufmax_in && h_gp, "gdsp_clump_slab_trim: NULL argument");
+	gdsp_ctx* c = cs->c;  gdsp_layout* E = cs->E;
+	GDSP_CUDA (cudaMemcpyAsync (cs->d_sufIn, h_sufmax_in, sizeof (double) * cs->nseg, cudaMemcpyHostToDevice, c->stream));
+	if (cs->above) k_clump_fixup<true><<<cs->nseg, 1024, 0, c->stream>>> (E->d, cs->tm.d_base, sig, cs->average, cs->wf, cs->d_sufIn);
+	else           k_clump_fixup<false><<<cs->nseg, 1024, 0, c->stream>>> (E->d, cs->tm.d_base, sig, cs->average, cs->wf, cs->d_sufIn);
+	GDSP_KERNEL_CHECK ();
+	k_clump_tilesum<<<(unsigned) ((cs->tm.ntiles + 7) / 8), 256, 0, c->stream>>> (cs->tm.ntiles, cs->wf);
+	GDSP_KERNEL_CHECK ();
+	k_clump_seggp<<<cs->nseg, 256, 0, c->stream>>> (cs->tm.d_base, cs->wf, cs->d_gp);
+	GDSP_KERNEL_CHECK ();
+	GDSP_CUDA (cudaMemcpyAsync (h_gp, cs->d_gp, sizeof (int) * cs->nseg, cudaMemcpyDeviceToHost, c->stream));
+	GDSP_CUDA (cudaStreamSynchronize (c->stream));
+	return GDSP_OK;
+	}
+
+// phase 4: h_cin[s] bit0 = a trimmed run reaches segment s from the left neighbour, bit1 = from the right;
+// h_allneg[s] = every d < 0 on the WHOLE chromosome (clump.c:545-565); writes one/zero into the owned cells
+extern "C" int gdsp_clump_slab_emit (gdsp_clump_slab* cs, double* sig, const unsigned char* h_cin, const int* h_allneg)
+	{
+	GDSP_REQUIRE (cs && sig && h_cin && h_allneg, "gdsp_clump_slab_emit: NULL argument");
+	gdsp_ctx* c = cs->c;  gdsp_layout* E = cs->E;
+	GDSP_CUDA (cudaMemcpyAsync (cs->d_cin, h_cin, cs->nseg, cudaMemcpyHostToDevice, c->stream));
+	GDSP_CUDA (cudaMemcpyAsync (cs->wf.segAllNeg, h_allneg, sizeof (int) * cs->nseg, cudaMemcpyHostToDevice, c->stream));
+	k_clump_tilecarry<<<cs->nseg, 256, 0, c->stream>>> (cs->tm.d_base, cs->wf, cs->d_cin);
+	GDSP_KERNEL_CHECK ();
+	k_clump_emit<<<(unsigned) cs->tm.ntiles, CL_THREADS, 0, c->stream>>> (E->d, cs->tm.d_base, cs->nseg, sig, cs->oneVal, cs->zeroVal, cs->wf);
+	GDSP_KERNEL_CHECK ();
+	return GDSP_OK;
+	}
+
+
+
 extern "C" size_t gdsp_clump_work_bytes (uint64_t buffer_cells)
 	{
 	return (size_t) (buffer_cells * 17 + 3 * 256 + 65536 * 4);
@@ -911,7 +1290,7 @@ extern "C" int gdsp_clump (gdsp_ctx* c, const gdsp_layout* L_, double* sig, uint
 	GDSP_REQUIRE (L->nseg <= 65536, "gdsp_clump: more than 65536 segments");
 	for (int s = 0; s < L->nseg; s++)
 		GDSP_REQUIRE (L->h[s].pos0 == 0 && L->h[s].hi - L->h[s].lo == L->h[s].chrom_len,
-		              "gdsp_clump: slab-sharded chromosomes need the carry variant (not in this build)");
+		              "gdsp_clump: a slab-sharded chromosome needs the carry variant (gdsp_clump_slab_*)");
 	TileMap tm;
 	GDSP_TRY (gdsp_layout_tilemap (L, CL_TILE, &tm));
 
@@ -941,6 +1320,7 @@ extern "C" int gdsp_clump (gdsp_ctx* c, const gdsp_layout* L_, double* sig, uint
 		wf.tsum = (unsigned char*) p;       p += (((size_t) tm.ntiles + 255) / 256) * 256;
 		wf.tcin = (unsigned char*) p;       p += (((size_t) tm.ntiles + 255) / 256) * 256;
 		wf.segAllNeg = (int*) p;
+		wf.segCarryIn = NULL;  wf.segSufMax = NULL;  wf.segFlags = NULL;
 		const uint32_t reach = maxLmin ? maxLmin : 1;
 		const size_t smem = ((size_t) ((reach + CLF_GROUP - 1) / CLF_GROUP) + CLF_GROUPS) * (CLF_GROUP / 16 * 17) * sizeof (double);
 		if (smem > 48 * 1024)
@@ -964,7 +1344,7 @@ extern "C" int gdsp_clump (gdsp_ctx* c, const gdsp_layout* L_, double* sig, uint
 		GDSP_KERNEL_CHECK ();
 		k_clump_tilesum<<<(unsigned) ((tm.ntiles + 7) / 8), 256, 0, c->stream>>> (tm.ntiles, wf);
 		GDSP_KERNEL_CHECK ();
-		k_clump_tilecarry<<<L->nseg, 256, 0, c->stream>>> (tm.d_base, wf);
+		k_clump_tilecarry<<<L->nseg, 256, 0, c->stream>>> (tm.d_base, wf, NULL);
 		GDSP_KERNEL_CHECK ();
 		k_clump_emit<<<(unsigned) tm.ntiles, CL_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, sig, oneVal, zeroVal, wf);
 		GDSP_KERNEL_CHECK ();

@@ -15,16 +15,37 @@ def _round_up(x, a):
     return (x + a - 1) // a * a
 
 
-def partition(sorted_lengths, world, rank, halo):
+def slab_cuts(sorted_lengths, world, align=1):
+    """genome coordinates of the world+1 slab boundaries.  A cut that falls inside a chromosome is moved
+    to the nearest multiple of `align` in CHROMOSOME coordinates (or to the chromosome's end), so that
+    with align = 8192 every kernel's tiles on a piece coincide with the whole chromosome's tiles -- the
+    carry variants of clump need that (4096), and tile-local sums then associate exactly as on one GPU."""
+    total = sum(sorted_lengths)
+    starts = [0]
+    for l in sorted_lengths:
+        starts.append(starts[-1] + l)
+    cuts = [0]
+    for r in range(1, world):
+        c = total * r // world
+        if align > 1:
+            si = max(i for i in range(len(sorted_lengths)) if starts[i] <= c) if sorted_lengths else 0
+            pos = c - starts[si]
+            pos = min(sorted_lengths[si], (pos + align // 2) // align * align)
+            c = starts[si] + pos
+        cuts.append(max(c, cuts[-1]))
+    cuts.append(total)
+    return cuts
+
+
+def partition(sorted_lengths, world, rank, halo, align=1):
     """-> (segs, buffer_cells) for `rank`.
 
     sorted_lengths: chromosome lengths in layout (chromsSorted) order.
     segs: list of (sorted_index, lo, hi, dlo, dhi, pos0) -- one per owned piece,
     buffer cell ranges as in gdsp_seg (lo multiple of 64).
     """
-    total = sum(sorted_lengths)
-    cut0 = total * rank // world
-    cut1 = total * (rank + 1) // world
+    cuts = slab_cuts(sorted_lengths, world, align)
+    cut0, cut1 = cuts[rank], cuts[rank + 1]
     segs = []
     g0 = 0                       # genome coordinate of the current chromosome's first base
     pos = 0                      # next free buffer cell
@@ -47,7 +68,7 @@ def partition(sorted_lengths, world, rank, halo):
     return segs, buffer_cells
 
 
-def halo_plan(sorted_lengths, world, rank, halo):
+def halo_plan(sorted_lengths, world, rank, halo, align=1):
     """-> list of (peer, send_lo, send_hi, recv_lo, recv_hi) in buffer cells for `rank`.
 
     Only the first piece can continue to the left and only the last piece to the
@@ -57,7 +78,7 @@ def halo_plan(sorted_lengths, world, rank, halo):
     never this rank's own halo: the two differ whenever a cut is close to a
     chromosome boundary.  A piece shorter than the halo its neighbour needs would
     need cells from two ranks away: refused (ValueError)."""
-    segs, _ = partition(sorted_lengths, world, rank, halo)
+    segs, _ = partition(sorted_lengths, world, rank, halo, align)
     plan = []
     if not segs:
         if world > 1 and halo > 0 and sum(sorted_lengths) > 0:
@@ -69,7 +90,7 @@ def halo_plan(sorted_lengths, world, rank, halo):
         peer = my right edge) or the right halo of its last piece"""
         if peer < 0 or peer >= world:
             return 0, None
-        psegs, _ = partition(sorted_lengths, world, peer, halo)
+        psegs, _ = partition(sorted_lengths, world, peer, halo, align)
         if not psegs:
             return 0, None
         si, lo, hi, dlo, dhi, pos0 = psegs[0] if side == "left" else psegs[-1]
@@ -637,6 +658,104 @@ def slab_clump(transport, gather, genome_factory, average=0.0, length=100, relat
         if whole is not None:
             whole.torch.cuda.synchronize()
             whole.close()
+
+
+def slab_clump_carries(parts, gather, average=0.0, length=100, relative_length=0.0, above=True, one=1.0, zero=0.0):
+    """clump_search (clump.c:494-736) on a slab-sharded genome WITHOUT moving the signal: the four
+    chromosome-wide dependencies travel as per-piece carries (gdsp_clump_slab_*), three small all-gathers:
+      1. {sum, minimum prefix sum} of every piece's head and tail  -> {P, M} entering every piece
+      2. maximum valid prefix sum of every piece                   -> suffix maximum entering from the right
+      3. generate/propagate pair of the run trimming               -> carry bits entering from both sides
+    Needs: the halos exchanged (>= 4096 cells), slab cuts at multiples of 4096 (partition(align=8192)),
+    minimum length <= 4096.  Bit-identical to the single-GPU kernels."""
+    import ctypes as C
+    from . import capi
+    comm = _as_comm(parts, gather)
+    neg_inf = -float("inf")
+    width = int(comm.gather_f64([_np.array([float(g.nseg)]) for g in parts]).max())
+    plans = []
+    for g in parts:
+        wb = g.lib.gdsp_clump_work_bytes(g.buffer_cells)
+        work = g.work(wb)
+        h = C.c_void_p()
+        capi.check(g.lib.gdsp_clump_slab_create(g.ctx, g.layout, g.buffer_cells, g._p(work), float(average), int(length),
+                                                float(relative_length), int(above), float(one), float(zero), C.byref(h)))
+        plans.append(h)
+    try:
+        def table(g, cols, fill):
+            """per-piece values of this rank padded to the common width, with (chromosome, pos0) keys"""
+            rec = _np.full((width, 2 + len(cols[0]) if cols else 2), fill, dtype=_np.float64)
+            rec[:, 0] = -1.0
+            for k in range(g.nseg):
+                rec[k, 0], rec[k, 1] = g.seg_chrom[k], g.segs[k][4]
+                rec[k, 2:] = cols[k]
+            return rec
+
+        def by_chrom(allrec):
+            out = {}
+            for row in allrec.reshape(-1, allrec.shape[-1]):
+                if row[0] >= 0:
+                    out.setdefault(int(row[0]), []).append(row)
+            for ci in out:
+                out[ci].sort(key=lambda r: r[1])
+            return out
+
+        # ---- 1: aggregates -> carries
+        local = []
+        for g, h in zip(parts, plans):
+            agg = (C.c_double * (5 * g.nseg))()
+            capi.check(g.lib.gdsp_clump_slab_reduce(h, g._p(g.sig), agg))
+            local.append(table(g, [[agg[5 * k + j] for j in range(5)] for k in range(g.nseg)], 0.0))
+        chrom = by_chrom(comm.gather_f64(local))
+        sufs = []
+        for g, h in zip(parts, plans):
+            cin = (C.c_double * (2 * g.nseg))()
+            for k in range(g.nseg):
+                P, M = 0.0, 0.0
+                rows = [r for r in chrom[g.seg_chrom[k]] if r[1] < g.segs[k][4]]
+                for i, r in enumerate(rows):                 # pieces to the left, in order: head, then tail
+                    M = min(M, P + r[3]); P = P + r[2]
+                    if i < len(rows) - 1:                    # the nearest piece's tail is this piece's halo tile
+                        M = min(M, P + r[5]); P = P + r[4]
+                cin[2 * k], cin[2 * k + 1] = P, M
+            suf = (C.c_double * g.nseg)()
+            capi.check(g.lib.gdsp_clump_slab_mark(h, g._p(g.sig), cin, suf))
+            sufs.append(suf)
+        # ---- 2: suffix maxima
+        local = [table(g, [[sufs[i][k]] for k in range(g.nseg)], neg_inf) for i, g in enumerate(parts)]
+        chrom2 = by_chrom(comm.gather_f64(local))
+        gps = []
+        for g, h in zip(parts, plans):
+            sin = (C.c_double * g.nseg)()
+            for k in range(g.nseg):
+                later = [r[2] for r in chrom2[g.seg_chrom[k]] if r[1] > g.segs[k][4]]
+                sin[k] = max(later) if later else neg_inf
+            gp = (C.c_int * g.nseg)()
+            capi.check(g.lib.gdsp_clump_slab_trim(h, g._p(g.sig), sin, gp))
+            gps.append(gp)
+        # ---- 3: trimming carries
+        local = [table(g, [[float(gps[i][k])] for k in range(g.nseg)], 0.0) for i, g in enumerate(parts)]
+        chrom3 = by_chrom(comm.gather_f64(local))
+        apply_gp = lambda gp, cin: (gp | ((gp >> 1) & cin)) & 1
+        for g, h in zip(parts, plans):
+            cin = (C.c_ubyte * g.nseg)()
+            neg = (C.c_int * g.nseg)()
+            for k in range(g.nseg):
+                rows = chrom3[g.seg_chrom[k]]
+                cu = 0
+                for r in rows:
+                    if r[1] < g.segs[k][4]:
+                        cu = apply_gp(int(r[2]) & 3, cu)
+                cd = 0
+                for r in reversed(rows):
+                    if r[1] > g.segs[k][4]:
+                        cd = apply_gp((int(r[2]) >> 2) & 3, cd)
+                cin[k] = cu | (cd << 1)
+                neg[k] = int(all(r[6] != 0.0 for r in chrom[g.seg_chrom[k]]))
+            capi.check(g.lib.gdsp_clump_slab_emit(h, g._p(g.sig), cin, neg))
+    finally:
+        for g, h in zip(parts, plans):
+            g.lib.gdsp_clump_slab_destroy(h)
 
 
 def slab_sorted_binarize(parts, gather, thr, ties_above=False, one=1.0, zero=0.0):

@@ -342,6 +342,31 @@ int  gdsp_clump (gdsp_ctx* ctx, const gdsp_layout* lay, double* sig,
                  uint32_t min_length, double relative_length, int above,
                  double one_val, double zero_val);
 
+/* clump / anticlump on a SLAB-SHARDED genome (one GPU owns a contiguous piece of a chromosome): the
+ * chromosome-wide dependencies of clump_search (prefix sums and minima going right, the suffix maximum
+ * of valid ends going left, the run trimming both ways) travel as per-piece carries; the signal never
+ * moves.  Four phases, each taking/returning a few host numbers per segment which the caller combines
+ * across ranks (NCCL all-gather; genodsp_b200/slab.py:slab_clump_carries shows the folds):
+ *   reduce  -> h_agg[5*s..]   = {head sum, head min prefix, tail sum, tail min prefix, all-negative flag}
+ *              (tail = the piece's last 4096-cell tile when the chromosome continues to the right)
+ *   mark    <- h_carry_in[2*s..] = {P, M} before the first cell of the segment's halo tile (M includes P[-1]=0)
+ *           -> h_sufmax[s]    = maximum valid prefix sum over the owned cells (-inf if none)
+ *   trim    <- h_sufmax_in[s] = maximum of h_sufmax over the pieces to the right (-inf if none)
+ *           -> h_gp[s]        = generate/propagate pair of the owned tiles (bits 0-1 upwards, 2-3 downwards)
+ *   emit    <- h_cin[s] bit0/1 = a trimmed run reaches the piece from the left/right; h_allneg[s] = the
+ *              whole chromosome has no qualifying cell (clump.c:545-565); writes one/zero in place.
+ * Requirements: segments with pos0 > 0 have >= 4096 valid halo cells on the left (dlo <= lo-4096), cuts are
+ * multiples of 4096 in chromosome coordinates, minimum length <= 4096.  `work` as for gdsp_clump. */
+typedef struct gdsp_clump_slab gdsp_clump_slab;
+int  gdsp_clump_slab_create (gdsp_ctx* ctx, const gdsp_layout* lay, uint64_t buffer_cells, void* work,
+                             double average, uint32_t min_length, double relative_length, int above,
+                             double one_val, double zero_val, gdsp_clump_slab** out);
+int  gdsp_clump_slab_reduce (gdsp_clump_slab* cs, const double* sig, double* h_agg);
+int  gdsp_clump_slab_mark   (gdsp_clump_slab* cs, const double* sig, const double* h_carry_in, double* h_sufmax);
+int  gdsp_clump_slab_trim   (gdsp_clump_slab* cs, const double* sig, const double* h_sufmax_in, int* h_gp);
+int  gdsp_clump_slab_emit   (gdsp_clump_slab* cs, double* sig, const unsigned char* h_cin, const int* h_allneg);
+void gdsp_clump_slab_destroy (gdsp_clump_slab* cs);
+
 /* ---- run-length output ------------------------------------------------------
  * report_intervals, genodsp.c:1561-1691: maximal runs of raw-equal values
  * (every cell its own run when collapse==0); runs of value 0 are dropped

@@ -120,3 +120,115 @@ def test_closed_form_and_bit_trimming_match_the_oracle(kind, tile_words):
             want = orc.clump(v.copy(), T, lmin, above, 1.0, 0.0) != 0
             got = clump_closed_form(v, T, lmin, above, tile_words)
             assert np.array_equal(want, got), (kind, trial, n, lmin, above, np.flatnonzero(want != got)[:5])
+
+
+# ----------------------------------------------------------------------------------------------
+# The slab-sharded variant (gdsp_clump_slab_* + slab.slab_clump_carries): a chromosome cut into pieces at
+# multiples of TILE; only per-piece carries cross the cuts.  Emulated piece by piece exactly as the phases
+# of the C-ABI see the data: a piece reads its own cells plus one halo tile to the left.
+# ----------------------------------------------------------------------------------------------
+def slab_clump_emulation(v, T, lmin, above, tile, cuts):
+    n = v.size
+    d_all = (v - T) if above else (T - v)
+    bounds = [0] + list(cuts) + [n]
+    pieces = [(bounds[k], bounds[k + 1]) for k in range(len(bounds) - 1)]
+    # phase 1: head/tail aggregates {S, m}: m = minimum inclusive prefix sum relative to the range start
+    def agg(a, b):
+        if b <= a:
+            return 0.0, np.inf
+        c = np.cumsum(d_all[a:b])
+        return float(c[-1]), float(c.min())
+    aggs = []
+    for k, (a, b) in enumerate(pieces):
+        cont_r = b < n
+        t = b - tile if cont_r else b
+        aggs.append((agg(a, t), agg(t, b), bool((d_all[max(0, a - (tile if a else 0)):b] < 0).all())))
+    allneg = all(x[2] for x in aggs)
+    # phase 2 per piece: carry-in at the halo tile start, P/M over halo+owned, marks without the right carry
+    marked_parts, sufmax_own, state = [], [], []
+    for k, (a, b) in enumerate(pieces):
+        P0, M0 = 0.0, 0.0
+        for q in range(k):
+            (Sh, mh), (St, mt), _ = aggs[q]
+            M0 = min(M0, P0 + mh); P0 += Sh
+            if q < k - 1:
+                M0 = min(M0, P0 + mt); P0 += St
+        e0 = a - tile if a else 0                         # first cell the piece can read
+        d = d_all[e0:b]
+        P = P0 + np.cumsum(d)
+        M = np.minimum(np.minimum.accumulate(P), M0)      # includes everything before e0 (and P[-1] = 0)
+        Mprev = np.concatenate(([M0], M[:-1]))            # M[p-1]
+        idx = np.arange(e0, b)
+        # M[i-lmin]: inside the readable range by construction (lmin <= tile)
+        sh = np.where(idx >= lmin, np.concatenate((np.full(lmin, M0), M))[:idx.size] if lmin else M, 0.0)
+        if lmin:
+            shifted = np.concatenate((np.full(lmin, np.nan), M))[:idx.size]
+            # cells whose i-lmin falls before e0 only occur in the halo tile (never used) or when e0 == 0
+            sh = np.where(idx >= lmin, shifted, 0.0)
+        q = np.where((idx + 1 >= lmin) & (sh <= P), P, -np.inf)
+        own = idx >= a
+        q_own = np.where(own, q, -np.inf)
+        suf = np.maximum.accumulate(q_own[::-1])[::-1]
+        marked = (suf >= Mprev) & own
+        marked_parts.append(marked[own])
+        sufmax_own.append(float(q_own.max()) if own.any() else -np.inf)
+        state.append((Mprev[own], own))
+    # phase 3: suffix maximum from the pieces to the right: everything with M[p-1] <= S_in is marked
+    for k in range(len(pieces)):
+        s_in = max(sufmax_own[k + 1:], default=-np.inf)
+        if s_in > -np.inf:
+            marked_parts[k] = marked_parts[k] | (state[k][0] <= s_in)
+    marked = np.concatenate(marked_parts)
+    qual = d_all >= 0
+    # trimming with piece-level generate/propagate pairs (cells instead of words: same algebra)
+    def piece_gp(mk, ql):
+        g, p = 0, 1
+        for m_, q_ in zip(mk, ql):
+            g, p = ((1 if (m_ and q_) else 0) | ((1 if m_ else 0) & g)), p & (1 if m_ else 0)
+        return g, p
+    ups = [piece_gp(marked[a:b], qual[a:b]) for a, b in pieces]
+    dns = [piece_gp(marked[a:b][::-1], qual[a:b][::-1]) for a, b in pieces]
+    out = np.zeros(n, bool)
+    for k, (a, b) in enumerate(pieces):
+        cu = 0
+        for q in range(k):
+            cu = ups[q][0] | (ups[q][1] & cu)
+        cd = 0
+        for q in range(len(pieces) - 1, k, -1):
+            cd = dns[q][0] | (dns[q][1] & cd)
+        mk, ql = marked[a:b], qual[a:b]
+        fu = np.zeros(b - a, bool); c = cu
+        for i in range(b - a):
+            c = 1 if (mk[i] and (ql[i] or c)) else 0
+            fu[i] = bool(c)
+        fd = np.zeros(b - a, bool); c = cd
+        for i in range(b - a - 1, -1, -1):
+            c = 1 if (mk[i] and (ql[i] or c)) else 0
+            fd[i] = bool(c)
+        out[a:b] = fu & fd
+    if allneg:
+        out[:] = False
+    return out
+
+
+@pytest.mark.parametrize("kind", ["int", "binary", "plateau"])
+def test_slab_carries_match_the_oracle(kind):
+    orc = Oracle()
+    rng = np.random.default_rng({"int": 11, "binary": 12, "plateau": 13}[kind])
+    tile = 64
+    for trial in range(30):
+        n = int(rng.integers(4 * tile, 30 * tile))
+        if kind == "int":
+            v, T = rng.poisson(5, n).astype(float), 5.5
+        elif kind == "binary":
+            v, T = (rng.random(n) < 0.3).astype(float), 0.5
+        else:
+            v, T = np.full(n, 4.0), 4.5
+            v[n // 5: n // 5 + n // 2] = 5.0; v[::17] = 9.0; v[(n // 5 + n // 2):] = 3.0
+        ncut = int(rng.integers(1, 4))
+        cuts = sorted(set(int(c) * tile for c in rng.integers(1, n // tile, ncut)))
+        lmin = int(rng.choice([1, 2, 10, 40, 64]))
+        for above in (True, False):
+            want = orc.clump(v.copy(), T, lmin, above, 1.0, 0.0) != 0
+            got = slab_clump_emulation(v, T, lmin, above, tile, cuts)
+            assert np.array_equal(want, got), (kind, trial, n, cuts, lmin, above, np.flatnonzero(want != got)[:8])

@@ -16,17 +16,18 @@ CHROMS = [("chr1", 90001), ("chr2", 50000), ("chr3", 30011), ("chr4", 777)]
 HALO = 600
 
 
-def make_ranks(world, halo=HALO):
+def make_ranks(world, halo=HALO, align=1, chroms=None):
     from genodsp_b200 import slab
     from genodsp_b200.genome import Genome
-    order = sorted(range(len(CHROMS)), key=lambda i: -CHROMS[i][1])
-    lengths = [CHROMS[i][1] for i in order]
+    chroms = chroms or CHROMS
+    order = sorted(range(len(chroms)), key=lambda i: -chroms[i][1])
+    lengths = [chroms[i][1] for i in order]
     ranks = []
     for r in range(world):
-        segs_s, cells = slab.partition(lengths, world, r, halo)
+        segs_s, cells = slab.partition(lengths, world, r, halo, align)
         segs = [(order[si], lo, hi, dlo, dhi, pos0) for si, lo, hi, dlo, dhi, pos0 in segs_s]
-        g = Genome(CHROMS, segs=segs, buffer_cells=cells)
-        g.plan = slab.halo_plan(lengths, world, r, halo)
+        g = Genome(chroms, segs=segs, buffer_cells=cells)
+        g.plan = slab.halo_plan(lengths, world, r, halo, align)
         ranks.append(g)
     return ranks, order
 
@@ -46,7 +47,7 @@ def scatter_signal(ranks, inputs):
 
 
 def gather_signal(ranks):
-    out = {n: np.zeros(l) for n, l in CHROMS}
+    out = {n: np.zeros(l) for n, l in ranks[0].chroms}
     for g in ranks:
         sig = g.sig.cpu().numpy()
         for k, (lo, hi, dlo, dhi, pos0, clen) in enumerate(g.segs):
@@ -272,6 +273,64 @@ def test_slab_percentile_then_binarize(world):
             got = gather_signal(ranks)
             cat = np.concatenate([got[CHROMS[i][0]] for i in order])
             assert np.array_equal(cat, want_sorted), (world, p, K)
+    finally:
+        for g in ranks:
+            g.close()
+
+
+CLUMP_CHROMS = [("chr1", 150001), ("chr2", 61440), ("chr3", 30011), ("chr4", 777)]
+
+
+def _clump_signals(rng):
+    """signals that make every carry of slab_clump_carries matter across the cuts"""
+    sig = {}
+    # (a) coverage-like noise: many short clumps, some straddling a cut
+    sig["noise"] = {name: rng.poisson(4, n).astype(np.float64) for name, n in CLUMP_CHROMS}
+    # (b) one long rise then a long decline: a clump that spans several pieces (suffix maximum from the right,
+    #     trimming carries from both sides), qualifying cells sparse
+    b = {}
+    for name, n in CLUMP_CHROMS:
+        v = np.full(n, 4.0)
+        v[n // 5: n // 5 + n // 2] = 5.0            # long stretch above T = 4.5
+        v[::97] = 9.0
+        v[(n // 5 + n // 2):] = 3.0
+        b[name] = v
+    sig["plateau"] = b
+    # (c) everything qualifies / nothing qualifies
+    sig["all"] = {name: np.full(n, 7.0) for name, n in CLUMP_CHROMS}
+    sig["none"] = {name: np.full(n, 1.0) for name, n in CLUMP_CHROMS}
+    # (d) slow drift: the prefix-sum minimum is reached far to the left of every end
+    d = {}
+    for name, n in CLUMP_CHROMS:
+        v = 4.0 + np.sign(np.sin(np.arange(n) / 9000.0)) * 1.0 + (rng.integers(0, 2, n) * 0.5)
+        d[name] = v
+    sig["drift"] = d
+    return sig
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_slab_clump_carries(world):
+    """clump / anticlump on slab pieces with per-piece carries (gdsp_clump_slab_*): only a few numbers per
+    piece cross the cuts, and the result equals the whole-chromosome oracle bit for bit"""
+    from genodsp_b200 import slab
+    orc = Oracle()
+    rng = np.random.default_rng(170 + world)
+    ranks, order = make_ranks(world, halo=4096, align=4096, chroms=CLUMP_CHROMS)
+    try:
+        cut = sum(1 for g in ranks for k in range(g.nseg) if g.segs[k][4] > 0)
+        assert cut >= 1
+        for label, sig in _clump_signals(rng).items():
+            for above, L in ((True, 40), (False, 40), (True, 1), (True, 1000), (True, 4096)):
+                if label in ("all", "none") and L not in (40, 4096):
+                    continue
+                scatter_signal(ranks, sig)
+                exchange(ranks)
+                slab.slab_clump_carries(ranks, slab.virtual_gather, average=4.5, length=L, above=above, one=2.0, zero=-1.0)
+                got = gather_signal(ranks)
+                for name, _ in CLUMP_CHROMS:
+                    want = orc.clump(sig[name].copy(), 4.5, L, above, 2.0, -1.0)
+                    bad = np.nonzero(bits(got[name]) != bits(want))[0]
+                    assert bad.size == 0, (label, world, above, L, name, bad.size, bad[:8], got[name][bad[:8]], want[bad[:8]])
     finally:
         for g in ranks:
             g.close()
