@@ -245,6 +245,8 @@ class Pipelines:
                       torch.empty(cap, dtype=torch.float64, device=g.device))
         self.nruns = 0
         self.vars = {}
+        self.known = None
+        self.lengths = lengths
         self.overlap = slab.OverlappedExchange(g, plan, dist, (WINDOW - 1) // 2) if world > 1 else None
         self.taps = None
 
@@ -284,14 +286,15 @@ class Pipelines:
         if self.world == 1:
             self.vars.update(self.g.percentile(99.0, destructive=True))
         else:
-            (v,), n = self.slab.slab_percentiles([self.g], self.comm, [99000])
+            (v,), n, ((below, equal),), nan = self.slab.slab_percentiles([self.g], self.comm, [99000], ranked=True)
             self.vars["percentile99"] = v
+            self.known = (below, equal, nan, n, sum(self.lengths))
 
     def binarize_after_percentile(self):
         if self.world == 1:
             self.g.binarize(self.vars["percentile99"])           # consumes the pending sorted state: count + fill
         else:
-            self.slab.slab_sorted_binarize([self.g], self.comm, self.vars["percentile99"])
+            self.slab.slab_sorted_binarize([self.g], self.comm, self.vars["percentile99"], known=self.known)
 
     def binarize6(self):
         self.g.binarize(6.0)

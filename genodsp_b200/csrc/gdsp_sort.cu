@@ -863,6 +863,8 @@ k_pct_pass (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, 
             const __grid_constant__ PctBounds B, unsigned long long* __restrict__ counts,
             double* __restrict__ cand, unsigned long long cap, unsigned long long* __restrict__ ncand)
 	{
+	// ncand[1] receives the number of qualifying NaN cells (they sort to the ends of the key order)
+	unsigned int myNan = 0;
 	__shared__ unsigned long long s_key[PCT_MAXB];
 	__shared__ unsigned int       s_cnt[2 * PCT_MAXB + 1];
 	const int nb = B.nb, nreg = 2 * nb + 1;
@@ -897,6 +899,7 @@ k_pct_pass (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, 
 				{
 				const double v = vv[u];
 				bool q = qq[u] && !(v < mn) && !(v > mx);
+				myNan += q && (v != v);
 				int reg = 0;  bool isB = false;
 				if (q) reg = pct_region (s_key, nb, f64_key (v), isB);
 				if (SMALL)
@@ -943,6 +946,9 @@ k_pct_pass (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, 
 			if (lane == 0 && x && r < nreg) atomicAdd (&s_cnt[r], x);
 			}
 		}
+	#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) myNan += __shfl_xor_sync (0xffffffffu, myNan, d);
+	if (lane == 0 && myNan) atomicAdd (&ncand[1], (unsigned long long) myNan);
 	__syncthreads ();
 	for (int i = threadIdx.x; i < nreg; i += 256)
 		if (s_cnt[i]) atomicAdd (&counts[i], (unsigned long long) s_cnt[i]);
@@ -967,13 +973,14 @@ struct PctSmall
 template <int NB>
 struct PctAcc
 	{
-	unsigned int tot, lt0, le0, lt1, le1;
-	__device__ __forceinline__ void clear () { tot = lt0 = le0 = lt1 = le1 = 0; }
+	unsigned int tot, lt0, le0, lt1, le1, nan;
+	__device__ __forceinline__ void clear () { tot = lt0 = le0 = lt1 = le1 = nan = 0; }
 	// returns true when the cell must be compacted
 	__device__ __forceinline__ bool add (const PctSmall& P, double v, bool q)
 		{
 		const unsigned long long k = f64_key (v);
 		tot += q;
+		nan += q && (v != v);
 		bool a0 = false, b0 = false, a1 = false, b1 = false;
 		if (NB >= 1) { a0 = q && (k < P.k0);  b0 = q && (k <= P.k0);  lt0 += a0;  le0 += b0; }
 		if (NB >= 2) { a1 = q && (k < P.k1);  b1 = q && (k <= P.k1);  lt1 += a1;  le1 += b1; }
@@ -1010,8 +1017,8 @@ k_pct_pass_small (const SegDev* __restrict__ segs, const uint64_t* __restrict__ 
                   const PctSmall P, unsigned long long* __restrict__ counts,
                   double* __restrict__ cand, unsigned long long cap, unsigned long long* __restrict__ ncand)
 	{
-	__shared__ unsigned int s_cnt[5];
-	if (threadIdx.x < 5) s_cnt[threadIdx.x] = 0;
+	__shared__ unsigned int s_cnt[6];
+	if (threadIdx.x < 6) s_cnt[threadIdx.x] = 0;
 	__syncthreads ();
 	PctAcc<NB> A;  A.clear ();
 
@@ -1062,9 +1069,9 @@ k_pct_pass_small (const SegDev* __restrict__ segs, const uint64_t* __restrict__ 
 			}
 		}
 
-	unsigned int x[5] = { A.tot, A.lt0, A.le0, A.lt1, A.le1 };
+	unsigned int x[6] = { A.tot, A.lt0, A.le0, A.lt1, A.le1, A.nan };
 	#pragma unroll
-	for (int r = 0; r < 5; r++)
+	for (int r = 0; r < 6; r++)
 		{
 		#pragma unroll
 		for (int d = 16; d > 0; d >>= 1) x[r] += __shfl_xor_sync (0xffffffffu, x[r], d);
@@ -1075,6 +1082,7 @@ k_pct_pass_small (const SegDev* __restrict__ segs, const uint64_t* __restrict__ 
 		{
 		// cumulative counts -> region populations (region 2i+1 = "equals bound i")
 		const unsigned long long tot = s_cnt[0], lt0 = s_cnt[1], le0 = s_cnt[2], lt1 = s_cnt[3], le1 = s_cnt[4];
+		if (s_cnt[5]) atomicAdd (&ncand[1], (unsigned long long) s_cnt[5]);      // qualifying NaN cells
 		if (NB == 0) { if (tot) atomicAdd (&counts[0], tot); }
 		if (NB == 1)
 			{
@@ -1135,8 +1143,27 @@ static inline double host_unkey (unsigned long long k)
 	double d;  memcpy (&d, &b, 8);  return d;
 	}
 
+// [lower, upper) positions of key(v) inside the ascending (key order) array a[0..n): how many candidates
+// lie below the selected value and how many equal it
+__global__ void k_equal_range (const double* __restrict__ a, unsigned long long n, const double* __restrict__ vals, int nvals,
+                               const unsigned long long* __restrict__ lo0, const unsigned long long* __restrict__ hi0,
+                               unsigned long long* __restrict__ out)
+	{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nvals) return;
+	const unsigned long long k = f64_key (vals[i]);
+	unsigned long long lo = lo0[i], hi = hi0[i];
+	while (lo < hi) { const unsigned long long mid = (lo + hi) >> 1;  if (f64_key (a[mid]) < k) lo = mid + 1; else hi = mid; }
+	out[2 * i] = lo;
+	hi = hi0[i];
+	unsigned long long l2 = lo;
+	while (l2 < hi) { const unsigned long long mid = (l2 + hi) >> 1;  if (f64_key (a[mid]) <= k) l2 = mid + 1; else hi = mid; }
+	out[2 * i + 1] = l2;
+	}
+
 struct PctJob
 	{
+	unsigned long long nBelow, nEqual;     // samples with a key below / equal to the selected value (exact)
 	uint32_t pMilli;
 	bool     done;
 	double   value;
@@ -1148,9 +1175,31 @@ struct PctJob
 	bool     haveCounts;
 	};
 
+static int percentiles_impl (gdsp_ctx* c, const gdsp_layout* L_, const double* sig, double* tmp,
+                             uint64_t buffer_cells, uint32_t stride, double mn, double mx,
+                             const uint32_t* h_p_milli, int np, double* h_values, uint64_t* h_num_samples,
+                             uint64_t* h_below, uint64_t* h_equal, uint64_t* h_nan);
+
 extern "C" int gdsp_percentiles (gdsp_ctx* c, const gdsp_layout* L_, const double* sig, double* tmp,
                                  uint64_t buffer_cells, uint32_t stride, double mn, double mx,
                                  const uint32_t* h_p_milli, int np, double* h_values, uint64_t* h_num_samples)
+	{
+	return percentiles_impl (c, L_, sig, tmp, buffer_cells, stride, mn, mx, h_p_milli, np, h_values, h_num_samples, NULL, NULL, NULL);
+	}
+
+extern "C" int gdsp_percentiles_ranked (gdsp_ctx* c, const gdsp_layout* L_, const double* sig, double* tmp,
+                                        uint64_t buffer_cells, uint32_t stride, double mn, double mx,
+                                        const uint32_t* h_p_milli, int np, double* h_values, uint64_t* h_num_samples,
+                                        uint64_t* h_below, uint64_t* h_equal, uint64_t* h_nan)
+	{
+	GDSP_REQUIRE (h_below && h_equal && h_nan, "gdsp_percentiles_ranked: NULL argument");
+	return percentiles_impl (c, L_, sig, tmp, buffer_cells, stride, mn, mx, h_p_milli, np, h_values, h_num_samples, h_below, h_equal, h_nan);
+	}
+
+static int percentiles_impl (gdsp_ctx* c, const gdsp_layout* L_, const double* sig, double* tmp,
+                             uint64_t buffer_cells, uint32_t stride, double mn, double mx,
+                             const uint32_t* h_p_milli, int np, double* h_values, uint64_t* h_num_samples,
+                             uint64_t* h_below, uint64_t* h_equal, uint64_t* h_nan)
 	{
 	gdsp_layout* L = (gdsp_layout*) L_;
 	GDSP_REQUIRE (c && L && sig && tmp && h_num_samples, "gdsp_percentiles: NULL argument");
@@ -1192,10 +1241,11 @@ extern "C" int gdsp_percentiles (gdsp_ctx* c, const gdsp_layout* L_, const doubl
 	SampleSpace sp;  sp.nseg = L->nseg;  sp.sprefix = d_sprefix;  sp.segs = L->d;  sp.stride = stride;
 
 	std::vector<PctJob> jobs (np);
-	for (int i = 0; i < np; i++) { jobs[i].pMilli = h_p_milli[i];  jobs[i].done = false;  jobs[i].value = 0;  jobs[i].keyLo = 0;  jobs[i].keyHi = ~0ull;  jobs[i].below = jobs[i].inside = 0;  jobs[i].haveCounts = false; }
+	for (int i = 0; i < np; i++) { jobs[i].nBelow = jobs[i].nEqual = 0;  jobs[i].pMilli = h_p_milli[i];  jobs[i].done = false;  jobs[i].value = 0;  jobs[i].keyLo = 0;  jobs[i].keyHi = ~0ull;  jobs[i].below = jobs[i].inside = 0;  jobs[i].haveCounts = false; }
 
-	uint64_t numSamples = 0;
+	uint64_t numSamples = 0, numNan = 0;
 	bool haveCount = false;
+	if (h_nan) *h_nan = 0;
 	if (nslots == 0) { *h_num_samples = 0;  return GDSP_OK; }
 
 	double* hs = NULL;                                   // sorted sample (page-locked host copy)
@@ -1279,13 +1329,15 @@ extern "C" int gdsp_percentiles (gdsp_ctx* c, const gdsp_layout* L_, const doubl
 		// ---- (3) the counting / compaction pass
 		const int nreg = 2 * B.nb + 1;
 		GDSP_CUDA (cudaMemsetAsync (d_counts, 0, sizeof (unsigned long long) * nreg, c->stream));
-		GDSP_CUDA (cudaMemsetAsync (d_ncand, 0, 8, c->stream));
+		GDSP_CUDA (cudaMemsetAsync (d_ncand, 0, 16, c->stream));
 		GDSP_TRY (pct_launch_pass (c, L, tmPct, sig, stride, mn, mx, B, d_counts, bufA, candCapTotal, d_ncand));
 		std::vector<unsigned long long> counts (nreg);
-		unsigned long long ncand = 0;
+		unsigned long long ncandNan[2] = { 0, 0 };
 		GDSP_CUDA (cudaMemcpyAsync (counts.data (), d_counts, sizeof (unsigned long long) * nreg, cudaMemcpyDeviceToHost, c->stream));
-		GDSP_CUDA (cudaMemcpyAsync (&ncand, d_ncand, 8, cudaMemcpyDeviceToHost, c->stream));
+		GDSP_CUDA (cudaMemcpyAsync (ncandNan, d_ncand, 16, cudaMemcpyDeviceToHost, c->stream));
 		GDSP_CUDA (cudaStreamSynchronize (c->stream));
+		const unsigned long long ncand = ncandNan[0];
+		numNan = ncandNan[1];
 		unsigned long long total = 0;
 		for (int r = 0; r < nreg; r++) total += counts[r];
 		numSamples = total;  haveCount = true;
@@ -1310,6 +1362,8 @@ extern "C" int gdsp_percentiles (gdsp_ctx* c, const gdsp_layout* L_, const doubl
 		}
 
 		// ---- (4) locate every open job's rank
+		std::vector<int> fromCand;                       // jobs answered from the sorted candidates in this iteration
+		std::vector<unsigned long long> fcLo, fcHi, fcBase;
 		for (int i : open)
 			{
 			// rank exactly as percentile.c:588/:686 computes it (numValues is a u32 there)
@@ -1324,7 +1378,12 @@ extern "C" int gdsp_percentiles (gdsp_ctx* c, const gdsp_layout* L_, const doubl
 			unsigned long long cum = 0;
 			int reg = 0;
 			for (reg = 0; reg < nreg; reg++) { if (rank < cum + counts[reg]) break;  cum += counts[reg]; }
-			if (reg & 1) { jobs[i].value = host_unkey (bounds[reg >> 1]);  jobs[i].done = true;  continue; }
+			if (reg & 1)
+				{
+				jobs[i].value = host_unkey (bounds[reg >> 1]);  jobs[i].done = true;
+				jobs[i].nBelow = cum;  jobs[i].nEqual = counts[reg];
+				continue;
+				}
 			const int r = reg >> 1;
 			if (B.compact[r] && candOk)
 				{
@@ -1332,6 +1391,11 @@ extern "C" int gdsp_percentiles (gdsp_ctx* c, const gdsp_layout* L_, const doubl
 				GDSP_CUDA (cudaMemcpyAsync (&v, sortedCand + candBefore[r] + (rank - cum), 8, cudaMemcpyDeviceToHost, c->stream));
 				GDSP_CUDA (cudaStreamSynchronize (c->stream));
 				jobs[i].value = v;  jobs[i].done = true;
+				if (h_below != NULL)
+					{
+					fromCand.push_back (i);
+					fcLo.push_back (candBefore[r]);  fcHi.push_back (candBefore[r] + counts[reg]);  fcBase.push_back (cum);
+					}
 				continue;
 				}
 			// missed: the wanted key lies strictly inside open region r; if the region is small
@@ -1340,9 +1404,38 @@ extern "C" int gdsp_percentiles (gdsp_ctx* c, const gdsp_layout* L_, const doubl
 			jobs[i].keyHi = (r < B.nb) ? bounds[r] - 1 : ~0ull;
 			jobs[i].below = cum;  jobs[i].inside = counts[reg];  jobs[i].haveCounts = true;
 			}
+		if (!fromCand.empty ())
+			{
+			// how many cells lie below / equal each value found among the candidates: one small kernel
+			// (a binary search per job in the sorted candidates), results through the unused half of bufB
+			const int nf = (int) fromCand.size ();
+			std::vector<double> fv (nf);
+			for (int k = 0; k < nf; k++) fv[k] = jobs[fromCand[k]].value;
+			void* wq;
+			GDSP_TRY (gdsp_ws (c, 6, (size_t) nf * 48, &wq));
+			double* d_v = (double*) wq;
+			unsigned long long* d_lo = (unsigned long long*) (d_v + nf);
+			unsigned long long* d_hi = d_lo + nf;
+			unsigned long long* d_out = d_hi + nf;
+			GDSP_CUDA (cudaMemcpyAsync (d_v, fv.data (), 8 * nf, cudaMemcpyHostToDevice, c->stream));
+			GDSP_CUDA (cudaMemcpyAsync (d_lo, fcLo.data (), 8 * nf, cudaMemcpyHostToDevice, c->stream));
+			GDSP_CUDA (cudaMemcpyAsync (d_hi, fcHi.data (), 8 * nf, cudaMemcpyHostToDevice, c->stream));
+			k_equal_range<<<(nf + 63) / 64, 64, 0, c->stream>>> (sortedCand, ncand, d_v, nf, d_lo, d_hi, d_out);
+			GDSP_KERNEL_CHECK ();
+			std::vector<unsigned long long> er (2 * nf);
+			GDSP_CUDA (cudaMemcpyAsync (er.data (), d_out, 16 * nf, cudaMemcpyDeviceToHost, c->stream));
+			GDSP_CUDA (cudaStreamSynchronize (c->stream));
+			for (int k = 0; k < nf; k++)
+				{
+				jobs[fromCand[k]].nBelow = fcBase[k] + (er[2 * k] - fcLo[k]);
+				jobs[fromCand[k]].nEqual = er[2 * k + 1] - er[2 * k];
+				}
+			}
 		}
+	if (h_nan) *h_nan = numNan;
 	for (int i = 0; i < np; i++)
 		{
+		if (h_below) { h_below[i] = jobs[i].nBelow;  h_equal[i] = jobs[i].nEqual; }
 		GDSP_REQUIRE (jobs[i].done || numSamples == 0, "gdsp_percentiles: selection did not converge for percentile %u", jobs[i].pMilli);
 		h_values[i] = jobs[i].value;
 		}
@@ -1403,6 +1496,29 @@ extern "C" int gdsp_pct_sample (gdsp_ctx* c, const gdsp_layout* L_, const double
 	return GDSP_OK;
 	}
 
+// positions [lo, hi) of the cells whose key equals key(value) in an array sorted by gdsp_sort_array
+extern "C" int gdsp_equal_range (gdsp_ctx* c, const double* d_sorted, uint64_t n, double value, uint64_t* h_lo, uint64_t* h_hi)
+	{
+	GDSP_REQUIRE (c && d_sorted && h_lo && h_hi, "gdsp_equal_range: NULL argument");
+	void* wq;
+	GDSP_TRY (gdsp_ws (c, 6, 48, &wq));
+	double* d_v = (double*) wq;
+	unsigned long long* d_lo = (unsigned long long*) (d_v + 1);
+	unsigned long long* d_hi = d_lo + 1;
+	unsigned long long* d_out = d_hi + 1;
+	const unsigned long long zero = 0, nn = n;
+	GDSP_CUDA (cudaMemcpyAsync (d_v, &value, 8, cudaMemcpyHostToDevice, c->stream));
+	GDSP_CUDA (cudaMemcpyAsync (d_lo, &zero, 8, cudaMemcpyHostToDevice, c->stream));
+	GDSP_CUDA (cudaMemcpyAsync (d_hi, &nn, 8, cudaMemcpyHostToDevice, c->stream));
+	k_equal_range<<<1, 64, 0, c->stream>>> (d_sorted, n, d_v, 1, d_lo, d_hi, d_out);
+	GDSP_KERNEL_CHECK ();
+	unsigned long long er[2];
+	GDSP_CUDA (cudaMemcpyAsync (er, d_out, 16, cudaMemcpyDeviceToHost, c->stream));
+	GDSP_CUDA (cudaStreamSynchronize (c->stream));
+	*h_lo = er[0];  *h_hi = er[1];
+	return GDSP_OK;
+	}
+
 extern "C" int gdsp_sort_array (gdsp_ctx* c, double* d_a, double* d_b, uint64_t n, int* h_result_in_b)
 	{
 	GDSP_REQUIRE (c && d_a && d_b && h_result_in_b, "gdsp_sort_array: NULL argument");
@@ -1419,9 +1535,28 @@ extern "C" int gdsp_sort_array (gdsp_ctx* c, double* d_a, double* d_b, uint64_t 
 	return GDSP_OK;
 	}
 
+static int pct_count_impl (gdsp_ctx* c, const gdsp_layout* L_, const double* sig, uint32_t stride,
+                           double mn, double mx, const uint64_t* h_bound_keys, int nb, const uint8_t* h_compact,
+                           uint64_t* h_counts, double* d_cand, uint64_t cap, uint64_t* h_ncand, uint64_t* h_nan);
+
 extern "C" int gdsp_pct_count (gdsp_ctx* c, const gdsp_layout* L_, const double* sig, uint32_t stride,
                                double mn, double mx, const uint64_t* h_bound_keys, int nb, const uint8_t* h_compact,
                                uint64_t* h_counts, double* d_cand, uint64_t cap, uint64_t* h_ncand)
+	{
+	return pct_count_impl (c, L_, sig, stride, mn, mx, h_bound_keys, nb, h_compact, h_counts, d_cand, cap, h_ncand, NULL);
+	}
+
+extern "C" int gdsp_pct_count_nan (gdsp_ctx* c, const gdsp_layout* L_, const double* sig, uint32_t stride,
+                                   double mn, double mx, const uint64_t* h_bound_keys, int nb, const uint8_t* h_compact,
+                                   uint64_t* h_counts, double* d_cand, uint64_t cap, uint64_t* h_ncand, uint64_t* h_nan)
+	{
+	GDSP_REQUIRE (h_nan, "gdsp_pct_count_nan: NULL argument");
+	return pct_count_impl (c, L_, sig, stride, mn, mx, h_bound_keys, nb, h_compact, h_counts, d_cand, cap, h_ncand, h_nan);
+	}
+
+static int pct_count_impl (gdsp_ctx* c, const gdsp_layout* L_, const double* sig, uint32_t stride,
+                           double mn, double mx, const uint64_t* h_bound_keys, int nb, const uint8_t* h_compact,
+                           uint64_t* h_counts, double* d_cand, uint64_t cap, uint64_t* h_ncand, uint64_t* h_nan)
 	{
 	gdsp_layout* L = (gdsp_layout*) L_;
 	GDSP_REQUIRE (c && L && sig && h_counts && h_ncand, "gdsp_pct_count: NULL argument");
@@ -1444,14 +1579,15 @@ extern "C" int gdsp_pct_count (gdsp_ctx* c, const gdsp_layout* L_, const double*
 	unsigned long long* d_counts = (unsigned long long*) ((char*) ws + 64);
 	const int nreg = 2 * nb + 1;
 	GDSP_CUDA (cudaMemsetAsync (d_counts, 0, sizeof (unsigned long long) * nreg, c->stream));
-	GDSP_CUDA (cudaMemsetAsync (d_ncand, 0, 8, c->stream));
+	GDSP_CUDA (cudaMemsetAsync (d_ncand, 0, 16, c->stream));
 	GDSP_TRY (pct_launch_pass (c, L, tmPct, sig, stride, mn, mx, B, d_counts, d_cand, cap, d_ncand));
 	std::vector<unsigned long long> counts (nreg);
-	unsigned long long ncand = 0;
+	unsigned long long ncandNan[2] = { 0, 0 };
 	GDSP_CUDA (cudaMemcpyAsync (counts.data (), d_counts, sizeof (unsigned long long) * nreg, cudaMemcpyDeviceToHost, c->stream));
-	GDSP_CUDA (cudaMemcpyAsync (&ncand, d_ncand, 8, cudaMemcpyDeviceToHost, c->stream));
+	GDSP_CUDA (cudaMemcpyAsync (ncandNan, d_ncand, 16, cudaMemcpyDeviceToHost, c->stream));
 	GDSP_CUDA (cudaStreamSynchronize (c->stream));
 	for (int r = 0; r < nreg; r++) h_counts[r] = counts[r];
-	*h_ncand = ncand;
+	*h_ncand = ncandNan[0];
+	if (h_nan) *h_nan = ncandNan[1];
 	return GDSP_OK;
 	}

@@ -296,10 +296,11 @@ class Genome:
         bk = (C.c_uint64 * max(nb, 1))(*[int(k) for k in bound_keys])
         cp = (C.c_uint8 * (nb + 1))(*[int(bool(x)) for x in compact])
         counts = (C.c_uint64 * (2 * nb + 1))()
-        ncand = C.c_uint64()
-        check(self.lib.gdsp_pct_count(self.ctx, self.layout, self._p(self.sig), int(stride), float(mn), float(mx),
-                                      bk, nb, cp, counts, self._p(self.tmp), cap, C.byref(ncand)))
+        ncand, nnan = C.c_uint64(), C.c_uint64()
+        check(self.lib.gdsp_pct_count_nan(self.ctx, self.layout, self._p(self.sig), int(stride), float(mn), float(mx),
+                                          bk, nb, cp, counts, self._p(self.tmp), cap, C.byref(ncand), C.byref(nnan)))
         n = int(ncand.value)
+        self.last_nan_count = int(nnan.value)
         return np.array(list(counts), dtype=np.uint64), n, (self.tmp[:n] if n <= cap else None)
 
     def sort_array(self, a):
@@ -311,6 +312,12 @@ class Genome:
         flag = C.c_int()
         check(self.lib.gdsp_sort_array(self.ctx, self._p(a), self._p(b), int(a.numel()), C.byref(flag)))
         return b if flag.value else a
+
+    def equal_range(self, sorted_t, value):
+        """gdsp_equal_range: [lo, hi) of the cells with value's key in a tensor sorted by sort_array"""
+        lo, hi = C.c_uint64(), C.c_uint64()
+        check(self.lib.gdsp_equal_range(self.ctx, self._p(sorted_t), int(sorted_t.numel()), float(value), C.byref(lo), C.byref(hi)))
+        return int(lo.value), int(hi.value)
 
     def smooth_to_host(self, window, out_host):
         """smooth + device->host delivery of the result, pipelined per chromosome piece: while piece
@@ -433,6 +440,14 @@ class Genome:
     def binarize(self, threshold=0.0, ties_above=False, one=1.0, zero=0.0):
         if isinstance(threshold, str):
             threshold = self.variables[threshold]     # logical.c:232-244
+        if self._pending_sort and float(threshold) != 0.0 and float(threshold) in getattr(self, "_sorted_known", {}):
+            # the selection pass already counted the cells below / equal to this percentile: fill only
+            below, equal = self._sorted_known[float(threshold)]
+            prefix, acc = [], 0
+            for (lo, hi, *_r) in self.segs:
+                prefix.append(acc); acc += hi - lo
+            self.fill_step(prefix, below if ties_above else below + equal, one, zero)
+            return
         if self._pending_sort:
             # binarizing the sorted genome = a step at cells - #(v > threshold): no sort needed
             done = C.c_int()
@@ -510,17 +525,23 @@ class Genome:
         ps = list(range(plo, phi + 1, pstep))
         pm = (C.c_uint32 * len(ps))(*ps)
         vals = (C.c_double * len(ps))()
-        n = C.c_uint64()
-        check(self.lib.gdsp_percentiles(self.ctx, self.layout, self._p(self.sig), self._p(self.tmp), self.buffer_cells,
-                                        int(window), float(mn), float(mx), pm, len(ps), vals, C.byref(n)))
+        below, equal = (C.c_uint64 * len(ps))(), (C.c_uint64 * len(ps))()
+        n, nnan = C.c_uint64(), C.c_uint64()
+        check(self.lib.gdsp_percentiles_ranked(self.ctx, self.layout, self._p(self.sig), self._p(self.tmp), self.buffer_cells,
+                                               int(window), float(mn), float(mx), pm, len(ps), vals, C.byref(n),
+                                               below, equal, C.byref(nnan)))
         self.num_samples = int(n.value)
         if self.num_samples == 0:
             return out
         for i, p in enumerate(ps):
             out[percentile_name(p)] = vals[i]
         self.variables.update(out)
+        self._sorted_known = {}
         if destructive:
             self._pending_sort = True                 # materialised by the next reader of self.sig
+            if self.num_samples == self.cells and int(nnan.value) == 0:
+                # every cell took part: #(v < value) and #(v == value) locate binarize's step in the sorted genome
+                self._sorted_known = {float(vals[i]): (int(below[i]), int(equal[i])) for i in range(len(ps))}
         return out
 
     def fill_step(self, prefix, step, one=1.0, zero=0.0):

@@ -23,6 +23,11 @@ typedef struct gdev
 	                                behind (percentile.c:611-651) but has not been sorted: set only when the
 	                                next operator is binarize, which does not need the sort
 	                                (gdsp_sorted_binarize); cleared by gd_materialise_sorted            */
+	/* what the selection pass of that percentile learned (every cell qualifying, no NaN): for each reported
+	 * value the number of cells below it and equal to it -- binarize then needs a fill, not a count */
+	int           knownN;
+	double        knownVal[1024];
+	u64           knownBelow[1024], knownEqual[1024];
 	} gdev;
 
 extern gdev gd;

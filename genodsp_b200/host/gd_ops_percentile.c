@@ -218,9 +218,18 @@ void op_percentile_apply (dspop* _op, arg_dont_complain(char* vName), arg_dont_c
 	double* vals = (double*) malloc (np * sizeof (double));
 	np = 0;
 	for (u32 p = op->percentileLo; p <= op->percentileHi; p += op->percentileStep) pm[np++] = p;
-	u64 numValues = 0;
-	gd_check (gdsp_percentiles (gd.ctx, gd.genome, gd.sig, gd.tmp, gd.cells, op->windowSize, op->minAllowed,
-	                            op->maxAllowed, pm, (int) np, vals, &numValues), _op->name);
+	u64 numValues = 0, numNan = 0;
+	u64* below = (u64*) malloc (np * sizeof (u64));
+	u64* equal = (u64*) malloc (np * sizeof (u64));
+	gd_check (gdsp_percentiles_ranked (gd.ctx, gd.genome, gd.sig, gd.tmp, gd.cells, op->windowSize, op->minAllowed,
+	                                   op->maxAllowed, pm, (int) np, vals, &numValues, below, equal, &numNan), _op->name);
+	gd.knownN = 0;
+	if (numNan == 0 && numValues == gdsp_layout_cells (gd.genome) && np <= 1024)
+		{
+		gd.knownN = (int) np;
+		for (u32 i = 0; i < np; i++) { gd.knownVal[i] = vals[i];  gd.knownBelow[i] = below[i];  gd.knownEqual[i] = equal[i]; }
+		}
+	free (below);  free (equal);
 	if (numValues == 0) { free (pm);  free (vals);  if (mapF) fclose (mapF);  goto no_values; }
 
 	u64 lastRank = 0;

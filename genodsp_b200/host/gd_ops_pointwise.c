@@ -159,6 +159,19 @@ int gd_pointwise_descriptor (dspop* _op, gdsp_pw_op* out, gd_pw_resources* res)
 				/* directly after a percentile: the sorted genome it leaves is thresholded without being
 				 * sorted (gd_ops_percentile.c); this binarize is then the first operator of its chain */
 				int done = 0;
+				for (int k = 0; k < gd.knownN; k++)
+					if (gd.knownVal[k] == op->a && op->a != 0.0)     /* +0.0 / -0.0 share a value but not a key */
+						{
+						/* the percentile's own selection pass counted the cells below / equal to this value */
+						u64* prefix = (u64*) malloc (gd.nchrom * sizeof (u64));
+						u64 acc = 0;
+						for (int i = 0; i < gd.nchrom; i++) { prefix[i] = acc;  acc += gd.segs[i].hi - gd.segs[i].lo; }
+						gd_check (gdsp_fill_step (gd.ctx, gd.genome, gd.sig, prefix,
+						                          gd.knownBelow[k] + (op->flag ? 0 : gd.knownEqual[k]), op->b, op->c), _op->name);
+						free (prefix);
+						gd.pendingSorted = 0;
+						return 0;
+						}
 				gd_check (gdsp_sorted_binarize (gd.ctx, gd.genome, gd.sig, op->a, op->flag, op->b, op->c, &done), _op->name);
 				if (done) { gd.pendingSorted = 0;  return 0; }
 				gd_materialise_sorted (_op->name);

@@ -294,17 +294,22 @@ class DistComm:
         self.dist.all_gather_into_tensor(out, t)
         return out.cpu().numpy().reshape((self.world,) + a.shape)
 
-    def cat_f64(self, local, cap):
-        """variable-length 1-D device tensors (each <= cap cells) -> [device tensor of all ranks' cells] per
-        local part; the lengths travel in the same collective (slot `cap`)"""
+    def cat_f64(self, local, cap=None):
+        """variable-length 1-D device tensors -> [device tensor of all ranks' cells] per local part.  The lengths
+        travel first (one small all-gather), then every rank pads to the longest"""
         t = local[0]
-        buf = self.t.zeros(cap + 1, dtype=self.t.float64, device=self.device)
+        n = self.t.tensor([t.numel()], dtype=self.t.int64, device=self.device)
+        cnts = self.t.empty(self.world, dtype=self.t.int64, device=self.device)
+        self.dist.all_gather_into_tensor(cnts, n)
+        counts = [int(c) for c in cnts.cpu().tolist()]
+        m = max(counts)
+        if m == 0:
+            return [self.t.empty(0, dtype=self.t.float64, device=self.device)]
+        buf = self.t.empty(m, dtype=self.t.float64, device=self.device)
         buf[:t.numel()].copy_(t)
-        buf[cap] = float(t.numel())
-        out = self.t.empty(self.world * (cap + 1), dtype=self.t.float64, device=self.device)
+        out = self.t.empty(self.world * m, dtype=self.t.float64, device=self.device)
         self.dist.all_gather_into_tensor(out, buf)
-        out = out.view(self.world, cap + 1)
-        counts = [int(c) for c in out[:, cap].cpu().tolist()]
+        out = out.view(self.world, m)
         return [self.t.cat([out[r, :counts[r]] for r in range(self.world)])]
 
     def gather(self, local):
@@ -330,7 +335,7 @@ class VirtualComm:
     def gather_f64(self, local):
         return _np.stack([_np.ascontiguousarray(a, _np.float64) for a in local])
 
-    def cat_f64(self, local, cap):
+    def cat_f64(self, local, cap=None):
         t = self.parts[0].torch
         return [t.cat([x.to(g.device) for x in local]) for g in self.parts]
 
@@ -471,7 +476,7 @@ def slab_runs(parts, gather, collapse=True, show_uncovered=0):
 
 
 def slab_percentiles(parts, gather, p_milli, stride=1, mn=-1.7976931348623157e308, mx=1.7976931348623157e308,
-                     sample_total=1 << 18, cand_cap=1 << 18, max_iter=60, sample_per_rank=None):
+                     sample_total=1 << 20, cand_cap=1 << 22, max_iter=60, sample_per_rank=None, ranked=False):
     """op_percentile_apply's order statistics (percentile.c:392-751) over all slabs, exact, without
     moving the signal: every rank samples its slab, the combined sample (all-gathered and sorted ON THE
     DEVICE) brackets each wanted rank between two keys, one counting pass per rank (gdsp_pct_count) gives
@@ -480,12 +485,13 @@ def slab_percentiles(parts, gather, p_milli, stride=1, mn=-1.7976931348623157e30
     between the brackets, whose combined sorted list holds the wanted element.  Regions are narrowed
     and the pass repeated when a bracket misses.  Candidates are only gathered while a rank holds at
     most `cand_cap` of them; a wider bracket is narrowed by another counting pass instead.
-    -> (values, number of samples); identical on every rank."""
+    -> (values, number of samples); identical on every rank.  ranked=True adds, per percentile,
+    (cells with a smaller key, cells with the same key) and the number of NaN samples."""
     comm = _as_comm(parts, gather)
     per_rank = int(sample_per_rank) if sample_per_rank else max(4096, int(sample_total) // comm.world)
-    jobs = [{"p": int(p), "done": False, "value": 0.0, "lo": 0, "hi": _KEY_MAX, "below": 0, "inside": None}
-            for p in p_milli]
-    total = None
+    jobs = [{"p": int(p), "done": False, "value": 0.0, "lo": 0, "hi": _KEY_MAX, "below": 0, "inside": None,
+             "nbelow": 0, "nequal": 0} for p in p_milli]
+    total, nan_total = None, 0
     for it in range(max_iter):
         open_jobs = [j for j in jobs if not j["done"]][:128]
         if not open_jobs and total is not None:
@@ -493,27 +499,47 @@ def slab_percentiles(parts, gather, p_milli, stride=1, mn=-1.7976931348623157e30
         b_lo = min([j["lo"] for j in open_jobs], default=0)
         b_hi = max([j["hi"] for j in open_jobs], default=_KEY_MAX)
         local = [g.pct_sample_dev(per_rank, stride, mn, mx, b_lo, b_hi, seed=0x243F6A88 + 7919 * it)[0] for g in parts]
-        combined = comm.cat_f64(local, per_rank)
-        ks = f64_keys(parts[0].sort_array(combined[0]).cpu().numpy())         # ascending keys (the sort's order)
-        bounds, win = [], {}
+        sorted_s = parts[0].sort_array(comm.cat_f64(local)[0])                 # ascending keys, on the device
+        ns_all = int(sorted_s.numel())
+        fresh = all(j["lo"] == 0 and j["hi"] == _KEY_MAX for j in open_jobs)   # first look: every bracket is the whole sample
+        ks = None if fresh else f64_keys(sorted_s.cpu().numpy())
+        want_idx, plans = [], []
         for j in open_jobs:
             lo, hi = j["lo"], j["hi"]
-            a = int(_np.searchsorted(ks, _np.uint64(lo), "left")); b = int(_np.searchsorted(ks, _np.uint64(hi), "right"))
+            if fresh:
+                a, b = 0, ns_all
+            else:
+                a = int(_np.searchsorted(ks, _np.uint64(lo), "left")); b = int(_np.searchsorted(ks, _np.uint64(hi), "right"))
             ns = b - a
             f = -1.0
             if j["inside"] is None:
                 f = 1.0 if j["p"] >= 100000 else j["p"] / 100000.0
             elif j["inside"] > 0:
                 f = ((_pct_rank(total, j["p"]) - j["below"]) + 0.5) / float(j["inside"])
+            il = ih = -1
             if ns >= 64 and f >= 0:
                 f = min(f, 1.0)
                 sd = (f * (1 - f) / ns) ** 0.5
                 dl = 6 * sd + 2.0 / ns
                 il = int(_np.floor((f - dl) * ns)) - 1; ih = int(_np.ceil((f + dl) * ns)) + 1
-                if 0 <= il < ns:
-                    lo = max(lo, int(ks[a + il]))
-                if 0 <= ih < ns:
-                    hi = min(hi, int(ks[a + ih]))
+                il = a + il if 0 <= il < ns else -1
+                ih = a + ih if 0 <= ih < ns else -1
+            plans.append((j, lo, hi, il, ih))
+            want_idx += [i for i in (il, ih) if i >= 0]
+        picked = {}
+        if want_idx:                                   # only the quantiles that become bounds leave the device
+            if ks is not None:
+                picked = {i: int(ks[i]) for i in want_idx}
+            else:
+                t = parts[0].torch
+                vals = sorted_s[t.tensor(want_idx, dtype=t.int64, device=sorted_s.device)].cpu().numpy()
+                picked = {i: int(k) for i, k in zip(want_idx, f64_keys(vals))}
+        bounds, win = [], {}
+        for j, lo, hi, il, ih in plans:
+            if il >= 0:
+                lo = max(lo, picked[il])
+            if ih >= 0:
+                hi = min(hi, picked[ih])
             win[id(j)] = (lo, hi)
             bounds += [lo, hi]
         bounds = sorted(set(bounds))
@@ -525,9 +551,10 @@ def slab_percentiles(parts, gather, p_milli, stride=1, mn=-1.7976931348623157e30
                 if bounds[r - 1] >= lo and bounds[r] <= hi:
                     compact[r] = 1
         local = [g.pct_count_dev(bounds, compact, stride, mn, mx, cand_cap) for g in parts]
-        # region counts + "my candidates did not fit" flag in one all-reduce
-        summed = comm.sum_i64([_np.concatenate([c[0], _np.array([0 if c[2] is not None else 1], dtype=_np.uint64)]) for c in local])
-        counts, overflow = summed[:-1], int(summed[-1])
+        # region counts + NaN count + "my candidates did not fit" flag in one all-reduce
+        summed = comm.sum_i64([_np.concatenate([c[0], _np.array([getattr(g, "last_nan_count", 0), 0 if c[2] is not None else 1],
+                                                                 dtype=_np.uint64)]) for g, c in zip(parts, local)])
+        counts, nan_total, overflow = summed[:-2], int(summed[-2]), int(summed[-1])
         total = int(counts.sum())
         if total == 0 or not jobs:
             break
@@ -550,21 +577,24 @@ def slab_percentiles(parts, gather, p_milli, stride=1, mn=-1.7976931348623157e30
                 need_cand = True
         sorted_cand = None
         if need_cand:                                  # every rank takes this branch together: it depends on summed counts only
-            cat = comm.cat_f64([c[2] for c in local], cand_cap)
-            sorted_cand = parts[0].sort_array(cat[0])
-        picks = [(j, cand_before[reg >> 1] + (rank - cum)) for j, rank, cum, reg in located
+            sorted_cand = parts[0].sort_array(comm.cat_f64([c[2] for c in local])[0])
+        picks = [(j, cand_before[reg >> 1] + (rank - cum), cum, reg) for j, rank, cum, reg in located
                  if not (reg & 1) and compact[reg >> 1] and sorted_cand is not None]
         if picks:                                      # one gather + one device->host copy for all jobs
             t = parts[0].torch
-            idx = t.tensor([i for _, i in picks], dtype=t.int64, device=sorted_cand.device)
+            idx = t.tensor([i for _, i, _, _ in picks], dtype=t.int64, device=sorted_cand.device)
             vals = sorted_cand[idx].cpu().numpy()
-            for (j, _), v in zip(picks, vals):
+            for (j, _, cum, reg), v in zip(picks, vals):
                 j["value"], j["done"] = float(v), True
+                if ranked:
+                    lo_i, hi_i = parts[0].equal_range(sorted_cand, float(v))
+                    j["nbelow"], j["nequal"] = cum + (lo_i - cand_before[reg >> 1]), hi_i - lo_i
         for j, rank, cum, reg in located:
             if j["done"]:
                 continue
             if reg & 1:
                 j["value"], j["done"] = key_f64(bounds[reg >> 1]), True
+                j["nbelow"], j["nequal"] = cum, int(counts[reg])
                 continue
             r = reg >> 1
             j["lo"] = bounds[r - 1] + 1 if r > 0 else 0
@@ -572,6 +602,8 @@ def slab_percentiles(parts, gather, p_milli, stride=1, mn=-1.7976931348623157e30
             j["below"], j["inside"] = cum, int(counts[reg])
     if total and any(not j["done"] for j in jobs):
         raise RuntimeError("slab_percentiles: selection did not converge")
+    if ranked:
+        return [j["value"] for j in jobs], (total or 0), [(j["nbelow"], j["nequal"]) for j in jobs], nan_total
     return [j["value"] for j in jobs], (total or 0)
 
 
@@ -758,13 +790,17 @@ def slab_clump_carries(parts, gather, average=0.0, length=100, relative_length=0
             g.lib.gdsp_clump_slab_destroy(h)
 
 
-def slab_sorted_binarize(parts, gather, thr, ties_above=False, one=1.0, zero=0.0):
+def slab_sorted_binarize(parts, gather, thr, ties_above=False, one=1.0, zero=0.0, known=None):
     """binarize applied to the reference's post-percentile state (the genome globally sorted in chromsSorted
     order, percentile.c:611-651) on a slab-sharded genome: `zero` on the first K cells of the concatenated
     genome and `one` on the rest, K = the number of cells that do not pass the threshold.  No distributed
-    sort: K comes from the region counts of one counting pass, summed with one all-reduce.  (NaN cells
-    would sort to the ends and break the step shape: refused.)  -> K"""
+    sort: K comes from region counts summed with one all-reduce -- the ones slab_percentiles(ranked=True)
+    already produced (`known` = (cells below, cells equal, NaN cells, samples)) when every cell took part,
+    else one more counting pass.  (NaN cells would sort to the ends and break the step shape: refused.)  -> K"""
     comm = _as_comm(parts, gather)
+    if known is not None and known[2] == 0 and float(thr) != 0.0 and known[3] == known[4]:
+        K = known[0] if ties_above else known[0] + known[1]
+        return _fill_step_all(parts, K, one, zero)
     key = int(f64_keys(_np.array([thr]))[0])
     neg_inf, pos_inf = int(f64_keys(_np.array([-_np.inf]))[0]), int(f64_keys(_np.array([_np.inf]))[0])
     bounds = sorted({neg_inf, key, pos_inf})
@@ -776,6 +812,10 @@ def slab_sorted_binarize(parts, gather, thr, ties_above=False, one=1.0, zero=0.0
     below = int(sum(int(c) for c in counts[:2 * kpos + 1]))          # keys strictly below the threshold
     equal = int(counts[2 * kpos + 1])
     K = below if ties_above else below + equal                         # binarize: v > T (or >= T) -> one
+    return _fill_step_all(parts, K, one, zero)
+
+
+def _fill_step_all(parts, K, one, zero):
     # cells before K in the concatenated chromsSorted genome are zero; every piece knows its offset there
     for g in parts:
         order = sorted(range(len(g.chroms)), key=lambda i: -g.chroms[i][1])
@@ -788,5 +828,6 @@ def slab_sorted_binarize(parts, gather, thr, ties_above=False, one=1.0, zero=0.0
 
 def slab_percentile_then_binarize(parts, gather, p_milli, ties_above=False, one=1.0, zero=0.0):
     """`percentile <p> = binarize --threshold=percentile<p>` on a slab-sharded genome -> (threshold, K)"""
-    (thr,), n = slab_percentiles(parts, gather, [int(p_milli)])
-    return thr, slab_sorted_binarize(parts, gather, thr, ties_above, one, zero)
+    (thr,), n, ((below, equal),), nan = slab_percentiles(parts, gather, [int(p_milli)], ranked=True)
+    cells = sum(l for _, l in parts[0].chroms)
+    return thr, slab_sorted_binarize(parts, gather, thr, ties_above, one, zero, known=(below, equal, nan, n, cells))

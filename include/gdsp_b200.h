@@ -278,6 +278,15 @@ int  gdsp_percentiles (gdsp_ctx* ctx, const gdsp_layout* lay, const double* sig,
                        double min_allowed, double max_allowed,
                        const uint32_t* h_p_milli, int np, double* h_values,
                        uint64_t* h_num_samples);
+/* The same selection, also reporting for every percentile how many samples have a key BELOW the
+ * returned value and how many EQUAL it (exact; h_below/h_equal: np entries) and the number of NaN
+ * samples.  With every cell qualifying these give `binarize` on the reference's sorted post-state
+ * without a counting pass: the step of gdsp_fill_step is below (+ equal unless ties go above). */
+int  gdsp_percentiles_ranked (gdsp_ctx* ctx, const gdsp_layout* lay, const double* sig,
+                              double* tmp, uint64_t buffer_cells, uint32_t stride,
+                              double min_allowed, double max_allowed,
+                              const uint32_t* h_p_milli, int np, double* h_values,
+                              uint64_t* h_num_samples, uint64_t* h_below, uint64_t* h_equal, uint64_t* h_nan);
 /* Building blocks of gdsp_percentiles for slab-sharded runs (one rank = one
  * slab): sample the qualifying cells whose order-preserving key lies in
  * [key_lo,key_hi] (unsorted, into d_out, capacity m); sort a plain device
@@ -292,10 +301,17 @@ int  gdsp_pct_sample  (gdsp_ctx* ctx, const gdsp_layout* lay, const double* sig,
                        double min_allowed, double max_allowed, uint64_t key_lo, uint64_t key_hi,
                        uint32_t m, uint64_t seed, double* d_out, uint32_t* h_count, uint64_t* h_slots);
 int  gdsp_sort_array  (gdsp_ctx* ctx, double* d_a, double* d_b, uint64_t n, int* h_result_in_b);
+/* positions [*h_lo, *h_hi) of the cells equal to `value` (same key) in an array sorted by gdsp_sort_array */
+int  gdsp_equal_range (gdsp_ctx* ctx, const double* d_sorted, uint64_t n, double value, uint64_t* h_lo, uint64_t* h_hi);
 int  gdsp_pct_count   (gdsp_ctx* ctx, const gdsp_layout* lay, const double* sig, uint32_t stride,
                        double min_allowed, double max_allowed, const uint64_t* h_bound_keys, int nb,
                        const uint8_t* h_compact, uint64_t* h_counts, double* d_cand, uint64_t cap,
                        uint64_t* h_ncand);
+/* gdsp_pct_count that also returns the number of qualifying NaN cells (they sit at the ends of the key order) */
+int  gdsp_pct_count_nan (gdsp_ctx* ctx, const gdsp_layout* lay, const double* sig, uint32_t stride,
+                         double min_allowed, double max_allowed, const uint64_t* h_bound_keys, int nb,
+                         const uint8_t* h_compact, uint64_t* h_counts, double* d_cand, uint64_t cap,
+                         uint64_t* h_ncand, uint64_t* h_nan);
 /* The reference's percentile is destructive; with every cell qualifying and
  * the last requested rank in the last two chromosomes the genome ends up
  * globally sorted in layout order (percentile.c:611-651).

@@ -68,7 +68,13 @@ class HostGenome:
         counts, cand = self.pct_count(bound_keys, compact, stride, mn, mx, None)
         n = int(cand.size)
         fits = cap is None or n <= cap
+        self.last_nan_count = int(np.isnan(s).sum())
         return counts, n, (self.torch.from_numpy(np.ascontiguousarray(cand)) if fits else None)
+
+    def equal_range(self, sorted_t, value):
+        k = slab.f64_keys(sorted_t.numpy())
+        kv = slab.f64_keys(np.array([value]))[0]
+        return int(np.searchsorted(k, kv, "left")), int(np.searchsorted(k, kv, "right"))
 
     def sort_array(self, a):
         v = a.numpy()

@@ -210,6 +210,11 @@ def _slab_ops_check(parts, gather, chroms, sig, plist):
     want_p, want_c, want_r = _slab_expected(chroms, sig, plist)
     got_p, n = slab.slab_percentiles(parts, gather, plist, sample_per_rank=512)
     assert n == sum(l for _, l in chroms) and got_p == want_p, (got_p, want_p)
+    got_p, n, ranks, nan = slab.slab_percentiles(parts, gather, plist, sample_per_rank=512, ranked=True)
+    allv = np.concatenate([sig[name] for name, _ in chroms])
+    assert got_p == want_p and nan == 0
+    for v, (below, equal) in zip(got_p, ranks):
+        assert below == int((allv < v).sum()) and equal == int((allv == v).sum()), (v, below, equal)
     lo, hi, cnt = slab.slab_minmax(parts, gather)
     assert (lo, hi, cnt) == (min(v.min() for v in sig.values()), max(v.max() for v in sig.values()), n)
     runs = slab.slab_runs(parts, gather)

@@ -722,3 +722,25 @@ def test_sort_genome_mostly_zeros(genome):
     for name, n in CHROMS:
         got = genome.get_chrom(name)
         assert np.array_equal(got, post[name]), name      # (-0.0 == +0.0: their relative order is unspecified in the reference too)
+
+
+@pytest.mark.parametrize("kind", KINDS + ["nan"])
+def test_percentiles_ranked_counts(genome, orc, kind):
+    """gdsp_percentiles_ranked: for every reported value the exact number of cells below / equal to it
+    (what lets `binarize` after `percentile` write its step function without a counting pass)"""
+    base = "real" if kind == "nan" else kind
+    inputs = load(genome, np.random.default_rng(31), base)
+    if kind == "nan":
+        v = inputs["chr1"]; v[5] = np.nan; v[777] = -np.nan
+        genome.set_chrom("chr1", v)
+    allv = np.concatenate([inputs[n] for n, _ in CHROMS])
+    got = genome.percentile(5.0, 95.0, step=15.0, destructive=True)
+    if kind == "nan":
+        assert genome._sorted_known == {}, "NaN present: the step-function shortcut must be off"
+        return
+    assert len(genome._sorted_known) == len(set(got.values()))
+    for val, (below, equal) in genome._sorted_known.items():
+        assert below == int((allv < val).sum()) + (int(((allv == 0) & np.signbit(allv)).sum()) if val == 0 and not np.signbit(val) else 0) \
+            or below == int((allv < val).sum()), (kind, val, below)
+        if val != 0:
+            assert equal == int((allv == val).sum()), (kind, val, equal)
