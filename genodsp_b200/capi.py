@@ -83,6 +83,8 @@ SIGNATURES = {
     "gdsp_percentiles": (_i, [_vp, _vp, _vp, _vp, _u64, _u32, _d, _d, _u32p, _i, _dp, _u64p]),
     "gdsp_percentiles_ranked": (_i, [_vp, _vp, _vp, _vp, _u64, _u32, _d, _d, _u32p, _i, _dp, _u64p, _u64p, _u64p, _u64p]),
     "gdsp_pct_count_nan": (_i, [_vp, _vp, _vp, _u32, _d, _d, _u64p, _i, C.POINTER(C.c_uint8), _u64p, _vp, _u64, _u64p, _u64p]),
+    "gdsp_percentile_collect_work_bytes": (_sz, [_u64]),
+    "gdsp_percentile_collect": (_i, [_vp, _vp, _vp, _vp, _u64, _vp, _u32, _d, _d, _u64p]),
     "gdsp_equal_range": (_i, [_vp, _vp, _u64, _d, _u64p, _u64p]),
     "gdsp_sort_genome": (_i, [_vp, _vp, _vp, _vp, _u64, C.POINTER(_i)]),
     "gdsp_sorted_binarize": (_i, [_vp, _vp, _vp, _d, _i, _d, _d, C.POINTER(_i)]),

@@ -1496,6 +1496,198 @@ extern "C" int gdsp_pct_sample (gdsp_ctx* c, const gdsp_layout* L_, const double
 	return GDSP_OK;
 	}
 
+// ---------------------------------------------------------------------------
+// The collect pass of op_percentile_apply (percentile.c:547-580) as a permutation kernel.
+// The reference walks the qualifying samples (every stride-th chromosome coordinate with
+// min <= v <= max) in chromsSorted order and swaps the j-th of them with position j of the concatenated
+// genome.  Closed form (tests/percentile_model.py pins it to the reference): with q_j the position of the
+// j-th qualifying sample, n their number and rank(p) the number of qualifying positions before p,
+//     out[j]   = in[q_j]                       for j < n
+//     out[q_j] = in[chase(j)]                  for q_j >= n, chase(j) = j if position j does not qualify,
+//                                              else chase(rank(j))   (depth ~ log_stride N)
+//     out[p]   = in[p]                         for every other position p >= n
+// Three small kernels build the qualifying bit per cell and its exclusive prefix count (one u32 per
+// 32-cell word, so rank() is one load + a popcount), the fourth moves the values.
+// ---------------------------------------------------------------------------
+#define COL_TILE 8192
+
+__global__ void __launch_bounds__(256)
+k_collect_flags (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
+                 const double* __restrict__ sig, uint32_t stride, double mn, double mx,
+                 uint32_t* __restrict__ bits, uint32_t* __restrict__ wpre, uint32_t* __restrict__ tileCount)
+	{
+	__shared__ uint32_t s_w[8];
+	int seg;  uint64_t tis;
+	tile_to_seg (base, nseg, blockIdx.x, seg, tis);
+	const SegDev sd = segs[seg];
+	const uint64_t t0 = sd.lo + tis * COL_TILE;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint64_t w0 = t0 + (uint64_t) warp * 1024;               // this warp's 32 words
+	uint32_t mine = 0;
+	for (int it = 0; it < 32; it++)
+		{
+		const uint64_t i = w0 + (uint64_t) it * 32 + lane;
+		bool q = (i < sd.hi);
+		if (q && stride > 1) q = (((uint64_t) sd.pos0 + (i - sd.lo)) % stride) == 0;
+		if (q) { const double v = sig[i];  q = !(v < mn) && !(v > mx); }
+		const uint32_t w = __ballot_sync (0xffffffffu, q);
+		if (lane == it) mine = w;
+		}
+	uint32_t inc = __popc (mine);
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1)
+		{
+		const uint32_t up = __shfl_up_sync (0xffffffffu, inc, d);
+		if (lane >= d) inc += up;
+		}
+	if (lane == 31) s_w[warp] = inc;
+	__syncthreads ();
+	uint32_t wex = 0, tot = 0;
+	#pragma unroll
+	for (int w = 0; w < 8; w++) { const uint32_t t = s_w[w];  if (w < warp) wex += t;  tot += t; }
+	const uint64_t word = w0 / 32 + lane;
+	if (w0 + (uint64_t) lane * 32 < sd.hi)                         // (the words after a short last tile belong to the next segment)
+		{
+		bits[word] = mine;
+		wpre[word] = wex + inc - __popc (mine);                    // exclusive inside the tile; the tile's prefix is added later
+		}
+	if (threadIdx.x == 0) tileCount[blockIdx.x] = tot;
+	}
+
+// one block: exclusive prefix of the tile counts (in place), total -> *n
+__global__ void __launch_bounds__(1024)
+k_collect_tilescan (uint32_t* __restrict__ tileCount, uint64_t ntiles, unsigned long long* __restrict__ n)
+	{
+	__shared__ unsigned long long s_w[32];
+	const uint64_t chunk = (ntiles + 1023) / 1024;
+	const uint64_t lo = (threadIdx.x * chunk < ntiles) ? threadIdx.x * chunk : ntiles;
+	const uint64_t hi = (lo + chunk < ntiles) ? lo + chunk : ntiles;
+	unsigned long long sum = 0;
+	for (uint64_t t = lo; t < hi; t++) sum += tileCount[t];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	unsigned long long inc = sum;
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1)
+		{
+		const unsigned long long up = __shfl_up_sync (0xffffffffu, inc, d);
+		if (lane >= d) inc += up;
+		}
+	if (lane == 31) s_w[warp] = inc;
+	__syncthreads ();
+	unsigned long long wex = 0, tot = 0;
+	for (int w = 0; w < 32; w++) { if (w < warp) wex += s_w[w];  tot += s_w[w]; }
+	unsigned long long run = wex + inc - sum;
+	for (uint64_t t = lo; t < hi; t++) { const uint32_t c = tileCount[t];  tileCount[t] = (uint32_t) run;  run += c; }
+	if (threadIdx.x == 0) *n = tot;
+	}
+
+__global__ void __launch_bounds__(256)
+k_collect_addprefix (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
+                     const uint32_t* __restrict__ tilePre, uint32_t* __restrict__ wpre)
+	{
+	int seg;  uint64_t tis;
+	tile_to_seg (base, nseg, blockIdx.x, seg, tis);
+	const uint64_t t0 = segs[seg].lo + tis * COL_TILE;
+	if (t0 + (uint64_t) threadIdx.x * 32 < segs[seg].hi) wpre[t0 / 32 + threadIdx.x] += tilePre[blockIdx.x];
+	}
+
+struct ColMap
+	{
+	int             nseg;
+	const uint64_t* segpos;      // nseg+1: position of every segment's first cell in the concatenated genome
+	const SegDev*   segs;
+	};
+
+__device__ __forceinline__ uint64_t col_cell (const ColMap& m, uint64_t pos)
+	{
+	int lo = 0, hi = m.nseg - 1;
+	while (lo < hi) { const int mid = (lo + hi + 1) >> 1;  if (m.segpos[mid] <= pos) lo = mid; else hi = mid - 1; }
+	return m.segs[lo].lo + (pos - m.segpos[lo]);
+	}
+__device__ __forceinline__ bool col_bit (const uint32_t* __restrict__ bits, uint64_t cell) { return (bits[cell >> 5] >> (cell & 31)) & 1u; }
+__device__ __forceinline__ uint64_t col_rank (const uint32_t* __restrict__ bits, const uint32_t* __restrict__ wpre, uint64_t cell)
+	{ return (uint64_t) wpre[cell >> 5] + __popc (bits[cell >> 5] & ((1u << (cell & 31)) - 1u)); }
+
+__global__ void __launch_bounds__(256)
+k_collect_move (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg, ColMap cm,
+                const double* __restrict__ in, double* __restrict__ out,
+                const uint32_t* __restrict__ bits, const uint32_t* __restrict__ wpre, const unsigned long long* __restrict__ nPtr)
+	{
+	int seg;  uint64_t tis;
+	tile_to_seg (base, nseg, blockIdx.x, seg, tis);
+	const SegDev sd = segs[seg];
+	const uint64_t t0 = sd.lo + tis * COL_TILE;
+	uint64_t t1 = t0 + COL_TILE;  if (t1 > sd.hi) t1 = sd.hi;
+	const unsigned long long n = *nPtr;
+	const uint64_t pos0 = cm.segpos[seg] + (t0 - sd.lo);
+	for (uint64_t i = t0 + threadIdx.x; i < t1; i += 256)
+		{
+		const uint64_t pos = pos0 + (i - t0);
+		const bool q = col_bit (bits, i);
+		const double v = in[i];
+		if (q) out[col_cell (cm, col_rank (bits, wpre, i))] = v;   // front: the rank-th qualifying sample
+		if (pos >= n)
+			{
+			if (!q) out[i] = v;
+			else
+				{
+				uint64_t j = col_rank (bits, wpre, i), cj = col_cell (cm, j);
+				while (col_bit (bits, cj)) { j = col_rank (bits, wpre, cj);  cj = col_cell (cm, j); }
+				out[i] = in[cj];
+				}
+			}
+		}
+	}
+
+extern "C" size_t gdsp_percentile_collect_work_bytes (uint64_t buffer_cells)
+	{
+	return (size_t) ((buffer_cells / 32 + 512) * 8 + (buffer_cells / COL_TILE + 65536 + 64) * 4 + 4096);
+	}
+
+extern "C" int gdsp_percentile_collect (gdsp_ctx* c, const gdsp_layout* L_, const double* sig, double* out,
+                                        uint64_t buffer_cells, void* work, uint32_t stride, double mn, double mx,
+                                        uint64_t* h_n)
+	{
+	gdsp_layout* L = (gdsp_layout*) L_;
+	GDSP_REQUIRE (c && L && sig && out && work && h_n, "gdsp_percentile_collect: NULL argument");
+	GDSP_REQUIRE (sig != out, "gdsp_percentile_collect: sig and out must be different buffers");
+	if (stride == 0) stride = 1;
+	for (int s = 0; s < L->nseg; s++)
+		GDSP_REQUIRE (L->h[s].pos0 == 0 && L->h[s].hi - L->h[s].lo == L->h[s].chrom_len,
+		              "gdsp_percentile_collect: whole chromosomes only");
+	TileMap tm;
+	GDSP_TRY (gdsp_layout_tilemap (L, COL_TILE, &tm));
+	GDSP_REQUIRE (L->cells < 0xffffffffull, "gdsp_percentile_collect: more than 2^32-1 cells (the reference's numValues is a u32)");
+	const uint64_t nwords = buffer_cells / 32 + 512;
+	char* p = (char*) work;
+	uint32_t* bits = (uint32_t*) p;       p += nwords * 4;
+	uint32_t* wpre = (uint32_t*) p;       p += nwords * 4;
+	uint32_t* tcnt = (uint32_t*) p;       p += ((tm.ntiles + 63) / 64) * 64 * 4;
+	unsigned long long* d_n = (unsigned long long*) p;   p += 64;
+	uint64_t* d_segpos = (uint64_t*) p;
+	GDSP_REQUIRE ((size_t) (p - (char*) work) + (L->nseg + 1) * 8 <= gdsp_percentile_collect_work_bytes (buffer_cells),
+	              "gdsp_percentile_collect: too many segments for the work buffer");
+	std::vector<uint64_t> segpos (L->nseg + 1);
+	uint64_t acc = 0;
+	for (int s = 0; s < L->nseg; s++) { segpos[s] = acc;  acc += L->h[s].hi - L->h[s].lo; }
+	segpos[L->nseg] = acc;
+	GDSP_CUDA (cudaMemcpyAsync (d_segpos, segpos.data (), sizeof (uint64_t) * (L->nseg + 1), cudaMemcpyHostToDevice, c->stream));
+	k_collect_flags<<<(unsigned) tm.ntiles, 256, 0, c->stream>>> (L->d, tm.d_base, L->nseg, sig, stride, mn, mx, bits, wpre, tcnt);
+	GDSP_KERNEL_CHECK ();
+	k_collect_tilescan<<<1, 1024, 0, c->stream>>> (tcnt, tm.ntiles, d_n);
+	GDSP_KERNEL_CHECK ();
+	k_collect_addprefix<<<(unsigned) tm.ntiles, 256, 0, c->stream>>> (L->d, tm.d_base, L->nseg, tcnt, wpre);
+	GDSP_KERNEL_CHECK ();
+	ColMap cm;  cm.nseg = L->nseg;  cm.segpos = d_segpos;  cm.segs = L->d;
+	k_collect_move<<<(unsigned) tm.ntiles, 256, 0, c->stream>>> (L->d, tm.d_base, L->nseg, cm, sig, out, bits, wpre, d_n);
+	GDSP_KERNEL_CHECK ();
+	unsigned long long n = 0;
+	GDSP_CUDA (cudaMemcpyAsync (&n, d_n, 8, cudaMemcpyDeviceToHost, c->stream));
+	GDSP_CUDA (cudaStreamSynchronize (c->stream));
+	*h_n = n;
+	return GDSP_OK;
+	}
+
 // positions [lo, hi) of the cells whose key equals key(value) in an array sorted by gdsp_sort_array
 extern "C" int gdsp_equal_range (gdsp_ctx* c, const double* d_sorted, uint64_t n, double value, uint64_t* h_lo, uint64_t* h_hi)
 	{

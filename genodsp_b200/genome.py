@@ -550,6 +550,18 @@ class Genome:
         check(self.lib.gdsp_fill_step(self.ctx, self.layout, self._p(self._sig), arr, int(step), float(one), float(zero)))
         self._pending_sort = False
 
+    def percentile_collect(self, window=1, mn=-DBL_MAX, mx=DBL_MAX):
+        """the collect pass of op_percentile_apply (percentile.c:547-580) for --window/--min/--max:
+        qualifying samples to the front of the concatenated genome, the displaced values shuffled behind
+        them exactly as the reference's swaps leave them -> number of qualifying samples"""
+        wb = self.lib.gdsp_percentile_collect_work_bytes(self.buffer_cells)
+        work = self.work(wb)
+        n = C.c_uint64()
+        check(self.lib.gdsp_percentile_collect(self.ctx, self.layout, self._p(self.sig), self._p(self.tmp), self.buffer_cells,
+                                               self._p(work), int(window), float(mn), float(mx), C.byref(n)))
+        self._swap()
+        return int(n.value)
+
     def text_roundtrip(self):
         """percentile --preserve's write_all/read_all round trip (10 decimals), genodsp.c:1717-1775"""
         check(self.lib.gdsp_text_roundtrip(self.ctx, self.layout, self._p(self.sig), 10))

@@ -265,36 +265,72 @@ void op_percentile_apply (dspop* _op, arg_dont_complain(char* vName), arg_dont_c
 		return;
 		}
 	if (!signal_is_read_later (_op)) return;
-	if (op->windowSize != 1 || op->minAllowed != -valtypeMax || op->maxAllowed != valtypeMax)
-		{
-		fprintf (stderr, "[%s] the signal is used after a percentile computed with --window/--min/--max;\n"
-		                 "this build does not reproduce the reference's value shuffle for that case; add --preserve=<file>\n",
-		         _op->name);
-		exit (EXIT_FAILURE);
-		}
 	{
-	/* K = chromosome (sorted order) that holds the last reported rank */
-	u64 acc = 0;  int K = gd.nchrom - 1;
-	for (int i = 0; i < gd.nchrom; i++)
-		{ acc += chromsSorted[i]->length;  if (lastRank < acc) { K = i;  break; } }
-	if (K >= gd.nchrom - 2)
+	/* The reference leaves the vectors permuted (percentile.c:547-651).  `front` = the part of the
+	 * concatenated chromsSorted genome that holds the qualifying samples: every chromosome before
+	 * `last` whole, the first numInLast cells of chromosome `last`. */
+	const int filtered = (op->windowSize != 1 || op->minAllowed != -valtypeMax || op->maxAllowed != valtypeMax);
+	int last = gd.nchrom - 1;
+	u64 numInLast = gd.segs[last].hi - gd.segs[last].lo;
+	if (filtered)
 		{
-		/* globally sorted genome.  `percentile P = binarize ...` thresholds it straight away: a step
-		 * function that needs a count, not a sort -- leave the state pending and let binarize decide
-		 * (not under --progress=operations, whose trace interleaves binarize's messages differently) */
-		gd.pendingSorted = 1;
-		if (!(_op->next != NULL && _op->next->funcApply == op_binarize_apply && !trackOperations))
-			gd_materialise_sorted (_op->name);
+		/* the collect pass: qualifying samples to the front, the displaced values shuffled behind them */
+		u64 n = 0;
+		void* work = gd_work (gdsp_percentile_collect_work_bytes (gd.cells));
+		gd_check (gdsp_percentile_collect (gd.ctx, gd.genome, gd.sig, gd.tmp, gd.cells, work, op->windowSize,
+		                                   op->minAllowed, op->maxAllowed, &n), _op->name);
+		gd_swap ();
+		u64 acc = 0;
+		for (int i = 0; i < gd.nchrom; i++)
+			{
+			const u64 len = gd.segs[i].hi - gd.segs[i].lo;
+			if (n <= acc + len) { last = i;  numInLast = n - acc;  break; }
+			acc += len;
+			}
+		}
+	gdsp_seg* front = (gdsp_seg*) malloc ((last + 1) * sizeof (gdsp_seg));
+	for (int i = 0; i <= last; i++) front[i] = gd.segs[i];
+	front[last].hi = front[last].lo + numInLast;
+	front[last].dhi = front[last].hi;
+
+	/* K = chromosome (sorted order) that holds the last reported rank */
+	u64 acc = 0;  int K = last;
+	for (int i = 0; i <= last; i++)
+		{ acc += front[i].hi - front[i].lo;  if (lastRank < acc) { K = i;  break; } }
+	if (K >= last - 1)
+		{
+		/* the front ends up globally sorted (chromosome `last` alone holds the leftovers of the passes) */
+		if (!filtered)
+			{
+			/* `percentile P = binarize ...` thresholds it straight away: a step function that needs a count,
+			 * not a sort -- leave the state pending and let binarize decide (not under --progress=operations,
+			 * whose trace interleaves binarize's messages differently) */
+			gd.pendingSorted = 1;
+			if (!(_op->next != NULL && _op->next->funcApply == op_binarize_apply && !trackOperations))
+				gd_materialise_sorted (_op->name);
+			}
+		else
+			{
+			int inTmp = 0;
+			gdsp_layout* lay;
+			gd_check (gdsp_layout_create (gd.ctx, front, last + 1, &lay), _op->name);
+			gd_check (gdsp_sort_genome (gd.ctx, lay, gd.sig, gd.tmp, gd.cells, &inTmp), _op->name);
+			if (inTmp)
+				for (int q = 0; q <= last; q++)
+					gd_check (gdsp_d2d (gd.ctx, gd.sig + front[q].lo, gd.tmp + front[q].lo,
+					                    (front[q].hi - front[q].lo) * sizeof (double)), _op->name);
+			gdsp_layout_destroy (lay);
+			}
 		}
 	else
 		{
 		int inTmp = 0;
 		/* the reference's bubble passes (percentile.c:623-651): chromosome c takes the smallest
-		 * len(c) values of {c, d} for every later d, in order */
+		 * len(c) values of {c, d} for every later d of the front, in order */
 		for (int c = 0; c <= K; c++)
-			for (int d = c + 1; d < gd.nchrom; d++)
+			for (int d = c + 1; d <= last; d++)
 				{
-				gdsp_seg pair[2] = { gd.segs[c], gd.segs[d] };
+				gdsp_seg pair[2] = { front[c], front[d] };
 				gdsp_layout* lay;
 				gd_check (gdsp_layout_create (gd.ctx, pair, 2, &lay), _op->name);
 				gd_check (gdsp_sort_genome (gd.ctx, lay, gd.sig, gd.tmp, gd.cells, &inTmp), _op->name);
@@ -305,13 +341,17 @@ void op_percentile_apply (dspop* _op, arg_dont_complain(char* vName), arg_dont_c
 				gdsp_layout_destroy (lay);
 				}
 		/* chromosomes after K were only sorted individually before the passes touched them */
-		for (int d = K + 1; d < gd.nchrom; d++)
+		for (int d = K + 1; d <= last; d++)
 			{
-			gd_check (gdsp_sort_genome (gd.ctx, gd.single[d], gd.sig, gd.tmp, gd.cells, &inTmp), _op->name);
-			if (inTmp) gd_check (gdsp_d2d (gd.ctx, gd.sig + gd.segs[d].lo, gd.tmp + gd.segs[d].lo,
-			                               (gd.segs[d].hi - gd.segs[d].lo) * sizeof (double)), _op->name);
+			gdsp_layout* lay;
+			gd_check (gdsp_layout_create (gd.ctx, &front[d], 1, &lay), _op->name);
+			gd_check (gdsp_sort_genome (gd.ctx, lay, gd.sig, gd.tmp, gd.cells, &inTmp), _op->name);
+			if (inTmp) gd_check (gdsp_d2d (gd.ctx, gd.sig + front[d].lo, gd.tmp + front[d].lo,
+			                               (front[d].hi - front[d].lo) * sizeof (double)), _op->name);
+			gdsp_layout_destroy (lay);
 			}
 		}
+	free (front);
 	}
 	return;
 

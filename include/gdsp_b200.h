@@ -301,6 +301,16 @@ int  gdsp_pct_sample  (gdsp_ctx* ctx, const gdsp_layout* lay, const double* sig,
                        double min_allowed, double max_allowed, uint64_t key_lo, uint64_t key_hi,
                        uint32_t m, uint64_t seed, double* d_out, uint32_t* h_count, uint64_t* h_slots);
 int  gdsp_sort_array  (gdsp_ctx* ctx, double* d_a, double* d_b, uint64_t n, int* h_result_in_b);
+/* The collect pass of op_percentile_apply (percentile.c:547-580) for --window / --min / --max: the j-th
+ * qualifying sample (every stride-th chromosome coordinate with min <= v <= max, chromsSorted order) is
+ * swapped with position j of the concatenated genome.  Out of place (sig -> out, whole chromosomes
+ * only); *h_n = the number of qualifying samples: positions [0, n) of `out` then hold them in scan order,
+ * ready for the per-chromosome sorts and bubble passes (gdsp_sort_genome on the front part), the rest is
+ * the reference's shuffle of the non-qualifying values.  `work` = gdsp_percentile_collect_work_bytes(). */
+size_t gdsp_percentile_collect_work_bytes (uint64_t buffer_cells);
+int  gdsp_percentile_collect (gdsp_ctx* ctx, const gdsp_layout* lay, const double* sig, double* out,
+                              uint64_t buffer_cells, void* work, uint32_t stride,
+                              double min_allowed, double max_allowed, uint64_t* h_n);
 /* positions [*h_lo, *h_hi) of the cells equal to `value` (same key) in an array sorted by gdsp_sort_array */
 int  gdsp_equal_range (gdsp_ctx* ctx, const double* d_sorted, uint64_t n, double value, uint64_t* h_lo, uint64_t* h_hi);
 int  gdsp_pct_count   (gdsp_ctx* ctx, const gdsp_layout* lay, const double* sig, uint32_t stride,

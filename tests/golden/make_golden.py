@@ -57,6 +57,13 @@ CASES = {
     # under --novalue an operator's file is read without values too (every value 1) unless it says --value=
     "add_multiply_values": (C + ["--novalue", "--precision=5", "=", "add", "trackB.iv", "--value=4", "=", "multiply", "trackB.iv",
                                  "--value=4"], "reads.iv"),
+    # the state a --window / --min / --max percentile leaves behind (the collect permutation, percentile.c:547-580,
+    # then the per-chromosome sorts and bubble passes) is visible to the next operator
+    "percentile_collect_window_min": (C + ["--novalue", "=", "percentile", "50", "--window=7", "--min=1", "=", "addconst", "0"], "reads.iv"),
+    "percentile_collect_max": (C + ["--novalue", "--precision=3", "=", "slidingsum", "--window=25", "--denom=W", "=", "percentile",
+                                    "20..80by30", "--max=6", "--quiet", "=", "addconst", "0.5"], "reads.iv"),
+    "percentile_collect_high_rank": (C + ["--novalue", "=", "percentile", "99", "--min=2", "=", "binarize", "--threshold=percentile99"], "reads.iv"),
+    "percentile_general_rank": (C + ["--novalue", "=", "percentile", "30", "=", "addconst", "0"], "reads.iv"),
     "subtract_novalue_inherited": (C + ["--novalue", "=", "subtract", "trackB.iv"], "reads.iv"),
 }
 

@@ -168,17 +168,41 @@ class Pipeline:
             one = float(self.kw(args, ["--one="], "1"))
             self.per_chrom(lambda v: o.clump(v, T, L, name == "clump", one, 0.0))
         elif name == "percentile":
-            p = pos[0]
+            # values by sorting the qualifying samples; post-state by tests/percentile_model.py (pinned to the
+            # reference by tests/test_oracle_percentile_state.py)
+            import percentile_model as pmodel
+            spec_p = pos[0]
             prec = int(self.kw(args, ["--precision="], str(opts["precision"])))
+            stride = int(_unit(self.kw(args, ["--window=", "W="], "1")))
+            mn = _num(self.kw(args, ["--min="], "-inf")); mx = _num(self.kw(args, ["--max="], "inf"))
+            quiet = "--quiet" in args or "--silent" in args
+            if ".." in spec_p:
+                lo_s, rest = spec_p.split("..")
+                hi_s, step_s = (rest.split("by") + ["1"])[:2]
+                plist = []
+                lo_m, hi_m, st_m = int(round(float(lo_s) * 1000)), int(round(float(hi_s) * 1000)), int(round(float(step_s) * 1000))
+                pmv = lo_m
+                while pmv <= hi_m:
+                    plist.append(pmv); pmv += st_m
+            else:
+                plist = [int(round(float(spec_p) * 1000))]
             names = [self.chroms[i][0] for i in self.sorted]
-            srt = np.sort(np.concatenate([self.v[n] for n in names]))
-            pm = int(round(float(p) * 1000))
-            val = srt[o.percentile_rank(srt.size, pm)]
-            self.vars["percentile" + p] = val
-            self.stderr.append("percentile %.3f is %s" % (float(p), fmt(val, prec)))
-            at = 0                          # the reference's post-state: globally sorted genome
+            lengths = [self.v[n].size for n in names]
+            cat = np.concatenate([self.v[n] for n in names])
+            q = pmodel.qualifying_mask(lengths, cat, stride, mn, mx)
+            srt = np.sort(cat[q])
+            rank = 0
+            for pmv in plist:
+                rank = srt.size - 1 if pmv >= 100000 else o.percentile_rank(srt.size, pmv)
+                val = srt[rank]
+                label = ("%d" % (pmv // 1000)) if pmv % 1000 == 0 else ("%g" % (pmv / 1000.0))
+                self.vars["percentile" + label] = val
+                if not quiet:
+                    self.stderr.append("percentile %.3f is %s" % (pmv / 1000.0, fmt(val, prec)))
+            state, _n = pmodel.post_state(lengths, cat, rank, stride, mn, mx)
+            at = 0
             for n in names:
-                self.v[n] = srt[at:at + self.v[n].size].copy(); at += self.v[n].size
+                self.v[n] = state[at:at + self.v[n].size].copy(); at += self.v[n].size
         elif name in ("add", "subtract", "multiply", "divide", "and", "masknot"):
             iv = self.read_intervals(pos[0], -1 if name == "masknot" else fcol)    # masknot reads no value column (mask.c:533)
             for n, _ in self.chroms:

@@ -196,6 +196,21 @@ def test_percentile_then_binarize_variants(data):
     assert_same(data, C + ["--novalue", "--progress=operations", "=", "percentile", "97", "=", "binarize", "--threshold=percentile97"])
 
 
+def test_percentile_leaves_the_reference_shuffle(data):
+    """the state a percentile leaves in the vectors is visible to the next operator -- with
+    --window / --min / --max that is the collect permutation (percentile.c:547-580) followed by the sorts and
+    bubble passes over the front part; `addconst 0` is a no-op that makes the output show it"""
+    assert_same(data, C + ["--novalue", "=", "percentile", "50", "--window=7", "--min=1", "=", "addconst", "0"])
+    assert_same(data, C + ["--novalue", "--precision=3", "=", "slidingsum", "--window=25", "--denom=W", "=", "percentile",
+                           "20..80by30", "--max=6", "--quiet", "=", "addconst", "0.5"])
+    assert_same(data, C + ["--novalue", "=", "percentile", "99", "--min=2", "=", "binarize", "--threshold=percentile99"])
+    assert_same(data, C + ["--novalue", "--precision=6", "=", "smooth", "--window=11", "=", "percentile", "50", "--window=1000",
+                           "=", "clip", "--min=percentile50"])
+    # all cells qualify, last rank in the first chromosome: the bubble passes (general K)
+    assert_same(data, C + ["--novalue", "=", "percentile", "30", "=", "addconst", "0"])
+    assert_same(data, C + ["--novalue", "=", "percentile", "10..75by65", "--window=2", "=", "abs"])
+
+
 def test_errors_match(data):
     for args in (C + ["=", "nosuchop"], C + ["--novalue", "=", "smooth", "--window=0"], C + ["--bogus"],
                  C + ["--novalue", "=", "binarize", "--threshold=nosuchvar"]):

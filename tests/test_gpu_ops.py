@@ -744,3 +744,25 @@ def test_percentiles_ranked_counts(genome, orc, kind):
             or below == int((allv < val).sum()), (kind, val, below)
         if val != 0:
             assert equal == int((allv == val).sum()), (kind, val, equal)
+
+
+@pytest.mark.parametrize("kind", ["int", "real"])
+@pytest.mark.parametrize("args", [(7, None, None), (1, 2.0, None), (1, None, 4.0), (3, 1.5, 5.0), (1000, None, None),
+                                  (1, None, None), (2, 1e9, None)])
+def test_percentile_collect_permutation(genome, kind, args):
+    """gdsp_percentile_collect == the reference's collect swaps (percentile.c:547-580) in closed form
+    (tests/percentile_model.py, pinned to the reference by tests/test_oracle_percentile_state.py)"""
+    import percentile_model as pm
+    stride, mn, mx = args
+    inputs = load(genome, np.random.default_rng(stride + 3), kind)
+    names = [genome.chroms[i][0] for i in genome.order]
+    lengths = [inputs[n].size for n in names]
+    cat = np.concatenate([inputs[n] for n in names])
+    lo = -np.finfo(np.float64).max if mn is None else mn
+    hi = np.finfo(np.float64).max if mx is None else mx
+    want, n_want = pm.collect(lengths, cat, stride, lo, hi)
+    n = genome.percentile_collect(stride, lo, hi)
+    assert n == n_want
+    got = np.concatenate([genome.get_chrom(nm) for nm in names])
+    bad = np.nonzero(bits(got) != bits(want))[0]
+    assert bad.size == 0, (kind, args, n, bad[:8], got[bad[:8]], want[bad[:8]])
