@@ -890,5 +890,6 @@ extern "C" int gdsp_cumulative_sum (gdsp_ctx* c, const gdsp_layout* L_, const do
 	gdsp_layout* L = (gdsp_layout*) L_;
 	GDSP_REQUIRE (c && L && in && out, "gdsp_cumulative_sum: NULL argument");
 	GDSP_REQUIRE_ALIGNED (in, "gdsp_cumulative_sum");  GDSP_REQUIRE_ALIGNED (out, "gdsp_cumulative_sum");
+	if (c->exact_order) return gdsp_cumulative_sum_exact (c, L, in, out);
 	return launch_scan (c, L, in, out, 0);
 	}

@@ -1310,7 +1310,7 @@ extern "C" int gdsp_clump (gdsp_ctx* c, const gdsp_layout* L_, double* sig, uint
 			}
 	const size_t fastBytes = (size_t) tm.ntiles * (CLF_GROUPS * 16 + 2 * CLF_WORDS * 4) + 2 * (((size_t) tm.ntiles + 255) / 256) * 256
 	                       + (size_t) L->nseg * 4;
-	if (maxLmin <= CLF_MAX_HALO && fastBytes <= gdsp_clump_work_bytes (buffer_cells) && !getenv ("GDSP_CLUMP_STORED"))
+	if (maxLmin <= CLF_MAX_HALO && fastBytes <= gdsp_clump_work_bytes (buffer_cells) && !getenv ("GDSP_CLUMP_STORED") && !c->exact_order)
 		{
 		ClumpFast wf;
 		char* p = (char*) work;
@@ -1362,12 +1362,20 @@ extern "C" int gdsp_clump (gdsp_ctx* c, const gdsp_layout* L_, double* sig, uint
 	k_fill_int<<<(L->nseg + 255) / 256, 256, 0, c->stream>>> (wk.segAllNeg, L->nseg, 1);
 	GDSP_KERNEL_CHECK ();
 
-	// pass A: sum scan (ws1) + min scan (ws2); the ticket of ws1 drives the tile order
-	GDSP_CUDA (cudaMemsetAsync (ws1, 0, scan_status_clear_bytes<double> (tm.ntiles), c->stream));
-	GDSP_CUDA (cudaMemsetAsync (ws2, 0, scan_status_clear_bytes<double> (tm.ntiles), c->stream));
-	k_clump_a<<<(unsigned) tm.ntiles, CL_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, sig, average, above ? 1 : 0, wk,
-	        scan_status_carve<double> (ws1, tm.ntiles), scan_status_carve<double> (ws2, tm.ntiles));
-	GDSP_KERNEL_CHECK ();
+	if (c->exact_order)
+		{
+		// the prefix sums in the reference's own order (clump.c:600): one warp per chromosome (gdsp_exact.cu)
+		GDSP_TRY (gdsp_clump_prefix_exact (c, L, sig, average, above ? 1 : 0, wk.P, wk.M, wk.segAllNeg));
+		}
+	else
+		{
+		// pass A: sum scan (ws1) + min scan (ws2); the ticket of ws1 drives the tile order
+		GDSP_CUDA (cudaMemsetAsync (ws1, 0, scan_status_clear_bytes<double> (tm.ntiles), c->stream));
+		GDSP_CUDA (cudaMemsetAsync (ws2, 0, scan_status_clear_bytes<double> (tm.ntiles), c->stream));
+		k_clump_a<<<(unsigned) tm.ntiles, CL_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, sig, average, above ? 1 : 0, wk,
+		        scan_status_carve<double> (ws1, tm.ntiles), scan_status_carve<double> (ws2, tm.ntiles));
+		GDSP_KERNEL_CHECK ();
+		}
 
 	// pass B: suffix max (ws1) + backward segmented OR (ws2)
 	GDSP_CUDA (cudaMemsetAsync (ws1, 0, scan_status_clear_bytes<double> (tm.ntiles), c->stream));

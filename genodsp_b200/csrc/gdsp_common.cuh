@@ -105,7 +105,14 @@ struct gdsp_ctx
 	uint32_t     taps_n;
 	void*        host_small;          // page-locked scratch for small device->host results (percentile samples)
 	size_t       host_small_bytes;
+	int          exact_order;         // gdsp_ctx_set_exact_order: sequential-order slidingsum / cumulativesum / clump
 	};
+
+// gdsp_exact.cu
+int gdsp_cumulative_sum_exact (gdsp_ctx* c, gdsp_layout* L, const double* in, double* out);
+int gdsp_sliding_sum_exact (gdsp_ctx* c, gdsp_layout* L, const double* in, double* out, uint32_t W, double denom);
+int gdsp_clump_prefix_exact (gdsp_ctx* c, gdsp_layout* L, const double* sig, double T, int above,
+                             double* P, double* M, int* segAllNeg);
 
 // grow-only device scratch (slot 0..GDSP_NUM_WS-1); contents undefined
 int gdsp_ws (gdsp_ctx* ctx, int slot, size_t bytes, void** out);

@@ -482,6 +482,7 @@ extern "C" int gdsp_sliding_sum (gdsp_ctx* c, const gdsp_layout* L_, const doubl
 	GDSP_REQUIRE (c && L && in && out, "gdsp_sliding_sum: NULL argument");
 	GDSP_REQUIRE (in != out, "gdsp_sliding_sum: in and out must be different buffers");
 	GDSP_REQUIRE (W >= 1, "gdsp_sliding_sum: window must be positive");
+	if (c->exact_order) return gdsp_sliding_sum_exact (c, L, in, out, W, denom);
 	uint32_t count = SS_TILE + W - 1;
 	size_t smem = (size_t) count * sizeof (double);
 	GDSP_REQUIRE (smem + 1024 <= c->smem_optin,

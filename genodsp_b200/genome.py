@@ -150,6 +150,21 @@ class Genome:
             self._work = self.torch.empty(int(nbytes), dtype=self.torch.uint8, device=self.device)
         return self._work
 
+    def exact_order(self, on=True):
+        """context manager: slidingsum / cumulativesum / clump in the reference's sequential summation order
+        (gdsp_ctx_set_exact_order) -- bit-identical on general reals, slow"""
+        g = self
+
+        class _Mode:
+            def __enter__(self_inner):
+                check(g.lib.gdsp_ctx_set_exact_order(g.ctx, 1 if on else 0))
+                return g
+
+            def __exit__(self_inner, *exc):
+                check(g.lib.gdsp_ctx_set_exact_order(g.ctx, 0))
+                return False
+        return _Mode()
+
     def sync(self):
         check(self.lib.gdsp_sync(self.ctx))
 

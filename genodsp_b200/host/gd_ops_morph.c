@@ -159,6 +159,7 @@ typedef struct dspop_clump
 	double  relativeLength;
 	valtype oneVal, zeroVal;
 	int     debug, debugDetail, progress;
+	int     exactOrder;          /* --exact-order (not in the reference): prefix sums in the reference's sequential order */
 	} dspop_clump;
 
 static void rel_fail (char* name, char* arg, const char* why)
@@ -239,6 +240,7 @@ static dspop* clump_parse (char* name, int argc, char** argv)
 		else if (strcmp (arg, "--debug") == 0)            op->debug = true;
 		else if (strcmp (arg, "--debug=detail") == 0)     op->debugDetail = true;
 		else if (strcmp_prefix (arg, "--progress=") == 0) op->progress = string_to_unitized_int (argVal, true);
+		else if (strcmp (arg, "--exact-order") == 0)      op->exactOrder = true;
 		else if (strcmp_prefix (arg, "--") == 0) bad_arg (name, arg);
 		else if (!haveAverage) { op->average = string_to_valtype (arg);  haveAverage = true; }
 		else bad_arg (name, arg);
@@ -260,6 +262,9 @@ static void clump_usage (char* name, FILE* f, char* indent, int above)
 	fprintf (f, "%s  --length=<length>        (L=) minimum interval length (default 100); also\n", indent);
 	fprintf (f, "%s                           CL, CL*<f>, <f>*CL, CL/<d> (relative to the chromosome\n", indent);
 	fprintf (f, "%s                           length) or max(<length>,<relative>)\n", indent);
+	fprintf (f, "%s  --exact-order            (this implementation only) prefix sums in the sequential order\n", indent);
+	fprintf (f, "%s                           of the original program: bit-identical on any real-valued\n", indent);
+	fprintf (f, "%s                           signal, much slower\n", indent);
 	fprintf (f, "%s  --one=<value>            (O=) value for positions in clumps (default 1.0)\n", indent);
 	fprintf (f, "%s  --zero=<value>           (Z=) value for other positions (default 0.0)\n", indent);
 	}
@@ -284,8 +289,10 @@ static void clump_apply (dspop* _op, valtype* v, int above)
 	dspop_clump* op = (dspop_clump*) _op;
 	clump_resolve (_op);
 	void* work = gd_work (gdsp_clump_work_bytes (gd.cells));
+	if (op->exactOrder) gd_check (gdsp_ctx_set_exact_order (gd.ctx, 1), _op->name);
 	gd_check (gdsp_clump (gd.ctx, gd_layout_for (v, NULL), gd.sig, gd.cells, work, op->average, op->minLength,
 	                      op->relativeLength, above, op->oneVal, op->zeroVal), _op->name);
+	if (op->exactOrder) gd_check (gdsp_ctx_set_exact_order (gd.ctx, 0), _op->name);
 	}
 
 static void clump_free (dspop* _op)

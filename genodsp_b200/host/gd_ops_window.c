@@ -16,6 +16,7 @@ typedef struct dspop_sum
 	valtype denominator;
 	valtype zeroVal;
 	int     windowIsChromosome, useActualDenom, denomIsWindowSize;
+	int     exactOrder;          /* --exact-order (not in the reference): the running sum in the reference's sequential order */
 	} dspop_sum;
 
 static int arg_is_denom (char* arg)
@@ -109,6 +110,9 @@ void op_sliding_sum_usage (char* name, FILE* f, char* indent)
 	fprintf (f, "%susage: %s [options]\n", indent, name);
 	fprintf (f, "%s  --window=<length>        (W=) size of window\n", indent);
 	fprintf (f, "%s  --denom=<value>          (D=) divide each sum by this (default: none)\n", indent);
+	fprintf (f, "%s  --exact-order            (this implementation only) add and subtract in the\n", indent);
+	fprintf (f, "%s                           sequential order of the original program: bit-identical\n", indent);
+	fprintf (f, "%s                           on any real-valued signal, much slower\n", indent);
 	}
 
 dspop* op_sliding_sum_parse (char* name, int argc, char** argv)
@@ -132,6 +136,7 @@ dspop* op_sliding_sum_parse (char* name, int argc, char** argv)
 				if (op->denominator == 0) chastise ("[%s] denominator can't be zero (\"%s\")\n", name, arg);
 				}
 			}
+		else if (strcmp (arg, "--exact-order") == 0) op->exactOrder = true;
 		else bad_arg (name, arg);
 		}
 	if (op->windowSize < 3)
@@ -149,7 +154,9 @@ void op_sliding_sum_apply (dspop* _op, arg_dont_complain(char* vName), arg_dont_
 	dspop_sum* op = (dspop_sum*) _op;
 	int ix;
 	const gdsp_layout* lay = gd_layout_for (v, &ix);
+	if (op->exactOrder) gd_check (gdsp_ctx_set_exact_order (gd.ctx, 1), _op->name);
 	gd_check (gdsp_sliding_sum (gd.ctx, lay, gd.sig, gd.tmp, op->windowSize, op->denominator), _op->name);
+	if (op->exactOrder) gd_check (gdsp_ctx_set_exact_order (gd.ctx, 0), _op->name);
 	gd_commit_tmp (v, ix);
 	}
 
@@ -236,18 +243,29 @@ void op_cumulative_sum_usage (char* name, FILE* f, char* indent)
 	fprintf (f, "%susage: %s\n", indent, name);
 	}
 
+typedef struct dspop_cumsum { dspop common;  int exactOrder; } dspop_cumsum;
+
 dspop* op_cumulative_sum_parse (char* name, int argc, char** argv)
 	{
-	dspop* op = (dspop*) op_alloc (name, sizeof (dspop));
-	op->atRandom = false;
-	if (argc > 0) bad_arg (name, argv[0]);
-	return op;
+	dspop_cumsum* op = (dspop_cumsum*) op_alloc (name, sizeof (dspop_cumsum));
+	op->common.atRandom = false;
+	for (; argc > 0; argv++, argc--)
+		{
+		if (strcmp (argv[0], "--exact-order") == 0) op->exactOrder = true;   /* not in the reference: sequential summation order */
+		else bad_arg (name, argv[0]);
+		}
+	return (dspop*) op;
 	}
 
 void op_cumulative_sum_free (dspop* op) { free (op); }
 
-void op_cumulative_sum_apply (dspop* op, arg_dont_complain(char* vName), arg_dont_complain(u32 vLen), valtype* v)
-	{ gd_check (gdsp_cumulative_sum (gd.ctx, gd_layout_for (v, NULL), gd.sig, gd.sig), op->name); }
+void op_cumulative_sum_apply (dspop* _op, arg_dont_complain(char* vName), arg_dont_complain(u32 vLen), valtype* v)
+	{
+	dspop_cumsum* op = (dspop_cumsum*) _op;
+	if (op->exactOrder) gd_check (gdsp_ctx_set_exact_order (gd.ctx, 1), _op->name);
+	gd_check (gdsp_cumulative_sum (gd.ctx, gd_layout_for (v, NULL), gd.sig, gd.sig), _op->name);
+	if (op->exactOrder) gd_check (gdsp_ctx_set_exact_order (gd.ctx, 0), _op->name);
+	}
 
 /* ========================================================= localmin / localmax */
 

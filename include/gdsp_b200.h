@@ -69,6 +69,13 @@ int  gdsp_ctx_create   (int device, void* stream, gdsp_ctx** out);
 void gdsp_ctx_destroy  (gdsp_ctx* ctx);
 int  gdsp_ctx_set_stream (gdsp_ctx* ctx, void* stream);
 int  gdsp_sync         (gdsp_ctx* ctx);
+/* Exact-order mode (off by default; `--exact-order` in the CLI).  While on, gdsp_sliding_sum,
+ * gdsp_cumulative_sum and gdsp_clump evaluate their running sums in the reference's own sequential order
+ * (sum.c:438-455, sum.c:786-790, clump.c:600): bit-identical to the reference on every input, general reals,
+ * inf and NaN included, one dependent FP64 add per cell and chromosome (seconds, not milliseconds, on a
+ * human genome).  Whole chromosomes only. */
+int  gdsp_ctx_set_exact_order (gdsp_ctx* ctx, int on);
+int  gdsp_ctx_get_exact_order (const gdsp_ctx* ctx);
 /* page-locked host memory (device<->host copies from it run at full PCIe speed) */
 int  gdsp_malloc_host (size_t bytes, void** out);
 int  gdsp_free_host   (void* p);
