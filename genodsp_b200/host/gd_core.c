@@ -16,6 +16,8 @@
 #include <stdarg.h>
 #include <math.h>
 #include <float.h>
+#include <unistd.h>
+#include <sys/stat.h>
 
 #define globals_owner
 #include "genodsp_interface.h"
@@ -351,13 +353,20 @@ static int riMissingEol = false;
  * file with nothing read) fed from 1 MB blocks: the locked per-call stdio path costs more than the
  * parsing of a 25-character line. */
 #define LR_CAP (1u << 20)
-static struct { FILE* f;  char* buf;  size_t pos, len;  int eof; } lr;
+static struct { FILE* f;  char* buf;  size_t pos, len;  int eof;  const char* mem;  size_t memLen; } lr;
+
+/* feed the line reader from memory: the next gd_fgets(…, f) calls return the lines of [p, p+n) and then NULL */
+static void gd_fgets_from_memory (FILE* f, const char* p, size_t n)
+	{
+	if (lr.buf == NULL) lr.buf = (char*) malloc (LR_CAP);
+	lr.f = f;  lr.mem = p;  lr.memLen = n;  lr.pos = lr.len = 0;  lr.eof = false;
+	}
 
 static char* gd_fgets (char* dst, int dstLen, FILE* f)
 	{
 	if (lr.f != f)
 		{
-		lr.f = f;  lr.pos = lr.len = 0;  lr.eof = false;
+		lr.f = f;  lr.pos = lr.len = 0;  lr.eof = false;  lr.mem = NULL;  lr.memLen = 0;
 		if (lr.buf == NULL) lr.buf = (char*) malloc (LR_CAP);
 		}
 	int n = 0;
@@ -366,7 +375,13 @@ static char* gd_fgets (char* dst, int dstLen, FILE* f)
 		if (lr.pos == lr.len)
 			{
 			if (lr.eof) break;
-			lr.len = fread (lr.buf, 1, LR_CAP, f);  lr.pos = 0;
+			if (lr.mem != NULL)
+				{
+				lr.len = (lr.memLen < LR_CAP) ? lr.memLen : LR_CAP;
+				memcpy (lr.buf, lr.mem, lr.len);  lr.mem += lr.len;  lr.memLen -= lr.len;
+				}
+			else lr.len = fread (lr.buf, 1, LR_CAP, f);
+			lr.pos = 0;
 			if (lr.len == 0) { lr.eof = true;  break; }
 			}
 		size_t avail = lr.len - lr.pos, room = (size_t) (dstLen - 1 - n);
@@ -496,25 +511,162 @@ int read_interval (FILE* f, char* buffer, int bufferLen, int valCol,
 	return true;
 	}
 
-/* read_intervals: text -> SoA batch on the host -> accumulation on the GPU.
- * Replaces the per-base loops of genodsp.c:1307-1330.  Validation (origin shift, clipping,
- * "beyond the end of the chromosome") happens here with the reference's messages. */
-void read_intervals (FILE* f, int valCol, int originOne_, int overlapOp, int clear, valtype missingVal)
+/* ---- parallel tokenizer ---------------------------------------------------------------------
+ * The interval text is read in 32 MB blocks cut at a newline; a block is split into sub-chunks at
+ * newlines and every sub-chunk is tokenized by its own thread into a private SoA batch, while the main
+ * thread already reads the next block.  A worker only accepts what the reference's read_interval accepts
+ * without a second look -- "chrom ws digits ws digits [ws ...]" lines of at most 1000 characters, "track "
+ * lines, blank lines, '#' comments -- and flags its sub-chunk as soon as it meets anything else (a field
+ * the fast parser does not take, a line that starts with a blank, an interval beyond its chromosome ...).
+ * A flagged sub-chunk is re-read by the sequential read_interval from memory, with the line counter where
+ * it belongs: acceptance, messages, line numbers and exit status are the reference's by construction
+ * (genodsp.c:1384-1534).  --progress=input, --report=comments, --debug=input and --progress=operations keep
+ * the one-line-at-a-time path. */
+#include <pthread.h>
+
+#define PR_BLOCK   (32u << 20)
+#define PR_MAXTHR  32
+
+typedef struct prchunk
+	{
+	const char* p;  size_t n;          /* whole lines (the stream's last line may lack its newline)   */
+	int     valCol, origin;
+	u32*    seg;  u32* start;  u32* end;  double* val;
+	u64     cnt, cap, lines;
+	int     flagged, allInt;
+	double  sumAbs;
+	} prchunk;
+
+static int ingest_interval (ivlist* l, spec* cs, int segIx, char* chrom, u32 start, u32 end, valtype val, u32 o,
+                            int* allInt, double* sumAbs, int quiet);
+
+static void* pr_worker (void* arg)
+	{
+	prchunk* c = (prchunk*) arg;
+	const char* p = c->p;  const char* stop = c->p + c->n;
+	char   prevName[1001];  size_t prevLen = (size_t) -1;
+	spec*  cs = NULL;  int segIx = -1;
+	const u32 o = (u32) c->origin;
+	c->cnt = 0;  c->lines = 0;  c->flagged = false;  c->allInt = true;  c->sumAbs = 0.0;
+	while (p < stop)
+		{
+		const char* nl = (const char*) memchr (p, '\n', (size_t) (stop - p));
+		const char* e  = (nl != NULL) ? nl : stop;                 /* line text is [p, e)                  */
+		const char* next = (nl != NULL) ? nl + 1 : stop;
+		if ((size_t) (next - p) > 1000) { c->flagged = true;  return NULL; }     /* fgets would split it         */
+		c->lines++;
+		const char* q = p;
+		if (e - p >= 6 && memcmp (p, "track ", 6) == 0) { p = next;  continue; }
+		while (q < e && is_ws (*q)) q++;
+		if (q == e || *q == '#') { p = next;  continue; }
+		if (q != p) { c->flagged = true;  return NULL; }           /* begins with whitespace               */
+		const char* nameEnd = q;
+		while (nameEnd < e && !is_ws (*nameEnd)) nameEnd++;
+		const size_t nameLen = (size_t) (nameEnd - q);
+		if (memchr (q, 0, (size_t) (e - q)) != NULL) { c->flagged = true;  return NULL; }   /* NUL inside the line */
+		u64 f[2];
+		const char* r = nameEnd;
+		for (int k = 0; k < 2; k++)
+			{
+			while (r < e && is_ws (*r)) r++;
+			if (r == e || *r < '0' || *r > '9') { c->flagged = true;  return NULL; }
+			u64 v = 0;
+			while (r < e && *r >= '0' && *r <= '9') { v = v * 10 + (u64) (*r - '0');  if (v > 0xffffffffull) { c->flagged = true;  return NULL; }  r++; }
+			if (r < e && !is_ws (*r)) { c->flagged = true;  return NULL; }
+			f[k] = v;
+			}
+		valtype val = 1.0;
+		if (c->valCol != -1)
+			{
+			const char* fs = NULL;  const char* fe = NULL;
+			for (int col = 3; col <= c->valCol; col++)
+				{
+				while (r < e && is_ws (*r)) r++;
+				if (r == e) { c->flagged = true;  return NULL; }
+				fs = r;
+				while (r < e && !is_ws (*r)) r++;
+				fe = r;
+				}
+			char tmp[64];
+			const size_t fl = (size_t) (fe - fs);
+			const char c0 = fs[0];
+			if (fl >= sizeof (tmp)
+			 || !((c0 >= '0' && c0 <= '9') || ((c0 == '-' || c0 == '+' || c0 == '.') && fl > 1 && fs[1] >= '0' && fs[1] <= '9')))
+				{ c->flagged = true;  return NULL; }
+			memcpy (tmp, fs, fl);  tmp[fl] = 0;
+			char* endp;
+			val = strtod (tmp, &endp);
+			if (*endp != 0) { c->flagged = true;  return NULL; }
+			}
+		if (nameLen != prevLen || memcmp (q, prevName, nameLen) != 0)
+			{
+			memcpy (prevName, q, nameLen);  prevName[nameLen] = 0;  prevLen = nameLen;
+			cs = find_chromosome_spec (prevName);
+			segIx = (cs != NULL) ? gd_sorted_index (cs) : -1;
+			}
+		p = next;
+		if (cs == NULL) continue;
+		ivlist one;                                                 /* a view on this chunk's arrays          */
+		one.n = c->cnt;  one.cap = c->cap;  one.seg = c->seg;  one.start = c->start;  one.end = c->end;  one.val = c->val;
+		if (!ingest_interval (&one, cs, segIx, prevName, (u32) f[0], (u32) f[1], val, o, &c->allInt, &c->sumAbs, true))
+			{ c->flagged = true;  return NULL; }
+		c->cnt = one.n;
+		}
+	return NULL;
+	}
+
+/* what read_intervals does with one parsed line (genodsp.c:1245-1330 up to the per-base loop): origin shift,
+ * clipping, the "beyond the end" check, then the interval joins the batch.  quiet: return false instead of
+ * printing the message and exiting (the parallel tokenizer then replays the line sequentially). */
+static int ingest_interval (ivlist* l, spec* cs, int segIx, char* chrom, u32 start, u32 end, valtype val, u32 o,
+                            int* allInt, double* sumAbs, int quiet)
+	{
+	start -= o;
+	u32 a = start, b = end;
+	if (clipToLength)
+		{
+		if (start > cs->start + cs->length) a = start = cs->start + cs->length;
+		if (end   > cs->start + cs->length) b = end   = cs->start + cs->length;
+		}
+	if (cs->start == 0)
+		{
+		if (end > cs->length)
+			{
+			if (quiet) return false;
+			fprintf (stderr, "%s %d %d is beyond the end of the chromosome (L=%d)\n", chrom, start, end, cs->length);
+			exit (EXIT_FAILURE);
+			}
+		}
+	else
+		{
+		if (end <= cs->start) return true;
+		b = end - cs->start;
+		a = (start <= cs->start) ? 0 : start - cs->start;
+		if (a >= cs->length) return true;
+		if (b >= cs->length) b = cs->length;
+		}
+	if (a >= b) return true;                  /* the reference's loop body would not execute */
+	if (val != floor (val) || fabs (val) > 1e6) *allInt = false;
+	*sumAbs += fabs (val);
+	if (quiet)
+		{
+		if (l->n == l->cap) return false;     /* cannot happen: cap = bytes / 6 + 16 */
+		l->seg[l->n] = (u32) segIx;  l->start[l->n] = a;  l->end[l->n] = b;  l->val[l->n] = val;  l->n++;
+		}
+	else ivlist_push (l, (u32) segIx, a, b, val);
+	return true;
+	}
+
+/* the one-line-at-a-time loop (also the replay of a flagged sub-chunk, fed from memory) */
+static void read_intervals_sequential (FILE* f, int valCol, u32 o, ivlist* l, int* allInt, double* sumAbs)
 	{
 	char   line[1001], prevChrom[1001];
 	char*  chrom;
 	spec*  cs = NULL;
 	int    segIx = -1;
-	u32    start, end, o = originOne_ ? 1 : 0;
+	u32    start, end;
 	valtype val;
-	ivlist l;
-
-	ivlist_init (&l);
-	if (trackOperations) for (int i = 0; i < gd.nchrom; i++) chromsSorted[i]->flag = false;
 	prevChrom[0] = 0;
-	int allInt = true;
-	double sumAbs = 0.0;
-
 	while (read_interval (f, line, sizeof (line), valCol, &chrom, &start, &end, &val))
 		{
 		if (strcmp (chrom, prevChrom) != 0)
@@ -525,34 +677,188 @@ void read_intervals (FILE* f, int valCol, int originOne_, int overlapOp, int cle
 			}
 		if (cs == NULL) continue;
 		if (trackOperations && !cs->flag) { tracking_report ("input(%s)\n", chrom);  cs->flag = true; }
-		start -= o;
-		u32 a = start, b = end;
-		if (clipToLength)
+		ingest_interval (l, cs, segIx, chrom, start, end, val, o, allInt, sumAbs, false);
+		}
+	}
+
+static void ivlist_append (ivlist* l, const prchunk* c)
+	{
+	if (l->n + c->cnt > l->cap)
+		{
+		u64 nc = l->cap ? l->cap : (1u << 16);
+		while (nc < l->n + c->cnt) nc *= 2;
+		l->seg   = (u32*) realloc (l->seg,   nc * sizeof (u32));
+		l->start = (u32*) realloc (l->start, nc * sizeof (u32));
+		l->end   = (u32*) realloc (l->end,   nc * sizeof (u32));
+		l->val   = (double*) realloc (l->val, nc * sizeof (double));
+		if (!l->seg || !l->start || !l->end || !l->val)
+			{ fprintf (stderr, "out of memory holding %llu intervals\n", (unsigned long long) nc);  exit (EXIT_FAILURE); }
+		l->cap = nc;
+		}
+	memcpy (l->seg + l->n,   c->seg,   c->cnt * sizeof (u32));
+	memcpy (l->start + l->n, c->start, c->cnt * sizeof (u32));
+	memcpy (l->end + l->n,   c->end,   c->cnt * sizeof (u32));
+	memcpy (l->val + l->n,   c->val,   c->cnt * sizeof (double));
+	l->n += c->cnt;
+	}
+
+static int pr_thread_count (void)
+	{
+	const char* e = getenv ("GENODSP_THREADS");
+	long n = (e != NULL) ? atol (e) : sysconf (_SC_NPROCESSORS_ONLN);
+	if (n < 1) n = 1;
+	if (n > PR_MAXTHR) n = PR_MAXTHR;
+	return (int) n;
+	}
+
+static size_t pr_fill (FILE* f, char* buf, size_t have, int* eof)
+	{
+	while (!*eof && have < PR_BLOCK)
+		{
+		size_t r = fread (buf + have, 1, PR_BLOCK - have, f);
+		if (r == 0) { *eof = true;  break; }
+		have += r;
+		}
+	return have;
+	}
+
+static void pr_merge (FILE* f, prchunk* ch, int used, int valCol, u32 o, ivlist* l, int* allInt, double* sumAbs)
+	{
+	for (int t = 0; t < used; t++)
+		{
+		if (!ch[t].flagged)
 			{
-			if (start > cs->start + cs->length) a = start = cs->start + cs->length;
-			if (end   > cs->start + cs->length) b = end   = cs->start + cs->length;
-			}
-		if (cs->start == 0)
-			{
-			if (end > cs->length)
-				{
-				fprintf (stderr, "%s %d %d is beyond the end of the chromosome (L=%d)\n", chrom, start, end, cs->length);
-				exit (EXIT_FAILURE);
-				}
+			ivlist_append (l, &ch[t]);
+			riLineNumber += ch[t].lines;
+			if (!ch[t].allInt) *allInt = false;
+			*sumAbs += ch[t].sumAbs;
 			}
 		else
 			{
-			if (end <= cs->start) continue;
-			b = end - cs->start;
-			a = (start <= cs->start) ? 0 : start - cs->start;
-			if (a >= cs->length) continue;
-			if (b >= cs->length) b = cs->length;
+			gd_fgets_from_memory (f, ch[t].p, ch[t].n);
+			read_intervals_sequential (f, valCol, o, l, allInt, sumAbs);
 			}
-		if (a >= b) continue;                 /* the reference's loop body would not execute */
-		if (val != floor (val) || fabs (val) > 1e6) allInt = false;
-		sumAbs += fabs (val);
-		ivlist_push (&l, (u32) segIx, a, b, val);
 		}
+	}
+
+static void read_intervals_parallel (FILE* f, int valCol, u32 o, ivlist* l, int* allInt, double* sumAbs, int nthr)
+	{
+	/* three text blocks in rotation: one being tokenized, one being merged (a flagged sub-chunk is replayed from
+	 * its text), one being filled; two sets of per-thread batches: the workers fill one while the main thread
+	 * merges the other into the interval list */
+	char* blk[3];
+	for (int b = 0; b < 3; b++) blk[b] = (char*) malloc (PR_BLOCK + 1024);
+	static prchunk ch[2][PR_MAXTHR];
+	pthread_t th[PR_MAXTHR];  int started[PR_MAXTHR];
+	const u64 cap = PR_BLOCK / 6 / (u64) nthr + 4096;          /* shares are equal up to one line; a 6-byte line is the shortest */
+	for (int s2 = 0; s2 < 2; s2++)
+		for (int t = 0; t < nthr; t++)
+			{
+			prchunk* c = &ch[s2][t];
+			memset (c, 0, sizeof (prchunk));
+			c->cap = cap;  c->valCol = valCol;  c->origin = (int) o;
+			c->seg = (u32*) malloc (cap * 4);  c->start = (u32*) malloc (cap * 4);  c->end = (u32*) malloc (cap * 4);
+			c->val = (double*) malloc (cap * 8);
+			if (!c->seg || !c->start || !c->end || !c->val) { fprintf (stderr, "out of memory for the input buffers\n");  exit (EXIT_FAILURE); }
+			}
+	if (!blk[0] || !blk[1] || !blk[2]) { fprintf (stderr, "out of memory for the input buffers\n");  exit (EXIT_FAILURE); }
+	/* a regular file tells its size: reserve the list once instead of doubling it */
+	{
+	struct stat st;
+	if (fstat (fileno (f), &st) == 0 && S_ISREG (st.st_mode) && st.st_size > 0)
+		{
+		prchunk none;  memset (&none, 0, sizeof (none));
+		const u64 want = (u64) st.st_size / 16 + 1024;
+		if (want > l->cap)
+			{
+			l->seg = (u32*) realloc (l->seg, want * 4);  l->start = (u32*) realloc (l->start, want * 4);
+			l->end = (u32*) realloc (l->end, want * 4);  l->val = (double*) realloc (l->val, want * 8);
+			if (!l->seg || !l->start || !l->end || !l->val) { fprintf (stderr, "out of memory holding %llu intervals\n", (unsigned long long) want);  exit (EXIT_FAILURE); }
+			l->cap = want;
+			}
+		}
+	}
+	int cur = 0, set = 0, eof = false, pendingUsed = 0;
+	size_t got = 0;
+	for (;;)
+		{
+		got = pr_fill (f, blk[cur], got, &eof);
+		if (got == 0) break;
+		size_t whole = got;                                   /* bytes that form whole lines */
+		if (!eof) while (whole > 0 && blk[cur][whole-1] != '\n') whole--;
+		if (whole == 0)
+			{
+			/* not one newline in 32 MB: the sequential reader reports the over-long line */
+			pr_merge (f, ch[set ^ 1], pendingUsed, valCol, o, l, allInt, sumAbs);  pendingUsed = 0;
+			gd_fgets_from_memory (f, blk[cur], got);
+			read_intervals_sequential (f, valCol, o, l, allInt, sumAbs);
+			got = 0;
+			continue;
+			}
+		int used = 0;
+		size_t at = 0;
+		for (int t = 0; t < nthr && at < whole; t++)          /* sub-chunks cut at newlines */
+			{
+			size_t end = (t == nthr - 1) ? whole : at + (whole - at) / (size_t) (nthr - t);
+			while (end < whole && blk[cur][end-1] != '\n') end++;
+			ch[set][t].p = blk[cur] + at;  ch[set][t].n = end - at;
+			at = end;  used = t + 1;
+			}
+		for (int t = 0; t < used; t++)
+			{
+			started[t] = (pthread_create (&th[t], NULL, pr_worker, &ch[set][t]) == 0);
+			if (!started[t]) pr_worker (&ch[set][t]);
+			}
+		/* while they tokenize: merge the previous block's batches, move the partial last line to the next text
+		 * block and read on behind it */
+		pr_merge (f, ch[set ^ 1], pendingUsed, valCol, o, l, allInt, sumAbs);
+		const int nxt = (cur + 1) % 3;
+		size_t nextGot = got - whole;
+		memcpy (blk[nxt], blk[cur] + whole, nextGot);
+		nextGot = pr_fill (f, blk[nxt], nextGot, &eof);
+		for (int t = 0; t < used; t++) if (started[t]) pthread_join (th[t], NULL);
+		pendingUsed = used;  set ^= 1;
+		cur = nxt;  got = nextGot;
+		}
+	pr_merge (f, ch[set ^ 1], pendingUsed, valCol, o, l, allInt, sumAbs);
+	for (int s2 = 0; s2 < 2; s2++)
+		for (int t = 0; t < nthr; t++) { free (ch[s2][t].seg);  free (ch[s2][t].start);  free (ch[s2][t].end);  free (ch[s2][t].val); }
+	for (int b = 0; b < 3; b++) free (blk[b]);
+	}
+
+/* read_intervals: text -> SoA batch on the host -> accumulation on the GPU.
+ * Replaces the per-base loops of genodsp.c:1307-1330.  Validation (origin shift, clipping,
+ * "beyond the end of the chromosome") happens here with the reference's messages. */
+void read_intervals (FILE* f, int valCol, int originOne_, int overlapOp, int clear, valtype missingVal)
+	{
+	u32    o = originOne_ ? 1 : 0;
+	ivlist l;
+
+	ivlist_init (&l);
+	if (trackOperations) for (int i = 0; i < gd.nchrom; i++) chromsSorted[i]->flag = false;
+	int allInt = true;
+	double sumAbs = 0.0;
+
+	const int nthr = pr_thread_count ();
+	if (nthr > 1 && !trackOperations && !dbgInput && reportInputProgress == 0 && !reportComments && !riMissingEol)
+		read_intervals_parallel (f, valCol, o, &l, &allInt, &sumAbs, nthr);
+	else
+		read_intervals_sequential (f, valCol, o, &l, &allInt, &sumAbs);
+	if (getenv ("GENODSP_PARSE_ONLY") != NULL)
+		{
+		/* tokenizer self-check (tests/test_cpu_suite.py): what was parsed, without touching the device */
+		u64 h = 1469598103934665603ull;
+		for (u64 i = 0; i < l.n; i++)
+			{
+			u64 bits;  memcpy (&bits, &l.val[i], 8);
+			u64 w[4] = { l.seg[i], l.start[i], l.end[i], bits };
+			for (int k = 0; k < 4; k++) { h ^= w[k];  h *= 1099511628211ull; }
+			}
+		printf ("intervals=%llu hash=%016llx allInt=%d lines=%llu\n", (unsigned long long) l.n, (unsigned long long) h,
+		        allInt, (unsigned long long) riLineNumber);
+		exit (EXIT_SUCCESS);
+		}
+	gd_device_wait ();                        /* the device was opening while the text was parsed */
 	if (trackOperations) tracking_report ("input(--done--)\n");
 
 	if (overlapOp != ri_overlapSum)
@@ -1023,12 +1329,13 @@ int main (int argc, char** argv)
 		for (int i = 0; chromsSorted[i] != NULL; i++)
 			tracking_report ("allocate(%s / %s bytes)\n", chromsSorted[i]->chrom, ucommatize (chromsSorted[i]->length));
 	phase_mark ("parse args");
-	gd_device_open ();
+	gd_device_open ();                        /* CUDA initialisation continues on a helper thread ... */
 	if (trackOperations) tracking_report ("allocate(--done--)\n");
-	phase_mark ("device open");
+	phase_mark ("device start");
 
 	if (pipeline == NULL || strcmp (pipeline->name, "input") != 0)
 		read_intervals (stdin, valColumn, originOne, ri_overlapSum, false, 0.0);
+	gd_device_wait ();                        /* ... and is joined after the text has been parsed */
 	if (getenv ("GENODSP_TIMING") != NULL) gdsp_sync (gd.ctx);
 	phase_mark ("input");
 

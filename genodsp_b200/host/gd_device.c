@@ -15,14 +15,37 @@ void gd_check (int status, const char* who)
 	exit (EXIT_FAILURE);
 	}
 
+/* Opening the device (CUDA initialisation, context, the two genome-sized buffers and their zero fill) takes
+ * a large part of a second and needs nothing from the input: it runs on a helper thread while the main
+ * thread parses the interval text.  gd_device_open() does the host-side bookkeeping and
+ * starts the thread; gd_device_wait() joins it (idempotent) and must precede the first device call. */
+#include <pthread.h>
+static pthread_t openThread;
+static int       openPending = 0;
+
+static void* device_open_thread (void* arg)
+	{
+	(void) arg;
+	const int n = gd.nchrom;
+	gdsp_ctx* ctx;
+	gd_check (gdsp_ctx_create (0, GDSP_STREAM_PRIVATE, &ctx), "genodsp");
+	gd.ctx = ctx;
+	gd_check (gdsp_layout_create (gd.ctx, gd.segs, n, &gd.genome), "genodsp");
+	for (int i = 0; i < n; i++)
+		gd_check (gdsp_layout_create (gd.ctx, &gd.segs[i], 1, &gd.single[i]), "genodsp");
+	void* p;
+	gd_check (gdsp_malloc (gd.ctx, gd.cells * sizeof (double), &p), "genodsp");  gd.sig = (double*) p;
+	gd_check (gdsp_malloc (gd.ctx, gd.cells * sizeof (double), &p), "genodsp");  gd.tmp = (double*) p;
+	gd_check (gdsp_fill (gd.ctx, gd.genome, gd.sig, 0.0), "genodsp");
+	return NULL;
+	}
+
 void gd_device_open (void)
 	{
 	int n = 0;
 	while (chromsSorted[n] != NULL) n++;
 	memset (&gd, 0, sizeof (gd));
 	gd.nchrom = n;
-	gd_check (gdsp_ctx_create (0, GDSP_STREAM_PRIVATE, &gd.ctx), "genodsp");
-
 	u32* lens = (u32*) malloc (n * sizeof (u32));
 	gd.segs   = (gdsp_seg*) malloc (n * sizeof (gdsp_seg));
 	gd.single = (gdsp_layout**) malloc (n * sizeof (gdsp_layout*));
@@ -34,19 +57,25 @@ void gd_device_open (void)
 	u64 total;
 	gd_check (gdsp_layout_pack (lens, n, gd.segs, &total), "genodsp");
 	gd.cells = total;
-	gd_check (gdsp_layout_create (gd.ctx, gd.segs, n, &gd.genome), "genodsp");
-	for (int i = 0; i < n; i++)
-		gd_check (gdsp_layout_create (gd.ctx, &gd.segs[i], 1, &gd.single[i]), "genodsp");
-	void* p;
-	gd_check (gdsp_malloc (gd.ctx, total * sizeof (double), &p), "genodsp");  gd.sig = (double*) p;
-	gd_check (gdsp_malloc (gd.ctx, total * sizeof (double), &p), "genodsp");  gd.tmp = (double*) p;
-	gd_check (gdsp_fill (gd.ctx, gd.genome, gd.sig, 0.0), "genodsp");
-	for (int i = 0; i < n; i++) chromsSorted[i]->valVector = gd.sig + gd.segs[i].lo;
 	free (lens);
+	if (getenv ("GENODSP_PARSE_ONLY") != NULL) return;      /* tokenizer self-check (tests): no device needed */
+	if (getenv ("GENODSP_SYNC_OPEN") != NULL || pthread_create (&openThread, NULL, device_open_thread, NULL) != 0)
+		device_open_thread (NULL);
+	else
+		openPending = 1;
+	if (!openPending) gd_device_wait ();
+	}
+
+void gd_device_wait (void)
+	{
+	if (openPending) { pthread_join (openThread, NULL);  openPending = 0; }
+	if (gd.sig != NULL && chromsSorted[0] != NULL && chromsSorted[0]->valVector == NULL)
+		for (int i = 0; i < gd.nchrom; i++) chromsSorted[i]->valVector = gd.sig + gd.segs[i].lo;
 	}
 
 void gd_device_close (void)
 	{
+	gd_device_wait ();
 	if (gd.ctx == NULL) return;
 	gdsp_sync (gd.ctx);
 	for (int i = 0; i < gd.nchrom; i++) gdsp_layout_destroy (gd.single[i]);

@@ -32,7 +32,9 @@ typedef struct gdev
 
 extern gdev gd;
 
-void  gd_device_open   (void);           /* after sort_chromosomes_by_length            */
+void  gd_device_open   (void);           /* after sort_chromosomes_by_length: host bookkeeping, then the CUDA
+                                            part on a helper thread                                     */
+void  gd_device_wait   (void);           /* join that thread; call before the first device access     */
 void  gd_device_close  (void);
 void  gd_check         (int status, const char* who);   /* fatal on error               */
 void  gd_materialise_sorted (const char* who);   /* gd_ops_percentile.c: sort now if pendingSorted */

@@ -337,3 +337,74 @@ def test_cli_refuses_to_run_without_a_device(tmp_path):
     (tmp_path / "g.chroms").write_text("chr1 100\n")
     p = _run_cli(OURS_BIN, ["--chromosomes=g.chroms", "=", "binarize"], cwd=tmp_path)
     assert p.returncode != 0 and b"no CUDA device" in p.stderr and p.stdout == b""
+
+
+# ----------------------------------------------------------------------------- parallel tokenizer (no GPU needed)
+def _parse_only(args, text, threads, cwd):
+    import subprocess
+    env = dict(os.environ, GENODSP_PARSE_ONLY="1", GENODSP_THREADS=str(threads))
+    return subprocess.run([OURS_BIN] + args, input=text, capture_output=True, cwd=cwd, env=env, timeout=120)
+
+
+@pytest.mark.skipif(not os.path.exists(OURS_BIN), reason="host CLI not built")
+def test_parallel_tokenizer_equals_line_at_a_time_reader(tmp_path):
+    """the block tokenizer on T threads (gd_core.c:read_intervals_parallel) must accept, reject and number
+    lines exactly as the one-line-at-a-time read_interval does (reference grammar genodsp.c:1384-1534):
+    same intervals in the same order, same first error message and exit status"""
+    rng = np.random.default_rng(11)
+    (tmp_path / "g.chroms").write_text("chr1 2000000\nchr2 900000\nchrX 50\n")
+    lines = ["track name=x", "# comment", "", "   ", "\t"]
+    for _ in range(200000):
+        c = ["chr1", "chr2", "chrUn", "chrX"][int(rng.integers(0, 4))]
+        L = {"chr1": 2000000, "chr2": 900000, "chrUn": 1000, "chrX": 50}[c]
+        a = int(rng.integers(0, L))
+        b = min(L, a + int(rng.integers(0, 300)))
+        sep = ["\t", " ", "  \t "][int(rng.integers(0, 3))]
+        v = ["1", "2.5", "-0.125", "1e3", "+4", ".5", "7"][int(rng.integers(0, 7))]
+        lines.append(sep.join([c, str(a), str(b), v, "extra"]) + ("  " if rng.random() < 0.1 else ""))
+        if rng.random() < 0.001:
+            lines.append("# interleaved comment")
+    good = ("\n".join(lines) + "\n").encode()
+    C = ["--chromosomes=g.chroms"]
+    for args in (C, C + ["--novalue"], C + ["--value=5"], C + ["--origin=one"]):
+        if "--origin=one" in args:
+            text = good.replace(b"\t0\t", b"\t1\t").replace(b" 0 ", b" 1 ")
+        else:
+            text = good
+        one = _parse_only(args, text, 1, tmp_path)
+        many = _parse_only(args, text, 7, tmp_path)
+        assert one.returncode == many.returncode, (args, one.stderr[-300:], many.stderr[-300:])
+        assert one.stdout == many.stdout and one.stderr == many.stderr, (args, one.stdout, many.stdout, many.stderr[-300:])
+    assert b"intervals=" in _parse_only(C, good, 7, tmp_path).stdout
+    # no trailing newline on the last line; a value field the fast path declines ("nan", "inf", hex) is replayed
+    odd = good[:-1] + b"\nchr1\t5\t9\tnan\nchr1\t5\t9\t0x10\nchr2 1 2 inf"
+    a, b = _parse_only(C, odd, 1, tmp_path), _parse_only(C, odd, 5, tmp_path)
+    assert a.returncode == b.returncode == 0 and a.stdout == b.stdout, (a.stdout, b.stdout, b.stderr[-300:])
+    # every kind of malformed line: same message (with its line number) and status from both readers
+    bad_lines = [b" chr1 5 9 1", b"chr1", b"chr1 5", b"chr1 5 9", b"chr1 x 9 1", b"chr1 5 y 1", b"chr1 5 3000000 1",
+                 b"chr1 5 9 zzz", b"chr1 99999999999 9 1", b"chr1 " + b"9" * 1200 + b" 5 1", b"chrX 10 51 1", b"chr1 -5 9 1"]
+    for pos in (10, len(lines) // 2, len(lines) - 3):
+        for bad in bad_lines:
+            text = b"\n".join([l.encode() for l in lines[:pos]] + [bad] + [l.encode() for l in lines[pos:]]) + b"\n"
+            a, b = _parse_only(C, text, 1, tmp_path), _parse_only(C, text, 6, tmp_path)
+            assert a.returncode == b.returncode, (bad, pos, a.stderr[-200:], b.stderr[-200:])
+            assert a.stderr == b.stderr and a.stdout == b.stdout, (bad, pos, a.stderr[-200:], b.stderr[-200:])
+            if pos != 10:
+                break
+
+
+@pytest.mark.skipif(not os.path.exists(OURS_BIN), reason="host CLI not built")
+def test_parallel_tokenizer_errors_match_the_reference(tmp_path):
+    """the first malformed line is reported with the reference's own words and line number"""
+    from checkers import REF_BIN, have_ref
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    import subprocess
+    (tmp_path / "g.chroms").write_text("chr1 2000000\n")
+    body = "".join("chr1\t%d\t%d\n" % (i, i + 10) for i in range(0, 300000, 3))
+    for bad in ("chr1 7\n", " chr1 1 2\n", "chr1 5 3000000\n", "chr1 " + "9" * 1100 + " 5\n"):
+        text = (body + bad + body).encode()
+        ref = subprocess.run([REF_BIN, "--chromosomes=g.chroms", "--novalue"], input=text, capture_output=True, cwd=tmp_path)
+        ours = _parse_only(["--chromosomes=g.chroms", "--novalue"], text, 8, tmp_path)
+        assert ref.returncode != 0 and ours.returncode == ref.returncode, (bad[:30], ours.stderr[-200:])
+        assert ours.stderr == ref.stderr, (bad[:30], ref.stderr[-200:], ours.stderr[-200:])
