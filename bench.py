@@ -383,7 +383,16 @@ def run_gpu_arm(args):
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
+    # the headline step as a two-stream pipeline: accumulation of chromosome group k+1 (side stream) behind the FIR
+    # of group k (compute stream); --no-overlap runs the two operators back to back on one stream
+    dsp = None if args.no_overlap else slab.DepthSmoothPipeline(g, plan, dist, WINDOW, seg_t, start_t, end_t, args.groups)
+
     def step_resident(timers=None):
+        if dsp is not None:
+            dsp.run(timed=timers is not None)
+            if timers is not None:
+                timers.append(dsp.stage_events)
+            return
         if timers is not None:
             timers[0].record()
         P.depth()
@@ -392,6 +401,20 @@ def run_gpu_arm(args):
         P.smooth()                       # at N > 1 the halo exchange runs on a side stream behind the interior FIR
         if timers is not None:
             timers[2].record()
+
+    # the pipelined step must leave the bits of accumulate() followed by smooth(): checked on this rank's cells
+    overlap_equal = None
+    if dsp is not None:
+        P.depth(); P.smooth()
+        want = g.sig.clone()
+        dsp.run()
+        torch.cuda.synchronize()
+        overlap_equal = all(bool(torch.equal(g.sig[lo:hi].view(torch.int64), want[lo:hi].view(torch.int64))) for (lo, hi, *_r) in g.segs)
+        del want
+        if world > 1:
+            flag = torch.tensor([1 if overlap_equal else 0], device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            overlap_equal = bool(flag.item())
 
     def barrier():
         if world > 1:
@@ -417,8 +440,13 @@ def run_gpu_arm(args):
     barrier()
     total_ms = t_begin.elapsed_time(t_end)
     clocks = sampler.stop() if rank == 0 else None
-    acc_ms = sum(e[0].elapsed_time(e[1]) for e in stage_ev) / args.steps
-    smo_ms = sum(e[1].elapsed_time(e[2]) for e in stage_ev) / args.steps
+    if dsp is not None:
+        # per-launch durations summed per stage (the stages overlap in time: their sum exceeds the step)
+        acc_ms = sum(sum(a.elapsed_time(b) for a, b in e[3][0]) for e in stage_ev) / args.steps
+        smo_ms = sum(sum(a.elapsed_time(b) for a, b in e[3][1]) for e in stage_ev) / args.steps
+    else:
+        acc_ms = sum(e[0].elapsed_time(e[1]) for e in stage_ev) / args.steps
+        smo_ms = sum(e[1].elapsed_time(e[2]) for e in stage_ev) / args.steps
 
     # ---- end to end through the C-ABI with HOST buffers: pinned interval arrays in, fp64 signal out
     e2e_steps = max(1, min(args.steps, 3))
@@ -555,15 +583,23 @@ def run_gpu_arm(args):
                                  "2*W=202 separately rounded FP64 instructions per base, so FP64 issue (64 lanes/SM), not HBM, is the "
                                  "binding limit for W=101: see binding_limit"},
         }
+        line["config"]["step"] = ("two-stream pipeline over %d chromosome groups: accumulate(group k+1) on a high-priority side stream "
+                                  "behind smooth(group k); stage times are sums of per-launch durations and overlap" % args.groups) \
+            if dsp is not None else "accumulate, then smooth, on one stream"
+        if overlap_equal is not None:
+            line["pipelined_step_bit_equal_to_sequential"] = bool(overlap_equal)
+            ok = ok and bool(overlap_equal)
         if "parity" in finals:
             par = finals["parity"]
-            ok = all(v["cells_differ"] == 0 and v["variables_equal"] for v in par.values())
+            ok = ok and all(v["cells_differ"] == 0 and v["variables_equal"] for v in par.values())
             line["parity_check"] = {"against": "the same pipelines run on the whole genome on rank 0's GPU (the N = 1 path)",
                                     "cut_chromosomes": max(v["cut_chromosome_pieces"] for v in par.values()) - 0,
                                     "bit_equal": ok, "pipelines": par}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_single()
         print(json.dumps(line), flush=True)
+    if dsp is not None:
+        dsp.close()
     P.close()
     g.close()
     if world > 1:
@@ -586,6 +622,8 @@ def main():
     ap.add_argument("--no-stages", action="store_true", help="skip the per-pipeline stage timings (pipe5, cfg3, cfg4, cfg5)")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the bit-comparison of the slab results with the whole-genome run on rank 0")
     ap.add_argument("--stage-reps", type=int, default=2)
+    ap.add_argument("--no-overlap", action="store_true", help="headline step: accumulate then smooth on one stream (no two-stream pipeline)")
+    ap.add_argument("--groups", type=int, default=6, help="chromosome groups of the two-stream pipeline")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -455,9 +455,13 @@ class Genome:
     def binarize(self, threshold=0.0, ties_above=False, one=1.0, zero=0.0):
         if isinstance(threshold, str):
             threshold = self.variables[threshold]     # logical.c:232-244
-        if self._pending_sort and float(threshold) != 0.0 and float(threshold) in getattr(self, "_sorted_known", {}):
+        # (+0.0 and -0.0 compare equal but have different sort keys: the key counts give the step only when
+        # the zeros that tie with the threshold all lie on the side the counts put them)
+        zero_ok = float(threshold) != 0.0 or (np.signbit(threshold) == bool(ties_above))
+        if self._pending_sort and zero_ok and float(threshold) in getattr(self, "_sorted_known", {}) \
+                and np.signbit(threshold) == self._sorted_known[float(threshold)][2]:
             # the selection pass already counted the cells below / equal to this percentile: fill only
-            below, equal = self._sorted_known[float(threshold)]
+            below, equal, _neg = self._sorted_known[float(threshold)]
             prefix, acc = [], 0
             for (lo, hi, *_r) in self.segs:
                 prefix.append(acc); acc += hi - lo
@@ -556,7 +560,7 @@ class Genome:
             self._pending_sort = True                 # materialised by the next reader of self.sig
             if self.num_samples == self.cells and int(nnan.value) == 0:
                 # every cell took part: #(v < value) and #(v == value) locate binarize's step in the sorted genome
-                self._sorted_known = {float(vals[i]): (int(below[i]), int(equal[i])) for i in range(len(ps))}
+                self._sorted_known = {float(vals[i]): (int(below[i]), int(equal[i]), bool(np.signbit(vals[i]))) for i in range(len(ps))}
         return out
 
     def fill_step(self, prefix, step, one=1.0, zero=0.0):

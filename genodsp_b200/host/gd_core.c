@@ -346,6 +346,8 @@ static void free_scratch_vectors (void)
  * numeric fields go through a fast decimal parser and fall back to the sscanf-based helpers for
  * anything unusual, so acceptance and error texts are unchanged. */
 
+static void phase_mark (const char* what);
+
 static u64 riLineNumber = 0;         /* never reset, like the reference's static counter */
 static int riMissingEol = false;
 
@@ -858,7 +860,9 @@ void read_intervals (FILE* f, int valCol, int originOne_, int overlapOp, int cle
 		        allInt, (unsigned long long) riLineNumber);
 		exit (EXIT_SUCCESS);
 		}
+	phase_mark ("text parse");
 	gd_device_wait ();                        /* the device was opening while the text was parsed */
+	phase_mark ("device wait");
 	if (trackOperations) tracking_report ("input(--done--)\n");
 
 	if (overlapOp != ri_overlapSum)
@@ -903,6 +907,8 @@ static inline void out_u32 (u32 v)
 	while (n) outBuf[outLen++] = tmp[--n];
 	}
 
+static FILE* outFile = NULL;             /* where out_value sends a value too long for the buffer */
+
 static inline void out_value (int precision, valtype v)
 	{
 	/* integers with precision 0 are by far the common case; everything else goes through printf
@@ -913,12 +919,25 @@ static inline void out_value (int precision, valtype v)
 		out_u32 ((u32) v);
 		}
 	else
-		outLen += (size_t) snprintf (outBuf + outLen, 400, valtypeFmtPrec, precision, v);
+		{
+		/* room left in the buffer: at least 1024 - (name + two numbers) here.  A value that does not fit
+		 * (--precision in the hundreds, DBL_MAX with many decimals) is flushed around: never advance by more
+		 * than was written */
+		const size_t room = OUT_CAP + 1024 - outLen - 2;
+		int n = snprintf (outBuf + outLen, room, valtypeFmtPrec, precision, v);
+		if (n >= 0 && (size_t) n < room) outLen += (size_t) n;
+		else
+			{
+			fwrite (outBuf, 1, outLen, outFile);  outLen = 0;
+			fprintf (outFile, valtypeFmtPrec, precision, v);
+			}
+		}
 	}
 
 static void out_line (FILE* f, const char* chrom, size_t chromLen, u32 s, u32 e, int kind, int precision, valtype v)
 	{
 	if (outLen + chromLen + 512 > OUT_CAP) out_flush (f);
+	outFile = f;
 	memcpy (outBuf + outLen, chrom, chromLen);  outLen += chromLen;
 	outBuf[outLen++] = '\t';  out_u32 (s);
 	outBuf[outLen++] = '\t';  out_u32 (e);

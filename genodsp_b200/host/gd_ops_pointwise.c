@@ -160,7 +160,10 @@ int gd_pointwise_descriptor (dspop* _op, gdsp_pw_op* out, gd_pw_resources* res)
 				 * sorted (gd_ops_percentile.c); this binarize is then the first operator of its chain */
 				int done = 0;
 				for (int k = 0; k < gd.knownN; k++)
-					if (gd.knownVal[k] == op->a && op->a != 0.0)     /* +0.0 / -0.0 share a value but not a key */
+					/* +0.0 / -0.0 share a value but not a sort key: the key counts give the step only when every
+					 * zero that ties with the threshold lies on the side the counts put it */
+					if (gd.knownVal[k] == op->a && signbit (gd.knownVal[k]) == signbit (op->a)
+					 && (op->a != 0.0 || ((signbit (op->a) != 0) == (op->flag != 0))))
 						{
 						/* the percentile's own selection pass counted the cells below / equal to this value */
 						u64* prefix = (u64*) malloc (gd.nchrom * sizeof (u64));

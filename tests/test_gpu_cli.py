@@ -260,6 +260,8 @@ def test_output_values_the_device_formatter_declines(data):
     with open(data / "odd.iv", "w") as f:
         f.write("chrA 10 20 nan\nchrA 30 40 1e300\nchrA 50 60 -2.5\nchrB 5 9 0.125\nchrC 1 2 9223372036854775808\n"
                 "chrC 7 9 9223372036854774784\nchrD 0 3 -0.0004\n")
+    # a precision beyond what the device formatter takes, long enough to overrun a fixed line buffer
+    assert_same(data, C + ["--precision=600"], stdin="odd.iv")
     for prec in ("0", "3", "17"):
         assert_same(data, C + ["--precision=" + prec], stdin="odd.iv")
         assert_same(data, C + ["--precision=" + prec, "--uncovered:show", "--origin=one", "--nocollapse"], stdin="odd.iv")

@@ -739,7 +739,7 @@ def test_percentiles_ranked_counts(genome, orc, kind):
         assert genome._sorted_known == {}, "NaN present: the step-function shortcut must be off"
         return
     assert len(genome._sorted_known) == len(set(got.values()))
-    for val, (below, equal) in genome._sorted_known.items():
+    for val, (below, equal, _neg) in genome._sorted_known.items():
         assert below == int((allv < val).sum()) + (int(((allv == 0) & np.signbit(allv)).sum()) if val == 0 and not np.signbit(val) else 0) \
             or below == int((allv < val).sum()), (kind, val, below)
         if val != 0:
