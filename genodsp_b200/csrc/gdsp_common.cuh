@@ -229,43 +229,18 @@ __device__ __forceinline__ void stage_tile (double* smem, const double* __restri
 	const uint32_t tid = threadIdx.x, nt = blockDim.x;
 	if (g0 >= (int64_t) dlo && g0 + (int64_t) count <= (int64_t) dhi)
 		{
-		// 256-bit loads (one lane = one whole 32-byte sector), four of them in flight per thread before
-		// the first shared-memory store: the staging loop used to run one 128-bit load deep, and ncu showed
-		// the windowed kernels waiting on it (long-scoreboard 5-6 per issue, profiles/round1_stages.md)
 		const double* p = in + g0;
-		const uint32_t j0 = (uint32_t) ((0 - g0) & 3);             // cells before the first 32-byte boundary
-		if (j0 >= count)
+		const uint32_t j0 = (uint32_t) (g0 & 1);                 // first cell on a 16-byte boundary
+		const uint32_t npair = (count - j0) >> 1;
+		if (j0 && tid == 0) smem[stage_idx<PADSHIFT> (0)] = __ldg (p);
+		for (uint32_t q = tid; q < npair; q += nt)
 			{
-			if (tid < count) smem[stage_idx<PADSHIFT> (tid)] = __ldg (p + tid);
+			const uint32_t j = j0 + 2 * q;
+			const double2 v = __ldg (reinterpret_cast<const double2*> (p + j));
+			smem[stage_idx<PADSHIFT> (j)]     = v.x;
+			smem[stage_idx<PADSHIFT> (j + 1)] = v.y;
 			}
-		else
-			{
-			const uint32_t nquad = (count - j0) >> 2;
-			const uint32_t tail0 = j0 + 4 * nquad;
-			if (tid < j0) smem[stage_idx<PADSHIFT> (tid)] = __ldg (p + tid);
-			if (tid < count - tail0) smem[stage_idx<PADSHIFT> (tail0 + tid)] = __ldg (p + tail0 + tid);
-			for (uint32_t q = tid; q < nquad; q += 4 * nt)
-				{
-				double v[4][4];
-				#pragma unroll
-				for (int u = 0; u < 4; u++)
-					{
-					const uint32_t qq = q + u * nt;
-					if (qq < nquad) ldg_stream4 (p + j0 + 4 * qq, v[u][0], v[u][1], v[u][2], v[u][3]);
-					}
-				#pragma unroll
-				for (int u = 0; u < 4; u++)
-					{
-					const uint32_t qq = q + u * nt;
-					if (qq < nquad)
-						{
-						const uint32_t j = j0 + 4 * qq;
-						#pragma unroll
-						for (int k = 0; k < 4; k++) smem[stage_idx<PADSHIFT> (j + k)] = v[u][k];
-						}
-					}
-				}
-			}
+		if (((count - j0) & 1) && tid == nt - 1) smem[stage_idx<PADSHIFT> (count - 1)] = __ldg (p + count - 1);
 		}
 	else
 		{

@@ -966,6 +966,7 @@ k_pct_pass (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, 
 struct PctSmall
 	{
 	unsigned long long k0, k1;
+	double             d0, d1;         // the same bounds as doubles (FAST path)
 	unsigned int       cmask;          // bit o: compact open region o
 	int                limits;         // 0: every value qualifies (no --min/--max)
 	};
@@ -973,8 +974,8 @@ struct PctSmall
 template <int NB>
 struct PctAcc
 	{
-	unsigned int tot, lt0, le0, lt1, le1, nan;
-	__device__ __forceinline__ void clear () { tot = lt0 = le0 = lt1 = le1 = nan = 0; }
+	unsigned int tot, lt0, le0, lt1, le1, nan, negz;
+	__device__ __forceinline__ void clear () { tot = lt0 = le0 = lt1 = le1 = nan = negz = 0; }
 	// returns true when the cell must be compacted
 	__device__ __forceinline__ bool add (const PctSmall& P, double v, bool q)
 		{
@@ -989,6 +990,28 @@ struct PctAcc
 		if (NB >= 1) { o = b0 ? 0 : 1;  isB = b0 && !a0; }
 		if (NB >= 2) { o += b1 ? 0 : 1; isB = isB || (b1 && !a1); }
 		return q && !isB && ((P.cmask >> o) & 1u);
+		}
+	// FAST: every cell qualifies, the bounds are finite and non-zero and the signal is expected to be finite,
+	// so a < b <=> key(a) < key(b) and the compares can run on the FP64 pipe (DSETP) instead of 64-bit
+	// integer compare pairs -- the integer pipe was what bound this kernel (ncu: ALU 73 %, 39 instructions
+	// per cell; profiles/r2_ncu_full_scale4_summaries.txt).  Cells that are NOT finite are counted in `nan`
+	// (one 32-bit test of the exponent field); if there are any the host repeats the pass on the key path.
+	// ZB: one of the bounds is a zero.  -0.0 and +0.0 are equal to DSETP but not by key, so the cells holding
+	// -0.0 are counted and the host moves them to the side of the bound their key puts them on.
+	template <bool ZB>
+	__device__ __forceinline__ bool add_fast (const PctSmall& P, double v)
+		{
+		nan += ((unsigned int) __double2hiint (v) & 0x7ff00000u) == 0x7ff00000u;
+		if (ZB) negz += (__double_as_longlong (v) == (long long) 0x8000000000000000ull);
+		bool a0 = false, b0 = false, a1 = false, b1 = false;
+		if (NB >= 1) { a0 = v < P.d0;  b0 = v <= P.d0;  lt0 += a0;  le0 += b0; }
+		if (NB >= 2) { a1 = v < P.d1;  b1 = v <= P.d1;  lt1 += a1;  le1 += b1; }
+		if (NB == 0) return (P.cmask & 1u) != 0;
+		int  o   = 0;
+		bool isB = false;
+		if (NB >= 1) { o = b0 ? 0 : 1;  isB = b0 && !a0; }
+		if (NB >= 2) { o += b1 ? 0 : 1; isB = isB || (b1 && !a1); }
+		return !isB && ((P.cmask >> o) & 1u);
 		}
 	};
 
@@ -1010,15 +1033,16 @@ __device__ __forceinline__ void pct_compact (bool c, double v, double* __restric
 		}
 	}
 
-template <int NB>
+// MODE 0: key compares (any limits, any bounds); 1: FAST; 2: FAST with a zero bound
+template <int NB, int MODE>
 __global__ void __launch_bounds__(256)
 k_pct_pass_small (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg, uint64_t ntiles,
                   const double* __restrict__ sig, uint32_t stride, double mn, double mx,
                   const PctSmall P, unsigned long long* __restrict__ counts,
                   double* __restrict__ cand, unsigned long long cap, unsigned long long* __restrict__ ncand)
 	{
-	__shared__ unsigned int s_cnt[6];
-	if (threadIdx.x < 6) s_cnt[threadIdx.x] = 0;
+	__shared__ unsigned int s_cnt[7];
+	if (threadIdx.x < 7) s_cnt[threadIdx.x] = 0;
 	__syncthreads ();
 	PctAcc<NB> A;  A.clear ();
 
@@ -1043,10 +1067,16 @@ k_pct_pass_small (const SegDev* __restrict__ segs, const uint64_t* __restrict__ 
 				#pragma unroll
 				for (int u = 0; u < 8; u++)
 					{
-					const bool q = P.limits ? (!(v[u] < mn) && !(v[u] > mx)) : true;
-					cc[u] = A.add (P, v[u], q);
+					if (MODE == 1) cc[u] = A.template add_fast<false> (P, v[u]);
+					else if (MODE == 2) cc[u] = A.template add_fast<true> (P, v[u]);
+					else
+						{
+						const bool q = P.limits ? (!(v[u] < mn) && !(v[u] > mx)) : true;
+						cc[u] = A.add (P, v[u], q);
+						}
 					any = any || cc[u];
 					}
+				if (MODE != 0) A.tot += 8;
 				if (__any_sync (0xffffffffu, any))
 					{
 					#pragma unroll
@@ -1069,9 +1099,9 @@ k_pct_pass_small (const SegDev* __restrict__ segs, const uint64_t* __restrict__ 
 			}
 		}
 
-	unsigned int x[6] = { A.tot, A.lt0, A.le0, A.lt1, A.le1, A.nan };
+	unsigned int x[7] = { A.tot, A.lt0, A.le0, A.lt1, A.le1, A.nan, A.negz };
 	#pragma unroll
-	for (int r = 0; r < 6; r++)
+	for (int r = 0; r < 7; r++)
 		{
 		#pragma unroll
 		for (int d = 16; d > 0; d >>= 1) x[r] += __shfl_xor_sync (0xffffffffu, x[r], d);
@@ -1082,7 +1112,8 @@ k_pct_pass_small (const SegDev* __restrict__ segs, const uint64_t* __restrict__ 
 		{
 		// cumulative counts -> region populations (region 2i+1 = "equals bound i")
 		const unsigned long long tot = s_cnt[0], lt0 = s_cnt[1], le0 = s_cnt[2], lt1 = s_cnt[3], le1 = s_cnt[4];
-		if (s_cnt[5]) atomicAdd (&ncand[1], (unsigned long long) s_cnt[5]);      // qualifying NaN cells
+		if (s_cnt[5]) atomicAdd (&ncand[1], (unsigned long long) s_cnt[5]);      // qualifying NaN (FAST: non-finite) cells
+		if (s_cnt[6]) atomicAdd (&ncand[3], (unsigned long long) s_cnt[6]);      // FAST with a zero bound: cells holding -0.0
 		if (NB == 0) { if (tot) atomicAdd (&counts[0], tot); }
 		if (NB == 1)
 			{
@@ -1102,10 +1133,14 @@ k_pct_pass_small (const SegDev* __restrict__ segs, const uint64_t* __restrict__ 
 	}
 
 // one counting / compaction pass over the layout (d_counts, d_ncand already zeroed)
+static inline double host_unkey (unsigned long long k);
+
 static int pct_launch_pass (gdsp_ctx* c, gdsp_layout* L, const TileMap& tmPct, const double* sig, uint32_t stride,
                             double mn, double mx, const PctBounds& B, unsigned long long* d_counts,
-                            double* d_cand, unsigned long long cap, unsigned long long* d_ncand)
+                            double* d_cand, unsigned long long cap, unsigned long long* d_ncand,
+                            bool allowFast = false, bool* usedFast = NULL)
 	{
+	if (usedFast) *usedFast = false;
 	int grid = c->sm_count * 8;
 	if ((uint64_t) grid > tmPct.ntiles) grid = (int) tmPct.ntiles;
 	if (B.nb <= 2 && (((uintptr_t) sig) & 31u) == 0)
@@ -1117,12 +1152,36 @@ static int pct_launch_pass (gdsp_ctx* c, gdsp_layout* L, const TileMap& tmPct, c
 		P.limits = !(mn == -HUGE_VAL && mx == HUGE_VAL);
 		// persistent grid: exactly the blocks that are resident at once (a larger grid runs a ragged second wave)
 		int perSM = 0;
-		GDSP_CUDA (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&perSM, k_pct_pass_small<2>, 256, 0));
+		GDSP_CUDA (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&perSM, k_pct_pass_small<2, 0>, 256, 0));
 		grid = c->sm_count * (perSM > 0 ? perSM : 1);
 		if ((uint64_t) grid > tmPct.ntiles) grid = (int) tmPct.ntiles;
-		if (B.nb == 0)      k_pct_pass_small<0><<<grid, 256, 0, c->stream>>> (L->d, tmPct.d_base, L->nseg, tmPct.ntiles, sig, stride, mn, mx, P, d_counts, d_cand, cap, d_ncand);
-		else if (B.nb == 1) k_pct_pass_small<1><<<grid, 256, 0, c->stream>>> (L->d, tmPct.d_base, L->nseg, tmPct.ntiles, sig, stride, mn, mx, P, d_counts, d_cand, cap, d_ncand);
-		else                k_pct_pass_small<2><<<grid, 256, 0, c->stream>>> (L->d, tmPct.d_base, L->nseg, tmPct.ntiles, sig, stride, mn, mx, P, d_counts, d_cand, cap, d_ncand);
+		// FAST: the default limits (-DBL_MAX..DBL_MAX, which only exclude +-inf) and finite non-zero bounds
+		P.d0 = (B.nb >= 1) ? host_unkey (B.key[0]) : 0.0;  P.d1 = (B.nb >= 2) ? host_unkey (B.key[1]) : 0.0;
+		bool fast = allowFast && stride == 1 && mn <= -DBL_MAX && mx >= DBL_MAX;
+		int zeroBounds = 0;
+		for (int r = 0; r < B.nb; r++)
+			{
+			const double d = host_unkey (B.key[r]);
+			if (!(d == d) || d > DBL_MAX || d < -DBL_MAX) fast = false;
+			if (d == 0.0) zeroBounds++;
+			}
+		// a zero bound: fine while nothing is compacted (the heavy-ties case: the wanted value IS the bound)
+		if (zeroBounds > 1 || (zeroBounds == 1 && P.cmask != 0)) fast = false;
+		if (usedFast) *usedFast = fast;
+		if (fast && zeroBounds == 0)
+			{
+			if (B.nb == 0)      k_pct_pass_small<0, 1><<<grid, 256, 0, c->stream>>> (L->d, tmPct.d_base, L->nseg, tmPct.ntiles, sig, stride, mn, mx, P, d_counts, d_cand, cap, d_ncand);
+			else if (B.nb == 1) k_pct_pass_small<1, 1><<<grid, 256, 0, c->stream>>> (L->d, tmPct.d_base, L->nseg, tmPct.ntiles, sig, stride, mn, mx, P, d_counts, d_cand, cap, d_ncand);
+			else                k_pct_pass_small<2, 1><<<grid, 256, 0, c->stream>>> (L->d, tmPct.d_base, L->nseg, tmPct.ntiles, sig, stride, mn, mx, P, d_counts, d_cand, cap, d_ncand);
+			}
+		else if (fast)
+			{
+			if (B.nb == 1) k_pct_pass_small<1, 2><<<grid, 256, 0, c->stream>>> (L->d, tmPct.d_base, L->nseg, tmPct.ntiles, sig, stride, mn, mx, P, d_counts, d_cand, cap, d_ncand);
+			else           k_pct_pass_small<2, 2><<<grid, 256, 0, c->stream>>> (L->d, tmPct.d_base, L->nseg, tmPct.ntiles, sig, stride, mn, mx, P, d_counts, d_cand, cap, d_ncand);
+			}
+		else if (B.nb == 0) k_pct_pass_small<0, 0><<<grid, 256, 0, c->stream>>> (L->d, tmPct.d_base, L->nseg, tmPct.ntiles, sig, stride, mn, mx, P, d_counts, d_cand, cap, d_ncand);
+		else if (B.nb == 1) k_pct_pass_small<1, 0><<<grid, 256, 0, c->stream>>> (L->d, tmPct.d_base, L->nseg, tmPct.ntiles, sig, stride, mn, mx, P, d_counts, d_cand, cap, d_ncand);
+		else                k_pct_pass_small<2, 0><<<grid, 256, 0, c->stream>>> (L->d, tmPct.d_base, L->nseg, tmPct.ntiles, sig, stride, mn, mx, P, d_counts, d_cand, cap, d_ncand);
 		}
 	else if (B.nb <= 2)
 		k_pct_pass<true><<<grid, 256, 0, c->stream>>> (L->d, tmPct.d_base, L->nseg, tmPct.ntiles, sig, stride, mn, mx, B, d_counts, d_cand, cap, d_ncand);
@@ -1159,6 +1218,43 @@ __global__ void k_equal_range (const double* __restrict__ a, unsigned long long 
 	unsigned long long l2 = lo;
 	while (l2 < hi) { const unsigned long long mid = (l2 + hi) >> 1;  if (f64_key (a[mid]) <= k) l2 = mid + 1; else hi = mid; }
 	out[2 * i + 1] = l2;
+	}
+
+// One counting / compaction pass with its results on the host.  The FAST kernel is tried first; it also
+// counts the cells that are not finite, and if there are any the pass is repeated on the key path (which
+// treats +-inf as the limits say and counts the NaNs).
+static int pct_run_pass (gdsp_ctx* c, gdsp_layout* L, const TileMap& tmPct, const double* sig, uint32_t stride,
+                         double mn, double mx, const PctBounds& B, unsigned long long* d_counts,
+                         double* d_cand, unsigned long long cap, unsigned long long* d_ncand,
+                         std::vector<unsigned long long>& counts, unsigned long long* ncand, unsigned long long* nnan)
+	{
+	const int nreg = 2 * B.nb + 1;
+	counts.assign (nreg, 0);
+	for (int attempt = 0; attempt < 2; attempt++)
+		{
+		bool usedFast = false;
+		GDSP_CUDA (cudaMemsetAsync (d_counts, 0, sizeof (unsigned long long) * nreg, c->stream));
+		GDSP_CUDA (cudaMemsetAsync (d_ncand, 0, 32, c->stream));
+		GDSP_TRY (pct_launch_pass (c, L, tmPct, sig, stride, mn, mx, B, d_counts, d_cand, cap, d_ncand, attempt == 0, &usedFast));
+		unsigned long long four[4] = { 0, 0, 0, 0 };
+		GDSP_CUDA (cudaMemcpyAsync (counts.data (), d_counts, sizeof (unsigned long long) * nreg, cudaMemcpyDeviceToHost, c->stream));
+		GDSP_CUDA (cudaMemcpyAsync (four, d_ncand, 32, cudaMemcpyDeviceToHost, c->stream));
+		GDSP_CUDA (cudaStreamSynchronize (c->stream));
+		*ncand = four[0];  *nnan = four[1];
+		if (usedFast && four[1] != 0) continue;         // non-finite cells met by the FAST kernel: once more, on keys
+		if (usedFast)
+			for (int r = 0; r < B.nb; r++)
+				{
+				// DSETP saw -0.0 == +0.0; by key -0.0 lies below +0.0: move the -0.0 cells where their key puts them
+				const double d = host_unkey (B.key[r]);
+				if (d != 0.0) continue;
+				const unsigned long long negz = four[3];
+				if (!std::signbit (d)) { counts[2 * r] += negz;  counts[2 * r + 1] -= negz; }                   // bound +0.0
+				else { counts[2 * r + 2] += counts[2 * r + 1] - negz;  counts[2 * r + 1] = negz; }             // bound -0.0
+				}
+		break;
+		}
+	return GDSP_OK;
 	}
 
 struct PctJob
@@ -1328,16 +1424,13 @@ static int percentiles_impl (gdsp_ctx* c, const gdsp_layout* L_, const double* s
 
 		// ---- (3) the counting / compaction pass
 		const int nreg = 2 * B.nb + 1;
-		GDSP_CUDA (cudaMemsetAsync (d_counts, 0, sizeof (unsigned long long) * nreg, c->stream));
-		GDSP_CUDA (cudaMemsetAsync (d_ncand, 0, 16, c->stream));
-		GDSP_TRY (pct_launch_pass (c, L, tmPct, sig, stride, mn, mx, B, d_counts, bufA, candCapTotal, d_ncand));
-		std::vector<unsigned long long> counts (nreg);
-		unsigned long long ncandNan[2] = { 0, 0 };
-		GDSP_CUDA (cudaMemcpyAsync (counts.data (), d_counts, sizeof (unsigned long long) * nreg, cudaMemcpyDeviceToHost, c->stream));
-		GDSP_CUDA (cudaMemcpyAsync (ncandNan, d_ncand, 16, cudaMemcpyDeviceToHost, c->stream));
-		GDSP_CUDA (cudaStreamSynchronize (c->stream));
-		const unsigned long long ncand = ncandNan[0];
-		numNan = ncandNan[1];
+		std::vector<unsigned long long> counts;
+		unsigned long long ncand = 0;
+		{
+		unsigned long long nn = 0;
+		GDSP_TRY (pct_run_pass (c, L, tmPct, sig, stride, mn, mx, B, d_counts, bufA, candCapTotal, d_ncand, counts, &ncand, &nn));
+		numNan = nn;
+		}
 		unsigned long long total = 0;
 		for (int r = 0; r < nreg; r++) total += counts[r];
 		numSamples = total;  haveCount = true;
@@ -1770,14 +1863,9 @@ static int pct_count_impl (gdsp_ctx* c, const gdsp_layout* L_, const double* sig
 	unsigned long long* d_ncand  = (unsigned long long*) ws;
 	unsigned long long* d_counts = (unsigned long long*) ((char*) ws + 64);
 	const int nreg = 2 * nb + 1;
-	GDSP_CUDA (cudaMemsetAsync (d_counts, 0, sizeof (unsigned long long) * nreg, c->stream));
-	GDSP_CUDA (cudaMemsetAsync (d_ncand, 0, 16, c->stream));
-	GDSP_TRY (pct_launch_pass (c, L, tmPct, sig, stride, mn, mx, B, d_counts, d_cand, cap, d_ncand));
-	std::vector<unsigned long long> counts (nreg);
+	std::vector<unsigned long long> counts;
 	unsigned long long ncandNan[2] = { 0, 0 };
-	GDSP_CUDA (cudaMemcpyAsync (counts.data (), d_counts, sizeof (unsigned long long) * nreg, cudaMemcpyDeviceToHost, c->stream));
-	GDSP_CUDA (cudaMemcpyAsync (ncandNan, d_ncand, 16, cudaMemcpyDeviceToHost, c->stream));
-	GDSP_CUDA (cudaStreamSynchronize (c->stream));
+	GDSP_TRY (pct_run_pass (c, L, tmPct, sig, stride, mn, mx, B, d_counts, d_cand, cap, d_ncand, counts, &ncandNan[0], &ncandNan[1]));
 	for (int r = 0; r < nreg; r++) h_counts[r] = counts[r];
 	*h_ncand = ncandNan[0];
 	if (h_nan) *h_nan = ncandNan[1];
