@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgdsp_b200.so")
+# GDSP_LIB_PATH: a differently built copy of the library (kernel experiments: scripts/build_variant.sh)
+LIB_PATH = os.environ.get("GDSP_LIB_PATH") or os.path.join(_HERE, "lib", "libgdsp_b200.so")
 
 
 class GdspError(RuntimeError):

@@ -718,8 +718,11 @@ __device__ __forceinline__ void clf_mark_tile (const double* __restrict__ sig, d
 		}
 	}
 
+#ifndef GDSP_CLUMP_MARK_OCC
+#define GDSP_CLUMP_MARK_OCC 4
+#endif
 template <bool ABOVE>
-__global__ void __launch_bounds__(CL_THREADS, 4)
+__global__ void __launch_bounds__(CL_THREADS, GDSP_CLUMP_MARK_OCC)
 k_clump_mark (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg, uint64_t ntiles,
               const double* __restrict__ sig, double T, uint32_t minLength, double relLength,
               ClumpFast wk, ScanStatus<double> stMax)

@@ -233,6 +233,30 @@ __device__ __forceinline__ void stage_tile (double* smem, const double* __restri
 		const uint32_t j0 = (uint32_t) (g0 & 1);                 // first cell on a 16-byte boundary
 		const uint32_t npair = (count - j0) >> 1;
 		if (j0 && tid == 0) smem[stage_idx<PADSHIFT> (0)] = __ldg (p);
+#ifdef GDSP_STAGE_DEEP
+		// experiment (profiles/r2_*): four 128-bit loads in flight per thread before the first store
+		for (uint32_t q = tid; q < npair; q += 4 * nt)
+			{
+			double2 v[4];
+			#pragma unroll
+			for (int u = 0; u < 4; u++)
+				{
+				const uint32_t qq = q + u * nt;
+				if (qq < npair) v[u] = __ldg (reinterpret_cast<const double2*> (p + j0 + 2 * qq));
+				}
+			#pragma unroll
+			for (int u = 0; u < 4; u++)
+				{
+				const uint32_t qq = q + u * nt;
+				if (qq < npair)
+					{
+					const uint32_t j = j0 + 2 * qq;
+					smem[stage_idx<PADSHIFT> (j)]     = v[u].x;
+					smem[stage_idx<PADSHIFT> (j + 1)] = v[u].y;
+					}
+				}
+			}
+#else
 		for (uint32_t q = tid; q < npair; q += nt)
 			{
 			const uint32_t j = j0 + 2 * q;
@@ -240,6 +264,7 @@ __device__ __forceinline__ void stage_tile (double* smem, const double* __restri
 			smem[stage_idx<PADSHIFT> (j)]     = v.x;
 			smem[stage_idx<PADSHIFT> (j + 1)] = v.y;
 			}
+#endif
 		if (((count - j0) & 1) && tid == nt - 1) smem[stage_idx<PADSHIFT> (count - 1)] = __ldg (p + count - 1);
 		}
 	else
