@@ -34,6 +34,22 @@ def main():
     bits = lambda a: np.ascontiguousarray(a, np.float64).view(np.uint64)
     checked = [0]
 
+    # guard cells: every cell of the two signal buffers that belongs to no chromosome (the alignment pads
+    # between segments and the spare cells at the end) holds a canary; a kernel that writes one cell past a
+    # segment end -- the typical tile-edge bug -- destroys it.  (compute-sanitizer is closed on this GPU pool,
+    # so this and the oracle comparison are the memory-safety evidence we can produce; profiles/r2_sanitizer.md)
+    CANARY = -6.02214076e23
+    pad = torch.ones(g.buffer_cells, dtype=torch.bool, device=g.device)
+    for (lo, hi, *_r) in g.segs:
+        pad[lo:hi] = False
+    g._sig[pad] = CANARY
+    g.tmp[pad] = CANARY
+    n_guard = int(pad.sum())
+
+    def guards_intact(what):
+        for buf in (g._sig, g.tmp):
+            assert bool((buf[pad] == CANARY).all()), "a guard cell was overwritten during: " + what
+
     def load(kind="int"):
         ins = {}
         for name, n in chroms:
@@ -45,6 +61,7 @@ def main():
         for name, n in chroms:
             want = fn(ins[name].copy()); got = g.get_chrom(name)
             assert np.array_equal(bits(got), bits(want)), (what, name)
+        guards_intact(what)
         checked[0] += 1
 
     # accumulate: binned unit path, valued int path, valued fp64 path
@@ -118,6 +135,7 @@ def main():
     # clump: fast path, stored-prefix path
     for L in (10, 1000, 5000):
         ins = load(); g.clump(5.5, L); check(ins, lambda v: orc.clump(v, 5.5, L, True), "clump %d" % L)
+    guards_intact("the whole single-GPU suite")
     g.close()
     # slab pieces: halos, slab clump carries, slab percentile
     schroms = [("chr1", 40001), ("chr2", 16384), ("chr3", 777)]
@@ -169,7 +187,8 @@ def main():
     for gg in ranks:
         gg.close()
     torch.cuda.synchronize()
-    print("sanitizer suite: %d operator groups ran and matched the oracle" % (checked[0] + 5))
+    print("sanitizer suite: %d operator groups ran and matched the oracle; %d guard cells around the chromosomes intact in both buffers"
+          % (checked[0] + 5, n_guard))
 
 
 if __name__ == "__main__":
