@@ -173,6 +173,52 @@ def cpu_baseline_single(n=160_000_000):        # 10-20 s of single-core work
             "stage_gbps": {"accumulate": n / acc / 1e9, "smooth": n / smo / 1e9}}
 
 
+def cli_cfg1():
+    """BASELINE configs[0] through the drop-in CLI, text in and text out (genodsp_b200/bin/genodsp), beside the
+    reference binary when it is built: wall clock of the whole process, CUDA initialisation included."""
+    import hashlib
+    import tempfile
+    import numpy as np
+    ours = os.path.join(ROOT, "genodsp_b200", "bin", "genodsp")
+    ref = os.path.join(ROOT, "oracle", "_ref", "genodsp")
+    if not os.path.exists(ours):
+        return None
+    rng = np.random.default_rng(1)
+    n, m = 10_000_000, 1_000_000
+    cmd = ["--chromosomes=g.chroms", "--novalue", "=", "sum", "--window=101", "=", "localmax", "--neighborhood=11"]
+    out = {"workload": "one 10 Mbp chromosome, 1 M intervals, --novalue = sum --window=101 = localmax --neighborhood=11 (text to text)"}
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as d:
+        with open(os.path.join(d, "g.chroms"), "w") as f:
+            f.write("chr1 %d\n" % n)
+        st = np.sort(rng.integers(0, n - 150, m)); en = st + rng.integers(50, 151, m)
+        with open(os.path.join(d, "reads.iv"), "w") as f:
+            f.write("".join("chr1\t%d\t%d\n" % (a, b) for a, b in zip(st.tolist(), en.tolist())))
+        digests = {}
+        for name, binary in (("ours", ours), ("reference", ref)):
+            if not os.path.exists(binary):
+                continue
+            best = None
+            for rep in range(2):
+                t0 = time.perf_counter()
+                with open(os.path.join(d, "reads.iv"), "rb") as fin, open(os.path.join(d, "out.txt"), "wb") as fout:
+                    p = subprocess.run([binary] + cmd, stdin=fin, stdout=fout, stderr=subprocess.PIPE, cwd=d,
+                                       env=dict(os.environ, GENODSP_TIMING="1"))
+                dt = time.perf_counter() - t0
+                if p.returncode != 0:
+                    return {"error": p.stderr.decode(errors="replace")[-300:]}
+                best = dt if best is None else min(best, dt)
+            digests[name] = hashlib.md5(open(os.path.join(d, "out.txt"), "rb").read()).hexdigest()
+            out[name + "_s"] = round(best, 3)
+            if name == "ours":
+                out["ours_phases_s"] = {" ".join(l.split()[1:-2]): float(l.split()[-2])
+                                        for l in p.stderr.decode(errors="replace").splitlines() if l.startswith("[timing]")}
+        if len(digests) == 2:
+            out["identical_output"] = digests["ours"] == digests["reference"]
+    out["note"] = ("the CUDA driver's initialisation (cuInit + context: 1.0-2.3 s on this pool, scripts/micro/cuda_init_time.cu) is most of our "
+                   "wall clock on a 10 Mbp toy; hg38/16 text-to-text is in profiles/r2_cli_bench.log")
+    return out
+
+
 def run_reference_arm(args):
     """--impl reference: the reference's CPU path on all host cores (one process per core, each a
     bounded sample of the workload: the reference has no threads, chromosomes are its only
@@ -597,6 +643,12 @@ def run_gpu_arm(args):
                                     "bit_equal": ok, "pipelines": par}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_single()
+            try:
+                cli = cli_cfg1()
+                if cli is not None:
+                    line["stages"]["cli"] = {"cfg1": cli}
+            except Exception as e:                            # the CLI leg never takes the bench line down
+                line["stages"]["cli"] = {"error": repr(e)[:200]}
         print(json.dumps(line), flush=True)
     if dsp is not None:
         dsp.close()
