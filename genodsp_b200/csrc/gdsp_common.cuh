@@ -222,7 +222,9 @@ __device__ __forceinline__ void ldg_stream4 (const double* p, double& a, double&
 template <int PADSHIFT>
 __device__ __forceinline__ uint32_t stage_idx (uint32_t j) { return PADSHIFT ? j + (j >> PADSHIFT) : j; }
 
-template <int PADSHIFT>
+// DEEP: four 128-bit loads in flight per thread before the first store.  Measured on hg38 (profiles/round2_stages.md):
+// localmax 10.83 -> 10.12 ms, bestmax 14.96 -> 13.77 ms, but slidingsum 9.84 -> 10.16 ms -- so it is a per-kernel choice.
+template <int PADSHIFT, bool DEEP = false>
 __device__ __forceinline__ void stage_tile (double* smem, const double* __restrict__ in, int64_t g0, uint32_t count,
                                             uint64_t dlo, uint64_t dhi, double neutral)
 	{
@@ -233,8 +235,7 @@ __device__ __forceinline__ void stage_tile (double* smem, const double* __restri
 		const uint32_t j0 = (uint32_t) (g0 & 1);                 // first cell on a 16-byte boundary
 		const uint32_t npair = (count - j0) >> 1;
 		if (j0 && tid == 0) smem[stage_idx<PADSHIFT> (0)] = __ldg (p);
-#ifdef GDSP_STAGE_DEEP
-		// experiment (profiles/r2_*): four 128-bit loads in flight per thread before the first store
+		if (DEEP)
 		for (uint32_t q = tid; q < npair; q += 4 * nt)
 			{
 			double2 v[4];
@@ -256,7 +257,7 @@ __device__ __forceinline__ void stage_tile (double* smem, const double* __restri
 					}
 				}
 			}
-#else
+		else
 		for (uint32_t q = tid; q < npair; q += nt)
 			{
 			const uint32_t j = j0 + 2 * q;
@@ -264,7 +265,6 @@ __device__ __forceinline__ void stage_tile (double* smem, const double* __restri
 			smem[stage_idx<PADSHIFT> (j)]     = v.x;
 			smem[stage_idx<PADSHIFT> (j + 1)] = v.y;
 			}
-#endif
 		if (((count - j0) & 1) && tid == nt - 1) smem[stage_idx<PADSHIFT> (count - 1)] = __ldg (p + count - 1);
 		}
 	else

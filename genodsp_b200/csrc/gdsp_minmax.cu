@@ -58,7 +58,7 @@ k_extrema (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, i
 	const uint32_t count = nOut + Wn - 1;
 	const int64_t  g0   = (int64_t) t0 - (int64_t) reachL;
 
-	stage_tile<LOGE> (A, in, g0, count, sd.dlo, sd.dhi, NEUTRAL);
+	stage_tile<LOGE, true> (A, in, g0, count, sd.dlo, sd.dhi, NEUTRAL);
 	for (uint32_t j = count + threadIdx.x; j < SCAP; j += MM_THREADS) A[mm_pad<LOGE> (j)] = NEUTRAL;
 	__syncthreads ();
 
@@ -193,7 +193,7 @@ k_extrema_small (const SegDev* __restrict__ segs, const uint64_t* __restrict__ b
 	const uint32_t nOut = (uint32_t) ((sd.hi - t0 < MS_TILE) ? (sd.hi - t0) : MS_TILE);
 	const int64_t  g0   = (int64_t) t0 - (int64_t) reachL;      // staged cell j <-> in[g0 + j]
 
-	stage_tile<3> (s_x, in, g0, XN, sd.dlo, sd.dhi, NEUTRAL);
+	stage_tile<3, true> (s_x, in, g0, XN, sd.dlo, sd.dhi, NEUTRAL);
 	__syncthreads ();
 
 	// A[j] for the 8 cells of this thread, by doubling

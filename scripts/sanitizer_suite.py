@@ -46,6 +46,11 @@ def main():
     g.tmp[pad] = CANARY
     n_guard = int(pad.sum())
 
+    def rearm():
+        """percentile / sort use the partner buffer as dense scratch (pads included, by design): set the canaries again"""
+        g._sig[pad] = CANARY
+        g.tmp[pad] = CANARY
+
     def guards_intact(what):
         for buf in (g._sig, g.tmp):
             assert bool((buf[pad] == CANARY).all()), "a guard cell was overwritten during: " + what
@@ -118,20 +123,25 @@ def main():
         name, n = g.chroms[g.seg_chrom[k]]; sel = tseg == k
         v = ins[name].copy(); orc.add_intervals(v, ts[sel], te[sel], tv[sel], 1.0); orc.sorted_intervals(v, ts[sel], te[sel], tv[sel], 0, 0.0)
         assert np.array_equal(bits(g.get_chrom(name)), bits(v)), ("ivl", name)
+    guards_intact("interval-table chain")
     g.maxover(table); g.minover(table)
+    guards_intact("maxover / minover")
     table.close(); checked[0] += 1
     # percentile (selection, ranked counts, fill step), sort, collect permutation, runs, text formatter
     ins = load()
     got = g.percentile(10.0, 90.0, step=40.0)
     g.binarize(got["percentile50"])
     ins = load("real"); g.percentile(99.0); _ = g.sig; g.percentile_collect(7, 1.0, 1e9)
+    rearm()                                       # (selection, sort and collect used the partner buffer as dense scratch)
     ins = load(); g.binarize(6.0); r = g.runs()
+    guards_intact("binarize + runs")
     for name, n in chroms:
         rs, re, rv = orc.runs(orc.binarize(ins[name].copy(), 6.0))
         assert np.array_equal(r[name][0], rs) and np.array_equal(r[name][1], re), ("runs", name)
     from genodsp_b200.genome import format_runs
     format_runs(g, "chr1", r["chr1"][0], r["chr1"][1], r["chr1"][2], 3)
     g.text_roundtrip(); g.map_values([0.0, 1.0, 5.0], [1.0, 0.0, 2.0]); g.minmax(); checked[0] += 1
+    guards_intact("format / text round trip / map / minmax")
     # clump: fast path, stored-prefix path
     for L in (10, 1000, 5000):
         ins = load(); g.clump(5.5, L); check(ins, lambda v: orc.clump(v, 5.5, L, True), "clump %d" % L)
