@@ -284,7 +284,12 @@ class Pipelines:
         self.t, self.dist, self.g, self.plan, self.world, self.rank = torch, dist, g, plan, world, rank
         self.slab, self.capi, self.np = slab, capi, np
         self.seg_t, self.start_t, self.end_t = intervals
-        self.comm = slab.DistComm(dist, g.device) if world > 1 else slab.VirtualComm([g])
+        # N > 1: the library's own NCCL binding (gdsp_comm_*: halos by ncclSend/ncclRecv, counts by ncclAllReduce);
+        # GDSP_BENCH_TORCH_COMM=1 falls back to torch.distributed collectives for comparison
+        if world > 1:
+            self.comm = slab.DistComm(dist, g.device) if os.environ.get("GDSP_BENCH_TORCH_COMM") else slab.GdspComm(g, dist)
+        else:
+            self.comm = slab.VirtualComm([g])
         self.tableB = second_track(g, np)
         cap = max(1024, g.cells // 4)
         self.rbufs = (torch.empty(cap, dtype=torch.int32, device=g.device), torch.empty(cap, dtype=torch.int32, device=g.device),
@@ -293,17 +298,23 @@ class Pipelines:
         self.vars = {}
         self.known = None
         self.lengths = lengths
-        self.overlap = slab.OverlappedExchange(g, plan, dist, (WINDOW - 1) // 2) if world > 1 else None
+        self.overlap = slab.OverlappedExchange(g, plan, dist, (WINDOW - 1) // 2,
+                                               use_gdsp_comm=not os.environ.get("GDSP_BENCH_TORCH_COMM")) if world > 1 else None
         self.taps = None
 
     def close(self):
         self.tableB.close()
         if self.overlap is not None:
             self.overlap.close()
+        if hasattr(self.comm, "close"):
+            self.comm.close()
 
     def xch(self, radius):
         if self.world > 1:
-            self.slab.exchange_halos(self.g.sig, self.plan, self.dist, radius)
+            if hasattr(self.comm, "exchange"):
+                self.comm.exchange(self.g.sig, self.plan, radius)            # ncclSend/ncclRecv from C, stream-ordered
+            else:
+                self.slab.exchange_halos(self.g.sig, self.plan, self.dist, radius)
 
     # ---- operators
     def depth(self):
@@ -502,7 +513,7 @@ def run_gpu_arm(args):
     def step_e2e():
         g.accumulate_pinned(seg_h, start_h, end_h)
         if plan:
-            slab.exchange_halos(g.sig, plan, dist, h)
+            P.xch(h)
         g.smooth_to_host(WINDOW, out_h)        # FIR of piece k+1 overlaps the D2H of piece k
 
     step_e2e()
@@ -597,7 +608,7 @@ def run_gpu_arm(args):
                                    "--window=%d" % (total_bases, "" if args.scale == 1 else " (lengths / %d)" % args.scale,
                                                     n_iv_total, DEPTH, WINDOW),
                        "l2": "inputs larger than L2 (%.1f GB signal per GPU)" % (8.0 * per_gpu_bases / 1e9),
-                       "parallelism": ("slab x%d, halo %d cells exchanged over NCCL send/recv on a side stream behind the interior FIR"
+                       "parallelism": ("slab x%d, halo %d cells exchanged by ncclSend/ncclRecv (gdsp_comm_exchange_halos) on a side stream behind the interior FIR"
                                        % (world, h)) if world > 1 else "single GPU"},
             "clocks": clocks,
             "e2e": {"value": total_bases / (e2e_ms / 1e3) / 1e9, "unit": "Gbp/s",

@@ -20,6 +20,10 @@ class Seg(C.Structure):
                 ("pos0", C.c_uint32), ("chrom_len", C.c_uint32)]
 
 
+class Halo(C.Structure):
+    _fields_ = [("peer", C.c_int32), ("send_lo", C.c_uint64), ("send_hi", C.c_uint64), ("recv_lo", C.c_uint64), ("recv_hi", C.c_uint64)]
+
+
 class PwOp(C.Structure):
     _fields_ = [("code", C.c_int32), ("flags", C.c_uint32), ("a", C.c_double), ("b", C.c_double),
                 ("c", C.c_double), ("table", C.c_void_p)]
@@ -108,6 +112,18 @@ SIGNATURES = {
     "gdsp_clump_slab_trim": (_i, [_vp, _vp, _dp, C.POINTER(_i)]),
     "gdsp_clump_slab_emit": (_i, [_vp, _vp, C.POINTER(C.c_ubyte), C.POINTER(_i)]),
     "gdsp_clump_slab_destroy": (None, [_vp]),
+    "gdsp_comm_unique_id": (_i, [C.POINTER(C.c_ubyte)]),
+    "gdsp_comm_create": (_i, [_vp, C.POINTER(C.c_ubyte), _i, _i, C.POINTER(_vp)]),
+    "gdsp_comm_create_all": (_i, [C.POINTER(_vp), _i, C.POINTER(_vp)]),
+    "gdsp_comm_destroy": (None, [_vp]),
+    "gdsp_comm_rank": (_i, [_vp]),
+    "gdsp_comm_size": (_i, [_vp]),
+    "gdsp_comm_exchange_halos": (_i, [_vp, _vp, C.POINTER(Halo), _i]),
+    "gdsp_comm_exchange_halos_all": (_i, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.POINTER(Halo)), C.POINTER(_i), _i]),
+    "gdsp_comm_allreduce_sum_u64": (_i, [_vp, _u64p, _i]),
+    "gdsp_comm_allgather_f64": (_i, [_vp, _dp, _i, _dp]),
+    "gdsp_comm_allgather_dev": (_i, [_vp, _vp, _u64, _vp]),
+    "gdsp_comm_broadcast_f64": (_i, [_vp, _dp, _i, _i]),
     "gdsp_runs": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _u64, _u64p, _u64p]),
 }
 

@@ -1033,6 +1033,34 @@ __device__ __forceinline__ void pct_compact (bool c, double v, double* __restric
 		}
 	}
 
+// Candidates are staged per block in shared memory and leave with ONE global atomic per tile: with a
+// warp-aggregated atomic per candidate-holding warp, the 3.7 M candidates of a percentile-99 window on a
+// smoothed hg38 track all hit the single counter `ncand` and the pass took 7.0 ms instead of 4.0
+// (profiles/round2_stages.md).  A tile that holds more than PCT_STAGE candidates spills the rest directly.
+#define PCT_STAGE 1024
+__device__ __forceinline__ void pct_stage (bool c, double v, double* __restrict__ s_stage, unsigned int* __restrict__ s_n,
+                                           double* __restrict__ cand, unsigned long long cap, unsigned long long* __restrict__ ncand)
+	{
+	const int lane = threadIdx.x & 31;
+	const unsigned cm = __ballot_sync (0xffffffffu, c);
+	if (cm)
+		{
+		unsigned int b0 = 0;
+		if (lane == __ffs (cm) - 1) b0 = atomicAdd (s_n, (unsigned int) __popc (cm));
+		b0 = __shfl_sync (0xffffffffu, b0, __ffs (cm) - 1);
+		if (c)
+			{
+			const unsigned int slot = b0 + __popc (cm & ((1u << lane) - 1u));
+			if (slot < PCT_STAGE) s_stage[slot] = v;
+			else
+				{
+				const unsigned long long g = atomicAdd (ncand, 1ull);      // rare: more than PCT_STAGE candidates in one tile
+				if (g < cap) cand[g] = v;
+				}
+			}
+		}
+	}
+
 // MODE 0: key compares (any limits, any bounds); 1: FAST; 2: FAST with a zero bound;
 // 3 / 4: FAST for two bounds when nearly every cell lies below (3) / above (4) the window -- the percentile 99
 // and percentile 1 shape: one DSETP settles those cells, only the few others take the four compares
@@ -1045,9 +1073,14 @@ k_pct_pass_small (const SegDev* __restrict__ segs, const uint64_t* __restrict__ 
                   double* __restrict__ cand, unsigned long long cap, unsigned long long* __restrict__ ncand)
 	{
 	__shared__ unsigned int s_cnt[7];
+	__shared__ double s_stage[PCT_STAGE];
+	__shared__ unsigned int s_nstage;
+	__shared__ unsigned long long s_base;
 	if (threadIdx.x < 7) s_cnt[threadIdx.x] = 0;
+	if (threadIdx.x == 0) s_nstage = 0;
 	__syncthreads ();
 	PctAcc<NB> A;  A.clear ();
+	const bool compacting = (P.cmask != 0);
 
 	for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x)
 		{
@@ -1103,10 +1136,26 @@ k_pct_pass_small (const SegDev* __restrict__ segs, const uint64_t* __restrict__ 
 				if (__any_sync (0xffffffffu, any))
 					{
 					#pragma unroll
-					for (int u = 0; u < 8; u++) pct_compact (cc[u], v[u], cand, cap, ncand);
+					for (int u = 0; u < 8; u++) pct_stage (cc[u], v[u], s_stage, &s_nstage, cand, cap, ncand);
 					}
 				}
-			}
+						if (compacting)
+				{
+				// the tile's candidates leave together: one global atomic, coalesced stores
+				__syncthreads ();
+				const unsigned int ns = (s_nstage < PCT_STAGE) ? s_nstage : PCT_STAGE;
+				if (ns)
+					{
+					if (threadIdx.x == 0) s_base = atomicAdd (ncand, (unsigned long long) ns);
+					__syncthreads ();
+					for (unsigned int i = threadIdx.x; i < ns; i += 256)
+						{ const unsigned long long g = s_base + i;  if (g < cap) cand[g] = s_stage[i]; }
+					__syncthreads ();
+					if (threadIdx.x == 0) s_nstage = 0;
+					__syncthreads ();
+					}
+				}
+}
 		else
 			{
 			for (uint32_t j0 = 0; j0 < n; j0 += 256)

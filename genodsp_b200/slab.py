@@ -121,17 +121,24 @@ def halo_plan(sorted_lengths, world, rank, halo, align=1):
     return plan
 
 
-def _plan_ops(buf, plan, dist, radius):
-    ops = []
+def _plan_ranges(plan, radius):
+    """(peer, send_lo, send_hi, recv_lo, recv_hi) with only the `radius` cells nearest to each cut"""
+    out = []
     for peer, s_lo, s_hi, r_lo, r_hi in plan:
         left = (r_hi == s_lo)                    # the peer holds the cells before my first piece
         ns, nr = s_hi - s_lo, r_hi - r_lo
-        if radius is not None:                   # only the `radius` cells nearest to the cut travel
+        if radius is not None:
             ns, nr = min(ns, radius), min(nr, radius)
         if left:
-            s_a, s_b, r_a, r_b = s_lo, s_lo + ns, r_hi - nr, r_hi
+            out.append((peer, s_lo, s_lo + ns, r_hi - nr, r_hi))
         else:
-            s_a, s_b, r_a, r_b = s_hi - ns, s_hi, r_lo, r_lo + nr
+            out.append((peer, s_hi - ns, s_hi, r_lo, r_lo + nr))
+    return out
+
+
+def _plan_ops(buf, plan, dist, radius):
+    ops = []
+    for peer, s_a, s_b, r_a, r_b in _plan_ranges(plan, radius):
         if s_b > s_a:
             ops.append(dist.P2POp(dist.isend, buf[s_a:s_b], peer))
         if r_b > r_a:
@@ -161,12 +168,20 @@ class OverlappedExchange:
     send/recv on a side stream, launches `op` on the interior on the compute stream, makes the
     compute stream wait for the exchange, and launches `op` on the edges."""
 
-    def __init__(self, genome, plan, dist, radius):
+    def __init__(self, genome, plan, dist, radius, use_gdsp_comm=True):
         import ctypes as C
         from . import capi
         t = genome.torch
         self.g, self.plan, self.dist, self.radius = genome, plan, dist, int(radius)
         self.side = t.cuda.Stream(device=genome.device)
+        self.side_ctx, self.side_comm = None, None
+        if use_gdsp_comm:
+            # the library's NCCL binding on a context bound to the side stream: the exchange is enqueued from C
+            # (every rank creates it, also one whose slab cuts no chromosome: communicator creation is collective)
+            ctx = C.c_void_p()
+            capi.check(genome.lib.gdsp_ctx_create(genome.device.index, C.c_void_p(self.side.cuda_stream), C.byref(ctx)))
+            self.side_ctx = ctx
+            self.side_comm = GdspComm(genome, dist, ctx=ctx)
         inner, edge = [], []
         for k, (lo, hi, dlo, dhi, pos0, clen) in enumerate(genome.segs):
             a, b = lo, hi
@@ -195,6 +210,17 @@ class OverlappedExchange:
         t = self.g.torch
         main = t.cuda.current_stream(self.g.device)
         inner, edge = self.layouts
+        if self.side_comm is not None:
+            if self.plan:
+                self.side.wait_stream(main)                  # the cells to send are final
+                self.side_comm.exchange(self.g.sig, self.plan, self.radius)
+            if inner is not None:
+                op(inner)
+            if self.plan:
+                main.wait_stream(self.side)
+            if edge is not None:
+                op(edge)
+            return
         ops = _plan_ops(self.g.sig, self.plan, self.dist, self.radius)
         if ops:
             self.side.wait_stream(main)                      # the cells to send are final
@@ -215,6 +241,10 @@ class OverlappedExchange:
             if lay is not None:
                 self.g.lib.gdsp_layout_destroy(lay)
         self.layouts = []
+        if self.side_comm is not None:
+            self.side_comm.close(); self.side_comm = None
+        if self.side_ctx is not None:
+            self.g.lib.gdsp_ctx_destroy(self.side_ctx); self.side_ctx = None
 
 
 class DepthSmoothPipeline:
@@ -440,6 +470,79 @@ class DistComm:
 
     def gather(self, local):
         """small host objects (piece tables at set-up time only; never per-base data)"""
+        out = [None] * self.world
+        self.dist.all_gather_object(out, local[0])
+        return out
+
+
+class GdspComm:
+    """Combining layer for real ranks through the library's own NCCL binding (gdsp_comm_*, include/gdsp_b200.h):
+    halos by ncclSend/ncclRecv, counts by ncclAllReduce, samples / candidates / carries by ncclAllGather -- all
+    enqueued on the context's stream from C.  torch.distributed is only the launcher's store: it ships the
+    128-byte NCCL id once, and small host tables at set-up time."""
+
+    def __init__(self, genome, dist, ctx=None):
+        import ctypes as C
+        from . import capi
+        self.g, self.dist, self.C, self.capi = genome, dist, C, capi
+        self.t, self.device = genome.torch, genome.device
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.ctx = ctx if ctx is not None else genome.ctx
+        ids = [None]
+        if self.rank == 0:
+            buf = (C.c_ubyte * 128)()
+            capi.check(genome.lib.gdsp_comm_unique_id(buf))
+            ids = [bytes(buf)]
+        dist.broadcast_object_list(ids, src=0)
+        idbuf = (C.c_ubyte * 128)(*ids[0])
+        h = C.c_void_p()
+        capi.check(genome.lib.gdsp_comm_create(self.ctx, idbuf, self.world, self.rank, C.byref(h)))
+        self.handle = h
+
+    def close(self):
+        if self.handle:
+            self.g.lib.gdsp_comm_destroy(self.handle); self.handle = None
+
+    def local_ranks(self):
+        return [self.rank]
+
+    def exchange(self, sig, plan, radius=None):
+        """halo exchange on the communicator's stream (no host synchronisation)"""
+        rng = [r for r in _plan_ranges(plan, radius) if r[2] > r[1] or r[4] > r[3]]
+        if not rng:
+            return
+        arr = (self.capi.Halo * len(rng))()
+        for i, (peer, s_a, s_b, r_a, r_b) in enumerate(rng):
+            arr[i].peer, arr[i].send_lo, arr[i].send_hi, arr[i].recv_lo, arr[i].recv_hi = peer, s_a, s_b, r_a, r_b
+        self.capi.check(self.g.lib.gdsp_comm_exchange_halos(self.handle, self.C.c_void_p(sig.data_ptr()), arr, len(rng)))
+
+    def sum_i64(self, local):
+        a = _np.ascontiguousarray(local[0]).astype(_np.uint64)
+        self.capi.check(self.g.lib.gdsp_comm_allreduce_sum_u64(self.handle, a.ctypes.data_as(self.C.POINTER(self.C.c_uint64)), int(a.size)))
+        return a
+
+    def gather_f64(self, local):
+        a = _np.ascontiguousarray(local[0], _np.float64)
+        out = _np.empty(self.world * a.size, _np.float64)
+        dp = self.C.POINTER(self.C.c_double)
+        self.capi.check(self.g.lib.gdsp_comm_allgather_f64(self.handle, a.ctypes.data_as(dp), int(a.size), out.ctypes.data_as(dp)))
+        return out.reshape((self.world,) + a.shape)
+
+    def cat_f64(self, local, cap=None):
+        t = local[0]
+        counts = [int(c) for c in self.gather_f64([_np.array([float(t.numel())])]).reshape(-1)]
+        m = max(counts)
+        if m == 0:
+            return [self.t.empty(0, dtype=self.t.float64, device=self.device)]
+        buf = self.t.empty(m, dtype=self.t.float64, device=self.device)
+        buf[:t.numel()].copy_(t)
+        out = self.t.empty(self.world * m, dtype=self.t.float64, device=self.device)
+        self.capi.check(self.g.lib.gdsp_comm_allgather_dev(self.handle, self.C.c_void_p(buf.data_ptr()), int(m),
+                                                           self.C.c_void_p(out.data_ptr())))
+        out = out.view(self.world, m)
+        return [self.t.cat([out[r, :counts[r]] for r in range(self.world)])]
+
+    def gather(self, local):
         out = [None] * self.world
         self.dist.all_gather_object(out, local[0])
         return out

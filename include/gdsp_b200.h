@@ -400,6 +400,33 @@ int  gdsp_clump_slab_trim   (gdsp_clump_slab* cs, const double* sig, const doubl
 int  gdsp_clump_slab_emit   (gdsp_clump_slab* cs, double* sig, const unsigned char* h_cin, const int* h_allneg);
 void gdsp_clump_slab_destroy (gdsp_clump_slab* cs);
 
+/* ---- multi-GPU plumbing: NCCL under the C boundary ---------------------------------
+ * SURVEY 8(e) / BASELINE north_star: slab halos travel by NCCL send/recv, region counts and variables by NCCL
+ * all-reduce / broadcast.  A communicator belongs to one context (one GPU, one stream); the exchanges are
+ * enqueued on that stream.  One process per GPU: rank 0 calls gdsp_comm_unique_id, the 128 bytes reach the other
+ * ranks through the launcher (torchrun's store, MPI, a file), every rank calls gdsp_comm_create.  One process for
+ * all GPUs of a box (a multi-GPU C host): gdsp_comm_create_all (ncclCommInitAll) and the *_all exchange. */
+typedef struct gdsp_comm gdsp_comm;
+#define GDSP_COMM_ID_BYTES 128
+typedef struct gdsp_halo
+	{
+	int32_t  peer;               /* rank holding the neighbouring slab                         */
+	uint64_t send_lo, send_hi;   /* owned cells next to the cut, sent to the peer               */
+	uint64_t recv_lo, recv_hi;   /* halo cells filled with the peer's cells                     */
+	} gdsp_halo;
+int  gdsp_comm_unique_id  (unsigned char* id128);
+int  gdsp_comm_create     (gdsp_ctx* ctx, const unsigned char* id128, int nranks, int rank, gdsp_comm** out);
+int  gdsp_comm_create_all (gdsp_ctx** ctxs, int n, gdsp_comm** out /* n entries */);
+void gdsp_comm_destroy    (gdsp_comm* comm);
+int  gdsp_comm_rank       (const gdsp_comm* comm);
+int  gdsp_comm_size       (const gdsp_comm* comm);
+int  gdsp_comm_exchange_halos     (gdsp_comm* comm, double* sig, const gdsp_halo* plan, int nplan);
+int  gdsp_comm_exchange_halos_all (gdsp_comm** comms, double** sigs, const gdsp_halo* const* plans, const int* nplans, int n);
+int  gdsp_comm_allreduce_sum_u64  (gdsp_comm* comm, uint64_t* h_values, int n);               /* host in/out  */
+int  gdsp_comm_allgather_f64      (gdsp_comm* comm, const double* h_in, int n, double* h_out); /* host; size*n out */
+int  gdsp_comm_allgather_dev      (gdsp_comm* comm, const double* d_in, uint64_t n, double* d_out); /* device, async */
+int  gdsp_comm_broadcast_f64      (gdsp_comm* comm, double* h_values, int n, int root);        /* host in/out  */
+
 /* ---- run-length output ------------------------------------------------------
  * report_intervals, genodsp.c:1561-1691: maximal runs of raw-equal values
  * (every cell its own run when collapse==0); runs of value 0 are dropped
