@@ -334,3 +334,41 @@ def test_slab_clump_carries(world):
     finally:
         for g in ranks:
             g.close()
+
+
+def test_gdsp_comm_single_rank_collectives():
+    """the library's NCCL binding (gdsp_comm_*) with a one-rank communicator: every collective is the
+    identity, which checks the staging, the stream ordering and the ABI.  (The N > 1 path is exercised by
+    `bench.py --gpus N`, which compares every cell with the single-GPU run; NCCL refuses two ranks on one
+    device, so it cannot run in this single-GPU suite.)"""
+    import ctypes as C
+    from genodsp_b200 import capi
+    from genodsp_b200.genome import Genome
+    g = Genome([("chr1", 5000)])
+    try:
+        lib = g.lib
+        idbuf = (C.c_ubyte * 128)()
+        capi.check(lib.gdsp_comm_unique_id(idbuf))
+        h = C.c_void_p()
+        capi.check(lib.gdsp_comm_create(g.ctx, idbuf, 1, 0, C.byref(h)))
+        assert lib.gdsp_comm_rank(h) == 0 and lib.gdsp_comm_size(h) == 1
+        counts = np.array([3, 0, 2 ** 40 + 5, 7], dtype=np.uint64)
+        capi.check(lib.gdsp_comm_allreduce_sum_u64(h, counts.ctypes.data_as(C.POINTER(C.c_uint64)), 4))
+        assert counts.tolist() == [3, 0, 2 ** 40 + 5, 7]
+        vin = np.array([1.5, -2.0, np.pi]); vout = np.zeros(3)
+        dp = C.POINTER(C.c_double)
+        capi.check(lib.gdsp_comm_allgather_f64(h, vin.ctypes.data_as(dp), 3, vout.ctypes.data_as(dp)))
+        assert np.array_equal(vin, vout)
+        capi.check(lib.gdsp_comm_broadcast_f64(h, vin.ctypes.data_as(dp), 3, 0))
+        t = g.torch
+        a = t.arange(1000, dtype=t.float64, device=g.device); b = t.zeros_like(a)
+        capi.check(lib.gdsp_comm_allgather_dev(h, C.c_void_p(a.data_ptr()), 1000, C.c_void_p(b.data_ptr())))
+        g.sync()
+        assert bool(t.equal(a, b))
+        capi.check(lib.gdsp_comm_exchange_halos(h, C.c_void_p(g.sig.data_ptr()), None, 0))
+        bad = (capi.Halo * 1)()
+        bad[0].peer = 0                                   # a rank cannot exchange with itself
+        assert lib.gdsp_comm_exchange_halos(h, C.c_void_p(g.sig.data_ptr()), bad, 1) != 0
+        lib.gdsp_comm_destroy(h)
+    finally:
+        g.close()
