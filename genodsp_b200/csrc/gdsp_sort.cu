@@ -781,7 +781,7 @@ extern "C" int gdsp_fill_step (gdsp_ctx* c, const gdsp_layout* L_, double* sig, 
 // ---------------------------------------------------------------------------
 
 #define PCT_MAXB    256                 // window bounds handled per pass
-#define PCT_SAMPLES (1u << 20)
+#define PCT_SAMPLES (1u << 19)      // sample sort + candidate sort are ~equal at this size (profiles/round2_stages.md)
 
 struct SampleSpace
 	{
