@@ -542,11 +542,87 @@ k_bin_scatter (const SegDev* __restrict__ segs, const uint64_t* __restrict__ bas
 		}
 	}
 
-template <int LOG, int THREADS, int MODE>
+// ---------------------------------------------------------------------------
+// Fixed-capacity buckets (round 2): the count pass and the offset prefix disappear.  Every tile owns
+// CAP = 2^capLog record slots (CAP ~ 2.5x the mean number of records per tile); a read takes its slot with the
+// same warp-aggregated returning atomic as before, on a per-tile counter that starts at zero, and the net
+// start-minus-end count per tile (the tile's starting depth after the per-chromosome prefix) is kept in the
+// same pass -- only reads that cross a tile boundary touch it.  A record that finds its bucket full goes to a
+// small overflow list {tile, record}; the final kernel scans that list only in tiles whose counter says they
+// overflowed.  The host looks at the overflow count once: beyond BIN_OVF_MAX entries (a pile-up far above the
+// mean) the whole input takes the exact-size path above instead.
+// ---------------------------------------------------------------------------
+#define BIN_OVF_MAX 65536u
+
+template <int LOG>
+__global__ void __launch_bounds__(256)
+k_bin_scatter_fixed (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
+                     uint32_t* __restrict__ cursor, int* __restrict__ tileSum, uint32_t* __restrict__ recs, uint32_t capLog,
+                     uint32_t* __restrict__ ovf, uint32_t* __restrict__ ovfCount,
+                     const uint32_t* __restrict__ iseg, const uint32_t* __restrict__ istart,
+                     const uint32_t* __restrict__ iend, uint64_t n)
+	{
+	const uint64_t k = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t CAP = 1u << capLog;
+	BinGeom<LOG> g;
+	g.ok = false;  g.ta = g.tb = 0;
+	if (k < n) g.of (segs, base, nseg, iseg[k], istart[k], iend[k]);
+	const uint32_t pa = bin_reserve (cursor, g.ta, g.ok);
+	if (g.ok)
+		{
+		if (pa < CAP) recs[(g.ta << capLog) + pa] = g.rec_first ();
+		else
+			{
+			const uint32_t o = atomicAdd (ovfCount, 1u);
+			if (o < BIN_OVF_MAX) { ovf[2 * o] = (uint32_t) g.ta;  ovf[2 * o + 1] = g.rec_first (); }
+			}
+		if (!g.hasB) atomicAdd (tileSum + g.ta, 1);
+		else if (g.tb != g.ta) { atomicAdd (tileSum + g.ta, 1);  atomicAdd (tileSum + g.tb, -1); }
+		}
+	const bool second = g.has_second ();
+	if (__any_sync (0xffffffffu, second))
+		{
+		const uint32_t pb = bin_reserve (cursor, g.tb, second);
+		if (second)
+			{
+			if (pb < CAP) recs[(g.tb << capLog) + pb] = g.rec_second ();
+			else
+				{
+				const uint32_t o = atomicAdd (ovfCount, 1u);
+				if (o < BIN_OVF_MAX) { ovf[2 * o] = (uint32_t) g.tb;  ovf[2 * o + 1] = g.rec_second (); }
+				}
+			}
+		}
+	}
+
+// the two ways a record changes a tile's counters
+template <int LOG>
+__device__ __forceinline__ void bin_apply_own (int* s_cnt, uint32_t r)
+	{
+	constexpr uint32_t TILE = 1u << LOG;
+	const uint32_t kind = r >> 30, cell = (r >> LOG) & (TILE - 1), len = r & (TILE - 1);
+	if (kind == BIN_REC_END) atomicAdd (&s_cnt[cell], -1);
+	else
+		{
+		atomicAdd (&s_cnt[cell], 1);
+		if (kind == BIN_REC_SHORT && cell + len < TILE) atomicAdd (&s_cnt[cell + len], -1);
+		}
+	}
+template <int LOG>
+__device__ __forceinline__ void bin_apply_spill (int* s_cnt, uint32_t r)        // a record of the PREVIOUS tile
+	{
+	constexpr uint32_t TILE = 1u << LOG;
+	const uint32_t kind = r >> 30, cell = (r >> LOG) & (TILE - 1), len = r & (TILE - 1);
+	if (kind == BIN_REC_SHORT && cell + len >= TILE) atomicAdd (&s_cnt[cell + len - TILE], -1);
+	}
+
+// FIXED: `off` is the per-tile record counter and a tile's bucket starts at tile << capLog
+template <int LOG, int THREADS, int MODE, bool FIXED = false>
 __global__ void __launch_bounds__(THREADS)
 k_bin_final (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
              const uint32_t* __restrict__ off, const uint32_t* __restrict__ recs,
-             const int* __restrict__ tilePrefix, double* __restrict__ out)
+             const int* __restrict__ tilePrefix, double* __restrict__ out,
+             uint32_t capLog = 0, const uint32_t* __restrict__ ovf = NULL, const uint32_t* __restrict__ ovfCount = NULL)
 	{
 	constexpr uint32_t TILE  = 1u << LOG;
 	constexpr int      WARPS = THREADS / 32;
@@ -563,12 +639,37 @@ k_bin_final (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base,
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
 	// bucket bounds first: the loads are in flight while the counters are cleared
-	const uint32_t e0 = off[tile], e1 = off[tile + 1];
-	const uint32_t p0 = (tis > 0) ? off[tile - 1] : e0;     // previous tile of the same chromosome: [p0, e0)
+	uint32_t e0 = 0, e1 = 0, p0 = 0, nOwn = 0, nPrev = 0;
+	if (FIXED) { nOwn = off[tile];  nPrev = (tis > 0) ? off[tile - 1] : 0u; }
+	else
+		{
+		e0 = off[tile];  e1 = off[tile + 1];
+		p0 = (tis > 0) ? off[tile - 1] : e0;                // previous tile of the same chromosome: [p0, e0)
+		}
 	for (uint32_t i = threadIdx.x; i < TILE / 4; i += THREADS)
 		reinterpret_cast<int4*> (s_cnt)[i] = make_int4 (0, 0, 0, 0);
 	__syncthreads ();
 
+	if (FIXED)
+		{
+		const uint32_t CAP = 1u << capLog;
+		const uint32_t cOwn = (nOwn < CAP) ? nOwn : CAP, cPrev = (nPrev < CAP) ? nPrev : CAP;
+		const uint32_t* own  = recs + (tile << capLog);
+		const uint32_t* prev = recs + ((tile - (tis > 0 ? 1 : 0)) << capLog);
+		for (uint32_t i = threadIdx.x; i < cOwn; i += THREADS)  bin_apply_own<LOG> (s_cnt, __ldg (own + i));
+		for (uint32_t i = threadIdx.x; i < cPrev; i += THREADS) bin_apply_spill<LOG> (s_cnt, __ldg (prev + i));
+		if (nOwn > CAP || nPrev > CAP)                       // this tile or the one before it overflowed: the list holds their rest
+			{
+			const uint32_t no = (*ovfCount < BIN_OVF_MAX) ? *ovfCount : BIN_OVF_MAX;
+			for (uint32_t i = threadIdx.x; i < no; i += THREADS)
+				{
+				const uint32_t t = __ldg (ovf + 2 * i), r = __ldg (ovf + 2 * i + 1);
+				if (t == (uint32_t) tile) bin_apply_own<LOG> (s_cnt, r);
+				else if (tis > 0 && t == (uint32_t) (tile - 1)) bin_apply_spill<LOG> (s_cnt, r);
+				}
+			}
+		}
+	else
 	for (uint32_t i = p0 + threadIdx.x; i < e1; i += THREADS)
 		{
 		const uint32_t r = __ldg (recs + i);
@@ -736,6 +837,61 @@ static bool binned_fits (gdsp_layout* L, uint64_t buffer_cells, uint64_t n, bool
 	return bin_carve (NULL, ntiles, n, staging).total <= (size_t) buffer_cells * sizeof (int);
 	}
 
+// fixed-capacity buckets: returns *done = 0 (nothing written) when the buckets do not fit the work buffer or
+// more than BIN_OVF_MAX records overflowed; the caller then takes the exact-size path
+template <int LOG, int THREADS>
+static int accumulate_binned_fixed_t (gdsp_ctx* c, gdsp_layout* L, double* sig, void* work, size_t workBytes,
+                                      const uint32_t* d_seg, const uint32_t* d_start, const uint32_t* d_end,
+                                      uint64_t n, int addTo, int* done)
+	{
+	*done = 0;
+	if (getenv ("GDSP_ACCUMULATE_EXACT_BUCKETS")) return GDSP_OK;           // tests / A-B timing: the count + prefix path
+	TileMap tm;
+	GDSP_TRY (gdsp_layout_tilemap (L, 1u << LOG, &tm));
+	if (tm.ntiles == 0 || tm.ntiles >= 0xffffffffull) return GDSP_OK;
+	// CAP: a power of two >= 2x the mean number of records per tile (+ slack for short inputs), 64 .. 4096
+	const uint64_t mean = (n + n / 64 + tm.ntiles - 1) / tm.ntiles;
+	uint32_t capLog = 6;
+	while ((1ull << capLog) < 2 * mean + 32 && capLog < 12) capLog++;
+	const size_t tb = up256 ((tm.ntiles + 1) * sizeof (uint32_t));
+	const size_t need = up256 (((size_t) tm.ntiles << capLog) * sizeof (uint32_t)) + 3 * tb + 256 + up256 (2 * (size_t) BIN_OVF_MAX * sizeof (uint32_t));
+	if (need > workBytes) return GDSP_OK;
+	char* p = (char*) work;
+	uint32_t* recs   = (uint32_t*) p;   p += up256 (((size_t) tm.ntiles << capLog) * sizeof (uint32_t));
+	uint32_t* cursor = (uint32_t*) p;   p += tb;
+	int* tileSum     = (int*) p;        p += tb;
+	uint32_t* ovfCount = (uint32_t*) p; p += 256;
+	int* tilePrefix  = (int*) p;        p += tb;
+	uint32_t* ovf    = (uint32_t*) p;
+	GDSP_CUDA (cudaMemsetAsync (cursor, 0, 2 * tb + 256, c->stream));       // cursor, tileSum, ovfCount
+	const unsigned blocks = (unsigned) ((n + 255) / 256);
+	k_bin_scatter_fixed<LOG><<<blocks, 256, 0, c->stream>>> (L->d, tm.d_base, L->nseg, cursor, tileSum, recs, capLog, ovf, ovfCount,
+	                                                        d_seg, d_start, d_end, n);
+	GDSP_KERNEL_CHECK ();
+	void* hp;
+	GDSP_TRY (gdsp_host_scratch (c, 64, &hp));
+	uint32_t* h_ovf = (uint32_t*) hp;
+	GDSP_CUDA (cudaMemcpyAsync (h_ovf, ovfCount, sizeof (uint32_t), cudaMemcpyDeviceToHost, c->stream));
+	k_tile_prefix<int><<<L->nseg, 1024, 0, c->stream>>> (tm.d_base, tileSum, tilePrefix);
+	GDSP_KERNEL_CHECK ();
+	GDSP_CUDA (cudaStreamSynchronize (c->stream));
+	if (*h_ovf > BIN_OVF_MAX) return GDSP_OK;                               // a pile-up far above the mean: exact-size buckets
+	const int smem = (int) (sizeof (int) << LOG);
+	if (addTo)
+		{
+		GDSP_CUDA (cudaFuncSetAttribute (k_bin_final<LOG, THREADS, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+		k_bin_final<LOG, THREADS, 1, true><<<(unsigned) tm.ntiles, THREADS, smem, c->stream>>> (L->d, tm.d_base, L->nseg, cursor, recs, tilePrefix, sig, capLog, ovf, ovfCount);
+		}
+	else
+		{
+		GDSP_CUDA (cudaFuncSetAttribute (k_bin_final<LOG, THREADS, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+		k_bin_final<LOG, THREADS, 0, true><<<(unsigned) tm.ntiles, THREADS, smem, c->stream>>> (L->d, tm.d_base, L->nseg, cursor, recs, tilePrefix, sig, capLog, ovf, ovfCount);
+		}
+	GDSP_KERNEL_CHECK ();
+	*done = 1;
+	return GDSP_OK;
+	}
+
 template <int LOG, int THREADS>
 static int accumulate_binned_t (gdsp_ctx* c, gdsp_layout* L, double* sig, void* work,
                                 const uint32_t* d_seg, const uint32_t* d_start, const uint32_t* d_end,
@@ -769,11 +925,19 @@ static int accumulate_binned_t (gdsp_ctx* c, gdsp_layout* L, double* sig, void* 
 	return GDSP_OK;
 	}
 
+// fixedOffset: bytes at the start of `work` the fixed-capacity attempt must leave alone (the host entry point
+// stages the interval arrays there)
 static int accumulate_binned (gdsp_ctx* c, gdsp_layout* L, double* sig, uint64_t buffer_cells, void* work,
                               const uint32_t* d_seg, const uint32_t* d_start, const uint32_t* d_end,
-                              uint64_t n, int addTo)
+                              uint64_t n, int addTo, size_t fixedOffset = 0)
 	{
-	(void) buffer_cells;
+	int done = 0;
+	const size_t workBytes = (size_t) buffer_cells * sizeof (int);
+	fixedOffset = up256 (fixedOffset);
+	if (fixedOffset < workBytes)
+		GDSP_TRY ((accumulate_binned_fixed_t<BIN_LOG, BIN_THREADS> (c, L, sig, (char*) work + fixedOffset, workBytes - fixedOffset,
+		                                                            d_seg, d_start, d_end, n, addTo, &done)));
+	if (done) return GDSP_OK;
 	return accumulate_binned_t<BIN_LOG, BIN_THREADS> (c, L, sig, work, d_seg, d_start, d_end, n, addTo);
 	}
 
@@ -881,7 +1045,7 @@ extern "C" int gdsp_accumulate_host (gdsp_ctx* c, const gdsp_layout* L_, double*
 			}
 		if (!binned) GDSP_TRY (accumulate_chunk (c, L, work, at, d_seg, d_start, d_end, d_val, m, mode));
 		}
-	if (binned) return accumulate_binned (c, L, sig, buffer_cells, work, bc.seg, bc.start, bc.end, n, addTo);
+	if (binned) return accumulate_binned (c, L, sig, buffer_cells, work, bc.seg, bc.start, bc.end, n, addTo, bc.total);
 	return accumulate_finish (c, L, sig, work, at, mode, addTo);
 	}
 

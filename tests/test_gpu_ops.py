@@ -766,3 +766,59 @@ def test_percentile_collect_permutation(genome, kind, args):
     got = np.concatenate([genome.get_chrom(nm) for nm in names])
     bad = np.nonzero(bits(got) != bits(want))[0]
     assert bad.size == 0, (kind, args, n, bad[:8], got[bad[:8]], want[bad[:8]])
+
+
+@pytest.mark.parametrize("path", ["host", "dev"])
+@pytest.mark.parametrize("buckets", ["fixed", "exact"])
+@pytest.mark.parametrize("shape", ["uniform", "hot_tiles", "pileup"])
+def test_accumulate_fixed_capacity_buckets(orc, monkeypatch, path, buckets, shape):
+    """round 2: reads go straight into fixed-capacity tile buckets (no count pass, no offset prefix); a tile
+    that receives more than its capacity spills into a small overflow list that only the overflowing tiles
+    scan, and a pile-up beyond BIN_OVF_MAX records sends the whole input down the exact-size path.  All three
+    regimes, and the exact-size path forced by GDSP_ACCUMULATE_EXACT_BUCKETS, must give the reference loop's
+    depth (genodsp.c:1325-1329) bit for bit."""
+    import torch
+    from genodsp_b200.genome import Genome
+    if buckets == "exact":
+        monkeypatch.setenv("GDSP_ACCUMULATE_EXACT_BUCKETS", "1")
+    chroms = [("chrA", 3_000_001), ("chrB", 1_000_000), ("chrC", 8192)]
+    g = Genome(chroms)
+    try:
+        rng = np.random.default_rng({"uniform": 1, "hot_tiles": 2, "pileup": 3}[shape])
+        m = 400_000
+        seg = rng.integers(0, 2, m).astype(np.uint32)
+        lens = np.array([g.segs[k][5] for k in seg])
+        if shape == "uniform":
+            start = (rng.random(m) * (lens - 200)).astype(np.uint32)
+        elif shape == "hot_tiles":          # a tenth of the reads in three narrow regions: a few tiles at 10-30x the mean
+            start = (rng.random(m) * (lens - 200)).astype(np.uint32)
+            hot = rng.random(m) < 0.1
+            start[hot] = (rng.choice([100_000, 500_000, 777_777], int(hot.sum())) + rng.integers(0, 3000, int(hot.sum()))).astype(np.uint32)
+        else:                               # half of all reads inside one tile: far more than the overflow list holds
+            start = (rng.random(m) * (lens - 200)).astype(np.uint32)
+            hot = rng.random(m) < 0.5
+            start[hot] = (250_000 + rng.integers(0, 5000, int(hot.sum()))).astype(np.uint32)
+        end = (start + rng.integers(1, 200, m)).astype(np.uint32)
+        g.fill(3.0)
+        if path == "host":
+            g.accumulate(seg, start, end)
+        else:
+            t = [torch.from_numpy(a.astype(np.int64)).to(g.device).to(torch.int32) for a in (seg, start, end)]
+            g.accumulate(t[0], t[1], t[2], host=False)
+        for k in range(g.nseg):
+            name, n = g.chroms[g.seg_chrom[k]]
+            sel = seg == k
+            want = orc.accumulate(np.zeros(n), start[sel], end[sel], None)
+            got = g.get_chrom(name)
+            bad = np.nonzero(bits(got) != bits(want))[0]
+            assert bad.size == 0, (shape, buckets, path, name, bad[:5], got[bad[:5]], want[bad[:5]])
+        # and on top of an existing signal
+        before = {name: g.get_chrom(name) for name, _ in chroms}
+        if path == "host":
+            g.accumulate(seg, start, end, add=True)
+        else:
+            g.accumulate(t[0], t[1], t[2], host=False, add=True)
+        for name, n in chroms:
+            assert np.array_equal(g.get_chrom(name), 2 * before[name]), (shape, buckets, path, name)
+    finally:
+        g.close()
