@@ -1080,6 +1080,7 @@ k_pct_pass_small (const SegDev* __restrict__ segs, const uint64_t* __restrict__ 
 	if (threadIdx.x == 0) s_nstage = 0;
 	__syncthreads ();
 	PctAcc<NB> A;  A.clear ();
+	unsigned int sLt = 0, sLe = 0;                       // MODE 3 / 4: cells settled by the first compare
 	const bool compacting = (P.cmask != 0);
 
 	for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x)
@@ -1107,8 +1108,15 @@ k_pct_pass_small (const SegDev* __restrict__ segs, const uint64_t* __restrict__ 
 					for (int u = 0; u < 8; u++)
 						{
 						A.nan += ((unsigned int) __double2hiint (v[u]) & 0x7ff00000u) == 0x7ff00000u;
-						const bool settled = (MODE == 3) ? (v[u] < P.d0) : (v[u] > P.d1);
-						if (MODE == 3) A.negz += settled;           // (reused as "cells below the window" in this mode)
+						// settled: at or beyond the bound on the crowded side (heavy ties sit ON the bound: 99 % zeros
+						// under a percentile-99 window that starts at 0.0); two compares tell "beyond" from "on"
+						bool settled;
+						if (MODE == 3)
+							{
+							settled = (v[u] <= P.d0);  sLe += settled;  sLt += (v[u] < P.d0);
+							A.negz += (__double_as_longlong (v[u]) == (long long) 0x8000000000000000ull);
+							}
+						else { settled = (v[u] >= P.d1);  sLe += settled;  sLt += (v[u] > P.d1); }
 						rest[u] = !settled;  anyRest = anyRest || rest[u];
 						cc[u] = false;
 						}
@@ -1171,7 +1179,8 @@ k_pct_pass_small (const SegDev* __restrict__ segs, const uint64_t* __restrict__ 
 			}
 		}
 
-	if (MODE == 3) { A.lt0 += A.negz;  A.le0 += A.negz;  A.lt1 += A.negz;  A.le1 += A.negz;  A.negz = 0; }   // below the window: below every bound
+	if (MODE == 3) { A.lt0 += sLt;  A.le0 += sLe;  A.lt1 += sLe;  A.le1 += sLe; }   // at or below the first bound: below the second
+	if (MODE == 4) { A.le1 += sLe - sLt; }                                          // on the last bound; beyond it: in no cumulative count
 	unsigned int x[7] = { A.tot, A.lt0, A.le0, A.lt1, A.le1, A.nan, A.negz };
 	#pragma unroll
 	for (int r = 0; r < 7; r++)
@@ -1239,12 +1248,24 @@ static int pct_launch_pass (gdsp_ctx* c, gdsp_layout* L, const TileMap& tmPct, c
 			if (!(d == d) || d > DBL_MAX || d < -DBL_MAX) fast = false;
 			if (d == 0.0) zeroBounds++;
 			}
-		// a zero bound: fine while nothing is compacted (the heavy-ties case: the wanted value IS the bound)
-		if (zeroBounds > 1 || (zeroBounds == 1 && P.cmask != 0)) fast = false;
+		// a zero bound: -0.0 and +0.0 are one value to DSETP and two keys.  The counts are repaired on the host from the
+		// number of -0.0 cells; the compaction is only right when the zeros on the far side of the bound's key are
+		// not in a compacted region: bound +0.0 -> the region below it, bound -0.0 -> the region above it
+		int zeroAt = -1;
+		for (int r = 0; r < B.nb; r++) if (host_unkey (B.key[r]) == 0.0) zeroAt = r;
+		if (zeroBounds > 1) fast = false;
+		if (zeroBounds == 1)
+			{
+			const bool negZero = std::signbit (host_unkey (B.key[zeroAt]));
+			if (!negZero && ((P.cmask >> zeroAt) & 1u)) fast = false;
+			if (negZero && ((P.cmask >> (zeroAt + 1)) & 1u)) fast = false;
+			}
 		if (usedFast) *usedFast = fast;
 		if (sideHint > 0 && (P.cmask & 1u)) sideHint = 0;   // the settled side must not be a region that is compacted
 		if (sideHint < 0 && (P.cmask & 4u)) sideHint = 0;
-		if (fast && zeroBounds == 0 && B.nb == 2 && sideHint != 0)
+		if (sideHint < 0 && zeroBounds != 0) sideHint = 0;
+		if (sideHint > 0 && zeroBounds == 1 && zeroAt != 0) sideHint = 0;      // (the settled-side variant repairs a zero FIRST bound only)
+		if (fast && B.nb == 2 && sideHint != 0)
 			{
 			if (sideHint > 0) k_pct_pass_small<2, 3><<<grid, 256, 0, c->stream>>> (L->d, tmPct.d_base, L->nseg, tmPct.ntiles, sig, stride, mn, mx, P, d_counts, d_cand, cap, d_ncand);
 			else              k_pct_pass_small<2, 4><<<grid, 256, 0, c->stream>>> (L->d, tmPct.d_base, L->nseg, tmPct.ntiles, sig, stride, mn, mx, P, d_counts, d_cand, cap, d_ncand);

@@ -822,3 +822,35 @@ def test_accumulate_fixed_capacity_buckets(orc, monkeypatch, path, buckets, shap
             assert np.array_equal(g.get_chrom(name), 2 * before[name]), (shape, buckets, path, name)
     finally:
         g.close()
+
+
+@pytest.mark.parametrize("zeros", ["plus", "mixed"])
+def test_percentile_window_that_starts_on_a_zero_plateau(genome, orc, zeros):
+    """the cfg3 shape (`sum --window=100` leaves 99 % zeros): the percentile-99 window starts ON the zero plateau,
+    so the counting pass runs with a zero bound and nearly every cell tied with it -- with +0.0 only, and with
+    -0.0 mixed in (equal to DSETP, different keys)"""
+    rng = np.random.default_rng(5 if zeros == "plus" else 6)
+    inputs = {}
+    for name, n in CHROMS:
+        v = np.zeros(n)
+        k = max(1, n // 100)
+        v[rng.choice(n, k, replace=False)] = rng.integers(1, 2000, k) / 100.0
+        if zeros == "mixed":
+            z = np.flatnonzero(v == 0)
+            v[z[::3]] = -0.0
+        inputs[name] = v
+        genome.set_chrom(name, v)
+    names = [genome.chroms[i][0] for i in genome.order]
+    srt = orc.sort(np.concatenate([inputs[n] for n in names]).copy())
+    for p_str, p in (("98.5", 98500), ("99", 99000), ("99.2", 99200), ("50", 50000), ("99.9", 99900)):
+        got = genome.percentile(float(p_str), destructive=False)["percentile" + p_str]
+        want = srt[orc.percentile_rank(srt.size, p)]
+        assert got == want, (zeros, p_str, got, want)
+        # (which of -0.0 / +0.0 is reported inside a tie is a property of the key order: -0.0 first)
+        assert np.signbit(got) == np.signbit(want), (zeros, p_str)
+    got = genome.percentile(99.0, destructive=True)["percentile99"]
+    genome.binarize(got)
+    allv = np.concatenate([inputs[n] for n in names])
+    want_sorted = np.where(srt > got, 1.0, 0.0)
+    cat = np.concatenate([genome.get_chrom(n) for n in names])
+    assert np.array_equal(cat, want_sorted)
