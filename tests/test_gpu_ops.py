@@ -845,9 +845,7 @@ def test_percentile_window_that_starts_on_a_zero_plateau(genome, orc, zeros):
     for p_str, p in (("98.5", 98500), ("99", 99000), ("99.2", 99200), ("50", 50000), ("99.9", 99900)):
         got = genome.percentile(float(p_str), destructive=False)["percentile" + p_str]
         want = srt[orc.percentile_rank(srt.size, p)]
-        assert got == want, (zeros, p_str, got, want)
-        # (which of -0.0 / +0.0 is reported inside a tie is a property of the key order: -0.0 first)
-        assert np.signbit(got) == np.signbit(want), (zeros, p_str)
+        assert got == want, (zeros, p_str, got, want)      # (inside a tie of -0.0 / +0.0 the reference's qsort order is unspecified)
     got = genome.percentile(99.0, destructive=True)["percentile99"]
     genome.binarize(got)
     allv = np.concatenate([inputs[n] for n in names])
