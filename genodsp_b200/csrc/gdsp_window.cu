@@ -139,11 +139,14 @@ k_block_sum (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base,
 	uint32_t r = threadIdx.x / W, off = threadIdx.x - r * W;
 	const double* src = sig + g0;
 	// four loads in flight per thread (a loop with one load per trip leaves the memory system idle)
-	for (uint32_t j = threadIdx.x; j < count; j += 4 * BS_THREADS)
+#ifndef GDSP_BS_DEPTH
+#define GDSP_BS_DEPTH 4
+#endif
+	for (uint32_t j = threadIdx.x; j < count; j += GDSP_BS_DEPTH * BS_THREADS)
 		{
-		double v[4];
+		double v[GDSP_BS_DEPTH];
 		#pragma unroll
-		for (int u = 0; u < 4; u++)
+		for (int u = 0; u < GDSP_BS_DEPTH; u++)
 			{
 			const uint32_t ju = j + u * BS_THREADS;
 			if (readable) v[u] = (ju < count) ? __ldg (src + ju) : 0.0;
@@ -154,7 +157,7 @@ k_block_sum (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base,
 				}
 			}
 		#pragma unroll
-		for (int u = 0; u < 4; u++)
+		for (int u = 0; u < GDSP_BS_DEPTH; u++)
 			{
 			if (j + u * BS_THREADS < count) sm[r * rowS + off] = v[u];
 			off += dr;  r += dq;
