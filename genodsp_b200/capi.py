@@ -50,6 +50,7 @@ SIGNATURES = {
     "gdsp_sync": (_i, [_vp]),
     "gdsp_ctx_set_exact_order": (_i, [_vp, _i]),
     "gdsp_ctx_get_exact_order": (_i, [_vp]),
+    "gdsp_ctx_set_smooth_direct": (_i, [_vp, _i]),
     "gdsp_malloc_host": (_i, [C.c_size_t, C.POINTER(_vp)]),
     "gdsp_free_host": (_i, [_vp]),
     "gdsp_last_error": (C.c_char_p, []),

@@ -106,7 +106,12 @@ struct gdsp_ctx
 	void*        host_small;          // page-locked scratch for small device->host results (percentile samples)
 	size_t       host_small_bytes;
 	int          exact_order;         // gdsp_ctx_set_exact_order: sequential-order slidingsum / cumulativesum / clump
+	int          smooth_direct;       // gdsp_ctx_set_smooth_direct: always the direct FIR (k_smooth_ct), for A/B measurements
 	};
+
+// gdsp_smooth_sym.cu
+int gdsp_smooth_sym_plan (const gdsp_layout* L, const double* in, uint32_t W, const double* h_taps);
+int gdsp_smooth_sym_launch (gdsp_ctx* c, gdsp_layout* L, const double* in, double* out, uint32_t W, const double* h_taps);
 
 // gdsp_exact.cu
 int gdsp_cumulative_sum_exact (gdsp_ctx* c, gdsp_layout* L, const double* in, double* out);

@@ -1013,6 +1013,27 @@ struct PctAcc
 		if (NB >= 2) { o += b1 ? 0 : 1; isB = isB || (b1 && !a1); }
 		return !isB && ((P.cmask >> o) & 1u);
 		}
+	// The cells the settled-side variants (MODE 3 / 4) did not settle, two bounds.  Written out instead of calling
+	// add_fast: nvcc 12.9 folded add_fast's compares with the caller's `!(v <= d0)` into a compaction test that
+	// only cells BELOW the first bound could pass (SASS: the cmask test predicated on !(v >= d0)), so every
+	// candidate of a percentile-99 window was counted and none was compacted.
+	// add_above_first: v > d0 (or NaN, counted by the caller: the pass is then repeated on keys)
+	__device__ __forceinline__ bool add_above_first (const PctSmall& P, double v)
+		{
+		const bool a1 = v < P.d1, e1 = (v == P.d1);
+		lt1 += a1;  le1 += (a1 || e1);
+		const unsigned int bit = a1 ? 2u : 4u;                 // open region 1 (inside the window) or 2 (above it)
+		return !e1 && (P.cmask & bit) != 0;
+		}
+	// add_below_last: v < d1 (or NaN)
+	__device__ __forceinline__ bool add_below_last (const PctSmall& P, double v)
+		{
+		const bool a0 = v < P.d0, e0 = (v == P.d0), in1 = v > P.d0;
+		lt0 += a0;  le0 += (a0 || e0);
+		lt1 += (a0 || e0 || in1);  le1 += (a0 || e0 || in1);   // every ordered cell here lies below the last bound
+		const unsigned int bit = a0 ? 1u : 2u;                 // open region 0 (below the window) or 1 (inside it)
+		return (a0 || in1) && (P.cmask & bit) != 0;
+		}
 	};
 
 __device__ __forceinline__ void pct_compact (bool c, double v, double* __restrict__ cand, unsigned long long cap,
@@ -1124,7 +1145,7 @@ k_pct_pass_small (const SegDev* __restrict__ segs, const uint64_t* __restrict__ 
 						{
 						#pragma unroll
 						for (int u = 0; u < 8; u++)
-							if (rest[u]) { cc[u] = A.template add_fast<false, false> (P, v[u]);  any = any || cc[u]; }
+							if (rest[u]) { cc[u] = (MODE == 3) ? A.add_above_first (P, v[u]) : A.add_below_last (P, v[u]);  any = any || cc[u]; }
 						}
 					}
 				else

@@ -573,6 +573,10 @@ extern "C" int gdsp_smooth (gdsp_ctx* c, const gdsp_layout* L_, const double* in
 	GDSP_REQUIRE_ALIGNED (out, "gdsp_smooth");
 	GDSP_REQUIRE (W >= 1, "gdsp_smooth: window must be positive");
 	TileMap tm;
+	// symmetric window (the reference's Hann window always is): every product of a tap pair computed once,
+	// same summation order (gdsp_smooth_sym.cu)
+	if (!c->smooth_direct && gdsp_smooth_sym_plan (L, in, W, h_taps))
+		return gdsp_smooth_sym_launch (c, L, in, out, W, h_taps);
 	if (W <= SC_MAXW)
 		{
 		SmoothTaps tp;                          // by-value kernel parameter (copied at launch)

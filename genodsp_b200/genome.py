@@ -236,13 +236,21 @@ class Genome:
                                         int(window), float(denom)))
         self._swap()
 
-    def smooth(self, window=101):
+    def smooth(self, window=101, direct=False):
+        """direct=True forces the direct FIR kernel (gdsp_ctx_set_smooth_direct); the default lets gdsp_smooth
+        use the shared-product kernel for symmetric windows -- both give the same bits"""
         W = int(window)
         if W % 2 == 0:
             W += 1                                  # sum.c:565-570
         taps = hann_taps(W)
-        check(self.lib.gdsp_smooth(self.ctx, self.layout, self._p(self.sig), self._p(self.tmp), W,
-                                   taps.ctypes.data_as(C.POINTER(C.c_double))))
+        if direct:
+            check(self.lib.gdsp_ctx_set_smooth_direct(self.ctx, 1))
+        try:
+            check(self.lib.gdsp_smooth(self.ctx, self.layout, self._p(self.sig), self._p(self.tmp), W,
+                                       taps.ctypes.data_as(C.POINTER(C.c_double))))
+        finally:
+            if direct:
+                check(self.lib.gdsp_ctx_set_smooth_direct(self.ctx, 0))
         self._swap()
 
     def _ensure_piece_layouts(self):

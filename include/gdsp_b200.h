@@ -76,6 +76,10 @@ int  gdsp_sync         (gdsp_ctx* ctx);
  * human genome).  Whole chromosomes only. */
 int  gdsp_ctx_set_exact_order (gdsp_ctx* ctx, int on);
 int  gdsp_ctx_get_exact_order (const gdsp_ctx* ctx);
+/* gdsp_smooth picks between two bit-identical kernels: the direct FIR (2W FP64 instructions per base) and, for
+ * the bit-symmetric windows the reference builds (sum.c:641), one that computes the product of a tap pair once
+ * (3(W-1)/2 + 2 per base).  `on` forces the direct FIR -- for A/B timing and parity tests of both. */
+int  gdsp_ctx_set_smooth_direct (gdsp_ctx* ctx, int on);
 /* page-locked host memory (device<->host copies from it run at full PCIe speed) */
 int  gdsp_malloc_host (size_t bytes, void** out);
 int  gdsp_free_host   (void* p);

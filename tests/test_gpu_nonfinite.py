@@ -118,8 +118,9 @@ def test_runs_nonfinite(genome, orc, kind, collapse, show):
 
 
 @pytest.mark.parametrize("kind", NONFINITE_KINDS)
-@pytest.mark.parametrize("W", [3, 101])
+@pytest.mark.parametrize("W", [3, 55, 101])
 def test_smooth_and_block_sum_nonfinite(genome, orc, kind, W):
+    """(W = 55 and 101 run the shared-product kernel, 3 the direct FIR)"""
     inputs = load(genome, W, kind)
     genome.smooth(W)
     check(genome, inputs, lambda v: orc.smooth(v, W), "smooth %d %s" % (W, kind))

@@ -286,10 +286,23 @@ def test_block_sum_whole_chromosome(genome, orc, kind):
 
 @pytest.mark.parametrize("kind", KINDS)
 @pytest.mark.parametrize("W", [3, 11, 101, 513, 1001])
-def test_smooth_bit_exact(genome, orc, kind, W):
+@pytest.mark.parametrize("direct", [False, True])
+def test_smooth_bit_exact(genome, orc, kind, W, direct):
+    """both kernels behind gdsp_smooth: the shared-product one (k_smooth_sym, the default for the reference's
+    symmetric windows) and the direct FIR (k_smooth_ct)"""
     inputs = load(genome, np.random.default_rng(W), kind)
-    genome.smooth(W)
+    genome.smooth(W, direct=direct)
     # chromosomes shorter than the window hit the reference's u32 wrap (sum.c:657); the oracle defines them
+    compare(genome, inputs, lambda v: orc.smooth(v, W), exact=True, what="smooth W=%d" % W)
+
+
+@pytest.mark.parametrize("W", [5, 7, 9, 13, 15, 17, 19, 21, 23, 31, 51, 53, 55, 77, 91, 93, 95, 97, 99, 103, 151])
+def test_smooth_shared_product_widths(genome, orc, W):
+    """k_smooth_sym holds (W-1)/2 pair accumulators per side in registers: every alignment class of the
+    stream lead ((W-1)/2 mod 4 decides how long a finished output waits for its aligned store), the widest
+    window it takes (101, in test_smooth_bit_exact) and the first ones it leaves to the direct FIR (7, 103)"""
+    inputs = load(genome, np.random.default_rng(W), "real")
+    genome.smooth(W)
     compare(genome, inputs, lambda v: orc.smooth(v, W), exact=True, what="smooth W=%d" % W)
 
 
@@ -690,7 +703,7 @@ def test_sort_genome_real_values(genome):
 
 
 def test_smooth_many_tiles_per_cta(orc):
-    """more tiles than resident CTAs: exercises the double-buffered TMA pipeline of k_smooth_pipe"""
+    """chromosomes of many strips / tiles, one shorter than every window"""
     from genodsp_b200.genome import Genome
     chroms = [("big", 2500000), ("mid", 1300000 + 7), ("tiny", 50)]
     g = Genome(chroms)
