@@ -37,10 +37,11 @@ DEPTH = 5
 READ_MIN, READ_MAX = 50, 150
 FP64_NOMINAL = 148 * 64 * 1.965e9      # FP64 lanes * SMs * max SM clock (instructions/s)
 FP64_MEASURED = 1.745e13               # scripts/micro/fp64_peak.cu on this pool's B200 (gpurun, round 1)
-SMOOTH_TRAFFIC_BYTES_PER_BASE = 15.99   # (24.71 GB read + 24.67 GB written) / 3,088,269,832 bases: ncu --set full
-SMOOTH_TRAFFIC_SOURCE = "profiles/r1_bench_kernels_ncu_full.csv"
-ACC_MOVED_BYTES_PER_BASE = 9.58         # 29.6 GB per accumulate launch set (k_bin_count/_offsets/_scatter/_final) / 3,088,269,832 bases
-ACC_MOVED_SOURCE = "ncu constant, profiles/r1_bench_kernels_ncu_full.csv (DRAM read + written by the four k_bin_* kernels)"
+FP64_PER_BASE = 3 * ((WINDOW - 1) // 2) + 2   # k_smooth_sym: one DMUL + two DADD per symmetric tap pair, DMUL + DADD for the centre
+SMOOTH_TRAFFIC_BYTES_PER_BASE = 16.27   # k_smooth_sym<50>: (25.92 GB read + 24.33 GB written) / 3,088,269,832 bases (strip ramps re-read 1.3 %)
+SMOOTH_TRAFFIC_SOURCE = "profiles/r2_bench_launches.csv"
+ACC_MOVED_BYTES_PER_BASE = 9.0          # 27.8 GB per accumulate launch set (k_bin_scatter_fixed 2.50 GB, k_bin_final 25.29 GB) / 3,088,269,832 bases
+ACC_MOVED_SOURCE = "ncu constant, profiles/r2_bench_launches.csv (DRAM read + written by k_bin_scatter_fixed, k_tile_prefix, k_bin_final)"
 METRIC = "Gbp/s, hg38 depth accumulation + smooth --window=101 (fp64)"
 
 
@@ -619,7 +620,7 @@ def run_gpu_arm(args):
         peak, peak_src = measured_hbm_peak()
         per_gpu_bases = total_bases / world
         smooth_gbs = 16.0 * per_gpu_bases / (smo_ms / 1e3) / 1e9
-        fp64_rate = 2.0 * WINDOW * per_gpu_bases / (smo_ms / 1e3)
+        fp64_rate = FP64_PER_BASE * per_gpu_bases / (smo_ms / 1e3)
         acc_bytes = 16.0 * per_gpu_bases + 28.0 * n_iv_total / world
         acc_moved = ACC_MOVED_BYTES_PER_BASE * per_gpu_bases
         pipes = {}
@@ -655,11 +656,11 @@ def run_gpu_arm(args):
                                       "frac_hbm_on_moved_bytes": acc_moved / (acc_ms / 1e3) / 1e9 / peak},
                        "smooth": {"ms": smo_ms, "gbp_s": total_bases / (smo_ms / 1e3) / 1e9,
                                   "achieved_gbs": smooth_gbs, "frac_hbm": smooth_gbs / peak,
-                                  "fp64_instr_per_base": 2 * WINDOW,
-                                  "fp64_lane_ops_per_s": 2 * WINDOW * per_gpu_bases / (smo_ms / 1e3),
+                                  "fp64_instr_per_base": FP64_PER_BASE,
+                                  "fp64_lane_ops_per_s": FP64_PER_BASE * per_gpu_bases / (smo_ms / 1e3),
                                   "includes": "halo exchange (side stream) + interior + edge launches" if world > 1 else "one launch"},
                        "pipelines": pipes},
-            "roofline": {"kernel": "k_smooth_ct", "bound": "fp64_issue", "achieved": smooth_gbs, "peak": peak, "unit": "GB/s",
+            "roofline": {"kernel": "k_smooth_sym<50>", "bound": "fp64_issue", "achieved": smooth_gbs, "peak": peak, "unit": "GB/s",
                          "frac": smooth_gbs / peak,
                          "traffic": SMOOTH_TRAFFIC_BYTES_PER_BASE * per_gpu_bases if SMOOTH_TRAFFIC_BYTES_PER_BASE else None,
                          "traffic_source": "ncu constant (dram__bytes_read.sum + dram__bytes_write.sum per base, %s), not measured in this run" % SMOOTH_TRAFFIC_SOURCE,
@@ -669,8 +670,9 @@ def run_gpu_arm(args):
                                            "peak_measured": FP64_MEASURED, "frac_measured": fp64_rate / FP64_MEASURED,
                                            "peak_measured_source": "scripts/micro/fp64_peak.cu (DMUL+DADD, constant-bank operand)"},
                          "note": "`achieved`/`frac` are the contract's HBM figures (16 B/bp algorithmic); the exact-order FIR needs "
-                                 "2*W=202 separately rounded FP64 instructions per base, so FP64 issue (64 lanes/SM), not HBM, is the "
-                                 "binding limit for W=101: see binding_limit"},
+                                 "separately rounded FP64 multiplies and adds -- 2*W = 202 per base done directly, 3*(W-1)/2+2 = 152 with the "
+                                 "product of each symmetric tap pair computed once (k_smooth_sym, round 2) -- so FP64 issue (64 lanes/SM), "
+                                 "not HBM, is the binding limit for W=101: see binding_limit"},
         }
         line["config"]["step"] = ("two-stream pipeline over %d chromosome groups: accumulate(group k+1) on a high-priority side stream "
                                   "behind smooth(group k); stage times are sums of per-launch durations and overlap" % args.groups) \

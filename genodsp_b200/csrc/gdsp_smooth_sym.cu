@@ -23,7 +23,7 @@
 // integer pipe); unrolling by h instead would need no moves and 125 KB of code.  Taps are read from the
 // constant bank (the kernel parameter), the thread's 4 input cells per block arrive with one 256-bit load
 // (next block in flight), its 4 outputs leave with one 256-bit store: no shared memory, no barriers, no
-// shuffles.  scripts/dbg/smooth_sym_model.py is a CPU model of the accumulator schedule.
+// shuffles.  scripts/smooth_sym_model.py is a CPU model of the accumulator schedule.
 //
 // (A first design dealt the pairs out to T lanes per strip with shuffles handing the accumulators on; on
 // B200 it never beat the direct FIR: 8-byte loads/stores per lane saturated the L1 data pipe, staging through
@@ -72,6 +72,18 @@ __device__ __forceinline__ void sym_fetch (const double* __restrict__ pin, uint3
 	asm volatile ("cp.async.commit_group;" ::: "memory");
 	}
 
+// Narrow windows are HBM-bound and their threads have registers to spare: one 256-bit load straight into registers,
+// the next block's in flight (hg38 W = 31: 10.9 ms against 12.6 ms through the ring)
+__device__ __forceinline__ void sym_load4 (const double* __restrict__ pin, uint32_t n, uint32_t nLo, uint32_t nHi, double (&v)[4])
+	{
+	if (n >= nLo && n + 4 <= nHi) ldg_stream4 (pin + n, v[0], v[1], v[2], v[3]);
+	else
+		{
+		#pragma unroll
+		for (int u = 0; u < 4; u++) v[u] = (n + u >= nLo && n + u < nHi) ? __ldg (pin + n + u) : 0.0;
+		}
+	}
+
 template <int U>
 __device__ __forceinline__ void sym_store (double* __restrict__ pout, uint32_t n, uint32_t out0, uint32_t out1, const double (&e)[U])
 	{
@@ -103,7 +115,8 @@ k_smooth_sym (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base
 	// taps beyond the uniform register file are read from shared memory (a broadcast LDS per use): ptxas keeps every
 	// tap of the loop in a uniform register and, past 63 of them, spills those into the registers the accumulators need
 	__shared__ double s_w[(K > KUNI) ? K - KUNI : 1];
-	__shared__ __align__(16) double s_ring[SY_PD][SY_THREADS][U];
+	constexpr bool RING = (K > 24);                // input through the cp.async ring (else straight into registers)
+	__shared__ __align__(16) double s_ring[RING ? SY_PD : 1][RING ? SY_THREADS : 1][U];
 	if (K > KUNI)
 		{
 		for (int i = threadIdx.x; i < K - KUNI; i += SY_THREADS) s_w[i] = tp.w[KUNI + i];
@@ -141,21 +154,29 @@ k_smooth_sym (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base
 	// prefetch ring: SY_PD blocks in flight, slot (block mod SY_PD) of this thread
 	const unsigned int ring = (unsigned int) __cvta_generic_to_shared (&s_ring[0][threadIdx.x][0]);
 	constexpr unsigned int SLOT = SY_THREADS * U * 8;
-	#pragma unroll
-	for (int q = 0; q < SY_PD; q++) sym_fetch<U> (pin, q * U, nLo, nHi, ring + q * SLOT);
+	double cur[4], nxt[4];                         // (U = 4 whenever the ring is not used)
+	if (RING)
+		{
+		#pragma unroll
+		for (int q = 0; q < SY_PD; q++) sym_fetch<U> (pin, q * U, nLo, nHi, ring + q * SLOT);
+		}
+	else sym_load4 (pin, 0, nLo, nHi, cur);
 	unsigned int q = 0;
 	for (uint32_t n = 0; n < total; n += U)
 		{
-		double cur[U];
-		asm volatile ("cp.async.wait_group %0;" :: "n"(SY_PD - 1) : "memory");
-		if (U == 4)
+		if (RING)
 			{
-			asm volatile ("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(cur[0]), "=d"(cur[1]) : "r"(ring + q * SLOT) : "memory");
-			asm volatile ("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(cur[U - 2]), "=d"(cur[U - 1]) : "r"(ring + q * SLOT + 16u) : "memory");
+			asm volatile ("cp.async.wait_group %0;" :: "n"(SY_PD - 1) : "memory");
+			if (U == 4)
+				{
+				asm volatile ("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(cur[0]), "=d"(cur[1]) : "r"(ring + q * SLOT) : "memory");
+				asm volatile ("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(cur[2]), "=d"(cur[3]) : "r"(ring + q * SLOT + 16u) : "memory");
+				}
+			else asm volatile ("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(cur[0]), "=d"(cur[1]) : "r"(ring + q * SLOT) : "memory");
+			sym_fetch<U> (pin, n + SY_PD * U, nLo, nHi, ring + q * SLOT);
+			q = (q + 1) & (SY_PD - 1);
 			}
-		else asm volatile ("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(cur[0]), "=d"(cur[1]) : "r"(ring + q * SLOT) : "memory");
-		sym_fetch<U> (pin, n + SY_PD * U, nLo, nHi, ring + q * SLOT);
-		q = (q + 1) & (SY_PD - 1);
+		else sym_load4 (pin, n + U, nLo, nHi, nxt);
 		double fin[U];
 		#pragma unroll
 		for (int u = 0; u < U; u++)
@@ -202,6 +223,11 @@ k_smooth_sym (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base
 			for (int i = 0; i < DELAY; i++) hist[i] = nh[i];
 			}
 		sym_store<U> (pout, n, out0, out1, em);
+		if (!RING)
+			{
+			#pragma unroll
+			for (int u = 0; u < 4; u++) cur[u] = nxt[u];
+			}
 		}
 	}
 

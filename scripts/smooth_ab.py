@@ -1,7 +1,7 @@
 """A/B timing of gdsp_smooth's two kernels on the hg38 layout (CUDA events, after warm-up).
 usage: smooth_ab.py <scale> <W[:T,K]> ...   (T,K: forced split of the shared-product kernel, GDSP_SYM_TK)"""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench, torch
 from genodsp_b200.genome import Genome
