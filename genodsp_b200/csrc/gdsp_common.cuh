@@ -284,6 +284,38 @@ __device__ __forceinline__ void stage_tile (double* smem, const double* __restri
 		}
 	}
 
+// Asynchronous variant: the cells go to shared memory with 8-byte cp.async (no registers in between), so that a
+// persistent block can have its NEXT tile in flight while it works on the current one.  The caller commits the
+// group, and waits + __syncthreads() before reading.  Tiles that leave the readable range are staged with plain
+// loads and stores (they are the first / last tile of a chromosome).
+__device__ __forceinline__ void cp_async_commit () { asm volatile ("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait () { asm volatile ("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+template <int PADSHIFT>
+__device__ __forceinline__ void stage_tile_async (double* smem, const double* __restrict__ in, int64_t g0, uint32_t count,
+                                                  uint64_t dlo, uint64_t dhi, double neutral)
+	{
+	const uint32_t tid = threadIdx.x, nt = blockDim.x;
+	if (g0 >= (int64_t) dlo && g0 + (int64_t) count <= (int64_t) dhi)
+		{
+		const double* p = in + g0;
+		const unsigned int s0 = (unsigned int) __cvta_generic_to_shared (smem);
+		for (uint32_t j = tid; j < count; j += nt)
+			asm volatile ("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(s0 + 8u * stage_idx<PADSHIFT> (j)), "l"(p + j) : "memory");
+		}
+	else
+		{
+		for (uint32_t j = tid; j < count; j += nt)
+			{
+			const int64_t g = g0 + (int64_t) j;
+			double v = neutral;
+			if (g >= (int64_t) dlo && g < (int64_t) dhi) v = __ldg (in + g);
+			smem[stage_idx<PADSHIFT> (j)] = v;
+			}
+		}
+	}
+
 // exact int32 -> double without the I2F.F64 conversion unit (a 16-per-clock-per-SM path that caps a
 // whole-genome kernel at ~5 ms): build 2^52 + (x + 2^31) from its bit pattern and subtract the bias
 // with one FP64 add (exact: both operands and the result are integers below 2^53)

@@ -257,6 +257,85 @@ static int launch_extrema_small_t (gdsp_ctx* c, gdsp_layout* L, const double* in
 	return GDSP_OK;
 	}
 
+// ---------------------------------------------------------------------------
+// localmax / localmin with a neighbourhood of at most 2*LD_HMAX+1 cells: the operator only asks whether SOME
+// cell of the neighbourhood beats the centre (minmax.c:1163-1189 keeps v unless the window extremum differs),
+// so no extremum is formed at all -- N-1 compares per cell, each one DSETP that ORs into the running
+// predicate, instead of the ~70 instructions per cell of the doubling kernel above (sanitize, log2(P) rounds
+// of 3-instruction compare-selects, two table passes): ncu had that kernel at 2.2 warp instructions per cell,
+// 53 % issue -- as much instruction- as memory-bound.  NaN neighbours never beat anything and a NaN centre is
+// never beaten (IEEE compares), which is what mapping NaN to the neutral element gave.
+// ---------------------------------------------------------------------------
+
+#define LD_THREADS 256
+#define LD_STRIP   8
+#define LD_TILE    (LD_THREADS * LD_STRIP)        // 2048 outputs per tile
+#define LD_HMAX    16
+
+template <int H, bool WANT_MAX>
+__global__ void __launch_bounds__(LD_THREADS)
+k_local_direct (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
+                const double* __restrict__ in, double* __restrict__ out, double fill)
+	{
+	constexpr uint32_t XN = LD_TILE + 2 * H;                    // staged cells
+	__shared__ double s_x[XN + (XN >> 3) + 2];
+	const double NEUTRAL = WANT_MAX ? -__longlong_as_double (0x7ff0000000000000ll) : __longlong_as_double (0x7ff0000000000000ll);
+
+	int seg;  uint64_t tis;
+	tile_to_seg (base, nseg, blockIdx.x, seg, tis);
+	const SegDev sd = segs[seg];
+	const uint64_t t0   = sd.lo + tis * LD_TILE;
+	const uint32_t nOut = (uint32_t) ((sd.hi - t0 < LD_TILE) ? (sd.hi - t0) : LD_TILE);
+	stage_tile<3, true> (s_x, in, (int64_t) t0 - H, XN, sd.dlo, sd.dhi, NEUTRAL);
+	__syncthreads ();
+
+	const uint32_t j0 = threadIdx.x * LD_STRIP;
+	if (j0 >= nOut) return;
+	double x[LD_STRIP + 2 * H];
+	#pragma unroll
+	for (int e = 0; e < LD_STRIP + 2 * H; e++) x[e] = s_x[ms_pad (j0 + e)];
+	double w[LD_STRIP];
+	#pragma unroll
+	for (int e = 0; e < LD_STRIP; e++)
+		{
+		const double v = x[e + H];
+		// one predicate, every compare ORs into it (setp.gt.or.f64): the C++ form of this loop compiled to a
+		// select per compare
+		int beaten;
+		beaten = 0;
+		#pragma unroll
+		for (int d = 0; d <= 2 * H; d++)
+			if (d != H)
+				{
+				if (WANT_MAX) asm ("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %0, 0;\n\tsetp.gt.or.f64 p, %1, %2, p;\n\tselp.s32 %0, 1, 0, p;\n\t}" : "+r"(beaten) : "d"(x[e + d]), "d"(v));
+				else          asm ("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %0, 0;\n\tsetp.lt.or.f64 p, %1, %2, p;\n\tselp.s32 %0, 1, 0, p;\n\t}" : "+r"(beaten) : "d"(x[e + d]), "d"(v));
+				}
+		w[e] = beaten ? fill : v;
+		}
+	double* o = out + t0 + j0;
+	if (j0 + LD_STRIP <= nOut)
+		{
+		stg_stream4 (o,     w[0], w[1], w[2], w[3]);
+		stg_stream4 (o + 4, w[4], w[5], w[6], w[7]);
+		}
+	else
+		{
+		#pragma unroll
+		for (int e = 0; e < LD_STRIP; e++) if (j0 + e < nOut) o[e] = w[e];
+		}
+	}
+
+template <int H, bool WANT_MAX>
+static int launch_local_direct_h (gdsp_ctx* c, gdsp_layout* L, const double* in, double* out, uint32_t h, double fill)
+	{
+	if ((uint32_t) H != h) return launch_local_direct_h<(H > 1 ? H - 1 : 1), WANT_MAX> (c, L, in, out, (H > 1) ? h : 1u, fill);
+	TileMap tm;
+	GDSP_TRY (gdsp_layout_tilemap (L, LD_TILE, &tm));
+	k_local_direct<H, WANT_MAX><<<(unsigned) tm.ntiles, LD_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, in, out, fill);
+	GDSP_KERNEL_CHECK ();
+	return GDSP_OK;
+	}
+
 // very wide windows: direct scan per output (correct for any width; slow)
 template <bool WANT_MAX, int MODE>
 __global__ void __launch_bounds__(256)
@@ -305,6 +384,8 @@ static int launch_extrema (gdsp_ctx* c, gdsp_layout* L, const double* in, double
                            uint32_t reachL, uint32_t reachR, double fill)
 	{
 	uint64_t Wn64 = (uint64_t) reachL + reachR + 1;
+	if (MODE == 1 && reachL == reachR && reachL >= 1 && reachL <= LD_HMAX)
+		return launch_local_direct_h<LD_HMAX, WANT_MAX> (c, L, in, out, reachL, fill);
 	if (Wn64 >= 2 && Wn64 < 64)
 		{
 		const uint32_t Wn = (uint32_t) Wn64;
