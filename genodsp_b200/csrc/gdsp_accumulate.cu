@@ -503,20 +503,31 @@ k_bin_offsets (uint64_t ntiles, const uint32_t* __restrict__ nRec, uint32_t* __r
 	if (threadIdx.x == 0) off[ntiles] = s_carry;
 	}
 
-// one slot in bucket `tile` per calling lane; lanes of the warp that name the same tile share one atomic
+// One slot in bucket `tile` per calling lane.  Neighbouring lanes that name the same tile share one atomic: a lane
+// starts a run when the lane below it is inactive or names another tile, and the run's first lane reserves for all
+// of it.  Position-sorted input gives one or two runs per warp (32 same-address atomics would serialise in L2);
+// random input gives a run per lane -- there MATCH.ANY found nothing more to share either and was what bound the
+// scatter kernel (ncu: 28 warps per issue in mio_throttle, 24 on the short scoreboard, L2 atomic unit 12 % busy).
 __device__ __forceinline__ uint32_t bin_reserve (uint32_t* __restrict__ cursor, uint64_t tile, bool active)
 	{
+	const int lane = threadIdx.x & 31;
+	const uint32_t t32 = (uint32_t) tile;
+	const uint32_t left = __shfl_up_sync (0xffffffffu, t32, 1);
 	const unsigned act = __ballot_sync (0xffffffffu, active);
+	const bool head = active && (lane == 0 || ((act >> (lane - 1)) & 1u) == 0 || left != t32);
+	const unsigned heads = __ballot_sync (0xffffffffu, head);
 	uint32_t pos = 0;
 	if (active)
 		{
-		const unsigned peers = __match_any_sync (act, tile);
-		const int leader = __ffs (peers) - 1;
-		const int lane = threadIdx.x & 31;
+		const unsigned upto = (lane == 31) ? 0xffffffffu : ((2u << lane) - 1u);
+		const int leader = 31 - __clz (heads & upto);                       // the run's first lane
+		const unsigned above = (leader == 31) ? 0u : ~((2u << leader) - 1u);
+		const unsigned stop = (heads | ~act) & above;                       // the next run's head or an inactive lane
+		const int end = stop ? __ffs (stop) - 1 : 32;
 		uint32_t b0 = 0;
-		if (lane == leader) b0 = atomicAdd (cursor + tile, (uint32_t) __popc (peers));
-		b0 = __shfl_sync (peers, b0, leader);
-		pos = b0 + (uint32_t) __popc (peers & ((1u << lane) - 1u));
+		if (lane == leader) b0 = atomicAdd (cursor + tile, (uint32_t) (end - leader));
+		b0 = __shfl_sync (act, b0, leader);
+		pos = b0 + (uint32_t) (lane - leader);
 		}
 	return pos;
 	}
