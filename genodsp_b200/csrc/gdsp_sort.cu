@@ -865,10 +865,12 @@ k_pct_pass (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, 
 	{
 	// ncand[1] receives the number of qualifying NaN cells (they sort to the ends of the key order)
 	unsigned int myNan = 0;
-	__shared__ unsigned long long s_key[PCT_MAXB];
+	__shared__ unsigned long long s_key[2 * PCT_MAXB];
 	__shared__ unsigned int       s_cnt[2 * PCT_MAXB + 1];
 	const int nb = B.nb, nreg = 2 * nb + 1;
-	for (int i = threadIdx.x; i < nb; i += 256) s_key[i] = B.key[i];
+	int half = 1;                                      // smallest power of two above nb, halved: first step of the search
+	while (2 * half <= nb) half *= 2;
+	for (int i = threadIdx.x; i < 2 * half; i += 256) s_key[i] = (i < nb) ? B.key[i] : ~0ull;
 	for (int i = threadIdx.x; i < nreg; i += 256) s_cnt[i] = 0;
 	__syncthreads ();
 	const int lane = threadIdx.x & 31;
@@ -901,7 +903,17 @@ k_pct_pass (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, 
 				bool q = qq[u] && !(v < mn) && !(v > mx);
 				myNan += q && (v != v);
 				int reg = 0;  bool isB = false;
-				if (q) reg = pct_region (s_key, nb, f64_key (v), isB);
+				if (SMALL) { if (q) reg = pct_region (s_key, nb, f64_key (v), isB); }
+				else
+					{
+					// branch-free search of the padded table (s_key[nb..] = the largest key): lo = number of bounds below k
+					const unsigned long long k = f64_key (v);
+					int lo = 0;
+					for (int step = half; step > 0; step >>= 1)
+						if (s_key[lo + step - 1] < k) lo += step;
+					isB = q && (lo < nb) && (s_key[lo] == k);
+					reg = q ? 2 * lo + (isB ? 1 : 0) : 0;
+					}
 				if (SMALL)
 					{
 					if (q)
@@ -912,11 +924,18 @@ k_pct_pass (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, 
 					}
 				else
 					{
+					// neighbouring lanes hold neighbouring cells: runs of equal regions share one shared-memory atomic
+					// (MATCH.ANY is a slow MIO instruction; a run per lane is what it found on noisy signals anyway)
 					const unsigned qm = __ballot_sync (0xffffffffu, q);
-					if (q)
+					const int left = __shfl_up_sync (0xffffffffu, reg, 1);
+					const bool head = q && (lane == 0 || ((qm >> (lane - 1)) & 1u) == 0 || left != reg);
+					const unsigned heads = __ballot_sync (0xffffffffu, head);
+					if (head)
 						{
-						const unsigned peers = __match_any_sync (qm, reg);
-						if (lane == __ffs (peers) - 1) atomicAdd (&s_cnt[reg], __popc (peers));
+						const unsigned above = (lane == 31) ? 0u : ~((2u << lane) - 1u);
+						const unsigned stop = (heads | ~qm) & above;
+						const int end = stop ? __ffs (stop) - 1 : 32;
+						atomicAdd (&s_cnt[reg], (unsigned int) (end - lane));
 						}
 					}
 				const bool c = q && !isB && B.compact[reg >> 1];
