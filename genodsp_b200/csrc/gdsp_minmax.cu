@@ -15,6 +15,7 @@
 // block-wide segmented scans: every thread owns a strip of E consecutive staged
 // cells in registers; strip aggregates are combined with warp shuffles.
 #include "gdsp_common.cuh"
+#include <stdlib.h>
 
 
 // fmax/fmin ignore a NaN operand, which is what the reference's `if (v[j] > best)` scans do with a NaN
@@ -336,6 +337,134 @@ static int launch_local_direct_h (gdsp_ctx* c, gdsp_layout* L, const double* in,
 	return GDSP_OK;
 	}
 
+// ---------------------------------------------------------------------------
+// 64 <= W <= 2049 (bestmax / bestmin, wide localmax / localmin): blocks of 16 staged cells, one per thread.
+// A thread forms the prefix and suffix extrema of its block in registers (30 compare-selects per 16 cells), a
+// sparse table over the 256 block extrema of the tile is built in shared memory (one compare-select per thread
+// and level), and the window of output c = 16j+e is
+//     ext( suffix of block j from e  [registers],  prefix of the block the window ends in  [shared memory],
+//          the whole blocks in between  [two table entries] )
+// where the whole blocks in between are the same for all 16 outputs of a thread up to one block at the far end:
+// two table look-ups per thread.  About 30 instructions per cell; the van Herk kernel above (k_extrema: block-wide
+// segmented scans in both directions, each as two passes over the strip, and a scalar output loop) needs ~56 and
+// ran at 0.55 of the HBM peak.
+// ---------------------------------------------------------------------------
+
+#define XB_THREADS 256
+#define XB_E       16
+#define XB_CELLS   (XB_THREADS * XB_E)            // 4096 staged cells per tile
+#define XB_LEVELS  8                              // table levels: windows of up to 2^7 whole blocks
+
+__device__ __forceinline__ uint32_t xb_pad (uint32_t j) { return j + (j >> 4); }
+
+template <bool WANT_MAX, int MODE>
+__global__ void __launch_bounds__(XB_THREADS)
+k_extrema_blocks (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
+                  const double* __restrict__ in, double* __restrict__ out,
+                  uint32_t reachL, uint32_t Wn, uint32_t tileOut, double fill)
+	{
+	extern __shared__ double xb_smem[];
+	double* const A  = xb_smem;                                 // staged cells, then the in-block prefix extrema (padded)
+	double* const Tb = xb_smem + XB_CELLS + (XB_CELLS >> 4) + 2; // Tb[k * 256 + j]: extremum of blocks j .. j + 2^k - 1
+	const double NEUTRAL = WANT_MAX ? -__longlong_as_double (0x7ff0000000000000ll) : __longlong_as_double (0x7ff0000000000000ll);
+
+	int seg;  uint64_t tis;
+	tile_to_seg (base, nseg, blockIdx.x, seg, tis);
+	const SegDev sd = segs[seg];
+	const uint64_t t0    = sd.lo + tis * tileOut;
+	const uint32_t nOut  = (uint32_t) ((sd.hi - t0 < tileOut) ? (sd.hi - t0) : tileOut);
+	const uint32_t count = nOut + Wn - 1;
+	stage_tile<4, true> (A, in, (int64_t) t0 - (int64_t) reachL, count, sd.dlo, sd.dhi, NEUTRAL);
+	for (uint32_t j = count + threadIdx.x; j < XB_CELLS; j += XB_THREADS) A[xb_pad (j)] = NEUTRAL;
+	__syncthreads ();
+
+	// own block: prefix extrema back to shared memory (in place), suffix extrema stay in registers
+	const uint32_t j0 = threadIdx.x * XB_E;
+	double suf[XB_E];
+	{
+	double a[XB_E];
+	#pragma unroll
+	for (int e = 0; e < XB_E; e++) a[e] = sanitize (A[xb_pad (j0) + e], NEUTRAL);
+	double run = a[0];
+	#pragma unroll
+	for (int e = 1; e < XB_E; e++) { run = ext<WANT_MAX> (run, a[e]);  A[xb_pad (j0) + e] = run; }
+	A[xb_pad (j0)] = a[0];
+	Tb[threadIdx.x] = run;
+	suf[XB_E - 1] = a[XB_E - 1];
+	#pragma unroll
+	for (int e = XB_E - 2; e >= 0; e--) suf[e] = ext<WANT_MAX> (suf[e + 1], a[e]);
+	}
+	// whole blocks between the first and the last block of a window: nfb or nfb+1 of them, the same for every thread
+	const uint32_t nfb = ((Wn - 1) >> 4) - 1;                   // >= 2 (Wn >= 64)
+	const int kTop = 31 - __clz (nfb + 1);
+	for (int k = 1; k <= kTop; k++)
+		{
+		__syncthreads ();
+		const uint32_t span = 1u << k;
+		if (threadIdx.x + span <= XB_THREADS)
+			Tb[k * XB_THREADS + threadIdx.x] = ext<WANT_MAX> (Tb[(k - 1) * XB_THREADS + threadIdx.x], Tb[(k - 1) * XB_THREADS + threadIdx.x + (span >> 1)]);
+		}
+	__syncthreads ();
+	if (j0 >= nOut) return;
+
+	// outputs 16j .. 16j+15: the window of output e ends at staged cell j0 + e + Wn - 1, in block j + 1 + nfb or the next
+	const uint32_t r    = (Wn - 1) & 15u;                       // the window end crosses into the next block when e + r >= 16
+	const int ka = 31 - __clz (nfb), kb = 31 - __clz (nfb + 1);
+	const uint32_t b1 = threadIdx.x + 1;
+	double midA = ext<WANT_MAX> (Tb[ka * XB_THREADS + b1], Tb[ka * XB_THREADS + b1 + nfb - (1u << ka)]);
+	double midB = midA;
+	if (r != 0 && b1 + nfb + 1 <= XB_THREADS)
+		midB = ext<WANT_MAX> (Tb[kb * XB_THREADS + b1], Tb[kb * XB_THREADS + b1 + nfb + 1 - (1u << kb)]);
+	double w[XB_E];
+	#pragma unroll
+	for (int e = 0; e < XB_E; e++)
+		{
+		uint32_t last = j0 + e + Wn - 1;
+		if (last > XB_CELLS - 1) last = XB_CELLS - 1;           // (outputs past nOut: computed, never stored)
+		const double pre = A[xb_pad (last)];
+		const double mid = ((uint32_t) e + r >= 16u) ? midB : midA;
+		w[e] = ext<WANT_MAX> (ext<WANT_MAX> (suf[e], pre), mid);
+		}
+	double* o = out + t0 + j0;
+	if (MODE == 1)
+		{
+		const double* ctr = in + t0 + j0;
+		#pragma unroll
+		for (int e = 0; e < XB_E; e++)
+			if (j0 + e < nOut)
+				{
+				const double v = __ldg (ctr + e);
+				w[e] = (WANT_MAX ? (w[e] > v) : (w[e] < v)) ? fill : v;
+				}
+		}
+	if (j0 + XB_E <= nOut)
+		{
+		#pragma unroll
+		for (int e = 0; e < XB_E; e += 4) stg_stream4 (o + e, w[e], w[e + 1], w[e + 2], w[e + 3]);
+		}
+	else
+		{
+		#pragma unroll
+		for (int e = 0; e < XB_E; e++) if (j0 + e < nOut) o[e] = w[e];
+		}
+	}
+
+template <bool WANT_MAX, int MODE>
+static int launch_extrema_blocks (gdsp_ctx* c, gdsp_layout* L, const double* in, double* out,
+                                  uint32_t reachL, uint32_t Wn, double fill)
+	{
+	uint32_t tileOut = XB_CELLS - (Wn - 1);
+	tileOut &= ~63u;                                   // keep tile starts 512-byte aligned
+	const size_t smem = sizeof (double) * ((size_t) XB_CELLS + (XB_CELLS >> 4) + 2 + (size_t) XB_LEVELS * XB_THREADS);
+	TileMap tm;
+	GDSP_TRY (gdsp_layout_tilemap (L, tileOut, &tm));
+	GDSP_CUDA (cudaFuncSetAttribute (k_extrema_blocks<WANT_MAX, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	k_extrema_blocks<WANT_MAX, MODE><<<(unsigned) tm.ntiles, XB_THREADS, smem, c->stream>>>
+		(L->d, tm.d_base, L->nseg, in, out, reachL, Wn, tileOut, fill);
+	GDSP_KERNEL_CHECK ();
+	return GDSP_OK;
+	}
+
 // very wide windows: direct scan per output (correct for any width; slow)
 template <bool WANT_MAX, int MODE>
 __global__ void __launch_bounds__(256)
@@ -395,6 +524,8 @@ static int launch_extrema (gdsp_ctx* c, gdsp_layout* L, const double* in, double
 		if (Wn < 32) return launch_extrema_small_t<4, WANT_MAX, MODE> (c, L, in, out, reachL, Wn, fill);
 		return launch_extrema_small_t<5, WANT_MAX, MODE> (c, L, in, out, reachL, Wn, fill);
 		}
+	if (Wn64 >= 64 && Wn64 <= 2049 && !getenv ("GDSP_EXTREMA_VANHERK"))
+		return launch_extrema_blocks<WANT_MAX, MODE> (c, L, in, out, reachL, (uint32_t) Wn64, fill);
 	if (Wn64 <= 2049) return launch_extrema_t<4, 256, WANT_MAX, MODE> (c, L, in, out, reachL, (uint32_t) Wn64, fill);
 	if (Wn64 <= 6145) return launch_extrema_t<4, 512, WANT_MAX, MODE> (c, L, in, out, reachL, (uint32_t) Wn64, fill);
 	TileMap tm;

@@ -336,6 +336,23 @@ def test_best_extrema(genome, orc, kind, W):
     compare(genome, inputs, lambda v: orc.best_extrema(v, W, False), what="bestmin W=%d" % W)
 
 
+@pytest.mark.parametrize("W", [64, 65, 66, 79, 80, 81, 95, 96, 97, 127, 128, 129, 513, 1024, 2033, 2048, 2049])
+def test_best_extrema_block_kernel_widths(genome, orc, W):
+    """k_extrema_blocks (64 <= W <= 2049): windows that end exactly on a 16-cell block boundary (W-1 a multiple of
+    16), just before and just after one, the narrowest (two whole blocks inside) and the widest it takes; also as
+    a wide localmax (the same kernel in its keep-unless-beaten mode)"""
+    inputs = load(genome, np.random.default_rng(W), "real")
+    genome.bestmax(W)
+    compare(genome, inputs, lambda v: orc.best_extrema(v, W, True), what="bestmax W=%d" % W)
+    inputs = load(genome, np.random.default_rng(W + 3), "int")
+    genome.bestmin(W)
+    compare(genome, inputs, lambda v: orc.best_extrema(v, W, False), what="bestmin W=%d" % W)
+    if W % 2 == 1:
+        inputs = load(genome, np.random.default_rng(W + 5), "real")
+        genome.localmax(W, zero=-2.0)
+        compare(genome, inputs, lambda v: orc.local_extrema(v, W, True, -2.0), what="localmax N=%d" % W)
+
+
 def test_best_extrema_very_wide(orc):
     from genodsp_b200.genome import Genome
     g = Genome([("a", 30000), ("b", 100)])
