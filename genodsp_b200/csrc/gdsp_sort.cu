@@ -866,13 +866,25 @@ k_pct_pass (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, 
 	// ncand[1] receives the number of qualifying NaN cells (they sort to the ends of the key order)
 	unsigned int myNan = 0;
 	__shared__ unsigned long long s_key[2 * PCT_MAXB];
-	__shared__ unsigned int       s_cnt[2 * PCT_MAXB + 1];
+	// one set of region counters per warp: on tied data (integer depth) a handful of regions take nearly every cell
+	// and the eight warps of a block serialised on the same shared-memory words
+	__shared__ unsigned int       s_cntAll[8][2 * PCT_MAXB + 1];
+	unsigned int* const s_cnt = s_cntAll[threadIdx.x >> 5];
 	const int nb = B.nb, nreg = 2 * nb + 1;
 	int half = 1;                                      // smallest power of two above nb, halved: first step of the search
 	while (2 * half <= nb) half *= 2;
 	for (int i = threadIdx.x; i < 2 * half; i += 256) s_key[i] = (i < nb) ? B.key[i] : ~0ull;
-	for (int i = threadIdx.x; i < nreg; i += 256) s_cnt[i] = 0;
+	for (int i = threadIdx.x; i < 8 * (2 * PCT_MAXB + 1); i += 256) (&s_cntAll[0][0])[i] = 0;
+	// the compaction flags in shared memory (a dynamically indexed kernel parameter is a constant-bank load per cell),
+	// and whether anything is compacted at all: on tied data every wanted rank falls ON a bound and nothing is
+	__shared__ unsigned char s_compact[PCT_MAXB + 1];
+	__shared__ int s_any;
+	if (threadIdx.x == 0) s_any = 0;
 	__syncthreads ();
+	for (int i = threadIdx.x; i <= nb; i += 256) { s_compact[i] = B.compact[i];  if (B.compact[i]) s_any = 1; }
+	__syncthreads ();
+	const bool anyCompact = (s_any != 0);
+	const bool limits = !(mn == -__longlong_as_double (0x7ff0000000000000ll) && mx == __longlong_as_double (0x7ff0000000000000ll));
 	const int lane = threadIdx.x & 31;
 
 	unsigned int mine[5] = { 0, 0, 0, 0, 0 };         // SMALL: nb <= 2 -> at most 5 regions, counted in registers
@@ -886,7 +898,8 @@ k_pct_pass (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, 
 		uint64_t t1 = t0 + PCT_TILE;  if (t1 > sd.hi) t1 = sd.hi;
 		for (uint64_t i0 = t0; i0 < t1; i0 += 256 * 4)
 			{
-			// four independent loads per thread before any of the warp votes below
+			// four independent loads per thread before any of the warp votes below (lanes hold NEIGHBOURING cells: a
+			// 256-bit load per lane would put them 4 cells apart and shorten the runs the counting shares: measured slower)
 			double vv[4];  bool qq[4];
 			#pragma unroll
 			for (int u = 0; u < 4; u++)
@@ -900,7 +913,8 @@ k_pct_pass (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, 
 			for (int u = 0; u < 4; u++)
 				{
 				const double v = vv[u];
-				bool q = qq[u] && !(v < mn) && !(v > mx);
+				bool q = qq[u];
+				if (limits) q = q && !(v < mn) && !(v > mx);
 				myNan += q && (v != v);
 				int reg = 0;  bool isB = false;
 				if (SMALL) { if (q) reg = pct_region (s_key, nb, f64_key (v), isB); }
@@ -938,8 +952,8 @@ k_pct_pass (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, 
 						atomicAdd (&s_cnt[reg], (unsigned int) (end - lane));
 						}
 					}
-				const bool c = q && !isB && B.compact[reg >> 1];
-				const unsigned cm = __ballot_sync (0xffffffffu, c);
+				const bool c = anyCompact && q && !isB && s_compact[reg >> 1];
+				const unsigned cm = anyCompact ? __ballot_sync (0xffffffffu, c) : 0u;
 				if (cm)
 					{
 					unsigned long long b0 = 0;
@@ -970,7 +984,12 @@ k_pct_pass (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, 
 	if (lane == 0 && myNan) atomicAdd (&ncand[1], (unsigned long long) myNan);
 	__syncthreads ();
 	for (int i = threadIdx.x; i < nreg; i += 256)
-		if (s_cnt[i]) atomicAdd (&counts[i], (unsigned long long) s_cnt[i]);
+		{
+		unsigned long long t = 0;
+		#pragma unroll
+		for (int w = 0; w < 8; w++) t += s_cntAll[w][i];
+		if (t) atomicAdd (&counts[i], t);
+		}
 	}
 
 // ---------------------------------------------------------------------------
