@@ -414,6 +414,9 @@ struct ClumpFast
 	uint32_t*      Bq;         // marked and qualifying (v >= T, <= T for anticlump)
 	unsigned char* tsum;       // per tile: bit0/1 generate/propagate upwards, bit2/3 downwards
 	unsigned char* tcin;       // per tile: bit0 carry entering from below, bit1 from above
+	unsigned char* tquiet;     // per tile: 1 = no cell of the tile can be a valid end (k_clump_classify, from the records alone)
+	double*        gmid;       // per group: its prefix sum after 256 cells, relative to the group (NaN when the group holds a
+	                           // qualifying cell or the tile is not whole): with the carries, P at every 256-cell boundary
 	int*           segAllNeg;
 	// slab-sharded chromosomes (gdsp_clump_slab_*); all NULL for whole chromosomes
 	const double2*       segCarryIn;  // per segment: {P, M} just before the segment's first cell
@@ -499,6 +502,8 @@ k_clump_groups (const SegDev* __restrict__ segs, const uint64_t* __restrict__ ba
 	#pragma unroll
 	for (int d = 16; d >= 1; d >>= 1) m = dmin2 (m, shfl_xor_f64 (m, d));
 	const bool any = __any_sync (0xffffffffu, q != 0);
+	// (for k_clump_classify) the prefix sum half way through the group, if the group holds no qualifying cell
+	if (lane == 15) wk.gmid[tile * CLF_GROUPS + warp] = (any || n != CL_TILE) ? __longlong_as_double (0x7ff8000000000000ll) : x[15];
 	if (lane == 0)
 		{
 		wk.carry[tile * CLF_GROUPS + warp] = make_double2 (total, m);
@@ -615,7 +620,7 @@ template <bool FAST, bool ABOVE>
 __device__ __forceinline__ void clf_mark_tile (const double* __restrict__ sig, double T, const ClumpFast& wk, const ScanStatus<double>& stMax,
                                                double* s_M, double* s_warp, double* s_carryD,
                                                uint64_t tile, uint32_t ticket, bool firstOfScan, uint64_t c0, uint64_t t0, uint32_t n,
-                                               uint32_t Lmin, uint32_t hrows, double* sufMaxOut)
+                                               uint32_t Lmin, uint32_t hrows, double* sufMaxOut, bool haveLook, double lookE)
 	{
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const double NEG = -CLF_INF;
@@ -686,7 +691,9 @@ __device__ __forceinline__ void clf_mark_tile (const double* __restrict__ sig, d
 		}
 	if (threadIdx.x < 32)
 		{
-		const double e = scan_lookback<double> (stMax, ticket, firstOfScan, tAgg, NEG, [] (double a, double b) { return (b > a) ? b : a; });
+		// (haveLook: the tile already took part in the look-back chain with the aggregate -inf, see k_clump_mark)
+		const double e = haveLook ? lookE
+		               : scan_lookback<double> (stMax, ticket, firstOfScan, tAgg, NEG, [] (double a, double b) { return (b > a) ? b : a; });
 		if (threadIdx.x == 0)
 			{
 			*s_carryD = e;
@@ -716,6 +723,55 @@ __device__ __forceinline__ void clf_mark_tile (const double* __restrict__ sig, d
 		const uint64_t w = tile * CLF_WORDS + warp * (CLF_GROUP / 32) + (lane >> 1);
 		wk.Bm[w] = wm;  wk.Bq[w] = wq;
 		}
+	}
+
+// ---- tiles that cannot hold a valid end, decided from the group records alone (no signal read) -------------
+// A group without a qualifying cell (every d < 0) has a prefix sum that never rises (rounding is monotone).  The
+// records give P at every 256-cell boundary: the carries at the group boundaries, carry + gmid half way.  Take a
+// 256-cell half h of the tile; i-Lmin for its cells i lies at least two halves back (Lmin >= 512), so a whole half
+// lies in between, and if the recorded P falls STRICTLY across it -- P at the end of the half holding (last cell of
+// h) - Lmin is above P before h -- then P[i-Lmin] > P[i] for every cell of h, as computed, without looking at a cell.
+// If all groups from the one holding (first cell of the group) - Lmin to the group itself never rise, and the
+// prefix minimum BEFORE the first of them is above P before the group, then M[i-Lmin] = min (that minimum,
+// P[..i-Lmin]) > P[i]: no cell of the group is a valid end.  One thread per tile; k_clump_mark reads the flag with
+// its first loads.
+__device__ __forceinline__ double clf_half_p (const ClumpFast& wk, uint64_t H)    // P before 256-cell half H (global index)
+	{
+	const double2 cr = wk.carry[H >> 1];
+	return (H & 1) ? cr.x + wk.gmid[H >> 1] : cr.x;
+	}
+
+__global__ void __launch_bounds__(256)
+k_clump_classify (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg, uint64_t ntiles,
+                  uint32_t minLength, double relLength, ClumpFast wk)
+	{
+	const uint64_t tile = (uint64_t) blockIdx.x * 256 + threadIdx.x;
+	if (tile >= ntiles) return;
+	int lo = 0, hi = nseg - 1;
+	while (lo < hi) { const int mid = (lo + hi + 1) >> 1;  if (base[mid] <= tile) lo = mid; else hi = mid - 1; }
+	const SegDev sd = segs[lo];
+	const uint64_t tis = tile - base[lo], tilesInSeg = base[lo + 1] - base[lo];
+	const uint64_t t0 = sd.lo + tis * CL_TILE;
+	const uint64_t c0 = (uint64_t) sd.pos0 + tis * CL_TILE;
+	uint32_t Lmin = minLength;
+	if (relLength > 0.0) { const uint32_t rl = (uint32_t) (relLength * sd.chromLen);  if (rl > Lmin) Lmin = rl; }
+	bool pass = (sd.hi - t0 >= CL_TILE) && (Lmin >= CLF_GROUP) && (c0 >= (uint64_t) Lmin) && (tis + 1 < tilesInSeg) && (wk.segFlags == NULL);
+	for (int w = 0; w < CLF_GROUPS && pass; w++)
+		{
+		const uint64_t G  = tile * CLF_GROUPS + w;
+		const uint64_t a  = c0 + (uint64_t) w * CLF_GROUP;                          // first cell of the group (chromosome index)
+		const uint64_t ga = G - ((a >> 9) - ((a - Lmin) >> 9));                      // group of the cell Lmin before it (512-aligned groups)
+		pass = (wk.carry[ga].y > wk.carry[G].x);
+		for (uint64_t g = ga; g <= G && pass; g++) { const double m = wk.gmid[g];  pass = (m == m); }   // none of them holds a qualifying cell
+		for (int h = 0; h < 2 && pass; h++)
+			{
+			const uint64_t H  = 2 * G + h;
+			const uint64_t bh = a + 256u * h + 255u;                                  // last cell of the half
+			const uint64_t Hl = H - ((bh >> 8) - ((bh - Lmin) >> 8));                  // half holding the cell Lmin before it
+			pass = (clf_half_p (wk, Hl + 1) > clf_half_p (wk, H));
+			}
+		}
+	wk.tquiet[tile] = pass ? 1 : 0;
 	}
 
 #ifndef GDSP_CLUMP_MARK_OCC
@@ -762,6 +818,29 @@ k_clump_mark (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base
 	const uint32_t reach = (Lmin > 0) ? Lmin : 1;                 // M[p-1] is needed even when Lmin is 0
 	const uint32_t hrows = (reach + CLF_GROUP - 1) / CLF_GROUP;   // <= 8 (the host checked): at most one per warp
 
+	// A tile k_clump_classify found without a valid end has the aggregate -inf in the suffix-maximum chain -- published
+	// at once, so the tiles on its left do not wait for any work here -- and with e the maximum valid prefix sum to its
+	// right, a cell p is marked iff e >= M[p-1] >= M at the tile's end: if e is below that, the tile's words are zero and
+	// the signal is never read.  On a thresholded track that is mostly below the threshold (clump after open/close in
+	// BASELINE config 4) that is nearly every tile.
+	bool haveLook = false;  double lookE = 0.0;
+	if (wk.tquiet[tile] != 0)
+		{
+		__shared__ double s_look;
+		if (threadIdx.x < 32)
+			{
+			const double e = scan_lookback<double> (stMax, ticket, false, -CLF_INF, -CLF_INF, [] (double a, double b) { return (b > a) ? b : a; });
+			if (threadIdx.x == 0) { s_look = e;  if (sufMaxOut != NULL) *sufMaxOut = e; }
+			}
+		__syncthreads ();
+		lookE = s_look;  haveLook = true;
+		if (lookE < wk.carry[(tile + 1) * CLF_GROUPS].y)          // (never the last tile of its segment: the next tile's carry exists)
+			{
+			if (threadIdx.x < CLF_WORDS) { wk.Bm[tile * CLF_WORDS + threadIdx.x] = 0u;  wk.Bq[tile * CLF_WORDS + threadIdx.x] = 0u; }
+			return;
+			}
+		}
+
 	// prefix minima of the halo groups (the tail of the previous tile of this chromosome)
 	if ((uint32_t) warp < hrows && (uint64_t) (hrows - warp) * CLF_GROUP <= c0)
 		{
@@ -776,9 +855,9 @@ k_clump_mark (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base
 		}
 
 	if (n == CL_TILE && c0 >= (uint64_t) Lmin && c0 > 0)
-		clf_mark_tile<true, ABOVE> (sig, T, wk, stMax, s_M, s_warp, &s_carryD, tile, ticket, firstOfScan, c0, t0, n, Lmin, hrows, sufMaxOut);
+		clf_mark_tile<true, ABOVE> (sig, T, wk, stMax, s_M, s_warp, &s_carryD, tile, ticket, firstOfScan, c0, t0, n, Lmin, hrows, sufMaxOut, haveLook, lookE);
 	else
-		clf_mark_tile<false, ABOVE> (sig, T, wk, stMax, s_M, s_warp, &s_carryD, tile, ticket, firstOfScan, c0, t0, n, Lmin, hrows, sufMaxOut);
+		clf_mark_tile<false, ABOVE> (sig, T, wk, stMax, s_M, s_warp, &s_carryD, tile, ticket, firstOfScan, c0, t0, n, Lmin, hrows, sufMaxOut, haveLook, lookE);
 	}
 
 // ---- run trimming on the bit words -------------------------------------------
@@ -1149,7 +1228,7 @@ extern "C" int gdsp_clump_slab_create (gdsp_ctx* c, const gdsp_layout* L_, uint6
 	st = gdsp_layout_tilemap (cs->E, CL_TILE, &cs->tm);
 	if (st != GDSP_OK) { gdsp_clump_slab_destroy (cs);  return st; }
 	const uint64_t ntiles = cs->tm.ntiles;
-	const size_t fastBytes = (size_t) ntiles * (CLF_GROUPS * 16 + 2 * CLF_WORDS * 4) + 2 * (((size_t) ntiles + 255) / 256) * 256 + (size_t) L->nseg * 4;
+	const size_t fastBytes = (size_t) ntiles * (CLF_GROUPS * 16 + 2 * CLF_WORDS * 4 + CLF_GROUPS * 8) + 256 + 3 * (((size_t) ntiles + 255) / 256) * 256 + (size_t) L->nseg * 4;
 	if (fastBytes > gdsp_clump_work_bytes (buffer_cells))
 		{
 		gdsp_clump_slab_destroy (cs);
@@ -1181,6 +1260,8 @@ extern "C" int gdsp_clump_slab_create (gdsp_ctx* c, const gdsp_layout* L_, uint6
 	wf.Bq = (uint32_t*) p;              p += (size_t) ntiles * CLF_WORDS * 4;
 	wf.tsum = (unsigned char*) p;       p += (((size_t) ntiles + 255) / 256) * 256;
 	wf.tcin = (unsigned char*) p;       p += (((size_t) ntiles + 255) / 256) * 256;
+	wf.tquiet = (unsigned char*) p;     p += (((size_t) ntiles + 255) / 256) * 256;
+	wf.gmid = (double*) p;              p += (((size_t) ntiles * CLF_GROUPS * 8 + 255) / 256) * 256;
 	wf.segAllNeg = (int*) p;
 	wf.segCarryIn = cs->d_carryIn;  wf.segSufMax = cs->d_sufMax;  wf.segFlags = cs->d_flags;
 	const uint32_t reach = maxLmin ? maxLmin : 1;
@@ -1229,6 +1310,8 @@ extern "C" int gdsp_clump_slab_mark (gdsp_clump_slab* cs, const double* sig, con
 	GDSP_TRY (gdsp_ws (c, 0, scan_status_bytes<double> (cs->tm.ntiles), &cs->ws1));
 	GDSP_CUDA (cudaMemcpyAsync (cs->d_carryIn, h_carry_in, sizeof (double) * 2 * cs->nseg, cudaMemcpyHostToDevice, c->stream));
 	k_clump_groupscan<<<cs->nseg, CLF_GS_THREADS, 0, c->stream>>> (cs->tm.d_base, cs->wf);
+	GDSP_KERNEL_CHECK ();
+	k_clump_classify<<<(unsigned) ((cs->tm.ntiles + 255) / 256), 256, 0, c->stream>>> (E->d, cs->tm.d_base, cs->nseg, cs->tm.ntiles, cs->minLength, cs->relLength, cs->wf);
 	GDSP_KERNEL_CHECK ();
 	GDSP_CUDA (cudaMemsetAsync (cs->ws1, 0, scan_status_clear_bytes<double> (cs->tm.ntiles), c->stream));
 	if (cs->above) k_clump_mark<true><<<(unsigned) cs->tm.ntiles, CL_THREADS, cs->smem, c->stream>>> (E->d, cs->tm.d_base, cs->nseg, cs->tm.ntiles, sig,
@@ -1311,7 +1394,7 @@ extern "C" int gdsp_clump (gdsp_ctx* c, const gdsp_layout* L_, double* sig, uint
 			const uint32_t rl = (uint32_t) (relLength * L->h[s].chrom_len);
 			if (rl > maxLmin) maxLmin = rl;
 			}
-	const size_t fastBytes = (size_t) tm.ntiles * (CLF_GROUPS * 16 + 2 * CLF_WORDS * 4) + 2 * (((size_t) tm.ntiles + 255) / 256) * 256
+	const size_t fastBytes = (size_t) tm.ntiles * (CLF_GROUPS * 16 + 2 * CLF_WORDS * 4 + CLF_GROUPS * 8) + 256 + 3 * (((size_t) tm.ntiles + 255) / 256) * 256
 	                       + (size_t) L->nseg * 4;
 	if (maxLmin <= CLF_MAX_HALO && fastBytes <= gdsp_clump_work_bytes (buffer_cells) && !getenv ("GDSP_CLUMP_STORED") && !c->exact_order)
 		{
@@ -1322,6 +1405,8 @@ extern "C" int gdsp_clump (gdsp_ctx* c, const gdsp_layout* L_, double* sig, uint
 		wf.Bq = (uint32_t*) p;              p += (size_t) tm.ntiles * CLF_WORDS * 4;
 		wf.tsum = (unsigned char*) p;       p += (((size_t) tm.ntiles + 255) / 256) * 256;
 		wf.tcin = (unsigned char*) p;       p += (((size_t) tm.ntiles + 255) / 256) * 256;
+		wf.tquiet = (unsigned char*) p;     p += (((size_t) tm.ntiles + 255) / 256) * 256;
+		wf.gmid = (double*) p;              p += (((size_t) tm.ntiles * CLF_GROUPS * 8 + 255) / 256) * 256;
 		wf.segAllNeg = (int*) p;
 		wf.segCarryIn = NULL;  wf.segSufMax = NULL;  wf.segFlags = NULL;
 		const uint32_t reach = maxLmin ? maxLmin : 1;
@@ -1338,6 +1423,8 @@ extern "C" int gdsp_clump (gdsp_ctx* c, const gdsp_layout* L_, double* sig, uint
 		else       k_clump_groups<false><<<(unsigned) tm.ntiles, CL_THREADS, 0, c->stream>>> (L->d, tm.d_base, L->nseg, sig, average, wf);
 		GDSP_KERNEL_CHECK ();
 		k_clump_groupscan<<<L->nseg, CLF_GS_THREADS, 0, c->stream>>> (tm.d_base, wf);
+		GDSP_KERNEL_CHECK ();
+		k_clump_classify<<<(unsigned) ((tm.ntiles + 255) / 256), 256, 0, c->stream>>> (L->d, tm.d_base, L->nseg, tm.ntiles, minLength, relLength, wf);
 		GDSP_KERNEL_CHECK ();
 		GDSP_CUDA (cudaMemsetAsync (ws1, 0, scan_status_clear_bytes<double> (tm.ntiles), c->stream));
 		if (above) k_clump_mark<true><<<(unsigned) tm.ntiles, CL_THREADS, smem, c->stream>>> (L->d, tm.d_base, L->nseg, tm.ntiles, sig, average,

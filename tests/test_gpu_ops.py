@@ -599,6 +599,39 @@ def test_clump_long_runs_and_halo_edges(genome, orc, L):
     compare(genome, inputs, lambda v: orc.clump(v, 1.5, L, False, 7.0, 0.5), what="anticlump long runs L=%d" % L)
 
 
+@pytest.mark.parametrize("L", [512, 1000, 3000, 4096])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_clump_mostly_below_threshold(genome, orc, L, seed):
+    """long stretches without a qualifying cell (whole 4096-cell tiles): k_clump_mark settles those tiles from the
+    group records without reading the signal.  The stretches sit beside humps of every size, so that all three
+    outcomes occur: no valid end and nothing marked; no valid end in the tile but cells marked from a hump on its
+    right (the early-out must fall through); valid ends inside a falling stretch because an old, deeper prefix
+    minimum lies behind it (the record test must fail)"""
+    rng = np.random.default_rng(100 * L + seed)
+    inputs = {}
+    for name, n in CHROMS:
+        v = np.full(n, -1.0)
+        pos = int(rng.integers(0, 3000))
+        while pos < n:
+            stretch = int(rng.choice([700, 5000, 9000, 20000, 45000]))
+            pos += stretch
+            hump = int(rng.choice([40, 600, 1500, 6000, 12000]))
+            height = float(rng.choice([0.5, 1.0, 4.0, 16.0]))
+            v[pos:pos + hump] = height
+            pos += hump
+        if seed == 2:
+            v[: n // 3] -= 3.0                      # a deep early minimum: later falling stretches stay above it
+            v[n // 3: n // 3 + 8000] = 12.0
+        inputs[name] = v
+        genome.set_chrom(name, v)
+    genome.clump(0.0, L, one=2.0, zero=-3.0)
+    compare(genome, inputs, lambda v: orc.clump(v, 0.0, L, True, 2.0, -3.0), what="clump mostly-below L=%d" % L)
+    for name, n in CHROMS:
+        genome.set_chrom(name, -inputs[name])
+    genome.anticlump(0.0, L)
+    compare(genome, {k: -v for k, v in inputs.items()}, lambda v: orc.clump(v, 0.0, L, False), what="anticlump mostly-above L=%d" % L)
+
+
 def test_clump_stored_prefix_passes_on_short_lengths(genome, orc, monkeypatch):
     """the stored-prefix passes (normally only for minimum lengths above 4096) on short ones"""
     monkeypatch.setenv("GDSP_CLUMP_STORED", "1")
