@@ -305,6 +305,19 @@ def _clump_signals(rng):
         v = 4.0 + np.sign(np.sin(np.arange(n) / 9000.0)) * 1.0 + (rng.integers(0, 2, n) * 0.5)
         d[name] = v
     sig["drift"] = d
+    # (e) long stretches below the threshold (whole tiles k_clump_mark settles from the group records alone) beside
+    #     humps of every size: quiet tiles next to cuts, marks reaching into quiet stretches from a hump on their right
+    e = {}
+    for name, n in CLUMP_CHROMS:
+        v = np.full(n, 3.0)
+        pos = int(rng.integers(0, 2000))
+        while pos < n:
+            pos += int(rng.choice([900, 6000, 14000, 30000]))
+            hump = int(rng.choice([50, 700, 2500, 9000]))
+            v[pos:pos + hump] = float(rng.choice([5.0, 8.0, 20.0]))
+            pos += hump
+        e[name] = v
+    sig["humps"] = e
     return sig
 
 
