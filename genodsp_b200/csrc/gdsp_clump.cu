@@ -755,7 +755,9 @@ k_clump_classify (const SegDev* __restrict__ segs, const uint64_t* __restrict__ 
 	const uint64_t c0 = (uint64_t) sd.pos0 + tis * CL_TILE;
 	uint32_t Lmin = minLength;
 	if (relLength > 0.0) { const uint32_t rl = (uint32_t) (relLength * sd.chromLen);  if (rl > Lmin) Lmin = rl; }
-	bool pass = (sd.hi - t0 >= CL_TILE) && (Lmin >= CLF_GROUP) && (c0 >= (uint64_t) Lmin) && (tis + 1 < tilesInSeg);
+	// (the groups the test looks back at must belong to this segment: a slab piece starts at chromosome coordinate
+	// pos0 > 0, and what lies before its first tile in the record arrays is another segment)
+	bool pass = (sd.hi - t0 >= CL_TILE) && (Lmin >= CLF_GROUP) && (tis * CL_TILE >= (uint64_t) Lmin) && (tis + 1 < tilesInSeg);
 	// (slab pieces: the tile of the neighbour's cells in front of a piece is never marked at all, k_clump_mark returns
 	// before it looks at this flag; its groups do serve as the Lmin cells before the piece's first own tile)
 	for (int w = 0; w < CLF_GROUPS && pass; w++)
