@@ -232,3 +232,82 @@ def test_slab_carries_match_the_oracle(kind):
             want = orc.clump(v.copy(), T, lmin, above, 1.0, 0.0) != 0
             got = slab_clump_emulation(v, T, lmin, above, tile, cuts)
             assert np.array_equal(want, got), (kind, trial, n, cuts, lmin, above, np.flatnonzero(want != got)[:8])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Quiet tiles (k_clump_classify + the early-out of k_clump_mark): from the group records alone
+# -- {P, M} before every 512-cell group, P after 256 cells of a group, "the group holds no qualifying cell" --
+# a 4096-cell tile is declared free of valid ends, and with e (the maximum valid P to its right) below M at the
+# tile's end, free of marks.  Restated on the CPU and checked against the definitions cell by cell.
+# ---------------------------------------------------------------------------------------------------------
+
+def _quiet_tiles(d, L, tile=4096, group=512):
+    """the classification rule of k_clump_classify for one whole chromosome (d = v - T per cell)"""
+    n = d.size
+    P = np.cumsum(d)
+    Pm1 = np.concatenate([[0.0], P])                         # Pm1[j] = P[j-1], P[-1] = 0
+    M = np.minimum.accumulate(Pm1)                           # M[j] (index j+1) = min(0, P[0..j]); M[-1] = 0 at index 0
+    ngroups = n // group
+    pbefore = Pm1[np.arange(ngroups + 1) * group]            # P before group g
+    mbefore = M[np.arange(ngroups + 1) * group]              # M before group g
+    falling = np.array([not np.any(d[g * group:(g + 1) * group] >= 0) for g in range(ngroups)])
+    def half_p(H):                                           # P before 256-cell half H
+        return Pm1[H * 256]
+    quiet = np.zeros(n // tile, bool)
+    for t in range(n // tile):
+        c0 = t * tile
+        ok = (L >= group) and (c0 >= L) and ((t + 1) * tile + group <= n)        # whole tile, not the last one
+        for w in range(tile // group):
+            if not ok:
+                break
+            G = c0 // group + w
+            a = c0 + w * group
+            ga = (a - L) // group
+            ok = mbefore[ga] > pbefore[G] and bool(np.all(falling[ga:G + 1]))
+            for h in range(2):
+                if not ok:
+                    break
+                H = 2 * G + h
+                bh = a + 256 * h + 255
+                Hl = (bh - L) // 256
+                ok = half_p(Hl + 1) > half_p(H)
+        quiet[t] = ok
+    return quiet, P, M
+
+
+@pytest.mark.parametrize("L", [512, 1000, 2500, 4096])
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_quiet_tile_rule_is_sound(L, seed):
+    rng = np.random.default_rng(10 * L + seed)
+    n = 40 * 4096
+    d = np.full(n, -1.0)
+    pos = int(rng.integers(0, 3000))
+    while pos < n:
+        pos += int(rng.choice([700, 5000, 9000, 20000, 45000]))
+        hump = int(rng.choice([40, 600, 1500, 6000, 12000]))
+        d[pos:pos + hump] = float(rng.choice([0.5, 1.0, 4.0, 16.0]))
+        pos += hump
+    if seed >= 2:
+        d[: n // 3] -= 3.0                                   # a deep early minimum: later falling stretches stay above it
+        d[n // 3: n // 3 + 8000] = 12.0
+    quiet, P, M = _quiet_tiles(d, L)
+    # the definitions (DESIGN section 8): end i is valid iff i+1 >= L and M[i-L] <= P[i]; S[p] = max valid P at or after p;
+    # cell p is marked iff S[p] >= M[p-1]
+    idx = np.arange(n)
+    Mlag = np.where(idx - L >= -1, M[np.clip(idx - L + 1, 0, n)], np.inf)
+    valid = (idx + 1 >= L) & (Mlag <= P)
+    S = np.maximum.accumulate(np.where(valid, P, -np.inf)[::-1])[::-1]
+    marked = S >= M[:n]                                      # M[p-1] sits at index p
+    assert quiet.any() and not quiet.all()
+    seen_fallthrough = False
+    for t in np.nonzero(quiet)[0]:
+        lo, hi = t * 4096, (t + 1) * 4096
+        assert not valid[lo:hi].any(), (L, seed, t)
+        e = S[hi] if hi < n else -np.inf                     # maximum valid P to the right of the tile
+        m_end = M[hi]                                        # M at the tile's last cell
+        if e < m_end:
+            assert not marked[lo:hi].any(), (L, seed, t)
+        else:
+            seen_fallthrough = True                           # the kernel runs the full path with e in hand
+    if seed < 2:
+        assert seen_fallthrough or L > 1000
