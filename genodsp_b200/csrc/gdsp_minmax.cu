@@ -1,5 +1,9 @@
-// gdsp_minmax.cu -- sliding-window extrema (van Herk / Gil-Werman in shared
-// memory with warp-shuffle segmented scans).
+// gdsp_minmax.cu -- sliding-window extrema.  By window width:
+//   localmax/localmin up to 33 cells   k_local_direct    chained compares, no extremum formed
+//   up to 63 cells                      k_extrema_small   sparse-table doubling in registers
+//   64 .. 2049 cells                    k_extrema_blocks  16-cell blocks per thread + sparse table over block extrema
+//   up to 6145 cells                    k_extrema         van Herk / Gil-Werman with warp-shuffle segmented scans
+//   beyond                              k_extrema_wide    direct scan per output
 //
 // Replaces op_local_maxima_apply (minmax.c:1183-1227), op_local_minima_apply
 // (minmax.c:981-1022), op_best_local_max_apply (minmax.c:1616-1721) and

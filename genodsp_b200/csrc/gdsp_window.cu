@@ -3,9 +3,10 @@
 // Replaces op_window_sum_apply (sum.c:211-252), op_sliding_sum_apply
 // (sum.c:420-463) and op_smooth_apply (sum.c:616-676).
 //
-// All three stage a tile of the signal plus its window halo in shared memory;
-// cells outside the chromosome's readable range [dlo,dhi) are staged as 0.0,
-// which is exactly the reference's "beyond the ends is zero" rule.
+// The sliding sum and the direct FIR stage a tile of the signal plus its window halo in shared memory; the
+// block sum streams (one thread per block), as does the shared-product FIR of gdsp_smooth_sym.cu (one thread
+// per strip).  Cells outside the chromosome's readable range [dlo,dhi) count as 0.0, which is exactly the
+// reference's "beyond the ends is zero" rule.
 #include "gdsp_common.cuh"
 
 // ---------------------------------------------------------------------------
