@@ -1253,6 +1253,18 @@ dspop* gd_pipeline_head (void) { return pipeline; }
 int    gd_output_inhibited (void) { return inhibitOutput; }
 
 /* run the operators [first, stop): consecutive pointwise ones as a single fused launch */
+/* NVTX ranges around every operator of the pipeline (and around a fused run of pointwise operators), so that a
+ * timeline (nsys) or an ncu report shows which kernels belong to which command-line operator.  Header-only
+ * (nvtx3): without a profiler attached a push/pop is a pointer test.  Built when the CUDA headers are present. */
+#ifdef GDSP_NVTX
+#include <nvtx3/nvToolsExt.h>
+#define GD_RANGE_PUSH(name) nvtxRangePushA (name)
+#define GD_RANGE_POP()      nvtxRangePop ()
+#else
+#define GD_RANGE_PUSH(name) ((void) 0)
+#define GD_RANGE_POP()      ((void) 0)
+#endif
+
 static void exec_range (dspop* first, dspop* stop)
 	{
 	dspop* op = first;
@@ -1270,17 +1282,21 @@ static void exec_range (dspop* first, dspop* stop)
 			}
 		if (scan != op)
 			{
+			GD_RANGE_PUSH ("pointwise (fused)");
 			if (n > 0) gd_check (gdsp_pointwise (gd.ctx, gd.genome, gd.sig, gd.sig, prog, n), "pointwise");
+			GD_RANGE_POP ();
 			for (int i = 0; i < n; i++) gd_pw_release (&res[i]);
 			op = scan;
 			continue;
 			}
+		GD_RANGE_PUSH (op->name);
 		if (op->atRandom || gd_is_genome_capable (op))
 			(*op->funcApply) (op, "*", gd.maxLength, NULL);
 		else
 			/* an operator written against the reference contract: one chromosome vector at a time */
 			for (int i = 0; i < gd.nchrom; i++)
 				(*op->funcApply) (op, chromsSorted[i]->chrom, chromsSorted[i]->length, chromsSorted[i]->valVector);
+		GD_RANGE_POP ();
 		op = op->next;
 		}
 	}
