@@ -286,6 +286,7 @@ int gdsp_smooth_sym_launch (gdsp_ctx* c, gdsp_layout* L, const double* in, doubl
 	TileMap tm;
 	GDSP_TRY (gdsp_layout_tilemap (L, (uint32_t) S, &tm));
 	const uint32_t S32 = (uint32_t) S;
+	if (tm.ntiles == 0) return GDSP_OK;                          // a layout without cells
 	const uint64_t blocks = (tm.ntiles + SY_THREADS - 1) / SY_THREADS;
 	sym_kernel_t kern = table[K];
 	void* args[] = { (void*) &L->d, (void*) &tm.d_base, (void*) &L->nseg, (void*) &tm.ntiles, (void*) &in, (void*) &out,
