@@ -1,5 +1,5 @@
-"""A/B timing of gdsp_smooth's two kernels on the hg38 layout (CUDA events, after warm-up).
-usage: smooth_ab.py <scale> <W[:T,K]> ...   (T,K: forced split of the shared-product kernel, GDSP_SYM_TK)"""
+"""A/B timing of gdsp_smooth's two kernels on the hg38 layout (CUDA events, best of 3 after warm-up), with a bit
+comparison of their results.  usage: smooth_ab.py <scale> <W> ...   (GDSP_SYM_STRIP=<cells> overrides the strip length)"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -23,9 +23,7 @@ def timed(fn, reps=3):
     return best
 last = None
 for spec in (sys.argv[2:] or ["101", "31", "11", "1001", "55"]):
-    W = int(spec.split(":")[0])
-    if ":" in spec: os.environ["GDSP_SYM_TK"] = spec.split(":")[1]
-    else: os.environ.pop("GDSP_SYM_TK", None)
+    W = int(spec)
     if last != W:
         g.sig.copy_(depth); g.smooth(W, direct=True); ref = g.sig.clone()
         td = timed(lambda: g.smooth(W, direct=True)); last = W
