@@ -8,6 +8,7 @@
 // per strip).  Cells outside the chromosome's readable range [dlo,dhi) count as 0.0, which is exactly the
 // reference's "beyond the ends is zero" rule.
 #include "gdsp_common.cuh"
+#include <stdlib.h>
 
 // ---------------------------------------------------------------------------
 // staging helper: smem[idx(j)] = in[g0 + j] for j in [0,count), zero outside
@@ -170,6 +171,90 @@ k_block_sum (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base,
 		}
 	// any other block (odd widths, the ends of a chromosome, a slab boundary): cell by cell; cells outside the readable
 	// range count as 0.0, only owned cells are written
+	{
+	const int64_t g = g0;
+	t = (g >= (int64_t) sd.dlo && g < (int64_t) sd.dhi) ? sig[g] : 0.0;
+	}
+	for (uint32_t k = 1; k < bl; k++)
+		{
+		const int64_t g = g0 + (int64_t) k;
+		t += (g >= (int64_t) sd.dlo && g < (int64_t) sd.dhi) ? sig[g] : 0.0;
+		}
+	const double y = denomActual ? t / (double) bl : t / denom;
+	for (uint32_t k = 0; k < bl; k++)
+		{
+		const int64_t g = g0 + (int64_t) k;
+		if (g >= (int64_t) sd.lo && g < (int64_t) sd.hi) sig[g] = (k == 0) ? y : zeroVal;
+		}
+	}
+
+// The same with FOUR lanes per block, for widths that are a multiple of 4 (--window=100): lane q of a group takes
+// cells 4q..4q+3 of every 16-cell chunk, so the group's 256-bit loads cover one whole 128-byte line and a warp-wide
+// load touches 8 lines instead of 32 (with a thread per block the L1 tag stage was the limit: ncu lg_throttle 107
+// warps per issue, 0.80 of the HBM peak).  The running sum still visits the cells in the reference's order: it is
+// handed from lane to lane with a shuffle every four additions.
+__global__ void __launch_bounds__(BS_THREADS)
+k_block_sum4 (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg, uint64_t nblocks,
+              double* __restrict__ sig, uint32_t W, double denom, int denomActual, double zeroVal)
+	{
+	const int lane = threadIdx.x & 31, q = lane & 3, g4 = lane & ~3;
+	const uint64_t gid = ((uint64_t) blockIdx.x * BS_THREADS + threadIdx.x) >> 2;
+	bool have = (gid < nblocks);
+	SegDev sd;  uint32_t bl = 0;  int64_t g0 = 0;
+	if (have)
+		{
+		const int seg = bs_block_seg (base, nseg, gid);
+		sd = segs[seg];
+		const uint64_t c0   = ((uint64_t) sd.pos0 / W + (gid - __ldg (base + seg))) * W;
+		const uint64_t cEnd = ((uint64_t) sd.pos0 + (sd.dhi - sd.lo) < (uint64_t) sd.chromLen)
+		                    ? (uint64_t) sd.pos0 + (sd.dhi - sd.lo) : (uint64_t) sd.chromLen;
+		uint64_t c1 = c0 + W;  if (c1 > cEnd) c1 = cEnd;
+		have = (c0 < c1);
+		bl = have ? (uint32_t) (c1 - c0) : 0u;
+		g0 = (int64_t) sd.lo + ((int64_t) c0 - (int64_t) sd.pos0);
+		}
+	const bool whole = have && (g0 >= (int64_t) sd.lo) && (g0 + (int64_t) bl <= (int64_t) sd.hi)      // readable and owned,
+	                        && (bl & 3u) == 0 && (g0 & 3) == 0;                                     // and made of aligned quads
+	// the four lanes of a group agree on `whole` (same block); groups of a warp may differ
+	double t = 0.0;
+	if (__any_sync (0xffffffffu, whole))
+		{
+		double* const p = sig + g0;
+		const uint32_t nq = whole ? bl >> 2 : 0u;                   // quads of the block; quad j belongs to lane j & 3
+		uint32_t nqMax = nq;
+		#pragma unroll
+		for (int d = 16; d >= 4; d >>= 1) { const uint32_t o = __shfl_xor_sync (0xffffffffu, nqMax, d);  nqMax = (o > nqMax) ? o : nqMax; }
+		double a[4] = { 0.0, 0.0, 0.0, 0.0 }, b[4];
+		if ((uint32_t) q < nq) ldg_stream4 (p + 4 * q, a[0], a[1], a[2], a[3]);
+		for (uint32_t j0 = 0; j0 < nqMax; j0 += 4)                  // one 16-cell chunk per trip
+			{
+			const uint32_t jn = j0 + 4 + q;                         // this lane's quad of the next chunk: in flight during the hops
+			if (jn < nq) ldg_stream4 (p + 4 * jn, b[0], b[1], b[2], b[3]);
+			#pragma unroll
+			for (int h = 0; h < 4; h++)
+				{
+				const double tin = __shfl_sync (0xffffffffu, t, g4 + ((h + 3) & 3));
+				if (q == h && j0 + h < nq)
+					{
+					if (j0 + h == 0) t = a[0];                          // the fold is seeded with the first cell (sum.c:230)
+					else { t = tin;  t += a[0]; }
+					t += a[1];  t += a[2];  t += a[3];
+					}
+				}
+			#pragma unroll
+			for (int k = 0; k < 4; k++) a[k] = b[k];
+			}
+		const double tot = __shfl_sync (0xffffffffu, t, g4 + (int) ((nq - 1) & 3u));              // the lane that added the last quad
+		if (whole)
+			{
+			const double y = denomActual ? tot / (double) bl : tot / denom;
+			for (uint32_t j = q; j < nq; j += 4)
+				stg_stream4 (p + 4 * j, (j == 0) ? y : zeroVal, zeroVal, zeroVal, zeroVal);
+			}
+		}
+	if (whole || !have || q != 0) return;
+	// any other block (the ends of a chromosome, a slab boundary): lane 0 of the group, cell by cell; cells outside the
+	// readable range count as 0.0, only owned cells are written
 	{
 	const int64_t g = g0;
 	t = (g >= (int64_t) sd.dlo && g < (int64_t) sd.dhi) ? sig[g] : 0.0;
@@ -513,8 +598,12 @@ extern "C" int gdsp_block_sum (gdsp_ctx* c, const gdsp_layout* L_, double* sig, 
 		GDSP_TRY (gdsp_ws (c, 2, sizeof (uint64_t) * (L->nseg + 1), &ws));
 		GDSP_CUDA (cudaMemcpyAsync (ws, base.data (), sizeof (uint64_t) * (L->nseg + 1), cudaMemcpyHostToDevice, c->stream));
 		GDSP_CUDA (cudaStreamSynchronize (c->stream));      // base[] is a host temporary
-		k_block_sum<<<(unsigned) ((nb + BS_THREADS - 1) / BS_THREADS), BS_THREADS, 0, c->stream>>> (L->d, (const uint64_t*) ws, L->nseg, nb, sig, W,
-		                                                                                         denom, denomActual, zeroVal);
+		if ((W & 3u) == 0 && W >= 16 && !getenv ("GDSP_BLOCKSUM_THREAD"))
+			k_block_sum4<<<(unsigned) ((4 * nb + BS_THREADS - 1) / BS_THREADS), BS_THREADS, 0, c->stream>>> (L->d, (const uint64_t*) ws, L->nseg, nb, sig, W,
+			                                                                                              denom, denomActual, zeroVal);
+		else
+			k_block_sum<<<(unsigned) ((nb + BS_THREADS - 1) / BS_THREADS), BS_THREADS, 0, c->stream>>> (L->d, (const uint64_t*) ws, L->nseg, nb, sig, W,
+			                                                                                         denom, denomActual, zeroVal);
 		GDSP_KERNEL_CHECK ();
 		return GDSP_OK;
 		}

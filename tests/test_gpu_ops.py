@@ -276,6 +276,16 @@ def test_block_sum(genome, orc, kind, W):
             scale_fn=lambda a: orc.block_sum(a, W, 1.0, W == 101, 0.0))
 
 
+@pytest.mark.parametrize("W", [4, 8, 12, 16, 20, 36, 64, 128, 260, 1000, 4092])
+def test_block_sum_four_lanes_per_block(genome, orc, W):
+    """k_block_sum4 (widths that are a multiple of 4, from 16 up: a block's quads are dealt out to four lanes and the
+    running sum is handed on between them) and its neighbours below 16; general reals, so that any change in the
+    order of the additions shows; `--denom=actual` makes the short last block of every chromosome count"""
+    inputs = load(genome, np.random.default_rng(W), "real")
+    genome.sum(W, denom=3.0, denom_actual=(W % 8 == 0), zero=0.25)
+    compare(genome, inputs, lambda v: orc.block_sum(v, W, 3.0, W % 8 == 0, 0.25), exact=True, what="sum W=%d" % W)
+
+
 @pytest.mark.parametrize("kind", ["int", "real"])
 def test_block_sum_whole_chromosome(genome, orc, kind):
     inputs = load(genome, np.random.default_rng(3), kind)
