@@ -758,6 +758,8 @@ k_clump_classify (const SegDev* __restrict__ segs, const uint64_t* __restrict__ 
 	// (the groups the test looks back at must belong to this segment: a slab piece starts at chromosome coordinate
 	// pos0 > 0, and what lies before its first tile in the record arrays is another segment)
 	bool pass = (sd.hi - t0 >= CL_TILE) && (Lmin >= CLF_GROUP) && (tis * CL_TILE >= (uint64_t) Lmin) && (tis + 1 < tilesInSeg);
+	// (the first own tile of a slab piece also reports the piece's suffix maximum: it takes the full path)
+	if (wk.segSufMax != NULL && wk.segFlags != NULL && tis == (uint64_t) (wk.segFlags[lo] & 1u)) pass = false;
 	// (slab pieces: the tile of the neighbour's cells in front of a piece is never marked at all, k_clump_mark returns
 	// before it looks at this flag; its groups do serve as the Lmin cells before the piece's first own tile)
 	for (int w = 0; w < CLF_GROUPS && pass; w++)
@@ -794,6 +796,32 @@ k_clump_mark (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base
 	// block waits on (the tiles to its right) has already started
 	const uint32_t ticket = scan_take_ticket (stMax.ticket);
 	const uint64_t tile = ntiles - 1 - ticket;
+
+	// A tile k_clump_classify found without a valid end has the aggregate -inf in the suffix-maximum chain -- published
+	// at once, so the tiles on its left do not wait for any work here -- and with e the maximum valid prefix sum to its
+	// right, a cell p is marked iff e >= M[p-1] >= M at the tile's end: if e is below that, the tile's words are zero and
+	// the signal is never read.  On a thresholded track that is mostly below the threshold (clump after open/close in
+	// BASELINE config 4) that is nearly every tile, so this comes first: it needs the tile's index and nothing else
+	// (a quiet tile is a whole one, neither the last of its chromosome nor a slab piece's halo or first own tile).
+	bool haveLook = false;  double lookE = 0.0;
+	if (wk.tquiet[tile] != 0)
+		{
+		__shared__ double s_look;
+		const double mEnd = wk.carry[(tile + 1) * CLF_GROUPS].y;   // M before the next tile = M at this tile's end
+		if (threadIdx.x < 32)
+			{
+			const double e = scan_lookback<double> (stMax, ticket, false, -CLF_INF, -CLF_INF, [] (double a, double b) { return (b > a) ? b : a; });
+			if (threadIdx.x == 0) s_look = e;
+			}
+		__syncthreads ();
+		lookE = s_look;  haveLook = true;
+		if (lookE < mEnd)
+			{
+			if (threadIdx.x < CLF_WORDS) { wk.Bm[tile * CLF_WORDS + threadIdx.x] = 0u;  wk.Bq[tile * CLF_WORDS + threadIdx.x] = 0u; }
+			return;
+			}
+		}
+
 	int seg;  uint64_t tis;
 	tile_to_seg (base, nseg, tile, seg, tis);
 	const SegDev sd = segs[seg];
@@ -821,29 +849,6 @@ k_clump_mark (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base
 		}
 	const uint32_t reach = (Lmin > 0) ? Lmin : 1;                 // M[p-1] is needed even when Lmin is 0
 	const uint32_t hrows = (reach + CLF_GROUP - 1) / CLF_GROUP;   // <= 8 (the host checked): at most one per warp
-
-	// A tile k_clump_classify found without a valid end has the aggregate -inf in the suffix-maximum chain -- published
-	// at once, so the tiles on its left do not wait for any work here -- and with e the maximum valid prefix sum to its
-	// right, a cell p is marked iff e >= M[p-1] >= M at the tile's end: if e is below that, the tile's words are zero and
-	// the signal is never read.  On a thresholded track that is mostly below the threshold (clump after open/close in
-	// BASELINE config 4) that is nearly every tile.
-	bool haveLook = false;  double lookE = 0.0;
-	if (wk.tquiet[tile] != 0)
-		{
-		__shared__ double s_look;
-		if (threadIdx.x < 32)
-			{
-			const double e = scan_lookback<double> (stMax, ticket, false, -CLF_INF, -CLF_INF, [] (double a, double b) { return (b > a) ? b : a; });
-			if (threadIdx.x == 0) { s_look = e;  if (sufMaxOut != NULL) *sufMaxOut = e; }
-			}
-		__syncthreads ();
-		lookE = s_look;  haveLook = true;
-		if (lookE < wk.carry[(tile + 1) * CLF_GROUPS].y)          // (never the last tile of its segment: the next tile's carry exists)
-			{
-			if (threadIdx.x < CLF_WORDS) { wk.Bm[tile * CLF_WORDS + threadIdx.x] = 0u;  wk.Bq[tile * CLF_WORDS + threadIdx.x] = 0u; }
-			return;
-			}
-		}
 
 	// prefix minima of the halo groups (the tail of the previous tile of this chromosome)
 	if ((uint32_t) warp < hrows && (uint64_t) (hrows - warp) * CLF_GROUP <= c0)
