@@ -88,6 +88,7 @@ SIGNATURES = {
     "gdsp_ivl_table_destroy": (None, [_vp]),
     "gdsp_pointwise": (_i, [_vp, _vp, _vp, _vp, C.POINTER(PwOp), _i]),
     "gdsp_minmax": (_i, [_vp, _vp, _vp, _u32, _d, _d, _dp, _dp, _u64p]),
+    "gdsp_count_non_integer": (_i, [_vp, _vp, _vp, _d, _u64p]),
     "gdsp_percentiles": (_i, [_vp, _vp, _vp, _vp, _u64, _u32, _d, _d, _u32p, _i, _dp, _u64p]),
     "gdsp_percentiles_ranked": (_i, [_vp, _vp, _vp, _vp, _u64, _u32, _d, _d, _u32p, _i, _dp, _u64p, _u64p, _u64p, _u64p]),
     "gdsp_pct_count_nan": (_i, [_vp, _vp, _vp, _u32, _d, _d, _u64p, _i, C.POINTER(C.c_uint8), _u64p, _vp, _u64, _u64p, _u64p]),

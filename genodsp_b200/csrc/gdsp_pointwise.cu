@@ -371,6 +371,27 @@ k_minmax (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, in
 		}
 	}
 
+// cells that are NOT integers of magnitude <= limit (NaN and infinities count): when there are none,
+// adding integer interval values in any order gives the reference's bits (add.c:280-281)
+__global__ void __launch_bounds__(256)
+k_count_non_integer (const SegDev* __restrict__ segs, const uint64_t* __restrict__ base, int nseg,
+                     const double* __restrict__ sig, double limit, unsigned long long* __restrict__ res)
+	{
+	int seg;  uint64_t tis;
+	tile_to_seg (base, nseg, blockIdx.x, seg, tis);
+	const SegDev sd = segs[seg];
+	const uint64_t t0 = sd.lo + tis * MMR_TILE;
+	uint64_t t1 = t0 + MMR_TILE;  if (t1 > sd.hi) t1 = sd.hi;
+	unsigned int bad = 0;
+	for (uint64_t i = t0 + threadIdx.x; i < t1; i += 256)
+		{
+		const double v = sig[i];
+		if (!(fabs (v) <= limit) || v != rint (v)) bad++;
+		}
+	bad = __reduce_add_sync (0xffffffffu, bad);
+	if ((threadIdx.x & 31) == 0 && bad != 0) atomicAdd (res, (unsigned long long) bad);
+	}
+
 // ---------------------------------------------------------------------------
 // C-ABI
 // ---------------------------------------------------------------------------
@@ -522,6 +543,27 @@ extern "C" int gdsp_minmax (gdsp_ctx* c, const gdsp_layout* L_, const double* si
 		};
 	if (h_min) *h_min = (res[0] == ~0ull && res[1] == 0ull) ? DBL_MAX  : unkey (res[0]);
 	if (h_max) *h_max = (res[0] == ~0ull && res[1] == 0ull) ? -DBL_MAX : unkey (res[1]);
+	return GDSP_OK;
+	}
+
+extern "C" int gdsp_count_non_integer (gdsp_ctx* c, const gdsp_layout* L_, const double* sig, double limit, uint64_t* h_count)
+	{
+	gdsp_layout* L = (gdsp_layout*) L_;
+	GDSP_REQUIRE (c && L && sig && h_count, "gdsp_count_non_integer: NULL argument");
+	void* ws;
+	GDSP_TRY (gdsp_ws (c, 2, 64, &ws));
+	GDSP_CUDA (cudaMemsetAsync (ws, 0, sizeof (unsigned long long), c->stream));
+	TileMap tm;
+	GDSP_TRY (gdsp_layout_tilemap (L, MMR_TILE, &tm));
+	if (tm.ntiles != 0)
+		{
+		k_count_non_integer<<<(unsigned) tm.ntiles, 256, 0, c->stream>>> (L->d, tm.d_base, L->nseg, sig, limit, (unsigned long long*) ws);
+		GDSP_KERNEL_CHECK ();
+		}
+	unsigned long long res = 0;
+	GDSP_CUDA (cudaMemcpyAsync (&res, ws, sizeof (res), cudaMemcpyDeviceToHost, c->stream));
+	GDSP_CUDA (cudaStreamSynchronize (c->stream));
+	*h_count = res;
 	return GDSP_OK;
 	}
 

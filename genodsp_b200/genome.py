@@ -504,6 +504,11 @@ class Genome:
                                    C.byref(a), C.byref(b), C.byref(n)))
         return a.value, b.value, int(n.value)
 
+    def count_non_integer(self, limit=2.0 ** 52):
+        n = C.c_uint64()
+        check(self.lib.gdsp_count_non_integer(self.ctx, self.layout, self._p(self.sig), float(limit), C.byref(n)))
+        return int(n.value)
+
     def invert(self, mid=None):
         if mid is None:                               # add.c:907-926
             lo, hi, _ = self.minmax()

@@ -873,8 +873,10 @@ void read_intervals (FILE* f, int valCol, int originOne_, int overlapOp, int cle
 		 * (genodsp.c:1327).  For missingVal==0 that is a plain sum; otherwise the uncovered cells are
 		 * set to missingVal afterwards through the union of the intervals. */
 		int mode = (valCol == -1 || (allInt && sumAbs < 2.0e9)) ? GDSP_ACC_I32 : GDSP_ACC_F64;
-		/* real (non-integer) values: every cell must see the reference's additions in file order */
-		if (mode == GDSP_ACC_F64
+		/* real (non-integer) values: every cell must see the reference's additions in file order.  So must
+		 * any input with a non-zero missingVal: a running sum that comes back to missingVal reads as "not
+		 * yet covered" and the next interval replaces it (--missing=3 --novalue: depth 4 gives 1) */
+		if ((mode == GDSP_ACC_F64 || (clear && missingVal != 0.0))
 		 && gd_apply_intervals_exact (&l, clear ? GD_EXACT_CLEAR : GD_EXACT_ADD, missingVal, "input"))
 			{ ivlist_free (&l);  return; }
 		void* work = gd_work (gdsp_accumulate_work_bytes (gd.genome, gd.cells, mode));

@@ -300,13 +300,10 @@ static int ex_by_pos (const void* a, const void* b)
 
 typedef struct exseg { u32* bp;  u64 np;  u32* cnt;  u64* off;  double* vals;  u32 maxDepth; } exseg;
 
-int gd_apply_intervals_exact (ivlist* l, int mode, valtype missing, const char* opName)
+/* phase 1 (host only): elementary pieces of every chromosome and their value lists in file order;
+ * false when some piece is too deep or the lists would not fit (ex is still to be released) */
+static int ex_build (ivlist* l, exseg* ex)
 	{
-	if (l->n == 0)
-		{
-		if (mode == GD_EXACT_CLEAR) gd_check (gdsp_fill (gd.ctx, gd.genome, gd.sig, missing), opName);
-		return true;
-		}
 	/* per chromosome (segment): intervals grouped, file order kept */
 	u64* segCount = (u64*) calloc ((size_t) gd.nchrom + 1, sizeof (u64));
 	for (u64 k = 0; k < l->n; k++) segCount[l->seg[k] + 1]++;
@@ -319,8 +316,6 @@ int gd_apply_intervals_exact (ivlist* l, int mode, valtype missing, const char* 
 	free (cur);
 	}
 
-	/* phase 1 (host only): elementary pieces of every chromosome and their value lists in file order */
-	exseg* ex = (exseg*) calloc ((size_t) gd.nchrom, sizeof (exseg));
 	int ok = true;
 	/* piece-value slots we are willing to hold: an interval that spans p elementary pieces takes p slots */
 	u64 budget = 64 * l->n + (1u << 20);
@@ -377,6 +372,56 @@ int gd_apply_intervals_exact (ivlist* l, int mode, valtype missing, const char* 
 		ex[s].off = off;  ex[s].vals = vals;
 		}
 	free (segCount);  free (order);
+	return ok;
+	}
+
+static void ex_release (exseg* ex)
+	{
+	for (int s = 0; s < gd.nchrom; s++) { free (ex[s].bp);  free (ex[s].cnt);  free (ex[s].off);  free (ex[s].vals); }
+	free (ex);
+	}
+
+/* `input --overlap=min|max` when the plain extreme is not what the reference computes.  Its rule per
+ * position, interval after interval in file order (genodsp.c:1307-1322), is
+ *     v == missingVal ? v = val : (val < v ? v = val : v)          (val > v for max)
+ * which is the smallest (largest) covering value UNLESS the running value comes back to missingVal --
+ * an interval whose value equals missingVal, e.g. a zero-valued bedGraph row with the default
+ * --missing=0 -- after which the next interval overwrites it; a NaN value sticks once it is assigned.
+ * The fold of every elementary piece's ordered value list is that rule itself.  Pieces come out in
+ * layout order; false (nothing appended) when the lists would not fit. */
+int gd_fold_intervals_minmax (ivlist* l, int wantMax, valtype missing, ivlist* outp)
+	{
+	if (l->n == 0) return true;
+	exseg* ex = (exseg*) calloc ((size_t) gd.nchrom, sizeof (exseg));
+	int ok = ex_build (l, ex);
+	if (ok)
+		for (int s = 0; s < gd.nchrom; s++)
+			for (u64 p = 0; p < ex[s].np; p++)
+				{
+				if (ex[s].cnt[p] == 0) continue;
+				const double* vals = ex[s].vals + ex[s].off[p];
+				double v = missing;
+				for (u32 k = 0; k < ex[s].cnt[p]; k++)
+					{
+					double val = vals[k];
+					if (v == missing) v = val;
+					else if (wantMax ? (val > v) : (val < v)) v = val;
+					}
+				ivlist_push (outp, (u32) s, ex[s].bp[p], ex[s].bp[p + 1], v);
+				}
+	ex_release (ex);
+	return ok;
+	}
+
+int gd_apply_intervals_exact (ivlist* l, int mode, valtype missing, const char* opName)
+	{
+	if (l->n == 0)
+		{
+		if (mode == GD_EXACT_CLEAR) gd_check (gdsp_fill (gd.ctx, gd.genome, gd.sig, missing), opName);
+		return true;
+		}
+	exseg* ex = (exseg*) calloc ((size_t) gd.nchrom, sizeof (exseg));
+	int ok = ex_build (l, ex);
 	if (getenv ("GENODSP_TIMING") != NULL)
 		fprintf (stderr, "[timing] exact interval application: %s\n", ok ? "yes" : "no (difference array)");
 
@@ -402,7 +447,6 @@ int gd_apply_intervals_exact (ivlist* l, int mode, valtype missing, const char* 
 				}
 		ivlist_free (&layer);
 		}
-	for (int s = 0; s < gd.nchrom; s++) { free (ex[s].bp);  free (ex[s].cnt);  free (ex[s].off);  free (ex[s].vals); }
-	free (ex);
+	ex_release (ex);
 	return ok;
 	}

@@ -65,6 +65,7 @@ typedef struct ivlist
 #define GD_EXACT_SUB   1
 #define GD_EXACT_CLEAR 2
 int  gd_apply_intervals_exact (ivlist* l, int mode, valtype missing, const char* opName);
+int  gd_fold_intervals_minmax (ivlist* l, int wantMax, valtype missing, ivlist* out);
 
 void ivlist_init    (ivlist* l);
 void ivlist_push    (ivlist* l, u32 seg, u32 start, u32 end, double val);

@@ -159,7 +159,16 @@ void gd_input_minmax (ivlist* l, int overlapOp, arg_dont_complain(int clear), va
 	gd_check (gdsp_fill (gd.ctx, gd.genome, gd.sig, missingVal), "input");
 	if (l->n == 0) return;
 	ivlist out;  ivlist_init (&out);
-	gd_paint_extreme (l, overlapOp == ri_overlapMax, &out);
+	/* the plain extreme is the reference's result unless a value equals missingVal (the running value
+	 * then reads as "not yet covered" and the next interval overwrites it) or is NaN: those inputs go
+	 * through the file-order fold of every piece (gd_device.c) */
+	int needFold = false;
+	for (u64 k = 0; k < l->n && !needFold; k++) needFold = (l->val[k] == missingVal) || (l->val[k] != l->val[k]);
+	if (!needFold || !gd_fold_intervals_minmax (l, overlapOp == ri_overlapMax, missingVal, &out))
+		{
+		if (needFold) fprintf (stderr, "[input] WARNING: intervals too deep for the file-order fold; a value equal to --missing counts as a value\n");
+		gd_paint_extreme (l, overlapOp == ri_overlapMax, &out);
+		}
 	gdsp_ivl_table* t;
 	gd_check (gdsp_ivl_table_create (gd.ctx, gd.genome, out.seg, out.start, out.end, out.val, out.n, &t), "input");
 	gdsp_pw_op p;  memset (&p, 0, sizeof (p));

@@ -73,9 +73,22 @@ static void resolve (dspop* _op, char** var, valtype* dst, const char* what, con
 
 /* ---- interval file -> device table ------------------------------------------ */
 
-/* ordered fold of overlapping add/subtract intervals into disjoint pieces would be needed for
- * bit-exact sums of arbitrary reals; integer and dyadic values (exact sums) go through the
- * accumulate kernels instead */
+/* true when the list is in layout order and no two intervals share a cell (one pass, no sort: a
+ * file in any other order counts as "may overlap") */
+static int ivlist_sorted_disjoint (const ivlist* l)
+	{
+	for (u64 k = 1; k < l->n; k++)
+		{
+		if (l->seg[k] < l->seg[k-1]) return false;
+		if (l->seg[k] == l->seg[k-1] && l->start[k] < l->end[k-1]) return false;
+		}
+	return true;
+	}
+
+/* The reference adds interval after interval, cell by cell: ((v+a)+b) (add.c:280-281).  Integer values
+ * on an integer-valued signal give the same bits in any order and go through the accumulate kernels
+ * (one difference array: v + (a+b)).  Everything else -- real values, or integer values that overlap
+ * on a signal holding non-integers -- is applied layer by layer in file order. */
 static void add_file_now (dspop_pw* op, double sign)
 	{
 	ivlist l;
@@ -89,7 +102,13 @@ static void add_file_now (dspop_pw* op, double sign)
 		sumAbs += fabs (l.val[k]);
 		}
 	int mode = (allInt && sumAbs < 2.0e9) ? GDSP_ACC_I32 : GDSP_ACC_F64;
-	/* real values: the reference's additions (subtractions) cell by cell in file order */
+	if (mode == GDSP_ACC_I32 && !ivlist_sorted_disjoint (&l))
+		{
+		u64 nonInt = 0;
+		gd_check (gdsp_count_non_integer (gd.ctx, gd.genome, gd.sig, 4503599627370496.0 /* 2^52 */, &nonInt), op->common.name);
+		if (nonInt != 0) mode = GDSP_ACC_F64;
+		}
+	/* the reference's additions (subtractions) cell by cell in file order */
 	if (mode == GDSP_ACC_F64 && gd_apply_intervals_exact (&l, sign < 0 ? GD_EXACT_SUB : GD_EXACT_ADD, 0.0, op->common.name))
 		{
 		ivlist_free (&l);

@@ -258,6 +258,12 @@ int  gdsp_minmax (gdsp_ctx* ctx, const gdsp_layout* lay, const double* sig,
                   uint32_t stride, double min_allowed, double max_allowed,
                   double* h_min, double* h_max, uint64_t* h_count);
 
+/* how many owned cells are NOT integers with |v| <= limit (NaN, infinities count).  The host's
+ * add / subtract <file> (add.c:280-281 adds interval after interval, cell by cell) may fold
+ * overlapping integer-valued intervals into one difference array only when this is 0. */
+int  gdsp_count_non_integer (gdsp_ctx* ctx, const gdsp_layout* lay, const double* sig,
+                             double limit, uint64_t* h_count);
+
 /* percentile --preserve: what write_all_chromosomes + read_all_chromosomes
  * (genodsp.c:1717-1775) leave in the vectors: every value v != 0 becomes
  * strtod(printf("%.10f", v)) (inf -> DBL_MAX), every zero +0.0.  Exact integer

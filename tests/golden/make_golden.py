@@ -65,6 +65,19 @@ CASES = {
     "percentile_collect_high_rank": (C + ["--novalue", "=", "percentile", "99", "--min=2", "=", "binarize", "--threshold=percentile99"], "reads.iv"),
     "percentile_general_rank": (C + ["--novalue", "=", "percentile", "30", "=", "addconst", "0"], "reads.iv"),
     "subtract_novalue_inherited": (C + ["--novalue", "=", "subtract", "trackB.iv"], "reads.iv"),
+    # read_intervals' per-cell rule (genodsp.c:1307-1330) when the running value comes back to missingVal: it reads as
+    # "not yet covered" and the next interval overwrites it -- zero-valued rows under --overlap=min|max, a depth that
+    # reaches --missing, a sum that passes through it
+    "input_overlap_min_zero_rows": (C + ["=", "input", "quirks.iv", "--overlap=min"], "vals.iv"),
+    "input_overlap_max_missing2": (C + ["--uncovered:show", "=", "input", "quirks.iv", "--overlap=max", "--missing=2"], "vals.iv"),
+    "input_overlap_min_missing_neg1": (C + ["--uncovered:show", "=", "input", "quirks.iv", "--overlap=minimum", "--missing=-1"], "vals.iv"),
+    "input_depth_missing3": (C + ["--uncovered:show", "=", "input", "reads.iv", "--novalue", "--missing=3"], "vals.iv"),
+    "input_sum_missing5": (C + ["--uncovered:show", "=", "input", "quirks.iv", "--missing=5"], "vals.iv"),
+    # add.c:280-281 adds interval after interval: overlapping integer values on a signal that holds non-integers are
+    # ((v+a)+b), not v+(a+b)
+    "add_overlapping_ints_on_reals": (C + ["--novalue", "--precision=17", "=", "smooth", "--window=11", "=", "add", "quirks.iv",
+                                           "--value=4", "=", "subtract", "quirks.iv", "--value=4"], "reads.iv"),
+    "add_overlapping_ints_on_ints": (C + ["--novalue", "=", "add", "quirks.iv", "--value=4"], "reads.iv"),
 }
 
 
@@ -102,6 +115,11 @@ def write_inputs():
         f.write("# depth -> score\n")
         for x in rng.permutation(np.arange(0, 26, 2)):
             f.write("%r %r\n" % (float(x), float(rng.integers(-40, 41)) / 8))
+    with open(os.path.join(HERE, "quirks.iv"), "w") as f:          # unsorted, deeply overlapping, small integer values
+        for _ in range(400):                                       # (many zeros, twos, fives and minus ones)
+            n, l = CHROMS[int(rng.integers(0, 3))]
+            a = int(rng.integers(0, l - 200))
+            f.write("%s\t%d\t%d\t%d\n" % (n, a, a + int(rng.integers(1, 200)), int(rng.choice([0, 0, 2, 5, -1, 3, 7, -4]))))
 
 
 def main():

@@ -203,6 +203,38 @@ class Pipeline:
             at = 0
             for n in names:
                 self.v[n] = state[at:at + self.v[n].size].copy(); at += self.v[n].size
+        elif name == "input":
+            # op_input_apply (opio.c:225-256) -> read_intervals with clear (genodsp.c:1307-1330): every vector
+            # starts at missingVal (an int, opio.c:35) and takes the intervals one after the other, cell by cell
+            icol = opts["val_col"]
+            if "--novalue" in args or "--novalues" in args or "--value=none" in args:
+                icol = -1
+            elif self.kw(args, ["--value="]) is not None:
+                icol = int(self.kw(args, ["--value="])) - 1
+            origin = opts["origin"]
+            if "--origin=one" in args or "--origin=1" in args:
+                origin = 1
+            if "--origin=zero" in args or "--origin=0" in args:
+                origin = 0
+            missing = float(int(float(self.kw(args, ["--missing="], "0"))))
+            ov = self.kw(args, ["--overlap="], "sum")[:3]
+            iv = self.read_intervals(pos[0], icol, origin)
+            for n, _ in self.chroms:
+                v = self.v[n]
+                v[:] = missing
+                for s, e, val in zip(*iv[n]):
+                    s, e = max(s, 0), min(e, v.size)
+                    if s >= e:
+                        continue
+                    seg = v[s:e]
+                    fresh = seg == missing
+                    with np.errstate(invalid="ignore"):
+                        if ov == "min":
+                            seg[:] = np.where(fresh | (val < seg), val, seg)
+                        elif ov == "max":
+                            seg[:] = np.where(fresh | (val > seg), val, seg)
+                        else:
+                            seg[:] = np.where(fresh, val, seg + val)
         elif name in ("add", "subtract", "multiply", "divide", "and", "masknot"):
             iv = self.read_intervals(pos[0], -1 if name == "masknot" else fcol)    # masknot reads no value column (mask.c:533)
             for n, _ in self.chroms:

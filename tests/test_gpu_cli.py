@@ -290,3 +290,34 @@ def test_real_valued_intervals_are_applied_in_file_order(data):
     assert_same(data, C + P, stdin="overlap.iv")
     assert_same(data, C + P + ["=", "add", "bedgraph.iv", "=", "subtract", "overlap.iv"], stdin="bedgraph.iv")
     assert_same(data, C + P + ["=", "input", "overlap.iv", "--missing=-1.5", "=", "add", "overlap.iv"], stdin="bedgraph.iv")
+
+
+def test_values_that_return_to_missing_and_integer_adds_on_real_signals(data):
+    """read_intervals' per-cell rule (genodsp.c:1307-1330): a running value equal to missingVal reads as "not yet
+    covered", so a zero-valued row under --overlap=min|max, a depth that reaches --missing or a sum that passes through
+    it is overwritten by the next interval; NaN sticks once assigned.  And add / subtract apply overlapping intervals
+    one after the other (add.c:280-281): integer values on a signal that holds non-integers are ((v+a)+b)."""
+    rng = np.random.default_rng(321)
+    with open(data / "quirks.iv", "w") as f:                   # unsorted, deeply overlapping, small integers + NaN
+        for _ in range(2000):
+            n, l = CHROMS[int(rng.integers(0, 4))]
+            a = int(rng.integers(0, max(1, l - 1500)))
+            v = ["0", "0", "2", "5", "-1", "3", "7", "-4", "nan", "2.5"][int(rng.integers(0, 10))]
+            f.write("%s\t%d\t%d\t%s\n" % (n, a, min(l, a + int(rng.integers(1, 1500))), v))
+    with open(data / "ints.iv", "w") as f:                     # the same without NaN / fractions
+        for _ in range(2000):
+            n, l = CHROMS[int(rng.integers(0, 4))]
+            a = int(rng.integers(0, max(1, l - 1500)))
+            f.write("%s\t%d\t%d\t%d\n" % (n, a, min(l, a + int(rng.integers(1, 1500))), int(rng.integers(-6, 9))))
+    P = ["--precision=17", "--uncovered:show"]
+    for ov in ("min", "max"):
+        for missing in ("0", "2", "-1"):
+            assert_same(data, C + P + ["=", "input", "quirks.iv", "--overlap=" + ov, "--missing=" + missing], stdin="vals.iv")
+        assert_same(data, C + P + ["=", "input", "ints.iv", "--overlap=" + ov], stdin="vals.iv")
+    for missing in ("3", "-2"):
+        assert_same(data, C + P + ["=", "input", "ints.iv", "--missing=" + missing], stdin="vals.iv")
+    for missing in ("3", "7"):
+        assert_same(data, C + P + ["=", "input", "reads.iv", "--novalue", "--missing=" + missing], stdin="vals.iv")
+    assert_same(data, C + ["--novalue", "--precision=17", "=", "smooth", "--window=31", "=", "add", "ints.iv", "--value=4",
+                           "=", "subtract", "ints.iv", "--value=4"])
+    assert_same(data, C + ["--novalue", "=", "add", "ints.iv", "--value=4", "=", "subtract", "ints.iv", "--value=4"])

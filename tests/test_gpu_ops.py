@@ -441,6 +441,27 @@ def test_invert_auto_mid(genome, orc):
     compare(genome, inputs, lambda v: orc.invert(v, mid), what="invert")
 
 
+def test_count_non_integer(genome):
+    """gdsp_count_non_integer: the check the host makes before it folds overlapping integer-valued
+    intervals of add / subtract into one difference array (add.c:280-281 adds them one by one)"""
+    rng = np.random.default_rng(81)
+    inputs = load(genome, rng, "int")
+    assert genome.count_non_integer() == 0
+    want = 0
+    for name, n in CHROMS:                           # a few of every kind of offender, some at tile edges
+        v = inputs[name].copy()
+        for pos, x in [(0, 0.5), (n - 1, np.nan), (n // 2, np.inf), (min(n - 1, 8191), -3.25), (min(n - 1, 8192), 2.0 ** 53),
+                       (n // 3, -0.0), (n // 5, -7.0), (n // 7, 2.0 ** 52)]:
+            v[pos] = x
+        want += int(np.count_nonzero(~((np.abs(v) <= 2.0 ** 52) & (v == np.rint(v)))))
+        genome.set_chrom(name, v)
+    assert want > 0
+    assert genome.count_non_integer() == want
+    assert genome.count_non_integer(limit=6.0) == sum(
+        int(np.count_nonzero(~((np.abs(genome.get_chrom(name)) <= 6.0) & (genome.get_chrom(name) == np.rint(genome.get_chrom(name))))))
+        for name, _ in CHROMS)
+
+
 def _sorted_disjoint(rng, genome, skip=()):
     seg, s, e, val = [], [], [], []
     for k in range(genome.nseg):
