@@ -96,6 +96,7 @@ SIGNATURES = {
     "gdsp_percentile_collect": (_i, [_vp, _vp, _vp, _vp, _u64, _vp, _u32, _d, _d, _u64p]),
     "gdsp_equal_range": (_i, [_vp, _vp, _u64, _d, _u64p, _u64p]),
     "gdsp_sort_genome": (_i, [_vp, _vp, _vp, _vp, _u64, C.POINTER(_i)]),
+    "gdsp_merge_exchange": (_i, [_vp, _vp, _vp, _u64, _u64, _u64, _u64, _u64p]),
     "gdsp_sorted_binarize": (_i, [_vp, _vp, _vp, _d, _i, _d, _d, C.POINTER(_i)]),
     "gdsp_fill_step": (_i, [_vp, _vp, _vp, _u64p, _u64, _d, _d]),
     "gdsp_ivl_arg_extrema": (_i, [_vp, _vp, _vp, _vp, _i]),

@@ -513,10 +513,12 @@ static int sort_scratch (gdsp_ctx* c, uint64_t ntilesMax, int nseg, SortScratch*
 
 // Sort the owned cells of `src` (viewed through plan `inPlan`) ascending.
 // Buffers a and b ping-pong; src may be a.  The result lands in *resultBuf
-// (a or b), laid out through `finalMap` (segmented) or linearly.
+// (a or b), laid out through `finalMap` (segmented) or linearly.  Every pass but the last writes
+// LINEARLY from the start of its buffer; with `lastDst` the last of two or more passes writes there
+// instead (so a and b can both be scratch and only the final, segmented pass touches the signal).
 static int radix_sort (gdsp_ctx* c, const SortPlan& inPlan, const SortPlan& linPlan, const double* src,
                        double* a, double* b, const OutMap& finalMap, const SortScratch& sc,
-                       double** resultBuf, int* passesRun)
+                       double** resultBuf, int* passesRun, double* lastDst = NULL)
 	{
 	unsigned long long init[4] = { 0ull, ~0ull, 0ull, 0ull };
 	GDSP_CUDA (cudaMemcpyAsync (sc.orand, init, sizeof (init), cudaMemcpyHostToDevice, c->stream));
@@ -542,8 +544,9 @@ static int radix_sort (gdsp_ctx* c, const SortPlan& inPlan, const SortPlan& linP
 	OutMap lin;  lin.nseg = 0;  lin.prefix = NULL;  lin.segs = NULL;
 	for (int p = 0; p < k; p++)
 		{
-		double* dst = (cur == a) ? b : a;
 		const bool last = (p == k - 1);
+		double* dst = (cur == a) ? b : a;
+		if (last && p > 0 && lastDst != NULL) dst = lastDst;
 		const uint64_t tp = pad8 (plan.ntiles);
 		GDSP_REQUIRE (tp <= sc.ntilesPadMax, "radix_sort: scratch too small");
 		const uint64_t entries = 256 * tp;
@@ -632,6 +635,21 @@ extern "C" int gdsp_sort_genome (gdsp_ctx* c, const gdsp_layout* L_, double* sig
 	GDSP_TRY (make_lin_plan (c, sc, L->cells, &linPlan));
 	OutMap fm;  fm.nseg = L->nseg;  fm.prefix = sc.prefix;  fm.segs = L->d;
 	double* res = NULL;  int passes = 0;
+	// The intermediate passes write linearly from the start of their buffer.  When the layout is the
+	// front of the buffer (the whole genome, or the first chromosomes of it) that region of `sig` holds
+	// only cells being sorted.  Any other layout (one chromosome in the middle of the genome: the
+	// per-chromosome sorts of the percentile passes) must not lose its neighbours: both ping-pong
+	// buffers are then halves of `tmp` and only the last, segmented pass writes into `sig`.
+	bool isFront = L->h[0].lo < GDSP_ALIGN;
+	for (int s = 0; s + 1 < L->nseg && isFront; s++)
+		isFront = L->h[s+1].lo >= L->h[s].hi && L->h[s+1].lo - L->h[s].hi < GDSP_ALIGN;
+	const uint64_t half = ((L->cells + 63) / 64) * 64;
+	if (!isFront && 2 * half <= buffer_cells)
+		{
+		GDSP_TRY (radix_sort (c, inPlan, linPlan, sig, tmp, tmp + half, fm, sc, &res, &passes, sig));
+		*h_result_in_tmp = (res == sig) ? 0 : 1;          // one pass: segmented into tmp; none: untouched; else sig
+		return GDSP_OK;
+		}
 	GDSP_TRY (radix_sort (c, inPlan, linPlan, sig, sig, tmp, fm, sc, &res, &passes));
 	*h_result_in_tmp = (res == tmp) ? 1 : 0;
 	return GDSP_OK;

@@ -607,6 +607,25 @@ class Genome:
         if flag.value:
             self._swap()
 
+    def piece_sort(self, k):
+        """sort owned piece k alone (the per-chromosome sorts of percentile.c:611-621); every other cell
+        of the signal keeps its value"""
+        lay = self._ensure_piece_layouts()[k]
+        flag = C.c_int()
+        check(self.lib.gdsp_sort_genome(self.ctx, lay, self._p(self.sig), self._p(self.tmp), self.buffer_cells, C.byref(flag)))
+        if flag.value:
+            lo, hi = self.segs[k][0], self.segs[k][1]
+            self.sig[lo:hi].copy_(self.tmp[lo:hi])
+
+    def merge_exchange(self, c, d):
+        """one bubble step of the percentile operator (combine_sorted_vectors, percentile.c:820-864) on
+        segments c and d, each already sorted: c keeps the smallest cells of both; returns how many moved"""
+        (clo, chi), (dlo, dhi) = self.segs[c][:2], self.segs[d][:2]
+        moved = C.c_uint64()
+        check(self.lib.gdsp_merge_exchange(self.ctx, self._p(self.sig), self._p(self.tmp), int(clo), int(chi - clo),
+                                           int(dlo), int(dhi - dlo), C.byref(moved)))
+        return int(moved.value)
+
     # ------------------------------------------------------------------ clump.c
     def clump(self, average=0.0, length=100, relative_length=0.0, above=True, one=1.0, zero=0.0):
         wb = self.lib.gdsp_clump_work_bytes(self.buffer_cells)

@@ -5,13 +5,14 @@
  * gdsp_percentiles (exact selection, no sort).  The reference's percentile is
  * destructive; when a later operator (or the final output) reads the signal,
  * the reference's post-state is materialised:
- *   - every position qualifies (window 1, no --min/--max): chromosomes
- *     0..K (K = chromosome holding the last reported rank) are made the sorted
- *     prefix by gdsp_sort_genome over pairs of chromosomes in the reference's
- *     combine order (one global sort when K is one of the last two);
- *   - otherwise (--window>1 / --min / --max) the collect permutation of
- *     percentile.c:547-580 is not reproduced: the operator stops with a message
- *     unless --preserve is given. */
+ *   - --window>1 / --min / --max first bring the qualifying values to the front with the
+ *     reference's collect permutation (gdsp_percentile_collect, percentile.c:547-580);
+ *   - the front (every chromosome when all positions qualify) is then left as the reference's
+ *     sorts and bubble passes leave it (percentile.c:611-651): chromosomes 0..K (K = chromosome
+ *     holding the last reported rank) become the sorted prefix.  When K is one of the last two
+ *     that is one global sort (thresholded without sorting when `binarize` follows); otherwise
+ *     every front chromosome is sorted on its own and each pass step (combine_sorted_vectors)
+ *     is a split search and two merges on the device (gdsp_merge_exchange). */
 #include <stdlib.h>
 #include <string.h>
 #include <stdio.h>
@@ -324,24 +325,12 @@ void op_percentile_apply (dspop* _op, arg_dont_complain(char* vName), arg_dont_c
 		}
 	else
 		{
+		/* the reference's passes (percentile.c:611-651): every front chromosome is sorted on its own, then
+		 * chromosome c takes the smallest len(c) values of {c, d} for every later d of the front, in order.
+		 * Both sides of a step are sorted, so the step is a split search and two merges
+		 * (gdsp_merge_exchange) rather than a sort of the pair. */
 		int inTmp = 0;
-		/* the reference's bubble passes (percentile.c:623-651): chromosome c takes the smallest
-		 * len(c) values of {c, d} for every later d of the front, in order */
-		for (int c = 0; c <= K; c++)
-			for (int d = c + 1; d <= last; d++)
-				{
-				gdsp_seg pair[2] = { front[c], front[d] };
-				gdsp_layout* lay;
-				gd_check (gdsp_layout_create (gd.ctx, pair, 2, &lay), _op->name);
-				gd_check (gdsp_sort_genome (gd.ctx, lay, gd.sig, gd.tmp, gd.cells, &inTmp), _op->name);
-				if (inTmp)
-					for (int q = 0; q < 2; q++)
-						gd_check (gdsp_d2d (gd.ctx, gd.sig + pair[q].lo, gd.tmp + pair[q].lo,
-						                    (pair[q].hi - pair[q].lo) * sizeof (double)), _op->name);
-				gdsp_layout_destroy (lay);
-				}
-		/* chromosomes after K were only sorted individually before the passes touched them */
-		for (int d = K + 1; d <= last; d++)
+		for (int d = 0; d <= last; d++)
 			{
 			gdsp_layout* lay;
 			gd_check (gdsp_layout_create (gd.ctx, &front[d], 1, &lay), _op->name);
@@ -350,6 +339,10 @@ void op_percentile_apply (dspop* _op, arg_dont_complain(char* vName), arg_dont_c
 			                               (front[d].hi - front[d].lo) * sizeof (double)), _op->name);
 			gdsp_layout_destroy (lay);
 			}
+		for (int c = 0; c <= K; c++)
+			for (int d = c + 1; d <= last; d++)
+				gd_check (gdsp_merge_exchange (gd.ctx, gd.sig, gd.tmp, front[c].lo, front[c].hi - front[c].lo,
+				                               front[d].lo, front[d].hi - front[d].lo, NULL), _op->name);
 		}
 	free (front);
 	}

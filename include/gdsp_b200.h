@@ -346,6 +346,13 @@ int  gdsp_pct_count_nan (gdsp_ctx* ctx, const gdsp_layout* lay, const double* si
  * in sig (*h_result_in_tmp = 0) or in tmp (= 1): the caller swaps its buffers. */
 int  gdsp_sort_genome (gdsp_ctx* ctx, const gdsp_layout* lay, double* sig,
                        double* tmp, uint64_t buffer_cells, int* h_result_in_tmp);
+/* One step of the reference's bubble passes, combine_sorted_vectors (percentile.c:820-864): the ranges
+ * [c_lo, c_lo+c_len) and [d_lo, d_lo+d_len) of sig are each sorted ascending (gdsp_sort_genome's order);
+ * afterwards the first holds the c_len smallest cells of both, the second the rest, both sorted -- the
+ * bytes a joint sort of the two would leave.  Done as a split search and two merges through tmp (same
+ * offsets), 16 B per cell.  *h_moved = how many cells changed sides (0: nothing was written). */
+int  gdsp_merge_exchange (gdsp_ctx* ctx, double* sig, double* tmp, uint64_t c_lo, uint64_t c_len,
+                          uint64_t d_lo, uint64_t d_len, uint64_t* h_moved);
 /* op_binarize_apply (logical.c:216-268) applied to the post-percentile state above WITHOUT sorting:
  * the binarized sorted genome is a step function at cells - #(v > threshold) (>= with ties above),
  * so one counting pass and one fill produce the same bytes.  *h_done = 0 (signal untouched) when

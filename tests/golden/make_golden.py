@@ -65,6 +65,9 @@ CASES = {
     "percentile_collect_high_rank": (C + ["--novalue", "=", "percentile", "99", "--min=2", "=", "binarize", "--threshold=percentile99"], "reads.iv"),
     "percentile_general_rank": (C + ["--novalue", "=", "percentile", "30", "=", "addconst", "0"], "reads.iv"),
     "subtract_novalue_inherited": (C + ["--novalue", "=", "subtract", "trackB.iv"], "reads.iv"),
+    # the bubble passes on real values (every chromosome sorted on its own, then combine_sorted_vectors steps)
+    "percentile_general_rank_reals": (C + ["--novalue", "--precision=9", "=", "smooth", "--window=11", "=", "percentile", "30",
+                                           "--precision=9", "=", "addconst", "0"], "reads.iv"),
     # read_intervals' per-cell rule (genodsp.c:1307-1330) when the running value comes back to missingVal: it reads as
     # "not yet covered" and the next interval overwrites it -- zero-valued rows under --overlap=min|max, a depth that
     # reaches --missing, a sum that passes through it

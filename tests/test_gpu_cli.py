@@ -321,3 +321,15 @@ def test_values_that_return_to_missing_and_integer_adds_on_real_signals(data):
     assert_same(data, C + ["--novalue", "--precision=17", "=", "smooth", "--window=31", "=", "add", "ints.iv", "--value=4",
                            "=", "subtract", "ints.iv", "--value=4"])
     assert_same(data, C + ["--novalue", "=", "add", "ints.iv", "--value=4", "=", "subtract", "ints.iv", "--value=4"])
+
+
+def test_percentile_bubble_passes_on_real_values(data):
+    """general rank, every position qualifying: the reference sorts every chromosome on its own and then runs
+    combine_sorted_vectors steps (percentile.c:611-651, :820-864); here each step is a split search and two
+    merges (gdsp_merge_exchange) and the per-chromosome sorts must not disturb their neighbours.  Real values
+    (many radix passes), K = first and K = second chromosome, the state read back by the next operator."""
+    P = ["--novalue", "--precision=9", "=", "smooth", "--window=11"]
+    assert_same(data, C + P + ["=", "percentile", "30", "--precision=9", "=", "addconst", "0"])
+    assert_same(data, C + P + ["=", "percentile", "70", "--precision=9", "=", "addconst", "0"])
+    assert_same(data, C + P + ["=", "percentile", "10..70by30", "--quiet", "=", "abs"])
+    assert_same(data, C + ["=", "percentile", "45", "--precision=3", "=", "addconst", "0"], stdin="vals.iv")

@@ -783,6 +783,67 @@ def test_sort_genome_real_values(genome):
         assert np.array_equal(genome.get_chrom(name), post[name]), name
 
 
+def _key_order(v):
+    """gdsp_sort_genome's total order (f64_key): by value, -0.0 before +0.0"""
+    b = np.ascontiguousarray(v, np.float64).view(np.uint64)
+    key = np.where(b >> np.uint64(63) != 0, ~b, b | np.uint64(1 << 63))
+    return v[np.argsort(key, kind="stable")]
+
+
+@pytest.mark.parametrize("kind", ["real", "int", "sparse"])
+def test_sort_one_chromosome_leaves_the_others_alone(genome, kind):
+    """the per-chromosome sorts of the percentile passes (percentile.c:611-621): a layout that is not the
+    front of the buffer must not spill its intermediate radix passes over its neighbours (real values
+    take more than two digit passes)"""
+    inputs = load(genome, np.random.default_rng(57), kind)
+    for k in range(genome.nseg):
+        genome.piece_sort(k)
+        name = genome.chroms[genome.seg_chrom[k]][0]
+        inputs[name] = _key_order(inputs[name])
+        for other, _ in CHROMS:
+            got = genome.get_chrom(other)
+            assert np.array_equal(bits(got), bits(inputs[other])), (kind, "after sorting", name, "chromosome", other)
+
+
+@pytest.mark.parametrize("kind", ["real", "int", "ties"])
+def test_merge_exchange_equals_joint_sort(genome, kind):
+    """gdsp_merge_exchange = combine_sorted_vectors (percentile.c:820-864): two sorted chromosomes, the first
+    ends up with the smallest cells of both, bytes of a joint sort; lengths 1, 63, tile multiples and +-1"""
+    rng = np.random.default_rng(91)
+    vals = {}
+    for name, n in CHROMS:
+        if kind == "ties":
+            v = rng.integers(-1, 3, n).astype(np.float64)
+            v[rng.random(n) < 0.1] = -0.0
+        else:
+            v = signal(rng, n, kind) + (rng.integers(-2, 3) if kind == "int" else rng.normal())
+        vals[name] = _key_order(v)
+        genome.set_chrom(name, vals[name])
+    seg_of = {genome.chroms[genome.seg_chrom[k]][0]: k for k in range(genome.nseg)}
+    for c, d in [("chr1", "chr7"), ("chr5", "chr6"), ("chr6", "chr5"), ("chr3", "chr4"), ("chr4", "chr2"), ("chr7", "chr5"),
+                 ("chr2", "chr1"), ("chr1", "chr7")]:
+        both = _key_order(np.concatenate([vals[c], vals[d]]))
+        moved = genome.merge_exchange(seg_of[c], seg_of[d])
+        want_c, want_d = both[:vals[c].size], both[vals[c].size:]
+        assert moved == _moved(vals[c], vals[d]), (kind, c, d)
+        vals[c], vals[d] = want_c, want_d
+        for name, _ in CHROMS:
+            assert np.array_equal(bits(genome.get_chrom(name)), bits(vals[name])), (kind, c, d, name)
+
+
+def _moved(cv, dv):
+    """the reference's count: first k with not (d[k] < c[len-1-k]) in key order"""
+    def key(v):
+        b = np.ascontiguousarray(v, np.float64).view(np.uint64)
+        return np.where(b >> np.uint64(63) != 0, ~b, b | np.uint64(1 << 63))
+    n = min(cv.size, dv.size)
+    if n == 0:
+        return 0
+    less = key(dv)[:n] < key(cv)[::-1][:n]
+    stop = np.nonzero(~less)[0]
+    return int(stop[0]) if stop.size else n
+
+
 def test_smooth_many_tiles_per_cta(orc):
     """chromosomes of many strips / tiles, one shorter than every window"""
     from genodsp_b200.genome import Genome
