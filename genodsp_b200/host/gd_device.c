@@ -59,6 +59,9 @@ void gd_device_open (void)
 	gd.cells = total;
 	free (lens);
 	if (getenv ("GENODSP_PARSE_ONLY") != NULL) return;      /* tokenizer self-check (tests): no device needed */
+	/* the CLI computes on device 0 only: unless the user chose devices, hide the others before the CUDA runtime
+	 * initialises, so that an 8-GPU node does not create eight primary-context candidates */
+	setenv ("CUDA_VISIBLE_DEVICES", "0", 0);
 	if (getenv ("GENODSP_SYNC_OPEN") != NULL || pthread_create (&openThread, NULL, device_open_thread, NULL) != 0)
 		device_open_thread (NULL);
 	else
